@@ -1,0 +1,376 @@
+/* sep.h -- the seplib C99 API, as served by seplib-b200 (B200 / sm_100a device path).
+ *
+ * This header is the drop-in boundary: programs written against the reference's include/sep.h
+ * (prgs/prg0.c ... prg6.c) compile against it unchanged and link with -lsep.  Type names, field
+ * names, field order, constants and prototypes follow the reference so that user code which reads
+ * atoms[i].x/v/f, sys.nupdate_neighb or ret.epot directly keeps working; each block cites the
+ * reference header it mirrors (paths relative to the reference root).
+ *
+ * What is different underneath: the per-timestep hot path (pair forces, neighbour list, bonded
+ * terms, Coulomb, DPD, thermostat, integrators) runs on the GPU through include/sepgpu.h.  There is
+ * no CPU implementation of that path in this library: without a usable CUDA device those calls stop
+ * with sep_error().
+ *
+ * Host/device coherence (env SEP_SYNC, or sep_gpu_set_sync):
+ *   step (default)  atoms[] is refreshed from the device at the end of every integrator call;
+ *                   sepret / sepsys scalars after every hot call.
+ *   lazy            atoms[] is refreshed only by library calls that read it (sep_eval_mom,
+ *                   sep_save_xyz, ...), by sep_gpu_sync() and by sep_close(); scalars after
+ *                   integrator calls.
+ *   full            like step, plus forces are written back after every force call.
+ * Writing into atoms[] from user code between hot calls needs sep_gpu_invalidate(atoms).
+ */
+#ifndef SEP_B200_SEP_H
+#define SEP_B200_SEP_H
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <stdbool.h>
+#include <stddef.h>
+#include <string.h>
+#include <math.h>
+#include <time.h>
+#include <float.h>
+#include <stdarg.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- constants (include/sepdef.h:16-64) --------------------------------------------------- */
+#define SEP_FALSE 0
+#define SEP_TRUE  1
+
+#define SEP_BOND  10            /* bonded partners kept per atom */
+#define SEP_ANGLE 10
+#define SEP_DIHED 20
+
+#define SEP_NEIGHB      3000    /* reference half-list capacity per atom */
+#define SEP_NUM_NEIGHB  3000
+#define SEP_NO_NEIGHB   0
+
+#define SEP_NEIGHB_ALL            1
+#define SEP_ALL                   1
+#define SEP_NEIGHB_EXCL_BONDED    2
+#define SEP_EXCL_BONDED           2
+#define SEP_NEIGHB_EXCL_SAME_MOL  3
+#define SEP_EXCL_SAME_MOL         3
+
+#define SEP_MAX_NUM_MOL 10000
+
+#define SEP_PI     3.14159265358979
+#define SEP_WCACF  1.12246204830937
+#define SEP_LJCF2  0.016316891136
+
+#define SEP_R250_LEN 250
+#define SEP_R521_LEN 521
+#define SEP_MAXNID   100000
+#define SEP_NRETVALS 10
+
+#define SEP_BRUTE            0
+#define SEP_NEIGHBLIST       1
+#define SEP_LLIST_NEIGHBLIST 2
+
+#define SEP_LEAPFROG   0
+#define SEP_NOSEHOOVER 1
+#define SEP_ANDERSEN   2
+#define SEP_SHAKE      3
+#define SEP_SHAKE_MAXIT 1000
+
+#define SEP_SUCCESS 1
+#define SEP_FAILURE 1           /* sic: identical in the reference (include/sepdef.h:63-64) */
+
+/* ---- macros (include/sepmisc.h:36-94) ------------------------------------------------------- */
+#define SEP_FLUSH  fflush(stdout)
+#define SEP_TICTOC clock_t time_then
+#define SEP_TIC    time_then = clock()
+#define SEP_TOC    ((int)(1000*(clock()-time_then)/CLOCKS_PER_SEC))%1000
+
+#define sep_rand()   ( rand()/(RAND_MAX+1.0) )
+#define sep_here(x)  { printf("%d\n", x); SEP_FLUSH; }
+#define sep_Sq(x)    ( (x)*(x) )
+#define sep_Abs(x)   ( (x) > 0.0 ? (x) : -(x) )
+#define sep_Wrap( x, y )  { if ( x > 0.5*y ) x -= y; else if ( x < -0.5*y ) x += y; }
+#define sep_Periodic( x, y )  { if ( x > y ) x -= y; else if ( x < 0 ) x += y; }
+
+/* ---- data model (include/sepstrct.h:23-204); field order kept so the layout is identical ---- */
+typedef struct {
+    double x[3];            /* position (wrapped into the box)            */
+    double v[3];            /* velocity                                   */
+    double f[3];            /* force                                      */
+    double a[3];            /* acceleration                               */
+    double m;               /* mass                                       */
+    char type;              /* one-character type label                   */
+    double z;               /* point charge                               */
+
+    int *neighb;            /* host neighbour row (filled only on request: sep_gpu_export_neighb) */
+
+    int cross_neighb[3];    /* box crossings since the last list build    */
+    int crossings[3];       /* box crossings since the start              */
+
+    int molindex;           /* owning molecule or -1                      */
+    int bond[SEP_BOND];     /* atoms sharing a bond with this one         */
+    int angle[SEP_ANGLE];   /* atoms sharing an angle                     */
+    int dihed[SEP_DIHED];   /* atoms sharing a dihedral                   */
+
+    double sigma;           /* hard-sphere diameter (unused here)         */
+    int *collid;
+    double *colltime;
+
+    double ldiff;
+
+    double xtrue[3];
+    double x0[3];
+    double xn[3];           /* position at the last list build            */
+    double xp[3];
+    double px[3];
+    double pv[3];           /* predicted velocity (DPD)                   */
+    double pa[3];           /* previous acceleration (DPD)                */
+    double randn[3];
+    double prevf[3];
+} seppart;
+
+typedef seppart sepatom;
+
+typedef struct {
+    unsigned num_mols;
+    unsigned max_nuau;
+
+    int flag_bonds, flag_angles, flag_dihedrals;
+
+    unsigned num_bonds;
+    unsigned *blist;        /* (a, b, type) per bond              */
+    unsigned num_btypes;
+
+    unsigned num_angles;
+    unsigned *alist;        /* (a, b, c, type) per angle          */
+    unsigned num_atypes;
+
+    unsigned num_dihedrals;
+    unsigned *dlist;        /* (a, b, c, d, type) per dihedral    */
+    unsigned num_dtypes;
+
+    double *blengths;
+    double *angles;
+    double *dihedrals;
+
+    unsigned flag_Fij;
+    float ***Fij;
+    float ***Fiajb;
+} sepmolinfo;
+
+typedef struct {
+    long int npart;
+    double length[3];
+    double volume;
+
+    int intgr_type;
+    double dt;
+    double tnow;
+    unsigned ndof;
+    double max_dist2;
+
+    double cf;
+    double lsubbox[3];
+    int nsubbox[3];
+    double skin;
+    unsigned neighb_update;
+    unsigned neighb_flag;
+    unsigned nupdate_neighb;
+
+    bool omp_flag;
+    unsigned int nthreads;
+
+    int fun_cstate;
+
+    sepmolinfo *molptr;
+} sep3D;
+
+typedef sep3D sepsys;
+
+typedef struct {
+    double m;
+    double x[3], xtrue[3];
+    double v[3];
+
+    unsigned nuau;
+    int *index;
+
+    double ete[3];
+    double re2;
+    double rg;
+    double S[3];
+
+    double s[3];
+    double inertia[3][3];
+    double w[3];
+    int method_w;
+    double pel[3];
+
+    char type;
+
+    unsigned nbonds;
+    double *blength;
+    int shake_flag;
+} sepmol;
+
+typedef struct {
+    double etot;
+    double ekin;
+    double epot;
+    double ecoul;
+    double sumv2;
+
+    double P[3][3];
+    double kin_P[3][3];
+    double pot_P[3][3];
+    double p;
+
+    double P_mol[3][3];
+    double kin_P_mol[3][3];
+    double pot_P_mol[3][3];
+    double p_mol;
+
+    double pot_P_conservative[3][3];
+    double pot_P_random[3][3];
+    double pot_P_dissipative[3][3];
+    double pot_P_bond[3][3];
+
+    double pot_T_mol[3][3];
+    double kin_T_mol[3][3];
+    double T_mol[3][3];
+    double t_mol;
+} sepret;
+
+/* ---- setup and teardown (include/sepinit.h:29-84) --------------------------------------------- */
+seppart *sep_init(size_t npart, size_t nneighb);
+void sep_close(seppart *ptr, size_t npart);
+seppart *sep_init_xyz(double *lbox, int *npart, const char *file, char verbose);
+sepsys sep_sys_setup(double lengthx, double lengthy, double lengthz,
+                     double maxsyscf, double dt, size_t npart, size_t update);
+void sep_free_sys(sepsys *ptr);
+void sep_set_lattice(seppart *ptr, sepsys sys);
+void sep_set_vel(seppart *ptr, double temp, sepsys sys);
+void sep_set_vel_seed(seppart *ptr, double temp, unsigned int seed, sepsys sys);
+void sep_set_vel_type(seppart *ptr, char type, double temp, unsigned int seed, sepsys sys);
+
+/* ---- pair forces and neighbour list (include/sepprfrc.h:49-93) --------------------------------- */
+int sep_force_pairs(seppart *ptr, const char *types, double cf,
+                    double (*fun)(double, char), sepsys *sys,
+                    sepret *retval, const unsigned opt);
+void sep_force_lj(seppart *ptr, const char *types, const double *param,
+                  sepsys *sys, sepret *retval, const unsigned opt);
+void sep_force_dpd(seppart *ptr, const char *types, const double cf, const double aij,
+                   const double temp_desired, const double sigma,
+                   sepsys *sys, sepret *retval, const unsigned opt);
+void sep_neighb(seppart *ptr, sepsys *sys);
+void sep_neighb_nonbonded(seppart *ptr, sepsys *sys);
+void sep_neighb_excl_same_mol(seppart *ptr, sepsys *sys);
+unsigned int sep_bond_share(seppart *ptr, int j1, int j2);
+unsigned int sep_angle_share(seppart *ptr, int j1, int j2);
+unsigned int sep_dihed_share(seppart *ptr, int j1, int j2);
+unsigned int sep_bonded(seppart *ptr, int i, int j);
+
+/* ---- shifted-force Coulomb (include/sepcoulomb.h:39-53) ----------------------------------------- */
+void sep_coulomb_sf(seppart *ptr, double cf, sepsys *sys, sepret *retval, const unsigned opt);
+
+/* ---- thermostat and integrators (include/sepintgr.h:27-90) -------------------------------------- */
+double sep_periodic(sepatom *atoms, unsigned n, sepsys *sys);
+void sep_leapfrog(seppart *ptr, sepsys *sys, sepret *retval);
+void sep_nosehoover(seppart *ptr, double Td, double *alpha, const double Q, sepsys *sys);
+void _sep_nosehoover_type(seppart *ptr, char type, double Td, double *alpha, const double Q, sepsys *sys);
+void sep_verlet_dpd(seppart *ptr, double lambda, int stepnow, sepsys *sys, sepret *retval);
+
+/* ---- molecules: topology and bonded forces (include/sepmol.h:18-100) ----------------------------- */
+void sep_read_topology_file(sepatom *aptr, const char *file, sepsys *sysptr, char opt);
+void sep_free_bonds(sepmolinfo *ptr);
+void sep_free_angles(sepmolinfo *ptr);
+void sep_free_dihedrals(sepmolinfo *ptr);
+sepmol *sep_init_mol(sepatom *atom, sepsys *sys);
+void sep_free_mol(sepmol *ptr, sepsys *sys);
+void sep_stretch_harmonic(sepatom *aptr, int type, const double lbond, const double ks,
+                          sepsys *sys, sepret *ret);
+void sep_angle_harmonic(sepatom *ptr, int type, const double angle0, const double k,
+                        sepsys *sys, sepret *ret);
+void sep_angle_cossq(sepatom *ptr, int type, const double angle0, const double k,
+                     sepsys *sys, sepret *ret);
+void sep_torsion_Ryckaert(sepatom *ptr, int type, const double g[6], sepsys *sys, sepret *ret);
+void sep_mol_cm(seppart *ptr, sepmol *mol, sepsys *sys);
+void sep_mol_velcm(seppart *atom, sepmol *mol, sepsys *sys);
+void sep_eval_mol_pressure_tensor(sepatom *atoms, sepmol *mols, sepret *ret, sepsys *sys);
+double sep_average_bondlengths(int type, sepsys *sys);
+
+/* ---- return values (include/sepret.h:36-67) ------------------------------------------------------- */
+void sep_reset_retval(sepret *retval);
+double sep_get_pressure(sepret *retval, sepsys *sys);
+double sep_get_temperature(sepret *retval, sepsys *sys);
+void sep_pressure_tensor(sepret *retval, sepsys *sys);
+void sep_mol_pressure_tensor(sepatom *atoms, sepmol *mols, sepret *ret, sepsys *sys);
+
+/* ---- miscellaneous runtime (include/sepmisc.h:101-450) ---------------------------------------------- */
+void sep_error(char *str, ...);
+void sep_warning(char *str, ...);
+double sep_lj(double r2, char opt);
+double sep_lj_shift(double r2, char opt);
+double sep_wca(double r2, char opt);
+void sep_reset_force(seppart *ptr, sepsys *sys);
+void sep_reset_force_mol(sepsys *sys);
+int sep_nsubbox(double cf, double delta, double lbox);
+double sep_box_length(double dens, int npart, int ndim);
+int sep_count_type(seppart *ptr, char spec, int npart);
+void sep_set_x0(seppart *ptr, int npart);
+void sep_set_xn(seppart *ptr, int npart);
+void sep_save_xyz(seppart *ptr, const char *partnames, const char *file, char *mode, sepsys *sys);
+double sep_eval_mom(seppart *ptr, int npart);
+double sep_eval_mom_type(seppart *ptr, char type, int dir, int npart);
+void sep_compress_box(sepatom *ptr, double rhoD, double xi, sepsys *sys);
+void sep_set_charge(seppart *ptr, char type, double z, sepsys sys);
+void sep_set_mass(seppart *ptr, char type, double m, sepsys sys);
+void sep_set_type(seppart *ptr, char spec, int numb, sepsys *sys);
+void sep_set_omp(unsigned nthreads, sepsys *sys);
+void sep_set_skin(sepsys *sys, double value);
+void sep_set_ndof(size_t ndof, sepsys *sys);
+void sep_reset_momentum(seppart *ptr, const char type, sepsys *sys);
+double sep_dist_ij(double *r, seppart *ptr, int i, int j, sepsys *sys);
+void sep_eval_xtrue(seppart *ptr, sepsys *sys);
+
+/* ---- array helpers used by the example programs (include/separray.h, include/seputil.h) -------------- */
+double *sep_vector(size_t length);
+int *sep_vector_int(size_t length);
+double **sep_matrix(size_t nrow, size_t ncol);
+void sep_free_matrix(double **ptr, size_t nrow);
+float ***sep_tensor_float(size_t nx, size_t ny, size_t nz);
+void sep_free_tensor_float(float ***ptr, size_t nx, size_t ny);
+double sep_dot(double *a, double *b, int length);
+void sep_vector_set(double *vec, size_t length, double value);
+
+/* ---- samplers (include/sepsampler.h): post-processing, outside the accelerated path.  The entry
+ * points the example programs call are provided so prg1/prg2 build; they record nothing. -------------- */
+typedef struct {
+    int nsamplers;
+    int warned;
+    sepmol *molptr;
+} sepsampler;
+sepsampler sep_init_sampler(void);
+void sep_add_sampler(sepsampler *sptr, const char *sampler, sepsys sys, int lvec, ...);
+void sep_add_mol_sampler(sepsampler *sptr, sepmol *mols);
+void sep_sample(seppart *pptr, sepsampler *sptr, sepret *ret, sepsys sys, unsigned n);
+void sep_close_sampler(sepsampler *ptr);
+
+/* ---- seplib-b200 extensions (not in the reference) -------------------------------------------------- */
+#define SEP_SYNC_LAZY 0
+#define SEP_SYNC_STEP 1
+#define SEP_SYNC_FULL 2
+void sep_gpu_set_sync(int mode);                 /* overrides env SEP_SYNC                              */
+void sep_gpu_sync(seppart *ptr);                 /* device -> atoms[] (everything that changed)         */
+void sep_gpu_invalidate(seppart *ptr);           /* atoms[] was edited by the caller: re-upload         */
+void sep_gpu_sync_scalars(seppart *ptr, sepsys *sys, sepret *ret);   /* sepret/sepsys scalars only   */
+long sep_gpu_export_neighb(seppart *ptr, sepsys *sys, int *pairs, long max_pairs);   /* list as (i<j) pairs */
+void *sep_gpu_handle(seppart *ptr);              /* the sepgpu_ctx behind an atom array (or NULL)       */
+void sep_gpu_set_dpd_seed(unsigned long long seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,181 @@
+/* sepgpu.h -- C ABI of the B200 (sm_100a) device layer of seplib-b200.
+ *
+ * Plain C: opaque handle, plain pointers and sizes, no C++/torch types.  The host layer
+ * (seplib_b200/csrc/host, the sep_* API of include/sep.h) is the only in-tree caller; tests and
+ * bench.py bind the same entry points through ctypes.  Every function returns 0 on success or a
+ * negative SEPGPU_E* code; sepgpu_last_error() gives the text.  There is NO CPU fallback: every
+ * entry point fails with SEPGPU_ENODEV when no CUDA device is usable.
+ *
+ * Each entry point names the reference interface it stands in for (paths relative to the
+ * reference root).
+ */
+#ifndef SEPGPU_H
+#define SEPGPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sepgpu_ctx sepgpu_ctx;
+
+/* error codes */
+#define SEPGPU_OK          0
+#define SEPGPU_ENODEV     -1   /* no CUDA device / driver */
+#define SEPGPU_ECUDA      -2   /* a CUDA runtime call failed */
+#define SEPGPU_EINVAL     -3   /* bad argument */
+#define SEPGPU_ECELL      -4   /* atom outside the cell grid ("Index larger than array length", source/sepprfrc.c:408) */
+#define SEPGPU_ENEIGHB    -5   /* "Too many neighbours" (source/sepprfrc.c:499): a half list reached SEP_NEIGHB */
+#define SEPGPU_ESTATE     -6   /* call order problem (e.g. list force without a list) */
+#define SEPGPU_ENCCL      -7   /* NCCL failure (domain decomposition) */
+
+/* per-atom fields for sepgpu_put / sepgpu_get.  Host element = what the reference keeps in seppart
+ * (include/sepstrct.h:23-61): 3 doubles for vectors, 1 double for scalars, 3 ints for counters. */
+enum {
+    SEPGPU_F_X = 0,          /* x[3]   wrapped position              */
+    SEPGPU_F_V,              /* v[3]                                  */
+    SEPGPU_F_F,              /* f[3]                                  */
+    SEPGPU_F_M,              /* m                                     */
+    SEPGPU_F_Z,              /* z      point charge                   */
+    SEPGPU_F_TYPE,           /* type   (char)                         */
+    SEPGPU_F_MOLINDEX,       /* molindex (int)                        */
+    SEPGPU_F_XN,             /* xn[3]  position at last list build    */
+    SEPGPU_F_CROSS_NEIGHB,   /* cross_neighb[3] (int)                 */
+    SEPGPU_F_CROSSINGS,      /* crossings[3]    (int)                 */
+    SEPGPU_F_PV,             /* pv[3]  predicted velocity (DPD)       */
+    SEPGPU_F_PA,             /* pa[3]  previous acceleration (DPD)    */
+    SEPGPU_F_A,              /* a[3]   acceleration (get only; = f/m) */
+    SEPGPU_F_BOND,           /* bond[SEP_BOND]   partner table (int)  */
+    SEPGPU_F_ANGLE,          /* angle[SEP_ANGLE] partner table (int)  */
+    SEPGPU_F_DIHED,          /* dihed[SEP_DIHED] partner table (int)  */
+    SEPGPU_F_COUNT
+};
+
+/* exclusion rule of the list builders (include/sepdef.h:29-36) */
+#define SEPGPU_ALL            1
+#define SEPGPU_EXCL_BONDED    2
+#define SEPGPU_EXCL_SAME_MOL  3
+
+/* pair-function family of sep_force_pairs / sep_force_lj (source/sepmisc.c:115-164,
+ * source/sepprfrc.c:782-795).  All are u = 4 eps[(s/r)^12 - aw (s/r)^6] - shift. */
+typedef struct {
+    double cf;        /* interaction cutoff                         */
+    double eps;       /* epsilon                                    */
+    double sigma;     /* sigma                                      */
+    double aw;        /* weight of the attractive term              */
+    double shift;     /* subtracted from u for every in-range pair  */
+} sepgpu_ljparam;
+
+/* run parameters the host passes on every call (mirror of the sepsys fields the hot path reads,
+ * include/sepstrct.h:104-135) */
+typedef struct {
+    double length[3];
+    double lsubbox[3];
+    int    nsubbox[3];
+    double cf;               /* maximum cutoff of the system  */
+    double skin;
+    double dt;
+    int    neighb_update;    /* SEP_BRUTE=0 / SEP_NEIGHBLIST=1 / SEP_LLIST_NEIGHBLIST=2 */
+} sepgpu_sys;
+
+/* scalar results, device-accumulated with the reference's assign/accumulate rules and copied
+ * out by sepgpu_read_scalars (mirror of the sepret/sepsys fields the hot path writes) */
+typedef struct {
+    double epot, ecoul, ekin;
+    double pot_P[9], kin_P[9], pot_P_bond[9];
+    double max_dist2;          /* sys->max_dist2                                   */
+    double sum_mv2;            /* sum m v^2 of the velocities now on the device     */
+    double alpha[4];           /* device copies of thermostat multipliers (slots)  */
+    int    neighb_flag;        /* 1 when the skin trigger fired in the last integrator call */
+    int    nbuild;             /* list builds executed so far                       */
+    int    error;              /* sticky device error (SEPGPU_E*) or 0              */
+    int    max_neighb;         /* longest full list seen at the last build          */
+    long long npairs_listed;   /* ordered (i->j) entries in the current list        */
+} sepgpu_scalars;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* device state for npart atoms; replaces the allocation side of sep_init (source/sepinit.c:15-56) */
+int  sepgpu_create(sepgpu_ctx **out, size_t npart, int device);
+void sepgpu_destroy(sepgpu_ctx *ctx);
+const char *sepgpu_last_error(void);
+int  sepgpu_device_count(void);
+
+/* ---- bulk state movement (host <-> HBM) ------------------------------------------------------- */
+/* strided host access so the host layer can point straight into its seppart AoS array
+ * (stride = sizeof(seppart)) while tests pass packed numpy arrays (stride = element size). */
+int sepgpu_put(sepgpu_ctx *ctx, int field, const void *host, size_t stride_bytes);
+int sepgpu_get(sepgpu_ctx *ctx, int field, void *host, size_t stride_bytes);
+/* topology lists in the reference layout (include/sepstrct.h:77-87): blist[3n], alist[4n], dlist[5n] */
+int sepgpu_set_topology(sepgpu_ctx *ctx, const unsigned *blist, unsigned nbonds,
+                        const unsigned *alist, unsigned nangles,
+                        const unsigned *dlist, unsigned ndihedrals);
+int sepgpu_get_bonded_values(sepgpu_ctx *ctx, double *blengths, double *angles, double *dihedrals);
+
+/* ---- per-step hot path -------------------------------------------------------------------------- */
+/* sep_reset_retval (source/sepret.c:19-47) */
+int sepgpu_reset_ret(sepgpu_ctx *ctx);
+/* sep_reset_force (source/sepmisc.c:393-400): f <- 0 and max_dist2 <- 0 */
+int sepgpu_reset_force(sepgpu_ctx *ctx);
+/* sep_neighb / sep_neighb_nonbonded / sep_neighb_excl_same_mol (source/sepprfrc.c:347-378):
+ * cell binning + Verlet list.  The pair SET equals the reference's bit for bit. */
+int sepgpu_neighb_build(sepgpu_ctx *ctx, const sepgpu_sys *sys, unsigned opt);
+/* sep_force_pairs list/brute branch and sep_force_lj (source/sepprfrc.c:226-274, 743-780).
+ * epot_assign=1 reproduces "retval->epot = epot" (:222), 0 accumulates (:64, :922). */
+int sepgpu_force_lj(sepgpu_ctx *ctx, const sepgpu_sys *sys, const char types[2],
+                    const sepgpu_ljparam *p, unsigned opt, int epot_assign);
+/* sep_coulomb_sf (source/sepcoulomb.c:5-18) */
+int sepgpu_coulomb_sf(sepgpu_ctx *ctx, const sepgpu_sys *sys, double cf, unsigned opt);
+/* sep_force_dpd (source/sepprfrc.c:278-301); counter-based pair noise keyed on (seed, step) */
+int sepgpu_force_dpd(sepgpu_ctx *ctx, const sepgpu_sys *sys, const char types[2], double cf,
+                     double aij, double temp, double sigma, unsigned opt,
+                     unsigned long long seed, unsigned long long step);
+/* sep_stretch_harmonic / sep_angle_harmonic / sep_angle_cossq / sep_torsion_Ryckaert
+ * (source/sepmol.c:372-414, 469-516, 418-467, 520-587) */
+int sepgpu_stretch_harmonic(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, double lbond, double ks);
+int sepgpu_angle_harmonic(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, double angle0, double k);
+int sepgpu_angle_cossq(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, double angle0, double k);
+int sepgpu_torsion_ryckaert(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, const double g[6]);
+/* sep_nosehoover (source/sepintgr.c:149-168).  alpha lives in device slot `slot` (0..3); the
+ * f -= alpha m v update is fused into the next integrator kernel. */
+int sepgpu_nosehoover(sepgpu_ctx *ctx, const sepgpu_sys *sys, double temp0, int slot, double tau);
+/* _sep_nosehoover_type (source/sepintgr.c:170-198): alpha3 is the caller's 3-slot history (in/out) */
+int sepgpu_nosehoover_type(sepgpu_ctx *ctx, const sepgpu_sys *sys, char type, double Td,
+                           double alpha3[3], double Q);
+int sepgpu_set_alpha(sepgpu_ctx *ctx, int slot, double alpha);
+/* sep_leapfrog (+ sep_periodic, skin trigger, sep_set_xn) (source/sepintgr.c:18-88) */
+int sepgpu_leapfrog(sepgpu_ctx *ctx, const sepgpu_sys *sys);
+/* sep_verlet_dpd (source/sepintgr.c:296-345) */
+int sepgpu_verlet_dpd(sepgpu_ctx *ctx, const sepgpu_sys *sys, double lambda, int stepnow);
+/* sep_reset_momentum (source/sepmisc.c:1173-1192) and the x-rescale of sep_compress_box (:1009-1010) */
+int sepgpu_reset_momentum(sepgpu_ctx *ctx, char type);
+int sepgpu_scale_positions(sepgpu_ctx *ctx, double xi);
+
+/* ---- results -------------------------------------------------------------------------------------- */
+/* stream-synchronising read of the scalar block */
+int sepgpu_read_scalars(sepgpu_ctx *ctx, sepgpu_scalars *out);
+int sepgpu_sync(sepgpu_ctx *ctx);
+/* current Verlet list as unordered pairs (i<j, original atom indices), for parity checks against
+ * ptr[i].neighb (source/sepprfrc.c:493-497).  Returns the pair count or a negative error. */
+long long sepgpu_get_pairs(sepgpu_ctx *ctx, int *pairs, long long max_pairs);
+/* force the next force call to rebuild (sys->neighb_flag = 1) */
+int sepgpu_request_rebuild(sepgpu_ctx *ctx);
+/* tuning: lanes cooperating on one atom in the list force kernels (1,2,4,8,16,32; 0 = default) */
+int sepgpu_set_option(sepgpu_ctx *ctx, const char *name, long long value);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------- */
+/* CUDA-event timing on the context's stream */
+int sepgpu_timer_start(sepgpu_ctx *ctx);
+int sepgpu_timer_stop(sepgpu_ctx *ctx, float *ms);
+/* device time spent in the list-force kernel since the last call (events around each launch) */
+int sepgpu_kernel_time(sepgpu_ctx *ctx, const char *which, float *ms_total, int *launches);
+/* FP64 FMA-chain and copy microbenchmarks: the box's own FP64 / HBM ceilings */
+int sepgpu_peak_fp64(int device, double *tflops);
+int sepgpu_peak_copy(int device, double *gbytes_per_s);
+/* write `bytes` of HBM to flush L2 between timed iterations */
+int sepgpu_flush_l2(sepgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,340 @@
+// sepgpu_force.cu -- pair-force kernels (Lennard-Jones family, shifted-force Coulomb, DPD).
+//
+// Stand-ins for sep_force_pair_neighb / sep_lj_pair_neighb / sep_force_pair_brute / sep_lj_pair_brute
+// (reference source/sepprfrc.c:94-224, 782-1000), sep_coulomb_sf_{neighb,brute}
+// (source/sepcoulomb.c:20-160) and sep_dpdforce_{neighb,brute} (source/sepprfrc.c:1007-1231).
+//
+// The reference scatters +f/-f over a half list.  Here every atom owns its force: TPA lanes share one
+// atom, stride through its FULL neighbour row, keep fx,fy,fz in registers, butterfly-reduce with warp
+// shuffles and issue exactly one 256-bit store per atom -- no global atomics.  Energy and virial are
+// reduced warp -> block -> one partial row per block -> fixed-order final sum (deterministic), and
+// halved because each pair is seen from both ends.
+//
+// Positions come from the cell-sorted copy xs (continuous coordinates since the last rebuild) so that
+// neighbour gathers hit L1/L2; each gather is one 32-byte sector fetched by a single LDG.256.
+// The periodic image of a pair is fixed at list-build time and stored in the top bits of the list
+// entry, which removes the 9 FP64 compare/adjust operations of sep_Wrap from the inner loop.
+#include "sepgpu_internal.cuh"
+
+#include <math.h>
+
+#define FORCE_BLOCK 128
+#define FORCE_MAX_GRID (148 * 16)
+
+struct LJDev {
+    double cf2, sig2, eps48, eps4, aw, awh, shift;
+    int t0, t1;
+};
+
+struct BoxDev { double Lx, Ly, Lz; };
+
+// 1/x to ~1 ulp: MUFU.RCP64H seed (2^-23) + two Newton steps (4 DFMA) instead of the IEEE division
+// sequence; inputs are r^2 of in-range pairs, far from denormals/inf.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // Newton: y <- y + y*(0.5 - 0.5*x*y*y)
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        double h = 0.5 * y;
+        double e = fma(-x * y, h, 0.5);
+        y = fma(y, e, y);
+    }
+    // one more correction step for full double accuracy
+    double h = 0.5 * y;
+    double e = fma(-x * y, h, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+
+__device__ __forceinline__ void apply_image(int code, const BoxDev &B, double &dx, double &dy, double &dz)
+{
+    // code = (sx+1) + 3(sy+1) + 9(sz+1); s = +1 means the reference's sep_Wrap subtracted L
+    const int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
+    dx -= sx * B.Lx; dy -= sy * B.Ly; dz -= sz * B.Lz;
+}
+
+// ---- Lennard-Jones, Verlet list ------------------------------------------------------------------------
+// STORE: first force kernel after sep_reset_force -> plain store instead of read-modify-write.
+template <int TPA, bool TYPED, bool STORE>
+__global__ void __launch_bounds__(FORCE_BLOCK)
+k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
+          const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, LJDev P, BoxDev B,
+          double *__restrict__ partial)
+{
+    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
+    const int sub = threadIdx.x % TPA;
+    const int groups_per_block = FORCE_BLOCK / TPA;
+    double acc[SEPGPU_NPART_F];      // uacc, (unused), vxx, vxy, vxz, vyy, vyz, vzz
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
+    int nin = 0;
+
+    for (int s0 = blockIdx.x * groups_per_block; s0 < n; s0 += gridDim.x * groups_per_block) {
+        const int s = s0 + threadIdx.x / TPA;
+        const bool valid = s < n;
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        if (valid) {
+            const d4 pi = xs[s];
+            int m = cnt[s];
+            int ti = 0;
+            if (TYPED) {
+                ti = tag_type(pi.w);
+                if (ti != P.t0 && ti != P.t1) m = 0;             // source/sepprfrc.c:164-165
+            }
+            const unsigned *row = nbr + s;
+#pragma unroll 2
+            for (int k = sub; k < m; k += TPA) {
+                const unsigned e = row[(size_t)k * npad];
+                const d4 pj = xs[e & SEPGPU_INDEX_MASK];
+                double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const int code = (int)(e >> SEPGPU_SHIFT_BITS);
+                if (code != 13) apply_image(code, B, dx, dy, dz);
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                bool in = r2 < P.cf2;
+                if (TYPED) {
+                    const int tj = tag_type(pj.w);
+                    in = in && ((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0));   // :171-172
+                }
+                if (in) {
+                    const double rri = P.sig2 * fast_rcp(r2);
+                    const double rri3 = rri * rri * rri;
+                    const double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;   // source/sepmisc.c:139, sepprfrc.c:888
+                    const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
+                    fx += gx; fy += gy; fz += gz;
+                    acc[0] = fma(rri3, rri3 - P.aw, acc[0]);                    // u/(4 eps) before the shift
+                    nin++;
+                    acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
+                    acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
+                }
+            }
+        }
+        // butterfly over the TPA lanes of this atom
+#pragma unroll
+        for (int o = TPA / 2; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (valid && sub == 0) {
+            const int i = order[s];
+            if (STORE) {
+                d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0;
+                f4[i] = o;
+            } else {
+                d4 o = f4[i];
+                o.x += fx; o.y += fy; o.z += fz;
+                f4[i] = o;
+            }
+        }
+    }
+    acc[0] = P.eps4 * acc[0] - P.shift * (double)nin;
+    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
+    }
+}
+
+// ---- Lennard-Jones, all pairs (SEP_BRUTE) ------------------------------------------------------------------
+// exact reference arithmetic for the separation (wrapped x, sep_Wrap branches)
+__device__ __forceinline__ int share_tab_f(const int *__restrict__ tab, int width, int a, int b)
+{
+    for (int k = 0; k < width; k++) {
+        int ta = tab[a * width + k], tb = tab[b * width + k];
+        if (ta == -1 || tb == -1) break;
+        if (ta == b || tb == a) return 1;
+    }
+    return 0;
+}
+
+template <bool STORE>
+__global__ void __launch_bounds__(FORCE_BLOCK)
+k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDev B, unsigned opt,
+           const int *__restrict__ excl_bond, double *__restrict__ partial)
+{
+    __shared__ d4 tile[FORCE_BLOCK];
+    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
+    const int i = blockIdx.x * FORCE_BLOCK + threadIdx.x;
+    const bool valid = i < n;
+    d4 pi; pi.x = pi.y = pi.z = 0; pi.w = 0;
+    if (valid) pi = x4[i];
+    const int ti = tag_type(pi.w), mi = tag_mol(pi.w);
+    const double hx = 0.5 * B.Lx, hy = 0.5 * B.Ly, hz = 0.5 * B.Lz;
+    double fx = 0, fy = 0, fz = 0;
+    double acc[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
+    int nin = 0;
+    for (int j0 = 0; j0 < n; j0 += FORCE_BLOCK) {
+        __syncthreads();
+        if (j0 + threadIdx.x < n) tile[threadIdx.x] = x4[j0 + threadIdx.x];
+        __syncthreads();
+        const int lim = min(FORCE_BLOCK, n - j0);
+        if (!valid) continue;
+        for (int t = 0; t < lim; t++) {
+            const int j = j0 + t;
+            if (j == i) continue;
+            const d4 pj = tile[t];
+            const int tj = tag_type(pj.w);
+            if (!((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0))) continue;
+            if (opt == SEPGPU_EXCL_SAME_MOL) { if (mi == tag_mol(pj.w) && mi != -1) continue; }   // :36-39
+            else if (opt == SEPGPU_EXCL_BONDED) { if (share_tab_f(excl_bond, 10, min(i, j), max(i, j)) == 1) continue; }  // :33
+            const double dx = wrap_exact(pi.x - pj.x, B.Lx, hx);
+            const double dy = wrap_exact(pi.y - pj.y, B.Ly, hy);
+            const double dz = wrap_exact(pi.z - pj.z, B.Lz, hz);
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (r2 < P.cf2) {
+                const double rri = P.sig2 / r2;
+                const double rri3 = rri * rri * rri;
+                const double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;
+                const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
+                fx += gx; fy += gy; fz += gz;
+                acc[0] = fma(rri3, rri3 - P.aw, acc[0]);
+                nin++;
+                acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
+                acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
+            }
+        }
+    }
+    if (valid) {
+        if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0; f4[i] = o; }
+        else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
+    }
+    acc[0] = P.eps4 * acc[0] - P.shift * (double)nin;
+    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
+}
+
+// ---- final reduction of the per-block partial rows ---------------------------------------------------------
+// flags: bit0 epot assign (source/sepprfrc.c:222), bit1 also add virial to pot_P_bond, bit2 add acc[1] to
+// ecoul AND epot (source/sepcoulomb.c:150-153)
+__global__ void __launch_bounds__(256)
+k_finalize_force(const double *__restrict__ partial, int nrows, DevScalars *scal, double scale, int flags)
+{
+    __shared__ double red[SEPGPU_NPART_F * 8];
+    double v[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) v[q] = 0.0;
+    for (int r = threadIdx.x; r < nrows; r += 256)
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_F; q++) v[q] += partial[r * SEPGPU_NPART_F + q];
+    block_sum<SEPGPU_NPART_F, 256>(v, red);
+    if (threadIdx.x == 0) {
+        const double e = v[0] * scale, ec = v[1] * scale;
+        if (flags & 1) scal->epot = e; else scal->epot += e;
+        if (flags & 4) { scal->epot += ec; scal->ecoul += ec; }
+        const double xx = v[2] * scale, xy = v[3] * scale, xz = v[4] * scale;
+        const double yy = v[5] * scale, yz = v[6] * scale, zz = v[7] * scale;
+        const double P[9] = {xx, xy, xz, xy, yy, yz, xz, yz, zz};
+        for (int k = 0; k < 9; k++) {
+            scal->pot_P[k] += P[k];
+            if (flags & 2) scal->pot_P_bond[k] += P[k];
+        }
+    }
+}
+
+int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
+{
+    k_finalize_force<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, scale, flags);
+    KERNEL_CHECK();
+    return 0;
+}
+
+int sepgpu_refresh_xs_identity(sepgpu_ctx *c)
+{
+    // brute mode works on x4 directly; nothing sorted
+    c->sorted_identity = true;
+    return 0;
+}
+
+static LJDev make_lj(const sepgpu_ljparam *p, const char types[2])
+{
+    LJDev d;
+    d.cf2 = p->cf * p->cf;
+    d.sig2 = p->sigma * p->sigma;
+    d.eps48 = 48.0 * p->eps;
+    d.eps4 = 4.0 * p->eps;
+    d.aw = p->aw;
+    d.awh = 0.5 * p->aw;
+    d.shift = p->shift;
+    d.t0 = (unsigned char)types[0];
+    d.t1 = (unsigned char)types[1];
+    return d;
+}
+
+template <int TPA>
+static void launch_lj_list(sepgpu_ctx *c, int grid, bool typed, bool store, const LJDev &P, const BoxDev &B)
+{
+#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial
+    if (typed) {
+        if (store) k_lj_list<TPA, true, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        else       k_lj_list<TPA, true, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+    } else {
+        if (store) k_lj_list<TPA, false, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        else       k_lj_list<TPA, false, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+    }
+#undef LJ_ARGS
+}
+
+extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2],
+                               const sepgpu_ljparam *p, unsigned opt, int epot_assign)
+{
+    if (!c || !sys || !types || !p) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const LJDev P = make_lj(p, types);
+    BoxDev B; B.Lx = sys->length[0]; B.Ly = sys->length[1]; B.Lz = sys->length[2];
+    const bool store = c->f_zero;
+    int rc;
+
+    if (sys->neighb_update == 0) {                       // SEP_BRUTE, source/sepprfrc.c:240-249
+        if (opt == SEPGPU_EXCL_BONDED && !c->excl_bond) {
+            sepgpu_set_error("force_lj: SEP_EXCL_BONDED needs the bond partner table");
+            return SEPGPU_ESTATE;
+        }
+        const int grid = (c->n + FORCE_BLOCK - 1) / FORCE_BLOCK;
+        ktimer_begin(c, &c->t_force);
+        if (store) k_lj_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial);
+        else       k_lj_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial);
+        ktimer_end(c, &c->t_force);
+        KERNEL_CHECK();
+        c->f_zero = false;
+        return sepgpu_finalize_force(c, grid, 0.5, epot_assign ? 1 : 0);
+    }
+
+    if (!c->list_valid) {
+        if ((rc = sepgpu_neighb_build(c, sys, opt))) return rc;
+    }
+    // the type test is compiled out when every atom carries the one requested type
+    const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
+    const int tpa = c->tpa;
+    const long long groups_per_block = FORCE_BLOCK / tpa;
+    long long want = ((long long)c->n + groups_per_block - 1) / groups_per_block;
+    const int grid = (int)(want < FORCE_MAX_GRID ? want : FORCE_MAX_GRID);
+    ktimer_begin(c, &c->t_force);
+    switch (tpa) {
+    case 1: launch_lj_list<1>(c, grid, typed, store, P, B); break;
+    case 2: launch_lj_list<2>(c, grid, typed, store, P, B); break;
+    case 4: launch_lj_list<4>(c, grid, typed, store, P, B); break;
+    case 8: launch_lj_list<8>(c, grid, typed, store, P, B); break;
+    case 16: launch_lj_list<16>(c, grid, typed, store, P, B); break;
+    default: launch_lj_list<32>(c, grid, typed, store, P, B); break;
+    }
+    ktimer_end(c, &c->t_force);
+    KERNEL_CHECK();
+    c->f_zero = false;
+    return sepgpu_finalize_force(c, grid, 0.5, epot_assign ? 1 : 0);
+}

@@ -1,0 +1,354 @@
+// sepgpu_force2.cu -- shifted-force Coulomb and DPD pair kernels.
+//
+// Stand-ins for sep_coulomb_sf_{neighb,brute} (reference source/sepcoulomb.c:96-160, 20-94) and
+// sep_dpdforce_{neighb,brute} (source/sepprfrc.c:1007-1133, 1135-1231).  Same ownership scheme as
+// the Lennard-Jones kernel in sepgpu_force.cu: full list, TPA lanes per atom, register accumulation,
+// shuffle reduction, one store per atom, per-block partial rows for energy and virial.
+#include "sepgpu_internal.cuh"
+
+#include <math.h>
+#include <float.h>
+
+#define FORCE_BLOCK 128
+#define FORCE_MAX_GRID (148 * 16)
+
+struct BoxC { double Lx, Ly, Lz; };
+
+int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags);
+int sepgpu_ensure_dpd(sepgpu_ctx *c);
+
+__device__ __forceinline__ double rsqrt_nr(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 3; it++) {            // y <- y + y*(0.5 - 0.5 x y^2)
+        const double h = 0.5 * y;
+        const double e = fma(-x * y, h, 0.5);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+
+__device__ __forceinline__ void apply_image_c(int code, const BoxC &B, double &dx, double &dy, double &dz)
+{
+    const int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
+    dx -= sx * B.Lx; dy -= sy * B.Ly; dz -= sz * B.Lz;
+}
+
+__global__ void k_sort_charges(const double *__restrict__ z, const int *__restrict__ order, double *__restrict__ zs, int n)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) zs[s] = z[order[s]];
+}
+
+// ---- Coulomb, Verlet list ----------------------------------------------------------------------------------------
+template <int TPA, bool STORE>
+__global__ void __launch_bounds__(FORCE_BLOCK)
+k_coulomb_list(const d4 *__restrict__ xs, const double *__restrict__ zs, const unsigned *__restrict__ nbr,
+               const int *__restrict__ cnt, const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad,
+               double cf, BoxC B, double *__restrict__ partial)
+{
+    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
+    const int sub = threadIdx.x % TPA;
+    const int groups_per_block = FORCE_BLOCK / TPA;
+    const double cf2 = cf * cf, icf2 = 1.0 / cf2, icf = 1.0 / cf;
+    double acc[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
+
+    for (int s0 = blockIdx.x * groups_per_block; s0 < n; s0 += gridDim.x * groups_per_block) {
+        const int s = s0 + threadIdx.x / TPA;
+        const bool valid = s < n;
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        if (valid) {
+            const d4 pi = xs[s];
+            const double zi = zs[s];
+            const int m = cnt[s];
+            const unsigned *row = nbr + s;
+#pragma unroll 2
+            for (int k = sub; k < m; k += TPA) {
+                const unsigned e = row[(size_t)k * npad];
+                const int j = (int)(e & SEPGPU_INDEX_MASK);
+                const d4 pj = xs[j];
+                const double zj = zs[j];
+                double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                const int code = (int)(e >> SEPGPU_SHIFT_BITS);
+                if (code != 13) apply_image_c(code, B, dx, dy, dz);
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                // the reference skips list owners with |z| < DBL_EPSILON (source/sepcoulomb.c:106); a pair
+                // with either charge below that contributes at most ~1e-16 z, so the product test is enough
+                const double zizj = zi * zj;
+                if (r2 < cf2 && zizj != 0.0) {
+                    const double rinv = rsqrt_nr(r2);
+                    const double r = r2 * rinv;
+                    const double ft = zizj * (rinv * rinv - icf2) * rinv;       // :121
+                    const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
+                    fx += gx; fy += gy; fz += gz;
+                    acc[1] += zizj * (rinv + (r - cf) * icf2 - icf);            // :150
+                    acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
+                    acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = TPA / 2; o > 0; o >>= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (valid && sub == 0) {
+            const int i = order[s];
+            if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0; f4[i] = o; }
+            else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
+        }
+    }
+    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
+}
+
+__device__ __forceinline__ int share_tab_c(const int *__restrict__ tab, int width, int a, int b)
+{
+    for (int k = 0; k < width; k++) {
+        int ta = tab[a * width + k], tb = tab[b * width + k];
+        if (ta == -1 || tb == -1) break;
+        if (ta == b || tb == a) return 1;
+    }
+    return 0;
+}
+
+// ---- Coulomb, all pairs ---------------------------------------------------------------------------------------------
+template <bool STORE>
+__global__ void __launch_bounds__(FORCE_BLOCK)
+k_coulomb_brute(const d4 *__restrict__ x4, const double *__restrict__ z, d4 *__restrict__ f4, int n, double cf,
+                BoxC B, unsigned opt, const int *__restrict__ eb, const int *__restrict__ ea,
+                const int *__restrict__ ed, double *__restrict__ partial)
+{
+    __shared__ d4 tile[FORCE_BLOCK];
+    __shared__ double ztile[FORCE_BLOCK];
+    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
+    const int i = blockIdx.x * FORCE_BLOCK + threadIdx.x;
+    const bool valid = i < n;
+    d4 pi; pi.x = pi.y = pi.z = 0; pi.w = 0;
+    double zi = 0.0;
+    if (valid) { pi = x4[i]; zi = z[i]; }
+    const int mi = tag_mol(pi.w);
+    const double cf2 = cf * cf, icf2 = 1.0 / cf2, icf = 1.0 / cf;
+    const double hx = 0.5 * B.Lx, hy = 0.5 * B.Ly, hz = 0.5 * B.Lz;
+    double fx = 0, fy = 0, fz = 0;
+    double acc[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
+    for (int j0 = 0; j0 < n; j0 += FORCE_BLOCK) {
+        __syncthreads();
+        if (j0 + threadIdx.x < n) { tile[threadIdx.x] = x4[j0 + threadIdx.x]; ztile[threadIdx.x] = z[j0 + threadIdx.x]; }
+        __syncthreads();
+        const int lim = min(FORCE_BLOCK, n - j0);
+        if (!valid) continue;
+        for (int t = 0; t < lim; t++) {
+            const int j = j0 + t;
+            if (j == i) continue;
+            const d4 pj = tile[t];
+            const double zj = ztile[t];
+            // the reference tests only the lower-index atom n of the pair (source/sepcoulomb.c:30)
+            const double zlow = i < j ? zi : zj;
+            if (fabs(zlow) < DBL_EPSILON) continue;
+            if (opt == SEPGPU_EXCL_SAME_MOL) { if (mi == tag_mol(pj.w) && mi != -1) continue; }
+            else if (opt == SEPGPU_EXCL_BONDED) {
+                const int a = min(i, j), b = max(i, j);
+                if (share_tab_c(eb, 10, a, b) + share_tab_c(ea, 10, a, b) + share_tab_c(ed, 20, a, b) == 1) continue;   // :37
+            }
+            const double dx = wrap_exact(pi.x - pj.x, B.Lx, hx);
+            const double dy = wrap_exact(pi.y - pj.y, B.Ly, hy);
+            const double dz = wrap_exact(pi.z - pj.z, B.Lz, hz);
+            const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (r2 < cf2) {
+                const double zizj = zi * zj;
+                const double r = sqrt(r2);
+                const double ft = zizj * (1.0 / r2 - icf2) / r;
+                const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
+                fx += gx; fy += gy; fz += gz;
+                acc[1] += zizj * (1.0 / r + (r - cf) * icf2 - icf);
+                acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
+                acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
+            }
+        }
+    }
+    if (valid) {
+        if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0; f4[i] = o; }
+        else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
+    }
+    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
+}
+
+template <int TPA>
+static void launch_coulomb(sepgpu_ctx *c, int grid, bool store, double cf, const BoxC &B)
+{
+    if (store) k_coulomb_list<TPA, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->zs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, cf, B, c->partial);
+    else       k_coulomb_list<TPA, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->zs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, cf, B, c->partial);
+}
+
+extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf, unsigned opt)
+{
+    if (!c || !sys) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    BoxC B; B.Lx = sys->length[0]; B.Ly = sys->length[1]; B.Lz = sys->length[2];
+    const bool store = c->f_zero;
+    if (sys->neighb_update == 0) {
+        if (opt == SEPGPU_EXCL_BONDED && !c->have_excl) {
+            sepgpu_set_error("coulomb_sf: SEP_EXCL_BONDED needs the partner tables");
+            return SEPGPU_ESTATE;
+        }
+        const int grid = (c->n + FORCE_BLOCK - 1) / FORCE_BLOCK;
+        ktimer_begin(c, &c->t_force);
+        if (store) k_coulomb_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial);
+        else       k_coulomb_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial);
+        ktimer_end(c, &c->t_force);
+        KERNEL_CHECK();
+        c->f_zero = false;
+        return sepgpu_finalize_force(c, grid, 0.5, 4);
+    }
+    // list mode: the reference neither builds nor checks the list here and ignores opt
+    // (source/sepcoulomb.c:8-16); it reuses whatever the preceding sep_force_pairs left behind.
+    if (!c->list_valid) {
+        sepgpu_set_error("coulomb_sf: no neighbour list (call sep_force_pairs first, as the reference requires)");
+        return SEPGPU_ESTATE;
+    }
+    if (!c->zs) CUDA_TRY(cudaMalloc((void **)&c->zs, sizeof(double) * (size_t)c->n));
+    k_sort_charges<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->z, c->order, c->zs, c->n);
+    const int tpa = c->tpa;
+    const long long gpb = FORCE_BLOCK / tpa;
+    long long want = ((long long)c->n + gpb - 1) / gpb;
+    const int grid = (int)(want < FORCE_MAX_GRID ? want : FORCE_MAX_GRID);
+    ktimer_begin(c, &c->t_force);
+    switch (tpa) {
+    case 1: launch_coulomb<1>(c, grid, store, cf, B); break;
+    case 2: launch_coulomb<2>(c, grid, store, cf, B); break;
+    case 4: launch_coulomb<4>(c, grid, store, cf, B); break;
+    case 8: launch_coulomb<8>(c, grid, store, cf, B); break;
+    case 16: launch_coulomb<16>(c, grid, store, cf, B); break;
+    default: launch_coulomb<32>(c, grid, store, cf, B); break;
+    }
+    ktimer_end(c, &c->t_force);
+    KERNEL_CHECK();
+    c->f_zero = false;
+    return sepgpu_finalize_force(c, grid, 0.5, 4);
+}
+
+// ---- DPD ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// pair-symmetric counter-based uniform in [0,1): both ends of a pair draw the same number, so the
+// random force obeys Newton's third law without communication.  Replaces the glibc rand() stream of
+// source/sepprfrc.c:1069, which no parallel evaluation order can reproduce.
+__device__ __forceinline__ double dpd_uniform(unsigned long long seed, unsigned long long step, unsigned i, unsigned j)
+{
+    const unsigned lo = i < j ? i : j, hi = i < j ? j : i;
+    unsigned long long h = mix64(seed ^ (step * 0xD1342543DE82EF95ULL));
+    h = mix64(h ^ (((unsigned long long)lo << 32) | hi));
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct DpdParams { double cf2, aij, gamma, sigma, isqrtdt, facchk; int t0, t1; unsigned long long seed, step; };
+
+// MODE 0: Verlet list (sorted indices, image codes); MODE 1: all pairs on x4
+template <int MODE, bool STORE>
+__global__ void __launch_bounds__(FORCE_BLOCK)
+k_dpd(const d4 *__restrict__ xs, const d4 *__restrict__ x4, const d4 *__restrict__ pv4,
+      const unsigned *__restrict__ nbr, const int *__restrict__ cnt, const int *__restrict__ order,
+      d4 *__restrict__ f4, int n, int npad, DpdParams P, BoxC B, double *__restrict__ partial)
+{
+    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
+    double acc[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
+    const int s = blockIdx.x * FORCE_BLOCK + threadIdx.x;
+    if (s < n) {
+        const int i = MODE == 0 ? order[s] : s;
+        const d4 pi = MODE == 0 ? xs[s] : x4[s];
+        const d4 vi = pv4[i];
+        const int ti = tag_type(pi.w);
+        const int m = MODE == 0 ? cnt[s] : n;
+        double fx = 0, fy = 0, fz = 0;
+        if (ti == P.t0 || ti == P.t1) {
+            for (int k = 0; k < m; k++) {
+                int j, jo; d4 pj; double dx, dy, dz;
+                if (MODE == 0) {
+                    const unsigned e = nbr[(size_t)k * npad + s];
+                    j = (int)(e & SEPGPU_INDEX_MASK); jo = order[j]; pj = xs[j];
+                    dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
+                    const int code = (int)(e >> SEPGPU_SHIFT_BITS);
+                    if (code != 13) apply_image_c(code, B, dx, dy, dz);
+                } else {
+                    j = k; jo = k; if (j == s) continue; pj = x4[j];
+                    dx = wrap_exact(pi.x - pj.x, B.Lx, 0.5 * B.Lx);
+                    dy = wrap_exact(pi.y - pj.y, B.Ly, 0.5 * B.Ly);
+                    dz = wrap_exact(pi.z - pj.z, B.Lz, 0.5 * B.Lz);
+                }
+                const int tj = tag_type(pj.w);
+                if (!((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0))) continue;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                if (!(r2 < P.cf2)) continue;
+                const double dij = sqrt(r2), w = 1.0 - dij;                     // source/sepprfrc.c:1058-1059
+                const double rx = dx / dij, ry = dy / dij, rz = dz / dij;
+                const d4 vj = pv4[jo];
+                const double dotrv = rx * (vi.x - vj.x) + ry * (vi.y - vj.y) + rz * (vi.z - vj.z);
+                const double xi = (dpd_uniform(P.seed, P.step, (unsigned)i, (unsigned)jo) - 0.5) * P.facchk;
+                const double mag = P.aij * w - P.gamma * w * w * dotrv + P.sigma * w * P.isqrtdt * xi;  // fC+fD+fR along rhat
+                fx += mag * rx; fy += mag * ry; fz += mag * rz;
+                acc[0] += 0.5 * P.aij * w * w;                                   // :1084
+                if (MODE == 1) {                                                 // brute path keeps the conservative virial (:1199-1201)
+                    const double cx = P.aij * w * rx, cy = P.aij * w * ry, cz = P.aij * w * rz;
+                    acc[2] += cx * dx; acc[3] += cx * dy; acc[4] += cx * dz;
+                    acc[5] += cy * dy; acc[6] += cy * dz; acc[7] += cz * dz;
+                }
+            }
+        }
+        if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0; f4[i] = o; }
+        else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
+    }
+    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
+}
+
+extern "C" int sepgpu_force_dpd(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], double cf,
+                                double aij, double temp, double sigma, unsigned opt,
+                                unsigned long long seed, unsigned long long step)
+{
+    if (!c || !sys || !types) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = sepgpu_ensure_dpd(c);
+    if (rc) return rc;
+    DpdParams P;
+    P.cf2 = cf * cf; P.aij = aij; P.gamma = sigma * sigma / (2.0 * temp); P.sigma = sigma;
+    P.isqrtdt = 1.0 / sqrt(sys->dt); P.facchk = 2.0 * sqrt(3.0);
+    P.t0 = (unsigned char)types[0]; P.t1 = (unsigned char)types[1];
+    P.seed = seed; P.step = step;
+    BoxC B; B.Lx = sys->length[0]; B.Ly = sys->length[1]; B.Lz = sys->length[2];
+    const bool store = c->f_zero;
+    const int grid = (c->n + FORCE_BLOCK - 1) / FORCE_BLOCK;
+    if (grid > SEPGPU_MAX_BLOCKS_PARTIAL) { sepgpu_set_error("force_dpd: system too large"); return SEPGPU_EINVAL; }
+    if (sys->neighb_update == 0) {
+        if (store) k_dpd<1, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
+        else       k_dpd<1, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
+        KERNEL_CHECK();
+        c->f_zero = false;
+        return sepgpu_finalize_force(c, grid, 0.5, 0);        // brute: epot += (source/sepprfrc.c:1196)
+    }
+    if (!c->list_valid && (rc = sepgpu_neighb_build(c, sys, opt))) return rc;    // :1021-1031
+    if (store) k_dpd<0, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
+    else       k_dpd<0, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
+    KERNEL_CHECK();
+    c->f_zero = false;
+    return sepgpu_finalize_force(c, grid, 0.5, 1);            // list: epot assigned (:1132), no virial (:1089-1116)
+}

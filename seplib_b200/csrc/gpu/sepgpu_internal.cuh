@@ -1,0 +1,211 @@
+// sepgpu_internal.cuh -- device-side data model of seplib-b200 (sm_100a only).
+//
+// HBM layout (all FP64, 32-byte vectors so that one atom == one DRAM sector and every per-atom
+// access is a single 256-bit LDG/STG, which sm_100a has natively):
+//
+//   primary state, ORIGINAL atom order (host indices, topology indices stay valid):
+//     x4[i]  = {x, y, z, tag}       wrapped position; tag = type | (molindex+1)<<8 as raw bits
+//     v4[i]  = {vx, vy, vz, m}
+//     f4[i]  = {fx, fy, fz, 0}
+//     xn4[i] = {xn, yn, zn, 0}      position at last list build (reference: seppart.xn)
+//     cr4[i] = {cross_neighb[3], packed crossings since the list was built}
+//     crossings[3i..]               total boundary crossings (written only when an atom wraps)
+//   cell-sorted copy used by the list build and the force kernels:
+//     xs[s]  = {xu, yu, zu, tag}    xu = x + (crossings since list build)*L : continuous between
+//                                   rebuilds, so the image shift stored with a list entry stays valid
+//     order[s] = i, rank[i] = s
+//   Verlet list: FULL list (i->j and j->i), transposed so a warp reads 128 contiguous bytes:
+//     nbr[k*npad + s] = j_sorted | shift_code << 26,   cnt[s]
+//
+// Reference counterparts are cited at each kernel.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sepgpu.h"
+
+struct __align__(32) d4 { double x, y, z, w; };
+struct __align__(16) i4 { int x, y, z, w; };
+
+#define SEPGPU_SHIFT_BITS 26
+#define SEPGPU_INDEX_MASK ((1u << SEPGPU_SHIFT_BITS) - 1u)
+#define SEPGPU_MAX_ATOMS  (1u << SEPGPU_SHIFT_BITS)
+
+// number of doubles one block writes as its partial result
+#define SEPGPU_NPART_F 8      // force kernels : e, ecoul, 6 virial
+#define SEPGPU_NPART_I 12     // integrators   : sum m vh^2, 6 kin_P, max d2, sum m v^2, 3 momentum
+#define SEPGPU_MAX_BLOCKS_PARTIAL 65536
+
+// device-resident scalar block (one per context)
+struct DevScalars {
+    double epot, ecoul, ekin;
+    double pot_P[9], kin_P[9], pot_P_bond[9];
+    double max_dist2;
+    double sum_mv2;
+    double alpha[4];
+    double mom[4];             // sum m v (3) + sum m, per sepgpu_reset_momentum
+    int neighb_flag;           // skin trigger fired in the LAST integrator call
+    int nbuild;
+    int error;
+    int max_neighb;
+    long long npairs_listed;
+    int xn_pending;            // (reserved)
+    int max_half;              // longest reference-style half list at the last build
+    int sum_mv2_valid;
+    int pad;
+};
+
+struct KernelTimer {
+    cudaEvent_t start[64], stop[64];
+    int used;
+    float total_ms;
+    int launches;
+    bool enabled;
+};
+
+struct sepgpu_ctx {
+    int n;                 // atoms
+    int npad;              // n rounded up to 32
+    int device;
+    cudaStream_t stream;
+
+    d4 *x4, *v4, *f4, *xn4, *pv4, *pa4;
+    i4 *cr4;
+    int *crossings;        // 3n
+    double *z;             // charges
+    char *type;
+    int *molindex;
+    double *zs;            // charges in cell-sorted order (valid while zs_valid)
+    bool zs_valid;
+    int *excl_bond, *excl_angle, *excl_dihed;   // partner tables, n*10 / n*10 / n*20
+    bool have_excl;
+    bool have_charge;
+    bool have_dpd;         // pv4/pa4 allocated
+
+    // cell-sorted side
+    d4 *xs;
+    float4 *xf;            // cell-relative FP32 copy for the list prefilter (w = raw cell index)
+    int *order, *rank;
+    int *cell_of;          // [n] cell index of atom i
+    int *cell_cnt, *cell_start;   // [ncell_cap+1]
+    int *tmp_slot;         // [n]
+    int ncell_cap;
+    int grid_n[3];         // cell grid the current list was built on
+
+    // Verlet list
+    unsigned *nbr;
+    int *cnt;
+    int cap;               // rows allocated (max neighbours per atom)
+    bool list_valid;
+    unsigned list_opt;
+    bool sorted_identity;  // brute mode: xs is x4 in original order
+
+    // topology
+    unsigned *blist, *alist, *dlist;
+    unsigned nb, na, nd;
+    int *atom_bond_ptr, *atom_bond_idx;     // inverse topology (CSR): term*4+role
+    int *atom_angle_ptr, *atom_angle_idx;
+    int *atom_dihed_ptr, *atom_dihed_idx;
+    double *blengths, *angles, *dihedrals;
+
+    // scalars and partial sums
+    DevScalars *scal;            // device
+    DevScalars *scal_host;       // pinned mirror
+    double *partial;             // [SEPGPU_MAX_BLOCKS_PARTIAL * 16]
+
+    // state flags
+    bool f_zero;                 // sep_reset_force seen, no force kernel since: first kernel stores, not adds
+    int  pending_alpha_slot;     // >=0: f -= alpha[slot] m v still to be applied by the integrator
+    int  pending_alpha_type;     // -1 all atoms, else restrict to this type char
+    bool xs_current;             // xs matches x4 (brute mode / after host put)
+
+    // staging
+    void *stage; size_t stage_bytes;     // pinned host
+    void *dstage; size_t dstage_bytes;   // device
+
+    int single_type;             // type char shared by all atoms, or -1 (mixed)
+    bool mv2_valid;              // scal->sum_mv2 matches the velocities now in v4
+
+    // options
+    int tpa;                     // lanes per atom in list force kernels
+    int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
+
+    // measurement
+    cudaEvent_t ev0, ev1;
+    KernelTimer t_force, t_build, t_intgr;
+    void *flush_buf; size_t flush_bytes;
+};
+
+// ---- error plumbing -------------------------------------------------------------------------------
+void sepgpu_set_error(const char *fmt, ...);
+#define CUDA_TRY(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            sepgpu_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                  \
+                             cudaGetErrorString(_e));                                       \
+            return SEPGPU_ECUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+// ---- small device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ long long tag_bits(double w) { return __double_as_longlong(w); }
+__device__ __forceinline__ int tag_type(double w) { return (int)(tag_bits(w) & 0xff); }
+__device__ __forceinline__ int tag_mol(double w) { return (int)((tag_bits(w) >> 8) & 0xffffffffLL) - 1; }
+__device__ __forceinline__ double make_tag(int type, int molindex)
+{
+    long long b = (long long)(type & 0xff) | ((long long)(unsigned)(molindex + 1) << 8);
+    return __longlong_as_double(b);
+}
+
+// sep_Wrap (include/sepmisc.h:81-85), exact branch form
+__device__ __forceinline__ double wrap_exact(double d, double len, double half)
+{
+    if (d > half) d -= len;
+    else if (d < -half) d += len;
+    return d;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block reduction of NV per-thread values; result valid in thread 0.  Fixed tree => deterministic.
+template <int NV, int BLOCK>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* NV * BLOCK/32 */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        double s = warp_sum(v[q]);
+        if (lane == 0) smem[q * (BLOCK / 32) + wid] = s;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            double s = lane < BLOCK / 32 ? smem[q * (BLOCK / 32) + lane] : 0.0;
+            v[q] = warp_sum(s);
+        }
+    }
+}
+
+// internal cross-file entry points
+int sepgpu_ensure_stage(sepgpu_ctx *c, size_t bytes);
+int sepgpu_apply_pending(sepgpu_ctx *c);          // flush a deferred thermostat update into f4
+int sepgpu_refresh_xs_identity(sepgpu_ctx *c);    // brute mode: xs <- x4
+void ktimer_begin(sepgpu_ctx *c, KernelTimer *t);
+void ktimer_end(sepgpu_ctx *c, KernelTimer *t);

@@ -1,0 +1,406 @@
+// sepgpu_intgr.cu -- fused thermostat + integrator kernels.
+//
+// Stand-ins for sep_nosehoover / _sep_nosehoover_type (reference source/sepintgr.c:149-198),
+// sep_leapfrog + sep_periodic + the skin trigger + sep_set_xn (source/sepintgr.c:18-88,
+// source/sepmisc.c:525-533), sep_verlet_dpd (source/sepintgr.c:296-345), sep_reset_momentum
+// (source/sepmisc.c:1173-1192) and the coordinate rescale of sep_compress_box (:1009-1010).
+//
+// The reference makes two passes for the thermostat (sum m v^2, then f -= alpha m v) and a third for
+// leapfrog.  Here the integrator kernel of step n emits sum m v^2 for the thermostat of step n+1, the
+// multiplier update is a one-thread kernel, and f -= alpha m v is applied inside the next integrator
+// kernel -- one streaming pass over the atoms per time step (HBM-bound: 144 B read + 128 B written).
+#include "sepgpu_internal.cuh"
+
+#define INTGR_BLOCK 256
+#define INTGR_MAX_GRID (148 * 8)
+
+struct IntgrParams {
+    double Lx, Ly, Lz;
+    double dt, skin;
+    int n;
+    int alpha_slot;     // -1: no pending thermostat
+    int alpha_type;     // -1: all atoms
+    int f_zero;         // force array logically zero
+    int write_xs;       // maintain the cell-sorted copy
+};
+
+__device__ __forceinline__ int pack_cl(int cx, int cy, int cz) { return (cx + 512) | ((cy + 512) << 10) | ((cz + 512) << 20); }
+__device__ __forceinline__ void unpack_cl(int w, int &cx, int &cy, int &cz)
+{
+    if (w == 0) { cx = cy = cz = 0; return; }
+    cx = (w & 1023) - 512; cy = ((w >> 10) & 1023) - 512; cz = ((w >> 20) & 1023) - 512;
+}
+
+// one component of sep_periodic (source/sepintgr.c:21-35); returns the squared displacement term
+__device__ __forceinline__ double periodic_1d(double &x, double L, int &cn, int &cl, int &cross_total, bool &changed, double xn)
+{
+    if (x > L) { x -= L; cn++; cl++; cross_total = 1; changed = true; }
+    else if (x < 0.0) { x += L; cn--; cl--; cross_total = -1; changed = true; }
+    const double ri = (x + cn * L) - xn;
+    return ri * ri;
+}
+
+template <bool DPD>
+__global__ void __launch_bounds__(INTGR_BLOCK)
+k_integrate(d4 *__restrict__ x4, d4 *__restrict__ v4, d4 *__restrict__ f4, const d4 *__restrict__ xn4,
+            i4 *__restrict__ cr4, int *__restrict__ crossings, const int *__restrict__ rank,
+            d4 *__restrict__ xs, d4 *__restrict__ pv4, d4 *__restrict__ pa4, const DevScalars *__restrict__ scal,
+            IntgrParams P, double lambda, int stepnow, double *__restrict__ partial)
+{
+    __shared__ double red[SEPGPU_NPART_I * (INTGR_BLOCK / 32)];
+    double acc[SEPGPU_NPART_I];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_I; q++) acc[q] = 0.0;
+    const double alpha = P.alpha_slot >= 0 ? scal->alpha[P.alpha_slot] : 0.0;
+    const double dt = P.dt;
+
+    for (int i = blockIdx.x * INTGR_BLOCK + threadIdx.x; i < P.n; i += gridDim.x * INTGR_BLOCK) {
+        d4 x = x4[i], v = v4[i], f;
+        if (P.f_zero) { f.x = f.y = f.z = f.w = 0.0; } else f = f4[i];
+        const double m = v.w;
+        bool f_changed = P.f_zero != 0;
+        if (P.alpha_slot >= 0 && (P.alpha_type < 0 || tag_type(x.w) == P.alpha_type)) {
+            // sep_nosehoover second pass: f[k] -= alpha*m*v[k]   (source/sepintgr.c:163-166)
+            // (_sep_nosehoover_type multiplies alpha*v*m, :193 -- same value up to rounding order)
+            const double am = alpha * m;
+            f.x -= am * v.x; f.y -= am * v.y; f.z -= am * v.z;
+            f_changed = true;
+        }
+        const double ax = f.x / m, ay = f.y / m, az = f.z / m;       // :53
+        double ux, uy, uz;                                            // velocity entering ekin / kin_P
+        if (!DPD) {
+            v.x += ax * dt; v.y += ay * dt; v.z += az * dt;           // :54
+            x.x += v.x * dt; x.y += v.y * dt; x.z += v.z * dt;        // :55
+            ux = v.x - 0.5 * ax * dt; uy = v.y - 0.5 * ay * dt; uz = v.z - 0.5 * az * dt;   // :57
+        } else {
+            d4 pa = pa4[i];
+            if (stepnow > 0) {                                         // source/sepintgr.c:311-312
+                v.x += 0.5 * dt * (ax + pa.x); v.y += 0.5 * dt * (ay + pa.y); v.z += 0.5 * dt * (az + pa.z);
+            }
+            x.x += v.x * dt + 0.5 * dt * dt * ax;                      // :314
+            x.y += v.y * dt + 0.5 * dt * dt * ay;
+            x.z += v.z * dt + 0.5 * dt * dt * az;
+            d4 pv; pv.x = v.x + lambda * dt * ax; pv.y = v.y + lambda * dt * ay; pv.z = v.z + lambda * dt * az; pv.w = 0;
+            pa.x = ax; pa.y = ay; pa.z = az;
+            pv4[i] = pv; pa4[i] = pa;
+            ux = v.x; uy = v.y; uz = v.z;                              // :321
+        }
+        acc[0] += ux * ux * m; acc[0] += uy * uy * m; acc[0] += uz * uz * m;      // :58
+        acc[1] += ux * ux * m; acc[2] += ux * uy * m; acc[3] += ux * uz * m;      // :66-68 (symmetric)
+        acc[4] += uy * uy * m; acc[5] += uy * uz * m; acc[6] += uz * uz * m;
+        acc[8] += (v.x * v.x + v.y * v.y + v.z * v.z) * m;           // for the next sep_nosehoover
+        acc[9] += v.x * m; acc[10] += v.y * m; acc[11] += v.z * m;
+
+        i4 cr = cr4[i];
+        const d4 xn = xn4[i];
+        int clx, cly, clz; unpack_cl(cr.w, clx, cly, clz);
+        int tx = 0, ty = 0, tz = 0; bool changed = false;
+        double d2 = 0.0;
+        d2 += periodic_1d(x.x, P.Lx, cr.x, clx, tx, changed, xn.x);
+        d2 += periodic_1d(x.y, P.Ly, cr.y, cly, ty, changed, xn.y);
+        d2 += periodic_1d(x.z, P.Lz, cr.z, clz, tz, changed, xn.z);
+        acc[7] = fmax(acc[7], d2);                                    // :62
+
+        x4[i] = x; v4[i] = v;
+        if (f_changed) f4[i] = f;
+        if (changed) {
+            cr.w = pack_cl(clx, cly, clz);
+            cr4[i] = cr;
+            if (tx) crossings[3 * i] += tx;
+            if (ty) crossings[3 * i + 1] += ty;
+            if (tz) crossings[3 * i + 2] += tz;
+        }
+        if (P.write_xs) {
+            d4 u; u.x = x.x + clx * P.Lx; u.y = x.y + cly * P.Ly; u.z = x.z + clz * P.Lz; u.w = x.w;
+            xs[rank[i]] = u;
+        }
+    }
+    // block reduction: sums for all but slot 7 (max)
+    const double mymax = acc[7];
+    acc[7] = 0.0;
+    block_sum<SEPGPU_NPART_I, INTGR_BLOCK>(acc, red);
+    __syncthreads();
+    double wm = warp_max(mymax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int w = 0; w < INTGR_BLOCK / 32; w++) mx = fmax(mx, red[w]);
+        acc[7] = mx;
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_I; q++) partial[blockIdx.x * SEPGPU_NPART_I + q] = acc[q];
+    }
+}
+
+// one block: reduce the partial rows, update sepret/sepsys scalars, evaluate the skin trigger
+__global__ void __launch_bounds__(256)
+k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin)
+{
+    __shared__ double red[SEPGPU_NPART_I * 8];
+    double v[SEPGPU_NPART_I];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_I; q++) v[q] = 0.0;
+    double mx = 0.0;
+    for (int r = threadIdx.x; r < nrows; r += 256) {
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_I; q++)
+            if (q != 7) v[q] += partial[r * SEPGPU_NPART_I + q];
+        mx = fmax(mx, partial[r * SEPGPU_NPART_I + 7]);
+    }
+    block_sum<SEPGPU_NPART_I, 256>(v, red);
+    __syncthreads();
+    double wm = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 8; w++) mx = fmax(mx, red[w]);
+        scal->ekin += 0.5 * v[0];                                     // source/sepintgr.c:87
+        const double K[9] = {v[1], v[2], v[3], v[2], v[4], v[5], v[3], v[5], v[6]};
+        for (int k = 0; k < 9; k++) scal->kin_P[k] += K[k];
+        if (mx > scal->max_dist2) scal->max_dist2 = mx;               // :62
+        scal->sum_mv2 = v[8];
+        scal->mom[0] = v[9]; scal->mom[1] = v[10]; scal->mom[2] = v[11];
+        scal->neighb_flag = sqrt(scal->max_dist2) > skin * 0.5 ? 1 : 0;   // :72
+    }
+}
+
+// xn <- x, cross_neighb <- 0 (source/sepintgr.c:76-82)
+__global__ void k_set_xn(const d4 *__restrict__ x4, d4 *__restrict__ xn4, i4 *__restrict__ cr4, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 x = x4[i]; x.w = 0.0;
+    xn4[i] = x;
+    i4 c = cr4[i]; c.x = c.y = c.z = 0;
+    cr4[i] = c;
+}
+
+int sepgpu_ensure_dpd(sepgpu_ctx *c);
+
+static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double lambda, int stepnow)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (dpd) { int rc = sepgpu_ensure_dpd(c); if (rc) return rc; }
+    IntgrParams P;
+    P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
+    P.dt = sys->dt; P.skin = sys->skin; P.n = c->n;
+    P.alpha_slot = c->pending_alpha_slot;
+    P.alpha_type = c->pending_alpha_type;
+    P.f_zero = c->f_zero ? 1 : 0;
+    P.write_xs = (sys->neighb_update != 0 && c->list_valid) ? 1 : 0;
+    long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+    const int grid = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
+    ktimer_begin(c, &c->t_intgr);
+    if (dpd)
+        k_integrate<true><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial);
+    else
+        k_integrate<false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial);
+    k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin);
+    ktimer_end(c, &c->t_intgr);
+    KERNEL_CHECK();
+    if (c->pending_alpha_slot >= 0 || c->f_zero) c->f_zero = false;   // f4 now holds the force that was used
+    c->pending_alpha_slot = -1;
+    c->pending_alpha_type = -1;
+    c->mv2_valid = true;
+    if (!P.write_xs) c->xs_current = false;
+
+    // the trigger is needed by the host before the next force call: small D2H + stream sync per step
+    CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->scal_host->neighb_flag) {
+        k_set_xn<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n);
+        KERNEL_CHECK();
+        c->list_valid = false;
+    }
+    return 0;
+}
+
+extern "C" int sepgpu_leapfrog(sepgpu_ctx *c, const sepgpu_sys *sys)
+{
+    if (!c || !sys) return SEPGPU_EINVAL;
+    return run_integrator(c, sys, false, 0.0, 0);
+}
+
+extern "C" int sepgpu_verlet_dpd(sepgpu_ctx *c, const sepgpu_sys *sys, double lambda, int stepnow)
+{
+    if (!c || !sys) return SEPGPU_EINVAL;
+    return run_integrator(c, sys, true, lambda, stepnow);
+}
+
+// ---- thermostat -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(INTGR_BLOCK)
+k_sum_mv2(const d4 *__restrict__ v4, const d4 *__restrict__ x4, int n, int type, double *__restrict__ partial)
+{
+    __shared__ double red[2 * (INTGR_BLOCK / 32)];
+    double acc[2] = {0.0, 0.0};
+    for (int i = blockIdx.x * INTGR_BLOCK + threadIdx.x; i < n; i += gridDim.x * INTGR_BLOCK) {
+        if (type >= 0 && tag_type(x4[i].w) != type) continue;
+        const d4 v = v4[i];
+        acc[0] += (v.x * v.x + v.y * v.y + v.z * v.z) * v.w;
+        acc[1] += 1.0;
+    }
+    block_sum<2, INTGR_BLOCK>(acc, red);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = acc[0]; partial[2 * blockIdx.x + 1] = acc[1]; }
+}
+
+// mode 0: sep_nosehoover (source/sepintgr.c:157-161); mode 1: _sep_nosehoover_type (:180-187)
+__global__ void __launch_bounds__(256)
+k_nh_update(const double *__restrict__ partial, int nrows, DevScalars *scal, int slot, int mode,
+            double temp0, double tau_or_Q, double dt, int npart, double a0, double a1, double a2)
+{
+    __shared__ double red[2 * 8];
+    double v[2] = {0.0, 0.0};
+    if (nrows > 0) {
+        for (int r = threadIdx.x; r < nrows; r += 256) { v[0] += partial[2 * r]; v[1] += partial[2 * r + 1]; }
+        block_sum<2, 256>(v, red);
+    }
+    if (threadIdx.x == 0) {
+        const double sum = nrows > 0 ? v[0] : scal->sum_mv2;
+        if (mode == 0) {
+            const double ekin = 0.5 * sum / npart;
+            const double temp = 0.666667 * ekin;
+            scal->alpha[slot] = scal->alpha[slot] + dt / (tau_or_Q * tau_or_Q) * (temp / temp0 - 1.0);
+        } else {
+            const double g = 3.0 * v[1] - 3.0;
+            // history shift: alpha[0]<-alpha[1], alpha[1]<-alpha[2], alpha[2]<-old alpha[0] + ...
+            scal->alpha[0] = a1;
+            scal->alpha[1] = a2;
+            scal->alpha[2] = a0 + 2.0 * dt * (sum - g * temp0) / tau_or_Q;
+        }
+    }
+}
+
+extern "C" int sepgpu_nosehoover(sepgpu_ctx *c, const sepgpu_sys *sys, double temp0, int slot, double tau)
+{
+    if (!c || !sys || slot < 0 || slot > 3) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = sepgpu_apply_pending(c);          // two thermostat calls in one step: flush the first
+    if (rc) return rc;
+    int nrows = 0;
+    if (!c->mv2_valid) {
+        long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+        nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
+        k_sum_mv2<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n, -1, c->partial);
+    }
+    k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, slot, 0, temp0, tau, sys->dt, c->n, 0, 0, 0);
+    KERNEL_CHECK();
+    c->pending_alpha_slot = slot;
+    c->pending_alpha_type = -1;
+    return 0;
+}
+
+extern "C" int sepgpu_nosehoover_type(sepgpu_ctx *c, const sepgpu_sys *sys, char type, double Td,
+                                      double alpha3[3], double Q)
+{
+    if (!c || !sys || !alpha3) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = sepgpu_apply_pending(c);
+    if (rc) return rc;
+    long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+    const int nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
+    k_sum_mv2<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n, (unsigned char)type, c->partial);
+    k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, 0, 1, Td, Q, sys->dt, c->n,
+                                          alpha3[0], alpha3[1], alpha3[2]);
+    KERNEL_CHECK();
+    // the history is host-visible state of the caller: read it back (3 doubles)
+    CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    alpha3[0] = c->scal_host->alpha[0]; alpha3[1] = c->scal_host->alpha[1]; alpha3[2] = c->scal_host->alpha[2];
+    c->pending_alpha_slot = 1;                 // the multiplier applied is alpha[1] (source/sepintgr.c:193)
+    c->pending_alpha_type = (unsigned char)type;
+    return 0;
+}
+
+__global__ void k_apply_alpha(d4 *__restrict__ f4, const d4 *__restrict__ v4, const d4 *__restrict__ x4,
+                              const DevScalars *__restrict__ scal, int slot, int type, int n, int f_zero)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 f;
+    if (f_zero) { f.x = f.y = f.z = f.w = 0.0; } else f = f4[i];
+    if (type < 0 || tag_type(x4[i].w) == type) {
+        const d4 v = v4[i];
+        const double am = scal->alpha[slot] * v.w;
+        f.x -= am * v.x; f.y -= am * v.y; f.z -= am * v.z;
+    }
+    f4[i] = f;
+}
+
+int sepgpu_apply_pending(sepgpu_ctx *c)
+{
+    if (c->pending_alpha_slot < 0) return 0;
+    k_apply_alpha<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->f4, c->v4, c->x4, c->scal, c->pending_alpha_slot,
+                                                            c->pending_alpha_type, c->n, c->f_zero ? 1 : 0);
+    KERNEL_CHECK();
+    c->pending_alpha_slot = -1;
+    c->pending_alpha_type = -1;
+    c->f_zero = false;
+    return 0;
+}
+
+// ---- momentum reset / rescale ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(INTGR_BLOCK)
+k_sum_mom(const d4 *__restrict__ v4, const d4 *__restrict__ x4, int n, int type, double *__restrict__ partial)
+{
+    __shared__ double red[4 * (INTGR_BLOCK / 32)];
+    double acc[4] = {0, 0, 0, 0};
+    for (int i = blockIdx.x * INTGR_BLOCK + threadIdx.x; i < n; i += gridDim.x * INTGR_BLOCK) {
+        if (tag_type(x4[i].w) != type) continue;
+        const d4 v = v4[i];
+        acc[0] += v.x * v.w; acc[1] += v.y * v.w; acc[2] += v.z * v.w; acc[3] += v.w;
+    }
+    block_sum<4, INTGR_BLOCK>(acc, red);
+    if (threadIdx.x == 0) for (int q = 0; q < 4; q++) partial[4 * blockIdx.x + q] = acc[q];
+}
+
+__global__ void __launch_bounds__(256) k_mom_final(const double *__restrict__ partial, int nrows, DevScalars *scal)
+{
+    __shared__ double red[4 * 8];
+    double v[4] = {0, 0, 0, 0};
+    for (int r = threadIdx.x; r < nrows; r += 256) for (int q = 0; q < 4; q++) v[q] += partial[4 * r + q];
+    block_sum<4, 256>(v, red);
+    if (threadIdx.x == 0) for (int q = 0; q < 4; q++) scal->mom[q] = v[q];
+}
+
+__global__ void k_sub_mom(d4 *__restrict__ v4, const d4 *__restrict__ x4, int n, int type, const DevScalars *__restrict__ scal)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || tag_type(x4[i].w) != type) return;
+    const double mass = scal->mom[3];
+    d4 v = v4[i];
+    v.x -= scal->mom[0] / mass; v.y -= scal->mom[1] / mass; v.z -= scal->mom[2] / mass;   // source/sepmisc.c:1190
+    v4[i] = v;
+}
+
+extern "C" int sepgpu_reset_momentum(sepgpu_ctx *c, char type)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+    const int nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
+    k_sum_mom<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n, (unsigned char)type, c->partial);
+    k_mom_final<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal);
+    k_sub_mom<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->v4, c->x4, c->n, (unsigned char)type, c->scal);
+    KERNEL_CHECK();
+    c->mv2_valid = false;
+    return 0;
+}
+
+__global__ void k_scale_x(d4 *__restrict__ x4, d4 *__restrict__ xs, int n, double xi, int scale_xs)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 x = x4[i]; x.x *= xi; x.y *= xi; x.z *= xi; x4[i] = x;
+    if (scale_xs) { d4 u = xs[i]; u.x *= xi; u.y *= xi; u.z *= xi; xs[i] = u; }
+}
+
+extern "C" int sepgpu_scale_positions(sepgpu_ctx *c, double xi)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    k_scale_x<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xs, c->n, xi, c->list_valid ? 1 : 0);
+    KERNEL_CHECK();
+    return 0;
+}

@@ -1,0 +1,643 @@
+// sepgpu_state.cu -- context lifetime, host<->HBM marshalling, scalar block, measurement helpers.
+#include "sepgpu_internal.cuh"
+
+#include <stdarg.h>
+#include <stdlib.h>
+
+static thread_local char g_err[512] = "";
+
+void sepgpu_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *sepgpu_last_error(void) { return g_err; }
+
+extern "C" int sepgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+template <typename T>
+static int dalloc(T **p, size_t count)
+{
+    CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    CUDA_TRY(cudaMemset(*p, 0, sizeof(T) * (count ? count : 1)));
+    return 0;
+}
+
+__global__ void k_init_tags(d4 *x4, d4 *v4, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // defaults of sep_init (source/sepinit.c:34-45): type 'A', m = 1, molindex = -1, z = 0
+    x4[i].w = make_tag('A', -1);
+    v4[i].w = 1.0;
+}
+
+__global__ void k_fill_int(int *p, int v, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
+{
+    if (!out || npart == 0 || npart >= SEPGPU_MAX_ATOMS) {
+        sepgpu_set_error("sepgpu_create: npart=%zu out of range (1..%u)", npart, SEPGPU_MAX_ATOMS - 1);
+        return SEPGPU_EINVAL;
+    }
+    int ndev = sepgpu_device_count();
+    if (ndev <= 0) {
+        sepgpu_set_error("sepgpu_create: no CUDA device available (seplib-b200 has no CPU path)");
+        return SEPGPU_ENODEV;
+    }
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % ndev : 0;
+    }
+    if (device >= ndev) { sepgpu_set_error("sepgpu_create: device %d of %d", device, ndev); return SEPGPU_EINVAL; }
+    CUDA_TRY(cudaSetDevice(device));
+
+    sepgpu_ctx *c = (sepgpu_ctx *)calloc(1, sizeof(sepgpu_ctx));
+    if (!c) return SEPGPU_EINVAL;
+    c->n = (int)npart;
+    c->npad = (c->n + 31) & ~31;
+    c->device = device;
+    c->pending_alpha_slot = -1;
+    c->pending_alpha_type = -1;
+    c->tpa = 4;
+    c->prefilter = 1;
+    c->single_type = 'A';
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+    const size_t n = npart;
+    if (dalloc(&c->x4, n) || dalloc(&c->v4, n) || dalloc(&c->f4, n) || dalloc(&c->xn4, n) ||
+        dalloc(&c->cr4, n) || dalloc(&c->crossings, 3 * n) || dalloc(&c->z, n) ||
+        dalloc(&c->xs, n) || dalloc(&c->xf, n) || dalloc(&c->order, n) || dalloc(&c->rank, n) ||
+        dalloc(&c->cell_of, n) || dalloc(&c->tmp_slot, n) || dalloc(&c->cnt, (size_t)c->npad) ||
+        dalloc(&c->scal, 1) || dalloc(&c->partial, (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * 16))
+        return SEPGPU_ECUDA;
+    CUDA_TRY(cudaMallocHost((void **)&c->scal_host, sizeof(DevScalars)));
+    memset(c->scal_host, 0, sizeof(DevScalars));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+
+    k_init_tags<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->x4, c->v4, c->n);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->f_zero = true;
+    *out = c;
+    return 0;
+}
+
+static void ktimer_free(KernelTimer *t)
+{
+    if (!t->enabled) return;
+    for (int i = 0; i < 64; i++) { cudaEventDestroy(t->start[i]); cudaEventDestroy(t->stop[i]); }
+}
+
+extern "C" void sepgpu_destroy(sepgpu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
+                    c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
+                    c->rank, c->cell_of, c->cell_cnt, c->cell_start, c->tmp_slot, c->nbr, c->cnt,
+                    c->blist, c->alist, c->dlist, c->atom_bond_ptr, c->atom_bond_idx,
+                    c->atom_angle_ptr, c->atom_angle_idx, c->atom_dihed_ptr, c->atom_dihed_idx,
+                    c->blengths, c->angles, c->dihedrals, c->scal, c->partial, c->dstage, c->flush_buf};
+    for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
+        if (ptrs[i]) cudaFree(ptrs[i]);
+    if (c->scal_host) cudaFreeHost(c->scal_host);
+    if (c->stage) cudaFreeHost(c->stage);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    ktimer_free(&c->t_force); ktimer_free(&c->t_build); ktimer_free(&c->t_intgr);
+    cudaStreamDestroy(c->stream);
+    free(c);
+}
+
+int sepgpu_ensure_stage(sepgpu_ctx *c, size_t bytes)
+{
+    if (c->stage_bytes < bytes) {
+        if (c->stage) cudaFreeHost(c->stage);
+        c->stage = NULL; c->stage_bytes = 0;
+        CUDA_TRY(cudaMallocHost(&c->stage, bytes));
+        c->stage_bytes = bytes;
+    }
+    if (c->dstage_bytes < bytes) {
+        if (c->dstage) cudaFree(c->dstage);
+        c->dstage = NULL; c->dstage_bytes = 0;
+        CUDA_TRY(cudaMalloc(&c->dstage, bytes));
+        c->dstage_bytes = bytes;
+    }
+    return 0;
+}
+
+// ---- packing kernels ----------------------------------------------------------------------------------
+__global__ void k_vec3_to_d4(d4 *dst, const double *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 v = dst[i];
+    v.x = src[3 * i]; v.y = src[3 * i + 1]; v.z = src[3 * i + 2];
+    dst[i] = v;
+}
+__global__ void k_d4_to_vec3(double *dst, const d4 *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 v = src[i];
+    dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
+}
+__global__ void k_scalar_to_w(d4 *dst, const double *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i].w = src[i];
+}
+__global__ void k_w_to_scalar(double *dst, const d4 *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i].w;
+}
+__global__ void k_set_type(d4 *x4, const char *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x4[i].w = make_tag((unsigned char)src[i], tag_mol(x4[i].w));
+}
+__global__ void k_get_type(char *dst, const d4 *x4, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (char)tag_type(x4[i].w);
+}
+__global__ void k_set_mol(d4 *x4, const int *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x4[i].w = make_tag(tag_type(x4[i].w), src[i]);
+}
+__global__ void k_get_mol(int *dst, const d4 *x4, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = tag_mol(x4[i].w);
+}
+__global__ void k_int3_to_cr(i4 *dst, const int *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i4 v = dst[i];
+    v.x = src[3 * i]; v.y = src[3 * i + 1]; v.z = src[3 * i + 2];
+    dst[i] = v;
+}
+__global__ void k_cr_to_int3(int *dst, const i4 *src, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    i4 v = src[i];
+    dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
+}
+__global__ void k_accel(double *dst, const d4 *f4, const d4 *v4, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 f = f4[i]; double m = v4[i].w;
+    dst[3 * i] = f.x / m; dst[3 * i + 1] = f.y / m; dst[3 * i + 2] = f.z / m;   // source/sepintgr.c:53
+}
+
+struct FieldInfo { size_t elem; int width; };   // host element size in bytes, and how many per atom
+
+static FieldInfo field_info(int field)
+{
+    switch (field) {
+    case SEPGPU_F_X: case SEPGPU_F_V: case SEPGPU_F_F: case SEPGPU_F_XN:
+    case SEPGPU_F_PV: case SEPGPU_F_PA: case SEPGPU_F_A: return {sizeof(double), 3};
+    case SEPGPU_F_M: case SEPGPU_F_Z: return {sizeof(double), 1};
+    case SEPGPU_F_TYPE: return {1, 1};
+    case SEPGPU_F_MOLINDEX: return {sizeof(int), 1};
+    case SEPGPU_F_CROSS_NEIGHB: case SEPGPU_F_CROSSINGS: return {sizeof(int), 3};
+    case SEPGPU_F_BOND: case SEPGPU_F_ANGLE: return {sizeof(int), 10};
+    case SEPGPU_F_DIHED: return {sizeof(int), 20};
+    default: return {0, 0};
+    }
+}
+
+static int ensure_dpd(sepgpu_ctx *c)
+{
+    if (c->have_dpd) return 0;
+    if (dalloc(&c->pv4, (size_t)c->n) || dalloc(&c->pa4, (size_t)c->n)) return SEPGPU_ECUDA;
+    c->have_dpd = true;
+    return 0;
+}
+int sepgpu_ensure_dpd(sepgpu_ctx *c) { return ensure_dpd(c); }
+
+extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t stride)
+{
+    if (!c || !host) return SEPGPU_EINVAL;
+    FieldInfo fi = field_info(field);
+    if (!fi.elem || field == SEPGPU_F_A) { sepgpu_set_error("sepgpu_put: bad field %d", field); return SEPGPU_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t row = fi.elem * fi.width, n = (size_t)c->n;
+    if (stride == 0) stride = row;
+    int rc = sepgpu_ensure_stage(c, row * n);
+    if (rc) return rc;
+    // the previous async copy out of the staging buffer must be done before we overwrite it
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const char *src = (const char *)host;
+    char *dst = (char *)c->stage;
+    if (stride == row) memcpy(dst, src, row * n);
+    else for (size_t i = 0; i < n; i++) memcpy(dst + i * row, src + i * stride, row);
+    CUDA_TRY(cudaMemcpyAsync(c->dstage, c->stage, row * n, cudaMemcpyHostToDevice, c->stream));
+    const int B = 256, G = (c->n + B - 1) / B;
+    switch (field) {
+    case SEPGPU_F_X:
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->x4, (const double *)c->dstage, c->n);
+        c->xs_current = false; c->list_valid = false;
+        break;
+    case SEPGPU_F_V:
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n);
+        c->mv2_valid = false;
+        break;
+    case SEPGPU_F_F:
+        if ((rc = sepgpu_apply_pending(c))) return rc;
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->f4, (const double *)c->dstage, c->n);
+        c->f_zero = false;
+        break;
+    case SEPGPU_F_XN:
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->xn4, (const double *)c->dstage, c->n);
+        break;
+    case SEPGPU_F_PV:
+        if ((rc = ensure_dpd(c))) return rc;
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pv4, (const double *)c->dstage, c->n);
+        break;
+    case SEPGPU_F_PA:
+        if ((rc = ensure_dpd(c))) return rc;
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pa4, (const double *)c->dstage, c->n);
+        break;
+    case SEPGPU_F_M:
+        k_scalar_to_w<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n);
+        c->mv2_valid = false;
+        break;
+    case SEPGPU_F_Z: {
+        CUDA_TRY(cudaMemcpyAsync(c->z, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        const double *hz = (const double *)c->stage;
+        bool any = false;
+        for (size_t i = 0; i < n && !any; i++) any = hz[i] != 0.0;
+        c->have_charge = any;
+        c->zs_valid = false;
+        break;
+    }
+    case SEPGPU_F_TYPE: {
+        k_set_type<<<G, B, 0, c->stream>>>(c->x4, (const char *)c->dstage, c->n);
+        const unsigned char *ht = (const unsigned char *)c->stage;
+        int st = ht[0];
+        for (size_t i = 1; i < n && st >= 0; i++) if (ht[i] != ht[0]) st = -1;
+        c->single_type = st;
+        c->xs_current = false; c->list_valid = false;
+        break;
+    }
+    case SEPGPU_F_MOLINDEX:
+        k_set_mol<<<G, B, 0, c->stream>>>(c->x4, (const int *)c->dstage, c->n);
+        c->xs_current = false; c->list_valid = false;
+        break;
+    case SEPGPU_F_CROSS_NEIGHB:
+        k_int3_to_cr<<<G, B, 0, c->stream>>>(c->cr4, (const int *)c->dstage, c->n);
+        break;
+    case SEPGPU_F_CROSSINGS:
+        CUDA_TRY(cudaMemcpyAsync(c->crossings, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        break;
+    case SEPGPU_F_BOND: case SEPGPU_F_ANGLE: case SEPGPU_F_DIHED: {
+        int **tab = field == SEPGPU_F_BOND ? &c->excl_bond : field == SEPGPU_F_ANGLE ? &c->excl_angle : &c->excl_dihed;
+        if (!*tab && dalloc(tab, (size_t)fi.width * n)) return SEPGPU_ECUDA;
+        CUDA_TRY(cudaMemcpyAsync(*tab, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        c->have_excl = c->excl_bond && c->excl_angle && c->excl_dihed;
+        c->list_valid = false;
+        break;
+    }
+    }
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int sepgpu_get(sepgpu_ctx *c, int field, void *host, size_t stride)
+{
+    if (!c || !host) return SEPGPU_EINVAL;
+    FieldInfo fi = field_info(field);
+    if (!fi.elem) { sepgpu_set_error("sepgpu_get: bad field %d", field); return SEPGPU_EINVAL; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t row = fi.elem * fi.width, n = (size_t)c->n;
+    if (stride == 0) stride = row;
+    int rc = sepgpu_ensure_stage(c, row * n);
+    if (rc) return rc;
+    const int B = 256, G = (c->n + B - 1) / B;
+    const void *dsrc = c->dstage;
+    switch (field) {
+    case SEPGPU_F_X: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->x4, c->n); break;
+    case SEPGPU_F_V: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n); break;
+    case SEPGPU_F_F:
+        if ((rc = sepgpu_apply_pending(c))) return rc;
+        if (c->f_zero) CUDA_TRY(cudaMemsetAsync(c->dstage, 0, row * n, c->stream));
+        else k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->n);
+        break;
+    case SEPGPU_F_A:
+        if ((rc = sepgpu_apply_pending(c))) return rc;
+        if (c->f_zero) CUDA_TRY(cudaMemsetAsync(c->dstage, 0, row * n, c->stream));
+        else k_accel<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->v4, c->n);
+        break;
+    case SEPGPU_F_XN: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->xn4, c->n); break;
+    case SEPGPU_F_PV: case SEPGPU_F_PA:
+        if (!c->have_dpd) { sepgpu_set_error("sepgpu_get: no DPD state"); return SEPGPU_ESTATE; }
+        k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, field == SEPGPU_F_PV ? c->pv4 : c->pa4, c->n);
+        break;
+    case SEPGPU_F_M: k_w_to_scalar<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n); break;
+    case SEPGPU_F_Z: dsrc = c->z; break;
+    case SEPGPU_F_TYPE: k_get_type<<<G, B, 0, c->stream>>>((char *)c->dstage, c->x4, c->n); break;
+    case SEPGPU_F_MOLINDEX: k_get_mol<<<G, B, 0, c->stream>>>((int *)c->dstage, c->x4, c->n); break;
+    case SEPGPU_F_CROSS_NEIGHB: k_cr_to_int3<<<G, B, 0, c->stream>>>((int *)c->dstage, c->cr4, c->n); break;
+    case SEPGPU_F_CROSSINGS: dsrc = c->crossings; break;
+    case SEPGPU_F_BOND: dsrc = c->excl_bond; break;
+    case SEPGPU_F_ANGLE: dsrc = c->excl_angle; break;
+    case SEPGPU_F_DIHED: dsrc = c->excl_dihed; break;
+    }
+    KERNEL_CHECK();
+    if (!dsrc) { sepgpu_set_error("sepgpu_get: field %d not present on device", field); return SEPGPU_ESTATE; }
+    CUDA_TRY(cudaMemcpyAsync(c->stage, dsrc, row * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    char *dst = (char *)host;
+    const char *src = (const char *)c->stage;
+    if (stride == row) memcpy(dst, src, row * n);
+    else for (size_t i = 0; i < n; i++) memcpy(dst + i * stride, src + i * row, row);
+    return 0;
+}
+
+// ---- scalars ----------------------------------------------------------------------------------------------
+__global__ void k_reset_ret(DevScalars *s)
+{
+    // sep_reset_retval (source/sepret.c:19-47)
+    int t = threadIdx.x;
+    if (t == 0) { s->epot = 0; s->ecoul = 0; s->ekin = 0; }
+    if (t < 9) { s->pot_P[t] = 0; s->kin_P[t] = 0; s->pot_P_bond[t] = 0; }
+}
+
+extern "C" int sepgpu_reset_ret(sepgpu_ctx *c)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    k_reset_ret<<<1, 32, 0, c->stream>>>(c->scal);
+    KERNEL_CHECK();
+    return 0;
+}
+
+__global__ void k_reset_maxdist(DevScalars *s) { s->max_dist2 = 0.0; }
+
+extern "C" int sepgpu_reset_force(sepgpu_ctx *c)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    // f <- 0 is not written out: the first force kernel after this call stores instead of adding.
+    c->f_zero = true;
+    c->pending_alpha_slot = -1;       // a pending f -= alpha m v dies with the force it would modify
+    k_reset_maxdist<<<1, 1, 0, c->stream>>>(c->scal);     // source/sepmisc.c:399
+    KERNEL_CHECK();
+    return 0;
+}
+
+extern "C" int sepgpu_read_scalars(sepgpu_ctx *c, sepgpu_scalars *out)
+{
+    if (!c || !out) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const DevScalars *s = c->scal_host;
+    out->epot = s->epot; out->ecoul = s->ecoul; out->ekin = s->ekin;
+    memcpy(out->pot_P, s->pot_P, sizeof out->pot_P);
+    memcpy(out->kin_P, s->kin_P, sizeof out->kin_P);
+    memcpy(out->pot_P_bond, s->pot_P_bond, sizeof out->pot_P_bond);
+    out->max_dist2 = s->max_dist2;
+    out->sum_mv2 = s->sum_mv2;
+    memcpy(out->alpha, s->alpha, sizeof out->alpha);
+    out->neighb_flag = s->neighb_flag;
+    out->nbuild = s->nbuild;
+    out->error = s->error;
+    out->max_neighb = s->max_neighb;
+    out->npairs_listed = s->npairs_listed;
+    return 0;
+}
+
+extern "C" int sepgpu_sync(sepgpu_ctx *c)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+__global__ void k_set_alpha(DevScalars *s, int slot, double a) { s->alpha[slot] = a; }
+
+extern "C" int sepgpu_set_alpha(sepgpu_ctx *c, int slot, double alpha)
+{
+    if (!c || slot < 0 || slot > 3) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    k_set_alpha<<<1, 1, 0, c->stream>>>(c->scal, slot, alpha);
+    KERNEL_CHECK();
+    return 0;
+}
+
+__global__ void k_set_flag(DevScalars *s) { s->neighb_flag = 1; }
+
+extern "C" int sepgpu_request_rebuild(sepgpu_ctx *c)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->list_valid = false;
+    k_set_flag<<<1, 1, 0, c->stream>>>(c->scal);
+    KERNEL_CHECK();
+    return 0;
+}
+
+static int ktimer_enable(KernelTimer *t)
+{
+    if (t->enabled) return 0;
+    for (int i = 0; i < 64; i++) {
+        CUDA_TRY(cudaEventCreate(&t->start[i]));
+        CUDA_TRY(cudaEventCreate(&t->stop[i]));
+    }
+    t->enabled = true; t->used = 0; t->total_ms = 0; t->launches = 0;
+    return 0;
+}
+
+static void ktimer_drain(KernelTimer *t)
+{
+    for (int i = 0; i < t->used; i++) {
+        float ms = 0;
+        cudaEventSynchronize(t->stop[i]);
+        cudaEventElapsedTime(&ms, t->start[i], t->stop[i]);
+        t->total_ms += ms; t->launches++;
+    }
+    t->used = 0;
+}
+
+void ktimer_begin(sepgpu_ctx *c, KernelTimer *t)
+{
+    if (!t->enabled) return;
+    if (t->used == 64) ktimer_drain(t);
+    cudaEventRecord(t->start[t->used], c->stream);
+}
+void ktimer_end(sepgpu_ctx *c, KernelTimer *t)
+{
+    if (!t->enabled) return;
+    cudaEventRecord(t->stop[t->used], c->stream);
+    t->used++;
+}
+
+extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long value)
+{
+    if (!c || !name) return SEPGPU_EINVAL;
+    if (!strcmp(name, "tpa")) {
+        if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32 && value != 0)
+            return SEPGPU_EINVAL;
+        c->tpa = value ? (int)value : 4;
+        return 0;
+    }
+    if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
+    if (!strcmp(name, "time_kernels")) {
+        if (value) { if (ktimer_enable(&c->t_force) || ktimer_enable(&c->t_build) || ktimer_enable(&c->t_intgr)) return SEPGPU_ECUDA; }
+        return 0;
+    }
+    if (!strcmp(name, "neighb_cap")) {
+        if (value < 8) return SEPGPU_EINVAL;
+        if (c->nbr) { cudaFree(c->nbr); c->nbr = NULL; }
+        c->cap = (int)value; c->list_valid = false;
+        return 0;
+    }
+    sepgpu_set_error("sepgpu_set_option: unknown option '%s'", name);
+    return SEPGPU_EINVAL;
+}
+
+extern "C" int sepgpu_kernel_time(sepgpu_ctx *c, const char *which, float *ms_total, int *launches)
+{
+    if (!c || !which) return SEPGPU_EINVAL;
+    KernelTimer *t = !strcmp(which, "force") ? &c->t_force : !strcmp(which, "build") ? &c->t_build
+                   : !strcmp(which, "intgr") ? &c->t_intgr : NULL;
+    if (!t || !t->enabled) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    ktimer_drain(t);
+    if (ms_total) *ms_total = t->total_ms;
+    if (launches) *launches = t->launches;
+    t->total_ms = 0; t->launches = 0;
+    return 0;
+}
+
+extern "C" int sepgpu_timer_start(sepgpu_ctx *c)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+
+extern "C" int sepgpu_timer_stop(sepgpu_ctx *c, float *ms)
+{
+    if (!c || !ms) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+__global__ void k_flush(double *p, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = (double)i;
+}
+
+extern "C" int sepgpu_flush_l2(sepgpu_ctx *c)
+{
+    if (!c) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->flush_buf) {
+        c->flush_bytes = (size_t)256 << 20;           // 256 MiB > 126 MB L2
+        CUDA_TRY(cudaMalloc(&c->flush_buf, c->flush_bytes));
+    }
+    k_flush<<<148 * 8, 256, 0, c->stream>>>((double *)c->flush_buf, c->flush_bytes / sizeof(double));
+    KERNEL_CHECK();
+    return 0;
+}
+
+// ---- box ceilings -------------------------------------------------------------------------------------------
+// 8 independent DFMA chains per thread; 2 flop per DFMA.
+__global__ void __launch_bounds__(256) k_fma64(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, cc = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+        a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int sepgpu_peak_fp64(int device, double *tflops)
+{
+    if (!tflops) return SEPGPU_EINVAL;
+    if (sepgpu_device_count() <= 0) { sepgpu_set_error("no CUDA device"); return SEPGPU_ENODEV; }
+    CUDA_TRY(cudaSetDevice(device < 0 ? 0 : device));
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+    double *out;
+    CUDA_TRY(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_fma64<<<blocks, threads>>>(out, iters);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms; CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops = best;
+    return 0;
+}
+
+__global__ void k_copy(const double4 *__restrict__ a, double4 *__restrict__ b, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) b[i] = a[i];
+}
+
+extern "C" int sepgpu_peak_copy(int device, double *gbs)
+{
+    if (!gbs) return SEPGPU_EINVAL;
+    if (sepgpu_device_count() <= 0) { sepgpu_set_error("no CUDA device"); return SEPGPU_ENODEV; }
+    CUDA_TRY(cudaSetDevice(device < 0 ? 0 : device));
+    const size_t bytes = (size_t)1 << 30, n = bytes / sizeof(double4);
+    double4 *a, *b;
+    CUDA_TRY(cudaMalloc(&a, bytes)); CUDA_TRY(cudaMalloc(&b, bytes));
+    CUDA_TRY(cudaMemset(a, 1, bytes));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_copy<<<148 * 16, 512>>>(a, b, n);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms; CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double g = 2.0 * bytes / (ms * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(a); cudaFree(b);
+    *gbs = best;
+    return 0;
+}

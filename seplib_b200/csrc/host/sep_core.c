@@ -1,0 +1,731 @@
+/* sep_core.c -- host side of the seplib API: allocation, system setup, host<->device binding,
+ * coherence, error reporting and the small scalar routines (pressure tensor, momentum, ...).
+ *
+ * The functions here mirror the behaviour of the reference's source/sepinit.c, source/sepret.c and
+ * the parts of source/sepmisc.c that the example programs use; each cites its counterpart.  They
+ * never compute forces or integrate: that is the device layer's job (include/sepgpu.h).
+ */
+#include "sep_host.h"
+
+#include <ctype.h>
+
+/* ---------------------------------------------------------------------------------------------------
+ * error reporting (source/sepmisc.c:16-113): mini-printf to stdout, then exit for errors
+ * ------------------------------------------------------------------------------------------------- */
+static void emit(const char *prefix, const char *fmt, va_list ap)
+{
+    fputs(prefix, stdout);
+    for (const char *p = fmt; *p; p++) {
+        if (*p != '%') { putchar(*p); continue; }
+        p++;
+        if (*p == 'd' || *p == 'i') printf("%d", va_arg(ap, int));
+        else if (*p == 'f') printf("%f", va_arg(ap, double));
+        else if (*p == 'c') printf("%c", va_arg(ap, int));
+        else if (*p == 's') { const char *s = va_arg(ap, char *); fputs(s ? s : "(null)", stdout); }
+        else if (*p == '\0') break;
+        else putchar(*p);
+    }
+    putchar('\n');
+}
+
+void sep_error(char *str, ...)
+{
+    va_list ap;
+    va_start(ap, str);
+    emit("sep-error -> ", str, ap);
+    va_end(ap);
+    printf("BAILING OUT\n");
+    fflush(stdout);
+    exit(EXIT_FAILURE);
+}
+
+void sep_warning(char *str, ...)
+{
+    va_list ap;
+    va_start(ap, str);
+    emit("sep-warning -> ", str, ap);
+    va_end(ap);
+    fflush(stdout);
+}
+
+void sepb_check(int rc, const char *where)
+{
+    if (rc == 0) return;
+    if (rc == SEPGPU_ENEIGHB) sep_error("%s: Too many neighbours", (char *)where);
+    if (rc == SEPGPU_ECELL) sep_error("%s: Index larger than array length", (char *)where);
+    if (rc == SEPGPU_ENODEV)
+        sep_error("%s: no CUDA device -- seplib-b200 has no CPU path (%s)", (char *)where, (char *)sepgpu_last_error());
+    sep_error("%s: device layer failed (%d): %s", (char *)where, rc, (char *)sepgpu_last_error());
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * registry of atom arrays
+ * ------------------------------------------------------------------------------------------------- */
+static sep_binding *g_bindings = NULL;
+static int g_sync_mode = -1;
+static unsigned long long g_dpd_seed = 0x5EB11B200ULL;
+
+int sep_sync_mode(void)
+{
+    if (g_sync_mode < 0) {
+        const char *e = getenv("SEP_SYNC");
+        g_sync_mode = SEP_SYNC_STEP;
+        if (e) {
+            if (!strcmp(e, "lazy")) g_sync_mode = SEP_SYNC_LAZY;
+            else if (!strcmp(e, "full")) g_sync_mode = SEP_SYNC_FULL;
+            else if (!strcmp(e, "step")) g_sync_mode = SEP_SYNC_STEP;
+            else sep_warning("SEP_SYNC=%s not understood (lazy|step|full); using step", (char *)e);
+        }
+    }
+    return g_sync_mode;
+}
+
+void sep_gpu_set_sync(int mode)
+{
+    if (mode == SEP_SYNC_LAZY || mode == SEP_SYNC_STEP || mode == SEP_SYNC_FULL) g_sync_mode = mode;
+}
+
+void sep_gpu_set_dpd_seed(unsigned long long seed) { g_dpd_seed = seed; }
+unsigned long long sep_dpd_seed(void) { return g_dpd_seed; }
+
+sep_binding *sepb_find(const seppart *atoms)
+{
+    for (sep_binding *b = g_bindings; b; b = b->next)
+        if (b->atoms == atoms) return b;
+    return NULL;
+}
+
+sep_binding *sepb_find_mol(const sepmolinfo *molptr)
+{
+    if (!molptr) return NULL;
+    for (sep_binding *b = g_bindings; b; b = b->next)
+        if (b->molptr == molptr) return b;
+    return NULL;
+}
+
+sep_binding *sepb_first(void) { return g_bindings; }
+
+sep_binding *sepb_register(seppart *atoms, size_t npart)
+{
+    sep_binding *b = calloc(1, sizeof *b);
+    if (!b) sep_error("%s at line %d: Couldn't allocate memory", (char *)__func__, __LINE__);
+    b->atoms = atoms;
+    b->npart = npart;
+    b->host_dirty = ~0u;
+    b->next = g_bindings;
+    g_bindings = b;
+    return b;
+}
+
+void sepb_unregister(seppart *atoms)
+{
+    sep_binding **pp = &g_bindings;
+    while (*pp) {
+        if ((*pp)->atoms == atoms) {
+            sep_binding *b = *pp;
+            *pp = b->next;
+            if (b->gpu) sepgpu_destroy(b->gpu);
+            free(b->blengths_host); free(b->angles_host); free(b->dihedrals_host);
+            free(b);
+            return;
+        }
+        pp = &(*pp)->next;
+    }
+}
+
+void sepb_mark_host_dirty(seppart *atoms, unsigned fields)
+{
+    sep_binding *b = sepb_find(atoms);
+    if (b) { b->host_dirty |= fields; b->dev_dirty &= ~fields; }
+}
+
+void sepb_fill_sys(const sepsys *sys, sepgpu_sys *out)
+{
+    for (int k = 0; k < 3; k++) {
+        out->length[k] = sys->length[k];
+        out->lsubbox[k] = sys->lsubbox[k];
+        out->nsubbox[k] = sys->nsubbox[k];
+    }
+    out->cf = sys->cf;
+    out->skin = sys->skin;
+    out->dt = sys->dt;
+    out->neighb_update = (int)sys->neighb_update;
+}
+
+#define FIELD_PTR(b, member) ((void *)&(b)->atoms[0].member)
+
+static void upload(sep_binding *b, unsigned bit, int field, void *base)
+{
+    if (!(b->host_dirty & bit)) return;
+    sepb_check(sepgpu_put(b->gpu, field, base, sizeof(seppart)), "upload");
+    b->host_dirty &= ~bit;
+    b->dev_dirty &= ~bit;
+}
+
+sep_binding *sepb_prepare(seppart *atoms, sepsys *sys)
+{
+    sep_binding *b = sepb_find(atoms);
+    if (!b) b = sepb_register(atoms, (size_t)sys->npart);    /* array not from sep_init (e.g. user malloc) */
+    if ((long)b->npart != sys->npart) {
+        if (b->gpu) sep_error("%s: sys.npart changed under a live device context", (char *)__func__);
+        b->npart = (size_t)sys->npart;
+    }
+    if (!b->gpu) {
+        sepb_check(sepgpu_create(&b->gpu, b->npart, -1), "sepgpu_create");
+        b->host_dirty = ~0u;
+        b->dev_dirty = 0;
+    }
+    if (sys->molptr) b->molptr = sys->molptr;
+    if (!b->host_dirty) return b;
+
+    upload(b, SEPB_X, SEPGPU_F_X, FIELD_PTR(b, x));
+    upload(b, SEPB_V, SEPGPU_F_V, FIELD_PTR(b, v));
+    upload(b, SEPB_M, SEPGPU_F_M, FIELD_PTR(b, m));
+    upload(b, SEPB_Z, SEPGPU_F_Z, FIELD_PTR(b, z));
+    upload(b, SEPB_TYPE, SEPGPU_F_TYPE, FIELD_PTR(b, type));
+    upload(b, SEPB_MOL, SEPGPU_F_MOLINDEX, FIELD_PTR(b, molindex));
+    upload(b, SEPB_XN, SEPGPU_F_XN, FIELD_PTR(b, xn));
+    upload(b, SEPB_CN, SEPGPU_F_CROSS_NEIGHB, FIELD_PTR(b, cross_neighb));
+    upload(b, SEPB_CR, SEPGPU_F_CROSSINGS, FIELD_PTR(b, crossings));
+    if (b->uploaded_once) upload(b, SEPB_F, SEPGPU_F_F, FIELD_PTR(b, f));
+    if (b->dpd_state_on_device) {
+        upload(b, SEPB_PV, SEPGPU_F_PV, FIELD_PTR(b, pv));
+        upload(b, SEPB_PA, SEPGPU_F_PA, FIELD_PTR(b, pa));
+    }
+    if ((b->host_dirty & SEPB_EXCL) && sys->molptr &&
+        (sys->molptr->flag_bonds || sys->molptr->flag_angles || sys->molptr->flag_dihedrals)) {
+        sepb_check(sepgpu_put(b->gpu, SEPGPU_F_BOND, FIELD_PTR(b, bond), sizeof(seppart)), "upload bond table");
+        sepb_check(sepgpu_put(b->gpu, SEPGPU_F_ANGLE, FIELD_PTR(b, angle), sizeof(seppart)), "upload angle table");
+        sepb_check(sepgpu_put(b->gpu, SEPGPU_F_DIHED, FIELD_PTR(b, dihed), sizeof(seppart)), "upload dihed table");
+    }
+    if ((b->host_dirty & SEPB_TOPO) && sys->molptr && sys->molptr->flag_bonds) {
+        const sepmolinfo *mp = sys->molptr;
+        sepb_check(sepgpu_set_topology(b->gpu, mp->blist, mp->num_bonds,
+                                       mp->flag_angles ? mp->alist : NULL, mp->flag_angles ? mp->num_angles : 0,
+                                       mp->flag_dihedrals ? mp->dlist : NULL, mp->flag_dihedrals ? mp->num_dihedrals : 0),
+                   "upload topology");
+    }
+    b->host_dirty = 0;
+    b->uploaded_once = 1;
+    return b;
+}
+
+void sepb_download(sep_binding *b, unsigned fields)
+{
+    if (!b || !b->gpu) return;
+    fields &= b->dev_dirty;
+    if (!fields) return;
+#define PULL(bit, fid, member)                                                                  \
+    if (fields & (bit)) sepb_check(sepgpu_get(b->gpu, fid, FIELD_PTR(b, member), sizeof(seppart)), "download")
+    PULL(SEPB_X, SEPGPU_F_X, x);
+    PULL(SEPB_V, SEPGPU_F_V, v);
+    PULL(SEPB_F, SEPGPU_F_F, f);
+    PULL(SEPB_A, SEPGPU_F_A, a);
+    PULL(SEPB_XN, SEPGPU_F_XN, xn);
+    PULL(SEPB_CN, SEPGPU_F_CROSS_NEIGHB, cross_neighb);
+    PULL(SEPB_CR, SEPGPU_F_CROSSINGS, crossings);
+    PULL(SEPB_PV, SEPGPU_F_PV, pv);
+    PULL(SEPB_PA, SEPGPU_F_PA, pa);
+#undef PULL
+    b->dev_dirty &= ~fields;
+}
+
+void sepb_pull_scalars(sep_binding *b, sepsys *sys, sepret *ret, sepgpu_scalars *out)
+{
+    sepgpu_scalars s;
+    sepb_check(sepgpu_read_scalars(b->gpu, &s), "read scalars");
+    if (ret) {
+        ret->epot = s.epot; ret->ecoul = s.ecoul; ret->ekin = s.ekin;
+        for (int k = 0; k < 3; k++)
+            for (int kk = 0; kk < 3; kk++) {
+                ret->pot_P[k][kk] = s.pot_P[3 * k + kk];
+                ret->kin_P[k][kk] = s.kin_P[3 * k + kk];
+                ret->pot_P_bond[k][kk] = s.pot_P_bond[3 * k + kk];
+            }
+    }
+    if (sys) sys->max_dist2 = s.max_dist2;
+    for (int k = 0; k < 4; k++)
+        if (b->alpha_ptr[k]) { *b->alpha_ptr[k] = s.alpha[k]; b->alpha_seen[k] = s.alpha[k]; }
+    if (out) *out = s;
+}
+
+void sepb_after_force(sep_binding *b, sepsys *sys, sepret *ret)
+{
+    b->dev_dirty |= SEPB_F | SEPB_A;
+    b->last_ret = ret;
+    const int mode = sep_sync_mode();
+    if (mode != SEP_SYNC_LAZY) sepb_pull_scalars(b, sys, ret, NULL);
+    if (mode == SEP_SYNC_FULL) sepb_download(b, SEPB_F);
+}
+
+void sep_gpu_sync(seppart *ptr)
+{
+    sep_binding *b = sepb_find(ptr);
+    if (b && b->gpu) sepb_download(b, ~0u);
+}
+
+void sep_gpu_invalidate(seppart *ptr)
+{
+    sep_binding *b = sepb_find(ptr);
+    if (!b) return;
+    b->host_dirty |= SEPB_ALL_STATE | SEPB_EXCL;
+    if (b->dpd_state_on_device) b->host_dirty |= SEPB_PV | SEPB_PA;
+    b->dev_dirty = 0;
+}
+
+void sep_gpu_sync_scalars(seppart *ptr, sepsys *sys, sepret *ret)
+{
+    sep_binding *b = sepb_find(ptr);
+    if (b && b->gpu) sepb_pull_scalars(b, sys, ret, NULL);
+}
+
+void *sep_gpu_handle(seppart *ptr)
+{
+    sep_binding *b = sepb_find(ptr);
+    return b ? (void *)b->gpu : NULL;
+}
+
+long sep_gpu_export_neighb(seppart *ptr, sepsys *sys, int *pairs, long max_pairs)
+{
+    (void)sys;
+    sep_binding *b = sepb_find(ptr);
+    if (!b || !b->gpu) return -1;
+    return (long)sepgpu_get_pairs(b->gpu, pairs, max_pairs);
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * allocation (source/sepinit.c:15-66)
+ * ------------------------------------------------------------------------------------------------- */
+seppart *sep_init(size_t npart, size_t nneighb)
+{
+    /* zero-filled so that xn starts at 0 (the reference leaves it uninitialised; fresh heap pages
+     * make it 0 in practice and the first leapfrog then requests a rebuild) */
+    seppart *p = calloc(npart ? npart : 1, sizeof(seppart));
+    if (!p) sep_error("%s at line %d: Couldn't allocate memory\n", (char *)__func__, __LINE__);
+    /* The reference gives every atom an int[nneighb] row (12 kB/atom at SEP_NEIGHB).  The device owns
+     * the list here; rows are not materialised (1 M atoms would need 12 GB of host memory). */
+    (void)nneighb;
+    for (size_t n = 0; n < npart; n++) {
+        p[n].type = 'A';
+        p[n].m = 1.0;
+        p[n].molindex = -1;
+        p[n].ldiff = 1.0;
+        p[n].neighb = NULL;
+        for (int k = 0; k < SEP_BOND; k++) p[n].bond[k] = -1;
+        for (int k = 0; k < SEP_ANGLE; k++) p[n].angle[k] = -1;
+        for (int k = 0; k < SEP_DIHED; k++) p[n].dihed[k] = -1;
+    }
+    sepb_register(p, npart);
+    return p;
+}
+
+void sep_close(seppart *ptr, size_t npart)
+{
+    (void)npart;
+    sep_binding *b = sepb_find(ptr);
+    if (b && b->gpu) sepb_download(b, ~0u);     /* final state visible to anyone still holding a copy */
+    sepb_unregister(ptr);
+    free(ptr);
+}
+
+/* source/sepinit.c:69-109 */
+seppart *sep_init_xyz(double *lbox, int *npart, const char *file, char verbose)
+{
+    if (verbose == 'v') fprintf(stdout, "Opening %s\n", file);
+    FILE *fin = fopen(file, "r");
+    if (!fin) sep_error("%s at line %d: Couldn't open file\n", (char *)__func__, __LINE__);
+    if (fscanf(fin, "%d", npart) != 1)
+        sep_error("%s at line %d: Error reading xyz file\n", (char *)__func__, __LINE__);
+    seppart *p = sep_init((size_t)*npart, SEP_NUM_NEIGHB);
+    if (fscanf(fin, "%lf%lf%lf\n", &lbox[0], &lbox[1], &lbox[2]) != 3)
+        sep_error("%s at line %d: Error reading xyz file\n", (char *)__func__, __LINE__);
+    for (int n = 0; n < *npart; n++) {
+        seppart *a = &p[n];
+        if (fscanf(fin, "%c%lf%lf%lf%lf%lf%lf%lf%lf\n", &a->type, &a->x[0], &a->x[1], &a->x[2],
+                   &a->v[0], &a->v[1], &a->v[2], &a->m, &a->z) != 9)
+            sep_error("%s at line %d: Error reading xyz file\n", (char *)__func__, __LINE__);
+    }
+    if (verbose == 'v') {
+        fprintf(stdout, "Closing file\n");
+        fprintf(stdout, "Number of particles: %d\n", *npart);
+        SEP_FLUSH;
+    }
+    fclose(fin);
+    return p;
+}
+
+/* source/sepmisc.c:454-463 */
+int sep_nsubbox(double cf, double delta, double lbox)
+{
+    const double cut = cf + delta;
+    return (int)(lbox / cut);
+}
+
+double sep_box_length(double dens, int npart, int ndim)
+{
+    return pow((double)npart / dens, (double)1.0 / ndim);
+}
+
+/* source/sepinit.c:246-305 */
+sepsys sep_sys_setup(double lengthx, double lengthy, double lengthz,
+                     double cf, double dt, size_t npart, size_t update)
+{
+    sepsys sys;
+    memset(&sys, 0, sizeof sys);
+    const double skinparam = 0.25;
+    const double len[3] = {lengthx, lengthy, lengthz};
+    static const char *dirname[3] = {"x", "y", "z"};
+    sys.volume = lengthx * lengthy * lengthz;
+    for (int k = 0; k < 3; k++) {
+        sys.length[k] = len[k];
+        sys.nsubbox[k] = sep_nsubbox(cf, skinparam, len[k]);
+        if (update > 1 && sys.nsubbox[k] < 3) {
+            char msg[128];
+            snprintf(msg, sizeof msg, "sep_sys_setup: Number of subboxes in %s direction are less than three", dirname[k]);
+            sep_warning(msg);
+        }
+        sys.lsubbox[k] = len[k] / sys.nsubbox[k];
+    }
+    sys.npart = (long)npart;
+    sys.cf = cf;
+    sys.dt = dt;
+    sys.ndof = (unsigned)(3 * npart - 3);
+    sys.tnow = 0.0;
+    sys.nupdate_neighb = 0;
+    sys.neighb_update = (unsigned)update;
+    sys.neighb_flag = 1;
+    sys.skin = skinparam;
+    sys.molptr = calloc(1, sizeof(sepmolinfo));
+    if (!sys.molptr) sep_error("%s at line %d: Couldn't allocate memory", (char *)__func__, __LINE__);
+    sys.omp_flag = false;
+    sys.fun_cstate = 0;
+    return sys;
+}
+
+void sep_free_sys(sepsys *ptr)
+{
+    sep_free_bonds(ptr->molptr);
+    sep_free_angles(ptr->molptr);
+    sep_free_dihedrals(ptr->molptr);
+}
+
+/* source/sepinit.c:317-357 : simple cubic lattice starting at (1,1,1) */
+void sep_set_lattice(seppart *ptr, sepsys sys)
+{
+    int numb[3];
+    double gap[3];
+    const double dens = sys.npart / (sys.length[0] * sys.length[1] * sys.length[2]);
+    for (int k = 0; k < 3; k++) {
+        numb[k] = (int)ceil(pow(dens, 1. / 3.) * sys.length[k]);
+        gap[k] = sys.length[k] / numb[k];
+    }
+    long n = 0;
+    for (int iz = 0; iz < numb[2] && n < sys.npart; iz++)
+        for (int iy = 0; iy < numb[1] && n < sys.npart; iy++)
+            for (int ix = 0; ix < numb[0] && n < sys.npart; ix++) {
+                ptr[n].x[0] = ix * gap[0] + 1.0;
+                ptr[n].x[1] = iy * gap[1] + 1.0;
+                ptr[n].x[2] = iz * gap[2] + 1.0;
+                n++;
+            }
+    sepb_mark_host_dirty(ptr, SEPB_X);
+}
+
+/* shared body of sep_set_vel / sep_set_vel_seed / sep_set_vel_type (source/sepinit.c:114-243).
+ * The glibc rand() stream is consumed in the reference's order so seeded runs start identically. */
+static void draw_velocities(seppart *ptr, long npart, int use_type, char type, double temp)
+{
+    double smom[3] = {0.0, 0.0, 0.0}, sekin = 0.0;
+    long ntype = 0;
+    for (long n = 0; n < npart; n++) {
+        if (use_type && ptr[n].type != type) continue;
+        ntype++;
+        for (int k = 0; k < 3; k++) {
+            ptr[n].v[k] = sep_rand() - 0.5;
+            smom[k] += ptr[n].v[k] * ptr[n].m;
+            sekin += ptr[n].v[k] * ptr[n].v[k] * ptr[n].m;
+        }
+    }
+    const int cnt = (int)ntype, ndim = 3;
+    const double scale = sqrt(cnt * ndim * temp / sekin);
+    for (long n = 0; n < npart; n++) {
+        if (use_type && ptr[n].type != type) continue;
+        for (int k = 0; k < 3; k++)
+            ptr[n].v[k] = (ptr[n].v[k] - smom[k] / (ptr[n].m * cnt)) * scale;
+    }
+}
+
+void sep_set_vel(seppart *ptr, double temp, sepsys sys)
+{
+    srand((unsigned)time(NULL));
+    draw_velocities(ptr, sys.npart, 0, 0, temp);
+    for (long n = 0; n < sys.npart; n++)
+        for (int k = 0; k < 3; k++) {
+            ptr[n].px[k] = ptr[n].x[k] + (sep_rand() - 0.5) * 0.01;
+            ptr[n].pv[k] = ptr[n].v[k] + (sep_rand() - 0.5) * 0.01;
+        }
+    sepb_mark_host_dirty(ptr, SEPB_V | SEPB_PV);
+}
+
+void sep_set_vel_seed(seppart *ptr, double temp, unsigned int seed, sepsys sys)
+{
+    srand(seed);
+    draw_velocities(ptr, sys.npart, 0, 0, temp);
+    for (long n = 0; n < sys.npart; n++)
+        for (int k = 0; k < 3; k++) {
+            (void)sep_rand(); (void)sep_rand();          /* the reference draws and discards two numbers */
+            ptr[n].px[k] = ptr[n].x[k];
+            ptr[n].pv[k] = ptr[n].v[k];
+            ptr[n].pa[k] = 0.0;
+        }
+    sepb_mark_host_dirty(ptr, SEPB_V | SEPB_PV | SEPB_PA);
+}
+
+void sep_set_vel_type(seppart *ptr, char type, double temp, unsigned int seed, sepsys sys)
+{
+    if (sep_count_type(ptr, type, (int)sys.npart) == 0) return;
+    srand(seed);
+    draw_velocities(ptr, sys.npart, 1, type, temp);
+    for (long n = 0; n < sys.npart; n++) {
+        if (ptr[n].type != type) continue;
+        for (int k = 0; k < 3; k++) {
+            ptr[n].px[k] = ptr[n].x[k] + (sep_rand() - 0.5) * 0.01;
+            ptr[n].pv[k] = ptr[n].v[k] + (sep_rand() - 0.5) * 0.01;
+        }
+    }
+    sepb_mark_host_dirty(ptr, SEPB_V | SEPB_PV);
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * pair functions (source/sepmisc.c:115-164).  On the device these are recognised by address and
+ * mapped to the Lennard-Jones kernel; the host versions exist for user code that calls them.
+ * ------------------------------------------------------------------------------------------------- */
+static double lj_family(double r2, char opt, double ushift)
+{
+    const double rri = 1.0 / r2, rri3 = rri * rri * rri;
+    if (opt == 'f') return 48.0 * rri3 * (rri3 - 0.5) * rri;
+    if (opt == 'u') return 4.0 * rri3 * (rri3 - 1.0) + ushift;
+    return 0.0;
+}
+double sep_lj(double r2, char opt) { return lj_family(r2, opt, 0.0); }
+double sep_lj_shift(double r2, char opt) { return lj_family(r2, opt, SEP_LJCF2); }
+double sep_wca(double r2, char opt) { return lj_family(r2, opt, 1.0); }
+
+/* ---------------------------------------------------------------------------------------------------
+ * per-step resets (source/sepret.c:19-47, source/sepmisc.c:393-430)
+ * ------------------------------------------------------------------------------------------------- */
+void sep_reset_retval(sepret *r)
+{
+    r->epot = 0; r->ecoul = 0; r->ekin = 0; r->sumv2 = 0;
+    double (*tens[])[3] = {r->pot_P, r->kin_P, r->P, r->pot_P_conservative, r->pot_P_random,
+                           r->pot_P_dissipative, r->pot_P_bond, r->pot_P_mol, r->kin_P_mol, r->P_mol,
+                           r->pot_T_mol, r->kin_T_mol, r->T_mol};
+    for (size_t t = 0; t < sizeof tens / sizeof tens[0]; t++)
+        for (int k = 0; k < 3; k++)
+            for (int kk = 0; kk < 3; kk++) tens[t][k][kk] = 0.0;
+    /* the device accumulators follow: every live context whose results go to this struct (or whose
+     * target is not known yet) is reset in stream order */
+    for (sep_binding *b = sepb_first(); b; b = b->next)
+        if (b->gpu && (b->last_ret == r || b->last_ret == NULL))
+            sepb_check(sepgpu_reset_ret(b->gpu), "sep_reset_retval");
+}
+
+void sep_reset_force(seppart *ptr, sepsys *sys)
+{
+    sep_binding *b = sepb_prepare(ptr, sys);
+    sepb_check(sepgpu_reset_force(b->gpu), "sep_reset_force");
+    sys->max_dist2 = 0.0;
+    b->host_dirty &= ~SEPB_F;
+    if (sep_sync_mode() != SEP_SYNC_LAZY) {
+        for (long n = 0; n < sys->npart; n++) ptr[n].f[0] = ptr[n].f[1] = ptr[n].f[2] = 0.0;
+        b->dev_dirty &= ~(SEPB_F | SEPB_A);
+    } else {
+        b->dev_dirty |= SEPB_F | SEPB_A;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * scalar results (source/sepret.c:50-82)
+ * ------------------------------------------------------------------------------------------------- */
+static void refresh_ret(sepret *ret, sepsys *sys)
+{
+    /* in lazy mode the force calls have not copied their sums out yet */
+    for (sep_binding *b = sepb_first(); b; b = b->next)
+        if (b->gpu && b->last_ret == ret) sepb_pull_scalars(b, sys, ret, NULL);
+}
+
+void sep_pressure_tensor(sepret *ret, sepsys *sys)
+{
+    if (sep_sync_mode() == SEP_SYNC_LAZY) refresh_ret(ret, sys);
+    const double ivol = 1.0 / sys->volume;
+    ret->p = 0.0;
+    for (int k = 0; k < 3; k++)
+        for (int kk = 0; kk < 3; kk++) ret->P[k][kk] = (ret->kin_P[k][kk] + ret->pot_P[k][kk]) * ivol;
+    for (int k = 0; k < 3; k++) ret->p += ret->P[k][k];
+    ret->p /= 3.0;
+}
+
+double sep_get_pressure(sepret *ret, sepsys *sys)
+{
+    sep_pressure_tensor(ret, sys);
+    return ret->p;
+}
+
+double sep_get_temperature(sepret *ret, sepsys *sys)
+{
+    if (sep_sync_mode() == SEP_SYNC_LAZY) refresh_ret(ret, sys);
+    return 2.0 / (3.0 * sys->ndof) * ret->ekin;
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * readers of the host array: bring it up to date first
+ * ------------------------------------------------------------------------------------------------- */
+double sep_eval_mom(seppart *ptr, int npart)
+{
+    sep_gpu_sync(ptr);
+    double mom = 0.0;
+    for (int n = 0; n < npart; n++)
+        for (int k = 0; k < 3; k++) mom += ptr[n].v[k] * ptr[n].m;
+    return mom / (npart * 3);
+}
+
+double sep_eval_mom_type(seppart *ptr, char type, int dir, int npart)
+{
+    sep_gpu_sync(ptr);
+    double mom = 0.0;
+    int cnt = 0;
+    for (int n = 0; n < npart; n++)
+        if (ptr[n].type == type) { mom += ptr[n].v[dir] * ptr[n].m; cnt++; }
+    return cnt ? mom / cnt : 0.0;
+}
+
+int sep_count_type(seppart *ptr, char spec, int npart)
+{
+    int c = 0;
+    for (int n = 0; n < npart; n++) c += ptr[n].type == spec;
+    return c;
+}
+
+/* source/sepmisc.c:536-573 */
+void sep_save_xyz(seppart *ptr, const char *partnames, const char *file, char *mode, sepsys *sys)
+{
+    sep_gpu_sync(ptr);
+    const long ntype = (long)strlen(partnames);
+    FILE *fout = fopen(file, mode);
+    if (!fout) sep_error("%s at line %d: I couldn't open file\n", (char *)__func__, __LINE__);
+    long ntotal = 0;
+    for (long k = 0; k < ntype; k++) ntotal += sep_count_type(ptr, partnames[k], (int)sys->npart);
+    fprintf(fout, "%lu\n%f %f %f\n", (unsigned long)ntotal, sys->length[0], sys->length[1], sys->length[2]);
+    for (long n = 0; n < sys->npart; n++)
+        for (long k = 0; k < ntype; k++)
+            if (ptr[n].type == partnames[k])
+                fprintf(fout, "%c %.15f %.15f %.15f %.15f %.15f %.15f %.15f %.15f\n", ptr[n].type,
+                        ptr[n].x[0], ptr[n].x[1], ptr[n].x[2], ptr[n].v[0], ptr[n].v[1], ptr[n].v[2],
+                        ptr[n].m, ptr[n].z);
+    fclose(fout);
+}
+
+void sep_set_x0(seppart *ptr, int npart)
+{
+    sep_gpu_sync(ptr);
+    for (int n = 0; n < npart; n++)
+        for (int k = 0; k < 3; k++) ptr[n].x0[k] = ptr[n].x[k];
+}
+
+void sep_set_xn(seppart *ptr, int npart)
+{
+    sep_gpu_sync(ptr);
+    for (int n = 0; n < npart; n++)
+        for (int k = 0; k < 3; k++) ptr[n].xn[k] = ptr[n].x[k];
+    sepb_mark_host_dirty(ptr, SEPB_XN);
+}
+
+double sep_dist_ij(double *r, seppart *ptr, int i, int j, sepsys *sys)
+{
+    sep_gpu_sync(ptr);
+    double r2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+        r[k] = ptr[i].x[k] - ptr[j].x[k];
+        sep_Wrap(r[k], sys->length[k]);
+        r2 += r[k] * r[k];
+    }
+    return sqrt(r2);
+}
+
+void sep_eval_xtrue(seppart *ptr, sepsys *sys)
+{
+    sep_gpu_sync(ptr);
+    for (long n = 0; n < sys->npart; n++)
+        for (int k = 0; k < 3; k++) ptr[n].xtrue[k] = ptr[n].x[k] + ptr[n].crossings[k] * sys->length[k];
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * setters (source/sepmisc.c:484-513, 1087-1129, 1196-1200)
+ * ------------------------------------------------------------------------------------------------- */
+void sep_set_charge(seppart *ptr, char type, double z, sepsys sys)
+{
+    for (long n = 0; n < sys.npart; n++) if (ptr[n].type == type) ptr[n].z = z;
+    sepb_mark_host_dirty(ptr, SEPB_Z);
+}
+
+void sep_set_mass(seppart *ptr, char type, double m, sepsys sys)
+{
+    for (long n = 0; n < sys.npart; n++) if (ptr[n].type == type) ptr[n].m = m;
+    sepb_mark_host_dirty(ptr, SEPB_M);
+}
+
+/* relabel `numb` randomly chosen 'A' atoms (source/sepmisc.c:484-513) */
+void sep_set_type(seppart *ptr, char spec, int numb, sepsys *sys)
+{
+    int done = 0;
+    long guard = 0;
+    while (done < numb && guard++ < 1000L * (sys->npart + 1)) {
+        long i = (long)(sep_rand() * sys->npart);
+        if (ptr[i].type == 'A') { ptr[i].type = spec; done++; }
+    }
+    sepb_mark_host_dirty(ptr, SEPB_TYPE);
+}
+
+void sep_set_omp(unsigned nthreads, sepsys *sys)
+{
+    /* accepted for source compatibility: the device path does not use host threads */
+    sys->omp_flag = true;
+    sys->nthreads = nthreads;
+}
+
+void sep_set_skin(sepsys *sys, double value) { sys->skin = value; }
+void sep_set_ndof(size_t ndof, sepsys *sys) { sys->ndof = (unsigned)ndof; }
+
+/* source/sepmisc.c:1173-1192 */
+void sep_reset_momentum(seppart *ptr, const char type, sepsys *sys)
+{
+    sep_binding *b = sepb_prepare(ptr, sys);
+    sepb_check(sepgpu_reset_momentum(b->gpu, type), "sep_reset_momentum");
+    b->dev_dirty |= SEPB_V;
+    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_V);
+}
+
+/* source/sepmisc.c:994-1026 */
+void sep_compress_box(sepatom *ptr, double rhoD, double xi, sepsys *sys)
+{
+    const double density = sys->npart / sys->volume;
+    if (fabs(density - rhoD) < 1e-6) return;
+    if (density > rhoD) xi = 1.0 / xi;
+    for (int k = 0; k < 3; k++) {
+        sys->length[k] *= xi;
+        if (sys->length[k] < sys->cf * 2.0)
+            sep_warning("sep_compress_box: Box length too small compared to the maximum cut-off");
+    }
+    sep_binding *b = sepb_prepare(ptr, sys);
+    sepb_check(sepgpu_scale_positions(b->gpu, xi), "sep_compress_box");
+    b->dev_dirty |= SEPB_X;
+    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_X);
+    if (sys->neighb_update != 0)
+        for (int k = 0; k < 3; k++) {
+            sys->nsubbox[k] = sep_nsubbox(sys->cf, sys->skin, sys->length[k]);
+            if (sys->nsubbox[k] < 3)
+                sep_warning("sep_compress_box: Number of subboxes in x direction are less than three");
+            sys->lsubbox[k] = sys->length[k] / sys->nsubbox[k];
+        }
+    sys->volume = sys->length[0] * sys->length[1] * sys->length[2];
+}

@@ -1,0 +1,63 @@
+/* sep_host.h -- internals of the C99 host layer: the binding between a caller-owned seppart array and
+ * its device context, and the coherence bookkeeping described at the top of include/sep.h. */
+#ifndef SEP_HOST_H
+#define SEP_HOST_H
+
+#include "sep.h"
+#include "sepgpu.h"
+
+/* bits for host_dirty (host newer than device) and dev_dirty (device newer than host) */
+#define SEPB_X      (1u << 0)
+#define SEPB_V      (1u << 1)
+#define SEPB_F      (1u << 2)
+#define SEPB_M      (1u << 3)
+#define SEPB_Z      (1u << 4)
+#define SEPB_TYPE   (1u << 5)
+#define SEPB_MOL    (1u << 6)
+#define SEPB_XN     (1u << 7)
+#define SEPB_CN     (1u << 8)
+#define SEPB_CR     (1u << 9)
+#define SEPB_PV     (1u << 10)
+#define SEPB_PA     (1u << 11)
+#define SEPB_A      (1u << 12)
+#define SEPB_EXCL   (1u << 13)
+#define SEPB_TOPO   (1u << 14)
+#define SEPB_ALL_STATE (SEPB_X | SEPB_V | SEPB_F | SEPB_M | SEPB_Z | SEPB_TYPE | SEPB_MOL | SEPB_XN | SEPB_CN | SEPB_CR)
+
+typedef struct sep_binding {
+    seppart *atoms;
+    size_t npart;
+    sepgpu_ctx *gpu;            /* created on the first hot call */
+    sepmolinfo *molptr;         /* secondary key: survives by-value copies of sepsys */
+    unsigned host_dirty;
+    unsigned dev_dirty;
+    int uploaded_once;
+    int dpd_state_on_device;
+    double *alpha_ptr[4];       /* caller-owned thermostat multipliers mapped to device slots */
+    double alpha_seen[4];
+    unsigned long long dpd_calls;
+    sepret *last_ret;
+    double *blengths_host, *angles_host, *dihedrals_host;
+    struct sep_binding *next;
+} sep_binding;
+
+sep_binding *sepb_find(const seppart *atoms);
+sep_binding *sepb_find_mol(const sepmolinfo *molptr);
+sep_binding *sepb_first(void);
+sep_binding *sepb_register(seppart *atoms, size_t npart);
+void sepb_unregister(seppart *atoms);
+
+/* make the device ready for a hot call: create the context, upload what the host changed */
+sep_binding *sepb_prepare(seppart *atoms, sepsys *sys);
+void sepb_fill_sys(const sepsys *sys, sepgpu_sys *out);
+/* device -> host for the given field bits (only those currently newer on the device) */
+void sepb_download(sep_binding *b, unsigned fields);
+/* sepret / sepsys scalars device -> host */
+void sepb_pull_scalars(sep_binding *b, sepsys *sys, sepret *ret, sepgpu_scalars *out);
+void sepb_mark_host_dirty(seppart *atoms, unsigned fields);
+void sepb_after_force(sep_binding *b, sepsys *sys, sepret *ret);
+int sep_sync_mode(void);
+void sepb_check(int rc, const char *where);
+unsigned long long sep_dpd_seed(void);
+
+#endif

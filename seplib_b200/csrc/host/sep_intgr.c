@@ -1,0 +1,92 @@
+/* sep_intgr.c -- thermostat and integrator entry points (reference source/sepintgr.c:18-88,
+ * 149-198, 296-345).  The arithmetic runs in sepgpu_intgr.cu; this file keeps the host-visible
+ * bookkeeping the reference does in the same calls: sys->tnow, sys->neighb_flag,
+ * sys->nupdate_neighb, sys->max_dist2, the caller's alpha, and the write-back of atoms[]. */
+#include "sep_host.h"
+
+static int alpha_slot(sep_binding *b, double *alpha)
+{
+    for (int k = 0; k < 4; k++)
+        if (b->alpha_ptr[k] == alpha) return k;
+    for (int k = 0; k < 4; k++)
+        if (!b->alpha_ptr[k]) { b->alpha_ptr[k] = alpha; b->alpha_seen[k] = *alpha - 1.0; return k; }
+    /* more than four thermostats: recycle slot 3 */
+    b->alpha_ptr[3] = alpha; b->alpha_seen[3] = *alpha - 1.0;
+    return 3;
+}
+
+void sep_nosehoover(sepatom *ptr, double temp0, double *alpha, const double tau, sepsys *sys)
+{
+    sep_binding *b = sepb_prepare(ptr, sys);
+    const int slot = alpha_slot(b, alpha);
+    if (*alpha != b->alpha_seen[slot]) {                 /* first use, or the caller changed it */
+        sepb_check(sepgpu_set_alpha(b->gpu, slot, *alpha), "sep_nosehoover");
+        b->alpha_seen[slot] = *alpha;
+    }
+    sepgpu_sys gs;
+    sepb_fill_sys(sys, &gs);
+    sepb_check(sepgpu_nosehoover(b->gpu, &gs, temp0, slot, tau), "sep_nosehoover");
+    b->dev_dirty |= SEPB_F | SEPB_A;
+    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_pull_scalars(b, sys, NULL, NULL);   /* refreshes *alpha */
+    if (sep_sync_mode() == SEP_SYNC_FULL) sepb_download(b, SEPB_F);
+}
+
+void _sep_nosehoover_type(seppart *ptr, char type, double Td, double *alpha, const double Q, sepsys *sys)
+{
+    sep_binding *b = sepb_prepare(ptr, sys);
+    sepgpu_sys gs;
+    sepb_fill_sys(sys, &gs);
+    sepb_check(sepgpu_nosehoover_type(b->gpu, &gs, type, Td, alpha, Q), "_sep_nosehoover_type");
+    b->dev_dirty |= SEPB_F | SEPB_A;
+    if (sep_sync_mode() == SEP_SYNC_FULL) sepb_download(b, SEPB_F);
+}
+
+static void after_integrator(sep_binding *b, sepsys *sys, sepret *ret, int count_update)
+{
+    sepgpu_scalars s;
+    b->last_ret = ret;
+    sepb_pull_scalars(b, sys, ret, &s);
+    b->dev_dirty |= SEPB_X | SEPB_V | SEPB_F | SEPB_A | SEPB_CN | SEPB_CR;
+    if (s.neighb_flag) {                                  /* source/sepintgr.c:72-84 */
+        sys->neighb_flag = 1;
+        if (count_update) sys->nupdate_neighb++;
+        b->dev_dirty |= SEPB_XN;
+    }
+    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, ~0u);
+}
+
+void sep_leapfrog(seppart *ptr, sepsys *sys, sepret *retval)
+{
+    sep_binding *b = sepb_prepare(ptr, sys);
+    sepgpu_sys gs;
+    sepb_fill_sys(sys, &gs);
+    sepb_check(sepgpu_leapfrog(b->gpu, &gs), "sep_leapfrog");
+    after_integrator(b, sys, retval, 1);
+    sys->tnow += sys->dt;                                 /* source/sepintgr.c:86 */
+}
+
+void sep_verlet_dpd(seppart *ptr, double lambda, int stepnow, sepsys *sys, sepret *retval)
+{
+    sep_binding *b = sepb_find(ptr);
+    if (b && !b->dpd_state_on_device) { b->dpd_state_on_device = 1; b->host_dirty |= SEPB_PV | SEPB_PA; }
+    b = sepb_prepare(ptr, sys);
+    sepgpu_sys gs;
+    sepb_fill_sys(sys, &gs);
+    sepb_check(sepgpu_verlet_dpd(b->gpu, &gs, lambda, stepnow), "sep_verlet_dpd");
+    b->dev_dirty |= SEPB_PV | SEPB_PA;
+    after_integrator(b, sys, retval, 0);                  /* does not count list updates (:336-342) */
+}
+
+/* sep_periodic on the HOST copy, for user code that calls it directly (source/sepintgr.c:18-40) */
+double sep_periodic(sepatom *atoms, unsigned n, sepsys *sys)
+{
+    double d2 = 0.0;
+    sepatom *a = &atoms[n];
+    for (int k = 0; k < 3; k++) {
+        if (a->x[k] > sys->length[k]) { a->x[k] -= sys->length[k]; a->cross_neighb[k]++; a->crossings[k]++; }
+        else if (a->x[k] < 0.0) { a->x[k] += sys->length[k]; a->cross_neighb[k]--; a->crossings[k]--; }
+        const double ri = (a->x[k] + a->cross_neighb[k] * sys->length[k]) - a->xn[k];
+        d2 += ri * ri;
+    }
+    return d2;
+}

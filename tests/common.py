@@ -1,0 +1,251 @@
+"""Shared test plumbing: bindings for the CPU oracle port (oracle/liboracle.so), for the compiled
+reference (oracle/_ref/libsep_ref.so, when it has been built) and synthetic-system generators.
+
+Only tests/ (and bench.py's cpu_baseline leg, __graft_entry__.smoke) may touch oracle/ -- it is the
+checker, never the product."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from seplib_b200 import capi  # noqa: E402
+
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libsep_ref.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+ALL, EXCL_BONDED, EXCL_SAME_MOL = 1, 2, 3
+POT_LJ, POT_LJ_SHIFT, POT_WCA, POT_LJ_PARAM = 0, 1, 2, 3
+
+
+class OrcRet(C.Structure):
+    _fields_ = [("epot", C.c_double), ("ecoul", C.c_double), ("ekin", C.c_double),
+                ("pot_P", C.c_double * 9), ("kin_P", C.c_double * 9), ("pot_P_bond", C.c_double * 9)]
+
+
+class OrcTopo(C.Structure):
+    _fields_ = [("molindex", C.c_void_p), ("bond", C.c_void_p), ("angle", C.c_void_p), ("dihed", C.c_void_p)]
+
+
+_oracle = None
+
+
+def oracle():
+    """liboracle.so, built on demand from oracle/sep_oracle.c (plain gcc, seconds)."""
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    src = os.path.join(ORACLE_DIR, "sep_oracle.c")
+    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "port"], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(ORACLE_SO, mode=C.RTLD_LOCAL)
+    vp, dbl, i32 = C.c_void_p, C.c_double, C.c_int
+    lib.orc_wrap.restype = dbl
+    lib.orc_wrap.argtypes = [dbl, dbl]
+    lib.orc_cell_geometry.argtypes = [vp, dbl, dbl, vp, vp]
+    lib.orc_neighb_pairs.restype = C.c_long
+    lib.orc_neighb_pairs.argtypes = [i32, vp, vp, vp, vp, dbl, C.c_uint, C.POINTER(OrcTopo), vp, C.c_long]
+    lib.orc_neighb_pairs_n2.restype = C.c_long
+    lib.orc_neighb_pairs_n2.argtypes = [i32, vp, vp, dbl, C.c_uint, C.POINTER(OrcTopo), vp, C.c_long]
+    lib.orc_force_pairs_list.argtypes = [i32, vp, vp, vp, vp, C.c_long, C.c_char_p, dbl, i32, vp, vp, C.POINTER(OrcRet)]
+    lib.orc_force_pairs_brute.argtypes = [i32, vp, vp, vp, C.c_char_p, dbl, i32, vp, C.c_uint, C.POINTER(OrcTopo), vp, C.POINTER(OrcRet)]
+    lib.orc_coulomb_sf_list.argtypes = [i32, vp, vp, vp, vp, C.c_long, dbl, vp, C.POINTER(OrcRet)]
+    lib.orc_coulomb_sf_brute.argtypes = [i32, vp, vp, vp, dbl, C.c_uint, C.POINTER(OrcTopo), vp, C.POINTER(OrcRet)]
+    lib.orc_stretch_harmonic.argtypes = [vp, vp, vp, C.c_uint, i32, dbl, dbl, vp, C.POINTER(OrcRet), vp]
+    lib.orc_angle_harmonic.argtypes = [vp, vp, vp, C.c_uint, i32, dbl, dbl, vp, C.POINTER(OrcRet), vp]
+    lib.orc_angle_cossq.argtypes = [vp, vp, vp, C.c_uint, i32, dbl, dbl, vp, C.POINTER(OrcRet), vp]
+    lib.orc_torsion_ryckaert.argtypes = [vp, vp, vp, C.c_uint, i32, vp, vp, C.POINTER(OrcRet), vp]
+    lib.orc_nosehoover.restype = dbl
+    lib.orc_nosehoover.argtypes = [i32, vp, vp, vp, dbl, dbl, dbl, dbl]
+    lib.orc_nosehoover_type.argtypes = [i32, vp, vp, vp, C.c_char, vp, dbl, vp, dbl, dbl]
+    lib.orc_leapfrog.restype = i32
+    lib.orc_leapfrog.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, vp, C.POINTER(OrcRet)]
+    lib.orc_verlet_dpd.restype = i32
+    lib.orc_verlet_dpd.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, i32, dbl, vp, C.POINTER(OrcRet)]
+    lib.orc_dpd_uniform.restype = dbl
+    lib.orc_dpd_uniform.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_uint, C.c_uint]
+    lib.orc_dpd_force_list.argtypes = [i32, vp, vp, vp, vp, vp, C.c_long, C.c_char_p, dbl, dbl, dbl, dbl, dbl,
+                                       C.c_ulonglong, C.c_ulonglong, vp, C.POINTER(OrcRet)]
+    _oracle = lib
+    return lib
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+_ref = None
+
+
+def ref():
+    """The compiled reference (unmodified sources, -O2 -fno-fast-math); None if not built."""
+    global _ref
+    if _ref is None and have_ref():
+        lib = C.CDLL(REF_SO, mode=C.RTLD_LOCAL)
+        capi.declare_sep_api(lib)
+        _ref = lib
+    return _ref
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def dvec3(v):
+    return np.ascontiguousarray(v, dtype=np.float64)
+
+
+class Topo:
+    """Per-atom partner tables as the reference's topology reader fills them."""
+
+    def __init__(self, n):
+        self.n = n
+        self.molindex = np.full(n, -1, dtype=np.int32)
+        self.bond = np.full((n, 10), -1, dtype=np.int32)
+        self.angle = np.full((n, 10), -1, dtype=np.int32)
+        self.dihed = np.full((n, 20), -1, dtype=np.int32)
+        self.blist = np.zeros((0, 3), dtype=np.uint32)
+        self.alist = np.zeros((0, 4), dtype=np.uint32)
+        self.dlist = np.zeros((0, 5), dtype=np.uint32)
+
+    @staticmethod
+    def _add(row, val):
+        k = int(np.argmax(row == -1))
+        assert row[k] == -1, "partner table full"
+        row[k] = val
+
+    def add_bond(self, mol, a, b, t=0):
+        self.blist = np.vstack([self.blist, np.array([[a, b, t]], dtype=np.uint32)])
+        self.molindex[a] = mol
+        self.molindex[b] = mol
+        self._add(self.bond[a], b)
+        self._add(self.bond[b], a)
+
+    def add_angle(self, a, b, c, t=0):
+        self.alist = np.vstack([self.alist, np.array([[a, b, c, t]], dtype=np.uint32)])
+        for p, q in ((a, b), (a, c), (b, a), (b, c), (c, a), (c, b)):
+            self._add(self.angle[p], q)
+
+    def add_dihedral(self, a, b, c, d, t=0):
+        self.dlist = np.vstack([self.dlist, np.array([[a, b, c, d, t]], dtype=np.uint32)])
+        q = (a, b, c, d)
+        for r in range(4):
+            for s in range(4):
+                if s != r:
+                    self._add(self.dihed[q[r]], q[s])
+
+    def c_struct(self):
+        t = OrcTopo()
+        t.molindex = self.molindex.ctypes.data
+        t.bond = self.bond.ctypes.data
+        t.angle = self.angle.ctypes.data
+        t.dihed = self.dihed.ctypes.data
+        return t
+
+
+def chain_topology(nmol, nuau):
+    """Linear chains of nuau atoms (butane: 4): bonds, angles and dihedrals along the chain, vectorised."""
+    n = nmol * nuau
+    t = Topo(n)
+    base = np.arange(nmol, dtype=np.uint32)[:, None] * nuau
+    t.molindex[:] = np.repeat(np.arange(nmol, dtype=np.int32), nuau)
+
+    def rows(k):
+        return (base + np.arange(nuau - k, dtype=np.uint32)[None, :]).reshape(-1)
+
+    if nuau >= 2:
+        a = rows(1)
+        t.blist = np.stack([a, a + 1, np.zeros_like(a)], axis=1).astype(np.uint32)
+    if nuau >= 3:
+        a = rows(2)
+        t.alist = np.stack([a, a + 1, a + 2, np.zeros_like(a)], axis=1).astype(np.uint32)
+    if nuau >= 4:
+        a = rows(3)
+        t.dlist = np.stack([a, a + 1, a + 2, a + 3, np.zeros_like(a)], axis=1).astype(np.uint32)
+    _fill_partner_tables(t)
+    return t
+
+
+def _fill_partner_tables(t):
+    """Partner tables from the term lists, in the reference reader's order (source/sepmol.c:84-95, 208-211, 312-327)."""
+    fill = np.zeros(t.n, dtype=np.int64)
+    for a, b, _ in t.blist:
+        t.bond[a, fill[a]] = b; fill[a] += 1
+        t.bond[b, fill[b]] = a; fill[b] += 1
+    fill[:] = 0
+    for a, b, c, _ in t.alist:
+        for p, q in ((a, b), (a, c), (b, a), (b, c), (c, a), (c, b)):
+            t.angle[p, fill[p]] = q; fill[p] += 1
+    fill[:] = 0
+    for row in t.dlist:
+        q = row[:4]
+        for r in range(4):
+            for s in range(4):
+                if s != r:
+                    t.dihed[q[r], fill[q[r]]] = q[s]; fill[q[r]] += 1
+
+
+def lattice(ncell, rho, jitter=0.0, seed=1):
+    """Simple cubic lattice of ncell^3 atoms strictly inside [0,L), optional jitter."""
+    n = ncell ** 3
+    L = (n / rho) ** (1.0 / 3.0)
+    a = L / ncell
+    g = (np.arange(ncell) + 0.5) * a
+    z, y, x = np.meshgrid(g, g, g, indexing="ij")
+    pos = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    if jitter > 0:
+        rng = np.random.default_rng(seed)
+        pos = pos + rng.uniform(-jitter, jitter, size=pos.shape) * a
+        pos = np.mod(pos, L)
+        pos[pos >= L] = 0.0
+    return np.ascontiguousarray(pos), L
+
+
+def velocities(n, temp, seed=2, m=None):
+    """Uniform(-1/2,1/2) velocities, drift removed, rescaled to temp as sep_set_vel_seed does (source/sepinit.c:148-171)."""
+    rng = np.random.default_rng(seed)
+    v = rng.random((n, 3)) - 0.5
+    m = np.ones(n) if m is None else m
+    v -= (v * m[:, None]).sum(axis=0) / m.sum()
+    sekin = (v * v * m[:, None]).sum()
+    v *= np.sqrt(3 * n * temp / sekin)
+    return np.ascontiguousarray(v)
+
+
+def pair_set(pairs):
+    """Canonical sorted array of (min,max) rows (multiset preserved)."""
+    p = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    p = np.sort(p, axis=1)
+    order = np.lexsort((p[:, 1], p[:, 0]))
+    return p[order]
+
+
+def oracle_pairs(x, L, cf, skin, opt=ALL, topo=None, grid_skin=0.25, max_pairs=None):
+    orc = oracle()
+    n = len(x)
+    length = dvec3([L, L, L] if np.isscalar(L) else L)
+    nsub = np.zeros(3, dtype=np.int32)
+    lsub = np.zeros(3)
+    orc.orc_cell_geometry(ptr(length), cf, grid_skin, ptr(nsub), ptr(lsub))
+    if max_pairs is None:
+        vol = float(np.prod(length))
+        max_pairs = int(1.5 * n * (2.1 * (cf + skin) ** 3 * n / vol) + 4096)
+    buf = np.empty((max_pairs, 2), dtype=np.int32)
+    tp = topo.c_struct() if topo is not None else OrcTopo()
+    xx = np.ascontiguousarray(x, dtype=np.float64)
+    np_ = orc.orc_neighb_pairs(n, ptr(xx), ptr(length), ptr(nsub), ptr(lsub), cf + skin, opt, C.byref(tp), ptr(buf), max_pairs)
+    assert np_ >= 0, f"oracle pair build failed ({np_})"
+    return buf[:np_].copy()
+
+
+def rel_force_err(f, fref):
+    """max_i |df_i| / max(f_rms, 1)  -- SURVEY.md section 8c normalisation."""
+    d = np.linalg.norm(f - fref, axis=1).max()
+    frms = np.sqrt((fref * fref).sum(axis=1).mean())
+    return d / max(frms, 1.0)
