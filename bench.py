@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- atom-timesteps/s of the seplib hot path on B200 (BASELINE.json metric).
+
+A "step" is one MD time step of the whole system:
+    sep_reset_retval -> sep_reset_force -> sep_force_pairs (LJ, rc=2.5, list rebuilt when the skin
+    trigger fired) -> sep_nosehoover -> sep_leapfrog
+on a lattice-initialised Lennard-Jones fluid (prg1-style NVT).
+
+  value     device-resident loop through the sepgpu_* C ABI (inputs already in HBM), CUDA-event timed
+  e2e       the same loop through the reference-facing sep_* API with HOST seppart[] buffers; the timed
+            region contains the host->device upload, a device->host read of the step's sepret/sepsys
+            scalars EVERY step, and the final download into the host array
+  roofline  the pair-force kernel (dominant): algorithmic bytes / CUDA-event time vs measured HBM peak,
+            plus its FP64 rate vs an FMA-chain peak measured on this box (the kernel is FP64-pipe bound)
+  cpu_baseline  the reference's own OpenMP CPU path (oracle/_ref, compiled from its unmodified sources)
+            on the box's host cores, bounded sample of the same workload
+
+--impl reference runs only that CPU arm and prints its own line.
+N>1 (torchrun): spatial domain decomposition when available (strong scaling of the 8M-atom config),
+otherwise independent replicas (weak scaling) -- stated in config.parallelism.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "atom-timesteps/sec (LJ, rc=2.5)"
+UNIT = "atom-timesteps/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------
+def lj_lattice(ncell, rho):
+    n = ncell ** 3
+    L = (n / rho) ** (1.0 / 3.0)
+    a = L / ncell
+    g = (np.arange(ncell) + 0.5) * a
+    z, y, x = np.meshgrid(g, g, g, indexing="ij")
+    return np.ascontiguousarray(np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)), L
+
+
+def lj_velocities(n, temp, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.random((n, 3)) - 0.5
+    v -= v.mean(axis=0)
+    v *= np.sqrt(3 * n * temp / (v * v).sum())
+    return np.ascontiguousarray(v)
+
+
+ALG_FLOPS_PER_LISTED = 13.0
+ALG_FLOPS_PER_INRANGE = 42.0
+
+
+def algorithmic_per_atom(rho, rc, skin):
+    """half-list pair counts, flops and compulsory bytes per atom-step."""
+    n_list = (2.0 * np.pi / 3.0) * rho * (rc + skin) ** 3
+    n_in = (2.0 * np.pi / 3.0) * rho * rc ** 3
+    flops = (ALG_FLOPS_PER_LISTED + ALG_FLOPS_PER_INRANGE) * n_in + ALG_FLOPS_PER_LISTED * (n_list - n_in)
+    nbytes = 4.0 * n_list + 32.0 + 32.0
+    return n_list, n_in, flops, nbytes
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception as e:      # noqa: BLE001
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            p = [q.strip() for q in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(p[1]))
+                smax = float(p[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active") and t0 - 0.05 <= ts <= t1 + 0.15:
+                    reasons.add(name)
+        if not sm:      # region shorter than a sample period: use everything we saw
+            for ts, line in self.rows:
+                p = [q.strip() for q in line.split(",")]
+                try:
+                    sm.append(float(p[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_arm(ncell, rho, rc, skin, dt, temp, tau, target_seconds, threads):
+    """Runs the prg1/prg4-style loop through the reference API (oracle/_ref/libsep_ref_fast.so, built from
+    the unmodified reference sources with its shipped flags -Ofast -fopenmp).  Falls back to the C port
+    (oracle/liboracle.so, scalar) when the reference build is absent.  Returns (value, info dict)."""
+    from seplib_b200 import capi
+    fast = os.path.join(ROOT, "oracle", "_ref", "libsep_ref_fast.so")
+    x, L = lj_lattice(ncell, rho)
+    n = len(x)
+    v = lj_velocities(n, temp, 12345)
+    if os.path.exists(fast):
+        lib = C.CDLL(fast, mode=C.RTLD_LOCAL)
+        capi.declare_sep_api(lib)
+        atoms = lib.sep_init(n, 3000)
+        sys_ = lib.sep_sys_setup(L, L, L, rc, dt, n, capi.SEP_LLIST_NEIGHBLIST)
+        view = capi.atoms_view(atoms, n)
+        view["x"][:] = x
+        view["v"][:] = v
+        view["xn"][:] = 0.0
+        if threads > 1:
+            lib.sep_set_omp(threads, C.byref(sys_))
+        lib.sep_set_skin(C.byref(sys_), skin)
+        ret = capi.SepRet()
+        alpha = C.c_double(0.1)
+        fun = C.cast(lib.sep_lj_shift, C.c_void_p)
+
+        def step():
+            lib.sep_reset_retval(C.byref(ret))
+            lib.sep_reset_force(atoms, C.byref(sys_))
+            lib.sep_force_pairs(atoms, b"AA", rc, fun, C.byref(sys_), C.byref(ret), capi.SEP_ALL)
+            lib.sep_nosehoover(atoms, temp, C.byref(alpha), tau, C.byref(sys_))
+            lib.sep_leapfrog(atoms, C.byref(sys_), C.byref(ret))
+
+        for _ in range(3):
+            step()
+        t0 = time.perf_counter()
+        step(); step()
+        per = (time.perf_counter() - t0) / 2
+        steps = int(max(5, min(2000, target_seconds / max(per, 1e-6))))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        el = time.perf_counter() - t0
+        epot = ret.epot / n
+        lib.sep_close(atoms, n)
+        kind = "reference"
+    else:
+        import common as cm
+        orc = cm.oracle()
+        threads = 1
+        m = np.ones(n); types = np.full(n, ord("A"), dtype=np.uint8)
+        xn = np.zeros((n, 3)); cn = np.zeros((n, 3), dtype=np.int32); cr = np.zeros((n, 3), dtype=np.int32)
+        a = np.zeros((n, 3)); length = np.array([L, L, L])
+        state = {"flag": 1, "pairs": None, "alpha": 0.1}
+        ret = cm.OrcRet()
+
+        def step():
+            f = np.zeros((n, 3)); md2 = C.c_double(0.0)
+            r = cm.OrcRet()
+            if state["flag"]:
+                state["pairs"] = np.ascontiguousarray(cm.oracle_pairs(x, L, rc, skin), dtype=np.int32)
+            p = state["pairs"]
+            orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(p), len(p), b"AA", rc,
+                                     cm.POT_LJ_SHIFT, None, cm.ptr(f), C.byref(r))
+            state["alpha"] = orc.orc_nosehoover(n, cm.ptr(v), cm.ptr(m), cm.ptr(f), temp, state["alpha"], tau, dt)
+            state["flag"] = orc.orc_leapfrog(n, cm.ptr(x), cm.ptr(v), cm.ptr(f), cm.ptr(m), cm.ptr(a), cm.ptr(xn),
+                                             cm.ptr(cn), cm.ptr(cr), cm.ptr(length), dt, skin, C.byref(md2), C.byref(r))
+            ret.epot = r.epot
+
+        for _ in range(3):
+            step()
+        t0 = time.perf_counter()
+        step(); step()
+        per = (time.perf_counter() - t0) / 2
+        steps = int(max(5, min(2000, target_seconds / max(per, 1e-6))))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        el = time.perf_counter() - t0
+        epot = ret.epot / n
+        kind = "port"
+    value = n * steps / el
+    info = {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{n} atoms (lattice {ncell}^3, rho={rho}, rc={rc}, skin={skin}, NH tau={tau}) x {steps} steps "
+                      f"in {el:.1f} s, epot/N={epot:.4f}",
+            "seconds": el, "steps": steps, "natoms": n}
+    return value, info
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ncell", type=int, default=100, help="lattice side: ncell^3 atoms per GPU (weak) / total (DD)")
+    ap.add_argument("--rho", type=float, default=0.8)
+    ap.add_argument("--skin", type=float, default=0.25)
+    ap.add_argument("--tpa", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-ncell", type=int, default=48)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rc, dt, temp, tau = 2.5, 0.005, 1.0, 0.01       # prg1's literals with the metric's rc (prgs/prg1.c:24-30)
+    K, W = args.steps, max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = host_cores()
+        value, info = cpu_reference_arm(args.cpu_ncell, args.rho, rc, args.skin, dt, temp, tau,
+                                        max(args.cpu_seconds, 5.0) * 2, threads)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": info["steps"], "warmup": 5, "ms_per_step": 1e3 * info["seconds"] / info["steps"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "prg1-style LJ NVT (rc=2.5, NH) bounded CPU sample", "natoms": info["natoms"],
+                           "rho": args.rho, "skin": args.skin, "l2": "n/a (host)"},
+                "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from seplib_b200 import capi
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    lib = capi.load()
+    if lib.sepgpu_device_count() <= 0:
+        raise RuntimeError("bench.py: no CUDA device -- seplib-b200 has no CPU path")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm -------------------------------------------------------
+    x, L = lj_lattice(args.ncell, args.rho)
+    n = len(x)
+    v = lj_velocities(n, temp, 1000 + rank)
+    s = capi.System(n, device=local_rank)
+    if args.tpa:
+        s.call("sepgpu_set_option", b"tpa", args.tpa)
+    s.put(capi.F_X, x)
+    s.put(capi.F_V, v)
+    s.call("sepgpu_set_alpha", 0, 0.1)
+    gsys = capi.make_sys([L] * 3, rc, dt, skin=args.skin)
+    ljp = capi.lj_param(rc, kind="lj_shift")
+    gs_ref, lj_ref = C.byref(gsys), C.byref(ljp)
+    fn = lib
+    ctx = s.ctx
+
+    def step_dev():
+        fn.sepgpu_reset_ret(ctx)
+        fn.sepgpu_reset_force(ctx)
+        rc_ = fn.sepgpu_force_lj(ctx, gs_ref, b"AA", lj_ref, 1, 1)     # rebuilds the list itself when the trigger fired
+        rc_ |= fn.sepgpu_nosehoover(ctx, gs_ref, temp, 0, tau)
+        rc_ |= fn.sepgpu_leapfrog(ctx, gs_ref)
+        if rc_:
+            raise RuntimeError("device step failed: " + fn.sepgpu_last_error().decode())
+
+    for _ in range(W):
+        step_dev()
+    nb0 = s.scalars().nbuild
+    s.call("sepgpu_set_option", b"time_kernels", 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t_wall0 = time.time()
+    s.call("sepgpu_timer_start")
+    for _ in range(K):
+        step_dev()
+    ms = C.c_float()
+    s.call("sepgpu_timer_stop", C.byref(ms))
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    sc = s.scalars()
+    nbuild = sc.nbuild - nb0
+    kt = {}
+    for which in ("force", "build", "intgr"):
+        tot, cnt = C.c_float(), C.c_int()
+        s.call("sepgpu_kernel_time", which.encode(), C.byref(tot), C.byref(cnt))
+        kt[which] = (tot.value, cnt.value)
+    t_ms = torch.tensor([ms.value], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    t_sec = float(t_ms.item()) * 1e-3
+    total_atoms = n * world
+    value = total_atoms * K / t_sec
+    epotN, ekinN = sc.epot / n, sc.ekin / n
+    pairs_per_atom = sc.npairs_listed / n / 2.0
+    s.close()
+
+    # ---------------- e2e arm: sep_* API, host seppart[] buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        lib.sep_gpu_set_sync(0)          # SEP_SYNC_LAZY: scalars every step, atoms[] at the end
+        Ke = max(10, min(K, 300))
+        atoms = lib.sep_init(n, 0)
+        view = capi.atoms_view(atoms, n)
+        view["x"][:] = x
+        view["v"][:] = v
+        hsys = lib.sep_sys_setup(L, L, L, rc, dt, n, capi.SEP_LLIST_NEIGHBLIST)
+        lib.sep_set_skin(C.byref(hsys), args.skin)
+        ret = capi.SepRet()
+        alpha = C.c_double(0.1)
+        fun = C.cast(lib.sep_lj_shift, C.c_void_p)
+
+        def step_api():
+            lib.sep_reset_retval(C.byref(ret))
+            lib.sep_reset_force(atoms, C.byref(hsys))
+            lib.sep_force_pairs(atoms, b"AA", rc, fun, C.byref(hsys), C.byref(ret), capi.SEP_ALL)
+            lib.sep_nosehoover(atoms, temp, C.byref(alpha), tau, C.byref(hsys))
+            lib.sep_leapfrog(atoms, C.byref(hsys), C.byref(ret))
+
+        # warm-up on a throw-away context state: run, then restore the host arrays and force a re-upload
+        for _ in range(max(3, min(W, 20))):
+            step_api()
+        view["x"][:] = x
+        view["v"][:] = v
+        view["xn"][:] = 0.0
+        view["cross_neighb"][:] = 0
+        view["crossings"][:] = 0
+        lib.sep_gpu_invalidate(atoms)
+        hsys.neighb_flag = 1
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            step_api()                   # first call uploads x,v,m,z,type,... from the host array
+        lib.sep_gpu_sync(atoms)          # final state back into atoms[]
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        t_e = torch.tensor([el], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        el = float(t_e.item())
+        h2d = n * (24 * 3 + 8 * 2 + 1 + 4 + 12 * 2)            # x, v, xn, m, z, type, molindex, cross_neighb, crossings
+        d2h_final = n * (24 * 4 + 12 * 2 + 24)                 # x, v, f, a, counters, xn
+        scal_bytes = 416                                       # sizeof(DevScalars) per integrator call
+        e2e = {"value": total_atoms * Ke / el, "unit": UNIT,
+               "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": scal_bytes + d2h_final / Ke,
+               "steps": Ke, "sync": "lazy: sepret/sepsys scalars D2H every step; seppart[] uploaded at step 0 "
+                                     "and downloaded after the last step, both inside the timed region",
+               "epot_per_atom": ret.epot / n}
+        lib.sep_close(atoms, n)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the pair-force kernel ----------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "measured (MEASURED_PEAKS.json)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_list, n_in, alg_flops, alg_bytes = algorithmic_per_atom(args.rho, rc, args.skin)
+    f_ms, f_cnt = kt["force"]
+    force_ms = f_ms / max(f_cnt, 1)
+    achieved_gbs = alg_bytes * n / (force_ms * 1e-3) / 1e9
+    fp64_peak = C.c_double()
+    lib.sepgpu_peak_fp64(local_rank, C.byref(fp64_peak))
+    achieved_tf = alg_flops * n / (force_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:      # noqa: BLE001
+            traffic = None
+    roofline = {"kernel": "k_lj_list", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_atom_step": alg_bytes, "avg_launch_ms": force_ms, "launches": f_cnt,
+                "share_of_step": f_ms / (t_sec * 1e3),
+                "fp64": {"note": "binding limit of this kernel is the FP64 pipe, not HBM",
+                         "algorithmic_flops_per_atom_step": alg_flops, "achieved_tflops": achieved_tf,
+                         "peak_tflops_fma_chain_measured_here": fp64_peak.value,
+                         "frac": achieved_tf / fp64_peak.value if fp64_peak.value else None}}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        try:
+            _, info = cpu_reference_arm(args.cpu_ncell, args.rho, rc, args.skin, dt, temp, tau, args.cpu_seconds, host_cores())
+            cpu = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:      # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+    launches = K * 7 + nbuild * 9      # reset_ret, reset_maxdist, force, finalize, nh_update, integrate, finalize (+1 set_xn, +8 build)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_sec * 1e3 / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C1 prg1-style LJ NVT: sep_force_pairs(sep_lj_shift, rc=2.5) + sep_nosehoover + sep_leapfrog",
+                   "natoms_per_gpu": n, "natoms_total": total_atoms, "rho": args.rho, "skin": args.skin, "dt": dt,
+                   "T0": temp, "tau": tau, "lattice": f"sc {args.ncell}^3",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
+                   "l2": "inputs larger than L2 (xs 32 MB + Verlet list %.0f MB + state > 126 MB)" % (n * pairs_per_atom * 8 / 1e6),
+                   "list_rebuilds_in_timed_region": nbuild, "half_pairs_per_atom": pairs_per_atom,
+                   "epot_per_atom": epotN, "ekin_per_atom": ekinN},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "kernel_ms": {k: {"total_ms": a, "launches": b} for k, (a, b) in kt.items()},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -99,6 +99,24 @@ class GpuScalars(C.Structure):
 
 PAIRFUN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_char)
 
+# numpy view of a seppart array (host AoS, 568-byte records) for bulk reads/writes in tests and bench
+ATOM_DTYPE = np.dtype({
+    "names": ["x", "v", "f", "a", "m", "type", "z", "cross_neighb", "crossings", "molindex", "bond",
+              "angle", "dihed", "xn", "pv", "pa"],
+    "formats": [(np.float64, 3), (np.float64, 3), (np.float64, 3), (np.float64, 3), np.float64, np.uint8,
+                np.float64, (np.int32, 3), (np.int32, 3), np.int32, (np.int32, 10), (np.int32, 10),
+                (np.int32, 20), (np.float64, 3), (np.float64, 3), (np.float64, 3)],
+    "offsets": [0, 24, 48, 72, 96, 104, 112, 128, 140, 152, 156, 196, 236, 400, 472, 496],
+    "itemsize": 568,
+})
+
+
+def atoms_view(ptr, n):
+    """Structured numpy view (no copy) of the seppart array returned by sep_init / sep_init_xyz."""
+    addr = C.addressof(ptr.contents)
+    buf = (C.c_char * (568 * n)).from_address(addr)
+    return np.frombuffer(buf, dtype=ATOM_DTYPE, count=n)
+
 # every symbol include/sepgpu.h declares (tests check that the library exports all of them)
 SEPGPU_SYMBOLS = [
     "sepgpu_create", "sepgpu_destroy", "sepgpu_last_error", "sepgpu_device_count", "sepgpu_put",

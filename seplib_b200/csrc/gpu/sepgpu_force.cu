@@ -67,25 +67,62 @@ __device__ __forceinline__ void apply_image(int code, const BoxDev &B, double &d
 }
 
 // ---- Lennard-Jones, Verlet list ------------------------------------------------------------------------
+struct PairAcc {
+    double fx, fy, fz;
+    double u, vxx, vxy, vxz, vyy, vyz, vzz;
+    int nin;
+};
+
+template <bool TYPED>
+__device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, int ti, const LJDev &P,
+                                        const BoxDev &B, PairAcc &A)
+{
+    double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    const int code = (int)(e >> SEPGPU_SHIFT_BITS);
+    if (code != 13) apply_image(code, B, dx, dy, dz);
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    bool in = r2 < P.cf2;
+    if (TYPED) {
+        const int tj = tag_type(pj.w);
+        in = in && ((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0));   // source/sepprfrc.c:171-172
+    }
+    if (in) {
+        const double rri = P.sig2 * fast_rcp(r2);
+        const double rri3 = rri * rri * rri;
+        const double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;   // source/sepmisc.c:139, sepprfrc.c:888
+        const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
+        A.fx += gx; A.fy += gy; A.fz += gz;
+        A.u = fma(rri3, rri3 - P.aw, A.u);                         // u/(4 eps) before the shift
+        A.nin++;
+        A.vxx = fma(gx, dx, A.vxx); A.vxy = fma(gx, dy, A.vxy); A.vxz = fma(gx, dz, A.vxz);
+        A.vyy = fma(gy, dy, A.vyy); A.vyz = fma(gy, dz, A.vyz); A.vzz = fma(gz, dz, A.vzz);
+    }
+}
+
 // STORE: first force kernel after sep_reset_force -> plain store instead of read-modify-write.
+// Each CTA walks a CONTIGUOUS range of the cell-sorted atoms so that the neighbour rows it gathers
+// stay resident in its SM's L1 while it moves along the x-row of cells; list entries are streamed
+// (ld.global.cs) because they are never reused.  The inner loop is unrolled by two with both list
+// entries and both neighbour sectors requested before any arithmetic, to keep more gathers in flight.
 template <int TPA, bool TYPED, bool STORE>
 __global__ void __launch_bounds__(FORCE_BLOCK)
 k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
-          const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, LJDev P, BoxDev B,
-          double *__restrict__ partial)
+          const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int atoms_per_cta,
+          LJDev P, BoxDev B, double *__restrict__ partial)
 {
     __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
     const int sub = threadIdx.x % TPA;
-    const int groups_per_block = FORCE_BLOCK / TPA;
-    double acc[SEPGPU_NPART_F];      // uacc, (unused), vxx, vxy, vxz, vyy, vyz, vzz
-#pragma unroll
-    for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
-    int nin = 0;
+    constexpr int GROUPS = FORCE_BLOCK / TPA;
+    PairAcc A;
+    A.u = A.vxx = A.vxy = A.vxz = A.vyy = A.vyz = A.vzz = 0.0;
+    A.nin = 0;
+    const int first = blockIdx.x * atoms_per_cta;
+    const int last = min(n, first + atoms_per_cta);
 
-    for (int s0 = blockIdx.x * groups_per_block; s0 < n; s0 += gridDim.x * groups_per_block) {
+    for (int s0 = first; s0 < last; s0 += GROUPS) {
         const int s = s0 + threadIdx.x / TPA;
-        const bool valid = s < n;
-        double fx = 0.0, fy = 0.0, fz = 0.0;
+        const bool valid = s < last;
+        A.fx = A.fy = A.fz = 0.0;
         if (valid) {
             const d4 pi = xs[s];
             int m = cnt[s];
@@ -95,52 +132,44 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
                 if (ti != P.t0 && ti != P.t1) m = 0;             // source/sepprfrc.c:164-165
             }
             const unsigned *row = nbr + s;
-#pragma unroll 2
-            for (int k = sub; k < m; k += TPA) {
-                const unsigned e = row[(size_t)k * npad];
-                const d4 pj = xs[e & SEPGPU_INDEX_MASK];
-                double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                const int code = (int)(e >> SEPGPU_SHIFT_BITS);
-                if (code != 13) apply_image(code, B, dx, dy, dz);
-                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                bool in = r2 < P.cf2;
-                if (TYPED) {
-                    const int tj = tag_type(pj.w);
-                    in = in && ((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0));   // :171-172
-                }
-                if (in) {
-                    const double rri = P.sig2 * fast_rcp(r2);
-                    const double rri3 = rri * rri * rri;
-                    const double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;   // source/sepmisc.c:139, sepprfrc.c:888
-                    const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
-                    fx += gx; fy += gy; fz += gz;
-                    acc[0] = fma(rri3, rri3 - P.aw, acc[0]);                    // u/(4 eps) before the shift
-                    nin++;
-                    acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
-                    acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
-                }
+            int k = sub;
+            for (; k + TPA < m; k += 2 * TPA) {
+                const unsigned e0 = __ldcs(row + (size_t)k * npad);
+                const unsigned e1 = __ldcs(row + (size_t)(k + TPA) * npad);
+                const d4 p0 = xs[e0 & SEPGPU_INDEX_MASK];
+                const d4 p1 = xs[e1 & SEPGPU_INDEX_MASK];
+                lj_pair<TYPED>(pi, p0, e0, ti, P, B, A);
+                lj_pair<TYPED>(pi, p1, e1, ti, P, B, A);
+            }
+            if (k < m) {
+                const unsigned e0 = __ldcs(row + (size_t)k * npad);
+                const d4 p0 = xs[e0 & SEPGPU_INDEX_MASK];
+                lj_pair<TYPED>(pi, p0, e0, ti, P, B, A);
             }
         }
         // butterfly over the TPA lanes of this atom
 #pragma unroll
         for (int o = TPA / 2; o > 0; o >>= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+            A.fx += __shfl_xor_sync(0xffffffffu, A.fx, o);
+            A.fy += __shfl_xor_sync(0xffffffffu, A.fy, o);
+            A.fz += __shfl_xor_sync(0xffffffffu, A.fz, o);
         }
         if (valid && sub == 0) {
             const int i = order[s];
             if (STORE) {
-                d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0;
+                d4 o; o.x = A.fx; o.y = A.fy; o.z = A.fz; o.w = 0.0;
                 f4[i] = o;
             } else {
                 d4 o = f4[i];
-                o.x += fx; o.y += fy; o.z += fz;
+                o.x += A.fx; o.y += A.fy; o.z += A.fz;
                 f4[i] = o;
             }
         }
     }
-    acc[0] = P.eps4 * acc[0] - P.shift * (double)nin;
+    double acc[SEPGPU_NPART_F];
+    acc[0] = P.eps4 * A.u - P.shift * (double)A.nin;
+    acc[1] = 0.0;
+    acc[2] = A.vxx; acc[3] = A.vxy; acc[4] = A.vxz; acc[5] = A.vyy; acc[6] = A.vyz; acc[7] = A.vzz;
     block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -277,9 +306,9 @@ static LJDev make_lj(const sepgpu_ljparam *p, const char types[2])
 }
 
 template <int TPA>
-static void launch_lj_list(sepgpu_ctx *c, int grid, bool typed, bool store, const LJDev &P, const BoxDev &B)
+static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
 {
-#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial
+#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial
     if (typed) {
         if (store) k_lj_list<TPA, true, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
         else       k_lj_list<TPA, true, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
@@ -321,17 +350,21 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     // the type test is compiled out when every atom carries the one requested type
     const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
     const int tpa = c->tpa;
-    const long long groups_per_block = FORCE_BLOCK / tpa;
-    long long want = ((long long)c->n + groups_per_block - 1) / groups_per_block;
-    const int grid = (int)(want < FORCE_MAX_GRID ? want : FORCE_MAX_GRID);
+    // contiguous ranges of the sorted atoms per CTA; several CTAs per SM, a few waves for load balance
+    const int groups = FORCE_BLOCK / tpa;
+    int grid = FORCE_MAX_GRID;
+    int apc = (c->n + grid - 1) / grid;
+    apc = ((apc + groups - 1) / groups) * groups;
+    if (apc < groups) apc = groups;
+    grid = (c->n + apc - 1) / apc;
     ktimer_begin(c, &c->t_force);
     switch (tpa) {
-    case 1: launch_lj_list<1>(c, grid, typed, store, P, B); break;
-    case 2: launch_lj_list<2>(c, grid, typed, store, P, B); break;
-    case 4: launch_lj_list<4>(c, grid, typed, store, P, B); break;
-    case 8: launch_lj_list<8>(c, grid, typed, store, P, B); break;
-    case 16: launch_lj_list<16>(c, grid, typed, store, P, B); break;
-    default: launch_lj_list<32>(c, grid, typed, store, P, B); break;
+    case 1: launch_lj_list<1>(c, grid, apc, typed, store, P, B); break;
+    case 2: launch_lj_list<2>(c, grid, apc, typed, store, P, B); break;
+    case 4: launch_lj_list<4>(c, grid, apc, typed, store, P, B); break;
+    case 8: launch_lj_list<8>(c, grid, apc, typed, store, P, B); break;
+    case 16: launch_lj_list<16>(c, grid, apc, typed, store, P, B); break;
+    default: launch_lj_list<32>(c, grid, apc, typed, store, P, B); break;
     }
     ktimer_end(c, &c->t_force);
     KERNEL_CHECK();

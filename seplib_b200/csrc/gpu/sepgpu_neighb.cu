@@ -233,6 +233,150 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
     }
 }
 
+// ---- tiled build: the fast path ------------------------------------------------------------------------------
+// One CTA owns TILE_CX consecutive home cells of one x-row (their atoms are contiguous in the sorted
+// array) and one THREAD owns one home atom.  For each of the 9 (dy,dz) rows the TILE_CX+2 candidate
+// cells are staged once into shared memory as FP32 positions already shifted to the right periodic
+// image; a thread then sweeps the 3 cells around its own cell.  Compared with one warp per atom this
+// reads every candidate once per CTA instead of once per atom and keeps all 32 lanes busy on different
+// atoms.  Candidates inside the FP32 error band of the cutoff take the exact FP64 test (pair_exact).
+#define TILE_CX 4
+#define TILE_THREADS 128
+#define TILE_STAGE 1024
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int *__restrict__ order,
+             const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
+             const int *__restrict__ excl_angle, const int *__restrict__ excl_dihed,
+             unsigned *__restrict__ nbr, int *__restrict__ cnt, DevScalars *scal, BuildParams P)
+{
+    __shared__ float4 cand[TILE_STAGE];
+    __shared__ int s_off[TILE_CX + 3];      // staged offset of candidate cell cc (cc = 0..ncx+1), +1 end marker
+    __shared__ int s_jbase[TILE_CX + 2];    // sorted index of a candidate = staged position + s_jbase[cc]
+    __shared__ int s_wx[TILE_CX + 2];       // x image of candidate cell cc
+    __shared__ int s_home[TILE_CX + 1];     // sorted-index boundaries of the home cells
+    __shared__ int s_red[3];
+
+    const int nseg = (P.nx + TILE_CX - 1) / TILE_CX;
+    const int seg = blockIdx.x % nseg;
+    const int cy = (blockIdx.x / nseg) % P.ny;
+    const int cz = blockIdx.x / (nseg * P.ny);
+    const int x0 = seg * TILE_CX;
+    const int ncx = min(TILE_CX, P.nx - x0);
+    const int row_home = (cy + cz * P.ny) * P.nx;
+    if (threadIdx.x <= ncx) s_home[threadIdx.x] = cell_start[row_home + x0 + threadIdx.x];
+    if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
+    __syncthreads();
+    const int a0 = s_home[0], nhome = s_home[ncx] - a0;
+    int blk_max = 0, blk_half = 0, blk_sum = 0;
+
+    for (int ab = 0; ab < nhome; ab += TILE_THREADS) {
+        const int s = a0 + ab + threadIdx.x;
+        const bool active = s < a0 + nhome;
+        int h = 0;                                   // my home cell inside the tile
+        float4 fi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            for (int q = 1; q < ncx; q++) h += (s >= s_home[q]);
+            fi = xf[s];
+        }
+        const int mol_i = __float_as_int(fi.w);
+        int count = 0, half_count = 0;
+        int i_orig = -1;
+
+        for (int r = 0; r < 9; r++) {
+            const int oy = r % 3 - 1, oz = r / 3 - 1;
+            int my = cy + oy, wy = 0, mz = cz + oz, wz = 0;
+            if (my == P.ny) { my = 0; wy = 1; } else if (my == -1) { my = P.ny - 1; wy = -1; }
+            if (mz == P.nz) { mz = 0; wz = 1; } else if (mz == -1) { mz = P.nz - 1; wz = -1; }
+            const int row = (my + mz * P.ny) * P.nx;
+            __syncthreads();                         // previous row fully consumed
+            if (threadIdx.x == 0) {
+                int off = 0;
+                for (int cc = 0; cc < ncx + 2; cc++) {
+                    int mx = x0 - 1 + cc, wx = 0;
+                    if (mx >= P.nx) { mx -= P.nx; wx = 1; } else if (mx < 0) { mx += P.nx; wx = -1; }
+                    const int b = cell_start[row + mx], e = cell_start[row + mx + 1];
+                    s_off[cc] = off; s_jbase[cc] = b - off; s_wx[cc] = wx;
+                    off += e - b;
+                }
+                s_off[ncx + 2] = off;
+            }
+            __syncthreads();
+            const int total = s_off[ncx + 2];
+            const float shy = wy * P.fLy, shz = wz * P.fLz;
+            const bool half_row = (oz == 1) || (oz == 0 && oy == 1);
+            const int code_yz = 3 * (wy + 1) + 9 * (wz + 1);
+
+            for (int base = 0; base < total; base += TILE_STAGE) {
+                const int lim = min(total - base, TILE_STAGE);
+                if (base > 0) __syncthreads();
+                for (int q = threadIdx.x; q < lim; q += TILE_THREADS) {
+                    const int g = base + q;
+                    int cc = 0;
+                    for (int t = 1; t < ncx + 2; t++) cc += (g >= s_off[t]);
+                    float4 f = xf[g + s_jbase[cc]];
+                    f.x += s_wx[cc] * P.fLx; f.y += shy; f.z += shz;
+                    cand[q] = f;
+                }
+                __syncthreads();
+                if (active) {
+                    for (int cc = h; cc < h + 3; cc++) {
+                        const int lo = max(s_off[cc], base) - base, hi = min(s_off[cc + 1], base + lim) - base;
+                        const int jb = s_jbase[cc] + base;
+                        const int code_c = (s_wx[cc] + 1) + code_yz;
+                        const int ox = cc - 1 - h;
+                        const bool in_half = half_row || (oz == 0 && oy == 0 && ox == 1);
+                        const bool same_cell = (oz == 0 && oy == 0 && ox == 0);
+                        for (int q = lo; q < hi; q++) {
+                            const float4 fj = cand[q];
+                            const float dx = fi.x - fj.x, dy = fi.y - fj.y, dz = fi.z - fj.z;
+                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            if (r2 > P.fcut_hi) continue;
+                            const int j = q + jb;
+                            if (j == s) continue;
+                            int code = code_c;
+                            bool ok = true;
+                            if (r2 >= P.fcut_lo) ok = pair_exact(xs[s], xs[j], P, code);      // inside the error band
+                            if (ok && P.opt == SEPGPU_EXCL_SAME_MOL) {
+                                const int mol_j = __float_as_int(fj.w);
+                                if (!(mol_i == -1 || mol_i != mol_j)) ok = false;             // :673-674
+                            } else if (ok && P.opt == SEPGPU_EXCL_BONDED) {
+                                if (i_orig < 0) i_orig = order[s];
+                                const int j_orig = order[j];
+                                if (share_tab(excl_bond, 10, i_orig, j_orig) + share_tab(excl_angle, 10, i_orig, j_orig) +
+                                    share_tab(excl_dihed, 20, i_orig, j_orig) != 0) ok = false;  // :583
+                            }
+                            if (!ok) continue;
+                            if (count < P.cap) nbr[(size_t)count * P.npad + s] = (unsigned)j | ((unsigned)code << SEPGPU_SHIFT_BITS);
+                            count++;
+                            half_count += (in_half || (same_cell && j > s)) ? 1 : 0;
+                        }
+                    }
+                }
+            }
+        }
+        if (active) {
+            cnt[s] = min(count, P.cap);
+            blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += count;
+        }
+    }
+    // block statistics: warp reduce, then three atomics per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        blk_max = max(blk_max, __shfl_xor_sync(0xffffffffu, blk_max, o));
+        blk_half = max(blk_half, __shfl_xor_sync(0xffffffffu, blk_half, o));
+        blk_sum += __shfl_xor_sync(0xffffffffu, blk_sum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&s_red[0], blk_max); atomicMax(&s_red[1], blk_half); atomicAdd(&s_red[2], blk_sum);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMax(&scal->max_neighb, s_red[0]);
+        atomicMax(&scal->max_half, s_red[1]);
+        atomicAdd((unsigned long long *)&scal->npairs_listed, (unsigned long long)s_red[2]);
+    }
+}
+
 __global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; s->neighb_flag = 0; }
 
@@ -298,9 +442,18 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         P.prefilter = c->prefilter && nx >= 4 && ny >= 4 && nz >= 4 && cut < 1.95 * wmin && band < 0.05 * P.cut2;
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
-        k_build_list<<<(c->n + BUILD_WARPS - 1) / BUILD_WARPS, BUILD_WARPS * 32, 0, c->stream>>>(
-            c->xs, c->xf, c->order, c->cell_of, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed,
-            c->nbr, c->cnt, c->scal, P);
+        if (P.prefilter) {
+            const int nseg = (nx + TILE_CX - 1) / TILE_CX;
+            k_build_tile<<<nseg * ny * nz, TILE_THREADS, 0, c->stream>>>(
+                c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed,
+                c->nbr, c->cnt, c->scal, P);
+        } else {
+            // small or degenerate grids (< 4 cells in a direction, oversized skin): exact FP64 test for
+            // every candidate, one warp per atom
+            k_build_list<<<(c->n + BUILD_WARPS - 1) / BUILD_WARPS, BUILD_WARPS * 32, 0, c->stream>>>(
+                c->xs, c->xf, c->order, c->cell_of, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed,
+                c->nbr, c->cnt, c->scal, P);
+        }
         k_build_end<<<1, 1, 0, c->stream>>>(c->scal);
         ktimer_end(c, &c->t_build);
         KERNEL_CHECK();
