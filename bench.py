@@ -239,6 +239,8 @@ def main():
     ap.add_argument("--rho", type=float, default=0.8)
     ap.add_argument("--skin", type=float, default=0.25)
     ap.add_argument("--tpa", type=int, default=0)
+    ap.add_argument("--unroll", type=int, default=0)
+    ap.add_argument("--force-grid", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-ncell", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true")
@@ -292,6 +294,10 @@ def main():
     s = capi.System(n, device=local_rank)
     if args.tpa:
         s.call("sepgpu_set_option", b"tpa", args.tpa)
+    if args.unroll:
+        s.call("sepgpu_set_option", b"unroll", args.unroll)
+    if args.force_grid:
+        s.call("sepgpu_set_option", b"force_grid", args.force_grid)
     s.put(capi.F_X, x)
     s.put(capi.F_V, v)
     s.call("sepgpu_set_alpha", 0, 0.1)

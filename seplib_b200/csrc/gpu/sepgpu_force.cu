@@ -104,7 +104,7 @@ __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, 
 // stay resident in its SM's L1 while it moves along the x-row of cells; list entries are streamed
 // (ld.global.cs) because they are never reused.  The inner loop is unrolled by two with both list
 // entries and both neighbour sectors requested before any arithmetic, to keep more gathers in flight.
-template <int TPA, bool TYPED, bool STORE>
+template <int TPA, bool TYPED, bool STORE, int UNROLL>
 __global__ void __launch_bounds__(FORCE_BLOCK)
 k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int atoms_per_cta,
@@ -133,6 +133,22 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
             }
             const unsigned *row = nbr + s;
             int k = sub;
+            if (UNROLL == 4) {
+                for (; k + 3 * TPA < m; k += 4 * TPA) {
+                    const unsigned e0 = __ldcs(row + (size_t)k * npad);
+                    const unsigned e1 = __ldcs(row + (size_t)(k + TPA) * npad);
+                    const unsigned e2 = __ldcs(row + (size_t)(k + 2 * TPA) * npad);
+                    const unsigned e3 = __ldcs(row + (size_t)(k + 3 * TPA) * npad);
+                    const d4 p0 = xs[e0 & SEPGPU_INDEX_MASK];
+                    const d4 p1 = xs[e1 & SEPGPU_INDEX_MASK];
+                    const d4 p2 = xs[e2 & SEPGPU_INDEX_MASK];
+                    const d4 p3 = xs[e3 & SEPGPU_INDEX_MASK];
+                    lj_pair<TYPED>(pi, p0, e0, ti, P, B, A);
+                    lj_pair<TYPED>(pi, p1, e1, ti, P, B, A);
+                    lj_pair<TYPED>(pi, p2, e2, ti, P, B, A);
+                    lj_pair<TYPED>(pi, p3, e3, ti, P, B, A);
+                }
+            }
             for (; k + TPA < m; k += 2 * TPA) {
                 const unsigned e0 = __ldcs(row + (size_t)k * npad);
                 const unsigned e1 = __ldcs(row + (size_t)(k + TPA) * npad);
@@ -305,18 +321,25 @@ static LJDev make_lj(const sepgpu_ljparam *p, const char types[2])
     return d;
 }
 
-template <int TPA>
-static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
+template <int TPA, int UNROLL>
+static void launch_lj_list_u(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
 {
 #define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial
     if (typed) {
-        if (store) k_lj_list<TPA, true, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
-        else       k_lj_list<TPA, true, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        if (store) k_lj_list<TPA, true, true, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        else       k_lj_list<TPA, true, false, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
     } else {
-        if (store) k_lj_list<TPA, false, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
-        else       k_lj_list<TPA, false, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        if (store) k_lj_list<TPA, false, true, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        else       k_lj_list<TPA, false, false, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
     }
 #undef LJ_ARGS
+}
+
+template <int TPA>
+static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
+{
+    if (c->unroll == 4) launch_lj_list_u<TPA, 4>(c, grid, apc, typed, store, P, B);
+    else launch_lj_list_u<TPA, 2>(c, grid, apc, typed, store, P, B);
 }
 
 extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2],
@@ -352,7 +375,7 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     const int tpa = c->tpa;
     // contiguous ranges of the sorted atoms per CTA; several CTAs per SM, a few waves for load balance
     const int groups = FORCE_BLOCK / tpa;
-    int grid = FORCE_MAX_GRID;
+    int grid = c->force_grid > 0 ? c->force_grid : FORCE_MAX_GRID;
     int apc = (c->n + grid - 1) / grid;
     apc = ((apc + groups - 1) / groups) * groups;
     if (apc < groups) apc = groups;

@@ -132,6 +132,8 @@ struct sepgpu_ctx {
     // options
     int tpa;                     // lanes per atom in list force kernels
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
+    int unroll;                  // gathers in flight per lane in the list force kernel (2 or 4)
+    int force_grid;              // CTAs of the list force kernel (0 = default)
 
     // measurement
     cudaEvent_t ev0, ev1;

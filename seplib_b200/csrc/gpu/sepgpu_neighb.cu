@@ -1,12 +1,13 @@
-// sepgpu_neighb.cu -- GPU cell binning + warp-cooperative Verlet-list build.
+// sepgpu_neighb.cu -- GPU cell binning + Verlet-list build.
 //
 // Stands in for sep_make_celllist + sep_make_neighblist_from_llist{,_nonbonded,_excl_same_mol}
 // (reference source/sepprfrc.c:394-415, 419-513, 517-603, 606-700).  The reference walks a linked
 // cell list serially and stores each pair once (half list); here
 //   1. atoms are binned with the reference's exact FP64 expression (int)(x/lsubbox) and
-//      counting-sorted by cell (ascending atom index inside a cell => deterministic),
-//   2. one warp per atom sweeps the 27 surrounding cells of the sorted array and compacts the
-//      accepted partners with ballot/popc into a transposed FULL list.
+//      counting-sorted by cell; inside a cell the order is ascending atom index (deterministic),
+//      and cells are laid out brick-major (bricks of BX x 4 x 4 cells, x fastest inside a brick) so
+//      that atoms close in space are close in memory in all three directions,
+//   2. a tiled kernel sweeps the 27 surrounding cells and writes a transposed FULL list.
 // Acceptance reproduces the reference bit for bit: r2 = ((0+dx*dx)+dy*dy)+dz*dz from wrapped
 // positions with the sep_Wrap branches, no FMA contraction, r2 < (cf+skin)^2.  r2 is symmetric in
 // (i,j) bit for bit, so the full list is exactly the reference's half list read both ways.
@@ -15,62 +16,116 @@
 #include "sepgpu_internal.cuh"
 
 #define BUILD_WARPS 8
+#define BRICK_YZ 4
+
+struct CellGrid {
+    int nx, ny, nz;         // reference cell grid (sys->nsubbox)
+    int bx;                 // brick extent along x (1,2,4,8); y and z extents are BRICK_YZ
+    int nbx, nby, nbz;      // bricks per direction
+};
+
+__host__ __device__ __forceinline__ int cell_key(int cx, int cy, int cz, const CellGrid &G)
+{
+    const int bxi = cx / G.bx, lx = cx % G.bx;
+    const int byi = cy / BRICK_YZ, ly = cy % BRICK_YZ;
+    const int bzi = cz / BRICK_YZ, lz = cz % BRICK_YZ;
+    return (((bzi * G.nby + byi) * G.nbx + bxi) * (BRICK_YZ * BRICK_YZ) + lz * BRICK_YZ + ly) * G.bx + lx;
+}
+
+__host__ __device__ __forceinline__ void key_cell(int key, const CellGrid &G, int &cx, int &cy, int &cz)
+{
+    const int lx = key % G.bx; key /= G.bx;
+    const int ly = key % BRICK_YZ; key /= BRICK_YZ;
+    const int lz = key % BRICK_YZ; key /= BRICK_YZ;
+    const int bxi = key % G.nbx; key /= G.nbx;
+    const int byi = key % G.nby; const int bzi = key / G.nby;
+    cx = bxi * G.bx + lx; cy = byi * BRICK_YZ + ly; cz = bzi * BRICK_YZ + lz;
+}
 
 // ---- binning ------------------------------------------------------------------------------------------
 __global__ void k_cell_count(const d4 *__restrict__ x4, int n, double lsx, double lsy, double lsz,
-                             int nx, int ny, int nz, int *__restrict__ cell_of,
-                             int *__restrict__ cell_cnt, DevScalars *scal)
+                             CellGrid G, int *__restrict__ cell_of, int *__restrict__ cell_cnt, DevScalars *scal)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     d4 p = x4[i];
     // source/sepprfrc.c:404-406, IEEE division then truncation
     int cx = (int)__ddiv_rn(p.x, lsx), cy = (int)__ddiv_rn(p.y, lsy), cz = (int)__ddiv_rn(p.z, lsz);
-    if (cx < 0 || cx >= nx || cy < 0 || cy >= ny || cz < 0 || cz >= nz || !(p.x == p.x)) {
+    if (cx < 0 || cx >= G.nx || cy < 0 || cy >= G.ny || cz < 0 || cz >= G.nz || !(p.x == p.x)) {
         scal->error = SEPGPU_ECELL;
-        cx = min(max(cx, 0), nx - 1); cy = min(max(cy, 0), ny - 1); cz = min(max(cz, 0), nz - 1);
+        cx = min(max(cx, 0), G.nx - 1); cy = min(max(cy, 0), G.ny - 1); cz = min(max(cz, 0), G.nz - 1);
     }
-    int c = cx + cy * nx + cz * nx * ny;
-    cell_of[i] = c;
-    atomicAdd(&cell_cnt[c], 1);
+    const int key = cell_key(cx, cy, cz, G);
+    cell_of[i] = key;
+    atomicAdd(&cell_cnt[key], 1);
 }
 
-// single-block exclusive scan over the cells; also clears the counters for the scatter pass
-__global__ void __launch_bounds__(1024) k_cell_scan(int *__restrict__ cell_cnt, int *__restrict__ cell_start, int ncell)
+// three-kernel exclusive scan over the cell counters (also clears them for the scatter pass)
+#define SCAN_BLOCK 1024
+#define SCAN_ITEMS 2
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_local(int *__restrict__ cnt, int *__restrict__ start, int *__restrict__ block_sum, int ncell)
 {
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int base = (blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+    int v[SCAN_ITEMS], tot = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) { v[q] = base + q < ncell ? cnt[base + q] : 0; tot += v[q]; }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        wsum[lane] = wi - w;
+        if (lane == 31) block_sum[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    int run = wsum[wid] + incl - tot;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++)
+        if (base + q < ncell) { start[base + q] = run; run += v[q]; cnt[base + q] = 0; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks(int *__restrict__ block_sum, int nblocks)
+{
+    // single block: exclusive scan of up to 1024*k block totals
     __shared__ int wsum[32];
     __shared__ int carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < ncell; base += 1024) {
-        int idx = base + threadIdx.x;
-        int v = idx < ncell ? cell_cnt[idx] : 0;
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < nblocks ? block_sum[idx] : 0;
         int incl = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         if (lane == 31) wsum[wid] = incl;
         __syncthreads();
         if (wid == 0) {
             int w = wsum[lane], wi = w;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
             wsum[lane] = wi - w;
         }
         __syncthreads();
-        int excl = carry + wsum[wid] + incl - v;
-        if (idx < ncell) { cell_start[idx] = excl; cell_cnt[idx] = 0; }
+        const int excl = carry + wsum[wid] + incl - v;
+        if (idx < nblocks) block_sum[idx] = excl;
         __syncthreads();
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) cell_start[ncell] = carry;
+}
+
+__global__ void k_scan_apply(int *__restrict__ start, const int *__restrict__ block_sum, int ncell, int n)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < ncell) start[idx] += block_sum[idx / (SCAN_BLOCK * SCAN_ITEMS)];
+    if (idx == 0) start[ncell] = n;
 }
 
 __global__ void k_cell_scatter(const int *__restrict__ cell_of, int n, const int *__restrict__ cell_start,
@@ -119,7 +174,7 @@ struct BuildParams {
     double Lx, Ly, Lz;
     double cut2;
     float fLx, fLy, fLz, fcut_lo, fcut_hi;
-    int nx, ny, nz;
+    CellGrid G;
     int n, npad, cap;
     unsigned opt;
     int prefilter;
@@ -138,6 +193,21 @@ __device__ __forceinline__ bool pair_exact(const d4 &a, const d4 &b, const Build
     return r2 < P.cut2;
 }
 
+template <unsigned OPT>
+__device__ __forceinline__ bool excluded(int mol_i, int mol_j, int s, int j, const int *__restrict__ order,
+                                         const int *__restrict__ eb, const int *__restrict__ ea,
+                                         const int *__restrict__ ed)
+{
+    if (OPT == SEPGPU_EXCL_SAME_MOL) return !(mol_i == -1 || mol_i != mol_j);                      // :673-674
+    if (OPT == SEPGPU_EXCL_BONDED) {
+        const int io = order[s], jo = order[j];
+        return share_tab(eb, 10, io, jo) + share_tab(ea, 10, io, jo) + share_tab(ed, 20, io, jo) != 0;   // :583
+    }
+    return false;
+}
+
+// ---- exact fallback: one warp per atom, FP64 test for every candidate -------------------------------------
+// Used for small or degenerate grids (< 4 cells in a direction, skin enlarged past the cell width).
 __global__ void __launch_bounds__(BUILD_WARPS * 32)
 k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int *__restrict__ order,
              const int *__restrict__ cell_of, const int *__restrict__ cell_start,
@@ -149,65 +219,38 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
     const int s = blockIdx.x * BUILD_WARPS + (threadIdx.x >> 5);
     if (s >= P.n) return;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const CellGrid G = P.G;
 
     const int i_orig = order[s];
-    const int c = cell_of[i_orig];
-    const int cx = c % P.nx, cy = (c / P.nx) % P.ny, cz = c / (P.nx * P.ny);
+    int cx, cy, cz;
+    key_cell(cell_of[i_orig], G, cx, cy, cz);
     const d4 pi = xs[s];
-    const float4 fi = xf[s];
-    const int mol_i = __float_as_int(fi.w);
+    const int mol_i = tag_mol(pi.w);
 
     int count = 0, half_count = 0;
 
     for (int oz = -1; oz <= 1; oz++) {
-        int mz = cz + oz; int wz = 0;
-        if (mz == P.nz) { mz = 0; wz = 1; } else if (mz == -1) { mz = P.nz - 1; wz = -1; }
+        int mz = cz + oz;
+        if (mz == G.nz) mz = 0; else if (mz == -1) mz = G.nz - 1;
         for (int oy = -1; oy <= 1; oy++) {
-            int my = cy + oy; int wy = 0;
-            if (my == P.ny) { my = 0; wy = 1; } else if (my == -1) { my = P.ny - 1; wy = -1; }
+            int my = cy + oy;
+            if (my == G.ny) my = 0; else if (my == -1) my = G.ny - 1;
             for (int ox = -1; ox <= 1; ox++) {
-                int mx = cx + ox; int wx = 0;
-                if (mx == P.nx) { mx = 0; wx = 1; } else if (mx == -1) { mx = P.nx - 1; wx = -1; }
-                const int m2 = mx + my * P.nx + mz * P.nx * P.ny;
+                int mx = cx + ox;
+                if (mx == G.nx) mx = 0; else if (mx == -1) mx = G.nx - 1;
+                const int m2 = cell_key(mx, my, mz, G);
                 const int jb = cell_start[m2], je = cell_start[m2 + 1];
                 // reference half-stencil membership (source/sepprfrc.c:424-426), for the half-list length
                 const bool in_half = (oz == 1) || (oz == 0 && (oy == 1 || (oy == 0 && ox == 1)));
                 const bool same_cell = (ox == 0 && oy == 0 && oz == 0);
-                // image of the candidate cell relative to the home atom: x_i - x_j is shifted by +w*L
-                const float sxf = fi.x - wx * P.fLx, syf = fi.y - wy * P.fLy, szf = fi.z - wz * P.fLz;
-                const int cell_code = (wx + 1) + 3 * (wy + 1) + 9 * (wz + 1);
-
                 for (int j0 = jb; j0 < je; j0 += 32) {
                     const int j = j0 + lane;
-                    bool ok = false; int code = cell_code; int j_orig = -1;
+                    bool ok = false; int code = 13;
                     if (j < je && j != s) {
-                        bool need_exact = !P.prefilter;
-                        if (P.prefilter) {
-                            const float4 fj = xf[j];
-                            const float dx = sxf - fj.x, dy = syf - fj.y, dz = szf - fj.z;
-                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            if (r2 < P.fcut_lo) ok = true;
-                            else if (r2 <= P.fcut_hi) need_exact = true;
-                            if (ok && P.opt == SEPGPU_EXCL_SAME_MOL) {
-                                const int mol_j = __float_as_int(fj.w);
-                                if (!(mol_i == -1 || mol_i != mol_j)) ok = false;   // :673-674
-                            }
-                        }
-                        if (need_exact) {
-                            const d4 pj = xs[j];
-                            ok = pair_exact(pi, pj, P, code);
-                            if (ok && P.opt == SEPGPU_EXCL_SAME_MOL) {
-                                const int mol_j = tag_mol(pj.w);
-                                if (!(mol_i == -1 || mol_i != mol_j)) ok = false;
-                            }
-                        }
-                        if (ok && P.opt == SEPGPU_EXCL_BONDED) {
-                            j_orig = order[j];
-                            const int b = share_tab(excl_bond, 10, i_orig, j_orig) +
-                                          share_tab(excl_angle, 10, i_orig, j_orig) +
-                                          share_tab(excl_dihed, 20, i_orig, j_orig);
-                            if (b != 0) ok = false;                                  // :583
-                        }
+                        const d4 pj = xs[j];
+                        ok = pair_exact(pi, pj, P, code);
+                        if (ok && P.opt == SEPGPU_EXCL_SAME_MOL) ok = !excluded<SEPGPU_EXCL_SAME_MOL>(mol_i, tag_mol(pj.w), s, j, order, excl_bond, excl_angle, excl_dihed);
+                        if (ok && P.opt == SEPGPU_EXCL_BONDED) ok = !excluded<SEPGPU_EXCL_BONDED>(0, 0, s, j, order, excl_bond, excl_angle, excl_dihed);
                     }
                     const unsigned mask = __ballot_sync(0xffffffffu, ok);
                     if (ok) {
@@ -234,40 +277,45 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 }
 
 // ---- tiled build: the fast path ------------------------------------------------------------------------------
-// One CTA owns TILE_CX consecutive home cells of one x-row (their atoms are contiguous in the sorted
-// array) and one THREAD owns one home atom.  For each of the 9 (dy,dz) rows the TILE_CX+2 candidate
-// cells are staged once into shared memory as FP32 positions already shifted to the right periodic
-// image; a thread then sweeps the 3 cells around its own cell.  Compared with one warp per atom this
-// reads every candidate once per CTA instead of once per atom and keeps all 32 lanes busy on different
-// atoms.  Candidates inside the FP32 error band of the cutoff take the exact FP64 test (pair_exact).
-#define TILE_CX 4
-#define TILE_THREADS 128
-#define TILE_STAGE 1024
+// One CTA owns one x-run of a brick (G.bx consecutive home cells of one x-row; their atoms are
+// contiguous in the sorted array) and one THREAD owns one home atom.  For each of the 9 (dy,dz) rows
+// the G.bx+2 candidate cells are staged once into shared memory as FP32 positions already shifted to
+// the right periodic image, with the finished list entry (sorted index | image code) in .w; a thread
+// then sweeps the 3 cells around its own cell in two passes: a branch-free pass that tests 32
+// candidates into a bit mask, and a pass over the set bits that appends entries.  Every candidate is
+// read from HBM once per CTA instead of once per atom and all lanes work on different atoms.
+// Candidates inside the FP32 error band of the cutoff take the exact FP64 test (pair_exact).
+#define TILE_MAXCX 8
+#define TILE_THREADS 160
+#define TILE_STAGE 768
+#define TILE_PAD 32
 
+template <unsigned OPT>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int *__restrict__ order,
              const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
              const int *__restrict__ excl_angle, const int *__restrict__ excl_dihed,
              unsigned *__restrict__ nbr, int *__restrict__ cnt, DevScalars *scal, BuildParams P)
 {
-    __shared__ float4 cand[TILE_STAGE];
-    __shared__ int s_off[TILE_CX + 3];      // staged offset of candidate cell cc (cc = 0..ncx+1), +1 end marker
-    __shared__ int s_jbase[TILE_CX + 2];    // sorted index of a candidate = staged position + s_jbase[cc]
-    __shared__ int s_wx[TILE_CX + 2];       // x image of candidate cell cc
-    __shared__ int s_home[TILE_CX + 1];     // sorted-index boundaries of the home cells
+    __shared__ float4 cand[TILE_STAGE + TILE_PAD];
+    __shared__ int cand_mol[OPT == SEPGPU_EXCL_SAME_MOL ? TILE_STAGE + TILE_PAD : 1];
+    __shared__ int s_off[TILE_MAXCX + 3];      // staged offset of candidate cell cc (cc = 0..ncx+1), +1 end marker
+    __shared__ int s_jbase[TILE_MAXCX + 2];    // sorted index of a candidate = staged position + s_jbase[cc]
+    __shared__ int s_wx[TILE_MAXCX + 2];       // x image of candidate cell cc
+    __shared__ int s_home[TILE_MAXCX + 1];     // sorted-index boundaries of the home cells
     __shared__ int s_red[3];
 
-    const int nseg = (P.nx + TILE_CX - 1) / TILE_CX;
-    const int seg = blockIdx.x % nseg;
-    const int cy = (blockIdx.x / nseg) % P.ny;
-    const int cz = blockIdx.x / (nseg * P.ny);
-    const int x0 = seg * TILE_CX;
-    const int ncx = min(TILE_CX, P.nx - x0);
-    const int row_home = (cy + cz * P.ny) * P.nx;
-    if (threadIdx.x <= ncx) s_home[threadIdx.x] = cell_start[row_home + x0 + threadIdx.x];
+    const CellGrid G = P.G;
+    int x0, cy, cz;
+    key_cell(blockIdx.x * G.bx, G, x0, cy, cz);
+    if (x0 >= G.nx || cy >= G.ny || cz >= G.nz) return;          // padding of the brick grid
+    const int ncx = min(G.bx, G.nx - x0);
+    const int key0 = blockIdx.x * G.bx;
+    if (threadIdx.x <= ncx) s_home[threadIdx.x] = cell_start[key0 + threadIdx.x];
     if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
     __syncthreads();
     const int a0 = s_home[0], nhome = s_home[ncx] - a0;
+    if (nhome == 0) return;
     int blk_max = 0, blk_half = 0, blk_sum = 0;
 
     for (int ab = 0; ab < nhome; ab += TILE_THREADS) {
@@ -281,23 +329,30 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
         }
         const int mol_i = __float_as_int(fi.w);
         int count = 0, half_count = 0;
-        int i_orig = -1;
+        unsigned *out = nbr + s;
 
         for (int r = 0; r < 9; r++) {
             const int oy = r % 3 - 1, oz = r / 3 - 1;
             int my = cy + oy, wy = 0, mz = cz + oz, wz = 0;
-            if (my == P.ny) { my = 0; wy = 1; } else if (my == -1) { my = P.ny - 1; wy = -1; }
-            if (mz == P.nz) { mz = 0; wz = 1; } else if (mz == -1) { mz = P.nz - 1; wz = -1; }
-            const int row = (my + mz * P.ny) * P.nx;
+            if (my == G.ny) { my = 0; wy = 1; } else if (my == -1) { my = G.ny - 1; wy = -1; }
+            if (mz == G.nz) { mz = 0; wz = 1; } else if (mz == -1) { mz = G.nz - 1; wz = -1; }
             __syncthreads();                         // previous row fully consumed
+            if (threadIdx.x < ncx + 2) {
+                const int cc = threadIdx.x;
+                int mx = x0 - 1 + cc, wx = 0;
+                if (mx >= G.nx) { mx -= G.nx; wx = 1; } else if (mx < 0) { mx += G.nx; wx = -1; }
+                const int key = cell_key(mx, my, mz, G);
+                s_jbase[cc] = cell_start[key];           // temporarily: begin
+                s_off[cc] = cell_start[key + 1] - s_jbase[cc];   // temporarily: length
+                s_wx[cc] = wx;
+            }
+            __syncthreads();
             if (threadIdx.x == 0) {
                 int off = 0;
                 for (int cc = 0; cc < ncx + 2; cc++) {
-                    int mx = x0 - 1 + cc, wx = 0;
-                    if (mx >= P.nx) { mx -= P.nx; wx = 1; } else if (mx < 0) { mx += P.nx; wx = -1; }
-                    const int b = cell_start[row + mx], e = cell_start[row + mx + 1];
-                    s_off[cc] = off; s_jbase[cc] = b - off; s_wx[cc] = wx;
-                    off += e - b;
+                    const int len = s_off[cc];
+                    s_off[cc] = off; s_jbase[cc] -= off;
+                    off += len;
                 }
                 s_off[ncx + 2] = off;
             }
@@ -305,51 +360,67 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             const int total = s_off[ncx + 2];
             const float shy = wy * P.fLy, shz = wz * P.fLz;
             const bool half_row = (oz == 1) || (oz == 0 && oy == 1);
-            const int code_yz = 3 * (wy + 1) + 9 * (wz + 1);
+            const bool centre_row = (oz == 0 && oy == 0);
+            const unsigned code_yz = 3u * (wy + 1) + 9u * (wz + 1);
 
             for (int base = 0; base < total; base += TILE_STAGE) {
                 const int lim = min(total - base, TILE_STAGE);
                 if (base > 0) __syncthreads();
-                for (int q = threadIdx.x; q < lim; q += TILE_THREADS) {
-                    const int g = base + q;
-                    int cc = 0;
-                    for (int t = 1; t < ncx + 2; t++) cc += (g >= s_off[t]);
-                    float4 f = xf[g + s_jbase[cc]];
-                    f.x += s_wx[cc] * P.fLx; f.y += shy; f.z += shz;
+                for (int q = threadIdx.x; q < lim + TILE_PAD; q += TILE_THREADS) {
+                    float4 f = make_float4(1e18f, 1e18f, 1e18f, 0.f);         // padding: never in range
+                    if (q < lim) {
+                        const int g = base + q;
+                        int cc = 0;
+                        for (int t = 1; t < ncx + 2; t++) cc += (g >= s_off[t]);
+                        const int j = g + s_jbase[cc];
+                        f = xf[j];
+                        if (OPT == SEPGPU_EXCL_SAME_MOL) cand_mol[q] = __float_as_int(f.w);
+                        f.x += s_wx[cc] * P.fLx; f.y += shy; f.z += shz;
+                        f.w = __uint_as_float((unsigned)j | (((unsigned)(s_wx[cc] + 1) + code_yz) << SEPGPU_SHIFT_BITS));
+                    }
                     cand[q] = f;
                 }
                 __syncthreads();
                 if (active) {
-                    for (int cc = h; cc < h + 3; cc++) {
-                        const int lo = max(s_off[cc], base) - base, hi = min(s_off[cc + 1], base + lim) - base;
-                        const int jb = s_jbase[cc] + base;
-                        const int code_c = (s_wx[cc] + 1) + code_yz;
-                        const int ox = cc - 1 - h;
-                        const bool in_half = half_row || (oz == 0 && oy == 0 && ox == 1);
-                        const bool same_cell = (oz == 0 && oy == 0 && ox == 0);
-                        for (int q = lo; q < hi; q++) {
-                            const float4 fj = cand[q];
+                    // my window: candidate cells h, h+1, h+2 -- contiguous in the staged row
+                    const int wlo = max(s_off[h], base) - base, whi = min(s_off[h + 3], base + lim) - base;
+                    // positions that split the window for the reference half-list count
+                    const int cut_a = min(max(s_off[h + 1] - base, wlo), whi);      // start of my own cell (ox = 0)
+                    const int cut_b = min(max(s_off[h + 2] - base, wlo), whi);      // start of cell ox = +1
+                    const int self_q = (centre_row ? s - s_jbase[h + 1] : -1) - base; // my own staged position
+                    for (int q0 = wlo; q0 < whi; q0 += 32) {
+                        unsigned mask = 0, band = 0;
+#pragma unroll
+                        for (int b = 0; b < 32; b++) {
+                            const float4 fj = cand[q0 + b];
                             const float dx = fi.x - fj.x, dy = fi.y - fj.y, dz = fi.z - fj.z;
                             const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            if (r2 > P.fcut_hi) continue;
-                            const int j = q + jb;
-                            if (j == s) continue;
-                            int code = code_c;
-                            bool ok = true;
-                            if (r2 >= P.fcut_lo) ok = pair_exact(xs[s], xs[j], P, code);      // inside the error band
-                            if (ok && P.opt == SEPGPU_EXCL_SAME_MOL) {
-                                const int mol_j = __float_as_int(fj.w);
-                                if (!(mol_i == -1 || mol_i != mol_j)) ok = false;             // :673-674
-                            } else if (ok && P.opt == SEPGPU_EXCL_BONDED) {
-                                if (i_orig < 0) i_orig = order[s];
-                                const int j_orig = order[j];
-                                if (share_tab(excl_bond, 10, i_orig, j_orig) + share_tab(excl_angle, 10, i_orig, j_orig) +
-                                    share_tab(excl_dihed, 20, i_orig, j_orig) != 0) ok = false;  // :583
+                            if (r2 <= P.fcut_hi) mask |= 1u << b;
+                            if (r2 >= P.fcut_lo) band |= 1u << b;
+                        }
+                        const int nvalid = whi - q0;
+                        if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+                        if ((unsigned)(self_q - q0) < 32u) mask &= ~(1u << (self_q - q0));
+                        band &= mask;
+                        while (mask) {
+                            const int b = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int q = q0 + b;
+                            unsigned entry = __float_as_uint(cand[q].w);
+                            const int j = (int)(entry & SEPGPU_INDEX_MASK);
+                            if ((band >> b) & 1u) {                                   // inside the FP32 error band
+                                int code;
+                                if (!pair_exact(xs[s], xs[j], P, code)) continue;
+                                entry = (unsigned)j | ((unsigned)code << SEPGPU_SHIFT_BITS);
                             }
-                            if (!ok) continue;
-                            if (count < P.cap) nbr[(size_t)count * P.npad + s] = (unsigned)j | ((unsigned)code << SEPGPU_SHIFT_BITS);
+                            if (OPT != SEPGPU_ALL &&
+                                excluded<OPT>(mol_i, OPT == SEPGPU_EXCL_SAME_MOL ? cand_mol[q] : 0, s, j, order,
+                                              excl_bond, excl_angle, excl_dihed)) continue;
+                            if (count < P.cap) out[(size_t)count * P.npad] = entry;
                             count++;
-                            half_count += (in_half || (same_cell && j > s)) ? 1 : 0;
+                            // reference half list: cells of the half stencil, or my own cell with j2 > j1
+                            const bool in_half = half_row || (centre_row && (q >= cut_b || (q >= cut_a && j > s)));
+                            half_count += in_half ? 1 : 0;
                         }
                     }
                 }
@@ -360,7 +431,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += count;
         }
     }
-    // block statistics: warp reduce, then three atomics per warp
+    // block statistics: warp reduce, then shared atomics, then three global atomics per CTA
     for (int o = 16; o > 0; o >>= 1) {
         blk_max = max(blk_max, __shfl_xor_sync(0xffffffffu, blk_max, o));
         blk_half = max(blk_half, __shfl_xor_sync(0xffffffffu, blk_half, o));
@@ -378,7 +449,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 }
 
 __global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; }
-__global__ void k_build_end(DevScalars *s) { s->nbuild += 1; s->neighb_flag = 0; }
+__global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
 static int estimate_cap(const sepgpu_ctx *c, const sepgpu_sys *sys)
 {
@@ -396,42 +467,55 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
     CUDA_TRY(cudaSetDevice(c->device));
     const int nx = sys->nsubbox[0], ny = sys->nsubbox[1], nz = sys->nsubbox[2];
     if (nx < 1 || ny < 1 || nz < 1) { sepgpu_set_error("neighb_build: empty cell grid"); return SEPGPU_EINVAL; }
+    if (opt < SEPGPU_ALL || opt > SEPGPU_EXCL_SAME_MOL) { sepgpu_set_error("neighb_build: bad opt %u", opt); return SEPGPU_EINVAL; }
     if (opt == SEPGPU_EXCL_BONDED && !c->have_excl) {
         sepgpu_set_error("neighb_build: SEP_EXCL_BONDED needs the bond/angle/dihed partner tables");
         return SEPGPU_ESTATE;
     }
-    const long long ncell_ll = (long long)nx * ny * nz;
-    if (ncell_ll > (1LL << 30)) { sepgpu_set_error("neighb_build: too many cells"); return SEPGPU_EINVAL; }
-    const int ncell = (int)ncell_ll;
-    if (ncell > c->ncell_cap) {
+    CellGrid G;
+    G.nx = nx; G.ny = ny; G.nz = nz;
+    // brick x-extent: as many cells as keep one x-run of home atoms within one pass of the tile kernel
+    const double mean_per_cell = (double)c->n / ((double)nx * ny * nz);
+    G.bx = 1;
+    while (G.bx < TILE_MAXCX && 2 * G.bx * mean_per_cell <= 0.9 * TILE_THREADS && 2 * G.bx <= nx) G.bx *= 2;
+    G.nbx = (nx + G.bx - 1) / G.bx; G.nby = (ny + BRICK_YZ - 1) / BRICK_YZ; G.nbz = (nz + BRICK_YZ - 1) / BRICK_YZ;
+    const long long nkey_ll = (long long)G.nbx * G.nby * G.nbz * G.bx * BRICK_YZ * BRICK_YZ;
+    if (nkey_ll > (1LL << 30)) { sepgpu_set_error("neighb_build: too many cells"); return SEPGPU_EINVAL; }
+    const int nkey = (int)nkey_ll;
+    const int scan_blocks = (nkey + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    if (nkey > c->ncell_cap) {
         if (c->cell_cnt) cudaFree(c->cell_cnt);
         if (c->cell_start) cudaFree(c->cell_start);
         c->cell_cnt = c->cell_start = NULL;
-        CUDA_TRY(cudaMalloc((void **)&c->cell_cnt, sizeof(int) * ((size_t)ncell + 1)));
-        CUDA_TRY(cudaMalloc((void **)&c->cell_start, sizeof(int) * ((size_t)ncell + 1)));
-        c->ncell_cap = ncell;
+        // cell_cnt doubles as scratch for the scan's block totals (stored after the counters)
+        CUDA_TRY(cudaMalloc((void **)&c->cell_cnt, sizeof(int) * ((size_t)nkey + 1 + scan_blocks + 1024)));
+        CUDA_TRY(cudaMalloc((void **)&c->cell_start, sizeof(int) * ((size_t)nkey + 1)));
+        c->ncell_cap = nkey;
     }
+    int *block_sum = c->cell_cnt + nkey + 1;
     if (c->cap == 0) c->cap = estimate_cap(c, sys);
 
-    const int B = 256, G = (c->n + B - 1) / B;
+    const int B = 256, Gn = (c->n + B - 1) / B;
     for (int attempt = 0; attempt < 6; attempt++) {
         if (!c->nbr) CUDA_TRY(cudaMalloc((void **)&c->nbr, sizeof(unsigned) * (size_t)c->cap * c->npad));
 
         ktimer_begin(c, &c->t_build);
-        CUDA_TRY(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * ((size_t)ncell + 1), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * ((size_t)nkey + 1), c->stream));
         k_build_begin<<<1, 1, 0, c->stream>>>(c->scal);
-        k_cell_count<<<G, B, 0, c->stream>>>(c->x4, c->n, sys->lsubbox[0], sys->lsubbox[1], sys->lsubbox[2],
-                                             nx, ny, nz, c->cell_of, c->cell_cnt, c->scal);
-        k_cell_scan<<<1, 1024, 0, c->stream>>>(c->cell_cnt, c->cell_start, ncell);
-        k_cell_scatter<<<G, B, 0, c->stream>>>(c->cell_of, c->n, c->cell_start, c->cell_cnt, c->tmp_slot);
-        k_cell_finalize<<<G, B, 0, c->stream>>>(c->tmp_slot, c->cell_of, c->cell_start, c->x4, c->n,
-                                                c->order, c->rank, c->xs, c->xf, c->cr4);
+        k_cell_count<<<Gn, B, 0, c->stream>>>(c->x4, c->n, sys->lsubbox[0], sys->lsubbox[1], sys->lsubbox[2],
+                                              G, c->cell_of, c->cell_cnt, c->scal);
+        k_scan_local<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->cell_cnt, c->cell_start, block_sum, nkey);
+        k_scan_blocks<<<1, 1024, 0, c->stream>>>(block_sum, scan_blocks);
+        k_scan_apply<<<(nkey + 255) / 256, 256, 0, c->stream>>>(c->cell_start, block_sum, nkey, c->n);
+        k_cell_scatter<<<Gn, B, 0, c->stream>>>(c->cell_of, c->n, c->cell_start, c->cell_cnt, c->tmp_slot);
+        k_cell_finalize<<<Gn, B, 0, c->stream>>>(c->tmp_slot, c->cell_of, c->cell_start, c->x4, c->n,
+                                                 c->order, c->rank, c->xs, c->xf, c->cr4);
         BuildParams P;
         P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
         const double cut = sys->cf + sys->skin;
         P.cut2 = cut * cut;                              // sep_Sq(sys->cf + sys->skin), :432
         P.fLx = (float)P.Lx; P.fLy = (float)P.Ly; P.fLz = (float)P.Lz;
-        P.nx = nx; P.ny = ny; P.nz = nz;
+        P.G = G;
         P.n = c->n; P.npad = c->npad; P.cap = c->cap; P.opt = opt;
         // FP32 prefilter: |r2_f32 - r2_exact| <= 2*sqrt(3)*cut * 4*Lmax*2^-24 (+ accumulation rounding);
         // the band below is 5x that bound.  It also needs cell image == minimum image, which holds when
@@ -443,13 +527,13 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
         if (P.prefilter) {
-            const int nseg = (nx + TILE_CX - 1) / TILE_CX;
-            k_build_tile<<<nseg * ny * nz, TILE_THREADS, 0, c->stream>>>(
-                c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed,
-                c->nbr, c->cnt, c->scal, P);
+            const int grid = nkey / G.bx;
+#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P
+            if (opt == SEPGPU_ALL) k_build_tile<SEPGPU_ALL><<<grid, TILE_THREADS, 0, c->stream>>>(TILE_ARGS);
+            else if (opt == SEPGPU_EXCL_SAME_MOL) k_build_tile<SEPGPU_EXCL_SAME_MOL><<<grid, TILE_THREADS, 0, c->stream>>>(TILE_ARGS);
+            else k_build_tile<SEPGPU_EXCL_BONDED><<<grid, TILE_THREADS, 0, c->stream>>>(TILE_ARGS);
+#undef TILE_ARGS
         } else {
-            // small or degenerate grids (< 4 cells in a direction, oversized skin): exact FP64 test for
-            // every candidate, one warp per atom
             k_build_list<<<(c->n + BUILD_WARPS - 1) / BUILD_WARPS, BUILD_WARPS * 32, 0, c->stream>>>(
                 c->xs, c->xf, c->order, c->cell_of, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed,
                 c->nbr, c->cnt, c->scal, P);
@@ -471,6 +555,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         }
         if (c->scal_host->max_neighb <= c->cap) {
             c->list_valid = true; c->list_opt = opt; c->sorted_identity = false; c->xs_current = true;
+            c->zs_valid = false;
             c->grid_n[0] = nx; c->grid_n[1] = ny; c->grid_n[2] = nz;
             return 0;
         }

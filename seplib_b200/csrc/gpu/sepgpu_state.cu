@@ -73,6 +73,7 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->pending_alpha_type = -1;
     c->tpa = 4;
     c->prefilter = 1;
+    c->unroll = 2;
     c->single_type = 'A';
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
@@ -505,6 +506,8 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
         return 0;
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
+    if (!strcmp(name, "unroll")) { c->unroll = value == 4 ? 4 : 2; return 0; }
+    if (!strcmp(name, "force_grid")) { c->force_grid = value > 0 && value <= SEPGPU_MAX_BLOCKS_PARTIAL ? (int)value : 0; return 0; }
     if (!strcmp(name, "time_kernels")) {
         if (value) { if (ktimer_enable(&c->t_force) || ktimer_enable(&c->t_build) || ktimer_enable(&c->t_intgr)) return SEPGPU_ECUDA; }
         return 0;
