@@ -19,7 +19,7 @@
 #include <math.h>
 
 #define FORCE_BLOCK 128
-#define FORCE_MAX_GRID (148 * 16)
+#define FORCE_MAX_GRID (148 * 64)
 
 struct LJDev {
     double cf2, sig2, eps48, eps4, aw, awh, shift;
@@ -73,6 +73,10 @@ struct PairAcc {
     int nin;
 };
 
+// One listed pair, branch-free: out-of-range (or wrong-type) pairs run the same arithmetic with the
+// force factor selected to zero.  In a warp some lane is almost always in range, so the branchy form
+// executes the full block anyway; without the branch the compiler can interleave the dependent DFMA
+// chains of two pairs.  r2 of a real pair is finite and non-zero, so the masked values stay finite.
 template <bool TYPED>
 __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, int ti, const LJDev &P,
                                         const BoxDev &B, PairAcc &A)
@@ -86,24 +90,25 @@ __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, 
         const int tj = tag_type(pj.w);
         in = in && ((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0));   // source/sepprfrc.c:171-172
     }
-    if (in) {
-        const double rri = P.sig2 * fast_rcp(r2);
-        const double rri3 = rri * rri * rri;
-        const double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;   // source/sepmisc.c:139, sepprfrc.c:888
-        const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
-        A.fx += gx; A.fy += gy; A.fz += gz;
-        A.u = fma(rri3, rri3 - P.aw, A.u);                         // u/(4 eps) before the shift
-        A.nin++;
-        A.vxx = fma(gx, dx, A.vxx); A.vxy = fma(gx, dy, A.vxy); A.vxz = fma(gx, dz, A.vxz);
-        A.vyy = fma(gy, dy, A.vyy); A.vyz = fma(gy, dz, A.vyz); A.vzz = fma(gz, dz, A.vzz);
-    }
+    const double rri = P.sig2 * fast_rcp(r2);
+    double rri3 = rri * rri * rri;
+    double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;             // source/sepmisc.c:139, sepprfrc.c:888
+    const double uu = rri3 - P.aw;
+    ft = in ? ft : 0.0;
+    rri3 = in ? rri3 : 0.0;
+    const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
+    A.fx += gx; A.fy += gy; A.fz += gz;
+    A.u = fma(rri3, uu, A.u);                                      // u/(4 eps) before the shift
+    A.nin += in ? 1 : 0;
+    A.vxx = fma(gx, dx, A.vxx); A.vxy = fma(gx, dy, A.vxy); A.vxz = fma(gx, dz, A.vxz);
+    A.vyy = fma(gy, dy, A.vyy); A.vyz = fma(gy, dz, A.vyz); A.vzz = fma(gz, dz, A.vzz);
 }
 
 // STORE: first force kernel after sep_reset_force -> plain store instead of read-modify-write.
 // Each CTA walks a CONTIGUOUS range of the cell-sorted atoms so that the neighbour rows it gathers
-// stay resident in its SM's L1 while it moves along the x-row of cells; list entries are streamed
-// (ld.global.cs) because they are never reused.  The inner loop is unrolled by two with both list
-// entries and both neighbour sectors requested before any arithmetic, to keep more gathers in flight.
+// stay resident in its SM's L1.  A lane reads its next FOUR list entries with one streaming 128-bit
+// load (ld.global.cs: never reused) issued one chunk ahead of use -- the list comes from HBM and was
+// the dominant stall -- and then gathers the four neighbour sectors two at a time.
 template <int TPA, bool TYPED, bool STORE, int UNROLL>
 __global__ void __launch_bounds__(FORCE_BLOCK)
 k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
@@ -118,6 +123,7 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
     A.nin = 0;
     const int first = blockIdx.x * atoms_per_cta;
     const int last = min(n, first + atoms_per_cta);
+    const uint4 *nbrv = reinterpret_cast<const uint4 *>(nbr);
 
     for (int s0 = first; s0 < last; s0 += GROUPS) {
         const int s = s0 + threadIdx.x / TPA;
@@ -131,36 +137,32 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
                 ti = tag_type(pi.w);
                 if (ti != P.t0 && ti != P.t1) m = 0;             // source/sepprfrc.c:164-165
             }
-            const unsigned *row = nbr + s;
-            int k = sub;
-            if (UNROLL == 4) {
-                for (; k + 3 * TPA < m; k += 4 * TPA) {
-                    const unsigned e0 = __ldcs(row + (size_t)k * npad);
-                    const unsigned e1 = __ldcs(row + (size_t)(k + TPA) * npad);
-                    const unsigned e2 = __ldcs(row + (size_t)(k + 2 * TPA) * npad);
-                    const unsigned e3 = __ldcs(row + (size_t)(k + 3 * TPA) * npad);
-                    const d4 p0 = xs[e0 & SEPGPU_INDEX_MASK];
-                    const d4 p1 = xs[e1 & SEPGPU_INDEX_MASK];
-                    const d4 p2 = xs[e2 & SEPGPU_INDEX_MASK];
-                    const d4 p3 = xs[e3 & SEPGPU_INDEX_MASK];
-                    lj_pair<TYPED>(pi, p0, e0, ti, P, B, A);
-                    lj_pair<TYPED>(pi, p1, e1, ti, P, B, A);
-                    lj_pair<TYPED>(pi, p2, e2, ti, P, B, A);
-                    lj_pair<TYPED>(pi, p3, e3, ti, P, B, A);
+            const int nch = (m + 3) >> 2;
+            const uint4 *row = nbrv + s;
+            int c = sub;
+            uint4 cur = make_uint4(0, 0, 0, 0);
+            if (c < nch) cur = __ldcs(row + (size_t)c * npad);
+            while (c < nch) {
+                const int cn = c + TPA;
+                uint4 nxt = make_uint4(0, 0, 0, 0);
+                if (cn < nch) nxt = __ldcs(row + (size_t)cn * npad);
+                const int left = m - 4 * c;                      // >= 1 valid entries in this chunk
+                {
+                    const bool v1 = left > 1;
+                    const d4 p0 = xs[cur.x & SEPGPU_INDEX_MASK];
+                    const d4 p1 = xs[v1 ? (cur.y & SEPGPU_INDEX_MASK) : (unsigned)s];
+                    lj_pair<TYPED>(pi, p0, cur.x, ti, P, B, A);
+                    if (v1) lj_pair<TYPED>(pi, p1, cur.y, ti, P, B, A);
                 }
-            }
-            for (; k + TPA < m; k += 2 * TPA) {
-                const unsigned e0 = __ldcs(row + (size_t)k * npad);
-                const unsigned e1 = __ldcs(row + (size_t)(k + TPA) * npad);
-                const d4 p0 = xs[e0 & SEPGPU_INDEX_MASK];
-                const d4 p1 = xs[e1 & SEPGPU_INDEX_MASK];
-                lj_pair<TYPED>(pi, p0, e0, ti, P, B, A);
-                lj_pair<TYPED>(pi, p1, e1, ti, P, B, A);
-            }
-            if (k < m) {
-                const unsigned e0 = __ldcs(row + (size_t)k * npad);
-                const d4 p0 = xs[e0 & SEPGPU_INDEX_MASK];
-                lj_pair<TYPED>(pi, p0, e0, ti, P, B, A);
+                if (left > 2) {
+                    const bool v3 = left > 3;
+                    const d4 p2 = xs[cur.z & SEPGPU_INDEX_MASK];
+                    const d4 p3 = xs[v3 ? (cur.w & SEPGPU_INDEX_MASK) : (unsigned)s];
+                    lj_pair<TYPED>(pi, p2, cur.z, ti, P, B, A);
+                    if (v3) lj_pair<TYPED>(pi, p3, cur.w, ti, P, B, A);
+                }
+                cur = nxt;
+                c = cn;
             }
         }
         // butterfly over the TPA lanes of this atom

@@ -65,10 +65,9 @@ k_coulomb_list(const d4 *__restrict__ xs, const double *__restrict__ zs, const u
             const d4 pi = xs[s];
             const double zi = zs[s];
             const int m = cnt[s];
-            const unsigned *row = nbr + s;
 #pragma unroll 2
             for (int k = sub; k < m; k += TPA) {
-                const unsigned e = row[(size_t)k * npad];
+                const unsigned e = nbr[nbr_index(k, s, npad)];
                 const int j = (int)(e & SEPGPU_INDEX_MASK);
                 const d4 pj = xs[j];
                 const double zj = zs[j];
@@ -283,7 +282,7 @@ k_dpd(const d4 *__restrict__ xs, const d4 *__restrict__ x4, const d4 *__restrict
             for (int k = 0; k < m; k++) {
                 int j, jo; d4 pj; double dx, dy, dz;
                 if (MODE == 0) {
-                    const unsigned e = nbr[(size_t)k * npad + s];
+                    const unsigned e = nbr[nbr_index(k, s, npad)];
                     j = (int)(e & SEPGPU_INDEX_MASK); jo = order[j]; pj = xs[j];
                     dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
                     const int code = (int)(e >> SEPGPU_SHIFT_BITS);

@@ -14,8 +14,9 @@
 //     xs[s]  = {xu, yu, zu, tag}    xu = x + (crossings since list build)*L : continuous between
 //                                   rebuilds, so the image shift stored with a list entry stays valid
 //     order[s] = i, rank[i] = s
-//   Verlet list: FULL list (i->j and j->i), transposed so a warp reads 128 contiguous bytes:
-//     nbr[k*npad + s] = j_sorted | shift_code << 26,   cnt[s]
+//   Verlet list: FULL list (i->j and j->i), transposed in chunks of 4 entries so that a lane reads its
+//   next four entries with one 128-bit load and a warp reads 512 contiguous bytes:
+//     nbr[((k/4)*npad + s)*4 + k%4] = j_sorted | shift_code << 26,   cnt[s]
 //
 // Reference counterparts are cited at each kernel.
 #pragma once
@@ -162,6 +163,12 @@ __device__ __forceinline__ double make_tag(int type, int molindex)
 {
     long long b = (long long)(type & 0xff) | ((long long)(unsigned)(molindex + 1) << 8);
     return __longlong_as_double(b);
+}
+
+// position of entry k of sorted atom s in the chunked, transposed neighbour array
+__host__ __device__ __forceinline__ size_t nbr_index(int k, int s, int npad)
+{
+    return ((size_t)(k >> 2) * npad + s) * 4 + (k & 3);
 }
 
 // sep_Wrap (include/sepmisc.h:81-85), exact branch form

@@ -255,7 +255,7 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                     const unsigned mask = __ballot_sync(0xffffffffu, ok);
                     if (ok) {
                         const int pos = count + __popc(mask & lt_mask);
-                        if (pos < P.cap) nbr[(size_t)pos * P.npad + s] = (unsigned)j | ((unsigned)code << SEPGPU_SHIFT_BITS);
+                        if (pos < P.cap) nbr[nbr_index(pos, s, P.npad)] = (unsigned)j | ((unsigned)code << SEPGPU_SHIFT_BITS);
                     }
                     count += __popc(mask);
                     if (in_half) half_count += __popc(mask);
@@ -329,7 +329,6 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
         }
         const int mol_i = __float_as_int(fi.w);
         int count = 0, half_count = 0;
-        unsigned *out = nbr + s;
 
         for (int r = 0; r < 9; r++) {
             const int oy = r % 3 - 1, oz = r / 3 - 1;
@@ -416,7 +415,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                             if (OPT != SEPGPU_ALL &&
                                 excluded<OPT>(mol_i, OPT == SEPGPU_EXCL_SAME_MOL ? cand_mol[q] : 0, s, j, order,
                                               excl_bond, excl_angle, excl_dihed)) continue;
-                            if (count < P.cap) out[(size_t)count * P.npad] = entry;
+                            if (count < P.cap) nbr[nbr_index(count, s, P.npad)] = entry;
                             count++;
                             // reference half list: cells of the half stencil, or my own cell with j2 > j1
                             const bool in_half = half_row || (centre_row && (q >= cut_b || (q >= cut_a && j > s)));
@@ -579,7 +578,7 @@ __global__ void k_export_pairs(const unsigned *__restrict__ nbr, const int *__re
     const int i = order[s];
     const int m = cnt[s];
     for (int k = 0; k < m; k++) {
-        const int j = order[nbr[(size_t)k * npad + s] & SEPGPU_INDEX_MASK];
+        const int j = order[nbr[nbr_index(k, s, npad)] & SEPGPU_INDEX_MASK];
         if (i < j) {
             unsigned long long p = atomicAdd(counter, 1ULL);
             if ((long long)p < max_pairs) { out[2 * p] = i; out[2 * p + 1] = j; }

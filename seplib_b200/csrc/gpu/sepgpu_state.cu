@@ -71,7 +71,7 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->device = device;
     c->pending_alpha_slot = -1;
     c->pending_alpha_type = -1;
-    c->tpa = 4;
+    c->tpa = 1;
     c->prefilter = 1;
     c->unroll = 2;
     c->single_type = 'A';
@@ -502,7 +502,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     if (!strcmp(name, "tpa")) {
         if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32 && value != 0)
             return SEPGPU_EINVAL;
-        c->tpa = value ? (int)value : 4;
+        c->tpa = value ? (int)value : 1;
         return 0;
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
