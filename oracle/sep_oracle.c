@@ -117,6 +117,21 @@ long orc_neighb_pairs(int n, const double *x, const double len[3], const int nsu
             }
         }
     }
+    /* The reference keeps the pairs in per-atom rows ptr[j1].neighb[] and its force loops walk the atoms
+     * in index order (source/sepprfrc.c:161-170): regroup by j1 (stable) so that a consumer of this
+     * pair array adds forces in exactly the reference's order. */
+    if (!status && np > 0) {
+        long *start = calloc((size_t)n + 1, sizeof(long));
+        int *tmp = malloc(sizeof(int) * 2 * (size_t)np);
+        for (long p = 0; p < np; p++) start[pairs[2 * p] + 1]++;
+        for (int i = 0; i < n; i++) start[i + 1] += start[i];
+        for (long p = 0; p < np; p++) {
+            const long q = start[pairs[2 * p]]++;
+            tmp[2 * q] = pairs[2 * p]; tmp[2 * q + 1] = pairs[2 * p + 1];
+        }
+        memcpy(pairs, tmp, sizeof(int) * 2 * (size_t)np);
+        free(start); free(tmp);
+    }
     free(head); free(next); free(count);
     return status ? status : np;
 }

@@ -249,3 +249,98 @@ def rel_force_err(f, fref):
     d = np.linalg.norm(f - fref, axis=1).max()
     frms = np.sqrt((fref * fref).sum(axis=1).mean())
     return d / max(frms, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# driving the compiled reference (or our libsep.so: same ABI) through the seplib API
+# ---------------------------------------------------------------------------------------------------
+class ApiSystem:
+    """A seplib system (sep_init + sep_sys_setup) on `lib`, with numpy views of the host seppart array."""
+
+    def __init__(self, lib, x, L, cf, dt, update=capi.SEP_LLIST_NEIGHBLIST, v=None, types=None, m=None, z=None,
+                 nneighb=3000):
+        self.lib = lib
+        self.n = len(x)
+        length = [L] * 3 if np.isscalar(L) else list(L)
+        self.atoms = lib.sep_init(self.n, nneighb)
+        self.sys = lib.sep_sys_setup(length[0], length[1], length[2], cf, dt, self.n, update)
+        self.ret = capi.SepRet()
+        self.view = capi.atoms_view(self.atoms, self.n)
+        self.view["x"][:] = x
+        self.view["xn"][:] = 0.0
+        self.view["pa"][:] = 0.0
+        self.view["pv"][:] = 0.0
+        if v is not None:
+            self.view["v"][:] = v
+        if types is not None:
+            self.view["type"][:] = types
+        if m is not None:
+            self.view["m"][:] = m
+        if z is not None:
+            self.view["z"][:] = z
+        self.closed = False
+
+    @classmethod
+    def from_xyz(cls, lib, xyz, top, cf, dt, update):
+        self = cls.__new__(cls)
+        self.lib = lib
+        lbox = (C.c_double * 3)()
+        npart = C.c_int()
+        self.atoms = lib.sep_init_xyz(lbox, C.byref(npart), xyz.encode(), b"q")
+        self.n = npart.value
+        self.sys = lib.sep_sys_setup(lbox[0], lbox[1], lbox[2], cf, dt, self.n, update)
+        self.ret = capi.SepRet()
+        self.view = capi.atoms_view(self.atoms, self.n)
+        self.view["xn"][:] = 0.0
+        if top:
+            lib.sep_read_topology_file(self.atoms, top.encode(), C.byref(self.sys), b"q")
+        self.closed = False
+        return self
+
+    # shorthand
+    @property
+    def S(self):
+        return C.byref(self.sys)
+
+    @property
+    def R(self):
+        return C.byref(self.ret)
+
+    def fun(self, name):
+        return C.cast(getattr(self.lib, name), C.c_void_p)
+
+    def neighb_pairs(self):
+        """Half list as stored in ptr[i].neighb (reference only: our library does not fill host rows)."""
+        out = []
+        for i in range(self.n):
+            row = self.atoms[i].neighb
+            k = 0
+            while row[k] != -1:
+                out.append((i, row[k]))
+                k += 1
+        return np.array(out, dtype=np.int32).reshape(-1, 2)
+
+    def topo(self):
+        t = Topo(self.n)
+        t.molindex[:] = self.view["molindex"]
+        t.bond[:] = self.view["bond"]
+        t.angle[:] = self.view["angle"]
+        t.dihed[:] = self.view["dihed"]
+        mp = self.sys.molptr.contents
+        if mp.flag_bonds:
+            t.blist = np.ctypeslib.as_array(mp.blist, shape=(mp.num_bonds, 3)).copy() if mp.num_bonds else t.blist
+        if mp.flag_angles and mp.num_angles:
+            t.alist = np.ctypeslib.as_array(mp.alist, shape=(mp.num_angles, 4)).copy()
+        if mp.flag_dihedrals and mp.num_dihedrals:
+            t.dlist = np.ctypeslib.as_array(mp.dlist, shape=(mp.num_dihedrals, 5)).copy()
+        return t
+
+    def ret_arrays(self):
+        r = self.ret
+        return dict(epot=r.epot, ecoul=r.ecoul, ekin=r.ekin, pot_P=np.array(r.pot_P).reshape(9).copy(),
+                    kin_P=np.array(r.kin_P).reshape(9).copy(), pot_P_bond=np.array(r.pot_P_bond).reshape(9).copy())
+
+    def close(self):
+        if not self.closed:
+            self.lib.sep_close(self.atoms, self.n)
+            self.closed = True

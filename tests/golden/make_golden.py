@@ -1,0 +1,232 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the REFERENCE itself (oracle/_ref/libsep_ref.so, compiled from the
+unmodified sources under /root/reference with -O2 -fno-fast-math -ffp-contract=off).
+
+Run in the build container only (needs /root/reference for the molecular start files):
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Each fixture stores an evolved (thermalised) state -- not a copy of any reference file -- and what the
+reference computes from it: the neighbour pair set read from ptr[i].neighb, forces after each force
+routine, the sepret sums, and the state after sep_nosehoover + sep_leapfrog.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import common as cm  # noqa: E402
+from seplib_b200 import capi  # noqa: E402
+
+REFROOT = "/root/reference"
+
+
+def snap_state(s):
+    v = s.view
+    return dict(x=v["x"].copy(), v=v["v"].copy(), f=v["f"].copy(), xn=v["xn"].copy(),
+                cross_neighb=v["cross_neighb"].copy(), crossings=v["crossings"].copy())
+
+
+def lj_fixture(lib):
+    """prg1/prg4-style LJ: 1000 atoms, rho 0.8, rc 2.5, NH; 150 reference steps to leave the lattice."""
+    x, L = cm.lattice(10, 0.8)
+    v = cm.velocities(len(x), 1.2, seed=77)
+    cf, dt, skin, temp, tau = 2.5, 0.005, 0.25, 1.2, 0.1
+    s = cm.ApiSystem(lib, x, L, cf, dt, v=v)
+    alpha = C.c_double(0.1)
+    fun = s.fun("sep_lj_shift")
+    for _ in range(150):
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+        lib.sep_nosehoover(s.atoms, temp, C.byref(alpha), tau, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+    out = dict(L=L, cf=cf, dt=dt, skin=skin, temp=temp, tau=tau, alpha0=alpha.value)
+    st = snap_state(s)
+    out.update({"x0": st["x"], "v0": st["v"], "xn0": st["xn"], "cn0": st["cross_neighb"], "cr0": st["crossings"],
+                "neighb_flag0": s.sys.neighb_flag})
+    # one fully recorded step, list rebuilt first
+    s.sys.neighb_flag = 1
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+    out["pairs"] = cm.pair_set(s.neighb_pairs()).astype(np.int32)
+    out["f_pairs"] = s.view["f"].copy()
+    r = s.ret_arrays(); out["epot"] = r["epot"]; out["pot_P"] = r["pot_P"]
+    lib.sep_nosehoover(s.atoms, temp, C.byref(alpha), tau, s.S)
+    out["f_nh"] = s.view["f"].copy(); out["alpha1"] = alpha.value
+    lib.sep_leapfrog(s.atoms, s.S, s.R)
+    st = snap_state(s)
+    out.update({"x1": st["x"], "v1": st["v"], "xn1": st["xn"], "cn1": st["cross_neighb"], "cr1": st["crossings"]})
+    r = s.ret_arrays(); out["ekin"] = r["ekin"]; out["kin_P"] = r["kin_P"]
+    out["max_dist2"] = s.sys.max_dist2; out["neighb_flag1"] = s.sys.neighb_flag
+    # 40 more steps: aggregate trajectory
+    traj = []
+    for _ in range(40):
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+        lib.sep_nosehoover(s.atoms, temp, C.byref(alpha), tau, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+        lib.sep_pressure_tensor(s.R, s.S)
+        traj.append([s.ret.epot, s.ret.ekin, s.ret.p, alpha.value, s.sys.nupdate_neighb])
+    out["traj"] = np.array(traj)
+    out["x41"] = s.view["x"].copy()
+    # the sep_force_lj variant and the other pair functions on the x0 state
+    s2 = cm.ApiSystem(lib, out["x0"], L, cf, dt, v=out["v0"])
+    for name, fn in (("lj", "sep_lj"), ("wca", "sep_wca")):
+        lib.sep_reset_retval(s2.R); lib.sep_reset_force(s2.atoms, s2.S)
+        rc = 2.5 if name == "lj" else 2.0 ** (1.0 / 6.0)
+        lib.sep_force_pairs(s2.atoms, b"AA", rc, s2.fun(fn), s2.S, s2.R, 1)
+        out[f"f_{name}"] = s2.view["f"].copy(); out[f"epot_{name}"] = s2.ret.epot
+        out[f"pot_P_{name}"] = s2.ret_arrays()["pot_P"]
+    par = (C.c_double * 4)(2.2, 0.8, 1.05, 0.7)
+    lib.sep_reset_retval(s2.R); lib.sep_reset_force(s2.atoms, s2.S)
+    lib.sep_force_lj(s2.atoms, b"AA", par, s2.S, s2.R, 1)
+    out["ljparam"] = np.array(par[:]); out["f_ljparam"] = s2.view["f"].copy(); out["epot_ljparam"] = s2.ret.epot
+    s.close(); s2.close()
+    np.savez_compressed(os.path.join(HERE, "lj_n1000.npz"), **out)
+    print("lj_n1000: pairs", len(out["pairs"]), "epot/N", out["epot"] / 1000)
+
+
+def butane_fixture(lib):
+    """prg2's system (4000 united atoms, 1000 butane chains), evolved 60 steps; every force routine recorded."""
+    cf, dt, temp = 2.5, 0.001, 4.0
+    rb = (C.c_double * 6)(15.5000, 20.3050, -21.9170, -5.1150, 43.8340, -52.6070)
+    s = cm.ApiSystem.from_xyz(lib, f"{REFROOT}/test/prg1.xyz", f"{REFROOT}/test/prg1.top", cf, dt, capi.SEP_LLIST_NEIGHBLIST)
+    alpha = C.c_double(0.1)
+    fun = s.fun("sep_lj_shift")
+
+    def forces():
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"CC", cf, fun, s.S, s.R, 3)
+        lib.sep_stretch_harmonic(s.atoms, 0, 0.407, 2074.0, s.S, s.R)
+        lib.sep_angle_harmonic(s.atoms, 0, 1.90, 400.0, s.S, s.R)
+        lib.sep_torsion_Ryckaert(s.atoms, 0, rb, s.S, s.R)
+
+    for _ in range(60):
+        forces()
+        lib.sep_nosehoover(s.atoms, temp, C.byref(alpha), 0.1, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+    out = dict(L=np.array(s.sys.length[:]), cf=cf, dt=dt, temp=temp, rb=np.array(rb[:]), alpha0=alpha.value)
+    st = snap_state(s)
+    out.update({"x0": st["x"], "v0": st["v"], "xn0": st["xn"], "cn0": st["cross_neighb"], "cr0": st["crossings"]})
+    t = s.topo()
+    out.update(molindex=t.molindex, bond=t.bond, angle=t.angle, dihed=t.dihed, blist=t.blist, alist=t.alist, dlist=t.dlist)
+    mp = s.sys.molptr.contents
+    s.sys.neighb_flag = 1
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_force_pairs(s.atoms, b"CC", cf, fun, s.S, s.R, 3)
+    out["pairs_same_mol"] = cm.pair_set(s.neighb_pairs()).astype(np.int32)
+    out["f_lj"] = s.view["f"].copy(); out["epot_lj"] = s.ret.epot; out["pot_P_lj"] = s.ret_arrays()["pot_P"]
+    lib.sep_stretch_harmonic(s.atoms, 0, 0.407, 2074.0, s.S, s.R)
+    out["f_bond"] = s.view["f"].copy(); out["epot_bond"] = s.ret.epot
+    r = s.ret_arrays(); out["pot_P_bond_total"] = r["pot_P"]; out["pot_P_bond"] = r["pot_P_bond"]
+    out["blengths"] = np.ctypeslib.as_array(mp.blengths, shape=(mp.num_bonds,)).copy()
+    lib.sep_angle_harmonic(s.atoms, 0, 1.90, 400.0, s.S, s.R)
+    out["f_angle"] = s.view["f"].copy(); out["epot_angle"] = s.ret.epot
+    out["angles"] = np.ctypeslib.as_array(mp.angles, shape=(mp.num_angles,)).copy()
+    lib.sep_torsion_Ryckaert(s.atoms, 0, rb, s.S, s.R)
+    out["f_torsion"] = s.view["f"].copy(); out["epot_torsion"] = s.ret.epot
+    out["dihedrals"] = np.ctypeslib.as_array(mp.dihedrals, shape=(mp.num_dihedrals,)).copy()
+    lib.sep_nosehoover(s.atoms, temp, C.byref(alpha), 0.1, s.S)
+    lib.sep_leapfrog(s.atoms, s.S, s.R)
+    st = snap_state(s)
+    out.update({"x1": st["x"], "v1": st["v"], "alpha1": alpha.value, "ekin": s.ret.ekin})
+    # the bonded-exclusion list (bond+angle+dihedral partners) on the x0 state
+    s.view["x"][:] = out["x0"]
+    s.sys.neighb_flag = 1
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_force_pairs(s.atoms, b"CC", cf, fun, s.S, s.R, 2)
+    out["pairs_nonbonded"] = cm.pair_set(s.neighb_pairs()).astype(np.int32)
+    out["f_lj_nonbonded"] = s.view["f"].copy()
+    # cos^2 angle potential (prg3 uses it for water; recorded here on the chains as well)
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_angle_cossq(s.atoms, 0, 1.90, 400.0, s.S, s.R)
+    out["f_cossq"] = s.view["f"].copy(); out["epot_cossq"] = s.ret.epot
+    s.close()
+    np.savez_compressed(os.path.join(HERE, "butane_n4000.npz"), **out)
+    print("butane_n4000: pairs", len(out["pairs_same_mol"]), len(out["pairs_nonbonded"]), "epot/N", out["epot_torsion"] / 4000)
+
+
+def water_fixture(lib):
+    """prg3's system (648 atoms, SPC/Fw water, SEP_BRUTE): LJ OO + bonds + cos^2 angles + SF Coulomb."""
+    cf, dt, temp = 2.9, 5.0e-4, 3.81
+    s = cm.ApiSystem.from_xyz(lib, f"{REFROOT}/test/prg2.xyz", f"{REFROOT}/test/prg2.top", cf, dt, capi.SEP_BRUTE)
+    lib.sep_set_vel_seed(s.atoms, temp, 42, s.sys)
+    alpha = (C.c_double * 3)(0.1, 0.0, 0.0)
+    fun = s.fun("sep_lj_shift")
+
+    def forces():
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"OO", 2.5, fun, s.S, s.R, 3)
+        lib.sep_stretch_harmonic(s.atoms, 0, 0.316, 68421.0, s.S, s.R)
+        lib.sep_angle_cossq(s.atoms, 0, 1.97, 490.0, s.S, s.R)
+        lib.sep_coulomb_sf(s.atoms, cf, s.S, s.R, 3)
+
+    for _ in range(40):
+        forces()
+        lib.sep_nosehoover(s.atoms, temp, alpha, 0.01, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+    out = dict(L=np.array(s.sys.length[:]), cf=cf, dt=dt, temp=temp, alpha0=alpha[0])
+    st = snap_state(s)
+    out.update({"x0": st["x"], "v0": st["v"], "xn0": st["xn"], "cn0": st["cross_neighb"], "cr0": st["crossings"]})
+    out["type"] = s.view["type"].copy(); out["m"] = s.view["m"].copy(); out["z"] = s.view["z"].copy()
+    t = s.topo()
+    out.update(molindex=t.molindex, bond=t.bond, angle=t.angle, dihed=t.dihed, blist=t.blist, alist=t.alist, dlist=t.dlist)
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_force_pairs(s.atoms, b"OO", 2.5, fun, s.S, s.R, 3)
+    out["f_lj"] = s.view["f"].copy(); out["epot_lj"] = s.ret.epot; out["pot_P_lj"] = s.ret_arrays()["pot_P"]
+    lib.sep_stretch_harmonic(s.atoms, 0, 0.316, 68421.0, s.S, s.R)
+    out["f_bond"] = s.view["f"].copy(); out["epot_bond"] = s.ret.epot
+    lib.sep_angle_cossq(s.atoms, 0, 1.97, 490.0, s.S, s.R)
+    out["f_angle"] = s.view["f"].copy(); out["epot_angle"] = s.ret.epot
+    lib.sep_coulomb_sf(s.atoms, cf, s.S, s.R, 3)
+    out["f_coul"] = s.view["f"].copy(); out["epot_coul"] = s.ret.epot; out["ecoul"] = s.ret.ecoul
+    out["pot_P_total"] = s.ret_arrays()["pot_P"]
+    lib.sep_nosehoover(s.atoms, temp, alpha, 0.01, s.S)
+    lib.sep_leapfrog(s.atoms, s.S, s.R)
+    st = snap_state(s)
+    out.update({"x1": st["x"], "v1": st["v"], "alpha1": alpha[0], "ekin": s.ret.ekin})
+    # brute Coulomb with the bonded rule (the "== 1" quirk, source/sepcoulomb.c:37)
+    s.view["x"][:] = out["x0"]
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_coulomb_sf(s.atoms, cf, s.S, s.R, 2)
+    out["f_coul_bonded"] = s.view["f"].copy(); out["ecoul_bonded"] = s.ret.ecoul
+    s.close()
+    np.savez_compressed(os.path.join(HERE, "water_n648.npz"), **out)
+    print("water_n648: epot/mol", out["epot_coul"] / 216, "ecoul", out["ecoul"])
+
+
+def dpd_fixture(lib):
+    """sep_verlet_dpd only (the force's glibc rand() stream is not reproducible in parallel): two calls."""
+    x, L = cm.lattice(8, 3.0, jitter=0.3, seed=5)
+    n = len(x)
+    rng = np.random.default_rng(9)
+    v = cm.velocities(n, 1.0, seed=6)
+    s = cm.ApiSystem(lib, x, L, 1.0, 0.02, v=v)
+    out = dict(L=L, dt=0.02, x0=x, v0=v)
+    for step in range(2):
+        f = rng.normal(size=(n, 3)) * 5.0
+        s.view["f"][:] = f
+        s.sys.max_dist2 = 0.0
+        s.sys.neighb_flag = 0           # record whether THIS call fired the trigger
+        lib.sep_reset_retval(s.R)
+        lib.sep_verlet_dpd(s.atoms, 0.5, step, s.S, s.R)
+        out[f"f{step}"] = f
+        out[f"x{step + 1}"] = s.view["x"].copy(); out[f"v{step + 1}"] = s.view["v"].copy()
+        out[f"pv{step + 1}"] = s.view["pv"].copy(); out[f"pa{step + 1}"] = s.view["pa"].copy()
+        out[f"ekin{step + 1}"] = s.ret.ekin; out[f"flag{step + 1}"] = s.sys.neighb_flag
+        out[f"cr{step + 1}"] = s.view["crossings"].copy()
+    s.close()
+    np.savez_compressed(os.path.join(HERE, "dpd_n512.npz"), **out)
+    print("dpd_n512 ok")
+
+
+if __name__ == "__main__":
+    lib = cm.ref()
+    if lib is None:
+        sys.exit("oracle/_ref/libsep_ref.so missing: run `make -C oracle ref` first")
+    lj_fixture(lib)
+    butane_fixture(lib)
+    water_fixture(lib)
+    dpd_fixture(lib)
