@@ -1,0 +1,256 @@
+"""GPU parity, part 2: list-mode shifted-force Coulomb, DPD pair force (counter-based noise shared with
+the oracle), per-type Nose-Hoover, momentum reset, box compression, edge cases, and the reference-facing
+sep_* API (host seppart[] buffers through libsep.so) against the reference's own golden trajectory."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import common as cm
+from seplib_b200 import capi
+
+pytestmark = pytest.mark.gpu
+FT = 1e-10
+
+
+def tiled_water(reps=2):
+    """golden water box (648 atoms) tiled reps^3 times so that the cell grid has >= 4 cells per side."""
+    g = np.load(os.path.join(cm.GOLDEN, "water_n648.npz"))
+    L0 = np.atleast_1d(g["L"]).astype(float)
+    n0 = len(g["x0"])
+    xs, ts, zs, ms, mols = [], [], [], [], []
+    k = 0
+    for iz in range(reps):
+        for iy in range(reps):
+            for ix in range(reps):
+                xs.append(g["x0"] + np.array([ix, iy, iz]) * L0)
+                ts.append(g["type"]); zs.append(g["z"]); ms.append(g["m"])
+                mols.append(g["molindex"] + k * (g["molindex"].max() + 1))
+                k += 1
+    x = np.ascontiguousarray(np.concatenate(xs))
+    return (x, np.concatenate(ts).astype(np.uint8), np.concatenate(zs), np.concatenate(ms),
+            np.concatenate(mols).astype(np.int32), L0 * reps, n0)
+
+
+def test_coulomb_list_matches_oracle():
+    """prg3-style water in list mode: sep_force_pairs('OO', EXCL_SAME_MOL) builds the list, sep_coulomb_sf
+    reuses it (reference source/sepcoulomb.c:8-16) with the full 2.9 cutoff."""
+    x, types, z, m, mol, L, _ = tiled_water(2)
+    n = len(x)
+    cf, skin = 2.9, 0.25
+    t = cm.Topo(n); t.molindex[:] = mol
+    pairs = np.ascontiguousarray(cm.oracle_pairs(x, L, cf, skin, opt=cm.EXCL_SAME_MOL, topo=t, max_pairs=4_000_000), dtype=np.int32)
+    orc = cm.oracle(); length = cm.dvec3(L)
+    fref = np.zeros((n, 3)); rref = cm.OrcRet()
+    orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pairs), len(pairs), b"OO", 2.5,
+                             cm.POT_LJ_SHIFT, None, cm.ptr(fref), C.byref(rref))
+    orc.orc_coulomb_sf_list(n, cm.ptr(x), cm.ptr(z), cm.ptr(length), cm.ptr(pairs), len(pairs), cf, cm.ptr(fref), C.byref(rref))
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_TYPE, types); s.put(capi.F_Z, z); s.put(capi.F_M, m); s.put(capi.F_MOLINDEX, mol)
+    sys_ = capi.make_sys(L, cf, 5e-4, skin=skin)
+    assert sys_.nsubbox[0] >= 4
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.EXCL_SAME_MOL)
+    assert np.array_equal(cm.pair_set(s.pairs(4_000_000)), cm.pair_set(pairs))
+    p = capi.lj_param(2.5, kind="lj_shift")
+    s.call("sepgpu_force_lj", C.byref(sys_), b"OO", C.byref(p), cm.EXCL_SAME_MOL, 1)
+    s.call("sepgpu_coulomb_sf", C.byref(sys_), cf, cm.EXCL_SAME_MOL)
+    f = s.get(capi.F_F); sc = s.scalars()
+    assert cm.rel_force_err(f, fref) <= FT
+    assert abs(sc.ecoul - rref.ecoul) <= FT * abs(rref.ecoul)
+    assert abs(sc.epot - rref.epot) <= FT * abs(rref.epot)
+    assert np.abs(np.array(sc.pot_P[:]) - np.array(rref.pot_P[:])).max() <= FT * np.abs(np.array(rref.pot_P[:])).max()
+    s.close()
+
+
+@pytest.mark.parametrize("mode", ["list", "brute"])
+def test_dpd_force_matches_oracle(mode):
+    """Groot-Warren DPD (prg6 parameters).  The pair noise is a counter-based generator keyed on
+    (seed, step, min(i,j), max(i,j)) implemented identically in the oracle, so forces agree to rounding;
+    parity with the reference's glibc rand() stream is statistical only."""
+    ncell = 12 if mode == "list" else 6
+    x, L = cm.lattice(ncell, 3.0, jitter=0.35, seed=13)
+    n = len(x)
+    pv = cm.velocities(n, 1.0, seed=14)
+    types = np.full(n, ord("A"), dtype=np.uint8)
+    cf, skin, dt, aij, temp, sigma = 1.0, 0.25, 0.02, 25.0, 1.0, 3.0
+    length = cm.dvec3([L] * 3)
+    if mode == "list":
+        pairs = cm.oracle_pairs(x, L, cf, skin)
+    else:
+        orc0 = cm.oracle(); buf = np.empty((n * n, 2), dtype=np.int32); tp = cm.OrcTopo()
+        k = orc0.orc_neighb_pairs_n2(n, cm.ptr(x), cm.ptr(length), cf, cm.ALL, C.byref(tp), cm.ptr(buf), n * n)
+        pairs = buf[:k]
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+    orc = cm.oracle()
+    fref = np.zeros((n, 3)); rref = cm.OrcRet()
+    orc.orc_dpd_force_list(n, cm.ptr(x), cm.ptr(pv), cm.ptr(types), cm.ptr(length), cm.ptr(pairs), len(pairs), b"AA",
+                           cf, aij, temp, sigma, dt, 1234, 7, cm.ptr(fref), C.byref(rref))
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_PV, pv)
+    sys_ = capi.make_sys([L] * 3, cf, dt, skin=skin,
+                         neighb_update=capi.SEP_LLIST_NEIGHBLIST if mode == "list" else capi.SEP_BRUTE)
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    s.call("sepgpu_force_dpd", C.byref(sys_), b"AA", cf, aij, temp, sigma, cm.ALL, 1234, 7)
+    f = s.get(capi.F_F); sc = s.scalars()
+    assert cm.rel_force_err(f, fref) <= 1e-9
+    assert abs(sc.epot - rref.epot) <= 1e-10 * abs(rref.epot)
+    assert np.abs(f.sum(axis=0)).max() <= 1e-8 * np.abs(f).sum()          # Newton's third law incl. the noise
+    s.close()
+
+
+def test_nosehoover_type_and_momentum_reset():
+    x, L = cm.lattice(8, 0.8, jitter=0.1, seed=3)
+    n = len(x)
+    rng = np.random.default_rng(4)
+    types = np.where(rng.random(n) < 0.5, ord("B"), ord("A")).astype(np.uint8)
+    m = np.where(types == ord("B"), 2.5, 1.0)
+    v = cm.velocities(n, 1.3, seed=5, m=m)
+    f0 = rng.normal(size=(n, 3))
+    orc = cm.oracle()
+    fref = f0.copy(); alpha = np.array([0.05, 0.07, 0.02])
+    orc.orc_nosehoover_type(n, cm.ptr(v), cm.ptr(m), cm.ptr(types), b"B", cm.ptr(fref), 1.1, cm.ptr(alpha), 10.0, 0.005)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_V, v); s.put(capi.F_TYPE, types); s.put(capi.F_M, m)
+    s.call("sepgpu_reset_force"); s.put(capi.F_F, f0)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    a3 = (C.c_double * 3)(0.05, 0.07, 0.02)
+    s.call("sepgpu_nosehoover_type", C.byref(sys_), b"B", 1.1, a3, 10.0)
+    assert np.abs(np.array(a3[:]) - alpha).max() <= 1e-13 * np.abs(alpha).max()
+    assert np.abs(s.get(capi.F_F) - fref).max() <= 1e-12 * np.abs(fref).max()
+    # sep_reset_momentum on one species (reference source/sepmisc.c:1173-1192)
+    s.call("sepgpu_reset_momentum", b"B")
+    vg = s.get(capi.F_V)
+    sel = types == ord("B")
+    vref = v.copy()
+    vref[sel] -= (v[sel] * m[sel, None]).sum(axis=0) / m[sel].sum()
+    assert np.abs(vg - vref).max() <= 1e-13
+    assert np.abs((vg[sel] * m[sel, None]).sum(axis=0)).max() <= 1e-10
+    s.close()
+
+
+def test_error_paths():
+    """Atom outside [0,L) -> the reference's 'Index larger than array length' class of error; bonded
+    exclusion without partner tables; list force without anything to build from is fine (auto build)."""
+    x, L = cm.lattice(8, 0.8, jitter=0.05, seed=1)
+    x[17, 0] = L * 1.5
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    rc = s.lib.sepgpu_neighb_build(s.ctx, C.byref(sys_), 1)
+    assert rc == -4                                                     # SEPGPU_ECELL
+    s.close()
+    x, L = cm.lattice(8, 0.8, jitter=0.05, seed=1)
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    assert s.lib.sepgpu_neighb_build(s.ctx, C.byref(sys_), cm.EXCL_BONDED) == -6     # SEPGPU_ESTATE
+    assert s.lib.sepgpu_coulomb_sf(s.ctx, C.byref(sys_), 2.5, 1) == -6               # no list yet
+    s.close()
+
+
+def test_small_grid_exact_fallback_and_capacity_growth():
+    """3 cells per side (prg1's own size) takes the exact warp-per-atom builder; a deliberately tiny
+    neighbour capacity must grow transparently."""
+    x, L = cm.lattice(9, 0.7, jitter=0.2, seed=8)           # L = 10.1 -> 3 cells of 3.38
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    s.call("sepgpu_set_option", b"neighb_cap", 8)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    assert sys_.nsubbox[0] == 3
+    s.call("sepgpu_neighb_build", C.byref(sys_), 1)
+    assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(cm.oracle_pairs(x, L, 2.5, 0.25)))
+    s.close()
+
+
+# ---- the reference-facing API: host seppart[] buffers through libsep.so -----------------------------------
+@pytest.mark.parametrize("sync", [1, 0])        # SEP_SYNC_STEP, SEP_SYNC_LAZY
+def test_sep_api_lj_loop_matches_reference_golden(sync):
+    """The prg1 loop written against include/sep.h, run through libsep.so on host buffers, reproduces the
+    reference's own recorded step (forces, positions, sepret, sys flags) and its 40-step trajectory."""
+    g = np.load(os.path.join(cm.GOLDEN, "lj_n1000.npz"))
+    lib = capi.load()
+    lib.sep_gpu_set_sync(sync)
+    L, cf, dt = float(g["L"]), float(g["cf"]), float(g["dt"])
+    s = cm.ApiSystem(lib, g["x0"], L, cf, dt, v=g["v0"], nneighb=0)
+    s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+    alpha = C.c_double(float(g["alpha0"]))
+    fun = s.fun("sep_lj_shift")
+    temp, tau = float(g["temp"]), float(g["tau"])
+
+    def step():
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+        lib.sep_nosehoover(s.atoms, temp, C.byref(alpha), tau, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+
+    step()
+    if sync == 0:
+        lib.sep_gpu_sync(s.atoms)
+    assert np.abs(s.view["x"] - g["x1"]).max() <= 1e-12 and np.abs(s.view["v"] - g["v1"]).max() <= 1e-12
+    assert cm.rel_force_err(s.view["f"], g["f_nh"]) <= FT
+    assert np.array_equal(s.view["crossings"], g["cr1"]) and np.array_equal(s.view["cross_neighb"], g["cn1"])
+    assert abs(alpha.value - float(g["alpha1"])) <= 1e-12 * abs(float(g["alpha1"]))
+    assert abs(s.ret.epot - float(g["epot"])) <= FT * abs(float(g["epot"]))
+    assert abs(s.ret.ekin - float(g["ekin"])) <= FT * float(g["ekin"])
+    assert int(s.sys.neighb_flag) == int(g["neighb_flag1"])
+    assert abs(s.sys.max_dist2 - float(g["max_dist2"])) <= 1e-12 * float(g["max_dist2"])
+    assert abs(s.sys.tnow - dt) <= 1e-15
+    nup0 = int(s.sys.nupdate_neighb)
+    traj = g["traj"]
+    for k in range(40):
+        step()
+        lib.sep_pressure_tensor(s.R, s.S)
+        tol = 1e-9 * (k + 2)
+        assert abs(s.ret.epot - traj[k, 0]) <= tol * abs(traj[k, 0])
+        assert abs(s.ret.ekin - traj[k, 1]) <= tol * abs(traj[k, 1])
+        assert abs(s.ret.p - traj[k, 2]) <= tol * max(abs(traj[k, 2]), 1.0)
+        assert abs(alpha.value - traj[k, 3]) <= tol * max(abs(traj[k, 3]), 1e-2)
+        if k == 0:
+            nup0 = int(s.sys.nupdate_neighb)
+    # list rebuild count over the last 39 steps equals the reference's
+    assert int(s.sys.nupdate_neighb) - nup0 == int(traj[-1, 4] - traj[0, 4])
+    mom = lib.sep_eval_mom(s.atoms, s.n)          # syncs atoms[] in lazy mode
+    assert abs(mom) < 1e-10
+    assert np.abs(s.view["x"] - g["x41"]).max() <= 1e-6
+    s.close()
+    lib.sep_gpu_set_sync(1)
+
+
+def test_sep_api_butane_and_water_steps():
+    """prg2 (butane, list mode, EXCL_SAME_MOL + bonded terms) and prg3 (water, SEP_BRUTE, SF Coulomb) force
+    sequences through the sep_* API on host buffers against the reference's recorded forces."""
+    lib = capi.load()
+    lib.sep_gpu_set_sync(1)
+    g = np.load(os.path.join(cm.GOLDEN, "butane_n4000.npz"))
+    n = len(g["x0"]); L = g["L"]
+    s = cm.ApiSystem(lib, g["x0"], L, float(g["cf"]), float(g["dt"]), v=g["v0"], types=np.full(n, ord("C"), dtype=np.uint8), nneighb=0)
+    s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+    # topology through our own .top reader: write the file from the golden lists
+    top = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"sepb200_butane_{os.getpid()}.top")
+    with open(top, "w") as fh:
+        fh.write("[ bonds ]\n;generated for the test\n")
+        for (a, b, t) in g["blist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {t}\n")
+        fh.write("\n[ angles ]\n;generated\n")
+        for (a, b, c, t) in g["alist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {c} {t}\n")
+        fh.write("\n[ dihedrals ]\n;generated\n")
+        for (a, b, c, d, t) in g["dlist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {c} {d} {t}\n")
+    lib.sep_read_topology_file(s.atoms, top.encode(), s.S, b"q")
+    os.unlink(top)
+    assert np.array_equal(s.view["molindex"], g["molindex"]) and np.array_equal(s.view["bond"], g["bond"])
+    assert np.array_equal(s.view["angle"], g["angle"]) and np.array_equal(s.view["dihed"], g["dihed"])
+    rb = (C.c_double * 6)(*g["rb"])
+    alpha = C.c_double(float(g["alpha0"]))
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_force_pairs(s.atoms, b"CC", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+    lib.sep_stretch_harmonic(s.atoms, 0, 0.407, 2074.0, s.S, s.R)
+    lib.sep_angle_harmonic(s.atoms, 0, 1.90, 400.0, s.S, s.R)
+    lib.sep_torsion_Ryckaert(s.atoms, 0, rb, s.S, s.R)
+    assert abs(s.ret.epot - float(g["epot_torsion"])) <= FT * abs(float(g["epot_torsion"]))
+    lib.sep_gpu_sync(s.atoms)
+    assert cm.rel_force_err(s.view["f"], g["f_torsion"]) <= FT
+    lib.sep_nosehoover(s.atoms, float(g["temp"]), C.byref(alpha), 0.1, s.S)
+    lib.sep_leapfrog(s.atoms, s.S, s.R)
+    assert np.abs(s.view["x"] - g["x1"]).max() <= 1e-11 and np.abs(s.view["v"] - g["v1"]).max() <= 1e-10
+    assert abs(s.ret.ekin - float(g["ekin"])) <= FT * float(g["ekin"])
+    s.close()
