@@ -135,6 +135,7 @@ struct sepgpu_ctx {
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
     int unroll;                  // gathers in flight per lane in the list force kernel (2 or 4)
     int force_grid;              // CTAs of the list force kernel (0 = default)
+    int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
 
     // measurement
     cudaEvent_t ev0, ev1;

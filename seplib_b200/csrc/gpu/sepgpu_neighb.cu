@@ -447,7 +447,9 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
     }
 }
 
-__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; }
+#include "sepgpu_neighb_tile.cuh"
+
+__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->xn_pending = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
 static int estimate_cap(const sepgpu_ctx *c, const sepgpu_sys *sys)
@@ -495,7 +497,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
     if (c->cap == 0) c->cap = estimate_cap(c, sys);
 
     const int B = 256, Gn = (c->n + B - 1) / B;
-    for (int attempt = 0; attempt < 6; attempt++) {
+    for (int attempt = 0; attempt < 8; attempt++) {
         if (!c->nbr) CUDA_TRY(cudaMalloc((void **)&c->nbr, sizeof(unsigned) * (size_t)c->cap * c->npad));
 
         ktimer_begin(c, &c->t_build);
@@ -527,10 +529,24 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         P.fcut_hi = (float)(P.cut2 + band);
         if (P.prefilter) {
             const int grid = nkey / G.bx;
-#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P
-            if (opt == SEPGPU_ALL) k_build_tile<SEPGPU_ALL><<<grid, TILE_THREADS, 0, c->stream>>>(TILE_ARGS);
-            else if (opt == SEPGPU_EXCL_SAME_MOL) k_build_tile<SEPGPU_EXCL_SAME_MOL><<<grid, TILE_THREADS, 0, c->stream>>>(TILE_ARGS);
-            else k_build_tile<SEPGPU_EXCL_BONDED><<<grid, TILE_THREADS, 0, c->stream>>>(TILE_ARGS);
+            if (c->tile_stage_cap == 0) {
+                // 9 rows x (bx+2) cells x mean occupancy, with head-room for density fluctuations
+                c->tile_stage_cap = ((int)(9.0 * (G.bx + 2) * mean_per_cell * 1.3) + 96 + 31) & ~31;
+            }
+            const int stage_cap = c->tile_stage_cap;
+            const size_t smem = (size_t)(stage_cap + TILE2_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
+            if (smem > 200 * 1024) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
+#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, stage_cap
+            if (opt == SEPGPU_ALL) {
+                CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<SEPGPU_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_build_tile2<SEPGPU_ALL><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);
+            } else if (opt == SEPGPU_EXCL_SAME_MOL) {
+                CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<SEPGPU_EXCL_SAME_MOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_build_tile2<SEPGPU_EXCL_SAME_MOL><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<SEPGPU_EXCL_BONDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_build_tile2<SEPGPU_EXCL_BONDED><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);
+            }
 #undef TILE_ARGS
         } else {
             k_build_list<<<(c->n + BUILD_WARPS - 1) / BUILD_WARPS, BUILD_WARPS * 32, 0, c->stream>>>(
@@ -551,6 +567,12 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (c->scal_host->max_half >= 3000) {         // SEP_NEIGHB, source/sepprfrc.c:499-501
             sepgpu_set_error("Too many neighbours");
             return SEPGPU_ENEIGHB;
+        }
+        if (c->scal_host->xn_pending > 0) {       // a tile needed a larger staging buffer: grow, rebuild
+            c->tile_stage_cap = (c->scal_host->xn_pending * 5 / 4 + 63) & ~31;
+            c->scal_host->nbuild -= 1;
+            CUDA_TRY(cudaMemcpyAsync(&c->scal->nbuild, &c->scal_host->nbuild, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            continue;
         }
         if (c->scal_host->max_neighb <= c->cap) {
             c->list_valid = true; c->list_opt = opt; c->sorted_identity = false; c->xs_current = true;
