@@ -49,6 +49,7 @@ enum {
     SEPGPU_F_BOND,           /* bond[SEP_BOND]   partner table (int)  */
     SEPGPU_F_ANGLE,          /* angle[SEP_ANGLE] partner table (int)  */
     SEPGPU_F_DIHED,          /* dihed[SEP_DIHED] partner table (int)  */
+    SEPGPU_F_GID,            /* global atom id (int), decomposed runs */
     SEPGPU_F_COUNT
 };
 
@@ -162,6 +163,19 @@ long long sepgpu_get_pairs(sepgpu_ctx *ctx, int *pairs, long long max_pairs);
 int sepgpu_request_rebuild(sepgpu_ctx *ctx);
 /* tuning: lanes cooperating on one atom in the list force kernels (1,2,4,8,16,32; 0 = default) */
 int sepgpu_set_option(sepgpu_ctx *ctx, const char *name, long long value);
+
+/* ---- spatial domain decomposition over the GPUs of one box (no reference counterpart: the reference
+ * is single-address-space OpenMP).  One process per GPU; slabs of whole cell layers along z; halo
+ * coordinates every step and migration at list rebuilds travel over NVLink with NCCL send/recv; one
+ * small all-reduce per step carries sum m v^2 (sep_nosehoover) and the maximum displacement (skin
+ * trigger).  Usage: create the context with capacity ncap >= owned + halo atoms, sepgpu_dd_init on
+ * every rank with the same id, sepgpu_dd_set_owned(n), sepgpu_put(X, V, GID, ...) for the atoms whose
+ * cell layer (int)(z/lsubbox[2]) lies in this rank's range, then the ordinary per-step calls.  All
+ * ranks must make the same calls in the same order (they are collective). ---- */
+int sepgpu_dd_unique_id(void *out128);
+int sepgpu_dd_init(sepgpu_ctx *ctx, int rank, int nranks, const void *id128, const sepgpu_sys *sys, long long n_global);
+int sepgpu_dd_set_owned(sepgpu_ctx *ctx, int n_own);
+int sepgpu_dd_layers(sepgpu_ctx *ctx, int *z0, int *z1, int *n_own, int *n_halo);
 
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------- */
 /* CUDA-event timing on the context's stream */

@@ -20,7 +20,7 @@ SEP_LJCF2 = 0.016316891136
 
 # sepgpu field ids (include/sepgpu.h)
 (F_X, F_V, F_F, F_M, F_Z, F_TYPE, F_MOLINDEX, F_XN, F_CROSS_NEIGHB, F_CROSSINGS, F_PV, F_PA, F_A,
- F_BOND, F_ANGLE, F_DIHED) = range(16)
+ F_BOND, F_ANGLE, F_DIHED, F_GID) = range(17)
 
 d3 = C.c_double * 3
 i3 = C.c_int * 3
@@ -128,6 +128,7 @@ SEPGPU_SYMBOLS = [
     "sepgpu_read_scalars", "sepgpu_sync", "sepgpu_get_pairs", "sepgpu_request_rebuild",
     "sepgpu_set_option", "sepgpu_timer_start", "sepgpu_timer_stop", "sepgpu_kernel_time",
     "sepgpu_peak_fp64", "sepgpu_peak_copy", "sepgpu_flush_l2",
+    "sepgpu_dd_unique_id", "sepgpu_dd_init", "sepgpu_dd_set_owned", "sepgpu_dd_layers",
 ]
 
 # the sep_* symbols include/sep.h declares
@@ -250,6 +251,10 @@ def load():
     lib.sepgpu_peak_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sepgpu_peak_copy.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sepgpu_flush_l2.argtypes = [ctx]
+    lib.sepgpu_dd_unique_id.argtypes = [C.c_void_p]
+    lib.sepgpu_dd_init.argtypes = [ctx, C.c_int, C.c_int, C.c_void_p, C.POINTER(GpuSys), C.c_longlong]
+    lib.sepgpu_dd_set_owned.argtypes = [ctx, C.c_int]
+    lib.sepgpu_dd_layers.argtypes = [ctx, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     declare_sep_api(lib)
     lib.sep_gpu_set_sync.argtypes = [C.c_int]
     lib.sep_gpu_sync.argtypes = [C.POINTER(SepPart)]
@@ -302,13 +307,14 @@ class System:
         except Exception:
             pass
 
-    _dtypes = {F_TYPE: (np.uint8, 1), F_MOLINDEX: (np.int32, 1), F_CROSS_NEIGHB: (np.int32, 3),
+    _dtypes = {F_TYPE: (np.uint8, 1), F_MOLINDEX: (np.int32, 1), F_GID: (np.int32, 1), F_CROSS_NEIGHB: (np.int32, 3),
                F_CROSSINGS: (np.int32, 3), F_BOND: (np.int32, 10), F_ANGLE: (np.int32, 10),
                F_DIHED: (np.int32, 20), F_M: (np.float64, 1), F_Z: (np.float64, 1)}
 
     def put(self, field, arr):
         dt, w = self._dtypes.get(field, (np.float64, 3))
         a = np.ascontiguousarray(arr, dtype=dt).reshape(self.n, w) if w > 1 else np.ascontiguousarray(arr, dtype=dt).reshape(self.n)
+        assert len(a) == self.n
         _ck(self.lib, self.lib.sepgpu_put(self.ctx, field, a.ctypes.data, 0), f"sepgpu_put({field})")
 
     def get(self, field):
@@ -316,6 +322,22 @@ class System:
         a = np.empty((self.n, w) if w > 1 else (self.n,), dtype=dt)
         _ck(self.lib, self.lib.sepgpu_get(self.ctx, field, a.ctypes.data, 0), f"sepgpu_get({field})")
         return a
+
+    # ---- slab domain decomposition (one process per GPU) -------------------------------------------
+    def dd_init(self, rank, world, id_bytes, gsys, n_global):
+        buf = (C.c_char * 128).from_buffer_copy(id_bytes)
+        _ck(self.lib, self.lib.sepgpu_dd_init(self.ctx, rank, world, buf, C.byref(gsys), n_global), "sepgpu_dd_init")
+        self.ncap = self.n
+
+    def dd_set_owned(self, n_own):
+        _ck(self.lib, self.lib.sepgpu_dd_set_owned(self.ctx, n_own), "sepgpu_dd_set_owned")
+        self.n = int(n_own)
+
+    def dd_layers(self):
+        z0, z1, no, nh = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _ck(self.lib, self.lib.sepgpu_dd_layers(self.ctx, C.byref(z0), C.byref(z1), C.byref(no), C.byref(nh)), "sepgpu_dd_layers")
+        self.n = no.value
+        return z0.value, z1.value, no.value, nh.value
 
     def call(self, name, *args):
         _ck(self.lib, getattr(self.lib, name)(self.ctx, *args), name)
@@ -347,6 +369,19 @@ class System:
         _ck(self.lib, self.lib.sepgpu_get_bonded_values(self.ctx, bl.ctypes.data, an.ctypes.data, di.ctypes.data),
             "sepgpu_get_bonded_values")
         return bl[:self._nb], an[:self._na], di[:self._nd]
+
+
+def dd_unique_id():
+    """128-byte NCCL unique id (call on rank 0, broadcast to the others)."""
+    lib = load()
+    buf = (C.c_char * 128)()
+    _ck(lib, lib.sepgpu_dd_unique_id(buf), "sepgpu_dd_unique_id")
+    return bytes(buf)
+
+
+def dd_slab_range(rank, world, nz):
+    """Global cell layers [z0,z1) owned by `rank` -- the same split as sepgpu_dd_init."""
+    return rank * nz // world, (rank + 1) * nz // world
 
 
 def lj_param(cf, eps=1.0, sigma=1.0, aw=1.0, shift=None, kind=None):

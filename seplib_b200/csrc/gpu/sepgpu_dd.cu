@@ -1,0 +1,464 @@
+// sepgpu_dd.cu -- spatial domain decomposition across the GPUs of one box: one process per GPU,
+// slabs of whole cell layers along z, halo exchange and migration over NVLink with NCCL point-to-point.
+//
+// The reference has nothing of the kind (single address space, OpenMP only).
+// What must be preserved is its semantics on GLOBAL quantities:
+//   * the neighbour-pair set: every rank bins its owned + halo atoms with the reference's exact
+//     expression on the GLOBAL cell grid (source/sepprfrc.c:404-406) and accepts pairs with the exact
+//     test, so the union over ranks is bit-identical to the single-GPU / reference set;
+//   * sep_nosehoover's temperature (sum m v^2 over ALL atoms / global npart, source/sepintgr.c:152-159)
+//     and the skin trigger (max displacement over ALL atoms, :72): one small all-reduce per step.
+//
+// Layout: rank r owns global cell layers [z0,z1); its local cell grid has (z1-z0)+2 layers, the first
+// and last holding copies ("halo") of the neighbouring ranks' boundary layers.  Local per-atom arrays
+// hold the owned atoms first, halo atoms after them.  Every time step the owners send the continuous
+// coordinates of their boundary-layer atoms (32 B per atom) to both neighbours; at a list rebuild atoms
+// that changed slab migrate with their full state and the halo membership is re-established.
+// Forces use the full list, so each rank computes the force on its own atoms only and nothing flows
+// back.  Compaction uses prefix sums (no atomics), so a run is reproducible bit for bit.
+//
+// NCCL is opened with dlopen at first use: the single-GPU library has no NCCL dependency.
+#include "sepgpu_internal.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdlib.h>
+
+int sepgpu_exclusive_scan(cudaStream_t st, int *cnt, int *start, int *scratch, int n);
+
+struct NcclApi {
+    void *lib;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+
+static int nccl_load(void)
+{
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (int k = 0; k < 2 && !g_nccl.lib; k++) g_nccl.lib = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl.lib) { sepgpu_set_error("domain decomposition: cannot dlopen libnccl.so.2 (%s)", dlerror()); return SEPGPU_ENCCL; }
+#define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name); if (!g_nccl.field) { sepgpu_set_error("NCCL symbol %s missing", name); return SEPGPU_ENCCL; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    return 0;
+}
+
+#define NCCL_TRY(call)                                                                         \
+    do {                                                                                       \
+        ncclResult_t _r = (call);                                                              \
+        if (_r != ncclSuccess) {                                                               \
+            sepgpu_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(_r)); \
+            return SEPGPU_ENCCL;                                                               \
+        }                                                                                      \
+    } while (0)
+
+#define REC_D4 4        // migration record: x4, v4, xn4, {cross_neighb[3], crossings[3], gid, list-crossings}
+
+struct DDState {
+    int rank, nranks;
+    ncclComm_t comm;
+    int nzg, z0, z1;            // global layers, owned range [z0,z1)
+    int lo_rank, hi_rank;
+    double *comm_buf;           // device scratch for all-reduces [64]
+    double *comm_host;          // pinned
+    // classification + scans
+    int *flag[5], *pos[5];      // stay, to_lo, to_hi, halo_lo, halo_hi
+    int *scan_scratch;
+    int *counts_dev, *counts_host;     // [16]
+    // double buffers for compaction
+    d4 *x4b, *v4b, *xn4b; i4 *cr4b; int *crossb, *gidb;
+    // transfer buffers (device)
+    d4 *send[2], *recv[2];      // [bufcap * REC_D4]
+    size_t bufcap;              // atoms per direction
+    int *send_idx[2];           // per-step halo send lists (local indices of owned atoms), lo and hi
+    int n_send[2], n_recv[2];   // halo atoms sent to lo/hi, received from hi/lo (in that order)
+    bool halo_current;
+};
+
+extern "C" int sepgpu_dd_unique_id(void *out128)
+{
+    if (!out128) return SEPGPU_EINVAL;
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+template <typename T>
+static int dmalloc(T **p, size_t count)
+{
+    CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    CUDA_TRY(cudaMemset(*p, 0, sizeof(T) * (count ? count : 1)));
+    return 0;
+}
+
+extern "C" int sepgpu_dd_init(sepgpu_ctx *c, int rank, int nranks, const void *id128, const sepgpu_sys *sys,
+                              long long n_global)
+{
+    if (!c || !id128 || !sys || nranks < 2 || rank < 0 || rank >= nranks) return SEPGPU_EINVAL;
+    if (c->dd) { sepgpu_set_error("dd_init: already decomposed"); return SEPGPU_ESTATE; }
+    int rc = nccl_load();
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int nzg = sys->nsubbox[2];
+    if (nzg < 2 * nranks || nzg < 4) {
+        sepgpu_set_error("dd_init: %d cell layers along z cannot be split over %d ranks", nzg, nranks);
+        return SEPGPU_EINVAL;
+    }
+    DDState *d = (DDState *)calloc(1, sizeof(DDState));
+    d->rank = rank; d->nranks = nranks; d->nzg = nzg;
+    d->z0 = (int)((long long)rank * nzg / nranks);
+    d->z1 = (int)((long long)(rank + 1) * nzg / nranks);
+    d->lo_rank = (rank + nranks - 1) % nranks;
+    d->hi_rank = (rank + 1) % nranks;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NCCL_TRY(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
+    const size_t cap = (size_t)c->ncap;
+    // a boundary layer holds about n_own / (owned layers); leave generous head-room
+    d->bufcap = cap / (size_t)(d->z1 - d->z0) * 2 + 4096;
+    if (d->bufcap > cap) d->bufcap = cap;
+    if (dmalloc(&d->comm_buf, 64)) return SEPGPU_ECUDA;
+    CUDA_TRY(cudaMallocHost((void **)&d->comm_host, sizeof(double) * 64));
+    for (int k = 0; k < 5; k++) if (dmalloc(&d->flag[k], cap + 1) || dmalloc(&d->pos[k], cap + 1)) return SEPGPU_ECUDA;
+    if (dmalloc(&d->scan_scratch, cap / 2048 + 1030) || dmalloc(&d->counts_dev, 16)) return SEPGPU_ECUDA;
+    CUDA_TRY(cudaMallocHost((void **)&d->counts_host, sizeof(int) * 16));
+    if (dmalloc(&d->x4b, cap) || dmalloc(&d->v4b, cap) || dmalloc(&d->xn4b, cap) || dmalloc(&d->cr4b, cap) ||
+        dmalloc(&d->crossb, 3 * cap) || dmalloc(&d->gidb, cap)) return SEPGPU_ECUDA;
+    for (int k = 0; k < 2; k++)
+        if (dmalloc(&d->send[k], d->bufcap * REC_D4) || dmalloc(&d->recv[k], d->bufcap * REC_D4) ||
+            dmalloc(&d->send_idx[k], d->bufcap)) return SEPGPU_ECUDA;
+    if (!c->gid && dmalloc(&c->gid, cap)) return SEPGPU_ECUDA;
+    c->dd = d;
+    c->n_global = n_global;
+    return 0;
+}
+
+extern "C" int sepgpu_dd_set_owned(sepgpu_ctx *c, int n_own)
+{
+    if (!c || n_own < 0 || n_own > c->ncap) return SEPGPU_EINVAL;
+    c->n_own = n_own;
+    c->n = n_own;
+    c->list_valid = false;
+    return 0;
+}
+
+extern "C" int sepgpu_dd_layers(sepgpu_ctx *c, int *z0, int *z1, int *n_own, int *n_halo)
+{
+    if (!c || !c->dd) return SEPGPU_EINVAL;
+    if (z0) *z0 = c->dd->z0;
+    if (z1) *z1 = c->dd->z1;
+    if (n_own) *n_own = c->n_own;
+    if (n_halo) *n_halo = c->n - c->n_own;
+    return 0;
+}
+
+void sepgpu_dd_destroy(sepgpu_ctx *c)
+{
+    DDState *d = c->dd;
+    if (!d) return;
+    if (d->comm) g_nccl.CommDestroy(d->comm);
+    void *ptrs[] = {d->comm_buf, d->scan_scratch, d->counts_dev, d->x4b, d->v4b, d->xn4b, d->cr4b, d->crossb, d->gidb,
+                    d->send[0], d->send[1], d->recv[0], d->recv[1], d->send_idx[0], d->send_idx[1],
+                    d->flag[0], d->flag[1], d->flag[2], d->flag[3], d->flag[4], d->pos[0], d->pos[1], d->pos[2], d->pos[3], d->pos[4]};
+    for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFree(ptrs[i]);
+    if (d->comm_host) cudaFreeHost(d->comm_host);
+    if (d->counts_host) cudaFreeHost(d->counts_host);
+    free(d);
+    c->dd = NULL;
+}
+
+double *sepgpu_dd_comm(sepgpu_ctx *c) { return c->dd->comm_buf; }
+
+int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax)
+{
+    DDState *d = c->dd;
+    NCCL_TRY(g_nccl.GroupStart());
+    if (nsum > 0) NCCL_TRY(g_nccl.AllReduce(sum_buf, sum_buf, (size_t)nsum, ncclDouble, ncclSum, d->comm, c->stream));
+    if (nmax > 0) NCCL_TRY(g_nccl.AllReduce(max_buf, max_buf, (size_t)nmax, ncclDouble, ncclMax, d->comm, c->stream));
+    NCCL_TRY(g_nccl.GroupEnd());
+    return 0;
+}
+
+// ---- rebuild: classification, migration, halo membership -------------------------------------------------
+__global__ void k_dd_classify(const d4 *__restrict__ x4, int n_own, double lsz, int nzg, int z0, int z1,
+                              int *f_stay, int *f_lo, int *f_hi, DevScalars *scal)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    const int cz = (int)__ddiv_rn(x4[i].z, lsz);                 // reference binning (source/sepprfrc.c:406)
+    int stay = 0, lo = 0, hi = 0;
+    if (cz >= z0 && cz < z1) stay = 1;
+    else if (cz == (z0 - 1 + nzg) % nzg) lo = 1;
+    else if (cz == z1 % nzg) hi = 1;
+    else scal->error = SEPGPU_ECELL;                             // moved more than one layer, or left the box
+    f_stay[i] = stay; f_lo[i] = lo; f_hi[i] = hi;
+}
+
+__global__ void k_dd_halo_flags(const d4 *__restrict__ x4, int n_own, double lsz, int z0, int z1, int *f_hlo, int *f_hhi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    const int cz = (int)__ddiv_rn(x4[i].z, lsz);
+    f_hlo[i] = cz == z0 ? 1 : 0;
+    f_hhi[i] = cz == z1 - 1 ? 1 : 0;
+}
+
+__device__ __forceinline__ d4 pack_aux(const i4 &cr, const int *crossings, int gid)
+{
+    d4 a;
+    a.x = __longlong_as_double(((long long)(unsigned)cr.x) | ((long long)(unsigned)cr.y << 32));
+    a.y = __longlong_as_double(((long long)(unsigned)cr.z) | ((long long)(unsigned)cr.w << 32));
+    a.z = __longlong_as_double(((long long)(unsigned)crossings[0]) | ((long long)(unsigned)crossings[1] << 32));
+    a.w = __longlong_as_double(((long long)(unsigned)crossings[2]) | ((long long)(unsigned)gid << 32));
+    return a;
+}
+__device__ __forceinline__ void unpack_aux(const d4 &a, i4 &cr, int *crossings, int &gid)
+{
+    long long b;
+    b = __double_as_longlong(a.x); cr.x = (int)(b & 0xffffffffLL); cr.y = (int)(b >> 32);
+    b = __double_as_longlong(a.y); cr.z = (int)(b & 0xffffffffLL); cr.w = (int)(b >> 32);
+    b = __double_as_longlong(a.z); crossings[0] = (int)(b & 0xffffffffLL); crossings[1] = (int)(b >> 32);
+    b = __double_as_longlong(a.w); crossings[2] = (int)(b & 0xffffffffLL); gid = (int)(b >> 32);
+}
+
+// stayers -> compacted copy; leavers -> send records (order = ascending local index: prefix sums)
+__global__ void k_dd_split(const d4 *__restrict__ x4, const d4 *__restrict__ v4, const d4 *__restrict__ xn4,
+                           const i4 *__restrict__ cr4, const int *__restrict__ crossings, const int *__restrict__ gid,
+                           int n_own, const int *__restrict__ pos_stay, const int *__restrict__ pos_lo,
+                           const int *__restrict__ pos_hi, d4 *x4b, d4 *v4b, d4 *xn4b, i4 *cr4b, int *crossb, int *gidb,
+                           d4 *send_lo, d4 *send_hi, size_t bufcap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    const int ps = pos_stay[i], pl = pos_lo[i], ph = pos_hi[i];
+    if (pos_stay[i + 1] > ps) {
+        x4b[ps] = x4[i]; v4b[ps] = v4[i]; xn4b[ps] = xn4[i]; cr4b[ps] = cr4[i];
+        crossb[3 * ps] = crossings[3 * i]; crossb[3 * ps + 1] = crossings[3 * i + 1]; crossb[3 * ps + 2] = crossings[3 * i + 2];
+        gidb[ps] = gid[i];
+    } else {
+        const bool to_lo = pos_lo[i + 1] > pl;
+        const int p = to_lo ? pl : ph;
+        if ((size_t)p >= bufcap) return;
+        d4 *rec = (to_lo ? send_lo : send_hi) + (size_t)p * REC_D4;
+        rec[0] = x4[i]; rec[1] = v4[i]; rec[2] = xn4[i];
+        rec[3] = pack_aux(cr4[i], crossings + 3 * i, gid[i]);
+    }
+}
+
+__global__ void k_dd_unpack_migrants(const d4 *__restrict__ recv, int nrec, int dst0, d4 *x4, d4 *v4, d4 *xn4, i4 *cr4,
+                                     int *crossings, int *gid)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nrec) return;
+    const d4 *rec = recv + (size_t)k * REC_D4;
+    const int i = dst0 + k;
+    x4[i] = rec[0]; v4[i] = rec[1]; xn4[i] = rec[2];
+    i4 cr; int g;
+    unpack_aux(rec[3], cr, crossings + 3 * i, g);
+    cr4[i] = cr; gid[i] = g;
+}
+
+// halo membership at a rebuild: wrapped position + tag and the global id; also records the send list
+__global__ void k_dd_pack_halo(const d4 *__restrict__ x4, const int *__restrict__ gid, int n_own,
+                               const int *__restrict__ pos, d4 *send, int *send_idx, size_t bufcap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    const int p = pos[i];
+    if (pos[i + 1] == p || (size_t)p >= bufcap) return;
+    send[2 * (size_t)p] = x4[i];
+    d4 a; a.x = __longlong_as_double((long long)gid[i]); a.y = a.z = a.w = 0.0;
+    send[2 * (size_t)p + 1] = a;
+    send_idx[p] = i;
+}
+
+__global__ void k_dd_unpack_halo(const d4 *__restrict__ recv, int nrec, int dst0, d4 *x4, d4 *v4, i4 *cr4, int *gid)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nrec) return;
+    const int i = dst0 + k;
+    x4[i] = recv[2 * (size_t)k];
+    gid[i] = (int)__double_as_longlong(recv[2 * (size_t)k + 1].x);
+    d4 v; v.x = v.y = v.z = 0.0; v.w = 1.0; v4[i] = v;
+    i4 z; z.x = z.y = z.z = z.w = 0; cr4[i] = z;
+}
+
+static int read_counts(sepgpu_ctx *c, int n)
+{
+    DDState *d = c->dd;
+    CUDA_TRY(cudaMemcpyAsync(d->counts_host, d->counts_dev, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+__global__ void k_dd_totals(const int *p0, const int *p1, const int *p2, int n, int *out)
+{
+    out[0] = p0[n]; out[1] = p1[n]; if (p2) out[2] = p2[n];
+}
+
+// exchange with both neighbours: what goes "down" (to lo_rank) arrives as the receiver's data "from above"
+static int exchange(sepgpu_ctx *c, const void *send_lo, size_t n_lo, const void *send_hi, size_t n_hi,
+                    void *recv_from_hi, size_t n_from_hi, void *recv_from_lo, size_t n_from_lo, size_t elem_bytes)
+{
+    DDState *d = c->dd;
+    NCCL_TRY(g_nccl.GroupStart());
+    if (n_lo) NCCL_TRY(g_nccl.Send(send_lo, n_lo * elem_bytes, ncclChar, d->lo_rank, d->comm, c->stream));
+    if (n_hi) NCCL_TRY(g_nccl.Send(send_hi, n_hi * elem_bytes, ncclChar, d->hi_rank, d->comm, c->stream));
+    if (n_from_hi) NCCL_TRY(g_nccl.Recv(recv_from_hi, n_from_hi * elem_bytes, ncclChar, d->hi_rank, d->comm, c->stream));
+    if (n_from_lo) NCCL_TRY(g_nccl.Recv(recv_from_lo, n_from_lo * elem_bytes, ncclChar, d->lo_rank, d->comm, c->stream));
+    NCCL_TRY(g_nccl.GroupEnd());
+    return 0;
+}
+
+int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local)
+{
+    DDState *d = c->dd;
+    if (!c->f_zero) {
+        sepgpu_set_error("decomposed rebuild: forces from an earlier call of this step would be lost "
+                         "(call the list-building force routine first after sep_reset_force)");
+        return SEPGPU_ESTATE;
+    }
+    if (sys->nsubbox[2] != d->nzg) { sepgpu_set_error("decomposed run: the cell grid along z changed"); return SEPGPU_ESTATE; }
+    const double lsz = sys->lsubbox[2];
+    const int B = 256;
+    int n_own = c->n_own;
+    int G = (n_own + B - 1) / B;
+    int rc;
+    // 1. who stays, who leaves
+    if (G) k_dd_classify<<<G, B, 0, c->stream>>>(c->x4, n_own, lsz, d->nzg, d->z0, d->z1, d->flag[0], d->flag[1], d->flag[2], c->scal);
+    for (int k = 0; k < 3; k++)
+        if ((rc = sepgpu_exclusive_scan(c->stream, d->flag[k], d->pos[k], d->scan_scratch, n_own))) return rc;
+    k_dd_totals<<<1, 1, 0, c->stream>>>(d->pos[0], d->pos[1], d->pos[2], n_own, d->counts_dev);
+    // 2. neighbours learn how many atoms arrive
+    if ((rc = exchange(c, d->counts_dev + 1, 1, d->counts_dev + 2, 1, d->counts_dev + 4, 1, d->counts_dev + 5, 1, sizeof(int)))) return rc;
+    if ((rc = read_counts(c, 8))) return rc;
+    const int n_stay = d->counts_host[0], n_to_lo = d->counts_host[1], n_to_hi = d->counts_host[2];
+    const int n_from_hi = d->counts_host[4], n_from_lo = d->counts_host[5];
+    if ((size_t)n_to_lo > d->bufcap || (size_t)n_to_hi > d->bufcap || (size_t)n_from_hi > d->bufcap || (size_t)n_from_lo > d->bufcap ||
+        n_stay + n_from_hi + n_from_lo > c->ncap) {
+        sepgpu_set_error("decomposed rebuild: migration exceeds the buffers (stay %d, out %d/%d, in %d/%d, cap %d)",
+                         n_stay, n_to_lo, n_to_hi, n_from_hi, n_from_lo, c->ncap);
+        return SEPGPU_EINVAL;
+    }
+    // 3. compact the stayers into the second buffer set, pack the leavers, swap buffers
+    if (G) k_dd_split<<<G, B, 0, c->stream>>>(c->x4, c->v4, c->xn4, c->cr4, c->crossings, c->gid, n_own, d->pos[0], d->pos[1], d->pos[2],
+                                               d->x4b, d->v4b, d->xn4b, d->cr4b, d->crossb, d->gidb, d->send[0], d->send[1], d->bufcap);
+    { d4 *t; i4 *ti; int *tn;
+      t = c->x4; c->x4 = d->x4b; d->x4b = t;  t = c->v4; c->v4 = d->v4b; d->v4b = t;  t = c->xn4; c->xn4 = d->xn4b; d->xn4b = t;
+      ti = c->cr4; c->cr4 = d->cr4b; d->cr4b = ti;  tn = c->crossings; c->crossings = d->crossb; d->crossb = tn;
+      tn = c->gid; c->gid = d->gidb; d->gidb = tn; }
+    if ((rc = exchange(c, d->send[0], (size_t)n_to_lo * REC_D4, d->send[1], (size_t)n_to_hi * REC_D4,
+                       d->recv[0], (size_t)n_from_hi * REC_D4, d->recv[1], (size_t)n_from_lo * REC_D4, sizeof(d4)))) return rc;
+    if (n_from_hi) k_dd_unpack_migrants<<<(n_from_hi + B - 1) / B, B, 0, c->stream>>>(d->recv[0], n_from_hi, n_stay, c->x4, c->v4, c->xn4, c->cr4, c->crossings, c->gid);
+    if (n_from_lo) k_dd_unpack_migrants<<<(n_from_lo + B - 1) / B, B, 0, c->stream>>>(d->recv[1], n_from_lo, n_stay + n_from_hi, c->x4, c->v4, c->xn4, c->cr4, c->crossings, c->gid);
+    n_own = n_stay + n_from_hi + n_from_lo;
+    G = (n_own + B - 1) / B;
+    // 4. halo membership of the new owned set
+    if (G) k_dd_halo_flags<<<G, B, 0, c->stream>>>(c->x4, n_own, lsz, d->z0, d->z1, d->flag[3], d->flag[4]);
+    for (int k = 3; k < 5; k++)
+        if ((rc = sepgpu_exclusive_scan(c->stream, d->flag[k], d->pos[k], d->scan_scratch, n_own))) return rc;
+    k_dd_totals<<<1, 1, 0, c->stream>>>(d->pos[3], d->pos[4], NULL, n_own, d->counts_dev + 8);
+    if ((rc = exchange(c, d->counts_dev + 8, 1, d->counts_dev + 9, 1, d->counts_dev + 10, 1, d->counts_dev + 11, 1, sizeof(int)))) return rc;
+    if ((rc = read_counts(c, 12))) return rc;
+    d->n_send[0] = d->counts_host[8]; d->n_send[1] = d->counts_host[9];
+    d->n_recv[0] = d->counts_host[10]; d->n_recv[1] = d->counts_host[11];          // from hi, from lo
+    const int n_halo = d->n_recv[0] + d->n_recv[1];
+    if ((size_t)d->n_send[0] > d->bufcap || (size_t)d->n_send[1] > d->bufcap || (size_t)d->n_recv[0] > d->bufcap ||
+        (size_t)d->n_recv[1] > d->bufcap || n_own + n_halo > c->ncap) {
+        sepgpu_set_error("decomposed rebuild: halo exceeds the buffers (own %d, halo %d, cap %d, buf %zu)", n_own, n_halo, c->ncap, d->bufcap);
+        return SEPGPU_EINVAL;
+    }
+    if (G) {
+        k_dd_pack_halo<<<G, B, 0, c->stream>>>(c->x4, c->gid, n_own, d->pos[3], d->send[0], d->send_idx[0], d->bufcap);
+        k_dd_pack_halo<<<G, B, 0, c->stream>>>(c->x4, c->gid, n_own, d->pos[4], d->send[1], d->send_idx[1], d->bufcap);
+    }
+    if ((rc = exchange(c, d->send[0], (size_t)d->n_send[0] * 2, d->send[1], (size_t)d->n_send[1] * 2,
+                       d->recv[0], (size_t)d->n_recv[0] * 2, d->recv[1], (size_t)d->n_recv[1] * 2, sizeof(d4)))) return rc;
+    if (d->n_recv[0]) k_dd_unpack_halo<<<(d->n_recv[0] + B - 1) / B, B, 0, c->stream>>>(d->recv[0], d->n_recv[0], n_own, c->x4, c->v4, c->cr4, c->gid);
+    if (d->n_recv[1]) k_dd_unpack_halo<<<(d->n_recv[1] + B - 1) / B, B, 0, c->stream>>>(d->recv[1], d->n_recv[1], n_own + d->n_recv[0], c->x4, c->v4, c->cr4, c->gid);
+    KERNEL_CHECK();
+    c->n_own = n_own;
+    c->n = n_own + n_halo;
+    d->halo_current = true;
+    *zoff = d->z0 - 1;
+    *nz_local = (d->z1 - d->z0) + 2;
+    return 0;
+}
+
+// ---- every step: refresh the halo coordinates ---------------------------------------------------------------
+__global__ void k_dd_pack_xu(const d4 *__restrict__ x4, const i4 *__restrict__ cr4, const int *__restrict__ idx, int n,
+                             double Lx, double Ly, double Lz, d4 *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = idx[k];
+    d4 x = x4[i];
+    const int w = cr4[i].w;                              // crossings since the list was built (packed, see sepgpu_intgr.cu)
+    if (w != 0) {
+        x.x += ((w & 1023) - 512) * Lx; x.y += (((w >> 10) & 1023) - 512) * Ly; x.z += (((w >> 20) & 1023) - 512) * Lz;
+    }
+    out[k] = x;
+}
+
+__global__ void k_dd_unpack_xu(const d4 *__restrict__ in, int n, int first_local, const int *__restrict__ rank, d4 *__restrict__ xs)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    xs[rank[first_local + k]] = in[k];
+}
+
+int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys)
+{
+    DDState *d = c->dd;
+    if (d->halo_current) return 0;
+    const int B = 256;
+    for (int k = 0; k < 2; k++)
+        if (d->n_send[k]) k_dd_pack_xu<<<(d->n_send[k] + B - 1) / B, B, 0, c->stream>>>(c->x4, c->cr4, d->send_idx[k], d->n_send[k],
+                                                                                      sys->length[0], sys->length[1], sys->length[2], d->send[k]);
+    int rc = exchange(c, d->send[0], (size_t)d->n_send[0], d->send[1], (size_t)d->n_send[1],
+                      d->recv[0], (size_t)d->n_recv[0], d->recv[1], (size_t)d->n_recv[1], sizeof(d4));
+    if (rc) return rc;
+    if (d->n_recv[0]) k_dd_unpack_xu<<<(d->n_recv[0] + B - 1) / B, B, 0, c->stream>>>(d->recv[0], d->n_recv[0], c->n_own, c->rank, c->xs);
+    if (d->n_recv[1]) k_dd_unpack_xu<<<(d->n_recv[1] + B - 1) / B, B, 0, c->stream>>>(d->recv[1], d->n_recv[1], c->n_own + d->n_recv[0], c->rank, c->xs);
+    KERNEL_CHECK();
+    d->halo_current = true;
+    return 0;
+}
+
+void sepgpu_dd_positions_moved(sepgpu_ctx *c) { if (c->dd) c->dd->halo_current = false; }
+
+// ---- scalars: force-derived sums are kept per rank and summed when read -----------------------------------
+__global__ void k_dd_gather_force_scalars(const DevScalars *s, double *comm)
+{
+    const int t = threadIdx.x;
+    if (t == 0) { comm[0] = s->epot; comm[1] = s->ecoul; }
+    if (t < 9) { comm[2 + t] = s->pot_P[t]; comm[11 + t] = s->pot_P_bond[t]; }
+}
+
+int sepgpu_dd_reduce_force_scalars(sepgpu_ctx *c, double *epot, double *ecoul, double *pot_P, double *pot_P_bond)
+{
+    DDState *d = c->dd;
+    k_dd_gather_force_scalars<<<1, 32, 0, c->stream>>>(c->scal, d->comm_buf + 16);
+    int rc = sepgpu_dd_allreduce(c, d->comm_buf + 16, 20, NULL, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d->comm_host, d->comm_buf + 16, sizeof(double) * 20, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *epot = d->comm_host[0]; *ecoul = d->comm_host[1];
+    memcpy(pot_P, d->comm_host + 2, sizeof(double) * 9);
+    memcpy(pot_P_bond, d->comm_host + 11, sizeof(double) * 9);
+    return 0;
+}

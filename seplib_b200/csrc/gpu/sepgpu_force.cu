@@ -294,6 +294,8 @@ k_finalize_force(const double *__restrict__ partial, int nrows, DevScalars *scal
     }
 }
 
+int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
+
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
 {
     k_finalize_force<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, scale, flags);
@@ -372,6 +374,7 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     if (!c->list_valid) {
         if ((rc = sepgpu_neighb_build(c, sys, opt))) return rc;
     }
+    if (c->dd && (rc = sepgpu_dd_halo_update(c, sys))) return rc;      // neighbours' boundary atoms moved too
     // the type test is compiled out when every atom carries the one requested type
     const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
     const int tpa = c->tpa;

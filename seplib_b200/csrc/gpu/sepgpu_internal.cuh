@@ -67,9 +67,16 @@ struct KernelTimer {
     bool enabled;
 };
 
+struct DDState;            // slab domain decomposition (sepgpu_dd.cu); NULL when the context is not decomposed
+
 struct sepgpu_ctx {
-    int n;                 // atoms
-    int npad;              // n rounded up to 32
+    int n;                 // atoms in the sorted arrays: owned + halo (== n_own when not decomposed)
+    int n_own;             // atoms this context integrates
+    int ncap;              // allocation size of the per-atom arrays
+    long long n_global;    // atoms of the whole system (sep_nosehoover divides by it)
+    int npad;              // ncap rounded up to 32: row stride of the neighbour list
+    DDState *dd;
+    int *gid;              // global atom id per local atom (decomposed runs only)
     int device;
     cudaStream_t stream;
 

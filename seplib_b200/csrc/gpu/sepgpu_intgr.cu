@@ -134,8 +134,22 @@ k_integrate(d4 *__restrict__ x4, d4 *__restrict__ v4, d4 *__restrict__ f4, const
 
 // one block: reduce the partial rows, update sepret/sepsys scalars, evaluate the skin trigger
 __global__ void __launch_bounds__(256)
-k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin)
+k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int mode, double *comm)
 {
+    // mode 0: single GPU.  mode 1: decomposed run, phase A -- local sums into comm[0..11], local max into
+    // comm[12]; the host all-reduces them (sum / max) over the ranks.  mode 2: phase B -- apply comm.
+    if (mode == 2) {
+        if (threadIdx.x == 0) {
+            scal->ekin += 0.5 * comm[0];
+            const double K[9] = {comm[1], comm[2], comm[3], comm[2], comm[4], comm[5], comm[3], comm[5], comm[6]};
+            for (int k = 0; k < 9; k++) scal->kin_P[k] += K[k];
+            if (comm[12] > scal->max_dist2) scal->max_dist2 = comm[12];
+            scal->sum_mv2 = comm[8];
+            scal->mom[0] = comm[9]; scal->mom[1] = comm[10]; scal->mom[2] = comm[11];
+            scal->neighb_flag = sqrt(scal->max_dist2) > skin * 0.5 ? 1 : 0;
+        }
+        return;
+    }
     __shared__ double red[SEPGPU_NPART_I * 8];
     double v[SEPGPU_NPART_I];
 #pragma unroll
@@ -154,6 +168,11 @@ k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 0; w < 8; w++) mx = fmax(mx, red[w]);
+        if (mode == 1) {
+            for (int q = 0; q < SEPGPU_NPART_I; q++) comm[q] = v[q];
+            comm[7] = 0.0; comm[12] = mx;
+            return;
+        }
         scal->ekin += 0.5 * v[0];                                     // source/sepintgr.c:87
         const double K[9] = {v[1], v[2], v[3], v[2], v[4], v[5], v[3], v[5], v[6]};
         for (int k = 0; k < 9; k++) scal->kin_P[k] += K[k];
@@ -176,6 +195,20 @@ __global__ void k_set_xn(const d4 *__restrict__ x4, d4 *__restrict__ xn4, i4 *__
 }
 
 int sepgpu_ensure_dpd(sepgpu_ctx *c);
+// domain-decomposition hooks (sepgpu_dd.cu)
+double *sepgpu_dd_comm(sepgpu_ctx *c);
+void sepgpu_dd_positions_moved(sepgpu_ctx *c);
+int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax);
+
+__global__ void k_partial2_to_comm(const double *__restrict__ partial, int nrows, double *comm)
+{
+    __shared__ double red[2 * 8];
+    double v[2] = {0.0, 0.0};
+    for (int r = threadIdx.x; r < nrows; r += 256) { v[0] += partial[2 * r]; v[1] += partial[2 * r + 1]; }
+    block_sum<2, 256>(v, red);
+    if (threadIdx.x == 0) { comm[0] = v[0]; comm[1] = v[1]; }
+}
+__global__ void k_comm_to_mv2(DevScalars *scal, const double *comm) { scal->sum_mv2 = comm[0]; }
 
 static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double lambda, int stepnow)
 {
@@ -183,12 +216,12 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     if (dpd) { int rc = sepgpu_ensure_dpd(c); if (rc) return rc; }
     IntgrParams P;
     P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
-    P.dt = sys->dt; P.skin = sys->skin; P.n = c->n;
+    P.dt = sys->dt; P.skin = sys->skin; P.n = c->n_own;
     P.alpha_slot = c->pending_alpha_slot;
     P.alpha_type = c->pending_alpha_type;
     P.f_zero = c->f_zero ? 1 : 0;
     P.write_xs = (sys->neighb_update != 0 && c->list_valid) ? 1 : 0;
-    long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+    long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
     const int grid = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
     ktimer_begin(c, &c->t_intgr);
     if (dpd)
@@ -197,7 +230,15 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     else
         k_integrate<false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
             c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial);
-    k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin);
+    if (c->dd) {
+        double *comm = sepgpu_dd_comm(c);
+        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 1, comm);
+        int rcd = sepgpu_dd_allreduce(c, comm, 12, comm + 12, 1);
+        if (rcd) return rcd;
+        k_finalize_intgr<<<1, 32, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 2, comm);
+    } else {
+        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 0, NULL);
+    }
     ktimer_end(c, &c->t_intgr);
     KERNEL_CHECK();
     if (c->pending_alpha_slot >= 0 || c->f_zero) c->f_zero = false;   // f4 now holds the force that was used
@@ -205,12 +246,13 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     c->pending_alpha_type = -1;
     c->mv2_valid = true;
     if (!P.write_xs) c->xs_current = false;
+    sepgpu_dd_positions_moved(c);
 
     // the trigger is needed by the host before the next force call: small D2H + stream sync per step
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (c->scal_host->neighb_flag) {
-        k_set_xn<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n);
+        k_set_xn<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n_own);
         KERNEL_CHECK();
         c->list_valid = false;
     }
@@ -248,7 +290,7 @@ k_sum_mv2(const d4 *__restrict__ v4, const d4 *__restrict__ x4, int n, int type,
 // mode 0: sep_nosehoover (source/sepintgr.c:157-161); mode 1: _sep_nosehoover_type (:180-187)
 __global__ void __launch_bounds__(256)
 k_nh_update(const double *__restrict__ partial, int nrows, DevScalars *scal, int slot, int mode,
-            double temp0, double tau_or_Q, double dt, int npart, double a0, double a1, double a2)
+            double temp0, double tau_or_Q, double dt, double npart, double a0, double a1, double a2)
 {
     __shared__ double red[2 * 8];
     double v[2] = {0.0, 0.0};
@@ -280,11 +322,18 @@ extern "C" int sepgpu_nosehoover(sepgpu_ctx *c, const sepgpu_sys *sys, double te
     if (rc) return rc;
     int nrows = 0;
     if (!c->mv2_valid) {
-        long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+        long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
         nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
-        k_sum_mv2<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n, -1, c->partial);
+        k_sum_mv2<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n_own, -1, c->partial);
+        if (c->dd) {                       // global sum m v^2 over the ranks
+            double *comm = sepgpu_dd_comm(c);
+            k_partial2_to_comm<<<1, 256, 0, c->stream>>>(c->partial, nrows, comm);
+            if ((rc = sepgpu_dd_allreduce(c, comm, 2, NULL, 0))) return rc;
+            k_comm_to_mv2<<<1, 1, 0, c->stream>>>(c->scal, comm);
+            nrows = 0;
+        }
     }
-    k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, slot, 0, temp0, tau, sys->dt, c->n, 0, 0, 0);
+    k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, slot, 0, temp0, tau, sys->dt, (double)c->n_global, 0, 0, 0);
     KERNEL_CHECK();
     c->pending_alpha_slot = slot;
     c->pending_alpha_type = -1;
@@ -298,10 +347,10 @@ extern "C" int sepgpu_nosehoover_type(sepgpu_ctx *c, const sepgpu_sys *sys, char
     CUDA_TRY(cudaSetDevice(c->device));
     int rc = sepgpu_apply_pending(c);
     if (rc) return rc;
-    long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+    long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
     const int nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
-    k_sum_mv2<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n, (unsigned char)type, c->partial);
-    k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, 0, 1, Td, Q, sys->dt, c->n,
+    k_sum_mv2<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n_own, (unsigned char)type, c->partial);
+    k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, 0, 1, Td, Q, sys->dt, (double)c->n_global,
                                           alpha3[0], alpha3[1], alpha3[2]);
     KERNEL_CHECK();
     // the history is host-visible state of the caller: read it back (3 doubles)
@@ -331,8 +380,8 @@ __global__ void k_apply_alpha(d4 *__restrict__ f4, const d4 *__restrict__ v4, co
 int sepgpu_apply_pending(sepgpu_ctx *c)
 {
     if (c->pending_alpha_slot < 0) return 0;
-    k_apply_alpha<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->f4, c->v4, c->x4, c->scal, c->pending_alpha_slot,
-                                                            c->pending_alpha_type, c->n, c->f_zero ? 1 : 0);
+    k_apply_alpha<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->f4, c->v4, c->x4, c->scal, c->pending_alpha_slot,
+                                                            c->pending_alpha_type, c->n_own, c->f_zero ? 1 : 0);
     KERNEL_CHECK();
     c->pending_alpha_slot = -1;
     c->pending_alpha_type = -1;
@@ -378,11 +427,11 @@ extern "C" int sepgpu_reset_momentum(sepgpu_ctx *c, char type)
 {
     if (!c) return SEPGPU_EINVAL;
     CUDA_TRY(cudaSetDevice(c->device));
-    long long want = ((long long)c->n + INTGR_BLOCK - 1) / INTGR_BLOCK;
+    long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
     const int nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
-    k_sum_mom<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n, (unsigned char)type, c->partial);
+    k_sum_mom<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n_own, (unsigned char)type, c->partial);
     k_mom_final<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal);
-    k_sub_mom<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->v4, c->x4, c->n, (unsigned char)type, c->scal);
+    k_sub_mom<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->v4, c->x4, c->n_own, (unsigned char)type, c->scal);
     KERNEL_CHECK();
     c->mv2_valid = false;
     return 0;
@@ -400,7 +449,7 @@ extern "C" int sepgpu_scale_positions(sepgpu_ctx *c, double xi)
 {
     if (!c) return SEPGPU_EINVAL;
     CUDA_TRY(cudaSetDevice(c->device));
-    k_scale_x<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xs, c->n, xi, c->list_valid ? 1 : 0);
+    k_scale_x<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xs, c->n_own, xi, c->list_valid ? 1 : 0);
     KERNEL_CHECK();
     return 0;
 }

@@ -22,6 +22,9 @@ struct CellGrid {
     int nx, ny, nz;         // reference cell grid (sys->nsubbox)
     int bx;                 // brick extent along x (1,2,4,8); y and z extents are BRICK_YZ
     int nbx, nby, nbz;      // bricks per direction
+    // slab decomposition along z (sepgpu_dd.cu): nz above is the number of LOCAL layers (owned layers
+    // plus one halo layer on each side); local layer l holds global layer zoff + l (mod nzg)
+    int dd, zoff, nzg;
 };
 
 __host__ __device__ __forceinline__ int cell_key(int cx, int cy, int cz, const CellGrid &G)
@@ -51,9 +54,15 @@ __global__ void k_cell_count(const d4 *__restrict__ x4, int n, double lsx, doubl
     d4 p = x4[i];
     // source/sepprfrc.c:404-406, IEEE division then truncation
     int cx = (int)__ddiv_rn(p.x, lsx), cy = (int)__ddiv_rn(p.y, lsy), cz = (int)__ddiv_rn(p.z, lsz);
-    if (cx < 0 || cx >= G.nx || cy < 0 || cy >= G.ny || cz < 0 || cz >= G.nz || !(p.x == p.x)) {
+    const int nzg = G.dd ? G.nzg : G.nz;
+    if (cx < 0 || cx >= G.nx || cy < 0 || cy >= G.ny || cz < 0 || cz >= nzg || !(p.x == p.x)) {
         scal->error = SEPGPU_ECELL;
-        cx = min(max(cx, 0), G.nx - 1); cy = min(max(cy, 0), G.ny - 1); cz = min(max(cz, 0), G.nz - 1);
+        cx = min(max(cx, 0), G.nx - 1); cy = min(max(cy, 0), G.ny - 1); cz = min(max(cz, 0), nzg - 1);
+    }
+    if (G.dd) {                         // global layer -> local layer of this slab
+        cz -= G.zoff;
+        if (cz < 0) cz += G.nzg; else if (cz >= G.nzg) cz -= G.nzg;
+        if (cz >= G.nz) { scal->error = SEPGPU_ECELL; cz = G.nz - 1; }
     }
     const int key = cell_key(cx, cy, cz, G);
     cell_of[i] = key;
@@ -119,13 +128,25 @@ __global__ void __launch_bounds__(1024) k_scan_blocks(int *__restrict__ block_su
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
+    if (threadIdx.x == 0) block_sum[nblocks] = carry;      // grand total
 }
 
-__global__ void k_scan_apply(int *__restrict__ start, const int *__restrict__ block_sum, int ncell, int n)
+__global__ void k_scan_apply(int *__restrict__ start, const int *__restrict__ block_sum, int ncell, int nblocks)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < ncell) start[idx] += block_sum[idx / (SCAN_BLOCK * SCAN_ITEMS)];
-    if (idx == 0) start[ncell] = n;
+    if (idx == 0) start[ncell] = block_sum[nblocks];
+}
+
+// exclusive scan of cnt[0..n) into start[0..n], start[n] = total; cnt is cleared.  scratch: n/2048 + 2 ints
+int sepgpu_exclusive_scan(cudaStream_t st, int *cnt, int *start, int *scratch, int n)
+{
+    const int nb = (n + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
+    k_scan_local<<<nb, SCAN_BLOCK, 0, st>>>(cnt, start, scratch, n);
+    k_scan_blocks<<<1, 1024, 0, st>>>(scratch, nb);
+    k_scan_apply<<<(n + 255) / 256 + 1, 256, 0, st>>>(start, scratch, n, nb);
+    KERNEL_CHECK();
+    return 0;
 }
 
 __global__ void k_cell_scatter(const int *__restrict__ cell_of, int n, const int *__restrict__ cell_start,
@@ -452,13 +473,15 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 __global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->xn_pending = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
+int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local);
+
 static int estimate_cap(const sepgpu_ctx *c, const sepgpu_sys *sys)
 {
     const double vol = sys->length[0] * sys->length[1] * sys->length[2];
     const double rc = sys->cf + sys->skin;
-    const double expect = 4.18879020478639 * rc * rc * rc * (double)c->n / vol;
+    const double expect = 4.18879020478639 * rc * rc * rc * (double)c->n_global / vol;
     int cap = (int)(expect * 1.5) + 24;
-    if (cap > c->n) cap = c->n;
+    if (cap > c->n_global) cap = (int)c->n_global;
     return (cap + 7) & ~7;
 }
 
@@ -475,11 +498,18 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
     }
     CellGrid G;
     G.nx = nx; G.ny = ny; G.nz = nz;
+    G.dd = 0; G.zoff = 0; G.nzg = nz;
+    if (c->dd) {
+        // migrate atoms that left the slab, refresh the halo layers, then build on owned + halo atoms
+        int rcd = sepgpu_dd_before_build(c, sys, &G.zoff, &G.nz);
+        if (rcd) return rcd;
+        G.dd = 1;
+    }
     // brick x-extent: as many cells as keep one x-run of home atoms within one pass of the tile kernel
-    const double mean_per_cell = (double)c->n / ((double)nx * ny * nz);
+    const double mean_per_cell = (double)c->n / ((double)nx * ny * G.nz);
     G.bx = 1;
     while (G.bx < TILE_MAXCX && 2 * G.bx * mean_per_cell <= 0.9 * TILE_THREADS && 2 * G.bx <= nx) G.bx *= 2;
-    G.nbx = (nx + G.bx - 1) / G.bx; G.nby = (ny + BRICK_YZ - 1) / BRICK_YZ; G.nbz = (nz + BRICK_YZ - 1) / BRICK_YZ;
+    G.nbx = (nx + G.bx - 1) / G.bx; G.nby = (ny + BRICK_YZ - 1) / BRICK_YZ; G.nbz = (G.nz + BRICK_YZ - 1) / BRICK_YZ;
     const long long nkey_ll = (long long)G.nbx * G.nby * G.nbz * G.bx * BRICK_YZ * BRICK_YZ;
     if (nkey_ll > (1LL << 30)) { sepgpu_set_error("neighb_build: too many cells"); return SEPGPU_EINVAL; }
     const int nkey = (int)nkey_ll;
@@ -505,9 +535,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         k_build_begin<<<1, 1, 0, c->stream>>>(c->scal);
         k_cell_count<<<Gn, B, 0, c->stream>>>(c->x4, c->n, sys->lsubbox[0], sys->lsubbox[1], sys->lsubbox[2],
                                               G, c->cell_of, c->cell_cnt, c->scal);
-        k_scan_local<<<scan_blocks, SCAN_BLOCK, 0, c->stream>>>(c->cell_cnt, c->cell_start, block_sum, nkey);
-        k_scan_blocks<<<1, 1024, 0, c->stream>>>(block_sum, scan_blocks);
-        k_scan_apply<<<(nkey + 255) / 256, 256, 0, c->stream>>>(c->cell_start, block_sum, nkey, c->n);
+        if (sepgpu_exclusive_scan(c->stream, c->cell_cnt, c->cell_start, block_sum, nkey)) return SEPGPU_ECUDA;
         k_cell_scatter<<<Gn, B, 0, c->stream>>>(c->cell_of, c->n, c->cell_start, c->cell_cnt, c->tmp_slot);
         k_cell_finalize<<<Gn, B, 0, c->stream>>>(c->tmp_slot, c->cell_of, c->cell_start, c->x4, c->n,
                                                  c->order, c->rank, c->xs, c->xf, c->cr4);
@@ -525,6 +553,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         const double wmin = fmin(sys->lsubbox[0], fmin(sys->lsubbox[1], sys->lsubbox[2]));
         const double band = 4.2e-6 * cut * Lmax + 2e-6 * P.cut2;
         P.prefilter = c->prefilter && nx >= 4 && ny >= 4 && nz >= 4 && cut < 1.95 * wmin && band < 0.05 * P.cut2;
+        if (c->dd && !P.prefilter) { sepgpu_set_error("neighb_build: decomposed runs need >= 4 cells per direction"); return SEPGPU_EINVAL; }
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
         if (P.prefilter) {
@@ -593,14 +622,17 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
 // ---- pair export -----------------------------------------------------------------------------------------------
 __global__ void k_export_pairs(const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
                                const int *__restrict__ order, int n, int npad, int *__restrict__ out,
-                               long long max_pairs, unsigned long long *counter)
+                               long long max_pairs, unsigned long long *counter, const int *__restrict__ gid, int n_own)
 {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const int i = order[s];
+    int i = order[s];
+    if (i >= n_own) return;                      // halo atoms own no rows
     const int m = cnt[s];
+    if (gid) i = gid[i];
     for (int k = 0; k < m; k++) {
-        const int j = order[nbr[nbr_index(k, s, npad)] & SEPGPU_INDEX_MASK];
+        int j = order[nbr[nbr_index(k, s, npad)] & SEPGPU_INDEX_MASK];
+        if (gid) j = gid[j];                     // decomposed run: global ids; a cross-rank pair is emitted by one rank only
         if (i < j) {
             unsigned long long p = atomicAdd(counter, 1ULL);
             if ((long long)p < max_pairs) { out[2 * p] = i; out[2 * p + 1] = j; }
@@ -617,7 +649,7 @@ extern "C" long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_p
     if (cudaMalloc((void **)&dout, sizeof(int) * 2 * (size_t)max_pairs) != cudaSuccess) return SEPGPU_ECUDA;
     if (cudaMalloc((void **)&dcount, sizeof(unsigned long long)) != cudaSuccess) { cudaFree(dout); return SEPGPU_ECUDA; }
     cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), c->stream);
-    k_export_pairs<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount);
+    k_export_pairs<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);

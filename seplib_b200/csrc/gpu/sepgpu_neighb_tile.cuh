@@ -41,6 +41,11 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
     const int ncx = min(G.bx, G.nx - x0);
     const int ncc = ncx + 2, ncell = 9 * ncc;
     const int key0 = blockIdx.x * G.bx;
+    if (G.dd && (cz == 0 || cz == G.nz - 1)) {                   // halo layer: its atoms own no rows
+        const int b = cell_start[key0], e = cell_start[key0 + ncx];
+        for (int q = b + threadIdx.x; q < e; q += TILE2_THREADS) cnt[q] = 0;
+        return;
+    }
     if (threadIdx.x <= ncx) s_home[threadIdx.x] = cell_start[key0 + threadIdx.x];
     if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
     if (threadIdx.x < ncell) {
@@ -49,7 +54,10 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
         int mx = x0 - 1 + cc, wx = 0, my = cy + oy, wy = 0, mz = cz + oz, wz = 0;
         if (mx >= G.nx) { mx -= G.nx; wx = 1; } else if (mx < 0) { mx += G.nx; wx = -1; }
         if (my == G.ny) { my = 0; wy = 1; } else if (my == -1) { my = G.ny - 1; wy = -1; }
-        if (mz == G.nz) { mz = 0; wz = 1; } else if (mz == -1) { mz = G.nz - 1; wz = -1; }
+        if (G.dd) {                       // slab: no wrap in the local layer index; the image follows the global layer
+            const int gl = G.zoff + mz;
+            wz = gl < 0 ? -1 : (gl >= G.nzg ? 1 : 0);
+        } else if (mz == G.nz) { mz = 0; wz = 1; } else if (mz == -1) { mz = G.nz - 1; wz = -1; }
         const int key = cell_key(mx, my, mz, G);
         const int b = cell_start[key];
         s_beg[threadIdx.x] = b;

@@ -4,6 +4,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+void sepgpu_dd_destroy(sepgpu_ctx *c);
+int sepgpu_dd_reduce_force_scalars(sepgpu_ctx *c, double *epot, double *ecoul, double *pot_P, double *pot_P_bond);
+
 static thread_local char g_err[512] = "";
 
 void sepgpu_set_error(const char *fmt, ...)
@@ -67,6 +70,9 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     sepgpu_ctx *c = (sepgpu_ctx *)calloc(1, sizeof(sepgpu_ctx));
     if (!c) return SEPGPU_EINVAL;
     c->n = (int)npart;
+    c->n_own = c->n;
+    c->ncap = c->n;
+    c->n_global = (long long)npart;
     c->npad = (c->n + 31) & ~31;
     c->device = device;
     c->pending_alpha_slot = -1;
@@ -108,6 +114,8 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    sepgpu_dd_destroy(c);
+    if (c->gid) cudaFree(c->gid);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
                     c->rank, c->cell_of, c->cell_cnt, c->cell_start, c->tmp_slot, c->nbr, c->cnt,
@@ -220,7 +228,7 @@ static FieldInfo field_info(int field)
     case SEPGPU_F_PV: case SEPGPU_F_PA: case SEPGPU_F_A: return {sizeof(double), 3};
     case SEPGPU_F_M: case SEPGPU_F_Z: return {sizeof(double), 1};
     case SEPGPU_F_TYPE: return {1, 1};
-    case SEPGPU_F_MOLINDEX: return {sizeof(int), 1};
+    case SEPGPU_F_MOLINDEX: case SEPGPU_F_GID: return {sizeof(int), 1};
     case SEPGPU_F_CROSS_NEIGHB: case SEPGPU_F_CROSSINGS: return {sizeof(int), 3};
     case SEPGPU_F_BOND: case SEPGPU_F_ANGLE: return {sizeof(int), 10};
     case SEPGPU_F_DIHED: return {sizeof(int), 20};
@@ -243,7 +251,7 @@ extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t str
     FieldInfo fi = field_info(field);
     if (!fi.elem || field == SEPGPU_F_A) { sepgpu_set_error("sepgpu_put: bad field %d", field); return SEPGPU_EINVAL; }
     CUDA_TRY(cudaSetDevice(c->device));
-    const size_t row = fi.elem * fi.width, n = (size_t)c->n;
+    const size_t row = fi.elem * fi.width, n = (size_t)c->n_own;
     if (stride == 0) stride = row;
     int rc = sepgpu_ensure_stage(c, row * n);
     if (rc) return rc;
@@ -254,34 +262,34 @@ extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t str
     if (stride == row) memcpy(dst, src, row * n);
     else for (size_t i = 0; i < n; i++) memcpy(dst + i * row, src + i * stride, row);
     CUDA_TRY(cudaMemcpyAsync(c->dstage, c->stage, row * n, cudaMemcpyHostToDevice, c->stream));
-    const int B = 256, G = (c->n + B - 1) / B;
+    const int B = 256, G = (c->n_own + B - 1) / B;
     switch (field) {
     case SEPGPU_F_X:
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->x4, (const double *)c->dstage, c->n);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->x4, (const double *)c->dstage, c->n_own);
         c->xs_current = false; c->list_valid = false;
         break;
     case SEPGPU_F_V:
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n_own);
         c->mv2_valid = false;
         break;
     case SEPGPU_F_F:
         if ((rc = sepgpu_apply_pending(c))) return rc;
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->f4, (const double *)c->dstage, c->n);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->f4, (const double *)c->dstage, c->n_own);
         c->f_zero = false;
         break;
     case SEPGPU_F_XN:
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->xn4, (const double *)c->dstage, c->n);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->xn4, (const double *)c->dstage, c->n_own);
         break;
     case SEPGPU_F_PV:
         if ((rc = ensure_dpd(c))) return rc;
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pv4, (const double *)c->dstage, c->n);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pv4, (const double *)c->dstage, c->n_own);
         break;
     case SEPGPU_F_PA:
         if ((rc = ensure_dpd(c))) return rc;
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pa4, (const double *)c->dstage, c->n);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pa4, (const double *)c->dstage, c->n_own);
         break;
     case SEPGPU_F_M:
-        k_scalar_to_w<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n);
+        k_scalar_to_w<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n_own);
         c->mv2_valid = false;
         break;
     case SEPGPU_F_Z: {
@@ -294,7 +302,7 @@ extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t str
         break;
     }
     case SEPGPU_F_TYPE: {
-        k_set_type<<<G, B, 0, c->stream>>>(c->x4, (const char *)c->dstage, c->n);
+        k_set_type<<<G, B, 0, c->stream>>>(c->x4, (const char *)c->dstage, c->n_own);
         const unsigned char *ht = (const unsigned char *)c->stage;
         int st = ht[0];
         for (size_t i = 1; i < n && st >= 0; i++) if (ht[i] != ht[0]) st = -1;
@@ -303,14 +311,18 @@ extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t str
         break;
     }
     case SEPGPU_F_MOLINDEX:
-        k_set_mol<<<G, B, 0, c->stream>>>(c->x4, (const int *)c->dstage, c->n);
+        k_set_mol<<<G, B, 0, c->stream>>>(c->x4, (const int *)c->dstage, c->n_own);
         c->xs_current = false; c->list_valid = false;
         break;
     case SEPGPU_F_CROSS_NEIGHB:
-        k_int3_to_cr<<<G, B, 0, c->stream>>>(c->cr4, (const int *)c->dstage, c->n);
+        k_int3_to_cr<<<G, B, 0, c->stream>>>(c->cr4, (const int *)c->dstage, c->n_own);
         break;
     case SEPGPU_F_CROSSINGS:
         CUDA_TRY(cudaMemcpyAsync(c->crossings, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        break;
+    case SEPGPU_F_GID:
+        if (!c->gid && dalloc(&c->gid, (size_t)c->ncap)) return SEPGPU_ECUDA;
+        CUDA_TRY(cudaMemcpyAsync(c->gid, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
         break;
     case SEPGPU_F_BOND: case SEPGPU_F_ANGLE: case SEPGPU_F_DIHED: {
         int **tab = field == SEPGPU_F_BOND ? &c->excl_bond : field == SEPGPU_F_ANGLE ? &c->excl_angle : &c->excl_dihed;
@@ -331,36 +343,37 @@ extern "C" int sepgpu_get(sepgpu_ctx *c, int field, void *host, size_t stride)
     FieldInfo fi = field_info(field);
     if (!fi.elem) { sepgpu_set_error("sepgpu_get: bad field %d", field); return SEPGPU_EINVAL; }
     CUDA_TRY(cudaSetDevice(c->device));
-    const size_t row = fi.elem * fi.width, n = (size_t)c->n;
+    const size_t row = fi.elem * fi.width, n = (size_t)c->n_own;
     if (stride == 0) stride = row;
     int rc = sepgpu_ensure_stage(c, row * n);
     if (rc) return rc;
-    const int B = 256, G = (c->n + B - 1) / B;
+    const int B = 256, G = (c->n_own + B - 1) / B;
     const void *dsrc = c->dstage;
     switch (field) {
-    case SEPGPU_F_X: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->x4, c->n); break;
-    case SEPGPU_F_V: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n); break;
+    case SEPGPU_F_X: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->x4, c->n_own); break;
+    case SEPGPU_F_V: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n_own); break;
     case SEPGPU_F_F:
         if ((rc = sepgpu_apply_pending(c))) return rc;
         if (c->f_zero) CUDA_TRY(cudaMemsetAsync(c->dstage, 0, row * n, c->stream));
-        else k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->n);
+        else k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->n_own);
         break;
     case SEPGPU_F_A:
         if ((rc = sepgpu_apply_pending(c))) return rc;
         if (c->f_zero) CUDA_TRY(cudaMemsetAsync(c->dstage, 0, row * n, c->stream));
-        else k_accel<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->v4, c->n);
+        else k_accel<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->v4, c->n_own);
         break;
-    case SEPGPU_F_XN: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->xn4, c->n); break;
+    case SEPGPU_F_XN: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->xn4, c->n_own); break;
     case SEPGPU_F_PV: case SEPGPU_F_PA:
         if (!c->have_dpd) { sepgpu_set_error("sepgpu_get: no DPD state"); return SEPGPU_ESTATE; }
-        k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, field == SEPGPU_F_PV ? c->pv4 : c->pa4, c->n);
+        k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, field == SEPGPU_F_PV ? c->pv4 : c->pa4, c->n_own);
         break;
-    case SEPGPU_F_M: k_w_to_scalar<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n); break;
+    case SEPGPU_F_M: k_w_to_scalar<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n_own); break;
     case SEPGPU_F_Z: dsrc = c->z; break;
-    case SEPGPU_F_TYPE: k_get_type<<<G, B, 0, c->stream>>>((char *)c->dstage, c->x4, c->n); break;
-    case SEPGPU_F_MOLINDEX: k_get_mol<<<G, B, 0, c->stream>>>((int *)c->dstage, c->x4, c->n); break;
-    case SEPGPU_F_CROSS_NEIGHB: k_cr_to_int3<<<G, B, 0, c->stream>>>((int *)c->dstage, c->cr4, c->n); break;
+    case SEPGPU_F_TYPE: k_get_type<<<G, B, 0, c->stream>>>((char *)c->dstage, c->x4, c->n_own); break;
+    case SEPGPU_F_MOLINDEX: k_get_mol<<<G, B, 0, c->stream>>>((int *)c->dstage, c->x4, c->n_own); break;
+    case SEPGPU_F_CROSS_NEIGHB: k_cr_to_int3<<<G, B, 0, c->stream>>>((int *)c->dstage, c->cr4, c->n_own); break;
     case SEPGPU_F_CROSSINGS: dsrc = c->crossings; break;
+    case SEPGPU_F_GID: dsrc = c->gid; break;
     case SEPGPU_F_BOND: dsrc = c->excl_bond; break;
     case SEPGPU_F_ANGLE: dsrc = c->excl_angle; break;
     case SEPGPU_F_DIHED: dsrc = c->excl_dihed; break;
@@ -427,6 +440,11 @@ extern "C" int sepgpu_read_scalars(sepgpu_ctx *c, sepgpu_scalars *out)
     out->error = s->error;
     out->max_neighb = s->max_neighb;
     out->npairs_listed = s->npairs_listed;
+    if (c->dd) {
+        // decomposed run: integrator-derived values are already global; force-derived sums are per rank
+        int rc = sepgpu_dd_reduce_force_scalars(c, &out->epot, &out->ecoul, out->pot_P, out->pot_P_bond);
+        if (rc) return rc;
+    }
     return 0;
 }
 
