@@ -229,13 +229,57 @@ def host_cores():
 
 
 # ---------------------------------------------------------------------------------------------------
+def weak_lattice_dims(ncell, world):
+    """Lattice sides for `world` GPUs at ncell^3 atoms per GPU (weak scaling, near-cubic box, z longest):
+    1 -> n,n,n ; 2 -> n,n,2n ; 4 -> n,2n,2n ; 8 -> 2n,2n,2n."""
+    dims = [ncell, ncell, ncell]
+    k, w = 2, world
+    while w > 1:
+        if w % 2:
+            raise ValueError("GPU count must be a power of two")
+        dims[k] *= 2
+        k = (k - 1) % 3
+        w //= 2
+    return dims
+
+
+def lattice_box(dims, rho):
+    a = (1.0 / rho) ** (1.0 / 3.0)
+    return [d * a for d in dims], a
+
+
+def slab_atoms(dims, a, zlo, zhi, lsz):
+    """Lattice atoms (global id, position) whose cell layer (int)(z/lsz) lies in [zlo,zhi)."""
+    nx, ny, nz = dims
+    gz = (np.arange(nz) + 0.5) * a
+    layer = np.floor(gz / lsz).astype(np.int64)
+    kz = np.nonzero((layer >= zlo) & (layer < zhi))[0]
+    gx = (np.arange(nx) + 0.5) * a
+    gy = (np.arange(ny) + 0.5) * a
+    z, y, x = np.meshgrid(gz[kz], gy, gx, indexing="ij")
+    pos = np.ascontiguousarray(np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1))
+    iz, iy, ix = np.meshgrid(kz, np.arange(ny), np.arange(nx), indexing="ij")
+    gid = (iz.ravel() * ny + iy.ravel()) * nx + ix.ravel()
+    return pos, gid.astype(np.int32)
+
+
+def slab_velocities(gid, n_total, temp, seed):
+    """Velocities drawn per global id (same on every decomposition), drift removed, rescaled to temp."""
+    rng = np.random.default_rng(seed)
+    v = rng.random((n_total, 3)) - 0.5
+    v -= v.mean(axis=0)
+    v *= np.sqrt(3 * n_total * temp / (v * v).sum())
+    return np.ascontiguousarray(v[gid])
+
+
+# ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ncell", type=int, default=100, help="lattice side: ncell^3 atoms per GPU (weak) / total (DD)")
+    ap.add_argument("--ncell", type=int, default=100, help="lattice side: ncell^3 atoms per GPU")
     ap.add_argument("--rho", type=float, default=0.8)
     ap.add_argument("--skin", type=float, default=0.25)
     ap.add_argument("--tpa", type=int, default=0)
@@ -245,7 +289,17 @@ def main():
     ap.add_argument("--cpu-ncell", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of domain decomposition")
     args = ap.parse_args()
+
+    # stdout carries exactly ONE line (the JSON): libraries that print banners to fd 1 (NCCL version line,
+    # the reference's sep-warning) are sent to stderr for the duration of the run.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -268,54 +322,88 @@ def main():
                 "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     import torch
     import torch.distributed as dist
     from seplib_b200 import capi
 
+    torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
     lib = capi.load()
     if lib.sepgpu_device_count() <= 0:
         raise RuntimeError("bench.py: no CUDA device -- seplib-b200 has no CPU path")
+    decomposed = world > 1 and not args.replicas
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm -------------------------------------------------------
-    x, L = lj_lattice(args.ncell, args.rho)
-    n = len(x)
-    v = lj_velocities(n, temp, 1000 + rank)
-    s = capi.System(n, device=local_rank)
-    if args.tpa:
-        s.call("sepgpu_set_option", b"tpa", args.tpa)
-    if args.unroll:
-        s.call("sepgpu_set_option", b"unroll", args.unroll)
-    if args.force_grid:
-        s.call("sepgpu_set_option", b"force_grid", args.force_grid)
-    s.put(capi.F_X, x)
-    s.put(capi.F_V, v)
-    s.call("sepgpu_set_alpha", 0, 0.1)
-    gsys = capi.make_sys([L] * 3, rc, dt, skin=args.skin)
+    # ---------------- workload ---------------------------------------------------------------------
+    if decomposed:
+        dims = weak_lattice_dims(args.ncell, world)
+    else:
+        dims = [args.ncell] * 3
+    Lvec, a_lat = lattice_box(dims, args.rho)
+    n_total = dims[0] * dims[1] * dims[2]
+    gsys = capi.make_sys(Lvec, rc, dt, skin=args.skin)
+    nzg = gsys.nsubbox[2]
+    if decomposed:
+        z0, z1 = capi.dd_slab_range(rank, world, nzg)
+        x, gid = slab_atoms(dims, a_lat, z0, z1, gsys.lsubbox[2])
+        v = slab_velocities(gid, n_total, temp, 1000)
+        n = len(x)
+        ncap = int(1.25 * n_total / world) + int(3.5 * n_total / nzg) + 4096
+    else:
+        x, gid = slab_atoms(dims, a_lat, 0, nzg + 1, gsys.lsubbox[2])
+        v = slab_velocities(gid, n_total, temp, 1000 + rank)
+        n = len(x)
+        ncap = n
     ljp = capi.lj_param(rc, kind="lj_shift")
     gs_ref, lj_ref = C.byref(gsys), C.byref(ljp)
-    fn = lib
-    ctx = s.ctx
 
-    def step_dev():
-        fn.sepgpu_reset_ret(ctx)
-        fn.sepgpu_reset_force(ctx)
-        rc_ = fn.sepgpu_force_lj(ctx, gs_ref, b"AA", lj_ref, 1, 1)     # rebuilds the list itself when the trigger fired
-        rc_ |= fn.sepgpu_nosehoover(ctx, gs_ref, temp, 0, tau)
-        rc_ |= fn.sepgpu_leapfrog(ctx, gs_ref)
-        if rc_:
-            raise RuntimeError("device step failed: " + fn.sepgpu_last_error().decode())
+    def new_system():
+        s_ = capi.System(ncap, device=local_rank)
+        if decomposed:
+            # one NCCL communicator per context: a fresh unique id from rank 0 each time
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(capi.dd_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            s_.dd_init(rank, world, bytes(idt.cpu().numpy().tobytes()), gsys, n_total)
+            s_.dd_set_owned(n)
+        for opt, val in (("tpa", args.tpa), ("unroll", args.unroll), ("force_grid", args.force_grid)):
+            if val:
+                s_.call("sepgpu_set_option", opt.encode(), val)
+        return s_
 
+    def upload(s_):
+        s_.put(capi.F_X, x)
+        s_.put(capi.F_V, v)
+        if decomposed:
+            s_.put(capi.F_GID, gid)
+        s_.call("sepgpu_set_alpha", 0, 0.1)
+
+    def make_step(s_):
+        ctx, fn = s_.ctx, lib
+
+        def step():
+            fn.sepgpu_reset_ret(ctx)
+            fn.sepgpu_reset_force(ctx)
+            r = fn.sepgpu_force_lj(ctx, gs_ref, b"AA", lj_ref, 1, 1)      # rebuilds the list itself when the trigger fired
+            r |= fn.sepgpu_nosehoover(ctx, gs_ref, temp, 0, tau)
+            r |= fn.sepgpu_leapfrog(ctx, gs_ref)
+            if r:
+                raise RuntimeError("device step failed: " + fn.sepgpu_last_error().decode())
+        return step
+
+    # ---------------- device-resident arm -------------------------------------------------------
+    s = new_system()
+    upload(s)
+    step_dev = make_step(s)
     for _ in range(W):
         step_dev()
     nb0 = s.scalars().nbuild
@@ -345,64 +433,94 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     t_sec = float(t_ms.item()) * 1e-3
-    total_atoms = n * world
+    total_atoms = n_total if decomposed else n * world
     value = total_atoms * K / t_sec
-    epotN, ekinN = sc.epot / n, sc.ekin / n
-    pairs_per_atom = sc.npairs_listed / n / 2.0
+    norm = n_total if decomposed else n
+    epotN, ekinN = sc.epot / norm, sc.ekin / norm
+    pairs_per_atom = sc.npairs_listed / max(s.dd_layers()[2] if decomposed else n, 1) / 2.0
+    own_halo = s.dd_layers()[2:] if decomposed else (n, 0)
     s.close()
 
-    # ---------------- e2e arm: sep_* API, host seppart[] buffers ------------------------------------
+    # ---------------- e2e arm: host buffers in, host buffers out ------------------------------------
     e2e = None
     if not args.no_e2e:
-        lib.sep_gpu_set_sync(0)          # SEP_SYNC_LAZY: scalars every step, atoms[] at the end
         Ke = max(10, min(K, 300))
-        atoms = lib.sep_init(n, 0)
-        view = capi.atoms_view(atoms, n)
-        view["x"][:] = x
-        view["v"][:] = v
-        hsys = lib.sep_sys_setup(L, L, L, rc, dt, n, capi.SEP_LLIST_NEIGHBLIST)
-        lib.sep_set_skin(C.byref(hsys), args.skin)
-        ret = capi.SepRet()
-        alpha = C.c_double(0.1)
-        fun = C.cast(lib.sep_lj_shift, C.c_void_p)
+        if not decomposed:
+            # the reference-facing sep_* API of include/sep.h on a host seppart[] array
+            lib.sep_gpu_set_sync(0)          # SEP_SYNC_LAZY: scalars every step, atoms[] at the end
+            atoms = lib.sep_init(n, 0)
+            view = capi.atoms_view(atoms, n)
+            view["x"][:] = x
+            view["v"][:] = v
+            hsys = lib.sep_sys_setup(Lvec[0], Lvec[1], Lvec[2], rc, dt, n, capi.SEP_LLIST_NEIGHBLIST)
+            lib.sep_set_skin(C.byref(hsys), args.skin)
+            ret = capi.SepRet()
+            alpha = C.c_double(0.1)
+            fun = C.cast(lib.sep_lj_shift, C.c_void_p)
 
-        def step_api():
-            lib.sep_reset_retval(C.byref(ret))
-            lib.sep_reset_force(atoms, C.byref(hsys))
-            lib.sep_force_pairs(atoms, b"AA", rc, fun, C.byref(hsys), C.byref(ret), capi.SEP_ALL)
-            lib.sep_nosehoover(atoms, temp, C.byref(alpha), tau, C.byref(hsys))
-            lib.sep_leapfrog(atoms, C.byref(hsys), C.byref(ret))
+            def step_api():
+                lib.sep_reset_retval(C.byref(ret))
+                lib.sep_reset_force(atoms, C.byref(hsys))
+                lib.sep_force_pairs(atoms, b"AA", rc, fun, C.byref(hsys), C.byref(ret), capi.SEP_ALL)
+                lib.sep_nosehoover(atoms, temp, C.byref(alpha), tau, C.byref(hsys))
+                lib.sep_leapfrog(atoms, C.byref(hsys), C.byref(ret))
 
-        # warm-up on a throw-away context state: run, then restore the host arrays and force a re-upload
-        for _ in range(max(3, min(W, 20))):
-            step_api()
-        view["x"][:] = x
-        view["v"][:] = v
-        view["xn"][:] = 0.0
-        view["cross_neighb"][:] = 0
-        view["crossings"][:] = 0
-        lib.sep_gpu_invalidate(atoms)
-        hsys.neighb_flag = 1
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(Ke):
-            step_api()                   # first call uploads x,v,m,z,type,... from the host array
-        lib.sep_gpu_sync(atoms)          # final state back into atoms[]
-        torch.cuda.synchronize()
-        el = time.perf_counter() - t0
+            for _ in range(max(3, min(W, 20))):          # warm-up, then restore the host arrays and re-upload
+                step_api()
+            view["x"][:] = x
+            view["v"][:] = v
+            view["xn"][:] = 0.0
+            view["cross_neighb"][:] = 0
+            view["crossings"][:] = 0
+            lib.sep_gpu_invalidate(atoms)
+            hsys.neighb_flag = 1
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                step_api()                   # first call uploads x,v,m,z,type,... from the host array
+            lib.sep_gpu_sync(atoms)          # final state back into atoms[]
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            e_epot = ret.epot / n
+            lib.sep_close(atoms, n)
+            how = ("sep_* API (include/sep.h), SEP_SYNC=lazy: sepret/sepsys scalars D2H every step; seppart[] uploaded at "
+                   "step 0 and downloaded after the last step, both inside the timed region")
+            h2d = n * (24 * 3 + 8 * 2 + 1 + 4 + 12 * 2)            # x, v, xn, m, z, type, molindex, cross_neighb, crossings
+            d2h_final = n * (24 * 4 + 12 * 2 + 24)                 # x, v, f, a, counters, xn
+        else:
+            # decomposed: the sepgpu_* C ABI with host numpy buffers (the sep_* API is one process / one GPU)
+            s2 = new_system()
+            step2 = make_step(s2)
+            upload(s2)
+            for _ in range(max(3, min(W, 20))):
+                step2()
+            s2.close()
+            s2 = new_system()
+            step2 = make_step(s2)
+            barrier()
+            t0 = time.perf_counter()
+            upload(s2)                       # H2D from host arrays
+            for _ in range(Ke):
+                step2()
+                sce = s2.scalars()           # D2H of the step's scalars (collective)
+            s2.dd_layers()
+            xo, vo, fo, go = s2.get(capi.F_X), s2.get(capi.F_V), s2.get(capi.F_F), s2.get(capi.F_GID)   # D2H
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            e_epot = sce.epot / n_total
+            s2.close()
+            how = ("sepgpu_* C ABI with host buffers (decomposed run): x,v,gid H2D at step 0, scalar block D2H every step, "
+                   "x,v,f,gid D2H after the last step, all inside the timed region")
+            h2d = n * (24 * 2 + 4)
+            d2h_final = n * (24 * 3 + 4)
         t_e = torch.tensor([el], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         el = float(t_e.item())
-        h2d = n * (24 * 3 + 8 * 2 + 1 + 4 + 12 * 2)            # x, v, xn, m, z, type, molindex, cross_neighb, crossings
-        d2h_final = n * (24 * 4 + 12 * 2 + 24)                 # x, v, f, a, counters, xn
-        scal_bytes = 416                                       # sizeof(DevScalars) per integrator call
+        scal_bytes = 416
         e2e = {"value": total_atoms * Ke / el, "unit": UNIT,
                "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": scal_bytes + d2h_final / Ke,
-               "steps": Ke, "sync": "lazy: sepret/sepsys scalars D2H every step; seppart[] uploaded at step 0 "
-                                     "and downloaded after the last step, both inside the timed region",
-               "epot_per_atom": ret.epot / n}
-        lib.sep_close(atoms, n)
+               "steps": Ke, "path": how, "epot_per_atom": e_epot}
 
     if rank != 0:
         if world > 1:
@@ -419,10 +537,11 @@ def main():
     n_list, n_in, alg_flops, alg_bytes = algorithmic_per_atom(args.rho, rc, args.skin)
     f_ms, f_cnt = kt["force"]
     force_ms = f_ms / max(f_cnt, 1)
-    achieved_gbs = alg_bytes * n / (force_ms * 1e-3) / 1e9
+    n_kernel = own_halo[0]                      # atoms whose rows one launch on this rank processes
+    achieved_gbs = alg_bytes * n_kernel / (force_ms * 1e-3) / 1e9
     fp64_peak = C.c_double()
     lib.sepgpu_peak_fp64(local_rank, C.byref(fp64_peak))
-    achieved_tf = alg_flops * n / (force_ms * 1e-3) / 1e12
+    achieved_tf = alg_flops * n_kernel / (force_ms * 1e-3) / 1e12
     traffic = None
     prof = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
     if os.path.exists(prof):
@@ -447,22 +566,31 @@ def main():
         except Exception as e:      # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
 
-    launches = K * 7 + nbuild * 9      # reset_ret, reset_maxdist, force, finalize, nh_update, integrate, finalize (+1 set_xn, +8 build)
+    # kernels of this rank in the timed region: reset_ret, reset_maxdist, force, finalize, nh_update, integrate,
+    # finalize (x2 + 2 halo pack/unpack when decomposed); per rebuild: set_xn + 10 build kernels (+ ~25 migration/halo)
+    per_step = 7 + (5 if decomposed else 0)
+    per_build = 11 + (25 if decomposed else 0)
+    launches = (K * per_step + nbuild * per_build) * (world if decomposed else 1)
+    if decomposed:
+        par = f"{world}-way slab domain decomposition along z (NCCL P2P halo + migration, all-reduce per step)"
+    else:
+        par = "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_sec * 1e3 / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C1 prg1-style LJ NVT: sep_force_pairs(sep_lj_shift, rc=2.5) + sep_nosehoover + sep_leapfrog",
-                   "natoms_per_gpu": n, "natoms_total": total_atoms, "rho": args.rho, "skin": args.skin, "dt": dt,
-                   "T0": temp, "tau": tau, "lattice": f"sc {args.ncell}^3",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one per GPU)",
-                   "l2": "inputs larger than L2 (xs 32 MB + Verlet list %.0f MB + state > 126 MB)" % (n * pairs_per_atom * 8 / 1e6),
+        "config": {"workload": "prg1-style LJ NVT: sep_force_pairs(sep_lj_shift, rc=2.5) + sep_nosehoover + sep_leapfrog"
+                               + (" (C1, 1M atoms)" if world == 1 else f" ({total_atoms} atoms; C4 at 8 GPUs)"),
+                   "natoms_per_gpu": total_atoms // world, "natoms_total": total_atoms, "rho": args.rho, "skin": args.skin,
+                   "dt": dt, "T0": temp, "tau": tau, "lattice": "sc %dx%dx%d" % tuple(dims), "parallelism": par,
+                   "rank0_owned_halo_atoms": list(own_halo),
+                   "l2": "inputs larger than L2 (xs 32 MB + Verlet list %.0f MB + state > 126 MB per GPU)" % (own_halo[0] * pairs_per_atom * 8 / 1e6),
                    "list_rebuilds_in_timed_region": nbuild, "half_pairs_per_atom": pairs_per_atom,
                    "epot_per_atom": epotN, "ekin_per_atom": ekinN},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "kernel_ms": {k: {"total_ms": a, "launches": b} for k, (a, b) in kt.items()},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
