@@ -56,8 +56,19 @@ __global__ void k_cell_count(const d4 *__restrict__ x4, int n, double lsx, doubl
     int cx = (int)__ddiv_rn(p.x, lsx), cy = (int)__ddiv_rn(p.y, lsy), cz = (int)__ddiv_rn(p.z, lsz);
     const int nzg = G.dd ? G.nzg : G.nz;
     if (cx < 0 || cx >= G.nx || cy < 0 || cy >= G.ny || cz < 0 || cz >= nzg || !(p.x == p.x)) {
-        scal->error = SEPGPU_ECELL;
-        cx = min(max(cx, 0), G.nx - 1); cy = min(max(cy, 0), G.ny - 1); cz = min(max(cz, 0), nzg - 1);
+        // The reference does not clamp: it forms the linear index cx + cy*nx + cz*nx*ny and, while that
+        // stays inside the head array, files the atom under whatever cell the index aliases to
+        // (source/sepprfrc.c:404-412; e.g. sep_set_lattice's +1.0 offset in prg6 puts atoms beyond L).
+        // Reproduce that, and make the host redo this build with the exact (minimum-image) builder,
+        // because an aliased atom breaks the cell-image == minimum-image premise of the fast one.
+        const long long lin = (long long)cx + (long long)cy * G.nx + (long long)cz * G.nx * G.ny;
+        if (G.dd || !(p.x == p.x) || lin < 0 || lin >= (long long)G.nx * G.ny * nzg) {
+            scal->error = SEPGPU_ECELL;
+            cx = min(max(cx, 0), G.nx - 1); cy = min(max(cy, 0), G.ny - 1); cz = min(max(cz, 0), nzg - 1);
+        } else {
+            cx = (int)(lin % G.nx); cy = (int)((lin / G.nx) % G.ny); cz = (int)(lin / ((long long)G.nx * G.ny));
+            scal->sum_mv2_valid = 1;            // "aliased atom seen" flag of this build
+        }
     }
     if (G.dd) {                         // global layer -> local layer of this slab
         cz -= G.zoff;
@@ -470,7 +481,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 
 #include "sepgpu_neighb_tile.cuh"
 
-__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->xn_pending = 0; }
+__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->xn_pending = 0; s->sum_mv2_valid = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
 int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local);
@@ -527,6 +538,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
     if (c->cap == 0) c->cap = estimate_cap(c, sys);
 
     const int B = 256, Gn = (c->n + B - 1) / B;
+    bool force_exact = false;
     for (int attempt = 0; attempt < 8; attempt++) {
         if (!c->nbr) CUDA_TRY(cudaMalloc((void **)&c->nbr, sizeof(unsigned) * (size_t)c->cap * c->npad));
 
@@ -552,7 +564,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         const double Lmax = fmax(P.Lx, fmax(P.Ly, P.Lz));
         const double wmin = fmin(sys->lsubbox[0], fmin(sys->lsubbox[1], sys->lsubbox[2]));
         const double band = 4.2e-6 * cut * Lmax + 2e-6 * P.cut2;
-        P.prefilter = c->prefilter && nx >= 4 && ny >= 4 && nz >= 4 && cut < 1.95 * wmin && band < 0.05 * P.cut2;
+        P.prefilter = c->prefilter && !force_exact && nx >= 4 && ny >= 4 && nz >= 4 && cut < 1.95 * wmin && band < 0.05 * P.cut2;
         if (c->dd && !P.prefilter) { sepgpu_set_error("neighb_build: decomposed runs need >= 4 cells per direction"); return SEPGPU_EINVAL; }
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
@@ -596,6 +608,12 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (c->scal_host->max_half >= 3000) {         // SEP_NEIGHB, source/sepprfrc.c:499-501
             sepgpu_set_error("Too many neighbours");
             return SEPGPU_ENEIGHB;
+        }
+        if (c->scal_host->sum_mv2_valid && P.prefilter) {      // an atom outside [0,L) was filed under an aliased cell
+            force_exact = true;
+            c->scal_host->nbuild -= 1;
+            CUDA_TRY(cudaMemcpyAsync(&c->scal->nbuild, &c->scal_host->nbuild, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            continue;
         }
         if (c->scal_host->xn_pending > 0) {       // a tile needed a larger staging buffer: grow, rebuild
             c->tile_stage_cap = (c->scal_host->xn_pending * 5 / 4 + 63) & ~31;

@@ -134,7 +134,7 @@ def test_error_paths():
     """Atom outside [0,L) -> the reference's 'Index larger than array length' class of error; bonded
     exclusion without partner tables; list force without anything to build from is fine (auto build)."""
     x, L = cm.lattice(8, 0.8, jitter=0.05, seed=1)
-    x[17, 0] = L * 1.5
+    x[-1, 2] = L * 1.5           # linear cell index beyond the grid (an x overshoot would alias like the reference's)
     s = capi.System(len(x)); s.put(capi.F_X, x)
     sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
     rc = s.lib.sepgpu_neighb_build(s.ctx, C.byref(sys_), 1)
@@ -144,6 +144,23 @@ def test_error_paths():
     s = capi.System(len(x)); s.put(capi.F_X, x)
     assert s.lib.sepgpu_neighb_build(s.ctx, C.byref(sys_), cm.EXCL_BONDED) == -6     # SEPGPU_ESTATE
     assert s.lib.sepgpu_coulomb_sf(s.ctx, C.byref(sys_), 2.5, 1) == -6               # no list yet
+    s.close()
+
+
+def test_positions_beyond_box_alias_like_the_reference():
+    """sep_set_lattice offsets atoms by +1.0 (reference source/sepinit.c:333-345), which in prg6 puts some at
+    x > L.  The reference files them under whatever cell the unclamped linear index hits
+    (source/sepprfrc.c:404-412); the oracle restates that, and the device build must list the same pairs."""
+    x, L = cm.lattice(16, 0.8, jitter=0.1, seed=12)
+    x[::37, 0] += L * 0.04          # a few atoms slightly beyond the box in x
+    x[5::41, 1] += L * 0.03
+    inside = x[:, 2] < L - 3.0      # keep z overshoots out: they would leave the head array
+    x = np.ascontiguousarray(x[inside])
+    ref_pairs = cm.pair_set(cm.oracle_pairs(x, L, 2.5, 0.25))
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    s.call("sepgpu_neighb_build", C.byref(sys_), 1)
+    assert np.array_equal(cm.pair_set(s.pairs()), ref_pairs)
     s.close()
 
 
