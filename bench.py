@@ -465,8 +465,9 @@ def main():
                 lib.sep_nosehoover(atoms, temp, C.byref(alpha), tau, C.byref(hsys))
                 lib.sep_leapfrog(atoms, C.byref(hsys), C.byref(ret))
 
-            for _ in range(max(3, min(W, 20))):          # warm-up, then restore the host arrays and re-upload
+            for _ in range(max(3, min(W, 20))):          # warm-up (both directions), then restore the host arrays and re-upload
                 step_api()
+            lib.sep_gpu_sync(atoms)
             view["x"][:] = x
             view["v"][:] = v
             view["xn"][:] = 0.0
@@ -476,11 +477,16 @@ def main():
             hsys.neighb_flag = 1
             barrier()
             t0 = time.perf_counter()
-            for _ in range(Ke):
-                step_api()                   # first call uploads x,v,m,z,type,... from the host array
+            step_api()                       # first call uploads x,v,m,z,type,... from the host array
+            t_up = time.perf_counter()
+            for _ in range(Ke - 1):
+                step_api()
+            t_st = time.perf_counter()
             lib.sep_gpu_sync(atoms)          # final state back into atoms[]
             torch.cuda.synchronize()
             el = time.perf_counter() - t0
+            log("e2e breakdown: first step incl. upload %.1f ms, %d steps %.1f ms, download %.1f ms"
+                % (1e3 * (t_up - t0), Ke - 1, 1e3 * (t_st - t_up), 1e3 * (time.perf_counter() - t_st)))
             e_epot = ret.epot / n
             lib.sep_close(atoms, n)
             how = ("sep_* API (include/sep.h), SEP_SYNC=lazy: sepret/sepsys scalars D2H every step; seppart[] uploaded at "

@@ -107,6 +107,12 @@ int  sepgpu_device_count(void);
  * (stride = sizeof(seppart)) while tests pass packed numpy arrays (stride = element size). */
 int sepgpu_put(sepgpu_ctx *ctx, int field, const void *host, size_t stride_bytes);
 int sepgpu_get(sepgpu_ctx *ctx, int field, void *host, size_t stride_bytes);
+/* several fields of one record array in a single pass over host memory (parallel host threads) and a
+ * single PCIe transfer: field f of atom i lives at base + i*stride_bytes + offsets[f] */
+int sepgpu_put_fields(sepgpu_ctx *ctx, const void *base, size_t stride_bytes, int nfields,
+                      const int *fields, const size_t *offsets);
+int sepgpu_get_fields(sepgpu_ctx *ctx, void *base, size_t stride_bytes, int nfields,
+                      const int *fields, const size_t *offsets);
 /* topology lists in the reference layout (include/sepstrct.h:77-87): blist[3n], alist[4n], dlist[5n] */
 int sepgpu_set_topology(sepgpu_ctx *ctx, const unsigned *blist, unsigned nbonds,
                         const unsigned *alist, unsigned nangles,

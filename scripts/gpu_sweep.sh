@@ -1,2 +1,3 @@
 #!/bin/bash
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python bench.py --no-cpu --steps 300 --warmup 50 2>gpurun_out/e.err | python scripts/summ.py "default"
+grep "e2e breakdown" gpurun_out/e.err

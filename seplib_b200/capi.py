@@ -120,7 +120,7 @@ def atoms_view(ptr, n):
 # every symbol include/sepgpu.h declares (tests check that the library exports all of them)
 SEPGPU_SYMBOLS = [
     "sepgpu_create", "sepgpu_destroy", "sepgpu_last_error", "sepgpu_device_count", "sepgpu_put",
-    "sepgpu_get", "sepgpu_set_topology", "sepgpu_get_bonded_values", "sepgpu_reset_ret",
+    "sepgpu_get", "sepgpu_put_fields", "sepgpu_get_fields", "sepgpu_set_topology", "sepgpu_get_bonded_values", "sepgpu_reset_ret",
     "sepgpu_reset_force", "sepgpu_neighb_build", "sepgpu_force_lj", "sepgpu_coulomb_sf",
     "sepgpu_force_dpd", "sepgpu_stretch_harmonic", "sepgpu_angle_harmonic", "sepgpu_angle_cossq",
     "sepgpu_torsion_ryckaert", "sepgpu_nosehoover", "sepgpu_nosehoover_type", "sepgpu_set_alpha",

@@ -268,19 +268,30 @@ k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDe
 
 // ---- final reduction of the per-block partial rows ---------------------------------------------------------
 // flags: bit0 epot assign (source/sepprfrc.c:222), bit1 also add virial to pot_P_bond, bit2 add acc[1] to
-// ecoul AND epot (source/sepcoulomb.c:150-153)
-__global__ void __launch_bounds__(256)
+// ecoul AND epot (source/sepcoulomb.c:150-153), bit3 a sep_reset_retval is pending: clear the block first
+#define FIN_THREADS 1024
+__device__ __forceinline__ void reset_ret_block(DevScalars *s)
+{
+    s->epot = 0; s->ecoul = 0; s->ekin = 0;                        // sep_reset_retval, source/sepret.c:19-47
+    for (int k = 0; k < 9; k++) { s->pot_P[k] = 0; s->kin_P[k] = 0; s->pot_P_bond[k] = 0; }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
 k_finalize_force(const double *__restrict__ partial, int nrows, DevScalars *scal, double scale, int flags)
 {
-    __shared__ double red[SEPGPU_NPART_F * 8];
+    __shared__ double red[SEPGPU_NPART_F * (FIN_THREADS / 32)];
     double v[SEPGPU_NPART_F];
 #pragma unroll
     for (int q = 0; q < SEPGPU_NPART_F; q++) v[q] = 0.0;
-    for (int r = threadIdx.x; r < nrows; r += 256)
-#pragma unroll
-        for (int q = 0; q < SEPGPU_NPART_F; q++) v[q] += partial[r * SEPGPU_NPART_F + q];
-    block_sum<SEPGPU_NPART_F, 256>(v, red);
+    // fixed assignment of rows to threads and a fixed reduction tree: deterministic sums
+    for (int r = threadIdx.x; r < nrows; r += FIN_THREADS) {
+        const double4 a = *reinterpret_cast<const double4 *>(partial + (size_t)r * SEPGPU_NPART_F);
+        const double4 b = *reinterpret_cast<const double4 *>(partial + (size_t)r * SEPGPU_NPART_F + 4);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    block_sum<SEPGPU_NPART_F, FIN_THREADS>(v, red);
     if (threadIdx.x == 0) {
+        if (flags & 8) reset_ret_block(scal);
         const double e = v[0] * scale, ec = v[1] * scale;
         if (flags & 1) scal->epot = e; else scal->epot += e;
         if (flags & 4) { scal->epot += ec; scal->ecoul += ec; }
@@ -298,7 +309,8 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
 {
-    k_finalize_force<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, scale, flags);
+    if (c->ret_reset_pending) { flags |= 8; c->ret_reset_pending = false; }
+    k_finalize_force<<<1, FIN_THREADS, 0, c->stream>>>(c->partial, nrows, c->scal, scale, flags);
     KERNEL_CHECK();
     return 0;
 }

@@ -129,6 +129,8 @@ struct sepgpu_ctx {
     int  pending_alpha_slot;     // >=0: f -= alpha[slot] m v still to be applied by the integrator
     int  pending_alpha_type;     // -1 all atoms, else restrict to this type char
     bool xs_current;             // xs matches x4 (brute mode / after host put)
+    bool ret_reset_pending;      // sep_reset_retval seen: the next kernel that touches the scalar block clears it first
+    bool maxd_reset_pending;     // sep_reset_force seen: the next integrator starts max_dist2 from zero
 
     // staging
     void *stage; size_t stage_bytes;     // pinned host

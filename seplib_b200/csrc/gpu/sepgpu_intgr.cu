@@ -134,8 +134,13 @@ k_integrate(d4 *__restrict__ x4, d4 *__restrict__ v4, d4 *__restrict__ f4, const
 
 // one block: reduce the partial rows, update sepret/sepsys scalars, evaluate the skin trigger
 __global__ void __launch_bounds__(256)
-k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int mode, double *comm)
+k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int mode, double *comm, int resets)
 {
+    // resets: bit0 a sep_reset_retval is pending, bit1 a sep_reset_force (max_dist2 <- 0) is pending
+    if (mode != 1 && threadIdx.x == 0) {
+        if (resets & 1) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
+        if (resets & 2) scal->max_dist2 = 0.0;
+    }
     // mode 0: single GPU.  mode 1: decomposed run, phase A -- local sums into comm[0..11], local max into
     // comm[12]; the host all-reduces them (sum / max) over the ranks.  mode 2: phase B -- apply comm.
     if (mode == 2) {
@@ -230,14 +235,16 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     else
         k_integrate<false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
             c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial);
+    const int resets = (c->ret_reset_pending ? 1 : 0) | (c->maxd_reset_pending ? 2 : 0);
+    c->ret_reset_pending = false; c->maxd_reset_pending = false;
     if (c->dd) {
         double *comm = sepgpu_dd_comm(c);
-        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 1, comm);
+        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 1, comm, 0);
         int rcd = sepgpu_dd_allreduce(c, comm, 12, comm + 12, 1);
         if (rcd) return rcd;
-        k_finalize_intgr<<<1, 32, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 2, comm);
+        k_finalize_intgr<<<1, 32, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 2, comm, resets);
     } else {
-        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 0, NULL);
+        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 0, NULL, resets);
     }
     ktimer_end(c, &c->t_intgr);
     KERNEL_CHECK();

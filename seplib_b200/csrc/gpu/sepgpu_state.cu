@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdlib.h>
+#include <functional>
 
 void sepgpu_dd_destroy(sepgpu_ctx *c);
 int sepgpu_dd_reduce_force_scalars(sepgpu_ctx *c, double *epot, double *ecoul, double *pot_P, double *pot_P_bond);
@@ -245,56 +246,65 @@ static int ensure_dpd(sepgpu_ctx *c)
 }
 int sepgpu_ensure_dpd(sepgpu_ctx *c) { return ensure_dpd(c); }
 
-extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t stride)
+// ---- host <-> device field movement ----------------------------------------------------------------------
+// One pass over the caller's array gathers every requested field (parallel host threads; the AoS
+// seppart array is 568 B per atom, so a pass per field would re-stream it each time), one H2D copy moves
+// the packed block, and a small kernel per field converts to the 32-byte device records.
+#include <thread>
+#include <vector>
+
+static void parallel_rows(size_t n, const std::function<void(size_t, size_t)> &fn)
 {
-    if (!c || !host) return SEPGPU_EINVAL;
-    FieldInfo fi = field_info(field);
-    if (!fi.elem || field == SEPGPU_F_A) { sepgpu_set_error("sepgpu_put: bad field %d", field); return SEPGPU_EINVAL; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = n < 65536 ? 1 : (hw ? (hw > 16 ? 16 : hw) : 4);
+    if (nt <= 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (size_t t = 0; t < nt; t++) {
+        const size_t b = t * chunk, e = b + chunk < n ? b + chunk : n;
+        if (b < e) th.emplace_back(fn, b, e);
+    }
+    for (auto &x : th) x.join();
+}
+
+static int put_dispatch(sepgpu_ctx *c, int field, const void *dsrc, const void *hsrc)
+{
+    const FieldInfo fi = field_info(field);
     const size_t row = fi.elem * fi.width, n = (size_t)c->n_own;
-    if (stride == 0) stride = row;
-    int rc = sepgpu_ensure_stage(c, row * n);
-    if (rc) return rc;
-    // the previous async copy out of the staging buffer must be done before we overwrite it
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    const char *src = (const char *)host;
-    char *dst = (char *)c->stage;
-    if (stride == row) memcpy(dst, src, row * n);
-    else for (size_t i = 0; i < n; i++) memcpy(dst + i * row, src + i * stride, row);
-    CUDA_TRY(cudaMemcpyAsync(c->dstage, c->stage, row * n, cudaMemcpyHostToDevice, c->stream));
     const int B = 256, G = (c->n_own + B - 1) / B;
+    int rc;
     switch (field) {
     case SEPGPU_F_X:
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->x4, (const double *)c->dstage, c->n_own);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->x4, (const double *)dsrc, c->n_own);
         c->xs_current = false; c->list_valid = false;
         break;
     case SEPGPU_F_V:
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n_own);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->v4, (const double *)dsrc, c->n_own);
         c->mv2_valid = false;
         break;
     case SEPGPU_F_F:
         if ((rc = sepgpu_apply_pending(c))) return rc;
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->f4, (const double *)c->dstage, c->n_own);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->f4, (const double *)dsrc, c->n_own);
         c->f_zero = false;
         break;
     case SEPGPU_F_XN:
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->xn4, (const double *)c->dstage, c->n_own);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->xn4, (const double *)dsrc, c->n_own);
         break;
     case SEPGPU_F_PV:
         if ((rc = ensure_dpd(c))) return rc;
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pv4, (const double *)c->dstage, c->n_own);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pv4, (const double *)dsrc, c->n_own);
         break;
     case SEPGPU_F_PA:
         if ((rc = ensure_dpd(c))) return rc;
-        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pa4, (const double *)c->dstage, c->n_own);
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->pa4, (const double *)dsrc, c->n_own);
         break;
     case SEPGPU_F_M:
-        k_scalar_to_w<<<G, B, 0, c->stream>>>(c->v4, (const double *)c->dstage, c->n_own);
+        k_scalar_to_w<<<G, B, 0, c->stream>>>(c->v4, (const double *)dsrc, c->n_own);
         c->mv2_valid = false;
         break;
     case SEPGPU_F_Z: {
-        CUDA_TRY(cudaMemcpyAsync(c->z, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
-        const double *hz = (const double *)c->stage;
+        CUDA_TRY(cudaMemcpyAsync(c->z, dsrc, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        const double *hz = (const double *)hsrc;
         bool any = false;
         for (size_t i = 0; i < n && !any; i++) any = hz[i] != 0.0;
         c->have_charge = any;
@@ -302,8 +312,8 @@ extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t str
         break;
     }
     case SEPGPU_F_TYPE: {
-        k_set_type<<<G, B, 0, c->stream>>>(c->x4, (const char *)c->dstage, c->n_own);
-        const unsigned char *ht = (const unsigned char *)c->stage;
+        k_set_type<<<G, B, 0, c->stream>>>(c->x4, (const char *)dsrc, c->n_own);
+        const unsigned char *ht = (const unsigned char *)hsrc;
         int st = ht[0];
         for (size_t i = 1; i < n && st >= 0; i++) if (ht[i] != ht[0]) st = -1;
         c->single_type = st;
@@ -311,23 +321,23 @@ extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t str
         break;
     }
     case SEPGPU_F_MOLINDEX:
-        k_set_mol<<<G, B, 0, c->stream>>>(c->x4, (const int *)c->dstage, c->n_own);
+        k_set_mol<<<G, B, 0, c->stream>>>(c->x4, (const int *)dsrc, c->n_own);
         c->xs_current = false; c->list_valid = false;
         break;
     case SEPGPU_F_CROSS_NEIGHB:
-        k_int3_to_cr<<<G, B, 0, c->stream>>>(c->cr4, (const int *)c->dstage, c->n_own);
+        k_int3_to_cr<<<G, B, 0, c->stream>>>(c->cr4, (const int *)dsrc, c->n_own);
         break;
     case SEPGPU_F_CROSSINGS:
-        CUDA_TRY(cudaMemcpyAsync(c->crossings, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->crossings, dsrc, row * n, cudaMemcpyDeviceToDevice, c->stream));
         break;
     case SEPGPU_F_GID:
         if (!c->gid && dalloc(&c->gid, (size_t)c->ncap)) return SEPGPU_ECUDA;
-        CUDA_TRY(cudaMemcpyAsync(c->gid, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->gid, dsrc, row * n, cudaMemcpyDeviceToDevice, c->stream));
         break;
     case SEPGPU_F_BOND: case SEPGPU_F_ANGLE: case SEPGPU_F_DIHED: {
         int **tab = field == SEPGPU_F_BOND ? &c->excl_bond : field == SEPGPU_F_ANGLE ? &c->excl_angle : &c->excl_dihed;
-        if (!*tab && dalloc(tab, (size_t)fi.width * n)) return SEPGPU_ECUDA;
-        CUDA_TRY(cudaMemcpyAsync(*tab, c->dstage, row * n, cudaMemcpyDeviceToDevice, c->stream));
+        if (!*tab && dalloc(tab, (size_t)fi.width * c->ncap)) return SEPGPU_ECUDA;
+        CUDA_TRY(cudaMemcpyAsync(*tab, dsrc, row * n, cudaMemcpyDeviceToDevice, c->stream));
         c->have_excl = c->excl_bond && c->excl_angle && c->excl_dihed;
         c->list_valid = false;
         break;
@@ -337,57 +347,135 @@ extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t str
     return 0;
 }
 
-extern "C" int sepgpu_get(sepgpu_ctx *c, int field, void *host, size_t stride)
+#define SEPGPU_MAX_FIELDS 24
+
+extern "C" int sepgpu_put_fields(sepgpu_ctx *c, const void *base, size_t stride, int nfields,
+                                 const int *fields, const size_t *offsets)
 {
-    if (!c || !host) return SEPGPU_EINVAL;
-    FieldInfo fi = field_info(field);
-    if (!fi.elem) { sepgpu_set_error("sepgpu_get: bad field %d", field); return SEPGPU_EINVAL; }
+    if (!c || !base || nfields <= 0 || nfields > SEPGPU_MAX_FIELDS || !fields) return SEPGPU_EINVAL;
     CUDA_TRY(cudaSetDevice(c->device));
-    const size_t row = fi.elem * fi.width, n = (size_t)c->n_own;
-    if (stride == 0) stride = row;
-    int rc = sepgpu_ensure_stage(c, row * n);
+    const size_t n = (size_t)c->n_own;
+    size_t row[SEPGPU_MAX_FIELDS], off[SEPGPU_MAX_FIELDS], hoff[SEPGPU_MAX_FIELDS], total = 0;
+    for (int f = 0; f < nfields; f++) {
+        const FieldInfo fi = field_info(fields[f]);
+        if (!fi.elem || fields[f] == SEPGPU_F_A) { sepgpu_set_error("sepgpu_put: bad field %d", fields[f]); return SEPGPU_EINVAL; }
+        row[f] = fi.elem * fi.width;
+        hoff[f] = offsets ? offsets[f] : 0;
+        off[f] = total;
+        total += (row[f] * n + 255) & ~(size_t)255;
+    }
+    if (stride == 0) { if (nfields != 1) return SEPGPU_EINVAL; stride = row[0]; }
+    int rc = sepgpu_ensure_stage(c, total);
     if (rc) return rc;
+    // the previous async copy out of the staging buffer must be done before we overwrite it
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const char *src = (const char *)base;
+    char *dst = (char *)c->stage;
+    if (nfields == 1 && stride == row[0]) memcpy(dst, src + hoff[0], row[0] * n);
+    else parallel_rows(n, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) {
+            const char *rec = src + i * stride;
+            for (int f = 0; f < nfields; f++) memcpy(dst + off[f] + i * row[f], rec + hoff[f], row[f]);
+        }
+    });
+    CUDA_TRY(cudaMemcpyAsync(c->dstage, c->stage, total, cudaMemcpyHostToDevice, c->stream));
+    for (int f = 0; f < nfields; f++)
+        if ((rc = put_dispatch(c, fields[f], (const char *)c->dstage + off[f], (const char *)c->stage + off[f]))) return rc;
+    return 0;
+}
+
+extern "C" int sepgpu_put(sepgpu_ctx *c, int field, const void *host, size_t stride)
+{
+    return sepgpu_put_fields(c, host, stride, 1, &field, NULL);
+}
+
+// fills ddst (device, packed) for `field`, or returns a device array that already has the packed layout
+static int get_prepare(sepgpu_ctx *c, int field, void *ddst, const void **direct)
+{
+    const FieldInfo fi = field_info(field);
+    const size_t row = fi.elem * fi.width, n = (size_t)c->n_own;
     const int B = 256, G = (c->n_own + B - 1) / B;
-    const void *dsrc = c->dstage;
+    int rc;
+    *direct = NULL;
     switch (field) {
-    case SEPGPU_F_X: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->x4, c->n_own); break;
-    case SEPGPU_F_V: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n_own); break;
+    case SEPGPU_F_X: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, c->x4, c->n_own); break;
+    case SEPGPU_F_V: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, c->v4, c->n_own); break;
     case SEPGPU_F_F:
         if ((rc = sepgpu_apply_pending(c))) return rc;
-        if (c->f_zero) CUDA_TRY(cudaMemsetAsync(c->dstage, 0, row * n, c->stream));
-        else k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->n_own);
+        if (c->f_zero) CUDA_TRY(cudaMemsetAsync(ddst, 0, row * n, c->stream));
+        else k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, c->f4, c->n_own);
         break;
     case SEPGPU_F_A:
         if ((rc = sepgpu_apply_pending(c))) return rc;
-        if (c->f_zero) CUDA_TRY(cudaMemsetAsync(c->dstage, 0, row * n, c->stream));
-        else k_accel<<<G, B, 0, c->stream>>>((double *)c->dstage, c->f4, c->v4, c->n_own);
+        if (c->f_zero) CUDA_TRY(cudaMemsetAsync(ddst, 0, row * n, c->stream));
+        else k_accel<<<G, B, 0, c->stream>>>((double *)ddst, c->f4, c->v4, c->n_own);
         break;
-    case SEPGPU_F_XN: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, c->xn4, c->n_own); break;
+    case SEPGPU_F_XN: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, c->xn4, c->n_own); break;
     case SEPGPU_F_PV: case SEPGPU_F_PA:
         if (!c->have_dpd) { sepgpu_set_error("sepgpu_get: no DPD state"); return SEPGPU_ESTATE; }
-        k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)c->dstage, field == SEPGPU_F_PV ? c->pv4 : c->pa4, c->n_own);
+        k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, field == SEPGPU_F_PV ? c->pv4 : c->pa4, c->n_own);
         break;
-    case SEPGPU_F_M: k_w_to_scalar<<<G, B, 0, c->stream>>>((double *)c->dstage, c->v4, c->n_own); break;
-    case SEPGPU_F_Z: dsrc = c->z; break;
-    case SEPGPU_F_TYPE: k_get_type<<<G, B, 0, c->stream>>>((char *)c->dstage, c->x4, c->n_own); break;
-    case SEPGPU_F_MOLINDEX: k_get_mol<<<G, B, 0, c->stream>>>((int *)c->dstage, c->x4, c->n_own); break;
-    case SEPGPU_F_CROSS_NEIGHB: k_cr_to_int3<<<G, B, 0, c->stream>>>((int *)c->dstage, c->cr4, c->n_own); break;
-    case SEPGPU_F_CROSSINGS: dsrc = c->crossings; break;
-    case SEPGPU_F_GID: dsrc = c->gid; break;
-    case SEPGPU_F_BOND: dsrc = c->excl_bond; break;
-    case SEPGPU_F_ANGLE: dsrc = c->excl_angle; break;
-    case SEPGPU_F_DIHED: dsrc = c->excl_dihed; break;
+    case SEPGPU_F_M: k_w_to_scalar<<<G, B, 0, c->stream>>>((double *)ddst, c->v4, c->n_own); break;
+    case SEPGPU_F_TYPE: k_get_type<<<G, B, 0, c->stream>>>((char *)ddst, c->x4, c->n_own); break;
+    case SEPGPU_F_MOLINDEX: k_get_mol<<<G, B, 0, c->stream>>>((int *)ddst, c->x4, c->n_own); break;
+    case SEPGPU_F_CROSS_NEIGHB: k_cr_to_int3<<<G, B, 0, c->stream>>>((int *)ddst, c->cr4, c->n_own); break;
+    case SEPGPU_F_Z: *direct = c->z; break;
+    case SEPGPU_F_CROSSINGS: *direct = c->crossings; break;
+    case SEPGPU_F_GID: *direct = c->gid; break;
+    case SEPGPU_F_BOND: *direct = c->excl_bond; break;
+    case SEPGPU_F_ANGLE: *direct = c->excl_angle; break;
+    case SEPGPU_F_DIHED: *direct = c->excl_dihed; break;
+    default: return SEPGPU_EINVAL;
     }
     KERNEL_CHECK();
-    if (!dsrc) { sepgpu_set_error("sepgpu_get: field %d not present on device", field); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaMemcpyAsync(c->stage, dsrc, row * n, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    char *dst = (char *)host;
-    const char *src = (const char *)c->stage;
-    if (stride == row) memcpy(dst, src, row * n);
-    else for (size_t i = 0; i < n; i++) memcpy(dst + i * stride, src + i * row, row);
+    if (field == SEPGPU_F_Z || field == SEPGPU_F_CROSSINGS || field == SEPGPU_F_GID || field >= SEPGPU_F_BOND) {
+        if (!*direct) { sepgpu_set_error("sepgpu_get: field %d not present on device", field); return SEPGPU_ESTATE; }
+        CUDA_TRY(cudaMemcpyAsync(ddst, *direct, row * n, cudaMemcpyDeviceToDevice, c->stream));
+    }
     return 0;
 }
+
+extern "C" int sepgpu_get_fields(sepgpu_ctx *c, void *base, size_t stride, int nfields,
+                                 const int *fields, const size_t *offsets)
+{
+    if (!c || !base || nfields <= 0 || nfields > SEPGPU_MAX_FIELDS || !fields) return SEPGPU_EINVAL;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->n_own;
+    size_t row[SEPGPU_MAX_FIELDS], off[SEPGPU_MAX_FIELDS], hoff[SEPGPU_MAX_FIELDS], total = 0;
+    for (int f = 0; f < nfields; f++) {
+        const FieldInfo fi = field_info(fields[f]);
+        if (!fi.elem) { sepgpu_set_error("sepgpu_get: bad field %d", fields[f]); return SEPGPU_EINVAL; }
+        row[f] = fi.elem * fi.width;
+        hoff[f] = offsets ? offsets[f] : 0;
+        off[f] = total;
+        total += (row[f] * n + 255) & ~(size_t)255;
+    }
+    if (stride == 0) { if (nfields != 1) return SEPGPU_EINVAL; stride = row[0]; }
+    int rc = sepgpu_ensure_stage(c, total);
+    if (rc) return rc;
+    for (int f = 0; f < nfields; f++) {
+        const void *direct;
+        if ((rc = get_prepare(c, fields[f], (char *)c->dstage + off[f], &direct))) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->stage, c->dstage, total, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    char *dst = (char *)base;
+    const char *src = (const char *)c->stage;
+    if (nfields == 1 && stride == row[0]) memcpy(dst + hoff[0], src, row[0] * n);
+    else parallel_rows(n, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; i++) {
+            char *rec = dst + i * stride;
+            for (int f = 0; f < nfields; f++) memcpy(rec + hoff[f], src + off[f] + i * row[f], row[f]);
+        }
+    });
+    return 0;
+}
+
+extern "C" int sepgpu_get(sepgpu_ctx *c, int field, void *host, size_t stride)
+{
+    return sepgpu_get_fields(c, host, stride, 1, &field, NULL);
+}
+
 
 // ---- scalars ----------------------------------------------------------------------------------------------
 __global__ void k_reset_ret(DevScalars *s)
@@ -401,9 +489,9 @@ __global__ void k_reset_ret(DevScalars *s)
 extern "C" int sepgpu_reset_ret(sepgpu_ctx *c)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
-    k_reset_ret<<<1, 32, 0, c->stream>>>(c->scal);
-    KERNEL_CHECK();
+    // no launch: the next kernel that accumulates into the scalar block clears it first
+    // (sepgpu_flush_resets does it explicitly when the block is read before that)
+    c->ret_reset_pending = true;
     return 0;
 }
 
@@ -416,7 +504,14 @@ extern "C" int sepgpu_reset_force(sepgpu_ctx *c)
     // f <- 0 is not written out: the first force kernel after this call stores instead of adding.
     c->f_zero = true;
     c->pending_alpha_slot = -1;       // a pending f -= alpha m v dies with the force it would modify
-    k_reset_maxdist<<<1, 1, 0, c->stream>>>(c->scal);     // source/sepmisc.c:399
+    c->maxd_reset_pending = true;                         // source/sepmisc.c:399, applied by the next integrator
+    return 0;
+}
+
+int sepgpu_flush_resets(sepgpu_ctx *c)
+{
+    if (c->ret_reset_pending) { k_reset_ret<<<1, 32, 0, c->stream>>>(c->scal); c->ret_reset_pending = false; }
+    if (c->maxd_reset_pending) { k_reset_maxdist<<<1, 1, 0, c->stream>>>(c->scal); c->maxd_reset_pending = false; }
     KERNEL_CHECK();
     return 0;
 }
@@ -425,6 +520,7 @@ extern "C" int sepgpu_read_scalars(sepgpu_ctx *c, sepgpu_scalars *out)
 {
     if (!c || !out) return SEPGPU_EINVAL;
     CUDA_TRY(cudaSetDevice(c->device));
+    { int rcf = sepgpu_flush_resets(c); if (rcf) return rcf; }
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     const DevScalars *s = c->scal_host;

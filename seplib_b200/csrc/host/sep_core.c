@@ -154,14 +154,6 @@ void sepb_fill_sys(const sepsys *sys, sepgpu_sys *out)
 
 #define FIELD_PTR(b, member) ((void *)&(b)->atoms[0].member)
 
-static void upload(sep_binding *b, unsigned bit, int field, void *base)
-{
-    if (!(b->host_dirty & bit)) return;
-    sepb_check(sepgpu_put(b->gpu, field, base, sizeof(seppart)), "upload");
-    b->host_dirty &= ~bit;
-    b->dev_dirty &= ~bit;
-}
-
 sep_binding *sepb_prepare(seppart *atoms, sepsys *sys)
 {
     sep_binding *b = sepb_find(atoms);
@@ -178,19 +170,17 @@ sep_binding *sepb_prepare(seppart *atoms, sepsys *sys)
     if (sys->molptr) b->molptr = sys->molptr;
     if (!b->host_dirty) return b;
 
-    upload(b, SEPB_X, SEPGPU_F_X, FIELD_PTR(b, x));
-    upload(b, SEPB_V, SEPGPU_F_V, FIELD_PTR(b, v));
-    upload(b, SEPB_M, SEPGPU_F_M, FIELD_PTR(b, m));
-    upload(b, SEPB_Z, SEPGPU_F_Z, FIELD_PTR(b, z));
-    upload(b, SEPB_TYPE, SEPGPU_F_TYPE, FIELD_PTR(b, type));
-    upload(b, SEPB_MOL, SEPGPU_F_MOLINDEX, FIELD_PTR(b, molindex));
-    upload(b, SEPB_XN, SEPGPU_F_XN, FIELD_PTR(b, xn));
-    upload(b, SEPB_CN, SEPGPU_F_CROSS_NEIGHB, FIELD_PTR(b, cross_neighb));
-    upload(b, SEPB_CR, SEPGPU_F_CROSSINGS, FIELD_PTR(b, crossings));
-    if (b->uploaded_once) upload(b, SEPB_F, SEPGPU_F_F, FIELD_PTR(b, f));
-    if (b->dpd_state_on_device) {
-        upload(b, SEPB_PV, SEPGPU_F_PV, FIELD_PTR(b, pv));
-        upload(b, SEPB_PA, SEPGPU_F_PA, FIELD_PTR(b, pa));
+    /* every dirty field in ONE pass over the 568-byte records and one PCIe transfer */
+    {
+        int fields[16]; size_t offs[16]; int nf = 0;
+#define WANT(bit, fid, member) if (b->host_dirty & (bit)) { fields[nf] = fid; offs[nf] = offsetof(seppart, member); nf++; }
+        WANT(SEPB_X, SEPGPU_F_X, x) WANT(SEPB_V, SEPGPU_F_V, v) WANT(SEPB_M, SEPGPU_F_M, m) WANT(SEPB_Z, SEPGPU_F_Z, z)
+        WANT(SEPB_TYPE, SEPGPU_F_TYPE, type) WANT(SEPB_MOL, SEPGPU_F_MOLINDEX, molindex) WANT(SEPB_XN, SEPGPU_F_XN, xn)
+        WANT(SEPB_CN, SEPGPU_F_CROSS_NEIGHB, cross_neighb) WANT(SEPB_CR, SEPGPU_F_CROSSINGS, crossings)
+        if (b->uploaded_once) WANT(SEPB_F, SEPGPU_F_F, f)
+        if (b->dpd_state_on_device) { WANT(SEPB_PV, SEPGPU_F_PV, pv) WANT(SEPB_PA, SEPGPU_F_PA, pa) }
+#undef WANT
+        if (nf) sepb_check(sepgpu_put_fields(b->gpu, b->atoms, sizeof(seppart), nf, fields, offs), "upload");
     }
     if ((b->host_dirty & SEPB_EXCL) && sys->molptr &&
         (sys->molptr->flag_bonds || sys->molptr->flag_angles || sys->molptr->flag_dihedrals)) {
@@ -215,18 +205,15 @@ void sepb_download(sep_binding *b, unsigned fields)
     if (!b || !b->gpu) return;
     fields &= b->dev_dirty;
     if (!fields) return;
-#define PULL(bit, fid, member)                                                                  \
-    if (fields & (bit)) sepb_check(sepgpu_get(b->gpu, fid, FIELD_PTR(b, member), sizeof(seppart)), "download")
-    PULL(SEPB_X, SEPGPU_F_X, x);
-    PULL(SEPB_V, SEPGPU_F_V, v);
-    PULL(SEPB_F, SEPGPU_F_F, f);
-    PULL(SEPB_A, SEPGPU_F_A, a);
-    PULL(SEPB_XN, SEPGPU_F_XN, xn);
-    PULL(SEPB_CN, SEPGPU_F_CROSS_NEIGHB, cross_neighb);
-    PULL(SEPB_CR, SEPGPU_F_CROSSINGS, crossings);
-    PULL(SEPB_PV, SEPGPU_F_PV, pv);
-    PULL(SEPB_PA, SEPGPU_F_PA, pa);
+    {
+        int fl[16]; size_t offs[16]; int nf = 0;
+#define PULL(bit, fid, member) if (fields & (bit)) { fl[nf] = fid; offs[nf] = offsetof(seppart, member); nf++; }
+        PULL(SEPB_X, SEPGPU_F_X, x) PULL(SEPB_V, SEPGPU_F_V, v) PULL(SEPB_F, SEPGPU_F_F, f) PULL(SEPB_A, SEPGPU_F_A, a)
+        PULL(SEPB_XN, SEPGPU_F_XN, xn) PULL(SEPB_CN, SEPGPU_F_CROSS_NEIGHB, cross_neighb) PULL(SEPB_CR, SEPGPU_F_CROSSINGS, crossings)
+        PULL(SEPB_PV, SEPGPU_F_PV, pv) PULL(SEPB_PA, SEPGPU_F_PA, pa)
 #undef PULL
+        if (nf) sepb_check(sepgpu_get_fields(b->gpu, b->atoms, sizeof(seppart), nf, fl, offs), "download");
+    }
     b->dev_dirty &= ~fields;
 }
 
