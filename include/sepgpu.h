@@ -158,6 +158,13 @@ int sepgpu_verlet_dpd(sepgpu_ctx *ctx, const sepgpu_sys *sys, double lambda, int
 int sepgpu_reset_momentum(sepgpu_ctx *ctx, char type);
 int sepgpu_scale_positions(sepgpu_ctx *ctx, double xi);
 
+/* molecule-molecule force table for the molecular pressure tensor: sepmolinfo.Fij (include/sepstrct.h:94),
+ * filled by the pair routines (source/sepprfrc.c:199-207, source/sepcoulomb.c:138-147), cleared by
+ * sep_reset_force_mol (source/sepmisc.c:403-430).  fij_get returns nmol*nmol*3 floats, [i][j][k]. */
+int sepgpu_fij_enable(sepgpu_ctx *ctx, int nmol);
+int sepgpu_fij_reset(sepgpu_ctx *ctx);
+int sepgpu_fij_get(sepgpu_ctx *ctx, float *out);
+
 /* ---- results -------------------------------------------------------------------------------------- */
 /* stream-synchronising read of the scalar block */
 int sepgpu_read_scalars(sepgpu_ctx *ctx, sepgpu_scalars *out);

@@ -1,3 +1,4 @@
 #!/bin/bash
-python bench.py --no-cpu --steps 300 --warmup 50 2>gpurun_out/e.err | python scripts/summ.py "default"
-grep "e2e breakdown" gpurun_out/e.err
+for cfg in "--unroll 2" "--unroll 4"; do
+python bench.py $cfg --no-cpu --no-e2e --steps 400 --warmup 100 2>/dev/null | python scripts/summ.py "$cfg minctas8"
+done

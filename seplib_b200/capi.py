@@ -128,6 +128,7 @@ SEPGPU_SYMBOLS = [
     "sepgpu_read_scalars", "sepgpu_sync", "sepgpu_get_pairs", "sepgpu_request_rebuild",
     "sepgpu_set_option", "sepgpu_timer_start", "sepgpu_timer_stop", "sepgpu_kernel_time",
     "sepgpu_peak_fp64", "sepgpu_peak_copy", "sepgpu_flush_l2",
+    "sepgpu_fij_enable", "sepgpu_fij_reset", "sepgpu_fij_get",
     "sepgpu_dd_unique_id", "sepgpu_dd_init", "sepgpu_dd_set_owned", "sepgpu_dd_layers",
 ]
 
@@ -251,6 +252,9 @@ def load():
     lib.sepgpu_peak_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sepgpu_peak_copy.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sepgpu_flush_l2.argtypes = [ctx]
+    lib.sepgpu_fij_enable.argtypes = [ctx, C.c_int]
+    lib.sepgpu_fij_reset.argtypes = [ctx]
+    lib.sepgpu_fij_get.argtypes = [ctx, C.c_void_p]
     lib.sepgpu_dd_unique_id.argtypes = [C.c_void_p]
     lib.sepgpu_dd_init.argtypes = [ctx, C.c_int, C.c_int, C.c_void_p, C.POINTER(GpuSys), C.c_longlong]
     lib.sepgpu_dd_set_owned.argtypes = [ctx, C.c_int]

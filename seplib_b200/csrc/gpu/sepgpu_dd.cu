@@ -131,7 +131,8 @@ extern "C" int sepgpu_dd_init(sepgpu_ctx *c, int rank, int nranks, const void *i
     // a boundary layer holds about n_own / (owned layers); leave generous head-room
     d->bufcap = cap / (size_t)(d->z1 - d->z0) * 2 + 4096;
     if (d->bufcap > cap) d->bufcap = cap;
-    if (dmalloc(&d->comm_buf, 64)) return SEPGPU_ECUDA;
+    if (nranks > 64) { sepgpu_set_error("dd_init: at most 64 ranks"); return SEPGPU_EINVAL; }
+    if (dmalloc(&d->comm_buf, 160)) return SEPGPU_ECUDA;
     CUDA_TRY(cudaMallocHost((void **)&d->comm_host, sizeof(double) * 64));
     for (int k = 0; k < 5; k++) if (dmalloc(&d->flag[k], cap + 1) || dmalloc(&d->pos[k], cap + 1)) return SEPGPU_ECUDA;
     if (dmalloc(&d->scan_scratch, cap / 2048 + 1030) || dmalloc(&d->counts_dev, 16)) return SEPGPU_ECUDA;
@@ -182,6 +183,7 @@ void sepgpu_dd_destroy(sepgpu_ctx *c)
 }
 
 double *sepgpu_dd_comm(sepgpu_ctx *c) { return c->dd->comm_buf; }
+void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks) { *rank = c->dd->rank; *nranks = c->dd->nranks; }
 
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax)
 {
@@ -421,19 +423,46 @@ __global__ void k_dd_unpack_xu(const d4 *__restrict__ in, int n, int first_local
     xs[rank[first_local + k]] = in[k];
 }
 
+// both directions in one launch
+__global__ void k_dd_pack_xu2(const d4 *__restrict__ x4, const i4 *__restrict__ cr4, const int *__restrict__ idx0, int n0,
+                              const int *__restrict__ idx1, int n1, double Lx, double Ly, double Lz,
+                              d4 *__restrict__ out0, d4 *__restrict__ out1)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n0 + n1) return;
+    const bool second = k >= n0;
+    if (second) k -= n0;
+    const int i = second ? idx1[k] : idx0[k];
+    d4 x = x4[i];
+    const int w = cr4[i].w;
+    if (w != 0) {
+        x.x += ((w & 1023) - 512) * Lx; x.y += (((w >> 10) & 1023) - 512) * Ly; x.z += (((w >> 20) & 1023) - 512) * Lz;
+    }
+    (second ? out1 : out0)[k] = x;
+}
+
+__global__ void k_dd_unpack_xu2(const d4 *__restrict__ in0, int n0, const d4 *__restrict__ in1, int n1, int first_local,
+                                const int *__restrict__ rank, d4 *__restrict__ xs)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n0 + n1) return;
+    xs[rank[first_local + k]] = k < n0 ? in0[k] : in1[k - n0];
+}
+
 int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys)
 {
     DDState *d = c->dd;
     if (d->halo_current) return 0;
     const int B = 256;
-    for (int k = 0; k < 2; k++)
-        if (d->n_send[k]) k_dd_pack_xu<<<(d->n_send[k] + B - 1) / B, B, 0, c->stream>>>(c->x4, c->cr4, d->send_idx[k], d->n_send[k],
-                                                                                      sys->length[0], sys->length[1], sys->length[2], d->send[k]);
+    if (d->n_send[0] + d->n_send[1])
+        k_dd_pack_xu2<<<(d->n_send[0] + d->n_send[1] + B - 1) / B, B, 0, c->stream>>>(c->x4, c->cr4, d->send_idx[0], d->n_send[0],
+            d->send_idx[1], d->n_send[1], sys->length[0], sys->length[1], sys->length[2], d->send[0], d->send[1]);
     int rc = exchange(c, d->send[0], (size_t)d->n_send[0], d->send[1], (size_t)d->n_send[1],
                       d->recv[0], (size_t)d->n_recv[0], d->recv[1], (size_t)d->n_recv[1], sizeof(d4));
     if (rc) return rc;
-    if (d->n_recv[0]) k_dd_unpack_xu<<<(d->n_recv[0] + B - 1) / B, B, 0, c->stream>>>(d->recv[0], d->n_recv[0], c->n_own, c->rank, c->xs);
-    if (d->n_recv[1]) k_dd_unpack_xu<<<(d->n_recv[1] + B - 1) / B, B, 0, c->stream>>>(d->recv[1], d->n_recv[1], c->n_own + d->n_recv[0], c->rank, c->xs);
+    if (d->n_recv[0] + d->n_recv[1])
+        k_dd_unpack_xu2<<<(d->n_recv[0] + d->n_recv[1] + B - 1) / B, B, 0, c->stream>>>(d->recv[0], d->n_recv[0], d->recv[1], d->n_recv[1],
+                                                                                      c->n_own, c->rank, c->xs);
     KERNEL_CHECK();
     d->halo_current = true;
     return 0;
@@ -452,10 +481,10 @@ __global__ void k_dd_gather_force_scalars(const DevScalars *s, double *comm)
 int sepgpu_dd_reduce_force_scalars(sepgpu_ctx *c, double *epot, double *ecoul, double *pot_P, double *pot_P_bond)
 {
     DDState *d = c->dd;
-    k_dd_gather_force_scalars<<<1, 32, 0, c->stream>>>(c->scal, d->comm_buf + 16);
-    int rc = sepgpu_dd_allreduce(c, d->comm_buf + 16, 20, NULL, 0);
+    k_dd_gather_force_scalars<<<1, 32, 0, c->stream>>>(c->scal, d->comm_buf + 96);
+    int rc = sepgpu_dd_allreduce(c, d->comm_buf + 96, 20, NULL, 0);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d->comm_host, d->comm_buf + 16, sizeof(double) * 20, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d->comm_host, d->comm_buf + 96, sizeof(double) * 20, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *epot = d->comm_host[0]; *ecoul = d->comm_host[1];
     memcpy(pot_P, d->comm_host + 2, sizeof(double) * 9);

@@ -20,6 +20,9 @@
 
 #define FORCE_BLOCK 128
 #define FORCE_MAX_GRID (148 * 64)
+#ifndef LJ_MIN_CTAS
+#define LJ_MIN_CTAS 7          // 72 registers per thread; forcing 8 CTAs (64 registers) spills and measured 11 % slower
+#endif
 
 struct LJDev {
     double cf2, sig2, eps48, eps4, aw, awh, shift;
@@ -77,9 +80,13 @@ struct PairAcc {
 // force factor selected to zero.  In a warp some lane is almost always in range, so the branchy form
 // executes the full block anyway; without the branch the compiler can interleave the dependent DFMA
 // chains of two pairs.  r2 of a real pair is finite and non-zero, so the masked values stay finite.
-template <bool TYPED>
+// FIJ: also accumulate the molecule-molecule force table Fij[mi][mj] += f (reference
+// source/sepprfrc.c:199-207; each directed pair adds its own direction, the partner thread adds -f to
+// Fij[mj][mi]).  Only small systems carry the table (<= SEP_MAX_NUM_MOL molecules), the adds are FP64
+// atomics on nmol^2*3 scattered addresses -- off for every benchmarked configuration.
+template <bool TYPED, bool FIJ>
 __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, int ti, const LJDev &P,
-                                        const BoxDev &B, PairAcc &A)
+                                        const BoxDev &B, PairAcc &A, double *fij = nullptr, int nmol = 0)
 {
     double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
     const int code = (int)(e >> SEPGPU_SHIFT_BITS);
@@ -102,6 +109,13 @@ __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, 
     A.nin += in ? 1 : 0;
     A.vxx = fma(gx, dx, A.vxx); A.vxy = fma(gx, dy, A.vxy); A.vxz = fma(gx, dz, A.vxz);
     A.vyy = fma(gy, dy, A.vyy); A.vyz = fma(gy, dz, A.vyz); A.vzz = fma(gz, dz, A.vzz);
+    if (FIJ && in) {
+        const int mi = tag_mol(pi.w), mj = tag_mol(pj.w);
+        if (mi != -1 && mj != -1 && mi != mj) {
+            double *t = fij + ((size_t)mi * nmol + mj) * 3;
+            atomicAdd(t, gx); atomicAdd(t + 1, gy); atomicAdd(t + 2, gz);
+        }
+    }
 }
 
 // STORE: first force kernel after sep_reset_force -> plain store instead of read-modify-write.
@@ -109,11 +123,11 @@ __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, 
 // stay resident in its SM's L1.  A lane reads its next FOUR list entries with one streaming 128-bit
 // load (ld.global.cs: never reused) issued one chunk ahead of use -- the list comes from HBM and was
 // the dominant stall -- and then gathers the four neighbour sectors two at a time.
-template <int TPA, bool TYPED, bool STORE, int UNROLL>
-__global__ void __launch_bounds__(FORCE_BLOCK)
+template <int TPA, bool TYPED, bool STORE, bool FIJ>
+__global__ void __launch_bounds__(FORCE_BLOCK, LJ_MIN_CTAS)
 k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int atoms_per_cta,
-          LJDev P, BoxDev B, double *__restrict__ partial)
+          LJDev P, BoxDev B, double *__restrict__ partial, double *fij, int nmol)
 {
     __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
     const int sub = threadIdx.x % TPA;
@@ -151,15 +165,15 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
                     const bool v1 = left > 1;
                     const d4 p0 = xs[cur.x & SEPGPU_INDEX_MASK];
                     const d4 p1 = xs[v1 ? (cur.y & SEPGPU_INDEX_MASK) : (unsigned)s];
-                    lj_pair<TYPED>(pi, p0, cur.x, ti, P, B, A);
-                    if (v1) lj_pair<TYPED>(pi, p1, cur.y, ti, P, B, A);
+                    lj_pair<TYPED, FIJ>(pi, p0, cur.x, ti, P, B, A, fij, nmol);
+                    if (v1) lj_pair<TYPED, FIJ>(pi, p1, cur.y, ti, P, B, A, fij, nmol);
                 }
                 if (left > 2) {
                     const bool v3 = left > 3;
                     const d4 p2 = xs[cur.z & SEPGPU_INDEX_MASK];
                     const d4 p3 = xs[v3 ? (cur.w & SEPGPU_INDEX_MASK) : (unsigned)s];
-                    lj_pair<TYPED>(pi, p2, cur.z, ti, P, B, A);
-                    if (v3) lj_pair<TYPED>(pi, p3, cur.w, ti, P, B, A);
+                    lj_pair<TYPED, FIJ>(pi, p2, cur.z, ti, P, B, A, fij, nmol);
+                    if (v3) lj_pair<TYPED, FIJ>(pi, p3, cur.w, ti, P, B, A, fij, nmol);
                 }
                 cur = nxt;
                 c = cn;
@@ -210,7 +224,7 @@ __device__ __forceinline__ int share_tab_f(const int *__restrict__ tab, int widt
 template <bool STORE>
 __global__ void __launch_bounds__(FORCE_BLOCK)
 k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDev B, unsigned opt,
-           const int *__restrict__ excl_bond, double *__restrict__ partial)
+           const int *__restrict__ excl_bond, double *__restrict__ partial, double *fij, int nmol)
 {
     __shared__ d4 tile[FORCE_BLOCK];
     __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
@@ -253,6 +267,13 @@ k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDe
                 nin++;
                 acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
                 acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
+                if (fij) {                                   // source/sepprfrc.c:70-80: both molecules known
+                    const int mj = tag_mol(pj.w);
+                    if (mi != -1 && mj != -1) {
+                        double *t = fij + ((size_t)mi * nmol + mj) * 3;
+                        atomicAdd(t, gx); atomicAdd(t + 1, gy); atomicAdd(t + 2, gz);
+                    }
+                }
             }
         }
     }
@@ -337,16 +358,16 @@ static LJDev make_lj(const sepgpu_ljparam *p, const char types[2])
     return d;
 }
 
-template <int TPA, int UNROLL>
-static void launch_lj_list_u(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
+template <int TPA, bool FIJ>
+static void launch_lj_list_f(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
 {
-#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial
+#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial, c->fij, c->nmol
     if (typed) {
-        if (store) k_lj_list<TPA, true, true, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
-        else       k_lj_list<TPA, true, false, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        if (store) k_lj_list<TPA, true, true, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        else       k_lj_list<TPA, true, false, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
     } else {
-        if (store) k_lj_list<TPA, false, true, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
-        else       k_lj_list<TPA, false, false, UNROLL><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        if (store) k_lj_list<TPA, false, true, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
+        else       k_lj_list<TPA, false, false, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
     }
 #undef LJ_ARGS
 }
@@ -354,8 +375,8 @@ static void launch_lj_list_u(sepgpu_ctx *c, int grid, int apc, bool typed, bool 
 template <int TPA>
 static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
 {
-    if (c->unroll == 4) launch_lj_list_u<TPA, 4>(c, grid, apc, typed, store, P, B);
-    else launch_lj_list_u<TPA, 2>(c, grid, apc, typed, store, P, B);
+    if (c->fij) launch_lj_list_f<TPA, true>(c, grid, apc, typed, store, P, B);
+    else launch_lj_list_f<TPA, false>(c, grid, apc, typed, store, P, B);
 }
 
 extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2],
@@ -375,8 +396,8 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
         }
         const int grid = (c->n + FORCE_BLOCK - 1) / FORCE_BLOCK;
         ktimer_begin(c, &c->t_force);
-        if (store) k_lj_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial);
-        else       k_lj_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial);
+        if (store) k_lj_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial, c->fij, c->nmol);
+        else       k_lj_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial, c->fij, c->nmol);
         ktimer_end(c, &c->t_force);
         KERNEL_CHECK();
         c->f_zero = false;
@@ -402,9 +423,7 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     case 1: launch_lj_list<1>(c, grid, apc, typed, store, P, B); break;
     case 2: launch_lj_list<2>(c, grid, apc, typed, store, P, B); break;
     case 4: launch_lj_list<4>(c, grid, apc, typed, store, P, B); break;
-    case 8: launch_lj_list<8>(c, grid, apc, typed, store, P, B); break;
-    case 16: launch_lj_list<16>(c, grid, apc, typed, store, P, B); break;
-    default: launch_lj_list<32>(c, grid, apc, typed, store, P, B); break;
+    default: launch_lj_list<8>(c, grid, apc, typed, store, P, B); break;
     }
     ktimer_end(c, &c->t_force);
     KERNEL_CHECK();

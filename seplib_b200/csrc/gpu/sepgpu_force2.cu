@@ -47,7 +47,7 @@ template <int TPA, bool STORE>
 __global__ void __launch_bounds__(FORCE_BLOCK)
 k_coulomb_list(const d4 *__restrict__ xs, const double *__restrict__ zs, const unsigned *__restrict__ nbr,
                const int *__restrict__ cnt, const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad,
-               double cf, BoxC B, double *__restrict__ partial)
+               double cf, BoxC B, double *__restrict__ partial, double *fij, int nmol)
 {
     __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
     const int sub = threadIdx.x % TPA;
@@ -87,6 +87,13 @@ k_coulomb_list(const d4 *__restrict__ xs, const double *__restrict__ zs, const u
                     acc[1] += zizj * (rinv + (r - cf) * icf2 - icf);            // :150
                     acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
                     acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
+                    if (fij) {                                                   // :138-147 (no mi != mj test here)
+                        const int mi = tag_mol(pi.w), mj = tag_mol(pj.w);
+                        if (mi != -1 && mj != -1) {
+                            double *t = fij + ((size_t)mi * nmol + mj) * 3;
+                            atomicAdd(t, gx); atomicAdd(t + 1, gy); atomicAdd(t + 2, gz);
+                        }
+                    }
                 }
             }
         }
@@ -122,7 +129,7 @@ template <bool STORE>
 __global__ void __launch_bounds__(FORCE_BLOCK)
 k_coulomb_brute(const d4 *__restrict__ x4, const double *__restrict__ z, d4 *__restrict__ f4, int n, double cf,
                 BoxC B, unsigned opt, const int *__restrict__ eb, const int *__restrict__ ea,
-                const int *__restrict__ ed, double *__restrict__ partial)
+                const int *__restrict__ ed, double *__restrict__ partial, double *fij, int nmol)
 {
     __shared__ d4 tile[FORCE_BLOCK];
     __shared__ double ztile[FORCE_BLOCK];
@@ -171,6 +178,13 @@ k_coulomb_brute(const d4 *__restrict__ x4, const double *__restrict__ z, d4 *__r
                 acc[1] += zizj * (1.0 / r + (r - cf) * icf2 - icf);
                 acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
                 acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
+                if (fij) {                                                       // source/sepcoulomb.c:68-82
+                    const int mj = tag_mol(pj.w);
+                    if (mi != -1 && mj != -1) {
+                        double *t = fij + ((size_t)mi * nmol + mj) * 3;
+                        atomicAdd(t, gx); atomicAdd(t + 1, gy); atomicAdd(t + 2, gz);
+                    }
+                }
             }
         }
     }
@@ -186,8 +200,8 @@ k_coulomb_brute(const d4 *__restrict__ x4, const double *__restrict__ z, d4 *__r
 template <int TPA>
 static void launch_coulomb(sepgpu_ctx *c, int grid, bool store, double cf, const BoxC &B)
 {
-    if (store) k_coulomb_list<TPA, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->zs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, cf, B, c->partial);
-    else       k_coulomb_list<TPA, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->zs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, cf, B, c->partial);
+    if (store) k_coulomb_list<TPA, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->zs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, cf, B, c->partial, c->fij, c->nmol);
+    else       k_coulomb_list<TPA, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->zs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, cf, B, c->partial, c->fij, c->nmol);
 }
 
 extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf, unsigned opt)
@@ -203,8 +217,8 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
         }
         const int grid = (c->n + FORCE_BLOCK - 1) / FORCE_BLOCK;
         ktimer_begin(c, &c->t_force);
-        if (store) k_coulomb_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial);
-        else       k_coulomb_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial);
+        if (store) k_coulomb_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial, c->fij, c->nmol);
+        else       k_coulomb_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial, c->fij, c->nmol);
         ktimer_end(c, &c->t_force);
         KERNEL_CHECK();
         c->f_zero = false;

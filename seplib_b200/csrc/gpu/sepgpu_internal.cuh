@@ -119,6 +119,10 @@ struct sepgpu_ctx {
     int *atom_dihed_ptr, *atom_dihed_idx;
     double *blengths, *angles, *dihedrals;
 
+    // molecule-molecule force table (reference sepmolinfo.Fij), nmol*nmol*3 doubles; NULL unless enabled
+    double *fij;
+    int nmol;
+
     // scalars and partial sums
     DevScalars *scal;            // device
     DevScalars *scal_host;       // pinned mirror

@@ -134,7 +134,8 @@ k_integrate(d4 *__restrict__ x4, d4 *__restrict__ v4, d4 *__restrict__ f4, const
 
 // one block: reduce the partial rows, update sepret/sepsys scalars, evaluate the skin trigger
 __global__ void __launch_bounds__(256)
-k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int mode, double *comm, int resets)
+k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int mode, double *comm, int resets,
+                 int rank, int nranks)
 {
     // resets: bit0 a sep_reset_retval is pending, bit1 a sep_reset_force (max_dist2 <- 0) is pending
     if (mode != 1 && threadIdx.x == 0) {
@@ -142,13 +143,16 @@ k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal
         if (resets & 2) scal->max_dist2 = 0.0;
     }
     // mode 0: single GPU.  mode 1: decomposed run, phase A -- local sums into comm[0..11], local max into
-    // comm[12]; the host all-reduces them (sum / max) over the ranks.  mode 2: phase B -- apply comm.
+    // comm[12 + rank] (the other ranks' slots zero), so that ONE sum all-reduce over 12 + nranks doubles also
+    // delivers every rank's maximum.  mode 2: phase B -- apply comm.
     if (mode == 2) {
         if (threadIdx.x == 0) {
             scal->ekin += 0.5 * comm[0];
             const double K[9] = {comm[1], comm[2], comm[3], comm[2], comm[4], comm[5], comm[3], comm[5], comm[6]};
             for (int k = 0; k < 9; k++) scal->kin_P[k] += K[k];
-            if (comm[12] > scal->max_dist2) scal->max_dist2 = comm[12];
+            double gmx = 0.0;
+            for (int r = 0; r < nranks; r++) gmx = fmax(gmx, comm[12 + r]);
+            if (gmx > scal->max_dist2) scal->max_dist2 = gmx;
             scal->sum_mv2 = comm[8];
             scal->mom[0] = comm[9]; scal->mom[1] = comm[10]; scal->mom[2] = comm[11];
             scal->neighb_flag = sqrt(scal->max_dist2) > skin * 0.5 ? 1 : 0;
@@ -175,7 +179,8 @@ k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal
         for (int w = 0; w < 8; w++) mx = fmax(mx, red[w]);
         if (mode == 1) {
             for (int q = 0; q < SEPGPU_NPART_I; q++) comm[q] = v[q];
-            comm[7] = 0.0; comm[12] = mx;
+            comm[7] = 0.0;
+            for (int r = 0; r < nranks; r++) comm[12 + r] = r == rank ? mx : 0.0;
             return;
         }
         scal->ekin += 0.5 * v[0];                                     // source/sepintgr.c:87
@@ -204,6 +209,7 @@ int sepgpu_ensure_dpd(sepgpu_ctx *c);
 double *sepgpu_dd_comm(sepgpu_ctx *c);
 void sepgpu_dd_positions_moved(sepgpu_ctx *c);
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax);
+void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks);
 
 __global__ void k_partial2_to_comm(const double *__restrict__ partial, int nrows, double *comm)
 {
@@ -239,12 +245,14 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     c->ret_reset_pending = false; c->maxd_reset_pending = false;
     if (c->dd) {
         double *comm = sepgpu_dd_comm(c);
-        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 1, comm, 0);
-        int rcd = sepgpu_dd_allreduce(c, comm, 12, comm + 12, 1);
+        int drank = 0, dn = 1;
+        sepgpu_dd_rank(c, &drank, &dn);
+        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 1, comm, 0, drank, dn);
+        int rcd = sepgpu_dd_allreduce(c, comm, 12 + dn, NULL, 0);
         if (rcd) return rcd;
-        k_finalize_intgr<<<1, 32, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 2, comm, resets);
+        k_finalize_intgr<<<1, 32, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 2, comm, resets, drank, dn);
     } else {
-        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 0, NULL, resets);
+        k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 0, NULL, resets, 0, 1);
     }
     ktimer_end(c, &c->t_intgr);
     KERNEL_CHECK();

@@ -117,6 +117,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     cudaStreamSynchronize(c->stream);
     sepgpu_dd_destroy(c);
     if (c->gid) cudaFree(c->gid);
+    if (c->fij) cudaFree(c->fij);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
                     c->rank, c->cell_of, c->cell_cnt, c->cell_start, c->tmp_slot, c->nbr, c->cnt,
@@ -477,6 +478,50 @@ extern "C" int sepgpu_get(sepgpu_ctx *c, int field, void *host, size_t stride)
 }
 
 
+// ---- molecule-molecule force table (reference sepmolinfo.Fij, include/sepstrct.h:94) ---------------------------
+extern "C" int sepgpu_fij_enable(sepgpu_ctx *c, int nmol)
+{
+    if (!c || nmol <= 0) return SEPGPU_EINVAL;
+    if (c->dd) { sepgpu_set_error("fij_enable: not available in decomposed runs"); return SEPGPU_ESTATE; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->fij && c->nmol == nmol) return 0;
+    if (c->fij) { cudaFree(c->fij); c->fij = NULL; }
+    CUDA_TRY(cudaMalloc((void **)&c->fij, sizeof(double) * 3 * (size_t)nmol * nmol));
+    CUDA_TRY(cudaMemsetAsync(c->fij, 0, sizeof(double) * 3 * (size_t)nmol * nmol, c->stream));
+    c->nmol = nmol;
+    return 0;
+}
+
+extern "C" int sepgpu_fij_reset(sepgpu_ctx *c)
+{
+    if (!c || !c->fij) return SEPGPU_ESTATE;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemsetAsync(c->fij, 0, sizeof(double) * 3 * (size_t)c->nmol * c->nmol, c->stream));
+    return 0;
+}
+
+__global__ void k_fij_to_float(const double *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+// the table as nmol*nmol*3 floats (the reference's element type), row-major [i][j][k]
+extern "C" int sepgpu_fij_get(sepgpu_ctx *c, float *out)
+{
+    if (!c || !out || !c->fij) return SEPGPU_ESTATE;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t cnt = 3 * (size_t)c->nmol * c->nmol;
+    int rc = sepgpu_ensure_stage(c, cnt * sizeof(float));
+    if (rc) return rc;
+    k_fij_to_float<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(c->fij, (float *)c->dstage, cnt);
+    KERNEL_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(c->stage, c->dstage, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->stage, cnt * sizeof(float));
+    return 0;
+}
+
 // ---- scalars ----------------------------------------------------------------------------------------------
 __global__ void k_reset_ret(DevScalars *s)
 {
@@ -616,7 +661,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     if (!strcmp(name, "tpa")) {
         if (value != 1 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32 && value != 0)
             return SEPGPU_EINVAL;
-        c->tpa = value ? (int)value : 1;
+        c->tpa = value ? (int)(value > 8 ? 8 : value) : 1;
         return 0;
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }

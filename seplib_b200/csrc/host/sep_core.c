@@ -168,6 +168,10 @@ sep_binding *sepb_prepare(seppart *atoms, sepsys *sys)
         b->dev_dirty = 0;
     }
     if (sys->molptr) b->molptr = sys->molptr;
+    if (sys->molptr && sys->molptr->flag_Fij == 1 && !b->fij_on && sys->molptr->num_mols > 0) {
+        sepb_check(sepgpu_fij_enable(b->gpu, (int)sys->molptr->num_mols), "molecular force table");
+        b->fij_on = 1;
+    }
     if (!b->host_dirty) return b;
 
     /* every dirty field in ONE pass over the 568-byte records and one PCIe transfer */

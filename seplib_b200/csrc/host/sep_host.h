@@ -33,6 +33,7 @@ typedef struct sep_binding {
     unsigned dev_dirty;
     int uploaded_once;
     int dpd_state_on_device;
+    int fij_on;                  /* device molecule-molecule force table enabled */
     double *alpha_ptr[4];       /* caller-owned thermostat multipliers mapped to device slots */
     double alpha_seen[4];
     unsigned long long dpd_calls;

@@ -291,27 +291,53 @@ void sep_torsion_Ryckaert(sepatom *ptr, int type, const double g[6], sepsys *sys
 }
 
 /* ---- molecular pressure tensor (source/sepmol.c:913-963, source/sepret.c:85-102) --------------------------
- * Needs the molecule-molecule force table Fij.  The device path does not fill Fij yet (SURVEY section
- * 8f, rank 1): the kinetic part is exact, the configurational part is reported as NaN so that a
- * caller cannot mistake it for a result. */
+ * The molecule-molecule force table Fij is accumulated on the device by the pair kernels (FP64 there,
+ * float in the reference); it is copied into the caller-visible float table when the tensor is evaluated. */
 void sep_reset_force_mol(sepsys *sys)
 {
     sys->fun_cstate = 0;
     if (sys->molptr->flag_Fij == 0)
         sep_error("%s: Tried to reset mol force, but flag is zero", (char *)__func__);
+    sep_binding *b = sepb_find_mol(sys->molptr);
+    if (b && b->gpu) {
+        sepb_check(sepgpu_fij_enable(b->gpu, (int)sys->molptr->num_mols), "sep_reset_force_mol");
+        sepb_check(sepgpu_fij_reset(b->gpu), "sep_reset_force_mol");
+    }
 }
 
 void sep_eval_mol_pressure_tensor(sepatom *atoms, sepmol *mols, sepret *ret, sepsys *sys)
 {
     if (sys->molptr->flag_Fij == 0) return;
     const int nmol = (int)sys->molptr->num_mols;
+    float ***Fij = sys->molptr->Fij;
+    sep_binding *b = sepb_find(atoms);
+    if (b && b->gpu) {
+        float *flat = malloc(sizeof(float) * 3 * (size_t)nmol * nmol);
+        if (!flat) sep_error("%s at %d: Couldn't allocate memory", (char *)__func__, __LINE__);
+        int rc = sepgpu_fij_get(b->gpu, flat);
+        if (rc == 0)
+            for (int i = 0; i < nmol; i++)
+                for (int j = 0; j < nmol; j++)
+                    for (int k = 0; k < 3; k++) Fij[i][j][k] = flat[((size_t)i * nmol + j) * 3 + k];
+        free(flat);
+    }
     sep_mol_cm(atoms, mols, sys);
     sep_mol_velcm(atoms, mols, sys);
     for (int k = 0; k < 3; k++)
-        for (int kk = 0; kk < 3; kk++) { ret->kin_P_mol[k][kk] = 0.0; ret->pot_P_mol[k][kk] = NAN; }
+        for (int kk = 0; kk < 3; kk++) ret->kin_P_mol[k][kk] = ret->pot_P_mol[k][kk] = 0.0;
     for (int i = 0; i < nmol; i++)
         for (int k = 0; k < 3; k++)
             for (int kk = 0; kk < 3; kk++) ret->kin_P_mol[k][kk] += mols[i].m * mols[i].v[k] * mols[i].v[kk];
+    for (int i = 0; i < nmol - 1; i++)
+        for (int j = i + 1; j < nmol; j++) {
+            double rij[3];
+            for (int k = 0; k < 3; k++) {
+                rij[k] = mols[i].x[k] - mols[j].x[k];
+                sep_Wrap(rij[k], sys->length[k]);
+            }
+            for (int k = 0; k < 3; k++)
+                for (int kk = 0; kk < 3; kk++) ret->pot_P_mol[k][kk] += Fij[i][j][k] * rij[kk];
+        }
 }
 
 void sep_mol_pressure_tensor(sepatom *atoms, sepmol *mols, sepret *ret, sepsys *sys)

@@ -222,11 +222,62 @@ def dpd_fixture(lib):
     print("dpd_n512 ok")
 
 
+def fij_array(s):
+    """sys->molptr->Fij (float ***) as an (nmol, nmol, 3) float32 array."""
+    mp = s.sys.molptr.contents
+    nm = mp.num_mols
+    rows = C.cast(mp.Fij, C.POINTER(C.POINTER(C.POINTER(C.c_float))))
+    out = np.zeros((nm, nm, 3), dtype=np.float32)
+    for i in range(nm):
+        ri = rows[i]
+        for j in range(nm):
+            out[i, j] = ri[j][0:3]
+    return out
+
+
+def molpress_fixture(lib):
+    """Molecule-molecule force table and molecular pressure tensor (sep_init_mol, sep_reset_force_mol,
+    sep_mol_pressure_tensor) on the recorded butane (list mode) and water (brute, with SF Coulomb) states."""
+    out = {}
+    g = np.load(os.path.join(HERE, "butane_n4000.npz"))
+    s = cm.ApiSystem.from_xyz(lib, f"{REFROOT}/test/prg1.xyz", f"{REFROOT}/test/prg1.top", 2.5, 0.001, capi.SEP_LLIST_NEIGHBLIST)
+    s.view["x"][:] = g["x0"]; s.view["v"][:] = g["v0"]; s.view["crossings"][:] = g["cr0"]
+    mols = lib.sep_init_mol(s.atoms, s.S)
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S); lib.sep_reset_force_mol(s.S)
+    lib.sep_force_pairs(s.atoms, b"CC", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+    lib.sep_mol_pressure_tensor(s.atoms, mols, s.R, s.S)
+    F = fij_array(s)
+    nz = np.argwhere(np.abs(F).sum(axis=2) > 0).astype(np.int32)
+    out.update(butane_fij_idx=nz, butane_fij_val=F[nz[:, 0], nz[:, 1]], butane_p_mol=s.ret.p_mol,
+               butane_P_mol=np.array([list(r) for r in s.ret.P_mol]), butane_kin_P_mol=np.array([list(r) for r in s.ret.kin_P_mol]),
+               butane_pot_P_mol=np.array([list(r) for r in s.ret.pot_P_mol]))
+    print("molpress butane: nonzero Fij", len(nz), "p_mol", s.ret.p_mol)
+    lib.sep_free_mol(mols, s.S)
+    s.close()
+
+    g = np.load(os.path.join(HERE, "water_n648.npz"))
+    s = cm.ApiSystem.from_xyz(lib, f"{REFROOT}/test/prg2.xyz", f"{REFROOT}/test/prg2.top", 2.9, 5.0e-4, capi.SEP_BRUTE)
+    s.view["x"][:] = g["x0"]; s.view["v"][:] = g["v0"]; s.view["crossings"][:] = g["cr0"]
+    mols = lib.sep_init_mol(s.atoms, s.S)
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S); lib.sep_reset_force_mol(s.S)
+    lib.sep_force_pairs(s.atoms, b"OO", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+    lib.sep_coulomb_sf(s.atoms, 2.9, s.S, s.R, 3)
+    lib.sep_mol_pressure_tensor(s.atoms, mols, s.R, s.S)
+    F = fij_array(s)
+    out.update(water_fij=F, water_p_mol=s.ret.p_mol, water_P_mol=np.array([list(r) for r in s.ret.P_mol]),
+               water_kin_P_mol=np.array([list(r) for r in s.ret.kin_P_mol]),
+               water_pot_P_mol=np.array([list(r) for r in s.ret.pot_P_mol]))
+    print("molpress water: p_mol", s.ret.p_mol)
+    lib.sep_free_mol(mols, s.S)
+    s.close()
+    np.savez_compressed(os.path.join(HERE, "molpress.npz"), **out)
+
+
 if __name__ == "__main__":
     lib = cm.ref()
     if lib is None:
         sys.exit("oracle/_ref/libsep_ref.so missing: run `make -C oracle ref` first")
-    lj_fixture(lib)
-    butane_fixture(lib)
-    water_fixture(lib)
-    dpd_fixture(lib)
+    which = sys.argv[1:] or ["lj", "butane", "water", "dpd", "molpress"]
+    for name in which:
+        {"lj": lj_fixture, "butane": butane_fixture, "water": water_fixture, "dpd": dpd_fixture,
+         "molpress": molpress_fixture}[name](lib)

@@ -271,3 +271,128 @@ def test_sep_api_butane_and_water_steps():
     assert np.abs(s.view["x"] - g["x1"]).max() <= 1e-11 and np.abs(s.view["v"] - g["v1"]).max() <= 1e-10
     assert abs(s.ret.ekin - float(g["ekin"])) <= FT * float(g["ekin"])
     s.close()
+
+
+def _write_top(g, tag):
+    top = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"sepb200_{tag}_{os.getpid()}.top")
+    with open(top, "w") as fh:
+        fh.write("[ bonds ]\n;generated for the test\n")
+        for (a, b, t) in g["blist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {t}\n")
+        fh.write("\n[ angles ]\n;generated\n")
+        for (a, b, c, t) in g["alist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {c} {t}\n")
+        if len(g["dlist"]):
+            fh.write("\n[ dihedrals ]\n;generated\n")
+            for (a, b, c, d, t) in g["dlist"]:
+                fh.write(f"{g['molindex'][a]} {a} {b} {c} {d} {t}\n")
+    return top
+
+
+def _fij_host(s):
+    mp = s.sys.molptr.contents
+    nm = mp.num_mols
+    rows = C.cast(mp.Fij, C.POINTER(C.POINTER(C.POINTER(C.c_float))))
+    out = np.zeros((nm, nm, 3), dtype=np.float32)
+    for i in range(nm):
+        ri = rows[i]
+        for j in range(nm):
+            out[i, j] = ri[j][0:3]
+    return out
+
+
+# The reference accumulates Fij in float (include/sepstrct.h:94); the device accumulates in FP64 and rounds
+# once on read-out, so the table agrees to float rounding of a sum of O(10) terms.
+FIJ_TOL = 2e-5
+
+
+@pytest.mark.parametrize("sync", [1, 0])
+def test_sep_api_molecular_pressure_tensor(sync):
+    """sep_init_mol / sep_reset_force_mol / sep_mol_pressure_tensor (source/sepmol.c:913-963) on the recorded
+    butane (list mode, EXCL_SAME_MOL) and water (brute LJ + brute SF Coulomb) states, against the reference's
+    own Fij table and P_mol (tests/golden/molpress.npz)."""
+    lib = capi.load()
+    lib.sep_gpu_set_sync(sync)
+    gm = np.load(os.path.join(cm.GOLDEN, "molpress.npz"))
+    # butane
+    g = np.load(os.path.join(cm.GOLDEN, "butane_n4000.npz"))
+    n = len(g["x0"])
+    s = cm.ApiSystem(lib, g["x0"], g["L"], 2.5, 0.001, v=g["v0"], types=np.full(n, ord("C"), dtype=np.uint8), nneighb=0)
+    s.view["crossings"][:] = g["cr0"]
+    top = _write_top(g, "mpb")
+    lib.sep_read_topology_file(s.atoms, top.encode(), s.S, b"q"); os.unlink(top)
+    mols = lib.sep_init_mol(s.atoms, s.S)
+    assert s.sys.molptr.contents.flag_Fij == 1 and s.sys.molptr.contents.num_mols == 1000
+    for rep in range(2):                    # second pass: the reset really clears the device table
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S); lib.sep_reset_force_mol(s.S)
+        lib.sep_force_pairs(s.atoms, b"CC", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+        lib.sep_mol_pressure_tensor(s.atoms, mols, s.R, s.S)
+        F = _fij_host(s)
+        ref = np.zeros_like(F)
+        idx = gm["butane_fij_idx"]
+        ref[idx[:, 0], idx[:, 1]] = gm["butane_fij_val"]
+        scale = np.abs(ref).max()
+        assert np.abs(F - ref).max() <= FIJ_TOL * scale
+        assert np.array_equal(np.abs(F).sum(axis=2) > 0, np.abs(ref).sum(axis=2) > 0)
+        kin = np.array([list(r) for r in s.ret.kin_P_mol]); pot = np.array([list(r) for r in s.ret.pot_P_mol])
+        assert np.abs(kin - gm["butane_kin_P_mol"]).max() <= 1e-10 * np.abs(gm["butane_kin_P_mol"]).max()
+        assert np.abs(pot - gm["butane_pot_P_mol"]).max() <= FIJ_TOL * np.abs(gm["butane_pot_P_mol"]).max()
+        assert abs(s.ret.p_mol - float(gm["butane_p_mol"])) <= FIJ_TOL * abs(float(gm["butane_p_mol"]))
+    lib.sep_free_mol(mols, s.S)
+    s.close()
+    # water
+    g = np.load(os.path.join(cm.GOLDEN, "water_n648.npz"))
+    s = cm.ApiSystem(lib, g["x0"], g["L"], 2.9, 5.0e-4, update=capi.SEP_BRUTE, v=g["v0"], types=g["type"], m=g["m"],
+                     z=g["z"], nneighb=0)
+    s.view["crossings"][:] = g["cr0"]
+    top = _write_top(g, "mpw")
+    lib.sep_read_topology_file(s.atoms, top.encode(), s.S, b"q"); os.unlink(top)
+    mols = lib.sep_init_mol(s.atoms, s.S)
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S); lib.sep_reset_force_mol(s.S)
+    lib.sep_force_pairs(s.atoms, b"OO", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+    lib.sep_coulomb_sf(s.atoms, 2.9, s.S, s.R, 3)
+    lib.sep_mol_pressure_tensor(s.atoms, mols, s.R, s.S)
+    F = _fij_host(s)
+    ref = gm["water_fij"]
+    assert np.abs(F - ref).max() <= FIJ_TOL * np.abs(ref).max()
+    pot = np.array([list(r) for r in s.ret.pot_P_mol])
+    assert np.abs(pot - gm["water_pot_P_mol"]).max() <= 5 * FIJ_TOL * np.abs(gm["water_pot_P_mol"]).max()
+    assert abs(s.ret.p_mol - float(gm["water_p_mol"])) <= 5 * FIJ_TOL * abs(float(gm["water_p_mol"]))
+    lib.sep_free_mol(mols, s.S)
+    s.close()
+    lib.sep_gpu_set_sync(1)
+
+
+def test_fij_list_equals_brute_and_sums_to_molecular_force():
+    """C-ABI: the molecule-molecule force table filled by the list kernels (source/sepprfrc.c:199-207,
+    source/sepcoulomb.c:138-147) equals the one filled by the brute kernels (source/sepprfrc.c:70-84,
+    source/sepcoulomb.c:68-82), and its row sums are the total pair force on each molecule."""
+    x, types, z, m, mol, L, _ = tiled_water(2)
+    n = len(x); nmol = int(mol.max()) + 1
+    cf, skin = 2.9, 0.25
+    p = capi.lj_param(2.5, kind="lj_shift")
+    tabs = []
+    for update in (capi.SEP_LLIST_NEIGHBLIST, capi.SEP_BRUTE):
+        s = capi.System(n)
+        s.put(capi.F_X, x); s.put(capi.F_TYPE, types); s.put(capi.F_Z, z); s.put(capi.F_M, m); s.put(capi.F_MOLINDEX, mol)
+        sys_ = capi.make_sys(L, cf, 5e-4, neighb_update=update, skin=skin)
+        s.call("sepgpu_fij_enable", nmol)
+        s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+        if update != capi.SEP_BRUTE:
+            s.call("sepgpu_neighb_build", C.byref(sys_), cm.EXCL_SAME_MOL)
+        s.call("sepgpu_force_lj", C.byref(sys_), b"OO", C.byref(p), cm.EXCL_SAME_MOL, 1)
+        s.call("sepgpu_coulomb_sf", C.byref(sys_), cf, cm.EXCL_SAME_MOL)
+        tab = np.zeros((nmol, nmol, 3), dtype=np.float32)
+        s.call("sepgpu_fij_get", tab.ctypes.data_as(C.c_void_p))
+        f = s.get(capi.F_F)
+        fmol = np.zeros((nmol, 3)); np.add.at(fmol, mol, f)
+        assert np.abs(tab.astype(np.float64).sum(axis=1) - fmol).max() <= 1e-4 * np.abs(fmol).max()
+        assert np.abs(tab + tab.transpose(1, 0, 2)).max() <= 1e-5 * np.abs(tab).max()     # Fij = -Fji
+        # reset clears it
+        s.call("sepgpu_fij_reset")
+        t0 = np.ones((nmol, nmol, 3), dtype=np.float32)
+        s.call("sepgpu_fij_get", t0.ctypes.data_as(C.c_void_p))
+        assert not t0.any()
+        tabs.append(tab)
+        s.close()
+    assert np.abs(tabs[0] - tabs[1]).max() <= 1e-5 * np.abs(tabs[1]).max()
