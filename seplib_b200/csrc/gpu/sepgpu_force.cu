@@ -31,8 +31,8 @@ struct LJDev {
 
 struct BoxDev { double Lx, Ly, Lz; };
 
-// 1/x to ~1 ulp: MUFU.RCP64H seed (2^-23) + two Newton steps (4 DFMA) instead of the IEEE division
-// sequence; inputs are r^2 of in-range pairs, far from denormals/inf.
+// 1/x to ~1 ulp: MUFU.RCP64H seed (relative error <= 2^-23) + two Newton steps (4 DFMA) instead of the
+// IEEE division sequence; inputs are r^2 of in-range pairs, far from denormals/inf.
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double y;
@@ -42,6 +42,17 @@ __device__ __forceinline__ double fast_rcp(double x)
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
     return y;
+}
+
+// Same seed, ONE third-order step: y1 = y0 (1 + e + e^2), e = 1 - x y0.  The error goes 2^-23 -> 2^-69,
+// below double rounding, in 3 DFMA instead of 4.
+__device__ __forceinline__ double fast_rcp3(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double e2 = fma(e, e, e);
+    return fma(y, e2, y);
 }
 
 __device__ __forceinline__ double fast_rsqrt(double x)
@@ -71,15 +82,36 @@ __device__ __forceinline__ void apply_image(int code, const BoxDev &B, double &d
 
 // ---- Lennard-Jones, Verlet list ------------------------------------------------------------------------
 struct PairAcc {
-    double fx, fy, fz;
-    double u, vxx, vxy, vxz, vyy, vyz, vzz;
+    double fx, fy, fz;                       // per atom, in units of 48 eps
+    double u;                                // per thread
     int nin;
+    double v[6];                             // per thread: xx xy xz yy yz zz, touched once per atom + on boundary pairs
 };
+
+__device__ __forceinline__ void virial_add(double *v, double gx, double gy, double gz, double sx, double sy, double sz)
+{
+    v[0] = fma(gx, sx, v[0]); v[1] = fma(gx, sy, v[1]); v[2] = fma(gx, sz, v[2]);
+    v[3] = fma(gy, sy, v[3]); v[4] = fma(gy, sz, v[4]); v[5] = fma(gz, sz, v[5]);
+}
 
 // One listed pair, branch-free: out-of-range (or wrong-type) pairs run the same arithmetic with the
 // force factor selected to zero.  In a warp some lane is almost always in range, so the branchy form
 // executes the full block anyway; without the branch the compiler can interleave the dependent DFMA
 // chains of two pairs.  r2 of a real pair is finite and non-zero, so the masked values stay finite.
+//
+// The pair body is 20 FP64 instructions (32 in the first version).  Measured on B200 the kernel time did
+// NOT follow (0.268 -> 0.265 ms at 1e6 atoms): the binding unit is the L1 tag stage -- the 32 lanes of one
+// neighbour gather touch ~22 different 128-byte lines (ncu: l1tex throughput 83 %, 23 cycles per warp
+// gather), the FP64 pipe needs ~10.  The leaner body is kept because it frees issue slots and power:
+//  * the cutoff test is a 64-bit INTEGER compare of the bit patterns (both sides are non-negative doubles);
+//  * the prefactor 48 eps is applied once per atom, not per pair;
+//  * the virial is NOT accumulated per pair.  With a full list every pair is seen from both ends with
+//    exactly negated separation d_ij = x_i - x_j - S_ij (S = image shift), so
+//        sum_i sum_j g_ij (x) d_ij  =  2 sum_i F_i (x) x_i  -  sum_i sum_j g_ij (x) S_ij ,
+//    i.e. one outer product per ATOM (list epilogue) plus a correction on the rare pairs that cross a
+//    periodic boundary (code != 13, already a branch).  F_i is the force of THIS call only.  The sum
+//    is the reference's pot_P (source/sepprfrc.c:195-197) up to rounding: terms are O(|F| L) instead of
+//    O(|F| rc), costing log10(L/rc) < 2 of the 16 digits.
 // FIJ: also accumulate the molecule-molecule force table Fij[mi][mj] += f (reference
 // source/sepprfrc.c:199-207; each directed pair adds its own direction, the partner thread adds -f to
 // Fij[mj][mi]).  Only small systems carry the table (<= SEP_MAX_NUM_MOL molecules), the adds are FP64
@@ -92,29 +124,79 @@ __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, 
     const int code = (int)(e >> SEPGPU_SHIFT_BITS);
     if (code != 13) apply_image(code, B, dx, dy, dz);
     const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    bool in = r2 < P.cf2;
+    bool in = __double_as_longlong(r2) < __double_as_longlong(P.cf2);
     if (TYPED) {
         const int tj = tag_type(pj.w);
         in = in && ((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0));   // source/sepprfrc.c:171-172
     }
-    const double rri = P.sig2 * fast_rcp(r2);
+    const double rri = P.sig2 * fast_rcp3(r2);
     double rri3 = rri * rri * rri;
-    double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;             // source/sepmisc.c:139, sepprfrc.c:888
+    double ft = rri3 * (rri3 - P.awh) * rri;                       // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
     const double uu = rri3 - P.aw;
     ft = in ? ft : 0.0;
     rri3 = in ? rri3 : 0.0;
-    const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
-    A.fx += gx; A.fy += gy; A.fz += gz;
+    A.fx = fma(ft, dx, A.fx); A.fy = fma(ft, dy, A.fy); A.fz = fma(ft, dz, A.fz);
     A.u = fma(rri3, uu, A.u);                                      // u/(4 eps) before the shift
     A.nin += in ? 1 : 0;
-    A.vxx = fma(gx, dx, A.vxx); A.vxy = fma(gx, dy, A.vxy); A.vxz = fma(gx, dz, A.vxz);
-    A.vyy = fma(gy, dy, A.vyy); A.vyz = fma(gy, dz, A.vyz); A.vzz = fma(gz, dz, A.vzz);
+    if (code != 13) {                                              // boundary-crossing pair: - g (x) S
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        apply_image(code, B, sx, sy, sz);                          // s = -S
+        const double g = P.eps48 * ft;
+        virial_add(A.v, g * dx, g * dy, g * dz, sx, sy, sz);
+    }
     if (FIJ && in) {
         const int mi = tag_mol(pi.w), mj = tag_mol(pj.w);
         if (mi != -1 && mj != -1 && mi != mj) {
+            const double g = P.eps48 * ft;
             double *t = fij + ((size_t)mi * nmol + mj) * 3;
-            atomicAdd(t, gx); atomicAdd(t + 1, gy); atomicAdd(t + 2, gz);
+            atomicAdd(t, g * dx); atomicAdd(t + 1, g * dy); atomicAdd(t + 2, g * dz);
         }
+    }
+}
+
+// Two listed pairs as ONE straight-line block, so that the scheduler interleaves their dependent FP64 chains
+// (a pair is ~16 dependent FP64 operations deep; one chain at a time leaves the pipe idle).  The image shift
+// and its virial correction are taken by both pairs when either needs them (code 13 shifts by zero).
+// valid1 == false: the second slot is past the end of the row; its gather points at a real atom and its
+// contribution is masked out.
+template <bool TYPED>
+__device__ __forceinline__ void lj_pair2(const d4 &pi, const d4 &p0, const d4 &p1, unsigned e0, unsigned e1, bool valid1,
+                                         int ti, const LJDev &P, const BoxDev &B, PairAcc &A)
+{
+    double dx0 = pi.x - p0.x, dy0 = pi.y - p0.y, dz0 = pi.z - p0.z;
+    double dx1 = pi.x - p1.x, dy1 = pi.y - p1.y, dz1 = pi.z - p1.z;
+    const int c0 = (int)(e0 >> SEPGPU_SHIFT_BITS), c1 = valid1 ? (int)(e1 >> SEPGPU_SHIFT_BITS) : 13;
+    const bool shifted = (c0 != 13) | (c1 != 13);
+    if (shifted) { apply_image(c0, B, dx0, dy0, dz0); apply_image(c1, B, dx1, dy1, dz1); }
+    const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+    const double r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+    bool in0 = __double_as_longlong(r20) < __double_as_longlong(P.cf2);
+    bool in1 = (__double_as_longlong(r21) < __double_as_longlong(P.cf2)) && valid1;
+    if (TYPED) {
+        const int t0 = tag_type(p0.w), t1 = tag_type(p1.w);
+        in0 = in0 && ((ti == P.t0 && t0 == P.t1) || (ti == P.t1 && t0 == P.t0));     // source/sepprfrc.c:171-172
+        in1 = in1 && ((ti == P.t0 && t1 == P.t1) || (ti == P.t1 && t1 == P.t0));
+    }
+    const double a0 = P.sig2 * fast_rcp3(r20), a1 = P.sig2 * fast_rcp3(r21);
+    double b0 = a0 * a0 * a0, b1 = a1 * a1 * a1;
+    double f0 = b0 * (b0 - P.awh) * a0, f1 = b1 * (b1 - P.awh) * a1;   // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
+    const double u0 = b0 - P.aw, u1 = b1 - P.aw;
+    f0 = in0 ? f0 : 0.0; f1 = in1 ? f1 : 0.0;
+    b0 = in0 ? b0 : 0.0; b1 = in1 ? b1 : 0.0;
+    A.fx = fma(f0, dx0, A.fx); A.fy = fma(f0, dy0, A.fy); A.fz = fma(f0, dz0, A.fz);
+    A.u = fma(b0, u0, A.u);
+    A.fx = fma(f1, dx1, A.fx); A.fy = fma(f1, dy1, A.fy); A.fz = fma(f1, dz1, A.fz);
+    A.u = fma(b1, in1 ? u1 : 0.0, A.u);
+    A.nin += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+    if (shifted) {                                                  // boundary-crossing pairs: - g (x) S
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        apply_image(c0, B, sx, sy, sz);
+        double g = P.eps48 * f0;
+        virial_add(A.v, g * dx0, g * dy0, g * dz0, sx, sy, sz);
+        sx = sy = sz = 0.0;
+        apply_image(c1, B, sx, sy, sz);
+        g = P.eps48 * f1;
+        virial_add(A.v, g * dx1, g * dy1, g * dz1, sx, sy, sz);
     }
 }
 
@@ -133,8 +215,10 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
     const int sub = threadIdx.x % TPA;
     constexpr int GROUPS = FORCE_BLOCK / TPA;
     PairAcc A;
-    A.u = A.vxx = A.vxy = A.vxz = A.vyy = A.vyz = A.vzz = 0.0;
+    A.u = 0.0;
     A.nin = 0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) A.v[q] = 0.0;
     const int first = blockIdx.x * atoms_per_cta;
     const int last = min(n, first + atoms_per_cta);
     const uint4 *nbrv = reinterpret_cast<const uint4 *>(nbr);
@@ -161,19 +245,32 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
                 uint4 nxt = make_uint4(0, 0, 0, 0);
                 if (cn < nch) nxt = __ldcs(row + (size_t)cn * npad);
                 const int left = m - 4 * c;                      // >= 1 valid entries in this chunk
-                {
+                if (FIJ) {
                     const bool v1 = left > 1;
                     const d4 p0 = xs[cur.x & SEPGPU_INDEX_MASK];
                     const d4 p1 = xs[v1 ? (cur.y & SEPGPU_INDEX_MASK) : (unsigned)s];
                     lj_pair<TYPED, FIJ>(pi, p0, cur.x, ti, P, B, A, fij, nmol);
                     if (v1) lj_pair<TYPED, FIJ>(pi, p1, cur.y, ti, P, B, A, fij, nmol);
-                }
-                if (left > 2) {
-                    const bool v3 = left > 3;
-                    const d4 p2 = xs[cur.z & SEPGPU_INDEX_MASK];
-                    const d4 p3 = xs[v3 ? (cur.w & SEPGPU_INDEX_MASK) : (unsigned)s];
-                    lj_pair<TYPED, FIJ>(pi, p2, cur.z, ti, P, B, A, fij, nmol);
-                    if (v3) lj_pair<TYPED, FIJ>(pi, p3, cur.w, ti, P, B, A, fij, nmol);
+                    if (left > 2) {
+                        const bool v3 = left > 3;
+                        const d4 p2 = xs[cur.z & SEPGPU_INDEX_MASK];
+                        const d4 p3 = xs[v3 ? (cur.w & SEPGPU_INDEX_MASK) : (unsigned)s];
+                        lj_pair<TYPED, FIJ>(pi, p2, cur.z, ti, P, B, A, fij, nmol);
+                        if (v3) lj_pair<TYPED, FIJ>(pi, p3, cur.w, ti, P, B, A, fij, nmol);
+                    }
+                } else {
+                    {
+                        const bool v1 = left > 1;
+                        const d4 p0 = xs[cur.x & SEPGPU_INDEX_MASK];
+                        const d4 p1 = xs[(v1 ? cur.y : cur.x) & SEPGPU_INDEX_MASK];
+                        lj_pair2<TYPED>(pi, p0, p1, cur.x, cur.y, v1, ti, P, B, A);
+                    }
+                    if (left > 2) {
+                        const bool v3 = left > 3;
+                        const d4 p2 = xs[cur.z & SEPGPU_INDEX_MASK];
+                        const d4 p3 = xs[(v3 ? cur.w : cur.z) & SEPGPU_INDEX_MASK];
+                        lj_pair2<TYPED>(pi, p2, p3, cur.z, cur.w, v3, ti, P, B, A);
+                    }
                 }
                 cur = nxt;
                 c = cn;
@@ -188,20 +285,26 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
         }
         if (valid && sub == 0) {
             const int i = order[s];
+            const double fx = P.eps48 * A.fx, fy = P.eps48 * A.fy, fz = P.eps48 * A.fz;
             if (STORE) {
-                d4 o; o.x = A.fx; o.y = A.fy; o.z = A.fz; o.w = 0.0;
+                d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0;
                 f4[i] = o;
             } else {
                 d4 o = f4[i];
-                o.x += A.fx; o.y += A.fy; o.z += A.fz;
+                o.x += fx; o.y += fy; o.z += fz;
                 f4[i] = o;
             }
+            // per-atom part of the virial (see lj_pair): 2 F_i (x) x_i, upper triangle
+            const d4 pi = xs[s];
+            const double tx = fx + fx, ty = fy + fy, tz = fz + fz;
+            virial_add(A.v, tx, ty, tz, pi.x, pi.y, pi.z);
         }
     }
     double acc[SEPGPU_NPART_F];
     acc[0] = P.eps4 * A.u - P.shift * (double)A.nin;
     acc[1] = 0.0;
-    acc[2] = A.vxx; acc[3] = A.vxy; acc[4] = A.vxz; acc[5] = A.vyy; acc[6] = A.vyz; acc[7] = A.vzz;
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc[2 + q] = A.v[q];
     block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
     if (threadIdx.x == 0) {
 #pragma unroll
