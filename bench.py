@@ -229,6 +229,237 @@ def host_cores():
 
 
 # ---------------------------------------------------------------------------------------------------
+# molecular workloads C2 (butane) and C3 (water): SURVEY.md section 8d, single GPU
+# ---------------------------------------------------------------------------------------------------
+def mol_api_system(lib, capi, w, P, update, nneighb, skin):
+    """The workload as a sep_* API system (host seppart[] + sepsys + topology read from a .top file)."""
+    import tempfile
+    from seplib_b200 import workloads as wl
+    n = w["n"]
+    atoms = lib.sep_init(n, nneighb)
+    view = capi.atoms_view(atoms, n)
+    view["x"][:] = w["x"]; view["v"][:] = w["v"]; view["type"][:] = w["type"]; view["m"][:] = w["m"]; view["z"][:] = w["z"]
+    view["xn"][:] = 0.0
+    L = w["L"]
+    hsys = lib.sep_sys_setup(L[0], L[1], L[2], P["cf"], P["dt"], n, update)
+    lib.sep_set_skin(C.byref(hsys), skin)
+    fd, top = tempfile.mkstemp(suffix=".top")
+    os.close(fd)
+    wl.write_top(w, top)
+    lib.sep_read_topology_file(atoms, top.encode(), C.byref(hsys), b"q")
+    os.unlink(top)
+    return atoms, view, hsys
+
+
+def mol_api_step(lib, capi, name, P, atoms, hsys, ret, alpha):
+    fun = C.cast(lib.sep_lj_shift, C.c_void_p)
+    S, R = C.byref(hsys), C.byref(ret)
+    if name == "butane":
+        rb = (C.c_double * 6)(*P["rb"])
+
+        def step():          # prgs/prg2.c:51-95
+            lib.sep_reset_retval(R); lib.sep_reset_force(atoms, S)
+            lib.sep_force_pairs(atoms, P["types"], P["cf"], fun, S, R, capi.SEP_EXCL_SAME_MOL)
+            lib.sep_stretch_harmonic(atoms, 0, P["lbond"], P["kbond"], S, R)
+            lib.sep_angle_harmonic(atoms, 0, P["angle"], P["kangle"], S, R)
+            lib.sep_torsion_Ryckaert(atoms, 0, rb, S, R)
+            lib.sep_nosehoover(atoms, P["temp"], C.byref(alpha), P["tau"], S)
+            lib.sep_leapfrog(atoms, S, R)
+    else:
+
+        def step():          # prgs/prg3.c:55-98 (without the box compression, which ended before this state)
+            lib.sep_reset_retval(R); lib.sep_reset_force(atoms, S)
+            lib.sep_force_pairs(atoms, P["types"], P["cf_lj"], fun, S, R, capi.SEP_EXCL_SAME_MOL)
+            lib.sep_stretch_harmonic(atoms, 0, P["lbond"], P["kbond"], S, R)
+            lib.sep_angle_cossq(atoms, 0, P["angle"], P["kangle"], S, R)
+            lib.sep_coulomb_sf(atoms, P["cf"], S, R, capi.SEP_EXCL_SAME_MOL)
+            lib.sep_nosehoover(atoms, P["temp"], C.byref(alpha), P["tau"], S)
+            lib.sep_leapfrog(atoms, S, R)
+    return step
+
+
+def mol_cpu_arm(name, skin, target_seconds, threads):
+    """Reference CPU build on a small tiling of the same unit cell (butane 4000 atoms; water 2^3 cells = 5184 atoms,
+    the smallest tiling whose cell grid has the 3 cells per side list mode needs)."""
+    from seplib_b200 import capi
+    from seplib_b200 import workloads as wl
+    fast = os.path.join(ROOT, "oracle", "_ref", "libsep_ref_fast.so")
+    if not os.path.exists(fast):
+        raise RuntimeError("oracle/_ref/libsep_ref_fast.so missing (the molecular CPU arm has no port fallback)")
+    lib = C.CDLL(fast, mode=C.RTLD_LOCAL)
+    capi.declare_sep_api(lib)
+    P = wl.BUTANE if name == "butane" else wl.WATER
+    w = wl.butane(1) if name == "butane" else wl.water(2)
+    atoms, view, hsys = mol_api_system(lib, capi, w, P, capi.SEP_LLIST_NEIGHBLIST, 3000, skin)
+    if threads > 1:
+        lib.sep_set_omp(threads, C.byref(hsys))
+    ret = capi.SepRet(); alpha = C.c_double(0.1)
+    step = mol_api_step(lib, capi, name, P, atoms, hsys, ret, alpha)
+    for _ in range(3):
+        step()
+    t0 = time.perf_counter()
+    step(); step()
+    per = (time.perf_counter() - t0) / 2
+    steps = int(max(5, min(5000, target_seconds / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    el = time.perf_counter() - t0
+    n = w["n"]
+    value = n * steps / el
+    lib.sep_close(atoms, n)
+    return value, {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": f"{name}: {n} atoms x {steps} steps in {el:.1f} s, epot/N={ret.epot / n:.4f}",
+                   "seconds": el, "steps": steps, "natoms": n}
+
+
+def run_molecular(args, emit, local_rank):
+    import torch
+    from seplib_b200 import capi
+    from seplib_b200 import workloads as wl
+    name = args.workload
+    P = wl.BUTANE if name == "butane" else wl.WATER
+    reps = args.reps or (6 if name == "butane" else 12)
+    K, W = args.steps, max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    lib = capi.load()
+    if lib.sepgpu_device_count() <= 0:
+        raise RuntimeError("bench.py: no CUDA device -- seplib-b200 has no CPU path")
+    w = wl.butane(reps) if name == "butane" else wl.water(reps)
+    n = w["n"]
+    gsys = capi.make_sys(w["L"], P["cf"], P["dt"], skin=args.skin)
+    gs = C.byref(gsys)
+    ljp = capi.lj_param(P["cf"] if name == "butane" else P["cf_lj"], kind="lj_shift")
+    ljr = C.byref(ljp)
+    rb = (C.c_double * 6)(*P["rb"]) if name == "butane" else None
+
+    s = capi.System(n, device=local_rank)
+    s.put(capi.F_X, w["x"]); s.put(capi.F_V, w["v"]); s.put(capi.F_TYPE, w["type"]); s.put(capi.F_M, w["m"])
+    s.put(capi.F_Z, w["z"]); s.put(capi.F_MOLINDEX, w["molindex"])
+    s.put(capi.F_BOND, w["bond"]); s.put(capi.F_ANGLE, w["angle"]); s.put(capi.F_DIHED, w["dihed"])
+    s.set_topology(w["blist"], w["alist"], w["dlist"])
+    s.call("sepgpu_set_alpha", 0, 0.1)
+    ctx, fn = s.ctx, lib
+
+    def step():
+        fn.sepgpu_reset_ret(ctx)
+        fn.sepgpu_reset_force(ctx)
+        r = fn.sepgpu_force_lj(ctx, gs, P["types"], ljr, 3, 1)
+        r |= fn.sepgpu_stretch_harmonic(ctx, gs, 0, P["lbond"], P["kbond"])
+        if name == "butane":
+            r |= fn.sepgpu_angle_harmonic(ctx, gs, 0, P["angle"], P["kangle"])
+            r |= fn.sepgpu_torsion_ryckaert(ctx, gs, 0, rb)
+        else:
+            r |= fn.sepgpu_angle_cossq(ctx, gs, 0, P["angle"], P["kangle"])
+            r |= fn.sepgpu_coulomb_sf(ctx, gs, P["cf"], 3)
+        r |= fn.sepgpu_nosehoover(ctx, gs, P["temp"], 0, P["tau"])
+        r |= fn.sepgpu_leapfrog(ctx, gs)
+        if r:
+            raise RuntimeError("device step failed: " + fn.sepgpu_last_error().decode())
+
+    for _ in range(W):
+        step()
+    nb0 = s.scalars().nbuild
+    s.call("sepgpu_set_option", b"time_kernels", 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    s.call("sepgpu_timer_start")
+    for _ in range(K):
+        step()
+    ms = C.c_float()
+    s.call("sepgpu_timer_stop", C.byref(ms))
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    sc = s.scalars()
+    nbuild = sc.nbuild - nb0
+    kt = {}
+    for which in ("force", "coulomb", "bonded", "build", "intgr"):
+        tot, cnt = C.c_float(), C.c_int()
+        s.call("sepgpu_kernel_time", which.encode(), C.byref(tot), C.byref(cnt))
+        kt[which] = (tot.value, cnt.value)
+    t_sec = ms.value * 1e-3
+    value = n * K / t_sec
+    full_entries = sc.npairs_listed / n
+    epotN, ekinN = sc.epot / n, sc.ekin / n
+    s.close()
+
+    # e2e: the sep_* API on a host seppart[] array, topology through the .top reader (SEP_SYNC=lazy)
+    e2e = None
+    if not args.no_e2e:
+        Ke = max(10, min(K, 200))
+        lib.sep_gpu_set_sync(0)
+        atoms, view, hsys = mol_api_system(lib, capi, w, P, capi.SEP_LLIST_NEIGHBLIST, 0, args.skin)
+        ret = capi.SepRet(); alpha = C.c_double(0.1)
+        step_api = mol_api_step(lib, capi, name, P, atoms, hsys, ret, alpha)
+        for _ in range(5):
+            step_api()
+        lib.sep_gpu_sync(atoms)
+        view["x"][:] = w["x"]; view["v"][:] = w["v"]; view["xn"][:] = 0.0
+        view["cross_neighb"][:] = 0; view["crossings"][:] = 0
+        lib.sep_gpu_invalidate(atoms)
+        hsys.neighb_flag = 1
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            step_api()
+        lib.sep_gpu_sync(atoms)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        e_epot = ret.epot / n
+        lib.sep_close(atoms, n)
+        h2d = n * (24 * 3 + 8 * 2 + 1 + 4 + 12 * 2)
+        d2h_final = n * (24 * 4 + 12 * 2 + 24)
+        e2e = {"value": n * Ke / el, "unit": UNIT, "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": 416 + d2h_final / Ke,
+               "steps": Ke, "epot_per_atom": e_epot,
+               "path": "sep_* API (include/sep.h), SEP_SYNC=lazy: scalars D2H every step; seppart[] uploaded at step 0 and "
+                       "downloaded after the last step, both inside the timed region"}
+
+    # roofline of the dominant pair kernel (k_lj_list for butane, k_coulomb_list for water): list + own row + force row
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = "coulomb" if name == "water" else "force"
+    d_ms, d_cnt = kt[dom]
+    dom_ms = d_ms / max(d_cnt, 1)
+    alg_bytes = 4.0 * full_entries / 2.0 + 64.0 + (8.0 if name == "water" else 0.0)     # half-list entries, SURVEY 8d convention
+    achieved = alg_bytes * n / (dom_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_coulomb_list" if name == "water" else "k_lj_list", "bound": "hbm", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_atom_step": alg_bytes, "avg_launch_ms": dom_ms, "launches": d_cnt,
+                "share_of_step": d_ms / (t_sec * 1e3)}
+    cpu = None
+    if not args.no_cpu:
+        try:
+            _, info = mol_cpu_arm(name, args.skin, args.cpu_seconds, host_cores())
+            cpu = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:      # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    per_step = 7 + (2 * 3 if name == "butane" else 2 * 3 + 1)
+    label = ("C2 butane: sep_force_pairs(CC, lj_shift, EXCL_SAME_MOL) + stretch + angle + Ryckaert torsion + NH + leapfrog"
+             if name == "butane" else
+             "C3 water: sep_force_pairs(OO) + stretch + cos^2 angle + sep_coulomb_sf(2.9) + NH + leapfrog")
+    emit({
+        "metric": METRIC.replace("LJ, rc=2.5", label.split(":")[0]), "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": t_sec * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "natoms_total": n, "molecules": w["nmol"], "tiling": f"{reps}^3 unit cells",
+                   "box": list(map(float, w["L"])), "cells": list(gsys.nsubbox[:]), "skin": args.skin, "dt": P["dt"],
+                   "parallelism": "single GPU", "l2": "inputs larger than L2 (Verlet list %.0f MB)" % (n * full_entries * 4 / 1e6),
+                   "list_rebuilds_in_timed_region": nbuild, "half_pairs_per_atom": full_entries / 2.0,
+                   "epot_per_atom": epotN, "ekin_per_atom": ekinN},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K * per_step + nbuild * 11, "clocks": clocks,
+        "kernel_ms": {k: {"total_ms": a, "launches": b} for k, (a, b) in kt.items()},
+    })
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
 def weak_lattice_dims(ncell, world):
     """Lattice sides for `world` GPUs at ncell^3 atoms per GPU (weak scaling, near-cubic box, z longest):
     1 -> n,n,n ; 2 -> n,n,2n ; 4 -> n,2n,2n ; 8 -> 2n,2n,2n."""
@@ -290,6 +521,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of domain decomposition")
+    ap.add_argument("--workload", default="lj", choices=["lj", "butane", "water"],
+                    help="lj = C1/C4 (the BASELINE metric, default); butane = C2; water = C3 (single GPU)")
+    ap.add_argument("--reps", type=int, default=0, help="molecular workloads: unit cells per side (default 6 / 12)")
     args = ap.parse_args()
 
     # stdout carries exactly ONE line (the JSON): libraries that print banners to fd 1 (NCCL version line,
@@ -306,6 +540,20 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     rc, dt, temp, tau = 2.5, 0.005, 1.0, 0.01       # prg1's literals with the metric's rc (prgs/prg1.c:24-30)
     K, W = args.steps, max(args.warmup, 3)
+
+    if args.workload != "lj":
+        if rank != 0:
+            return 0
+        if args.impl == "reference":
+            value, info = mol_cpu_arm(args.workload, args.skin, max(args.cpu_seconds, 5.0) * 2, host_cores())
+            emit({"impl": "reference", "metric": METRIC.replace("LJ, rc=2.5", args.workload), "value": value, "unit": UNIT,
+                  "n_gpus": args.gpus, "steps": info["steps"], "warmup": 5, "ms_per_step": 1e3 * info["seconds"] / info["steps"],
+                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": args.workload + " bounded CPU sample", "natoms": info["natoms"], "l2": "n/a (host)"},
+                  "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                  "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+            return 0
+        return run_molecular(args, emit, local_rank)
 
     if args.impl == "reference":
         if rank != 0:
@@ -559,7 +807,7 @@ def main():
                 "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_atom_step": alg_bytes, "avg_launch_ms": force_ms, "launches": f_cnt,
                 "share_of_step": f_ms / (t_sec * 1e3),
-                "fp64": {"note": "binding limit of this kernel is the FP64 pipe, not HBM",
+                "fp64": {"note": "neither HBM nor the FP64 pipe binds this kernel: the L1 tag stage does (each warp-wide neighbour gather touches ~22 distinct 128-B lines; ncu l1tex 83 %, profiles/r01_k_lj_list_ncu_full.txt)",
                          "algorithmic_flops_per_atom_step": alg_flops, "achieved_tflops": achieved_tf,
                          "peak_tflops_fma_chain_measured_here": fp64_peak.value,
                          "frac": achieved_tf / fp64_peak.value if fp64_peak.value else None}}

@@ -283,8 +283,10 @@ extern "C" int sepgpu_stretch_harmonic(sepgpu_ctx *c, const sepgpu_sys *sys, int
     if (!c->atom_bond_ptr) { sepgpu_set_error("stretch_harmonic: no topology on the device"); return SEPGPU_ESTATE; }
     CUDA_TRY(cudaSetDevice(c->device));
     const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
+    ktimer_begin(c, &c->t_bonded);
     k_bond<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->blist, c->atom_bond_ptr, c->atom_bond_idx,
                                                  type, lbond, ks, make_box(sys), c->f_zero ? 1 : 0, c->blengths, c->partial);
+    ktimer_end(c, &c->t_bonded);
     KERNEL_CHECK();
     c->f_zero = false;
     return sepgpu_finalize_force(c, grid, 1.0, 2);      // epot +=, pot_P += and pot_P_bond += (source/sepmol.c:403-409)
@@ -297,12 +299,14 @@ static int run_angle(sepgpu_ctx *c, const sepgpu_sys *sys, int type, double angl
     CUDA_TRY(cudaSetDevice(c->device));
     const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
     const double cCon = cos(SEPGPU_PI - angle0);        // host libm, as the reference (source/sepmol.c:422)
+    ktimer_begin(c, &c->t_bonded);
     if (cossq)
         k_angle<true><<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->alist, c->atom_angle_ptr, c->atom_angle_idx,
                                                             type, angle0, k, cCon, make_box(sys), c->f_zero ? 1 : 0, c->angles, c->partial);
     else
         k_angle<false><<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->alist, c->atom_angle_ptr, c->atom_angle_idx,
                                                              type, angle0, k, cCon, make_box(sys), c->f_zero ? 1 : 0, c->angles, c->partial);
+    ktimer_end(c, &c->t_bonded);
     KERNEL_CHECK();
     c->f_zero = false;
     return sepgpu_finalize_force(c, grid, 1.0, 0);      // no virial from angles (partial rows carry zeros)
@@ -325,8 +329,10 @@ extern "C" int sepgpu_torsion_ryckaert(sepgpu_ctx *c, const sepgpu_sys *sys, int
     CUDA_TRY(cudaSetDevice(c->device));
     const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
     RBCoef G; for (int k = 0; k < 6; k++) G.g[k] = g[k];
+    ktimer_begin(c, &c->t_bonded);
     k_torsion<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->dlist, c->atom_dihed_ptr, c->atom_dihed_idx,
                                                     type, G, make_box(sys), c->f_zero ? 1 : 0, c->dihedrals, c->partial);
+    ktimer_end(c, &c->t_bonded);
     KERNEL_CHECK();
     c->f_zero = false;
     return sepgpu_finalize_force(c, grid, 1.0, 0);

@@ -216,10 +216,10 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
             return SEPGPU_ESTATE;
         }
         const int grid = (c->n + FORCE_BLOCK - 1) / FORCE_BLOCK;
-        ktimer_begin(c, &c->t_force);
+        ktimer_begin(c, &c->t_coul);
         if (store) k_coulomb_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial, c->fij, c->nmol);
         else       k_coulomb_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->z, c->f4, c->n, cf, B, opt, c->excl_bond, c->excl_angle, c->excl_dihed, c->partial, c->fij, c->nmol);
-        ktimer_end(c, &c->t_force);
+        ktimer_end(c, &c->t_coul);
         KERNEL_CHECK();
         c->f_zero = false;
         return sepgpu_finalize_force(c, grid, 0.5, 4);
@@ -236,7 +236,7 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
     const long long gpb = FORCE_BLOCK / tpa;
     long long want = ((long long)c->n + gpb - 1) / gpb;
     const int grid = (int)(want < FORCE_MAX_GRID ? want : FORCE_MAX_GRID);
-    ktimer_begin(c, &c->t_force);
+    ktimer_begin(c, &c->t_coul);
     switch (tpa) {
     case 1: launch_coulomb<1>(c, grid, store, cf, B); break;
     case 2: launch_coulomb<2>(c, grid, store, cf, B); break;
@@ -245,7 +245,7 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
     case 16: launch_coulomb<16>(c, grid, store, cf, B); break;
     default: launch_coulomb<32>(c, grid, store, cf, B); break;
     }
-    ktimer_end(c, &c->t_force);
+    ktimer_end(c, &c->t_coul);
     KERNEL_CHECK();
     c->f_zero = false;
     return sepgpu_finalize_force(c, grid, 0.5, 4);

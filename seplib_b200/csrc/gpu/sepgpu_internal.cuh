@@ -152,7 +152,7 @@ struct sepgpu_ctx {
 
     // measurement
     cudaEvent_t ev0, ev1;
-    KernelTimer t_force, t_build, t_intgr;
+    KernelTimer t_force, t_build, t_intgr, t_coul, t_bonded;
     void *flush_buf; size_t flush_bytes;
 };
 

@@ -120,7 +120,7 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
                 const bool centre_row = (oz == 0 && oy == 0);
                 const int c0 = r * ncc + h;              // candidate cells c0 (ox=-1), c0+1 (own column), c0+2 (ox=+1)
                 const int wlo = s_off[c0], whi = s_off[c0 + 3];
-                const int cut_a = s_off[c0 + 1], cut_b = s_off[c0 + 2];
+                const int cut_a = s_off[c0 + 1];
                 const int self_q = centre_row ? cut_a + (s - s_beg[c0 + 1]) : -1;
 #pragma unroll 1
                 for (int q0 = wlo; q0 < whi; q0 += 32) {

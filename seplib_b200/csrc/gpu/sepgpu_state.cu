@@ -130,7 +130,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->stage) cudaFreeHost(c->stage);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
-    ktimer_free(&c->t_force); ktimer_free(&c->t_build); ktimer_free(&c->t_intgr);
+    ktimer_free(&c->t_force); ktimer_free(&c->t_build); ktimer_free(&c->t_intgr); ktimer_free(&c->t_coul); ktimer_free(&c->t_bonded);
     cudaStreamDestroy(c->stream);
     free(c);
 }
@@ -668,7 +668,8 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     if (!strcmp(name, "unroll")) { c->unroll = value == 4 ? 4 : 2; return 0; }
     if (!strcmp(name, "force_grid")) { c->force_grid = value > 0 && value <= SEPGPU_MAX_BLOCKS_PARTIAL ? (int)value : 0; return 0; }
     if (!strcmp(name, "time_kernels")) {
-        if (value) { if (ktimer_enable(&c->t_force) || ktimer_enable(&c->t_build) || ktimer_enable(&c->t_intgr)) return SEPGPU_ECUDA; }
+        if (value) { if (ktimer_enable(&c->t_force) || ktimer_enable(&c->t_build) || ktimer_enable(&c->t_intgr) ||
+                         ktimer_enable(&c->t_coul) || ktimer_enable(&c->t_bonded)) return SEPGPU_ECUDA; }
         return 0;
     }
     if (!strcmp(name, "neighb_cap")) {
@@ -685,7 +686,8 @@ extern "C" int sepgpu_kernel_time(sepgpu_ctx *c, const char *which, float *ms_to
 {
     if (!c || !which) return SEPGPU_EINVAL;
     KernelTimer *t = !strcmp(which, "force") ? &c->t_force : !strcmp(which, "build") ? &c->t_build
-                   : !strcmp(which, "intgr") ? &c->t_intgr : NULL;
+                   : !strcmp(which, "intgr") ? &c->t_intgr : !strcmp(which, "coulomb") ? &c->t_coul
+                   : !strcmp(which, "bonded") ? &c->t_bonded : NULL;
     if (!t || !t->enabled) return SEPGPU_EINVAL;
     CUDA_TRY(cudaSetDevice(c->device));
     ktimer_drain(t);

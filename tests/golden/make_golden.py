@@ -148,11 +148,16 @@ def butane_fixture(lib):
     print("butane_n4000: pairs", len(out["pairs_same_mol"]), len(out["pairs_nonbonded"]), "epot/N", out["epot_torsion"] / 4000)
 
 
-def water_fixture(lib):
-    """prg3's system (648 atoms, SPC/Fw water, SEP_BRUTE): LJ OO + bonds + cos^2 angles + SF Coulomb."""
+def water_fixture(lib, dense=False):
+    """prg3's system (648 atoms, SPC/Fw water, SEP_BRUTE): LJ OO + bonds + cos^2 angles + SF Coulomb.
+    dense=True: the compressed state prg3 ends in (rho = 3.15, the reference's cuda/start_water.xyz, which
+    carries velocities) -- the unit cell of the C3 benchmark workload."""
     cf, dt, temp = 2.9, 5.0e-4, 3.81
-    s = cm.ApiSystem.from_xyz(lib, f"{REFROOT}/test/prg2.xyz", f"{REFROOT}/test/prg2.top", cf, dt, capi.SEP_BRUTE)
-    lib.sep_set_vel_seed(s.atoms, temp, 42, s.sys)
+    if dense:
+        s = cm.ApiSystem.from_xyz(lib, f"{REFROOT}/cuda/start_water.xyz", f"{REFROOT}/cuda/start_water.top", cf, dt, capi.SEP_BRUTE)
+    else:
+        s = cm.ApiSystem.from_xyz(lib, f"{REFROOT}/test/prg2.xyz", f"{REFROOT}/test/prg2.top", cf, dt, capi.SEP_BRUTE)
+        lib.sep_set_vel_seed(s.atoms, temp, 42, s.sys)
     alpha = (C.c_double * 3)(0.1, 0.0, 0.0)
     fun = s.fun("sep_lj_shift")
 
@@ -193,8 +198,9 @@ def water_fixture(lib):
     lib.sep_coulomb_sf(s.atoms, cf, s.S, s.R, 2)
     out["f_coul_bonded"] = s.view["f"].copy(); out["ecoul_bonded"] = s.ret.ecoul
     s.close()
-    np.savez_compressed(os.path.join(HERE, "water_n648.npz"), **out)
-    print("water_n648: epot/mol", out["epot_coul"] / 216, "ecoul", out["ecoul"])
+    name = "water_dense_n648" if dense else "water_n648"
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, ": L", out["L"], "epot/mol", out["epot_coul"] / 216, "ecoul", out["ecoul"])
 
 
 def dpd_fixture(lib):
@@ -277,7 +283,7 @@ if __name__ == "__main__":
     lib = cm.ref()
     if lib is None:
         sys.exit("oracle/_ref/libsep_ref.so missing: run `make -C oracle ref` first")
-    which = sys.argv[1:] or ["lj", "butane", "water", "dpd", "molpress"]
+    which = sys.argv[1:] or ["lj", "butane", "water", "dpd", "molpress", "water_dense"]
     for name in which:
         {"lj": lj_fixture, "butane": butane_fixture, "water": water_fixture, "dpd": dpd_fixture,
-         "molpress": molpress_fixture}[name](lib)
+         "molpress": molpress_fixture, "water_dense": lambda l: water_fixture(l, dense=True)}[name](lib)

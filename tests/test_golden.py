@@ -123,8 +123,9 @@ def test_oracle_butane_golden():
     assert relerr(f2, g["f_cossq"]) <= EXACT and abs(r2.epot - float(g["epot_cossq"])) <= EXACT * abs(float(g["epot_cossq"]))
 
 
-def test_oracle_water_golden():
-    g = load("water_n648.npz")
+@pytest.mark.parametrize("fixture", ["water_n648.npz", "water_dense_n648.npz"])
+def test_oracle_water_golden(fixture):
+    g = load(fixture)
     x = np.ascontiguousarray(g["x0"]); n = len(x)
     length = Lvec(g); cf = float(g["cf"])
     t = topo_from(g, n)
@@ -327,8 +328,9 @@ def test_gpu_butane_golden():
 
 
 @pytest.mark.gpu
-def test_gpu_water_golden():
-    g = load("water_n648.npz")
+@pytest.mark.parametrize("fixture", ["water_n648.npz", "water_dense_n648.npz"])
+def test_gpu_water_golden(fixture):
+    g = load(fixture)
     n = len(g["x0"])
     t = topo_from(g, n)
     s = capi.System(n)
