@@ -516,6 +516,7 @@ def main():
     ap.add_argument("--tpa", type=int, default=0)
     ap.add_argument("--unroll", type=int, default=0)
     ap.add_argument("--force-grid", type=int, default=0)
+    ap.add_argument("--overlap", type=int, default=-1, help="decomposed runs: 0 = halo exchange before the force pass, 1 = beside it (default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--cpu-ncell", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true")
@@ -626,6 +627,8 @@ def main():
         for opt, val in (("tpa", args.tpa), ("unroll", args.unroll), ("force_grid", args.force_grid)):
             if val:
                 s_.call("sepgpu_set_option", opt.encode(), val)
+        if args.overlap >= 0:
+            s_.call("sepgpu_set_option", b"overlap", args.overlap)
         return s_
 
     def upload(s_):
@@ -673,7 +676,7 @@ def main():
     sc = s.scalars()
     nbuild = sc.nbuild - nb0
     kt = {}
-    for which in ("force", "build", "intgr"):
+    for which in ("force", "build", "intgr") + (("halo", "migrate") if decomposed else ()):
         tot, cnt = C.c_float(), C.c_int()
         s.call("sepgpu_kernel_time", which.encode(), C.byref(tot), C.byref(cnt))
         kt[which] = (tot.value, cnt.value)

@@ -34,6 +34,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)(void);
     ncclResult_t (*GroupEnd)(void);
     const char *(*GetErrorString)(ncclResult_t);
@@ -48,7 +49,7 @@ static int nccl_load(void)
     if (!g_nccl.lib) { sepgpu_set_error("domain decomposition: cannot dlopen libnccl.so.2 (%s)", dlerror()); return SEPGPU_ENCCL; }
 #define SYM(field, name) *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name); if (!g_nccl.field) { sepgpu_set_error("NCCL symbol %s missing", name); return SEPGPU_ENCCL; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather")
     SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     return 0;
@@ -84,6 +85,23 @@ struct DDState {
     int *send_idx[2];           // per-step halo send lists (local indices of owned atoms), lo and hi
     int n_send[2], n_recv[2];   // halo atoms sent to lo/hi, received from hi/lo (in that order)
     bool halo_current;
+    // second stream: the per-step halo refresh (NCCL path) runs beside the interior force pass
+    cudaStream_t stream2;
+    cudaEvent_t ev_ready, ev_halo;
+    bool halo_inflight;
+    // peer-memory halo push (NVLink P2P through CUDA IPC).  Every rank owns one block
+    //   [from-hi buffer: bufcap d4][from-lo buffer: bufcap d4][flags: 2 x u64]
+    // that both neighbours map; the pack kernel of a neighbour stores straight into it and then raises the flag.
+    bool p2p;
+    unsigned char *ipc_base;
+    size_t ipc_flag_off;
+    void *peer_base[2];               // mapping of the lo / hi neighbour's block (the same pointer when they coincide)
+    d4 *peer_dst[2];                  // lo neighbour's from-hi buffer, hi neighbour's from-lo buffer
+    unsigned long long *peer_flag[2];
+    d4 *p2p_recv[2];                  // my from-hi / from-lo buffers
+    unsigned long long *p2p_flag;     // my flags: [0] raised by the hi neighbour, [1] by the lo neighbour
+    unsigned long long seq;           // halo refreshes so far (identical on all ranks)
+    unsigned int *done_ctr;
 };
 
 extern "C" int sepgpu_dd_unique_id(void *out128)
@@ -102,6 +120,81 @@ static int dmalloc(T **p, size_t count)
 {
     CUDA_TRY(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
     CUDA_TRY(cudaMemset(*p, 0, sizeof(T) * (count ? count : 1)));
+    return 0;
+}
+
+// ---- peer-memory set-up ---------------------------------------------------------------------------------------
+// One cudaMalloc block per rank, its IPC handle all-gathered over the NCCL communicator, the two neighbours'
+// blocks mapped with cudaIpcOpenMemHandle (NVLink peer access).  All ranks agree on the outcome: when any
+// rank cannot export or map a block, every rank keeps the NCCL send/recv path.  SEPGPU_DD_P2P=0 disables it.
+static int p2p_setup(sepgpu_ctx *c)
+{
+    DDState *d = c->dd;
+    d->p2p = false;
+    const char *env = getenv("SEPGPU_DD_P2P");
+    int want = !(env && env[0] == '0');
+    const size_t buf_bytes = d->bufcap * sizeof(d4);
+    d->ipc_flag_off = 2 * buf_bytes;
+    const size_t total = 2 * buf_bytes + 256;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    int ok = want;
+    if (ok) {
+        if (cudaMalloc((void **)&d->ipc_base, total < ((size_t)4 << 20) ? ((size_t)4 << 20) : total) != cudaSuccess) { ok = 0; d->ipc_base = NULL; }
+        else if (cudaMemset(d->ipc_base, 0, total) != cudaSuccess || cudaIpcGetMemHandle(&mine, d->ipc_base) != cudaSuccess) ok = 0;
+        cudaGetLastError();
+    }
+    // all-gather {handle, ok}
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    unsigned char *dev = NULL, *host = (unsigned char *)calloc(d->nranks, rec);
+    CUDA_TRY(cudaMalloc((void **)&dev, rec * d->nranks));
+    memcpy(host + rec * d->rank, &mine, sizeof mine);
+    host[rec * d->rank + sizeof mine] = (unsigned char)ok;
+    CUDA_TRY(cudaMemcpy(dev + rec * d->rank, host + rec * d->rank, rec, cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.AllGather(dev + rec * d->rank, dev, rec, ncclChar, d->comm, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(host, dev, rec * d->nranks, cudaMemcpyDeviceToHost));
+    int all_ok = 1;
+    for (int r = 0; r < d->nranks; r++) all_ok &= host[rec * r + sizeof mine];
+    int mapped = all_ok;
+    if (all_ok) {
+        const int peers[2] = {d->lo_rank, d->hi_rank};
+        for (int k = 0; k < 2 && mapped; k++) {
+            if (k == 1 && peers[1] == peers[0]) { d->peer_base[1] = d->peer_base[0]; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, host + rec * peers[k], sizeof h);
+            if (cudaIpcOpenMemHandle(&d->peer_base[k], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                d->peer_base[k] = NULL;
+                mapped = 0;
+            }
+        }
+    }
+    // second agreement round: did everybody map both neighbours?
+    double *flag = d->comm_buf + 150;
+    double v = mapped ? 0.0 : 1.0;
+    CUDA_TRY(cudaMemcpy(flag, &v, sizeof v, cudaMemcpyHostToDevice));
+    NCCL_TRY(g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclSum, d->comm, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost));
+    cudaFree(dev); free(host);
+    if (v != 0.0) {
+        if (d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[0]);
+        if (d->peer_base[1] && d->peer_base[1] != d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[1]);
+        d->peer_base[0] = d->peer_base[1] = NULL;
+        return 0;                                         // NCCL path on every rank
+    }
+    d->p2p_recv[0] = (d4 *)d->ipc_base;
+    d->p2p_recv[1] = (d4 *)(d->ipc_base + buf_bytes);
+    d->p2p_flag = (unsigned long long *)(d->ipc_base + d->ipc_flag_off);
+    // what I send "down" is the lo neighbour's data "from above" and the other way round
+    d->peer_dst[0] = (d4 *)d->peer_base[0];
+    d->peer_flag[0] = (unsigned long long *)((unsigned char *)d->peer_base[0] + d->ipc_flag_off);
+    d->peer_dst[1] = (d4 *)((unsigned char *)d->peer_base[1] + buf_bytes);
+    d->peer_flag[1] = (unsigned long long *)((unsigned char *)d->peer_base[1] + d->ipc_flag_off) + 1;
+    if (dmalloc(&d->done_ctr, 1)) return SEPGPU_ECUDA;
+    d->seq = 0;
+    d->p2p = true;
     return 0;
 }
 
@@ -144,6 +237,11 @@ extern "C" int sepgpu_dd_init(sepgpu_ctx *c, int rank, int nranks, const void *i
             dmalloc(&d->send_idx[k], d->bufcap)) return SEPGPU_ECUDA;
     if (!c->gid && dmalloc(&c->gid, cap)) return SEPGPU_ECUDA;
     c->dd = d;
+    if ((rc = p2p_setup(c))) { c->dd = NULL; return rc; }
+    CUDA_TRY(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&d->ev_ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&d->ev_halo, cudaEventDisableTiming));
+    c->dd = d;
     c->n_global = n_global;
     return 0;
 }
@@ -171,6 +269,14 @@ void sepgpu_dd_destroy(sepgpu_ctx *c)
 {
     DDState *d = c->dd;
     if (!d) return;
+    if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
+    cudaStreamSynchronize(c->stream);
+    if (d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[0]);
+    if (d->peer_base[1] && d->peer_base[1] != d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[1]);
+    if (d->ipc_base) cudaFree(d->ipc_base);
+    if (d->done_ctr) cudaFree(d->done_ctr);
+    if (d->ev_ready) cudaEventDestroy(d->ev_ready);
+    if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     if (d->comm) g_nccl.CommDestroy(d->comm);
     void *ptrs[] = {d->comm_buf, d->scan_scratch, d->counts_dev, d->x4b, d->v4b, d->xn4b, d->cr4b, d->crossb, d->gidb,
                     d->send[0], d->send[1], d->recv[0], d->recv[1], d->send_idx[0], d->send_idx[1],
@@ -314,14 +420,16 @@ __global__ void k_dd_totals(const int *p0, const int *p1, const int *p2, int n, 
 
 // exchange with both neighbours: what goes "down" (to lo_rank) arrives as the receiver's data "from above"
 static int exchange(sepgpu_ctx *c, const void *send_lo, size_t n_lo, const void *send_hi, size_t n_hi,
-                    void *recv_from_hi, size_t n_from_hi, void *recv_from_lo, size_t n_from_lo, size_t elem_bytes)
+                    void *recv_from_hi, size_t n_from_hi, void *recv_from_lo, size_t n_from_lo, size_t elem_bytes,
+                    cudaStream_t st = 0)
 {
     DDState *d = c->dd;
+    if (!st) st = c->stream;
     NCCL_TRY(g_nccl.GroupStart());
-    if (n_lo) NCCL_TRY(g_nccl.Send(send_lo, n_lo * elem_bytes, ncclChar, d->lo_rank, d->comm, c->stream));
-    if (n_hi) NCCL_TRY(g_nccl.Send(send_hi, n_hi * elem_bytes, ncclChar, d->hi_rank, d->comm, c->stream));
-    if (n_from_hi) NCCL_TRY(g_nccl.Recv(recv_from_hi, n_from_hi * elem_bytes, ncclChar, d->hi_rank, d->comm, c->stream));
-    if (n_from_lo) NCCL_TRY(g_nccl.Recv(recv_from_lo, n_from_lo * elem_bytes, ncclChar, d->lo_rank, d->comm, c->stream));
+    if (n_lo) NCCL_TRY(g_nccl.Send(send_lo, n_lo * elem_bytes, ncclChar, d->lo_rank, d->comm, st));
+    if (n_hi) NCCL_TRY(g_nccl.Send(send_hi, n_hi * elem_bytes, ncclChar, d->hi_rank, d->comm, st));
+    if (n_from_hi) NCCL_TRY(g_nccl.Recv(recv_from_hi, n_from_hi * elem_bytes, ncclChar, d->hi_rank, d->comm, st));
+    if (n_from_lo) NCCL_TRY(g_nccl.Recv(recv_from_lo, n_from_lo * elem_bytes, ncclChar, d->lo_rank, d->comm, st));
     NCCL_TRY(g_nccl.GroupEnd());
     return 0;
 }
@@ -340,6 +448,7 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
     int n_own = c->n_own;
     int G = (n_own + B - 1) / B;
     int rc;
+    ktimer_begin(c, &c->t_migr);
     // 1. who stays, who leaves
     if (G) k_dd_classify<<<G, B, 0, c->stream>>>(c->x4, n_own, lsz, d->nzg, d->z0, d->z1, d->flag[0], d->flag[1], d->flag[2], c->scal);
     for (int k = 0; k < 3; k++)
@@ -392,6 +501,7 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
                        d->recv[0], (size_t)d->n_recv[0] * 2, d->recv[1], (size_t)d->n_recv[1] * 2, sizeof(d4)))) return rc;
     if (d->n_recv[0]) k_dd_unpack_halo<<<(d->n_recv[0] + B - 1) / B, B, 0, c->stream>>>(d->recv[0], d->n_recv[0], n_own, c->x4, c->v4, c->cr4, c->gid);
     if (d->n_recv[1]) k_dd_unpack_halo<<<(d->n_recv[1] + B - 1) / B, B, 0, c->stream>>>(d->recv[1], d->n_recv[1], n_own + d->n_recv[0], c->x4, c->v4, c->cr4, c->gid);
+    ktimer_end(c, &c->t_migr);
     KERNEL_CHECK();
     c->n_own = n_own;
     c->n = n_own + n_halo;
@@ -449,23 +559,134 @@ __global__ void k_dd_unpack_xu2(const d4 *__restrict__ in0, int n0, const d4 *__
     xs[rank[first_local + k]] = k < n0 ? in0[k] : in1[k - n0];
 }
 
-int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys)
+// ---- peer-memory variant: the pack kernel stores into the neighbours' buffers over NVLink ---------------------
+__global__ void k_dd_push_xu2(const d4 *__restrict__ x4, const i4 *__restrict__ cr4, const int *__restrict__ idx0, int n0,
+                              const int *__restrict__ idx1, int n1, double Lx, double Ly, double Lz,
+                              d4 *out0, d4 *out1, unsigned long long *flag0, unsigned long long *flag1,
+                              unsigned long long seq, unsigned int *done)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n0 + n1) {
+        const bool second = k >= n0;
+        if (second) k -= n0;
+        const int i = second ? idx1[k] : idx0[k];
+        d4 x = x4[i];
+        const int w = cr4[i].w;
+        if (w != 0) {
+            x.x += ((w & 1023) - 512) * Lx; x.y += (((w >> 10) & 1023) - 512) * Ly; x.z += (((w >> 20) & 1023) - 512) * Lz;
+        }
+        (second ? out1 : out0)[k] = x;
+    }
+    // every block publishes its stores system-wide, the last one to finish raises both flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(done, 1u);
+        if (t == gridDim.x - 1) {
+            *done = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag0), "l"(seq) : "memory");
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag1), "l"(seq) : "memory");
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// waits until both neighbours have delivered refresh number `seq`, then scatters into the halo slots of xs.
+// The spin is bounded (~2 s): a neighbour that never arrives sets the sticky device error instead of hanging.
+__global__ void k_dd_wait_unpack_xu2(const d4 *in0, int n0, const d4 *in1, int n1, int first_local,
+                                     const int *__restrict__ rank, d4 *__restrict__ xs,
+                                     const unsigned long long *flags, unsigned long long seq, DevScalars *scal)
+{
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags) < seq || ld_acquire_sys(flags + 1) < seq) {
+            if (clock64() - t0 > 4000000000LL) { scal->error = SEPGPU_ENCCL; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n0 + n1) return;
+    const double2 *src = reinterpret_cast<const double2 *>(k < n0 ? in0 + k : in1 + (k - n0));
+    const double2 a = __ldcg(src), b = __ldcg(src + 1);         // written by another GPU: never through L1
+    d4 v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
+    xs[rank[first_local + k]] = v;
+}
+
+// The refresh as two halves, so that a caller can put work that needs no halo between them:
+//   begin : second stream waits for everything already queued on the main stream (the integrator that moved
+//           the atoms), then packs, exchanges with both neighbours and scatters into the halo slots of xs;
+//   end   : the main stream waits for that.
+// Returns 1 from begin when a transfer was started, 0 when the halo was current already.
+int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys)
 {
     DDState *d = c->dd;
-    if (d->halo_current) return 0;
+    if (d->halo_current || d->halo_inflight) return 0;
     const int B = 256;
+    if (d->p2p) {
+        // same stream, no hand-shake: remote stores and the flag travel while the caller's next kernels run
+        d->seq++;
+        const int nsend = d->n_send[0] + d->n_send[1];
+        k_dd_push_xu2<<<nsend ? (nsend + B - 1) / B : 1, B, 0, c->stream>>>(c->x4, c->cr4, d->send_idx[0], d->n_send[0],
+            d->send_idx[1], d->n_send[1], sys->length[0], sys->length[1], sys->length[2], d->peer_dst[0], d->peer_dst[1],
+            d->peer_flag[0], d->peer_flag[1], d->seq, d->done_ctr);
+        KERNEL_CHECK();
+        d->halo_inflight = true;
+        return 1;
+    }
+    cudaStream_t st = d->stream2;
+    if (cudaEventRecord(d->ev_ready, c->stream) != cudaSuccess || cudaStreamWaitEvent(st, d->ev_ready, 0) != cudaSuccess) {
+        sepgpu_set_error("halo refresh: stream hand-over failed");
+        return SEPGPU_ECUDA;
+    }
     if (d->n_send[0] + d->n_send[1])
-        k_dd_pack_xu2<<<(d->n_send[0] + d->n_send[1] + B - 1) / B, B, 0, c->stream>>>(c->x4, c->cr4, d->send_idx[0], d->n_send[0],
+        k_dd_pack_xu2<<<(d->n_send[0] + d->n_send[1] + B - 1) / B, B, 0, st>>>(c->x4, c->cr4, d->send_idx[0], d->n_send[0],
             d->send_idx[1], d->n_send[1], sys->length[0], sys->length[1], sys->length[2], d->send[0], d->send[1]);
     int rc = exchange(c, d->send[0], (size_t)d->n_send[0], d->send[1], (size_t)d->n_send[1],
-                      d->recv[0], (size_t)d->n_recv[0], d->recv[1], (size_t)d->n_recv[1], sizeof(d4));
+                      d->recv[0], (size_t)d->n_recv[0], d->recv[1], (size_t)d->n_recv[1], sizeof(d4), st);
     if (rc) return rc;
     if (d->n_recv[0] + d->n_recv[1])
-        k_dd_unpack_xu2<<<(d->n_recv[0] + d->n_recv[1] + B - 1) / B, B, 0, c->stream>>>(d->recv[0], d->n_recv[0], d->recv[1], d->n_recv[1],
-                                                                                      c->n_own, c->rank, c->xs);
+        k_dd_unpack_xu2<<<(d->n_recv[0] + d->n_recv[1] + B - 1) / B, B, 0, st>>>(d->recv[0], d->n_recv[0], d->recv[1], d->n_recv[1],
+                                                                               c->n_own, c->rank, c->xs);
     KERNEL_CHECK();
+    CUDA_TRY(cudaEventRecord(d->ev_halo, st));
+    d->halo_inflight = true;
+    return 1;
+}
+
+int sepgpu_dd_halo_end(sepgpu_ctx *c)
+{
+    DDState *d = c->dd;
+    if (!d->halo_inflight) return 0;
+    if (d->p2p) {
+        const int B = 256;
+        const int nrecv = d->n_recv[0] + d->n_recv[1];
+        k_dd_wait_unpack_xu2<<<nrecv ? (nrecv + B - 1) / B : 1, B, 0, c->stream>>>(d->p2p_recv[0], d->n_recv[0], d->p2p_recv[1],
+            d->n_recv[1], c->n_own, c->rank, c->xs, d->p2p_flag, d->seq, c->scal);
+        KERNEL_CHECK();
+    } else {
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, d->ev_halo, 0));
+    }
+    d->halo_inflight = false;
     d->halo_current = true;
     return 0;
+}
+
+int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys)
+{
+    ktimer_begin(c, &c->t_halo);
+    int rc = sepgpu_dd_halo_begin(c, sys);
+    if (rc < 0) return rc;
+    rc = sepgpu_dd_halo_end(c);
+    ktimer_end(c, &c->t_halo);
+    return rc;
 }
 
 void sepgpu_dd_positions_moved(sepgpu_ctx *c) { if (c->dd) c->dd->halo_current = false; }

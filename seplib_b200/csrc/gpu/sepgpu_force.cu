@@ -209,7 +209,8 @@ template <int TPA, bool TYPED, bool STORE, bool FIJ>
 __global__ void __launch_bounds__(FORCE_BLOCK, LJ_MIN_CTAS)
 k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int atoms_per_cta,
-          LJDev P, BoxDev B, double *__restrict__ partial, double *fij, int nmol)
+          LJDev P, BoxDev B, double *__restrict__ partial, double *fij, int nmol,
+          const unsigned char *__restrict__ cls, int want)
 {
     __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
     const int sub = threadIdx.x % TPA;
@@ -225,7 +226,9 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
 
     for (int s0 = first; s0 < last; s0 += GROUPS) {
         const int s = s0 + threadIdx.x / TPA;
-        const bool valid = s < last;
+        // cls != NULL: decomposed run split into an interior pass (want 0, needs no halo) and a pass over the
+        // atoms next to a halo layer (want 1); halo atoms themselves own no rows
+        const bool valid = s < last && (cls == nullptr || cls[s] == want);
         A.fx = A.fy = A.fz = 0.0;
         if (valid) {
             const d4 pi = xs[s];
@@ -430,6 +433,8 @@ k_finalize_force(const double *__restrict__ partial, int nrows, DevScalars *scal
 }
 
 int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
+int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys);
+int sepgpu_dd_halo_end(sepgpu_ctx *c);
 
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
 {
@@ -462,9 +467,10 @@ static LJDev make_lj(const sepgpu_ljparam *p, const char types[2])
 }
 
 template <int TPA, bool FIJ>
-static void launch_lj_list_f(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
+static void launch_lj_list_f(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
+                             double *part, const unsigned char *cls, int want)
 {
-#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial, c->fij, c->nmol
+#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, part, c->fij, c->nmol, cls, want
     if (typed) {
         if (store) k_lj_list<TPA, true, true, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
         else       k_lj_list<TPA, true, false, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
@@ -476,10 +482,22 @@ static void launch_lj_list_f(sepgpu_ctx *c, int grid, int apc, bool typed, bool 
 }
 
 template <int TPA>
-static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B)
+static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
+                           double *part, const unsigned char *cls, int want)
 {
-    if (c->fij) launch_lj_list_f<TPA, true>(c, grid, apc, typed, store, P, B);
-    else launch_lj_list_f<TPA, false>(c, grid, apc, typed, store, P, B);
+    if (c->fij) launch_lj_list_f<TPA, true>(c, grid, apc, typed, store, P, B, part, cls, want);
+    else launch_lj_list_f<TPA, false>(c, grid, apc, typed, store, P, B, part, cls, want);
+}
+
+static void launch_lj_list_tpa(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
+                               double *part, const unsigned char *cls, int want)
+{
+    switch (c->tpa) {
+    case 1: launch_lj_list<1>(c, grid, apc, typed, store, P, B, part, cls, want); break;
+    case 2: launch_lj_list<2>(c, grid, apc, typed, store, P, B, part, cls, want); break;
+    case 4: launch_lj_list<4>(c, grid, apc, typed, store, P, B, part, cls, want); break;
+    default: launch_lj_list<8>(c, grid, apc, typed, store, P, B, part, cls, want); break;
+    }
 }
 
 extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2],
@@ -510,7 +528,6 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     if (!c->list_valid) {
         if ((rc = sepgpu_neighb_build(c, sys, opt))) return rc;
     }
-    if (c->dd && (rc = sepgpu_dd_halo_update(c, sys))) return rc;      // neighbours' boundary atoms moved too
     // the type test is compiled out when every atom carries the one requested type
     const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
     const int tpa = c->tpa;
@@ -521,15 +538,33 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     apc = ((apc + groups - 1) / groups) * groups;
     if (apc < groups) apc = groups;
     grid = (c->n + apc - 1) / apc;
-    ktimer_begin(c, &c->t_force);
-    switch (tpa) {
-    case 1: launch_lj_list<1>(c, grid, apc, typed, store, P, B); break;
-    case 2: launch_lj_list<2>(c, grid, apc, typed, store, P, B); break;
-    case 4: launch_lj_list<4>(c, grid, apc, typed, store, P, B); break;
-    default: launch_lj_list<8>(c, grid, apc, typed, store, P, B); break;
+    int nrows = grid;
+    if (c->dd) {
+        // neighbours' boundary atoms moved too: refresh the halo coordinates.  Option "overlap": the transfer
+        // proceeds while this stream computes every atom whose neighbourhood is all local (about 1 - 2/layers of
+        // them); the atoms next to a halo layer follow once the halo has arrived.  Off by default -- on B200 with
+        // the peer-memory push the refresh costs 20 us, less than the extra, mostly empty, boundary wave.
+        const int started = c->overlap && c->cls ? sepgpu_dd_halo_begin(c, sys) : 0;
+        if (started < 0) return started;
+        if (started) {
+            ktimer_begin(c, &c->t_force);
+            launch_lj_list_tpa(c, grid, apc, typed, store, P, B, c->partial, c->cls, 0);
+            if ((rc = sepgpu_dd_halo_end(c))) return rc;
+            launch_lj_list_tpa(c, grid, apc, typed, store, P, B, c->partial + (size_t)grid * SEPGPU_NPART_F, c->cls, 1);
+            ktimer_end(c, &c->t_force);
+            nrows = 2 * grid;
+        } else {
+            if ((rc = sepgpu_dd_halo_update(c, sys))) return rc;
+            ktimer_begin(c, &c->t_force);
+            launch_lj_list_tpa(c, grid, apc, typed, store, P, B, c->partial, NULL, 0);
+            ktimer_end(c, &c->t_force);
+        }
+    } else {
+        ktimer_begin(c, &c->t_force);
+        launch_lj_list_tpa(c, grid, apc, typed, store, P, B, c->partial, NULL, 0);
+        ktimer_end(c, &c->t_force);
     }
-    ktimer_end(c, &c->t_force);
     KERNEL_CHECK();
     c->f_zero = false;
-    return sepgpu_finalize_force(c, grid, 0.5, epot_assign ? 1 : 0);
+    return sepgpu_finalize_force(c, nrows, 0.5, epot_assign ? 1 : 0);
 }

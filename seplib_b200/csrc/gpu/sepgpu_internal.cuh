@@ -98,6 +98,7 @@ struct sepgpu_ctx {
     float4 *xf;            // cell-relative FP32 copy for the list prefilter (w = raw cell index)
     int *order, *rank;
     int *cell_of;          // [n] cell index of atom i
+    unsigned char *cls;    // [n] decomposed runs: class of SORTED atom s: 0 interior, 1 next to a halo layer, 2 halo
     int *cell_cnt, *cell_start;   // [ncell_cap+1]
     int *tmp_slot;         // [n]
     int ncell_cap;
@@ -149,10 +150,12 @@ struct sepgpu_ctx {
     int unroll;                  // gathers in flight per lane in the list force kernel (2 or 4)
     int force_grid;              // CTAs of the list force kernel (0 = default)
     int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
+    int overlap;                 // decomposed runs: halo refresh beside an interior-only force pass (default 0: measured slower,
+                                 // the boundary pass is a nearly empty wave that costs more than the 20 us refresh)
 
     // measurement
     cudaEvent_t ev0, ev1;
-    KernelTimer t_force, t_build, t_intgr, t_coul, t_bonded;
+    KernelTimer t_force, t_build, t_intgr, t_coul, t_bonded, t_halo, t_migr;
     void *flush_buf; size_t flush_bytes;
 };
 

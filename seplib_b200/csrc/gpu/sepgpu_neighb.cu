@@ -173,7 +173,8 @@ __global__ void k_cell_scatter(const int *__restrict__ cell_of, int n, const int
 __global__ void k_cell_finalize(const int *__restrict__ tmp_slot, const int *__restrict__ cell_of,
                                 const int *__restrict__ cell_start, const d4 *__restrict__ x4,
                                 int n, int *__restrict__ order, int *__restrict__ rank,
-                                d4 *__restrict__ xs, float4 *__restrict__ xf, i4 *__restrict__ cr4)
+                                d4 *__restrict__ xs, float4 *__restrict__ xf, i4 *__restrict__ cr4,
+                                unsigned char *__restrict__ cls, CellGrid G)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -189,6 +190,11 @@ __global__ void k_cell_finalize(const int *__restrict__ tmp_slot, const int *__r
     xs[s] = p;
     xf[s] = make_float4((float)p.x, (float)p.y, (float)p.z, __int_as_float(tag_mol(p.w)));
     cr4[i].w = 0;          // crossings since list build
+    if (cls) {             // slab decomposition: does this atom's neighbourhood reach into a halo layer?
+        int cx, cy, cz;
+        key_cell(c, G, cx, cy, cz);
+        cls[s] = (cz == 0 || cz == G.nz - 1) ? 2 : ((cz == 1 || cz == G.nz - 2) ? 1 : 0);
+    }
 }
 
 // ---- exclusion predicates (source/sepprfrc.c:703-740), original atom indices ----------------------------
@@ -549,8 +555,9 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
                                               G, c->cell_of, c->cell_cnt, c->scal);
         if (sepgpu_exclusive_scan(c->stream, c->cell_cnt, c->cell_start, block_sum, nkey)) return SEPGPU_ECUDA;
         k_cell_scatter<<<Gn, B, 0, c->stream>>>(c->cell_of, c->n, c->cell_start, c->cell_cnt, c->tmp_slot);
+        if (c->dd && !c->cls) CUDA_TRY(cudaMalloc((void **)&c->cls, (size_t)c->ncap));
         k_cell_finalize<<<Gn, B, 0, c->stream>>>(c->tmp_slot, c->cell_of, c->cell_start, c->x4, c->n,
-                                                 c->order, c->rank, c->xs, c->xf, c->cr4);
+                                                 c->order, c->rank, c->xs, c->xf, c->cr4, c->dd ? c->cls : NULL, G);
         BuildParams P;
         P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
         const double cut = sys->cf + sys->skin;

@@ -81,6 +81,7 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->tpa = 1;
     c->prefilter = 1;
     c->unroll = 2;
+    c->overlap = 0;
     c->single_type = 'A';
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
@@ -118,6 +119,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     sepgpu_dd_destroy(c);
     if (c->gid) cudaFree(c->gid);
     if (c->fij) cudaFree(c->fij);
+    if (c->cls) cudaFree(c->cls);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
                     c->rank, c->cell_of, c->cell_cnt, c->cell_start, c->tmp_slot, c->nbr, c->cnt,
@@ -130,7 +132,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->stage) cudaFreeHost(c->stage);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
-    ktimer_free(&c->t_force); ktimer_free(&c->t_build); ktimer_free(&c->t_intgr); ktimer_free(&c->t_coul); ktimer_free(&c->t_bonded);
+    ktimer_free(&c->t_force); ktimer_free(&c->t_build); ktimer_free(&c->t_intgr); ktimer_free(&c->t_coul); ktimer_free(&c->t_bonded); ktimer_free(&c->t_halo); ktimer_free(&c->t_migr);
     cudaStreamDestroy(c->stream);
     free(c);
 }
@@ -665,11 +667,13 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
         return 0;
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
+    if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
     if (!strcmp(name, "unroll")) { c->unroll = value == 4 ? 4 : 2; return 0; }
     if (!strcmp(name, "force_grid")) { c->force_grid = value > 0 && value <= SEPGPU_MAX_BLOCKS_PARTIAL ? (int)value : 0; return 0; }
     if (!strcmp(name, "time_kernels")) {
         if (value) { if (ktimer_enable(&c->t_force) || ktimer_enable(&c->t_build) || ktimer_enable(&c->t_intgr) ||
-                         ktimer_enable(&c->t_coul) || ktimer_enable(&c->t_bonded)) return SEPGPU_ECUDA; }
+                         ktimer_enable(&c->t_coul) || ktimer_enable(&c->t_bonded) || ktimer_enable(&c->t_halo) ||
+                         ktimer_enable(&c->t_migr)) return SEPGPU_ECUDA; }
         return 0;
     }
     if (!strcmp(name, "neighb_cap")) {
@@ -687,7 +691,8 @@ extern "C" int sepgpu_kernel_time(sepgpu_ctx *c, const char *which, float *ms_to
     if (!c || !which) return SEPGPU_EINVAL;
     KernelTimer *t = !strcmp(which, "force") ? &c->t_force : !strcmp(which, "build") ? &c->t_build
                    : !strcmp(which, "intgr") ? &c->t_intgr : !strcmp(which, "coulomb") ? &c->t_coul
-                   : !strcmp(which, "bonded") ? &c->t_bonded : NULL;
+                   : !strcmp(which, "bonded") ? &c->t_bonded : !strcmp(which, "halo") ? &c->t_halo
+                   : !strcmp(which, "migrate") ? &c->t_migr : NULL;
     if (!t || !t->enabled) return SEPGPU_EINVAL;
     CUDA_TRY(cudaSetDevice(c->device));
     ktimer_drain(t);
