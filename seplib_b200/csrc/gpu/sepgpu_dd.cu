@@ -100,8 +100,14 @@ struct DDState {
     unsigned long long *peer_flag[2];
     d4 *p2p_recv[2];                  // my from-hi / from-lo buffers
     unsigned long long *p2p_flag;     // my flags: [0] raised by the hi neighbour, [1] by the lo neighbour
+    size_t peer_cap[2];               // atoms the lo / hi neighbour's buffers hold
     unsigned long long seq;           // halo refreshes so far (identical on all ranks)
     unsigned int *done_ctr;
+    // all ranks' blocks (for the all-gather of the integrator sums)
+    void *peer_all[64];
+    unsigned char **bases_dev;
+    size_t gather_off, gflag_off;
+    unsigned long long gseq;
 };
 
 extern "C" int sepgpu_dd_unique_id(void *out128)
@@ -133,9 +139,14 @@ static int p2p_setup(sepgpu_ctx *c)
     d->p2p = false;
     const char *env = getenv("SEPGPU_DD_P2P");
     int want = !(env && env[0] == '0');
+    // block layout: a fixed-size header (flags, gather table) followed by the two receive buffers.  Ranks own
+    // different numbers of layers, so the buffer size is per rank and travels with the handle.
     const size_t buf_bytes = d->bufcap * sizeof(d4);
-    d->ipc_flag_off = 2 * buf_bytes;
-    const size_t total = 2 * buf_bytes + 256;
+    d->ipc_flag_off = 0;
+    d->gather_off = 256;
+    d->gflag_off = d->gather_off + sizeof(double) * 2 * 64 * SEPGPU_GATHER_W;
+    const size_t hdr = 32768;
+    const size_t total = hdr + 2 * buf_bytes;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
     int ok = want;
@@ -145,11 +156,12 @@ static int p2p_setup(sepgpu_ctx *c)
         cudaGetLastError();
     }
     // all-gather {handle, ok}
-    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 16;
     unsigned char *dev = NULL, *host = (unsigned char *)calloc(d->nranks, rec);
     CUDA_TRY(cudaMalloc((void **)&dev, rec * d->nranks));
     memcpy(host + rec * d->rank, &mine, sizeof mine);
     host[rec * d->rank + sizeof mine] = (unsigned char)ok;
+    { unsigned long long bb = buf_bytes; memcpy(host + rec * d->rank + sizeof mine + 8, &bb, 8); }
     CUDA_TRY(cudaMemcpy(dev + rec * d->rank, host + rec * d->rank, rec, cudaMemcpyHostToDevice));
     NCCL_TRY(g_nccl.AllGather(dev + rec * d->rank, dev, rec, ncclChar, d->comm, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -158,17 +170,18 @@ static int p2p_setup(sepgpu_ctx *c)
     for (int r = 0; r < d->nranks; r++) all_ok &= host[rec * r + sizeof mine];
     int mapped = all_ok;
     if (all_ok) {
-        const int peers[2] = {d->lo_rank, d->hi_rank};
-        for (int k = 0; k < 2 && mapped; k++) {
-            if (k == 1 && peers[1] == peers[0]) { d->peer_base[1] = d->peer_base[0]; continue; }
+        for (int r = 0; r < d->nranks && mapped; r++) {
+            if (r == d->rank) { d->peer_all[r] = d->ipc_base; continue; }
             cudaIpcMemHandle_t h;
-            memcpy(&h, host + rec * peers[k], sizeof h);
-            if (cudaIpcOpenMemHandle(&d->peer_base[k], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            memcpy(&h, host + rec * r, sizeof h);
+            if (cudaIpcOpenMemHandle(&d->peer_all[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
-                d->peer_base[k] = NULL;
+                d->peer_all[r] = NULL;
                 mapped = 0;
             }
         }
+        d->peer_base[0] = d->peer_all[d->lo_rank];
+        d->peer_base[1] = d->peer_all[d->hi_rank];
     }
     // second agreement round: did everybody map both neighbours?
     double *flag = d->comm_buf + 150;
@@ -177,21 +190,31 @@ static int p2p_setup(sepgpu_ctx *c)
     NCCL_TRY(g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclSum, d->comm, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost));
-    cudaFree(dev); free(host);
+    cudaFree(dev);
     if (v != 0.0) {
-        if (d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[0]);
-        if (d->peer_base[1] && d->peer_base[1] != d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[1]);
+        free(host);
+        for (int r = 0; r < d->nranks; r++)
+            if (r != d->rank && d->peer_all[r]) { cudaIpcCloseMemHandle(d->peer_all[r]); d->peer_all[r] = NULL; }
         d->peer_base[0] = d->peer_base[1] = NULL;
         return 0;                                         // NCCL path on every rank
     }
-    d->p2p_recv[0] = (d4 *)d->ipc_base;
-    d->p2p_recv[1] = (d4 *)(d->ipc_base + buf_bytes);
+    if (dmalloc(&d->bases_dev, (size_t)d->nranks)) return SEPGPU_ECUDA;
+    CUDA_TRY(cudaMemcpy(d->bases_dev, d->peer_all, sizeof(void *) * d->nranks, cudaMemcpyHostToDevice));
+    d->gseq = 0;
+    unsigned long long peer_bytes[2];
+    memcpy(&peer_bytes[0], host + rec * d->lo_rank + sizeof mine + 8, 8);
+    memcpy(&peer_bytes[1], host + rec * d->hi_rank + sizeof mine + 8, 8);
+    d->p2p_recv[0] = (d4 *)(d->ipc_base + hdr);
+    d->p2p_recv[1] = (d4 *)(d->ipc_base + hdr + buf_bytes);
     d->p2p_flag = (unsigned long long *)(d->ipc_base + d->ipc_flag_off);
     // what I send "down" is the lo neighbour's data "from above" and the other way round
-    d->peer_dst[0] = (d4 *)d->peer_base[0];
+    d->peer_dst[0] = (d4 *)((unsigned char *)d->peer_base[0] + hdr);
     d->peer_flag[0] = (unsigned long long *)((unsigned char *)d->peer_base[0] + d->ipc_flag_off);
-    d->peer_dst[1] = (d4 *)((unsigned char *)d->peer_base[1] + buf_bytes);
+    d->peer_dst[1] = (d4 *)((unsigned char *)d->peer_base[1] + hdr + peer_bytes[1]);
     d->peer_flag[1] = (unsigned long long *)((unsigned char *)d->peer_base[1] + d->ipc_flag_off) + 1;
+    d->peer_cap[0] = peer_bytes[0] / sizeof(d4);
+    d->peer_cap[1] = peer_bytes[1] / sizeof(d4);
+    free(host);
     if (dmalloc(&d->done_ctr, 1)) return SEPGPU_ECUDA;
     d->seq = 0;
     d->p2p = true;
@@ -271,8 +294,9 @@ void sepgpu_dd_destroy(sepgpu_ctx *c)
     if (!d) return;
     if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
     cudaStreamSynchronize(c->stream);
-    if (d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[0]);
-    if (d->peer_base[1] && d->peer_base[1] != d->peer_base[0]) cudaIpcCloseMemHandle(d->peer_base[1]);
+    for (int r = 0; r < d->nranks; r++)
+        if (r != d->rank && d->peer_all[r]) cudaIpcCloseMemHandle(d->peer_all[r]);
+    if (d->bases_dev) cudaFree(d->bases_dev);
     if (d->ipc_base) cudaFree(d->ipc_base);
     if (d->done_ctr) cudaFree(d->done_ctr);
     if (d->ev_ready) cudaEventDestroy(d->ev_ready);
@@ -289,6 +313,17 @@ void sepgpu_dd_destroy(sepgpu_ctx *c)
 }
 
 double *sepgpu_dd_comm(sepgpu_ctx *c) { return c->dd->comm_buf; }
+
+// peer-memory all-gather available?  Fills the kernel argument and advances the sequence number.
+bool sepgpu_dd_gather_next(sepgpu_ctx *c, GatherDev *g)
+{
+    DDState *d = c->dd;
+    if (!d->p2p) return false;
+    d->gseq++;
+    g->bases = d->bases_dev; g->gather_off = d->gather_off; g->gflag_off = d->gflag_off;
+    g->seq = d->gseq; g->rank = d->rank; g->nranks = d->nranks;
+    return true;
+}
 void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks) { *rank = c->dd->rank; *nranks = c->dd->nranks; }
 
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax)
@@ -488,6 +523,10 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
     d->n_send[0] = d->counts_host[8]; d->n_send[1] = d->counts_host[9];
     d->n_recv[0] = d->counts_host[10]; d->n_recv[1] = d->counts_host[11];          // from hi, from lo
     const int n_halo = d->n_recv[0] + d->n_recv[1];
+    if (d->p2p && ((size_t)d->n_send[0] > d->peer_cap[0] || (size_t)d->n_send[1] > d->peer_cap[1])) {
+        sepgpu_set_error("decomposed rebuild: halo (%d / %d atoms) exceeds a neighbour's receive buffer", d->n_send[0], d->n_send[1]);
+        return SEPGPU_EINVAL;
+    }
     if ((size_t)d->n_send[0] > d->bufcap || (size_t)d->n_send[1] > d->bufcap || (size_t)d->n_recv[0] > d->bufcap ||
         (size_t)d->n_recv[1] > d->bufcap || n_own + n_halo > c->ncap) {
         sepgpu_set_error("decomposed rebuild: halo exceeds the buffers (own %d, halo %d, cap %d, buf %zu)", n_own, n_halo, c->ncap, d->bufcap);
@@ -599,7 +638,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 // waits until both neighbours have delivered refresh number `seq`, then scatters into the halo slots of xs.
-// The spin is bounded (~2 s): a neighbour that never arrives sets the sticky device error instead of hanging.
+// The spin is bounded (~0.5 s): a neighbour that never arrives sets the sticky device error instead of hanging.
 __global__ void k_dd_wait_unpack_xu2(const d4 *in0, int n0, const d4 *in1, int n1, int first_local,
                                      const int *__restrict__ rank, d4 *__restrict__ xs,
                                      const unsigned long long *flags, unsigned long long seq, DevScalars *scal)
@@ -607,7 +646,7 @@ __global__ void k_dd_wait_unpack_xu2(const d4 *in0, int n0, const d4 *in1, int n
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_acquire_sys(flags) < seq || ld_acquire_sys(flags + 1) < seq) {
-            if (clock64() - t0 > 4000000000LL) { scal->error = SEPGPU_ENCCL; break; }
+            if (clock64() - t0 > 1000000000LL) { scal->error = SEPGPU_ENCCL; break; }
             __nanosleep(100);
         }
     }

@@ -229,6 +229,17 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* NV * 
     }
 }
 
+// decomposed runs, peer-memory all-gather of the integrator's per-rank sums (sepgpu_dd.cu sets it up,
+// k_finalize_intgr_p2p in sepgpu_intgr.cu uses it)
+#define SEPGPU_GATHER_W 16
+struct GatherDev {
+    unsigned char **bases;       // device array [nranks]: every rank's shared block as mapped here (own block included)
+    size_t gather_off;           // double gather[2][nranks][SEPGPU_GATHER_W]
+    size_t gflag_off;            // unsigned long long gflag[2][nranks]
+    unsigned long long seq;
+    int rank, nranks;
+};
+
 // internal cross-file entry points
 int sepgpu_ensure_stage(sepgpu_ctx *c, size_t bytes);
 int sepgpu_apply_pending(sepgpu_ctx *c);          // flush a deferred thermostat update into f4

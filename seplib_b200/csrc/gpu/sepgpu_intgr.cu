@@ -193,6 +193,82 @@ k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal
     }
 }
 
+// Decomposed run with peer memory: ONE kernel reduces this rank's partial rows, stores the 12 sums into every
+// rank's gather table over NVLink (slot = seq & 1, row = my rank), raises the per-sender flag, waits for all
+// senders' flags and then adds the rows in rank order -- every rank computes bit-identical totals and so takes
+// the same rebuild decision.  Replaces finalize(phase A) + NCCL all-reduce + finalize(phase B).
+// Slot reuse is safe: nobody can be two refreshes ahead of a rank whose contribution it still needs.
+__global__ void __launch_bounds__(256)
+k_finalize_intgr_p2p(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int resets, GatherDev G)
+{
+    __shared__ double red[SEPGPU_NPART_I * 8];
+    __shared__ double mine[SEPGPU_NPART_I];
+    if (threadIdx.x == 0) {
+        if (resets & 1) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
+        if (resets & 2) scal->max_dist2 = 0.0;
+    }
+    double v[SEPGPU_NPART_I];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_I; q++) v[q] = 0.0;
+    double mx = 0.0;
+    for (int r = threadIdx.x; r < nrows; r += 256) {
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_I; q++)
+            if (q != 7) v[q] += partial[r * SEPGPU_NPART_I + q];
+        mx = fmax(mx, partial[r * SEPGPU_NPART_I + 7]);
+    }
+    block_sum<SEPGPU_NPART_I, 256>(v, red);
+    __syncthreads();
+    double wm = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 8; w++) mx = fmax(mx, red[w]);
+        for (int q = 0; q < SEPGPU_NPART_I; q++) mine[q] = v[q];
+        mine[7] = mx;
+    }
+    __syncthreads();
+    const int slot = (int)(G.seq & 1);
+    const int t = threadIdx.x;
+    if (t < G.nranks) {                                   // thread t serves peer t
+        unsigned char *base = G.bases[t];
+        double *row = reinterpret_cast<double *>(base + G.gather_off) + ((size_t)slot * G.nranks + G.rank) * SEPGPU_GATHER_W;
+        for (int q = 0; q < SEPGPU_NPART_I; q++) row[q] = mine[q];
+        __threadfence_system();
+        unsigned long long *fl = reinterpret_cast<unsigned long long *>(base + G.gflag_off) + (size_t)slot * G.nranks + G.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(G.seq) : "memory");
+        // ... and waits for sender t
+        const unsigned long long *my = reinterpret_cast<const unsigned long long *>(G.bases[G.rank] + G.gflag_off) + (size_t)slot * G.nranks + t;
+        const long long t0 = clock64();
+        unsigned long long got;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(my) : "memory");
+            if (got >= G.seq) break;
+            if (clock64() - t0 > 1000000000LL) { scal->error = SEPGPU_ENCCL; break; }
+        } while (true);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double *tab = reinterpret_cast<const double *>(G.bases[G.rank] + G.gather_off) + (size_t)slot * G.nranks * SEPGPU_GATHER_W;
+        double s[SEPGPU_NPART_I];
+        for (int q = 0; q < SEPGPU_NPART_I; q++) s[q] = 0.0;
+        double gmx = 0.0;
+        for (int r = 0; r < G.nranks; r++) {
+            for (int q = 0; q < SEPGPU_NPART_I; q++) {
+                const double x = __ldcg(tab + (size_t)r * SEPGPU_GATHER_W + q);
+                if (q == 7) gmx = fmax(gmx, x); else s[q] += x;
+            }
+        }
+        scal->ekin += 0.5 * s[0];
+        const double K[9] = {s[1], s[2], s[3], s[2], s[4], s[5], s[3], s[5], s[6]};
+        for (int k = 0; k < 9; k++) scal->kin_P[k] += K[k];
+        if (gmx > scal->max_dist2) scal->max_dist2 = gmx;
+        scal->sum_mv2 = s[8];
+        scal->mom[0] = s[9]; scal->mom[1] = s[10]; scal->mom[2] = s[11];
+        scal->neighb_flag = sqrt(scal->max_dist2) > skin * 0.5 ? 1 : 0;
+    }
+}
+
 // xn <- x, cross_neighb <- 0 (source/sepintgr.c:76-82)
 __global__ void k_set_xn(const d4 *__restrict__ x4, d4 *__restrict__ xn4, i4 *__restrict__ cr4, int n)
 {
@@ -210,6 +286,7 @@ double *sepgpu_dd_comm(sepgpu_ctx *c);
 void sepgpu_dd_positions_moved(sepgpu_ctx *c);
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax);
 void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks);
+bool sepgpu_dd_gather_next(sepgpu_ctx *c, GatherDev *g);
 
 __global__ void k_partial2_to_comm(const double *__restrict__ partial, int nrows, double *comm)
 {
@@ -243,7 +320,10 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
             c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial);
     const int resets = (c->ret_reset_pending ? 1 : 0) | (c->maxd_reset_pending ? 2 : 0);
     c->ret_reset_pending = false; c->maxd_reset_pending = false;
-    if (c->dd) {
+    GatherDev gd;
+    if (c->dd && sepgpu_dd_gather_next(c, &gd)) {
+        k_finalize_intgr_p2p<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, resets, gd);
+    } else if (c->dd) {
         double *comm = sepgpu_dd_comm(c);
         int drank = 0, dn = 1;
         sepgpu_dd_rank(c, &drank, &dn);
@@ -266,6 +346,10 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     // the trigger is needed by the host before the next force call: small D2H + stream sync per step
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->dd && c->scal_host->error == SEPGPU_ENCCL) {
+        sepgpu_set_error("decomposed step: a neighbour's data never arrived (peer-memory wait timed out)");
+        return SEPGPU_ENCCL;
+    }
     if (c->scal_host->neighb_flag) {
         k_set_xn<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n_own);
         KERNEL_CHECK();
