@@ -638,7 +638,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 // waits until both neighbours have delivered refresh number `seq`, then scatters into the halo slots of xs.
-// The spin is bounded (~0.5 s): a neighbour that never arrives sets the sticky device error instead of hanging.
+// The spin is bounded (SEPGPU_SPIN_LIMIT): a neighbour that never arrives sets the sticky device error instead of hanging.
 __global__ void k_dd_wait_unpack_xu2(const d4 *in0, int n0, const d4 *in1, int n1, int first_local,
                                      const int *__restrict__ rank, d4 *__restrict__ xs,
                                      const unsigned long long *flags, unsigned long long seq, DevScalars *scal)
@@ -646,7 +646,7 @@ __global__ void k_dd_wait_unpack_xu2(const d4 *in0, int n0, const d4 *in1, int n
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_acquire_sys(flags) < seq || ld_acquire_sys(flags + 1) < seq) {
-            if (clock64() - t0 > 1000000000LL) { scal->error = SEPGPU_ENCCL; break; }
+            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
             __nanosleep(100);
         }
     }

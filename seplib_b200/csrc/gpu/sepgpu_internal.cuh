@@ -232,6 +232,9 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *smem /* NV * 
 // decomposed runs, peer-memory all-gather of the integrator's per-rank sums (sepgpu_dd.cu sets it up,
 // k_finalize_intgr_p2p in sepgpu_intgr.cu uses it)
 #define SEPGPU_GATHER_W 16
+// Bound of the peer-memory spin waits, in SM clocks (~60 s).  A peer may legitimately be late by seconds (host work
+// between steps on one rank); only a dead peer takes longer, and then the sticky device error is set instead of hanging.
+#define SEPGPU_SPIN_LIMIT 120000000000LL
 struct GatherDev {
     unsigned char **bases;       // device array [nranks]: every rank's shared block as mapped here (own block included)
     size_t gather_off;           // double gather[2][nranks][SEPGPU_GATHER_W]

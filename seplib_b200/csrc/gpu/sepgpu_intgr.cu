@@ -244,7 +244,7 @@ k_finalize_intgr_p2p(const double *__restrict__ partial, int nrows, DevScalars *
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(my) : "memory");
             if (got >= G.seq) break;
-            if (clock64() - t0 > 1000000000LL) { scal->error = SEPGPU_ENCCL; break; }
+            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
         } while (true);
     }
     __syncthreads();
