@@ -325,6 +325,13 @@ void sep_save_xyz(seppart *ptr, const char *partnames, const char *file, char *m
 double sep_eval_mom(seppart *ptr, int npart);
 double sep_eval_mom_type(seppart *ptr, char type, int dir, int npart);
 void sep_compress_box(sepatom *ptr, double rhoD, double xi, sepsys *sys);
+void sep_compress_box_dir(sepatom *ptr, double rhoD, double xi, int dir, sepsys *sys);
+void sep_compress_box_dir_length(sepatom *ptr, double length, double xi, int dir, sepsys *sys);
+void sep_berendsen(sepatom *ptr, double Pd, double beta, sepret *ret, sepsys *sys);
+void sep_berendsen_iso(sepatom *ptr, double Pd, double beta, sepret *ret, sepsys *sys);
+void sep_relax_temp(seppart *ptr, char type, double Td, double tau, sepsys *sys);
+double sep_spring_x0(double r2, char opt);
+void sep_force_x0(seppart *ptr, char type, double (*fun)(double, char), sepsys *sys);
 void sep_set_charge(seppart *ptr, char type, double z, sepsys sys);
 void sep_set_mass(seppart *ptr, char type, double m, sepsys sys);
 void sep_set_type(seppart *ptr, char spec, int numb, sepsys *sys);

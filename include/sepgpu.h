@@ -50,6 +50,7 @@ enum {
     SEPGPU_F_ANGLE,          /* angle[SEP_ANGLE] partner table (int)  */
     SEPGPU_F_DIHED,          /* dihed[SEP_DIHED] partner table (int)  */
     SEPGPU_F_GID,            /* global atom id (int), decomposed runs */
+    SEPGPU_F_X0,             /* x0[3]  tether position (sep_set_x0)   */
     SEPGPU_F_COUNT
 };
 
@@ -164,6 +165,17 @@ int sepgpu_scale_positions(sepgpu_ctx *ctx, double xi);
 int sepgpu_fij_enable(sepgpu_ctx *ctx, int nmol);
 int sepgpu_fij_reset(sepgpu_ctx *ctx);
 int sepgpu_fij_get(sepgpu_ctx *ctx, float *out);
+
+/* ---- callers either side of the hot path -------------------------------------- */
+/* x <- x * scale[k]; the box becomes new_length.  Device side of sep_compress_box, sep_compress_box_dir,
+ * sep_compress_box_dir_length (source/sepmisc.c:994-1083) and sep_berendsen, sep_berendsen_iso (:892-944); the
+ * host layer updates sys->length / nsubbox / lsubbox / volume as those routines do. */
+int sepgpu_scale_box(sepgpu_ctx *ctx, const double scale[3], const double new_length[3]);
+/* sep_relax_temp (source/sepmisc.c:357-390): rescale the velocities of one type towards Td, then remove that
+ * type's momentum.  ekin_type (may be NULL) receives the type's kinetic energy before the rescale. */
+int sepgpu_relax_temp(sepgpu_ctx *ctx, const sepgpu_sys *sys, char type, double Td, double tau, double *ekin_type);
+/* sep_force_x0 with sep_spring_x0 (source/sepmisc.c:167-181, 645-670): harmonic tether of one type to SEPGPU_F_X0 */
+int sepgpu_force_x0(sepgpu_ctx *ctx, const sepgpu_sys *sys, char type, double kspring);
 
 /* ---- results -------------------------------------------------------------------------------------- */
 /* stream-synchronising read of the scalar block */

@@ -20,7 +20,7 @@ SEP_LJCF2 = 0.016316891136
 
 # sepgpu field ids (include/sepgpu.h)
 (F_X, F_V, F_F, F_M, F_Z, F_TYPE, F_MOLINDEX, F_XN, F_CROSS_NEIGHB, F_CROSSINGS, F_PV, F_PA, F_A,
- F_BOND, F_ANGLE, F_DIHED, F_GID) = range(17)
+ F_BOND, F_ANGLE, F_DIHED, F_GID, F_X0) = range(18)
 
 d3 = C.c_double * 3
 i3 = C.c_int * 3
@@ -128,7 +128,7 @@ SEPGPU_SYMBOLS = [
     "sepgpu_read_scalars", "sepgpu_sync", "sepgpu_get_pairs", "sepgpu_request_rebuild",
     "sepgpu_set_option", "sepgpu_timer_start", "sepgpu_timer_stop", "sepgpu_kernel_time",
     "sepgpu_peak_fp64", "sepgpu_peak_copy", "sepgpu_flush_l2",
-    "sepgpu_fij_enable", "sepgpu_fij_reset", "sepgpu_fij_get",
+    "sepgpu_fij_enable", "sepgpu_fij_reset", "sepgpu_fij_get", "sepgpu_scale_box", "sepgpu_relax_temp", "sepgpu_force_x0",
     "sepgpu_dd_unique_id", "sepgpu_dd_init", "sepgpu_dd_set_owned", "sepgpu_dd_layers",
 ]
 
@@ -153,6 +153,8 @@ SEP_SYMBOLS = [
     "sep_add_sampler", "sep_add_mol_sampler", "sep_sample", "sep_close_sampler", "sep_gpu_set_sync",
     "sep_gpu_sync", "sep_gpu_invalidate", "sep_gpu_sync_scalars", "sep_gpu_export_neighb",
     "sep_gpu_handle", "sep_gpu_set_dpd_seed",
+    "sep_compress_box_dir", "sep_compress_box_dir_length", "sep_berendsen", "sep_berendsen_iso", "sep_relax_temp",
+    "sep_spring_x0", "sep_force_x0",
 ]
 
 
@@ -192,6 +194,13 @@ def declare_sep_api(lib):
     lib.sep_eval_mom.restype = C.c_double
     lib.sep_eval_mom.argtypes = [P, C.c_int]
     lib.sep_compress_box.argtypes = [P, C.c_double, C.c_double, S]
+    lib.sep_compress_box_dir.argtypes = [P, C.c_double, C.c_double, C.c_int, S]
+    lib.sep_compress_box_dir_length.argtypes = [P, C.c_double, C.c_double, C.c_int, S]
+    lib.sep_berendsen.argtypes = [P, C.c_double, C.c_double, R, S]
+    lib.sep_berendsen_iso.argtypes = [P, C.c_double, C.c_double, R, S]
+    lib.sep_relax_temp.argtypes = [P, C.c_char, C.c_double, C.c_double, S]
+    lib.sep_force_x0.argtypes = [P, C.c_char, C.c_void_p, S]
+    lib.sep_set_x0.argtypes = [P, C.c_int]
     lib.sep_reset_momentum.argtypes = [P, C.c_char, S]
     lib.sep_set_skin.argtypes = [S, C.c_double]
     lib.sep_set_omp.argtypes = [C.c_uint, S]
@@ -252,6 +261,9 @@ def load():
     lib.sepgpu_peak_fp64.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sepgpu_peak_copy.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.sepgpu_flush_l2.argtypes = [ctx]
+    lib.sepgpu_scale_box.argtypes = [ctx, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.sepgpu_relax_temp.argtypes = [ctx, C.POINTER(GpuSys), C.c_char, C.c_double, C.c_double, C.POINTER(C.c_double)]
+    lib.sepgpu_force_x0.argtypes = [ctx, C.POINTER(GpuSys), C.c_char, C.c_double]
     lib.sepgpu_fij_enable.argtypes = [ctx, C.c_int]
     lib.sepgpu_fij_reset.argtypes = [ctx]
     lib.sepgpu_fij_get.argtypes = [ctx, C.c_void_p]

@@ -81,6 +81,7 @@ struct sepgpu_ctx {
     cudaStream_t stream;
 
     d4 *x4, *v4, *f4, *xn4, *pv4, *pa4;
+    d4 *x0;                // tether positions (sep_set_x0), allocated on first upload
     i4 *cr4;
     int *crossings;        // 3n
     double *z;             // charges

@@ -120,6 +120,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->gid) cudaFree(c->gid);
     if (c->fij) cudaFree(c->fij);
     if (c->cls) cudaFree(c->cls);
+    if (c->x0) cudaFree(c->x0);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
                     c->rank, c->cell_of, c->cell_cnt, c->cell_start, c->tmp_slot, c->nbr, c->cnt,
@@ -229,7 +230,7 @@ static FieldInfo field_info(int field)
 {
     switch (field) {
     case SEPGPU_F_X: case SEPGPU_F_V: case SEPGPU_F_F: case SEPGPU_F_XN:
-    case SEPGPU_F_PV: case SEPGPU_F_PA: case SEPGPU_F_A: return {sizeof(double), 3};
+    case SEPGPU_F_PV: case SEPGPU_F_PA: case SEPGPU_F_A: case SEPGPU_F_X0: return {sizeof(double), 3};
     case SEPGPU_F_M: case SEPGPU_F_Z: return {sizeof(double), 1};
     case SEPGPU_F_TYPE: return {1, 1};
     case SEPGPU_F_MOLINDEX: case SEPGPU_F_GID: return {sizeof(int), 1};
@@ -292,6 +293,10 @@ static int put_dispatch(sepgpu_ctx *c, int field, const void *dsrc, const void *
         break;
     case SEPGPU_F_XN:
         k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->xn4, (const double *)dsrc, c->n_own);
+        break;
+    case SEPGPU_F_X0:
+        if (!c->x0 && dalloc(&c->x0, (size_t)c->ncap)) return SEPGPU_ECUDA;
+        k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->x0, (const double *)dsrc, c->n_own);
         break;
     case SEPGPU_F_PV:
         if ((rc = ensure_dpd(c))) return rc;
@@ -414,6 +419,10 @@ static int get_prepare(sepgpu_ctx *c, int field, void *ddst, const void **direct
         else k_accel<<<G, B, 0, c->stream>>>((double *)ddst, c->f4, c->v4, c->n_own);
         break;
     case SEPGPU_F_XN: k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, c->xn4, c->n_own); break;
+    case SEPGPU_F_X0:
+        if (!c->x0) { sepgpu_set_error("sepgpu_get: no tether positions on the device"); return SEPGPU_ESTATE; }
+        k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, c->x0, c->n_own);
+        break;
     case SEPGPU_F_PV: case SEPGPU_F_PA:
         if (!c->have_dpd) { sepgpu_set_error("sepgpu_get: no DPD state"); return SEPGPU_ESTATE; }
         k_d4_to_vec3<<<G, B, 0, c->stream>>>((double *)ddst, field == SEPGPU_F_PV ? c->pv4 : c->pa4, c->n_own);
@@ -431,7 +440,7 @@ static int get_prepare(sepgpu_ctx *c, int field, void *ddst, const void **direct
     default: return SEPGPU_EINVAL;
     }
     KERNEL_CHECK();
-    if (field == SEPGPU_F_Z || field == SEPGPU_F_CROSSINGS || field == SEPGPU_F_GID || field >= SEPGPU_F_BOND) {
+    if (field == SEPGPU_F_Z || field == SEPGPU_F_CROSSINGS || (field >= SEPGPU_F_BOND && field <= SEPGPU_F_GID)) {
         if (!*direct) { sepgpu_set_error("sepgpu_get: field %d not present on device", field); return SEPGPU_ESTATE; }
         CUDA_TRY(cudaMemcpyAsync(ddst, *direct, row * n, cudaMemcpyDeviceToDevice, c->stream));
     }

@@ -6,6 +6,7 @@
  * never compute forces or integrate: that is the device layer's job (include/sepgpu.h).
  */
 #include "sep_host.h"
+#include <float.h>
 
 #include <ctype.h>
 
@@ -183,6 +184,7 @@ sep_binding *sepb_prepare(seppart *atoms, sepsys *sys)
         WANT(SEPB_CN, SEPGPU_F_CROSS_NEIGHB, cross_neighb) WANT(SEPB_CR, SEPGPU_F_CROSSINGS, crossings)
         if (b->uploaded_once) WANT(SEPB_F, SEPGPU_F_F, f)
         if (b->dpd_state_on_device) { WANT(SEPB_PV, SEPGPU_F_PV, pv) WANT(SEPB_PA, SEPGPU_F_PA, pa) }
+        if (b->x0_on_device) WANT(SEPB_X0, SEPGPU_F_X0, x0)
 #undef WANT
         if (nf) sepb_check(sepgpu_put_fields(b->gpu, b->atoms, sizeof(seppart), nf, fields, offs), "upload");
     }
@@ -621,6 +623,7 @@ void sep_set_x0(seppart *ptr, int npart)
     sep_gpu_sync(ptr);
     for (int n = 0; n < npart; n++)
         for (int k = 0; k < 3; k++) ptr[n].x0[k] = ptr[n].x[k];
+    sepb_mark_host_dirty(ptr, SEPB_X0);
 }
 
 void sep_set_xn(seppart *ptr, int npart)
@@ -697,6 +700,27 @@ void sep_reset_momentum(seppart *ptr, const char type, sepsys *sys)
 }
 
 /* source/sepmisc.c:994-1026 */
+/* ---- box-changing callers (reference source/sepmisc.c:892-1083) ------------------------------------------
+ * The host keeps the reference's bookkeeping of sys->length / nsubbox / lsubbox / volume line by line; the
+ * positions are scaled on the device (sepgpu_scale_box), which also re-derives its sorted copy for the new box.
+ * As in the reference the neighbour list is NOT invalidated by a box change. */
+static void scale_box_on_device(sepatom *ptr, sepsys *sys, double sx, double sy, double sz, const char *who)
+{
+    sep_binding *b = sepb_prepare(ptr, sys);
+    const double sc[3] = {sx, sy, sz};
+    sepb_check(sepgpu_scale_box(b->gpu, sc, sys->length), who);
+    b->dev_dirty |= SEPB_X;
+    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_X);
+}
+
+static void resize_subbox(sepsys *sys, int k, double skin, const char *who)
+{
+    sys->nsubbox[k] = sep_nsubbox(sys->cf, skin, sys->length[k]);
+    if (sys->nsubbox[k] < 3)
+        sep_warning("%s: Number of subboxes in x direction are less than three", (char *)who);
+    sys->lsubbox[k] = sys->length[k] / sys->nsubbox[k];
+}
+
 void sep_compress_box(sepatom *ptr, double rhoD, double xi, sepsys *sys)
 {
     const double density = sys->npart / sys->volume;
@@ -707,16 +731,100 @@ void sep_compress_box(sepatom *ptr, double rhoD, double xi, sepsys *sys)
         if (sys->length[k] < sys->cf * 2.0)
             sep_warning("sep_compress_box: Box length too small compared to the maximum cut-off");
     }
-    sep_binding *b = sepb_prepare(ptr, sys);
-    sepb_check(sepgpu_scale_positions(b->gpu, xi), "sep_compress_box");
-    b->dev_dirty |= SEPB_X;
-    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_X);
+    scale_box_on_device(ptr, sys, xi, xi, xi, "sep_compress_box");
     if (sys->neighb_update != 0)
-        for (int k = 0; k < 3; k++) {
-            sys->nsubbox[k] = sep_nsubbox(sys->cf, sys->skin, sys->length[k]);
-            if (sys->nsubbox[k] < 3)
-                sep_warning("sep_compress_box: Number of subboxes in x direction are less than three");
-            sys->lsubbox[k] = sys->length[k] / sys->nsubbox[k];
-        }
+        for (int k = 0; k < 3; k++) resize_subbox(sys, k, sys->skin, "sep_compress_box");      /* :1014-1021, with skin */
     sys->volume = sys->length[0] * sys->length[1] * sys->length[2];
+}
+
+/* one direction; positions move by xi^(1/3) while the length moves by xi (:1037-1038) and the sub-boxes are
+ * resized WITHOUT the skin (:1042) -- both reference quirks kept */
+void sep_compress_box_dir(sepatom *ptr, double rhoD, double xi, int dir, sepsys *sys)
+{
+    if (sys->npart / sys->volume < rhoD) {
+        sys->length[dir] *= xi;
+        if (sys->length[dir] < sys->cf * 2.0)
+            sep_warning("sep_compress_box_dir: Box length too small compared to the maximum cut-off");
+        const double scale = pow(xi, 1.0 / 3.0);
+        scale_box_on_device(ptr, sys, dir == 0 ? scale : 1.0, dir == 1 ? scale : 1.0, dir == 2 ? scale : 1.0, "sep_compress_box_dir");
+        if (sys->neighb_update != 0) resize_subbox(sys, dir, 0.0, "sep_compress_box_dir");
+        sys->volume = sys->length[0] * sys->length[1] * sys->length[2];
+    }
+}
+
+void sep_compress_box_dir_length(sepatom *ptr, double length, double xi, int dir, sepsys *sys)
+{
+    if (sys->length[dir] > length) {
+        sys->length[dir] *= xi;
+        if (sys->length[dir] < sys->cf * 2.0)
+            sep_warning("sep_compress_box_dir_length: Box length too small compared to the maximum cut-off");
+        const double scale = pow(xi, 1.0 / 3.0);
+        scale_box_on_device(ptr, sys, dir == 0 ? scale : 1.0, dir == 1 ? scale : 1.0, dir == 2 ? scale : 1.0, "sep_compress_box_dir_length");
+        if (sys->neighb_update != 0) resize_subbox(sys, dir, 0.0, "sep_compress_box_dir_length");
+        sys->volume = sys->length[0] * sys->length[1] * sys->length[2];
+    }
+}
+
+/* Berendsen barostat along z (:892-914) and isotropic (:918-944) */
+void sep_berendsen(sepatom *ptr, double Pd, double beta, sepret *ret, sepsys *sys)
+{
+    sep_pressure_tensor(ret, sys);
+    const double xi = 1 - beta * sys->dt * (Pd - ret->p);
+    sys->length[2] *= xi;
+    const double scale = pow(xi, 1.0 / 3.0);
+    scale_box_on_device(ptr, sys, 1.0, 1.0, scale, "sep_berendsen");
+    sys->volume = sys->length[0] * sys->length[1] * sys->length[2];
+    if (sys->neighb_update != 0) resize_subbox(sys, 2, 0.0, "sep_berendsen");
+}
+
+void sep_berendsen_iso(sepatom *ptr, double Pd, double beta, sepret *ret, sepsys *sys)
+{
+    sep_pressure_tensor(ret, sys);
+    const double xi = 1 - beta * sys->dt * (Pd - ret->p);
+    for (int k = 0; k < 3; k++) sys->length[k] *= xi;
+    const double scale = pow(xi, 1.0 / 3.0);
+    scale_box_on_device(ptr, sys, scale, scale, scale, "sep_berendsen_iso");
+    sys->volume = sys->length[0] * sys->length[1] * sys->length[2];
+    if (sys->neighb_update != 0)
+        for (int k = 0; k < 3; k++) resize_subbox(sys, k, 0.0, "sep_berendsen_iso");
+}
+
+/* ---- per-type temperature relaxation and tethering springs (:357-390, :167-181, :645-670) ------------------ */
+void sep_relax_temp(seppart *ptr, char type, double Td, double tau, sepsys *sys)
+{
+    sep_binding *b = sepb_prepare(ptr, sys);
+    sepgpu_sys gs;
+    sepb_fill_sys(sys, &gs);
+    double ekin = 0.0;
+    sepb_check(sepgpu_relax_temp(b->gpu, &gs, type, Td, tau, &ekin), "sep_relax_temp");
+    if (ekin < DBL_EPSILON)
+        sep_warning("sep_relax_temp: Zero kinetic energy - check your the types.");
+    b->dev_dirty |= SEPB_V;
+    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_V);
+}
+
+double sep_spring_x0(double r2, char opt)
+{
+    const double k = 500.0;
+    double ret = 0.0;
+    switch (opt) {
+    case 'f': ret = -k; break;
+    case 'u': ret = 0.5 * r2 * k; break;
+    }
+    return ret;
+}
+
+void sep_force_x0(seppart *ptr, char type, double (*fun)(double, char), sepsys *sys)
+{
+    if (fun != sep_spring_x0)
+        sep_error("sep_force_x0: only sep_spring_x0 can run on the device (no CPU path)");
+    sep_binding *b = sepb_find(ptr);
+    if (!b) b = sepb_register(ptr, (size_t)sys->npart);
+    if (!b->x0_on_device) { b->x0_on_device = 1; b->host_dirty |= SEPB_X0; }
+    b = sepb_prepare(ptr, sys);
+    sepgpu_sys gs;
+    sepb_fill_sys(sys, &gs);
+    sepb_check(sepgpu_force_x0(b->gpu, &gs, type, -fun(0.0, 'f')), "sep_force_x0");
+    b->dev_dirty |= SEPB_F | SEPB_A;
+    if (sep_sync_mode() == SEP_SYNC_FULL) sepb_download(b, SEPB_F);
 }

@@ -22,6 +22,7 @@
 #define SEPB_A      (1u << 12)
 #define SEPB_EXCL   (1u << 13)
 #define SEPB_TOPO   (1u << 14)
+#define SEPB_X0     (1u << 15)
 #define SEPB_ALL_STATE (SEPB_X | SEPB_V | SEPB_F | SEPB_M | SEPB_Z | SEPB_TYPE | SEPB_MOL | SEPB_XN | SEPB_CN | SEPB_CR)
 
 typedef struct sep_binding {
@@ -34,6 +35,7 @@ typedef struct sep_binding {
     int uploaded_once;
     int dpd_state_on_device;
     int fij_on;                  /* device molecule-molecule force table enabled */
+    int x0_on_device;            /* tether positions (seppart.x0) are mirrored on the device */
     double *alpha_ptr[4];       /* caller-owned thermostat multipliers mapped to device slots */
     double alpha_seen[4];
     unsigned long long dpd_calls;

@@ -344,3 +344,75 @@ class ApiSystem:
         if not self.closed:
             self.lib.sep_close(self.atoms, self.n)
             self.closed = True
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# drivers of the "next" rows of SURVEY.md section 8f (box-changing callers, per-type relaxation, tether springs).
+# The same code runs against the reference build (to record tests/golden/next_rows.npz) and against libsep.so.
+# ---------------------------------------------------------------------------------------------------------------
+def _final(s, rec):
+    s.lib.sep_eval_mom(s.atoms, s.n)             # a host reader: brings atoms[] up to date in every sync mode
+    rec["x"] = s.view["x"].copy(); rec["v"] = s.view["v"].copy()
+    rec["length"] = np.array(s.sys.length[:]); rec["nsubbox"] = np.array(s.sys.nsubbox[:]); rec["volume"] = s.sys.volume
+    return rec
+
+
+def drive_compress(lib, x, v, L, steps=24, every=3, xi=0.99, rho_target=1.1):
+    """prg3's box compression (reference prgs/prg3.c:76-79) on an LJ fluid in list mode; the cell grid goes from
+    4 to 3 cells per side on the way."""
+    s = ApiSystem(lib, x, L, 2.5, 0.005, v=v, nneighb=3000)
+    alpha = C.c_double(0.1)
+    fun = s.fun("sep_lj_shift")
+    tr = []
+    for n in range(steps):
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"AA", 2.5, fun, s.S, s.R, 1)
+        lib.sep_nosehoover(s.atoms, 1.0, C.byref(alpha), 0.1, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+        if n % every == 0:
+            lib.sep_compress_box(s.atoms, rho_target, xi, s.S)
+        tr.append((s.ret.epot, s.ret.ekin, s.sys.length[0], s.sys.nsubbox[0], s.sys.volume))
+    rec = _final(s, {"traj": np.array(tr)})
+    s.close()
+    return rec
+
+
+def drive_berendsen(lib, x, v, L, steps=30, iso=False, update=capi.SEP_BRUTE):
+    """prg7's loop (reference prgs/prg7.c:37-56): LJ + Nose-Hoover + leapfrog + Berendsen barostat every step."""
+    s = ApiSystem(lib, x, L, 2.5, 0.005, v=v, update=update, nneighb=3000)
+    alpha = C.c_double(0.1)
+    fun = s.fun("sep_lj_shift")
+    tr = []
+    for n in range(steps):
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"AA", 2.5, fun, s.S, s.R, 1)
+        lib.sep_nosehoover(s.atoms, 0.8, C.byref(alpha), 0.1, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+        (lib.sep_berendsen_iso if iso else lib.sep_berendsen)(s.atoms, 5.91, 0.1, s.R, s.S)
+        tr.append((s.ret.epot, s.ret.ekin, s.ret.p, s.sys.length[2], s.sys.volume, s.sys.nsubbox[2]))
+    rec = _final(s, {"traj": np.array(tr)})
+    s.close()
+    return rec
+
+
+def drive_slit(lib, x, v, L, steps=30):
+    """prg8's loop (reference prgs/prg8.c:41-66): fluid 'F' between tethered wall atoms 'W' -- three typed pair
+    calls on one list, sep_force_x0 with sep_spring_x0, leapfrog, sep_relax_temp on the wall."""
+    types = np.where(x[:, 2] < 2.2, ord("W"), ord("F")).astype(np.uint8)
+    s = ApiSystem(lib, x, L, 2.5, 0.005, v=v, types=types, nneighb=3000)
+    lib.sep_set_x0(s.atoms, s.n)
+    lj, wca, spring = s.fun("sep_lj_shift"), s.fun("sep_wca"), s.fun("sep_spring_x0")
+    rc_ww = 2.0 ** (1.0 / 6.0)
+    tr = []
+    for n in range(steps):
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"FF", 2.5, lj, s.S, s.R, 1)
+        lib.sep_force_pairs(s.atoms, b"WF", 2.5, lj, s.S, s.R, 1)
+        lib.sep_force_pairs(s.atoms, b"WW", rc_ww, wca, s.S, s.R, 1)
+        lib.sep_force_x0(s.atoms, b"W", spring, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+        lib.sep_relax_temp(s.atoms, b"W", 1.4, 0.01, s.S)
+        tr.append((s.ret.epot, s.ret.ekin))
+    rec = _final(s, {"traj": np.array(tr), "types": types})
+    s.close()
+    return rec

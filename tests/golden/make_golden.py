@@ -279,11 +279,36 @@ def molpress_fixture(lib):
     np.savez_compressed(os.path.join(HERE, "molpress.npz"), **out)
 
 
+def next_rows_fixture(lib):
+    """Box-changing callers, sep_relax_temp and sep_force_x0, driven by the
+    shared loops in tests/common.py on the reference build."""
+    out = {}
+    x, L = cm.lattice(11, 0.8, jitter=0.08, seed=21)
+    v = cm.velocities(len(x), 1.0, seed=22)
+    out.update(c_x0=x, c_v0=v, c_L=L)
+    for k, val in cm.drive_compress(lib, x, v, L).items():
+        out["compress_" + k] = val
+    for k, val in cm.drive_berendsen(lib, x, v, L, steps=12, iso=True, update=capi.SEP_LLIST_NEIGHBLIST).items():
+        out["beriso_" + k] = val
+    xb, Lb = cm.lattice(6, 0.844, jitter=0.05, seed=23)
+    vb = cm.velocities(len(xb), 0.728, seed=24)
+    out.update(b_x0=xb, b_v0=vb, b_L=Lb)
+    for k, val in cm.drive_berendsen(lib, xb, vb, Lb).items():
+        out["ber_" + k] = val
+    for k, val in cm.drive_slit(lib, x, v, L).items():
+        out["slit_" + k] = val
+    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), **out)
+    print("next_rows: compress L", out["compress_traj"][0, 2], "->", out["compress_traj"][-1, 2], "cells", out["compress_traj"][0, 3], "->",
+          out["compress_traj"][-1, 3], "| berendsen Lz", out["ber_traj"][0, 3], "->", out["ber_traj"][-1, 3], "p", out["ber_traj"][-1, 2],
+          "| slit ekin", out["slit_traj"][-1, 1], "walls", int((out["slit_types"] == ord("W")).sum()))
+
+
 if __name__ == "__main__":
     lib = cm.ref()
     if lib is None:
         sys.exit("oracle/_ref/libsep_ref.so missing: run `make -C oracle ref` first")
-    which = sys.argv[1:] or ["lj", "butane", "water", "dpd", "molpress", "water_dense"]
+    which = sys.argv[1:] or ["lj", "butane", "water", "dpd", "molpress", "water_dense", "next_rows"]
     for name in which:
         {"lj": lj_fixture, "butane": butane_fixture, "water": water_fixture, "dpd": dpd_fixture,
-         "molpress": molpress_fixture, "water_dense": lambda l: water_fixture(l, dense=True)}[name](lib)
+         "molpress": molpress_fixture, "water_dense": lambda l: water_fixture(l, dense=True),
+         "next_rows": next_rows_fixture}[name](lib)
