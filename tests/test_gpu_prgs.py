@@ -115,35 +115,3 @@ def test_prg2_prg3_prg6_run(tmp_path):
     assert abs(got6[10:, 4].mean() - 1.0) < 0.05                             # DPD thermostat holds T = 1.0
     assert np.abs(got6[:, 6]).max() < 1e-10                                  # momentum conserved by the pair noise
 
-
-def test_prg7_berendsen_npt(tmp_path):
-    """columns: n t epot/N ekin/N T etot/N sum_p p volume   (reference prgs/prg7.c:60-64): brute LJ + Nose-Hoover +
-    sep_berendsen every step.  Step-0 line to printed precision, then the state point the barostat/thermostat hold."""
-    got, _ = run_prg("prg7", tmp_path=tmp_path)
-    ref = golden("prg7.ref.out")
-    assert got.shape == ref.shape
-    assert np.allclose(got[0, 2:6], ref[0, 2:6], rtol=0, atol=2e-6)
-    assert np.allclose(got[0, 7:9], ref[0, 7:9], rtol=0, atol=2e-3)          # p and volume are printed with 3 decimals
-    assert np.allclose(got[1, 2:6], ref[1, 2:6], rtol=0, atol=1e-4)          # 100 steps in: still the same trajectory
-    half = len(ref) // 2
-    assert abs(got[half:, 4].mean() - ref[half:, 4].mean()) < 0.02           # thermostat level (T = 0.5)
-    assert abs(got[half:, 7].mean() - ref[half:, 7].mean()) < 0.35           # pressure level (Pd = 5.91)
-    assert abs(got[half:, 8].mean() / ref[half:, 8].mean() - 1.0) < 0.01     # volume
-    assert np.abs(got[:, 6]).max() < 1e-12                                   # momentum
-
-
-def test_prg8_slit_pore_runs(tmp_path):
-    """prg8 (reference prgs/prg8.c): fluid between tethered walls -- three typed pair calls per step, sep_force_x0
-    with sep_spring_x0, sep_relax_temp on the wall, profile sampler accepted.  The start file is written from the
-    slit fixture of tests/golden/next_rows.npz."""
-    g = np.load(os.path.join(cm.GOLDEN, "next_rows.npz"))
-    x, v, L, types = g["c_x0"], g["c_v0"], float(g["c_L"]), g["slit_types"]
-    with open(tmp_path / "prg8.xyz", "w") as fh:
-        fh.write(f"{len(x)}\n{L:.6f} {L:.6f} {L:.6f}\n")
-        for i in range(len(x)):
-            fh.write("%c %.15f %.15f %.15f %.15f %.15f %.15f %.15f %.15f\n" % (chr(types[i]), *x[i], *v[i], 1.0, 0.0))
-    got, txt = run_prg("prg8", tmp_path=tmp_path)
-    # columns: n  2/3 ekin/N
-    assert len(got) == 100 and np.isfinite(got).all()
-    assert 0.8 < got[20:, 1].mean() < 2.0                                    # wall thermostat at 1.4 carries the fluid along
-    assert os.path.exists(tmp_path / "slitpore.xyz")

@@ -7,12 +7,15 @@ Tolerances: sums 1e-9 relative per step (rounding-order noise grows with the ste
 final positions/velocities 1e-7 absolute after 12-30 steps; box lengths, volume and cell counts 1e-12 / exact.
 """
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
 
 import common as cm
 from seplib_b200 import capi
+from test_gpu_prgs import golden, run_prg
 
 pytestmark = pytest.mark.gpu
 
@@ -38,30 +41,62 @@ def _check(rec, prefix, scalar_cols, exact_cols=(), xtol=1e-7):
     assert np.abs(rec["v"] - G[prefix + "_v"]).max() <= xtol * 10, (prefix, np.abs(rec["v"] - G[prefix + "_v"]).max())
 
 
+def _run(what, sync, tmp_path):
+    """one loop in its own process (tests/next_driver.py): a sep_error() exit fails this test only"""
+    out = str(tmp_path / f"{what}_{sync}.npz")
+    r = subprocess.run([sys.executable, os.path.join(cm.ROOT, "tests", "next_driver.py"), what, str(sync), out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and os.path.exists(out), (r.stdout[-1500:], r.stderr[-1500:])
+    return dict(np.load(out))
+
+
 @pytest.mark.parametrize("sync", [1, 0])
-def test_compress_box_list_mode(sync):
-    lib = capi.load()
-    lib.sep_gpu_set_sync(sync)
-    rec = cm.drive_compress(lib, G["c_x0"], G["c_v0"], float(G["c_L"]))
-    lib.sep_gpu_set_sync(1)
+def test_compress_box_list_mode(sync, tmp_path):
+    rec = _run("compress", sync, tmp_path)
     _check(rec, "compress", scalar_cols=(0, 1, 2, 4), exact_cols=(3,))
     assert rec["traj"][0, 3] == 4 and rec["traj"][-1, 3] == 3      # the grid really changed on the way
 
 
-def test_berendsen_z_brute_and_iso_list():
-    lib = capi.load()
-    lib.sep_gpu_set_sync(1)
-    rec = cm.drive_berendsen(lib, G["b_x0"], G["b_v0"], float(G["b_L"]))
-    _check(rec, "ber", scalar_cols=(0, 1, 2, 3, 4), exact_cols=(5,))
-    rec = cm.drive_berendsen(lib, G["c_x0"], G["c_v0"], float(G["c_L"]), steps=12, iso=True, update=capi.SEP_LLIST_NEIGHBLIST)
-    _check(rec, "beriso", scalar_cols=(0, 1, 2, 3, 4), exact_cols=(5,))
+def test_berendsen_z_brute_and_iso_list(tmp_path):
+    _check(_run("ber", 1, tmp_path), "ber", scalar_cols=(0, 1, 2, 3, 4), exact_cols=(5,))
+    _check(_run("beriso", 1, tmp_path), "beriso", scalar_cols=(0, 1, 2, 3, 4), exact_cols=(5,))
 
 
 @pytest.mark.parametrize("sync", [1, 0])
-def test_slit_pore_relax_temp_and_tethers(sync):
-    lib = capi.load()
-    lib.sep_gpu_set_sync(sync)
-    rec = cm.drive_slit(lib, G["c_x0"], G["c_v0"], float(G["c_L"]))
-    lib.sep_gpu_set_sync(1)
+def test_slit_pore_relax_temp_and_tethers(sync, tmp_path):
+    rec = _run("slit", sync, tmp_path)
     assert np.array_equal(rec["types"], G["slit_types"])
     _check(rec, "slit", scalar_cols=(0, 1))
+
+
+def test_prg7_berendsen_npt(tmp_path):
+    """columns: n t epot/N ekin/N T etot/N sum_p p volume   (reference prgs/prg7.c:60-64): brute LJ + Nose-Hoover +
+    sep_berendsen every step.  Step-0 line to printed precision, then the state point the barostat/thermostat hold."""
+    got, _ = run_prg("prg7", tmp_path=tmp_path)
+    ref = golden("prg7.ref.out")
+    assert got.shape == ref.shape
+    assert np.allclose(got[0, 2:6], ref[0, 2:6], rtol=0, atol=2e-6)
+    assert np.allclose(got[0, 7:9], ref[0, 7:9], rtol=0, atol=2e-3)          # p and volume are printed with 3 decimals
+    assert np.allclose(got[1, 2:6], ref[1, 2:6], rtol=0, atol=1e-4)          # 100 steps in: still the same trajectory
+    half = len(ref) // 2
+    assert abs(got[half:, 4].mean() - ref[half:, 4].mean()) < 0.02           # thermostat level (T = 0.5)
+    assert abs(got[half:, 7].mean() - ref[half:, 7].mean()) < 0.35           # pressure level (Pd = 5.91)
+    assert abs(got[half:, 8].mean() / ref[half:, 8].mean() - 1.0) < 0.01     # volume
+    assert np.abs(got[:, 6]).max() < 1e-12                                   # momentum
+
+
+def test_prg8_slit_pore_runs(tmp_path):
+    """prg8 (reference prgs/prg8.c): fluid between tethered walls -- three typed pair calls per step, sep_force_x0
+    with sep_spring_x0, sep_relax_temp on the wall, profile sampler accepted.  The start file is written from the
+    slit fixture of tests/golden/next_rows.npz."""
+    g = np.load(os.path.join(cm.GOLDEN, "next_rows.npz"))
+    x, v, L, types = g["c_x0"], g["c_v0"], float(g["c_L"]), g["slit_types"]
+    with open(tmp_path / "prg8.xyz", "w") as fh:
+        fh.write(f"{len(x)}\n{L:.6f} {L:.6f} {L:.6f}\n")
+        for i in range(len(x)):
+            fh.write("%c %.15f %.15f %.15f %.15f %.15f %.15f %.15f %.15f\n" % (chr(types[i]), *x[i], *v[i], 1.0, 0.0))
+    got, txt = run_prg("prg8", tmp_path=tmp_path)
+    # columns: n  2/3 ekin/N
+    assert len(got) == 100 and np.isfinite(got).all()
+    assert 0.8 < got[20:, 1].mean() < 2.0                                    # wall thermostat at 1.4 carries the fluid along
+    assert os.path.exists(tmp_path / "slitpore.xyz")
