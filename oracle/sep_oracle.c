@@ -574,3 +574,81 @@ void orc_dpd_force_list(int n, const double *x, const double *pv, const char *ty
     }
     ret->epot = epot;                                    /* assignment, source/sepprfrc.c:1132 */
 }
+
+/* ---- callers either side of the hot path ---------------------------------- */
+static int nsubbox_of(double cf, double delta, double lbox) { return (int)(lbox / (cf + delta)); }   /* source/sepmisc.c:454-463 */
+
+double orc_relax_temp(int n, double *v, const double *m, const char *type, char which, double Td, double tau, double dt)
+{
+    double ekin = 0.0;
+    int ntype = 0;
+    for (int i = 0; i < n; i++)
+        if (type[i] == which) {
+            ntype++;
+            for (int k = 0; k < 3; k++) ekin += m[i] * (v[3 * i + k] * v[3 * i + k]);     /* :364-367 */
+        }
+    ekin = 0.5 * ekin;
+    const double Ta = 2.0 * ekin / (3 * ntype);                                            /* :376 */
+    const double fact = sqrt(1.0 + (dt / tau) * (Td / Ta - 1.0));                          /* :378 */
+    for (int i = 0; i < n; i++)
+        if (type[i] == which)
+            for (int k = 0; k < 3; k++) v[3 * i + k] *= fact;
+    /* sep_reset_momentum, :1173-1192 */
+    double mom[3] = {0.0, 0.0, 0.0}, mass = 0.0;
+    for (int i = 0; i < n; i++)
+        if (type[i] == which) {
+            for (int k = 0; k < 3; k++) mom[k] += v[3 * i + k] * m[i];
+            mass += m[i];
+        }
+    for (int i = 0; i < n; i++)
+        if (type[i] == which)
+            for (int k = 0; k < 3; k++) v[3 * i + k] -= mom[k] / mass;
+    return ekin;
+}
+
+void orc_force_x0(int n, const double *x, const double *x0, const char *type, char which, const double len[3], double *f)
+{
+    const double kspring = 500.0;                                                          /* sep_spring_x0, :168 */
+    for (int i = 0; i < n; i++) {
+        if (type[i] != which) continue;
+        for (int k = 0; k < 3; k++) {
+            const double r = orc_wrap(x0[3 * i + k] - x[3 * i + k], len[k]);               /* :655-657 */
+            const double ft = -kspring;                                                    /* fun(r2,'f') */
+            f[3 * i + k] -= ft * r;                                                        /* :660-662 */
+        }
+    }
+}
+
+int orc_compress_box(int n, double *x, double rhoD, double xi, double len[3], int nsub[3], double lsub[3],
+                     double *volume, double cf, double skin, int list_mode)
+{
+    const double density = n / *volume;
+    if (fabs(density - rhoD) < 1e-6) return 0;
+    if (density > rhoD) xi = 1.0 / xi;
+    for (int k = 0; k < 3; k++) len[k] *= xi;
+    for (int i = 0; i < 3 * n; i++) x[i] *= xi;
+    if (list_mode)
+        for (int k = 0; k < 3; k++) {
+            nsub[k] = nsubbox_of(cf, skin, len[k]);                                        /* with the skin, :1016 */
+            lsub[k] = len[k] / nsub[k];
+        }
+    *volume = len[0] * len[1] * len[2];
+    return 1;
+}
+
+void orc_berendsen(int n, double *x, double Pd, double beta, double p, double dt, int iso, double len[3],
+                   int nsub[3], double lsub[3], double *volume, double cf, int list_mode)
+{
+    const double xi = 1 - beta * dt * (Pd - p);
+    const double scale = pow(xi, 1.0 / 3.0);            /* positions move by xi^(1/3), lengths by xi (:897-901) */
+    for (int k = iso ? 0 : 2; k < 3; k++) {
+        len[k] *= xi;
+        for (int i = 0; i < n; i++) x[3 * i + k] *= scale;
+    }
+    *volume = len[0] * len[1] * len[2];
+    if (list_mode)
+        for (int k = iso ? 0 : 2; k < 3; k++) {
+            nsub[k] = nsubbox_of(cf, 0.0, len[k]);                                         /* without the skin, :906 */
+            lsub[k] = len[k] / nsub[k];
+        }
+}

@@ -120,6 +120,19 @@ int orc_verlet_dpd(int n, double *x, double *v, const double *f, const double *m
                    const double len[3], double dt, double lambda, int stepnow, double skin,
                    double *max_dist2, orc_ret *ret);
 
+/* ---- callers either side of the hot path ---- */
+/* sep_relax_temp + sep_reset_momentum (source/sepmisc.c:357-390, :1173-1192).  Returns the type's kinetic
+ * energy before the rescale. */
+double orc_relax_temp(int n, double *v, const double *m, const char *type, char which, double Td, double tau, double dt);
+/* sep_force_x0 with sep_spring_x0 (source/sepmisc.c:167-181, :645-670): f accumulated, no energy returned */
+void orc_force_x0(int n, const double *x, const double *x0, const char *type, char which, const double len[3], double *f);
+/* sep_compress_box (source/sepmisc.c:994-1026).  len/nsub/lsub/volume in-out; returns 1 when the box changed. */
+int orc_compress_box(int n, double *x, double rhoD, double xi, double len[3], int nsub[3], double lsub[3],
+                     double *volume, double cf, double skin, int list_mode);
+/* sep_berendsen (iso = 0, z only, :892-914) and sep_berendsen_iso (iso = 1, :918-944); p is ret->p. */
+void orc_berendsen(int n, double *x, double Pd, double beta, double p, double dt, int iso, double len[3],
+                   int nsub[3], double lsub[3], double *volume, double cf, int list_mode);
+
 /* sep_dpdforce_neighb (source/sepprfrc.c:1007-1133) with the reference's glibc rand() stream
  * replaced by the product's counter-based pair generator (see orc_dpd_uniform); the reference's
  * stream cannot be reproduced by any parallel evaluation order. */

@@ -68,6 +68,12 @@ def oracle():
     lib.orc_leapfrog.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, vp, C.POINTER(OrcRet)]
     lib.orc_verlet_dpd.restype = i32
     lib.orc_verlet_dpd.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, i32, dbl, vp, C.POINTER(OrcRet)]
+    lib.orc_relax_temp.restype = dbl
+    lib.orc_relax_temp.argtypes = [i32, vp, vp, vp, C.c_char, dbl, dbl, dbl]
+    lib.orc_force_x0.argtypes = [i32, vp, vp, vp, C.c_char, vp, vp]
+    lib.orc_compress_box.restype = i32
+    lib.orc_compress_box.argtypes = [i32, vp, dbl, dbl, vp, vp, vp, vp, dbl, dbl, i32]
+    lib.orc_berendsen.argtypes = [i32, vp, dbl, dbl, dbl, dbl, i32, vp, vp, vp, vp, dbl, i32]
     lib.orc_dpd_uniform.restype = dbl
     lib.orc_dpd_uniform.argtypes = [C.c_ulonglong, C.c_ulonglong, C.c_uint, C.c_uint]
     lib.orc_dpd_force_list.argtypes = [i32, vp, vp, vp, vp, vp, C.c_long, C.c_char_p, dbl, dbl, dbl, dbl, dbl,
@@ -415,4 +421,99 @@ def drive_slit(lib, x, v, L, steps=30):
         tr.append((s.ret.epot, s.ret.ekin))
     rec = _final(s, {"traj": np.array(tr), "types": types})
     s.close()
+    return rec
+
+
+# ---- the same three loops on the oracle (CPU): pins its restatements of the section-8f rows to the golden vectors ----
+class OracleLoop:
+    """State of one system stepped with oracle primitives the way the reference's API steps it."""
+
+    def __init__(self, x, v, L, cf, dt, types=None, list_mode=True, skin=0.25):
+        self.orc = oracle()
+        self.n = len(x)
+        self.x = np.ascontiguousarray(x, dtype=np.float64).copy(); self.v = np.ascontiguousarray(v, dtype=np.float64).copy()
+        self.m = np.ones(self.n); self.a = np.zeros((self.n, 3)); self.f = np.zeros((self.n, 3))
+        self.types = np.full(self.n, ord("A"), dtype=np.uint8) if types is None else np.ascontiguousarray(types, dtype=np.uint8)
+        self.xn = np.zeros((self.n, 3)); self.cn = np.zeros((self.n, 3), dtype=np.int32); self.cr = np.zeros((self.n, 3), dtype=np.int32)
+        self.len = dvec3([L] * 3); self.cf, self.dt, self.skin, self.list_mode = cf, dt, skin, list_mode
+        self.nsub = np.zeros(3, dtype=np.int32); self.lsub = np.zeros(3)
+        self.orc.orc_cell_geometry(ptr(self.len), cf, 0.25, ptr(self.nsub), ptr(self.lsub))     # sep_sys_setup: fixed 0.25
+        self.volume = C.c_double(float(np.prod(self.len)))
+        self.flag, self.pairs, self.maxd2 = 1, None, C.c_double(0.0)
+        self.ret = OrcRet()
+
+    def reset(self):
+        self.ret = OrcRet(); self.f[:] = 0.0; self.maxd2.value = 0.0
+
+    def pair_force(self, types, cf, pot):
+        if self.list_mode:
+            if self.flag:
+                cap = int(40 * self.n * (self.cf + self.skin) ** 3 * self.n / self.volume.value / 8 + 65536)
+                buf = np.empty((cap, 2), dtype=np.int32)
+                k = self.orc.orc_neighb_pairs(self.n, ptr(self.x), ptr(self.len), ptr(self.nsub), ptr(self.lsub), self.cf + self.skin,
+                                              ALL, C.byref(OrcTopo()), ptr(buf), cap)
+                assert k >= 0
+                self.pairs = np.ascontiguousarray(buf[:k]); self.flag = 0
+            self.orc.orc_force_pairs_list(self.n, ptr(self.x), ptr(self.types), ptr(self.len), ptr(self.pairs), len(self.pairs),
+                                          types, cf, pot, None, ptr(self.f), C.byref(self.ret))
+        else:
+            self.orc.orc_force_pairs_brute(self.n, ptr(self.x), ptr(self.types), ptr(self.len), types, cf, pot, None, ALL,
+                                           C.byref(OrcTopo()), ptr(self.f), C.byref(self.ret))
+
+    def leapfrog(self):
+        self.flag |= self.orc.orc_leapfrog(self.n, ptr(self.x), ptr(self.v), ptr(self.f), ptr(self.m), ptr(self.a), ptr(self.xn),
+                                           ptr(self.cn), ptr(self.cr), ptr(self.len), self.dt, self.skin, C.byref(self.maxd2), C.byref(self.ret))
+
+    def pressure(self):
+        kin, pot = np.array(self.ret.kin_P[:]), np.array(self.ret.pot_P[:])
+        P = (kin + pot) / self.volume.value
+        return (P[0] + P[4] + P[8]) / 3.0
+
+    def record(self):
+        return {"x": self.x.copy(), "v": self.v.copy(), "length": np.array(self.len), "nsubbox": self.nsub.copy(),
+                "volume": self.volume.value}
+
+
+def oracle_compress(x, v, L, steps=24, every=3, xi=0.99, rho_target=1.1):
+    o = OracleLoop(x, v, L, 2.5, 0.005)
+    alpha, tr = 0.1, []
+    for n in range(steps):
+        o.reset(); o.pair_force(b"AA", 2.5, POT_LJ_SHIFT)
+        alpha = o.orc.orc_nosehoover(o.n, ptr(o.v), ptr(o.m), ptr(o.f), 1.0, alpha, 0.1, o.dt)
+        o.leapfrog()
+        if n % every == 0:
+            o.orc.orc_compress_box(o.n, ptr(o.x), rho_target, xi, ptr(o.len), ptr(o.nsub), ptr(o.lsub), C.byref(o.volume), o.cf, o.skin, 1)
+        tr.append((o.ret.epot, o.ret.ekin, o.len[0], o.nsub[0], o.volume.value))
+    rec = o.record(); rec["traj"] = np.array(tr)
+    return rec
+
+
+def oracle_berendsen(x, v, L, steps=30, iso=False, list_mode=False):
+    o = OracleLoop(x, v, L, 2.5, 0.005, list_mode=list_mode)
+    alpha, tr = 0.1, []
+    for n in range(steps):
+        o.reset(); o.pair_force(b"AA", 2.5, POT_LJ_SHIFT)
+        alpha = o.orc.orc_nosehoover(o.n, ptr(o.v), ptr(o.m), ptr(o.f), 0.8, alpha, 0.1, o.dt)
+        o.leapfrog()
+        p = o.pressure()
+        o.orc.orc_berendsen(o.n, ptr(o.x), 5.91, 0.1, p, o.dt, 1 if iso else 0, ptr(o.len), ptr(o.nsub), ptr(o.lsub),
+                            C.byref(o.volume), o.cf, 1 if list_mode else 0)
+        tr.append((o.ret.epot, o.ret.ekin, p, o.len[2], o.volume.value, o.nsub[2]))
+    rec = o.record(); rec["traj"] = np.array(tr)
+    return rec
+
+
+def oracle_slit(x, v, L, steps=30):
+    types = np.where(x[:, 2] < 2.2, ord("W"), ord("F")).astype(np.uint8)
+    o = OracleLoop(x, v, L, 2.5, 0.005, types=types)
+    x0 = o.x.copy()
+    tr = []
+    for n in range(steps):
+        o.reset()
+        o.pair_force(b"FF", 2.5, POT_LJ_SHIFT); o.pair_force(b"WF", 2.5, POT_LJ_SHIFT); o.pair_force(b"WW", 2.0 ** (1.0 / 6.0), POT_WCA)
+        o.orc.orc_force_x0(o.n, ptr(o.x), ptr(x0), ptr(o.types), b"W", ptr(o.len), ptr(o.f))
+        o.leapfrog()
+        o.orc.orc_relax_temp(o.n, ptr(o.v), ptr(o.m), ptr(o.types), b"W", 1.4, 0.01, o.dt)
+        tr.append((o.ret.epot, o.ret.ekin))
+    rec = o.record(); rec["traj"] = np.array(tr); rec["types"] = types
     return rec

@@ -387,3 +387,22 @@ def test_gpu_verlet_dpd_golden():
         assert sc.neighb_flag == int(g[f"flag{step + 1}"])
         assert abs(sc.ekin - float(g[f"ekin{step + 1}"])) <= FT * sc.ekin
     s.close()
+
+
+def test_oracle_next_rows_golden():
+    """Section-8f rows on the oracle (orc_compress_box, orc_berendsen, orc_relax_temp, orc_force_x0 inside the same
+    loops the reference ran, tests/common.py) against tests/golden/next_rows.npz.  Trajectories of 12-30 steps:
+    per-step sums to 1e-11 relative, final positions and velocities to 1e-10."""
+    g = load("next_rows.npz")
+    runs = (("compress", cm.oracle_compress(g["c_x0"], g["c_v0"], float(g["c_L"]))),
+            ("beriso", cm.oracle_berendsen(g["c_x0"], g["c_v0"], float(g["c_L"]), steps=12, iso=True, list_mode=True)),
+            ("ber", cm.oracle_berendsen(g["b_x0"], g["b_v0"], float(g["b_L"]))),
+            ("slit", cm.oracle_slit(g["c_x0"], g["c_v0"], float(g["c_L"]))))
+    for name, rec in runs:
+        ref = g[name + "_traj"]
+        assert rec["traj"].shape == ref.shape, name
+        scale = np.abs(ref).max(axis=0)
+        assert (np.abs(rec["traj"] - ref).max(axis=0) <= 1e-11 * scale).all(), (name, np.abs(rec["traj"] - ref).max(axis=0) / scale)
+        assert np.abs(rec["x"] - g[name + "_x"]).max() <= 1e-10, (name, np.abs(rec["x"] - g[name + "_x"]).max())
+        assert np.abs(rec["v"] - g[name + "_v"]).max() <= 1e-10, name
+        assert np.array_equal(rec["nsubbox"], g[name + "_nsubbox"]) and abs(rec["volume"] - float(g[name + "_volume"])) <= 1e-12 * rec["volume"]
