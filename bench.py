@@ -514,7 +514,6 @@ def main():
     ap.add_argument("--rho", type=float, default=0.8)
     ap.add_argument("--skin", type=float, default=0.25)
     ap.add_argument("--tpa", type=int, default=0)
-    ap.add_argument("--unroll", type=int, default=0)
     ap.add_argument("--force-grid", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="decomposed runs: 0 = halo exchange before the force pass, 1 = beside it (default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -624,7 +623,7 @@ def main():
             dist.broadcast(idt, 0)
             s_.dd_init(rank, world, bytes(idt.cpu().numpy().tobytes()), gsys, n_total)
             s_.dd_set_owned(n)
-        for opt, val in (("tpa", args.tpa), ("unroll", args.unroll), ("force_grid", args.force_grid)):
+        for opt, val in (("tpa", args.tpa), ("force_grid", args.force_grid)):
             if val:
                 s_.call("sepgpu_set_option", opt.encode(), val)
         if args.overlap >= 0:

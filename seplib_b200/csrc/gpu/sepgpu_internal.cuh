@@ -53,9 +53,9 @@ struct DevScalars {
     int error;
     int max_neighb;
     long long npairs_listed;
-    int xn_pending;            // (reserved)
+    int stage_needed;          // list build: largest candidate count a tile wanted to stage (host grows the buffer)
     int max_half;              // longest reference-style half list at the last build
-    int sum_mv2_valid;
+    int aliased_seen;          // list build: an atom outside [0,L) was filed under an aliased cell (reference behaviour)
     int pad;
 };
 
@@ -148,7 +148,6 @@ struct sepgpu_ctx {
     // options
     int tpa;                     // lanes per atom in list force kernels
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
-    int unroll;                  // gathers in flight per lane in the list force kernel (2 or 4)
     int force_grid;              // CTAs of the list force kernel (0 = default)
     int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
     int overlap;                 // decomposed runs: halo refresh beside an interior-only force pass (default 0: measured slower,

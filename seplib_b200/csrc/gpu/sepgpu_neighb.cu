@@ -67,7 +67,7 @@ __global__ void k_cell_count(const d4 *__restrict__ x4, int n, double lsx, doubl
             cx = min(max(cx, 0), G.nx - 1); cy = min(max(cy, 0), G.ny - 1); cz = min(max(cz, 0), nzg - 1);
         } else {
             cx = (int)(lin % G.nx); cy = (int)((lin / G.nx) % G.ny); cz = (int)(lin / ((long long)G.nx * G.ny));
-            scal->sum_mv2_valid = 1;            // "aliased atom seen" flag of this build
+            scal->aliased_seen = 1;            // "aliased atom seen" flag of this build
         }
     }
     if (G.dd) {                         // global layer -> local layer of this slab
@@ -487,7 +487,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 
 #include "sepgpu_neighb_tile.cuh"
 
-__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->xn_pending = 0; s->sum_mv2_valid = 0; }
+__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->stage_needed = 0; s->aliased_seen = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
 int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local);
@@ -616,14 +616,14 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             sepgpu_set_error("Too many neighbours");
             return SEPGPU_ENEIGHB;
         }
-        if (c->scal_host->sum_mv2_valid && P.prefilter) {      // an atom outside [0,L) was filed under an aliased cell
+        if (c->scal_host->aliased_seen && P.prefilter) {      // an atom outside [0,L) was filed under an aliased cell
             force_exact = true;
             c->scal_host->nbuild -= 1;
             CUDA_TRY(cudaMemcpyAsync(&c->scal->nbuild, &c->scal_host->nbuild, sizeof(int), cudaMemcpyHostToDevice, c->stream));
             continue;
         }
-        if (c->scal_host->xn_pending > 0) {       // a tile needed a larger staging buffer: grow, rebuild
-            c->tile_stage_cap = (c->scal_host->xn_pending * 5 / 4 + 63) & ~31;
+        if (c->scal_host->stage_needed > 0) {       // a tile needed a larger staging buffer: grow, rebuild
+            c->tile_stage_cap = (c->scal_host->stage_needed * 5 / 4 + 63) & ~31;
             c->scal_host->nbuild -= 1;
             CUDA_TRY(cudaMemcpyAsync(&c->scal->nbuild, &c->scal_host->nbuild, sizeof(int), cudaMemcpyHostToDevice, c->stream));
             continue;

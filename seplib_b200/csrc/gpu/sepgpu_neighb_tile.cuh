@@ -83,7 +83,7 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
     __syncthreads();
     const int total = s_off[ncell];
     if (total > stage_cap) {                                      // host grows the staging buffer and relaunches
-        if (threadIdx.x == 0) atomicMax(&scal->xn_pending, total);
+        if (threadIdx.x == 0) atomicMax(&scal->stage_needed, total);
         return;
     }
     // ---- stage every candidate of the tile once ----

@@ -80,7 +80,6 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->pending_alpha_type = -1;
     c->tpa = 1;
     c->prefilter = 1;
-    c->unroll = 2;
     c->overlap = 0;
     c->single_type = 'A';
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -677,7 +676,6 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
-    if (!strcmp(name, "unroll")) { c->unroll = value == 4 ? 4 : 2; return 0; }
     if (!strcmp(name, "force_grid")) { c->force_grid = value > 0 && value <= SEPGPU_MAX_BLOCKS_PARTIAL ? (int)value : 0; return 0; }
     if (!strcmp(name, "time_kernels")) {
         if (value) { if (ktimer_enable(&c->t_force) || ktimer_enable(&c->t_build) || ktimer_enable(&c->t_intgr) ||
