@@ -352,12 +352,14 @@ void sep_free_tensor_float(float ***ptr, size_t nx, size_t ny);
 double sep_dot(double *a, double *b, int length);
 void sep_vector_set(double *vec, size_t length, double value);
 
-/* ---- samplers (include/sepsampler.h): post-processing, outside the accelerated path.  The entry
- * points the example programs call are provided so prg1/prg2 build; they record nothing. -------------- */
+/* ---- samplers (reference include/sepsampler.h): host post-processing of the synchronised data.
+ * "sacf", "vacf", "msd", "profs", "radial", "msacf" and "mvacf" write the reference's files in the reference's
+ * format (seplib_b200/csrc/host/sep_sampler.c); the remaining names are accepted and record nothing.
+ * The per-sampler state is private to the library. ----------------------------------------------------- */
 typedef struct {
-    int nsamplers;
-    int warned;
     sepmol *molptr;
+    void *impl;
+    long unsigned msd_counter;
 } sepsampler;
 sepsampler sep_init_sampler(void);
 void sep_add_sampler(sepsampler *sptr, const char *sampler, sepsys sys, int lvec, ...);

@@ -69,31 +69,3 @@ void sep_vector_set(double *vec, size_t length, double value)
 {
     for (size_t n = 0; n < length; n++) vec[n] = value;
 }
-
-/* ---- samplers: accepted, not recorded ---------------------------------------------------------------- */
-sepsampler sep_init_sampler(void)
-{
-    sepsampler s;
-    s.nsamplers = 0; s.warned = 0; s.molptr = NULL;
-    return s;
-}
-
-void sep_add_sampler(sepsampler *sptr, const char *sampler, sepsys sys, int lvec, ...)
-{
-    (void)sys; (void)lvec;
-    sptr->nsamplers++;
-    if (!sptr->warned) {
-        sep_warning("samplers are host post-processing and not part of seplib-b200; '%s' (and any further sampler) records nothing",
-                    (char *)sampler);
-        sptr->warned = 1;
-    }
-}
-
-void sep_add_mol_sampler(sepsampler *sptr, sepmol *mols) { sptr->molptr = mols; }
-
-void sep_sample(seppart *pptr, sepsampler *sptr, sepret *ret, sepsys sys, unsigned n)
-{
-    (void)pptr; (void)sptr; (void)ret; (void)sys; (void)n;
-}
-
-void sep_close_sampler(sepsampler *ptr) { ptr->nsamplers = 0; }
