@@ -825,9 +825,9 @@ def main():
         except Exception as e:      # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
 
-    # kernels of this rank in the timed region: reset_ret, reset_maxdist, force, finalize, nh_update, integrate,
-    # finalize (x2 + 2 halo pack/unpack when decomposed); per rebuild: set_xn + 10 build kernels (+ ~25 migration/halo)
-    per_step = 7 + (5 if decomposed else 0)
+    # kernels of this rank in the timed region: force, finalize, nh_update, integrate, finalize (+ lazy resets);
+    # decomposed: + halo push and wait/unpack (peer-memory path); per rebuild: set_xn + 10 build kernels (+ ~25 migration/halo)
+    per_step = 7 + (2 if decomposed else 0)
     per_build = 11 + (25 if decomposed else 0)
     launches = (K * per_step + nbuild * per_build) * (world if decomposed else 1)
     if decomposed:

@@ -10,7 +10,9 @@
  *   "radial" radial distribution functions     -> radial_info.dat radial.dat   (:361-468)
  *   "msacf"  molecular stress autocorrelation  -> msacf.dat                    (:725-821)
  *   "mvacf"  molecular velocity autocorrelation-> mvacf.dat                    (:1757-1826)
- * The wave-vector dependent samplers ("gh", "mgh", "scatt"), "mprofs", "mcacf", "mavacf" and "mmsd" are accepted
+ *   "gh"     generalised hydrodynamics: density, momentum, energy correlations at wave vectors (0, k, 0)
+ *                                              -> gh-wavevector.dat gh-*-acf.dat gh-*-ccf.dat   (:823-1107)
+ * "mgh", "mprofs", "mcacf", "mavacf" (they need molecular spin / couple tensors), "mmsd" and "scatt" are accepted
  * and record nothing (one warning each).
  *
  * All correlation samplers share one block accumulator: lvec rows of ncol channels are collected, then every
@@ -18,6 +20,7 @@
  */
 #include "sep_host.h"
 
+#include <complex.h>
 #include <math.h>
 
 /* ---- block correlation accumulator ------------------------------------------------------------------- */
@@ -95,8 +98,120 @@ typedef struct {
     int *cross;            /* [npart][3] */
 } sep_msdacc;
 
+/* generalised hydrodynamics: five Fourier fields at +k and -k, eleven time correlation functions between them */
+enum { GH_RHO, GH_TV, GH_LV, GH_E, GH_X, GH_NFIELD };
+typedef struct { const char *file; int fa, sa, la, fb, sb, lb; } gh_corr_spec;   /* field, sign (0:+k 1:-k), lagged? */
+static const gh_corr_spec GH_CORR[] = {                                         /* source/sepsampler.c:992-1009 */
+    {"gh-trans-momentum-acf.dat", GH_TV, 1, 0, GH_TV, 0, 1},
+    {"gh-long-momentum-acf.dat", GH_LV, 1, 0, GH_LV, 0, 1},
+    {"gh-rho-acf.dat", GH_RHO, 0, 0, GH_RHO, 1, 1},
+    {"gh-energy-acf.dat", GH_E, 0, 0, GH_E, 1, 1},
+    {"gh-rho-energy-ccf.dat", GH_RHO, 0, 0, GH_E, 1, 1},
+    {"gh-rho-long-momentum-ccf.dat", GH_RHO, 0, 0, GH_LV, 1, 1},
+    {"gh-energy-long-momentum-ccf.dat", GH_E, 0, 0, GH_LV, 1, 1},
+    {"gh-energy-rho-ccf.dat", GH_RHO, 0, 1, GH_E, 1, 0},
+    {"gh-long-momentum-rho-ccf.dat", GH_RHO, 0, 1, GH_LV, 1, 0},
+    {"gh-long-momentum-energy-ccf.dat", GH_E, 0, 1, GH_LV, 1, 0},
+    {"gh-X-acf.dat", GH_X, 0, 0, GH_LV, 1, 1},
+};
+#define GH_NCORR ((int)(sizeof GH_CORR / sizeof GH_CORR[0]))
+
+typedef struct {
+    unsigned lvec, fill, nsample, isample, nwave, ncalls;
+    double dtsample, avekin;
+    double *k;
+    double complex *field;      /* [GH_NFIELD][2][lvec][nwave] */
+    double complex *corr;       /* [GH_NCORR][lvec][nwave]     */
+} sep_ghacc;
+
+static double complex *gh_field(sep_ghacc *g, int f, int sign, unsigned t)
+{
+    return g->field + (((size_t)f * 2 + sign) * g->lvec + t) * g->nwave;
+}
+
+static sep_ghacc *gh_new(int lvec, double tsample, double dt, int nwave, double Ldir)
+{
+    sep_ghacc *g = calloc(1, sizeof *g);
+    if (!g || lvec <= 0 || nwave <= 0) sep_error("sep_gh_init: Couldn't allocate memory");
+    g->lvec = (unsigned)lvec; g->nwave = (unsigned)nwave;
+    g->dtsample = tsample / lvec;
+    g->isample = (unsigned)(int)(g->dtsample / dt);
+    if ((int)(g->dtsample / dt) < 1) sep_error("sep_gh_init: isample is too small - CHECK lvec argument");
+    g->k = sep_vector((size_t)nwave);
+    g->field = calloc((size_t)GH_NFIELD * 2 * lvec * nwave, sizeof(double complex));
+    g->corr = calloc((size_t)GH_NCORR * lvec * nwave, sizeof(double complex));
+    FILE *fout = fopen("gh-wavevector.dat", "w");
+    if (!fout || !g->field || !g->corr) sep_error("sep_gh_init: Couldn't open file k.dat");
+    for (int n = 1; n <= nwave; n++) {
+        g->k[n - 1] = 2 * SEP_PI * n / Ldir;
+        fprintf(fout, "%f\n", g->k[n - 1]);
+    }
+    fclose(fout);
+    return g;
+}
+
+static void sample_gh(sep_ghacc *g, seppart *atoms, sepsys *sys)
+{
+    const int kdir = 1, tdir = 0;                 /* wave vector (0, k, 0), transverse direction x (:848-849) */
+    const unsigned t = g->fill;
+    sep_eval_xtrue(atoms, sys);
+    double sumv2 = 0.0;
+    for (long m = 0; m < sys->npart; m++)
+        for (int kk = 0; kk < 3; kk++) sumv2 += 0.5 * atoms[m].m * sep_Sq(atoms[m].v[kk]);
+    g->ncalls++;
+    g->avekin += sumv2 / (sys->npart * g->ncalls);             /* the reference's running value, :940 */
+    for (unsigned n = 0; n < g->nwave; n++) {
+        double complex acc[GH_NFIELD][2];
+        for (int f = 0; f < GH_NFIELD; f++) acc[f][0] = acc[f][1] = 0.0;
+        for (long m = 0; m < sys->npart; m++) {
+            const double mass = atoms[m].m;
+            const double complex kf[2] = {cexp(I * g->k[n] * atoms[m].xtrue[kdir]), cexp(-I * g->k[n] * atoms[m].xtrue[kdir])};
+            double ekin = 0.0;
+            for (int kk = 0; kk < 3; kk++) ekin += 0.5 * mass * sep_Sq(atoms[m].v[kk]);
+            const double complex aux = mass * (atoms[m].a[1] - I * g->k[n] * sep_Sq(atoms[m].v[1]));
+            for (int sgn = 0; sgn < 2; sgn++) {
+                acc[GH_RHO][sgn] += mass * kf[sgn];
+                acc[GH_TV][sgn] += mass * atoms[m].v[tdir] * kf[sgn];
+                acc[GH_LV][sgn] += mass * atoms[m].v[kdir] * kf[sgn];
+                acc[GH_E][sgn] += (ekin - g->avekin) * kf[sgn];
+                acc[GH_X][sgn] += aux * kf[sgn];
+            }
+        }
+        for (int f = 0; f < GH_NFIELD; f++)
+            for (int sgn = 0; sgn < 2; sgn++) gh_field(g, f, sgn, t)[n] = acc[f][sgn];
+    }
+    if (++g->fill < g->lvec) return;
+    for (int c = 0; c < GH_NCORR; c++) {
+        const gh_corr_spec *sp = &GH_CORR[c];
+        for (unsigned k = 0; k < g->nwave; k++)
+            for (unsigned n = 0; n < g->lvec; n++) {
+                double complex sum = 0.0;
+                for (unsigned nn = 0; nn + n < g->lvec; nn++)
+                    sum += gh_field(g, sp->fa, sp->sa, sp->la ? nn + n : nn)[k] * gh_field(g, sp->fb, sp->sb, sp->lb ? nn + n : nn)[k];
+                g->corr[((size_t)c * g->lvec + n) * g->nwave + k] += sum;
+            }
+    }
+    g->nsample++;
+    for (int c = 0; c < GH_NCORR; c++) {
+        FILE *fout = fopen(GH_CORR[c].file, "w");
+        if (!fout) sep_error("sep_gh_sampler: Error opening files");
+        for (unsigned n = 0; n < g->lvec; n++) {
+            const double fac = 1.0 / (g->nsample * sys->volume * (g->lvec - n));
+            fprintf(fout, "%f ", n * g->dtsample);
+            for (unsigned k = 0; k < g->nwave; k++) {
+                const double complex v = g->corr[((size_t)c * g->lvec + n) * g->nwave + k] * fac;
+                fprintf(fout, "%f %f ", creal(v), cimag(v));
+            }
+            fprintf(fout, "\n");
+        }
+        fclose(fout);
+    }
+    g->fill = 0;
+}
+
 struct sep_sampler_set {
     sep_corr *sacf, *vacf, *msacf, *mvacf;
+    sep_ghacc *gh;
     sep_profile *profs;
     sep_rdf *radial;
     sep_msdacc *msd;
@@ -205,6 +320,12 @@ void sep_add_sampler(sepsampler *sptr, const char *sampler, sepsys sys, int lvec
             fclose(fout);
             S->radial = r;
         }
+    } else if (!strcmp(sampler, "gh")) {
+        if (!S->gh) {
+            const double tsample = va_arg(args, double);
+            const int nwave = va_arg(args, int);
+            S->gh = gh_new(lvec, tsample, sys.dt, nwave, sys.length[1]);
+        }
     } else if (!strcmp(sampler, "msd")) {
         if (!S->msd) {
             const double tsample = va_arg(args, double);
@@ -213,9 +334,9 @@ void sep_add_sampler(sepsampler *sptr, const char *sampler, sepsys sys, int lvec
             S->msd = msd_new(lvec, tsample, nk, type, &sys);
         }
     } else {
-        static const char *later[] = {"gh", "mgh", "mprofs", "mcacf", "mavacf", "mmsd", "scatt"};
+        static const char *later[] = {"mgh", "mprofs", "mcacf", "mavacf", "mmsd", "scatt"};
         int known = -1;
-        for (int k = 0; k < 7; k++) if (!strcmp(sampler, later[k])) known = k;
+        for (int k = 0; k < 6; k++) if (!strcmp(sampler, later[k])) known = k;
         if (known < 0) sep_error("sep_add_sampler: Sampler %s is not recognized", (char *)sampler);
         if (!(S->warned & (1u << known))) {
             sep_warning("sampler '%s' is not implemented in seplib-b200; it records nothing", (char *)sampler);
@@ -424,12 +545,13 @@ void sep_sample(seppart *pptr, sepsampler *sptr, sepret *ret, sepsys sys, unsign
 {
     struct sep_sampler_set *S = (struct sep_sampler_set *)sptr->impl;
     if (!S) return;
-    if ((S->vacf && n % S->vacf->isample == 0) || (S->profs && n % S->profs->isample == 0) ||
+    if ((S->vacf && n % S->vacf->isample == 0) || (S->profs && n % S->profs->isample == 0) || (S->gh && n % S->gh->isample == 0) ||
         (S->radial && n % (unsigned)S->radial->isample == 0) || S->msd)
         sep_gpu_sync(pptr);                                    /* the samplers below read atoms[] on the host */
     if (S->sacf && n % S->sacf->isample == 0) sample_sacf(S->sacf, ret, &sys);
     if (S->vacf && n % S->vacf->isample == 0) sample_vacf(S->vacf, pptr, &sys);
     if (S->msacf && n % S->msacf->isample == 0) sample_msacf(S->msacf, pptr, sptr->molptr, ret, &sys);
+    if (S->gh && n % S->gh->isample == 0) sample_gh(S->gh, pptr, &sys);
     if (S->profs && n % S->profs->isample == 0) sample_profs(S->profs, pptr, &sys);
     if (S->mvacf && n % S->mvacf->isample == 0) sample_mvacf(S->mvacf, pptr, sptr->molptr, &sys);
     if (S->radial && n % (unsigned)S->radial->isample == 0) sample_radial(S->radial, pptr, &sys);
@@ -452,6 +574,7 @@ void sep_close_sampler(sepsampler *ptr)
     corr_free(S->sacf); corr_free(S->vacf); corr_free(S->msacf); corr_free(S->mvacf);
     if (S->profs) { free(S->profs->momc); free(S->profs->dens); free(S->profs->temp); free(S->profs->svel); free(S->profs); }
     if (S->radial) { free(S->radial->hist); free(S->radial); }
+    if (S->gh) { free(S->gh->k); free(S->gh->field); free(S->gh->corr); free(S->gh); }
     if (S->msd) {
         sep_msdacc *m = S->msd;
         free(m->time); free(m->msd); free(m->msdsq); free(m->k); free(m->fs); free(m->prev); free(m->pos0); free(m->cross);

@@ -80,6 +80,7 @@ def test_atomic_samplers_match_reference(libs, tmp_path):
             _add(lib, smp, b"msd", s.sys, 15, C.c_double(1.5), C.c_int(3), C.c_int(ord("A")))
             _add(lib, smp, b"profs", s.sys, 10, C.c_int(ord("A")), C.c_int(2))
             _add(lib, smp, b"radial", s.sys, 50, C.c_int(50), C.c_char_p(b"AB"))
+            _add(lib, smp, b"gh", s.sys, 10, C.c_double(0.5), C.c_int(3))
         fun = s.fun("sep_lj_shift")
         alpha = C.c_double(0.1)
         for n in range(650):
@@ -96,7 +97,10 @@ def test_atomic_samplers_match_reference(libs, tmp_path):
         os.chdir(cwd)
         s.close()
     _compare_dirs(da, db, ["vacf.dat", "sacf.dat", "msd-k.dat", "msd.dat", "msd-gaussparam.dat", "msd-incoherent.dat",
-                           "profs.dat", "radial_info.dat", "radial.dat"])
+                           "profs.dat", "radial_info.dat", "radial.dat", "gh-wavevector.dat", "gh-trans-momentum-acf.dat",
+                           "gh-long-momentum-acf.dat", "gh-rho-acf.dat", "gh-energy-acf.dat", "gh-rho-energy-ccf.dat",
+                           "gh-rho-long-momentum-ccf.dat", "gh-energy-long-momentum-ccf.dat", "gh-energy-rho-ccf.dat",
+                           "gh-long-momentum-rho-ccf.dat", "gh-long-momentum-energy-ccf.dat", "gh-X-acf.dat"])
 
 
 def test_log_spaced_msd_matches_reference(libs, tmp_path):
