@@ -11,13 +11,14 @@ on a lattice-initialised Lennard-Jones fluid (prg1-style NVT, SURVEY.md section 
             region contains the host->device upload, a device->host read of the step's sepret/sepsys
             scalars EVERY step, and the final download into the host array
   roofline  the pair-force kernel (dominant): algorithmic bytes / CUDA-event time vs measured HBM peak,
-            plus its FP64 rate vs an FMA-chain peak measured on this box (the kernel is FP64-pipe bound)
+            plus its FP64 rate vs an FMA-chain peak measured on this box (the kernel is bound by neither: the L1
+            tag stage of the neighbour gathers is)
   cpu_baseline  the reference's own OpenMP CPU path (oracle/_ref, compiled from its unmodified sources)
             on the box's host cores, bounded sample of the same workload
 
 --impl reference runs only that CPU arm and prints its own line.
-N>1 (torchrun): spatial domain decomposition when available (strong scaling of the 8M-atom config),
-otherwise independent replicas (weak scaling) -- stated in config.parallelism.
+N>1 (torchrun): slab domain decomposition, N x 1 M atoms (weak scaling; 8 GPUs = the 8 M-atom C4 configuration);
+--replicas runs N independent copies instead.  --workload butane|water runs the C2 / C3 configurations (1 GPU).
 """
 import argparse
 import ctypes as C

@@ -1,9 +1,5 @@
-/* sep_compat.c -- small host helpers the example programs call (allocators from the reference's
- * source/separray.c:16-213, sep_dot from source/seputil.c:393-403) and the sampler entry points.
- *
- * Samplers (reference source/sepsampler.c, 2.2 kLoC of post-processing) are outside the accelerated
- * path (out of scope): the functions below accept the calls prg1/prg2 make and
- * record nothing, saying so once. */
+/* sep_compat.c -- small host helpers the example programs call: allocators (reference
+ * source/separray.c:16-213) and sep_dot (source/seputil.c:393-403).  The samplers live in sep_sampler.c. */
 #include "sep_host.h"
 
 double *sep_vector(size_t length)
