@@ -94,153 +94,80 @@ extern "C" {
 #define sep_Wrap( x, y )  { if ( x > 0.5*y ) x -= y; else if ( x < -0.5*y ) x += y; }
 #define sep_Periodic( x, y )  { if ( x > y ) x -= y; else if ( x < 0 ) x += y; }
 
-/* ---- data model (include/sepstrct.h:23-204); field order kept so the layout is identical ---- */
+/* ---- data model (reference include/sepstrct.h:23-204) -------------------------------------------------
+ * Programs built against the reference read and write these records directly, so every member keeps the
+ * reference's name, type and position (tests/test_cpu_host.py compares sizes and offsets with the compiled
+ * reference).  Members this library maintains:
+ *   seppart   x v f a m type z   state of one atom (x wrapped into the box);  neighb: host list row, filled only by
+ *             sep_gpu_export_neighb;  cross_neighb / crossings: box crossings since the last list build / since
+ *             the start;  molindex (-1: none) and the bonded partner tables bond / angle / dihed (-1 terminated);
+ *             xtrue x0 xn: unwrapped, tether and last-list-build positions;  pv pa: DPD predictor state.
+ *             sigma collid colltime ldiff xp px randn prevf belong to integrators that are not part of this library.
+ *   sepmolinfo  topology lists (blist: a b type; alist: a b c type; dlist: a b c d type), their measured
+ *             values, and the molecule-pair force table Fij.
+ *   sepsys    box, time step, cell grid, neighbour-list switches and the rebuild flag.
+ *   sepmol    per-molecule derived data (centre of mass, velocity, member atoms).
+ *   sepret    sums returned by the hot calls (energies, pressure tensors). */
 typedef struct {
-    double x[3];            /* position (wrapped into the box)            */
-    double v[3];            /* velocity                                   */
-    double f[3];            /* force                                      */
-    double a[3];            /* acceleration                               */
-    double m;               /* mass                                       */
-    char type;              /* one-character type label                   */
-    double z;               /* point charge                               */
-
-    int *neighb;            /* host neighbour row (filled only on request: sep_gpu_export_neighb) */
-
-    int cross_neighb[3];    /* box crossings since the last list build    */
-    int crossings[3];       /* box crossings since the start              */
-
-    int molindex;           /* owning molecule or -1                      */
-    int bond[SEP_BOND];     /* atoms sharing a bond with this one         */
-    int angle[SEP_ANGLE];   /* atoms sharing an angle                     */
-    int dihed[SEP_DIHED];   /* atoms sharing a dihedral                   */
-
-    double sigma;           /* hard-sphere diameter (unused here)         */
+    double x[3], v[3], f[3], a[3], m;
+    char type;
+    double z;
+    int *neighb;
+    int cross_neighb[3], crossings[3], molindex, bond[SEP_BOND], angle[SEP_ANGLE], dihed[SEP_DIHED];
+    double sigma;
     int *collid;
     double *colltime;
-
-    double ldiff;
-
-    double xtrue[3];
-    double x0[3];
-    double xn[3];           /* position at the last list build            */
-    double xp[3];
-    double px[3];
-    double pv[3];           /* predicted velocity (DPD)                   */
-    double pa[3];           /* previous acceleration (DPD)                */
-    double randn[3];
-    double prevf[3];
+    double ldiff, xtrue[3], x0[3], xn[3], xp[3], px[3], pv[3], pa[3], randn[3], prevf[3];
 } seppart;
-
 typedef seppart sepatom;
 
 typedef struct {
-    unsigned num_mols;
-    unsigned max_nuau;
-
+    unsigned num_mols, max_nuau;
     int flag_bonds, flag_angles, flag_dihedrals;
-
-    unsigned num_bonds;
-    unsigned *blist;        /* (a, b, type) per bond              */
-    unsigned num_btypes;
-
-    unsigned num_angles;
-    unsigned *alist;        /* (a, b, c, type) per angle          */
-    unsigned num_atypes;
-
-    unsigned num_dihedrals;
-    unsigned *dlist;        /* (a, b, c, d, type) per dihedral    */
-    unsigned num_dtypes;
-
-    double *blengths;
-    double *angles;
-    double *dihedrals;
-
+    unsigned num_bonds, *blist, num_btypes;
+    unsigned num_angles, *alist, num_atypes;
+    unsigned num_dihedrals, *dlist, num_dtypes;
+    double *blengths, *angles, *dihedrals;
     unsigned flag_Fij;
-    float ***Fij;
-    float ***Fiajb;
+    float ***Fij, ***Fiajb;
 } sepmolinfo;
 
 typedef struct {
     long int npart;
-    double length[3];
-    double volume;
-
+    double length[3], volume;
     int intgr_type;
-    double dt;
-    double tnow;
+    double dt, tnow;
     unsigned ndof;
-    double max_dist2;
-
-    double cf;
-    double lsubbox[3];
+    double max_dist2, cf, lsubbox[3];
     int nsubbox[3];
     double skin;
-    unsigned neighb_update;
-    unsigned neighb_flag;
-    unsigned nupdate_neighb;
-
+    unsigned neighb_update, neighb_flag, nupdate_neighb;
     bool omp_flag;
     unsigned int nthreads;
-
     int fun_cstate;
-
     sepmolinfo *molptr;
 } sep3D;
-
 typedef sep3D sepsys;
 
 typedef struct {
-    double m;
-    double x[3], xtrue[3];
-    double v[3];
-
+    double m, x[3], xtrue[3], v[3];
     unsigned nuau;
     int *index;
-
-    double ete[3];
-    double re2;
-    double rg;
-    double S[3];
-
-    double s[3];
-    double inertia[3][3];
-    double w[3];
+    double ete[3], re2, rg, S[3], s[3], inertia[3][3], w[3];
     int method_w;
     double pel[3];
-
     char type;
-
     unsigned nbonds;
     double *blength;
     int shake_flag;
 } sepmol;
 
 typedef struct {
-    double etot;
-    double ekin;
-    double epot;
-    double ecoul;
-    double sumv2;
-
-    double P[3][3];
-    double kin_P[3][3];
-    double pot_P[3][3];
-    double p;
-
-    double P_mol[3][3];
-    double kin_P_mol[3][3];
-    double pot_P_mol[3][3];
-    double p_mol;
-
-    double pot_P_conservative[3][3];
-    double pot_P_random[3][3];
-    double pot_P_dissipative[3][3];
-    double pot_P_bond[3][3];
-
-    double pot_T_mol[3][3];
-    double kin_T_mol[3][3];
-    double T_mol[3][3];
-    double t_mol;
+    double etot, ekin, epot, ecoul, sumv2;
+    double P[3][3], kin_P[3][3], pot_P[3][3], p;
+    double P_mol[3][3], kin_P_mol[3][3], pot_P_mol[3][3], p_mol;
+    double pot_P_conservative[3][3], pot_P_random[3][3], pot_P_dissipative[3][3], pot_P_bond[3][3];
+    double pot_T_mol[3][3], kin_T_mol[3][3], T_mol[3][3], t_mol;
 } sepret;
 
 /* ---- setup and teardown (include/sepinit.h:29-84) --------------------------------------------- */
