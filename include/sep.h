@@ -224,6 +224,9 @@ void sep_angle_cossq(sepatom *ptr, int type, const double angle0, const double k
                      sepsys *sys, sepret *ret);
 void sep_torsion_Ryckaert(sepatom *ptr, int type, const double g[6], sepsys *sys, sepret *ret);
 void sep_mol_cm(seppart *ptr, sepmol *mol, sepsys *sys);
+void sep_mol_eval_xtrue(seppart *ptr, sepmol *mol, sepsys sys);
+void sep_mol_spin(sepatom *atom, sepmol *mol, sepsys *sys, bool safe);
+void sep_mol_dipoles(seppart *atom, sepmol *mol, sepsys *sys);
 void sep_mol_velcm(seppart *atom, sepmol *mol, sepsys *sys);
 void sep_eval_mol_pressure_tensor(sepatom *atoms, sepmol *mols, sepret *ret, sepsys *sys);
 double sep_average_bondlengths(int type, sepsys *sys);
@@ -280,7 +283,7 @@ double sep_dot(double *a, double *b, int length);
 void sep_vector_set(double *vec, size_t length, double value);
 
 /* ---- samplers (reference include/sepsampler.h): host post-processing of the synchronised data.
- * "sacf", "vacf", "msd", "profs", "radial", "msacf" and "mvacf" write the reference's files in the reference's
+ * "sacf", "vacf", "msd", "gh", "profs", "radial", "msacf", "mvacf" and "mgh" write the reference's files in the reference's
  * format (seplib_b200/csrc/host/sep_sampler.c); the remaining names are accepted and record nothing.
  * The per-sampler state is private to the library. ----------------------------------------------------- */
 typedef struct {

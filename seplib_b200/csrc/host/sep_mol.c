@@ -7,6 +7,7 @@
  * (source/sepmol.c:372-587) are device kernels (sepgpu_bonded.cu).
  */
 #include "sep_host.h"
+#include <float.h>
 
 /* ---- .top reader ----------------------------------------------------------------------------------- */
 typedef struct { unsigned *v; size_t n, cap; } uvec;
@@ -233,6 +234,107 @@ void sep_mol_velcm(seppart *atom, sepmol *mol, sepsys *sys)
             for (int k = 0; k < 3; k++) mol[i].v[k] += atom[a].v[k] * atom[a].m;
         }
         for (int k = 0; k < 3; k++) mol[i].v[k] /= mol[i].m;
+    }
+}
+
+/* ---- per-molecule derived quantities used by the molecular samplers (host, on synchronised atoms[]) ---------- */
+/* unwrapped centre of mass, source/sepmol.c:1127-1148 */
+void sep_mol_eval_xtrue(seppart *ptr, sepmol *mol, sepsys sys)
+{
+    sep_eval_xtrue(ptr, &sys);
+    for (unsigned n = 0; n < sys.molptr->num_mols; n++) {
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (unsigned m = 0; m < mol[n].nuau; m++) {
+            const int i = mol[n].index[m];
+            for (int k = 0; k < 3; k++) acc[k] += ptr[i].m * ptr[i].xtrue[k];
+        }
+        for (int k = 0; k < 3; k++) mol[n].xtrue[k] = acc[k] / mol[n].m;
+    }
+}
+
+static double det3(double a[3][3])
+{
+    return a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+           a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+}
+
+/* angular momentum s about the centre of mass, inertia tensor and (unless safe) angular velocity w = I^-1 s;
+ * a singular tensor (linear molecule) falls back to the mean principal moment, source/sepmol.c:750-817 */
+void sep_mol_spin(sepatom *atom, sepmol *mol, sepsys *sys, bool safe)
+{
+    sep_mol_cm(atom, mol, sys);
+    for (unsigned i = 0; i < sys->molptr->num_mols; i++) {
+        double in[3][3] = {{0}}, s[3] = {0.0, 0.0, 0.0}, w[3] = {0.0, 0.0, 0.0};
+        for (unsigned n = 0; n < mol[i].nuau; n++) {
+            const int ia = mol[i].index[n];
+            if (ia == -1) break;
+            const double mia = atom[ia].m;
+            double d[3], p[3];
+            for (int k = 0; k < 3; k++) {
+                d[k] = atom[ia].x[k] - mol[i].x[k];
+                sep_Wrap(d[k], sys->length[k]);
+                p[k] = atom[ia].v[k] * mia;
+            }
+            s[0] += d[1] * p[2] - d[2] * p[1];
+            s[1] += d[2] * p[0] - d[0] * p[2];
+            s[2] += d[0] * p[1] - d[1] * p[0];
+            in[0][0] += mia * (sep_Sq(d[1]) + sep_Sq(d[2]));
+            in[1][1] += mia * (sep_Sq(d[0]) + sep_Sq(d[2]));
+            in[2][2] += mia * (sep_Sq(d[0]) + sep_Sq(d[1]));
+            in[0][1] -= mia * d[0] * d[1];
+            in[0][2] -= mia * d[0] * d[2];
+            in[1][2] -= mia * d[1] * d[2];
+        }
+        in[1][0] = in[0][1]; in[2][0] = in[0][2]; in[2][1] = in[1][2];
+        if (!safe) {
+            const double det = det3(in);
+            if (fabs(det) < DBL_EPSILON) {
+                const double Ip = (in[0][0] + in[1][1] + in[2][2]) / 3.0;       /* mean eigenvalue = trace / 3 */
+                for (int k = 0; k < 3; k++) w[k] = s[k] / Ip;
+                mol[i].method_w = 0;
+            } else {                                                           /* Cramer's rule on the 3x3 system */
+                for (int c = 0; c < 3; c++) {
+                    double t[3][3];
+                    for (int r = 0; r < 3; r++)
+                        for (int q = 0; q < 3; q++) t[r][q] = q == c ? s[r] : in[r][q];
+                    w[c] = det3(t) / det;
+                }
+                mol[i].method_w = 1;
+            }
+        }
+        for (int k = 0; k < 3; k++) {
+            if (!safe) mol[i].w[k] = w[k];
+            mol[i].s[k] = s[k];
+            for (int kk = 0; kk < 3; kk++) mol[i].inertia[k][kk] = in[k][kk];
+        }
+    }
+}
+
+/* electric dipole from the mean positions of the positive and of the negative sites, source/sepmol.c:1036-1083 */
+void sep_mol_dipoles(seppart *atom, sepmol *mol, sepsys *sys)
+{
+    sep_mol_cm(atom, mol, sys);
+    for (unsigned i = 0; i < sys->molptr->num_mols; i++) {
+        double sumz = 0.0, rpos[3] = {0.0, 0.0, 0.0}, rneg[3] = {0.0, 0.0, 0.0};
+        int npos = 0, nneg = 0;
+        for (unsigned n = 0; n < mol[i].nuau; n++) {
+            const int ia = mol[i].index[n];
+            double off[3] = {0.0, 0.0, 0.0};
+            for (int k = 0; k < 3; k++) {
+                const double d = atom[ia].x[k] - mol[i].x[k];
+                if (fabs(d) > 0.5 * sys->length[k]) off[k] = d > 0.0 ? -sys->length[k] : sys->length[k];
+            }
+            if (atom[ia].z > 0.0) {
+                for (int k = 0; k < 3; k++) rpos[k] += atom[ia].x[k] + off[k];
+                sumz += atom[ia].z;
+                npos++;
+            } else if (atom[ia].z < 0.0) {
+                for (int k = 0; k < 3; k++) rneg[k] += atom[ia].x[k] + off[k];
+                nneg++;
+            }
+        }
+        if (nneg > 0 && npos > 0)
+            for (int k = 0; k < 3; k++) mol[i].pel[k] = sumz * (rpos[k] / npos - rneg[k] / nneg);
     }
 }
 

@@ -12,8 +12,9 @@
  *   "mvacf"  molecular velocity autocorrelation-> mvacf.dat                    (:1757-1826)
  *   "gh"     generalised hydrodynamics: density, momentum, energy correlations at wave vectors (0, k, 0)
  *                                              -> gh-wavevector.dat gh-*-acf.dat gh-*-ccf.dat   (:823-1107)
- * "mgh", "mprofs", "mcacf", "mavacf" (they need molecular spin / couple tensors), "mmsd" and "scatt" are accepted
- * and record nothing (one warning each).
+ *   "mgh"    the molecular counterpart (centre-of-mass fields, angular momentum, dipole)
+ *                                              -> mgh-wavevector.dat mgh-*-acf.dat mgh-*-ccf.dat (:1110-1415)
+ * "mprofs", "mcacf", "mavacf", "mmsd" and "scatt" are accepted and record nothing (one warning each).
  *
  * All correlation samplers share one block accumulator: lvec rows of ncol channels are collected, then every
  * channel's products x[t0] x[t0+t] are added to acf[t] and the file is rewritten.
@@ -98,50 +99,42 @@ typedef struct {
     int *cross;            /* [npart][3] */
 } sep_msdacc;
 
-/* generalised hydrodynamics: five Fourier fields at +k and -k, eleven time correlation functions between them */
-enum { GH_RHO, GH_TV, GH_LV, GH_E, GH_X, GH_NFIELD };
-typedef struct { const char *file; int fa, sa, la, fb, sb, lb; } gh_corr_spec;   /* field, sign (0:+k 1:-k), lagged? */
-static const gh_corr_spec GH_CORR[] = {                                         /* source/sepsampler.c:992-1009 */
-    {"gh-trans-momentum-acf.dat", GH_TV, 1, 0, GH_TV, 0, 1},
-    {"gh-long-momentum-acf.dat", GH_LV, 1, 0, GH_LV, 0, 1},
-    {"gh-rho-acf.dat", GH_RHO, 0, 0, GH_RHO, 1, 1},
-    {"gh-energy-acf.dat", GH_E, 0, 0, GH_E, 1, 1},
-    {"gh-rho-energy-ccf.dat", GH_RHO, 0, 0, GH_E, 1, 1},
-    {"gh-rho-long-momentum-ccf.dat", GH_RHO, 0, 0, GH_LV, 1, 1},
-    {"gh-energy-long-momentum-ccf.dat", GH_E, 0, 0, GH_LV, 1, 1},
-    {"gh-energy-rho-ccf.dat", GH_RHO, 0, 1, GH_E, 1, 0},
-    {"gh-long-momentum-rho-ccf.dat", GH_RHO, 0, 1, GH_LV, 1, 0},
-    {"gh-long-momentum-energy-ccf.dat", GH_E, 0, 1, GH_LV, 1, 0},
-    {"gh-X-acf.dat", GH_X, 0, 0, GH_LV, 1, 1},
-};
-#define GH_NCORR ((int)(sizeof GH_CORR / sizeof GH_CORR[0]))
+/* ---- wave-vector dependent correlators ("gh", "mgh") ------------------------------------------------------
+ * A set of Fourier fields A_f(+k, t) and A_f(-k, t) at wave vectors (0, k_n, 0) is recorded for lvec sample
+ * times; when the block is full every listed product  A(t0) B(t0 + t)  (or A(t0 + t) B(t0)) is added to its
+ * correlation function and all files are rewritten (real and imaginary part per wave vector). */
+#define FK_MAXFIELD 10
+typedef struct { const char *file; int fa, sa, la, fb, sb, lb; int unsafe_only; } fk_corr_spec;   /* field, sign (0:+k 1:-k), lagged? */
 
 typedef struct {
     unsigned lvec, fill, nsample, isample, nwave, ncalls;
+    int nfield, ncorr, safe;
+    const fk_corr_spec *spec;
     double dtsample, avekin;
     double *k;
-    double complex *field;      /* [GH_NFIELD][2][lvec][nwave] */
-    double complex *corr;       /* [GH_NCORR][lvec][nwave]     */
-} sep_ghacc;
+    double complex *field;      /* [nfield][2][lvec][nwave] */
+    double complex *corr;       /* [ncorr][lvec][nwave]     */
+} sep_fkacc;
 
-static double complex *gh_field(sep_ghacc *g, int f, int sign, unsigned t)
+static double complex *fk_field(sep_fkacc *g, int f, int sign, unsigned t)
 {
     return g->field + (((size_t)f * 2 + sign) * g->lvec + t) * g->nwave;
 }
 
-static sep_ghacc *gh_new(int lvec, double tsample, double dt, int nwave, double Ldir)
+static sep_fkacc *fk_new(const char *who, const char *kfile, int lvec, double tsample, double dt, int nwave, double Ldir,
+                         int nfield, const fk_corr_spec *spec, int ncorr)
 {
-    sep_ghacc *g = calloc(1, sizeof *g);
-    if (!g || lvec <= 0 || nwave <= 0) sep_error("sep_gh_init: Couldn't allocate memory");
-    g->lvec = (unsigned)lvec; g->nwave = (unsigned)nwave;
+    sep_fkacc *g = calloc(1, sizeof *g);
+    if (!g || lvec <= 0 || nwave <= 0) sep_error("%s: Couldn't allocate memory", (char *)who);
+    g->lvec = (unsigned)lvec; g->nwave = (unsigned)nwave; g->nfield = nfield; g->spec = spec; g->ncorr = ncorr; g->safe = 1;
     g->dtsample = tsample / lvec;
     g->isample = (unsigned)(int)(g->dtsample / dt);
-    if ((int)(g->dtsample / dt) < 1) sep_error("sep_gh_init: isample is too small - CHECK lvec argument");
+    if ((int)(g->dtsample / dt) < 1) sep_error("%s: isample is too small - CHECK lvec argument", (char *)who);
     g->k = sep_vector((size_t)nwave);
-    g->field = calloc((size_t)GH_NFIELD * 2 * lvec * nwave, sizeof(double complex));
-    g->corr = calloc((size_t)GH_NCORR * lvec * nwave, sizeof(double complex));
-    FILE *fout = fopen("gh-wavevector.dat", "w");
-    if (!fout || !g->field || !g->corr) sep_error("sep_gh_init: Couldn't open file k.dat");
+    g->field = calloc((size_t)nfield * 2 * lvec * nwave, sizeof(double complex));
+    g->corr = calloc((size_t)ncorr * lvec * nwave, sizeof(double complex));
+    FILE *fout = fopen(kfile, "w");
+    if (!fout || !g->field || !g->corr) sep_error("%s: Couldn't open file k.dat", (char *)who);
     for (int n = 1; n <= nwave; n++) {
         g->k[n - 1] = 2 * SEP_PI * n / Ldir;
         fprintf(fout, "%f\n", g->k[n - 1]);
@@ -150,7 +143,63 @@ static sep_ghacc *gh_new(int lvec, double tsample, double dt, int nwave, double 
     return g;
 }
 
-static void sample_gh(sep_ghacc *g, seppart *atoms, sepsys *sys)
+static void fk_free(sep_fkacc *g)
+{
+    if (!g) return;
+    free(g->k); free(g->field); free(g->corr); free(g);
+}
+
+/* called after the fields of sample time g->fill were stored */
+static void fk_push(sep_fkacc *g, const char *who, double volume)
+{
+    if (++g->fill < g->lvec) return;
+    for (int c = 0; c < g->ncorr; c++) {
+        const fk_corr_spec *sp = &g->spec[c];
+        if (sp->unsafe_only && g->safe) continue;
+        for (unsigned k = 0; k < g->nwave; k++)
+            for (unsigned n = 0; n < g->lvec; n++) {
+                double complex sum = 0.0;
+                for (unsigned nn = 0; nn + n < g->lvec; nn++)
+                    sum += fk_field(g, sp->fa, sp->sa, sp->la ? nn + n : nn)[k] * fk_field(g, sp->fb, sp->sb, sp->lb ? nn + n : nn)[k];
+                g->corr[((size_t)c * g->lvec + n) * g->nwave + k] += sum;
+            }
+    }
+    g->nsample++;
+    for (int c = 0; c < g->ncorr; c++) {
+        FILE *fout = fopen(g->spec[c].file, "w");
+        if (!fout) sep_error("%s: Error opening files", (char *)who);
+        if (!(g->spec[c].unsafe_only && g->safe))
+            for (unsigned n = 0; n < g->lvec; n++) {
+                const double fac = 1.0 / (g->nsample * volume * (g->lvec - n));
+                fprintf(fout, "%f ", n * g->dtsample);
+                for (unsigned k = 0; k < g->nwave; k++) {
+                    const double complex v = g->corr[((size_t)c * g->lvec + n) * g->nwave + k] * fac;
+                    fprintf(fout, "%f %f ", creal(v), cimag(v));
+                }
+                fprintf(fout, "\n");
+            }
+        fclose(fout);
+    }
+    g->fill = 0;
+}
+
+/* atomic: density, transverse / longitudinal momentum, energy, auxiliary X (source/sepsampler.c:926-1107) */
+enum { GH_RHO, GH_TV, GH_LV, GH_E, GH_X, GH_NFIELD };
+static const fk_corr_spec GH_CORR[] = {
+    {"gh-trans-momentum-acf.dat", GH_TV, 1, 0, GH_TV, 0, 1, 0},
+    {"gh-long-momentum-acf.dat", GH_LV, 1, 0, GH_LV, 0, 1, 0},
+    {"gh-rho-acf.dat", GH_RHO, 0, 0, GH_RHO, 1, 1, 0},
+    {"gh-energy-acf.dat", GH_E, 0, 0, GH_E, 1, 1, 0},
+    {"gh-rho-energy-ccf.dat", GH_RHO, 0, 0, GH_E, 1, 1, 0},
+    {"gh-rho-long-momentum-ccf.dat", GH_RHO, 0, 0, GH_LV, 1, 1, 0},
+    {"gh-energy-long-momentum-ccf.dat", GH_E, 0, 0, GH_LV, 1, 1, 0},
+    {"gh-energy-rho-ccf.dat", GH_RHO, 0, 1, GH_E, 1, 0, 0},
+    {"gh-long-momentum-rho-ccf.dat", GH_RHO, 0, 1, GH_LV, 1, 0, 0},
+    {"gh-long-momentum-energy-ccf.dat", GH_E, 0, 1, GH_LV, 1, 0, 0},
+    {"gh-X-acf.dat", GH_X, 0, 0, GH_LV, 1, 1, 0},
+};
+
+static void sample_gh(sep_fkacc *g, seppart *atoms, sepsys *sys)
 {
     const int kdir = 1, tdir = 0;                 /* wave vector (0, k, 0), transverse direction x (:848-849) */
     const unsigned t = g->fill;
@@ -178,40 +227,70 @@ static void sample_gh(sep_ghacc *g, seppart *atoms, sepsys *sys)
             }
         }
         for (int f = 0; f < GH_NFIELD; f++)
-            for (int sgn = 0; sgn < 2; sgn++) gh_field(g, f, sgn, t)[n] = acc[f][sgn];
+            for (int sgn = 0; sgn < 2; sgn++) fk_field(g, f, sgn, t)[n] = acc[f][sgn];
     }
-    if (++g->fill < g->lvec) return;
-    for (int c = 0; c < GH_NCORR; c++) {
-        const gh_corr_spec *sp = &GH_CORR[c];
-        for (unsigned k = 0; k < g->nwave; k++)
-            for (unsigned n = 0; n < g->lvec; n++) {
-                double complex sum = 0.0;
-                for (unsigned nn = 0; nn + n < g->lvec; nn++)
-                    sum += gh_field(g, sp->fa, sp->sa, sp->la ? nn + n : nn)[k] * gh_field(g, sp->fb, sp->sb, sp->lb ? nn + n : nn)[k];
-                g->corr[((size_t)c * g->lvec + n) * g->nwave + k] += sum;
+    fk_push(g, "sep_gh_sampler", sys->volume);
+}
+
+/* molecular: centre-of-mass density / momentum / energy, angular momentum, dipole (source/sepsampler.c:1231-1415).
+ * The wave factor uses the WRAPPED centre of mass (mols[m].x[1], :1270) although xtrue is evaluated, and the
+ * momentum / angular-momentum cross function pairs s_z(+k) with m v_x(-k) (:1300-1301): both kept. */
+enum { MGH_RHO, MGH_TV, MGH_LV, MGH_E, MGH_TAV, MGH_LAV, MGH_VAV, MGH_DIP, MGH_X, MGH_NFIELD };
+static const fk_corr_spec MGH_CORR[] = {
+    {"mgh-trans-momentum-acf.dat", MGH_TV, 1, 0, MGH_TV, 0, 1, 0},
+    {"mgh-long-momentum-acf.dat", MGH_LV, 1, 0, MGH_LV, 0, 1, 0},
+    {"mgh-rho-acf.dat", MGH_RHO, 0, 0, MGH_RHO, 1, 1, 0},
+    {"mgh-energy-acf.dat", MGH_E, 0, 0, MGH_E, 1, 1, 0},
+    {"mgh-trans-angmomentum-acf.dat", MGH_TAV, 1, 0, MGH_TAV, 0, 1, 0},
+    {"mgh-long-angmomentum-acf.dat", MGH_LAV, 1, 0, MGH_LAV, 0, 1, 0},
+    {"mgh-momentum-angmomentum-ccf.dat", MGH_VAV, 1, 0, MGH_VAV, 0, 1, 0},
+    {"mgh-dipole-acf.dat", MGH_DIP, 1, 0, MGH_DIP, 0, 1, 0},
+    {"mgh-X-cf.dat", MGH_X, 1, 0, MGH_X, 0, 1, 1},
+};
+
+static void sample_mgh(sep_fkacc *g, seppart *atoms, sepmol *mols, sepsys *sys)
+{
+    const unsigned nmol = sys->molptr->num_mols;
+    const unsigned t = g->fill;
+    sep_mol_cm(atoms, mols, sys);
+    sep_mol_velcm(atoms, mols, sys);
+    sep_mol_eval_xtrue(atoms, mols, *sys);
+    sep_mol_spin(atoms, mols, sys, g->safe ? true : false);
+    sep_mol_dipoles(atoms, mols, sys);
+    double sumv2 = 0.0;
+    for (unsigned m = 0; m < nmol; m++)
+        for (int kk = 0; kk < 3; kk++) sumv2 += 0.5 * mols[m].m * sep_Sq(mols[m].v[kk]);
+    g->ncalls++;
+    g->avekin += sumv2 / ((double)nmol * g->ncalls);
+    for (unsigned n = 0; n < g->nwave; n++) {
+        double complex acc[MGH_NFIELD][2];
+        for (int f = 0; f < MGH_NFIELD; f++) acc[f][0] = acc[f][1] = 0.0;
+        for (unsigned m = 0; m < nmol; m++) {
+            const double mass = mols[m].m;
+            const double complex kf[2] = {cexp(I * g->k[n] * mols[m].x[1]), cexp(-I * g->k[n] * mols[m].x[1])};
+            double ekin = 0.0;
+            for (int kk = 0; kk < 3; kk++) ekin += 0.5 * mass * sep_Sq(mols[m].v[kk]);
+            for (int sgn = 0; sgn < 2; sgn++) {
+                acc[MGH_RHO][sgn] += mass * kf[sgn];
+                acc[MGH_TV][sgn] += mass * mols[m].v[0] * kf[sgn];
+                acc[MGH_LV][sgn] += mass * mols[m].v[1] * kf[sgn];
+                acc[MGH_E][sgn] += (ekin - g->avekin) * kf[sgn];
+                acc[MGH_TAV][sgn] += mols[m].s[2] * kf[sgn];
+                acc[MGH_LAV][sgn] += mols[m].s[1] * kf[sgn];
+                acc[MGH_VAV][sgn] += (sgn == 0 ? mols[m].s[2] : mass * mols[m].v[0]) * kf[sgn];
+                acc[MGH_DIP][sgn] += mols[m].pel[1] * kf[sgn];
+                if (!g->safe) acc[MGH_X][sgn] += mols[m].w[0] * kf[sgn];
             }
-    }
-    g->nsample++;
-    for (int c = 0; c < GH_NCORR; c++) {
-        FILE *fout = fopen(GH_CORR[c].file, "w");
-        if (!fout) sep_error("sep_gh_sampler: Error opening files");
-        for (unsigned n = 0; n < g->lvec; n++) {
-            const double fac = 1.0 / (g->nsample * sys->volume * (g->lvec - n));
-            fprintf(fout, "%f ", n * g->dtsample);
-            for (unsigned k = 0; k < g->nwave; k++) {
-                const double complex v = g->corr[((size_t)c * g->lvec + n) * g->nwave + k] * fac;
-                fprintf(fout, "%f %f ", creal(v), cimag(v));
-            }
-            fprintf(fout, "\n");
         }
-        fclose(fout);
+        for (int f = 0; f < MGH_NFIELD; f++)
+            for (int sgn = 0; sgn < 2; sgn++) fk_field(g, f, sgn, t)[n] = acc[f][sgn];
     }
-    g->fill = 0;
+    fk_push(g, "sep_mgh_sampler", sys->volume);
 }
 
 struct sep_sampler_set {
     sep_corr *sacf, *vacf, *msacf, *mvacf;
-    sep_ghacc *gh;
+    sep_fkacc *gh, *mgh;
     sep_profile *profs;
     sep_rdf *radial;
     sep_msdacc *msd;
@@ -324,7 +403,19 @@ void sep_add_sampler(sepsampler *sptr, const char *sampler, sepsys sys, int lvec
         if (!S->gh) {
             const double tsample = va_arg(args, double);
             const int nwave = va_arg(args, int);
-            S->gh = gh_new(lvec, tsample, sys.dt, nwave, sys.length[1]);
+            S->gh = fk_new("sep_gh_init", "gh-wavevector.dat", lvec, tsample, sys.dt, nwave, sys.length[1], GH_NFIELD, GH_CORR,
+                           (int)(sizeof GH_CORR / sizeof GH_CORR[0]));
+        }
+    } else if (!strcmp(sampler, "mgh")) {
+        if (!sptr->molptr) sep_error("sep_add_sampler: molpointer not initialized");
+        if (!S->mgh) {
+            const double tsample = va_arg(args, double);
+            const int nwave = va_arg(args, int);
+            const int safe = va_arg(args, int);
+            S->mgh = fk_new("sep_mgh_init", "mgh-wavevector.dat", lvec, tsample, sys.dt, nwave, sys.length[1], MGH_NFIELD, MGH_CORR,
+                            (int)(sizeof MGH_CORR / sizeof MGH_CORR[0]));
+            S->mgh->safe = safe ? 1 : 0;
+            if (!safe) sep_warning("ACHTUNG - unsafe mode for mgh sampler. Assuming uniaxial single component system");
         }
     } else if (!strcmp(sampler, "msd")) {
         if (!S->msd) {
@@ -334,9 +425,9 @@ void sep_add_sampler(sepsampler *sptr, const char *sampler, sepsys sys, int lvec
             S->msd = msd_new(lvec, tsample, nk, type, &sys);
         }
     } else {
-        static const char *later[] = {"mgh", "mprofs", "mcacf", "mavacf", "mmsd", "scatt"};
+        static const char *later[] = {"mprofs", "mcacf", "mavacf", "mmsd", "scatt"};
         int known = -1;
-        for (int k = 0; k < 6; k++) if (!strcmp(sampler, later[k])) known = k;
+        for (int k = 0; k < 5; k++) if (!strcmp(sampler, later[k])) known = k;
         if (known < 0) sep_error("sep_add_sampler: Sampler %s is not recognized", (char *)sampler);
         if (!(S->warned & (1u << known))) {
             sep_warning("sampler '%s' is not implemented in seplib-b200; it records nothing", (char *)sampler);
@@ -552,6 +643,7 @@ void sep_sample(seppart *pptr, sepsampler *sptr, sepret *ret, sepsys sys, unsign
     if (S->vacf && n % S->vacf->isample == 0) sample_vacf(S->vacf, pptr, &sys);
     if (S->msacf && n % S->msacf->isample == 0) sample_msacf(S->msacf, pptr, sptr->molptr, ret, &sys);
     if (S->gh && n % S->gh->isample == 0) sample_gh(S->gh, pptr, &sys);
+    if (S->mgh && n % S->mgh->isample == 0) sample_mgh(S->mgh, pptr, sptr->molptr, &sys);
     if (S->profs && n % S->profs->isample == 0) sample_profs(S->profs, pptr, &sys);
     if (S->mvacf && n % S->mvacf->isample == 0) sample_mvacf(S->mvacf, pptr, sptr->molptr, &sys);
     if (S->radial && n % (unsigned)S->radial->isample == 0) sample_radial(S->radial, pptr, &sys);
@@ -574,7 +666,7 @@ void sep_close_sampler(sepsampler *ptr)
     corr_free(S->sacf); corr_free(S->vacf); corr_free(S->msacf); corr_free(S->mvacf);
     if (S->profs) { free(S->profs->momc); free(S->profs->dens); free(S->profs->temp); free(S->profs->svel); free(S->profs); }
     if (S->radial) { free(S->radial->hist); free(S->radial); }
-    if (S->gh) { free(S->gh->k); free(S->gh->field); free(S->gh->corr); free(S->gh); }
+    fk_free(S->gh); fk_free(S->mgh);
     if (S->msd) {
         sep_msdacc *m = S->msd;
         free(m->time); free(m->msd); free(m->msdsq); free(m->k); free(m->fs); free(m->prev); free(m->pos0); free(m->cross);

@@ -161,6 +161,7 @@ def test_molecular_samplers_match_reference(libs, tmp_path):
             os.chdir(d)
             _add(lib, smp, b"msacf", s.sys, 8, C.c_double(0.04))
             _add(lib, smp, b"mvacf", s.sys, 8, C.c_double(0.04))
+            _add(lib, smp, b"mgh", s.sys, 8, C.c_double(0.04), C.c_int(2), C.c_int(1))
         fun = s.fun("sep_lj_shift")
         for step in range(90):
             ref.sep_reset_retval(s.R); ref.sep_reset_force(s.atoms, s.S); ref.sep_reset_force_mol(s.S)
@@ -176,4 +177,55 @@ def test_molecular_samplers_match_reference(libs, tmp_path):
     finally:
         os.chdir(cwd)
         s.close()
-    _compare_dirs(da, db, ["msacf.dat", "mvacf.dat"])
+    _compare_dirs(da, db, ["msacf.dat", "mvacf.dat", "mgh-wavevector.dat"] + MGH_FILES)
+
+
+# mgh-energy-acf.dat is not compared: the reference never initialises sepmgh.avekin (sep_mgh_init,
+# source/sepsampler.c:1110-1190, unlike sep_gh_init :835), so its energy fluctuation is taken about heap garbage
+MGH_FILES = ["mgh-trans-momentum-acf.dat", "mgh-long-momentum-acf.dat", "mgh-rho-acf.dat",
+             "mgh-trans-angmomentum-acf.dat", "mgh-long-angmomentum-acf.dat", "mgh-momentum-angmomentum-ccf.dat",
+             "mgh-dipole-acf.dat"]
+
+
+def test_mgh_unsafe_mode_on_water_matches_reference(libs, tmp_path):
+    """charged, non-linear molecules: dipoles and angular velocities (w = I^-1 s) enter the 'unsafe' mgh sampler"""
+    ref, ours = libs
+    da, db = str(tmp_path / "ref"), str(tmp_path / "ours")
+    os.makedirs(da); os.makedirs(db)
+    g = np.load(os.path.join(cm.GOLDEN, "water_dense_n648.npz"))
+    top = str(tmp_path / "water.top")
+    with open(top, "w") as fh:
+        fh.write("[ bonds ]\n;generated\n")
+        for (a, b, t) in g["blist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {t}\n")
+        fh.write("\n[ angles ]\n;generated\n")
+        for (a, b, c, t) in g["alist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {c} {t}\n")
+    s = cm.ApiSystem(ref, g["x0"], g["L"], 2.9, 5.0e-4, update=capi.SEP_BRUTE, v=g["v0"], types=g["type"], m=g["m"], z=g["z"], nneighb=0)
+    ref.sep_read_topology_file(s.atoms, top.encode(), s.S, b"q")
+    mols = ref.sep_init_mol(s.atoms, s.S)
+    _bind(ref, RefSampler); _bind(ours, OurSampler)
+    alpha = (C.c_double * 3)(0.1, 0.0, 0.0)
+    cwd = os.getcwd()
+    try:
+        sr, so = ref.sep_init_sampler(), ours.sep_init_sampler()
+        ref.sep_add_mol_sampler(C.byref(sr), mols); ours.sep_add_mol_sampler(C.byref(so), mols)
+        for lib, smp, d in ((ref, sr, da), (ours, so, db)):
+            os.chdir(d)
+            _add(lib, smp, b"mgh", s.sys, 6, C.c_double(0.015), C.c_int(2), C.c_int(0))
+        fun = s.fun("sep_lj_shift")
+        for step in range(40):
+            ref.sep_reset_retval(s.R); ref.sep_reset_force(s.atoms, s.S)
+            ref.sep_force_pairs(s.atoms, b"OO", 2.5, fun, s.S, s.R, 3)
+            ref.sep_stretch_harmonic(s.atoms, 0, 0.316, 68421.0, s.S, s.R)
+            ref.sep_angle_cossq(s.atoms, 0, 1.97, 490.0, s.S, s.R)
+            ref.sep_coulomb_sf(s.atoms, 2.9, s.S, s.R, 3)
+            ref.sep_nosehoover(s.atoms, 3.81, alpha, 0.01, s.S)
+            ref.sep_leapfrog(s.atoms, s.S, s.R)
+            os.chdir(da); ref.sep_sample(s.atoms, C.byref(sr), s.R, s.sys, step)
+            os.chdir(db); ours.sep_sample(s.atoms, C.byref(so), s.R, s.sys, step)
+        ours.sep_close_sampler(C.byref(so))
+    finally:
+        os.chdir(cwd)
+        s.close()
+    _compare_dirs(da, db, ["mgh-wavevector.dat"] + MGH_FILES + ["mgh-X-cf.dat"])
