@@ -154,7 +154,7 @@ SEP_SYMBOLS = [
     "sep_gpu_sync", "sep_gpu_invalidate", "sep_gpu_sync_scalars", "sep_gpu_export_neighb",
     "sep_gpu_handle", "sep_gpu_set_dpd_seed",
     "sep_compress_box_dir", "sep_compress_box_dir_length", "sep_berendsen", "sep_berendsen_iso", "sep_relax_temp",
-    "sep_spring_x0", "sep_force_x0",
+    "sep_spring_x0", "sep_force_x0", "sep_mol_eval_xtrue", "sep_mol_spin", "sep_mol_dipoles",
 ]
 
 
