@@ -260,6 +260,10 @@ void sep_compress_box_dir_length(sepatom *ptr, double length, double xi, int dir
 void sep_berendsen(sepatom *ptr, double Pd, double beta, sepret *ret, sepsys *sys);
 void sep_berendsen_iso(sepatom *ptr, double Pd, double beta, sepret *ret, sepsys *sys);
 void sep_relax_temp(seppart *ptr, char type, double Td, double tau, sepsys *sys);
+double sep_randn(void);
+void sep_fp(seppart *ptr, double temp_desired, sepsys *sys, sepret *retval);
+void sep_langevinGJF(sepatom *ptr, double temp0, double alpha, sepsys *sys, sepret *retval);
+void sep_set_ldiff(sepatom *ptr, char type, double ldiff, sepsys sys);
 double sep_spring_x0(double r2, char opt);
 void sep_force_x0(seppart *ptr, char type, double (*fun)(double, char), sepsys *sys);
 void sep_set_charge(seppart *ptr, char type, double z, sepsys sys);

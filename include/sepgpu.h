@@ -177,6 +177,12 @@ int sepgpu_relax_temp(sepgpu_ctx *ctx, const sepgpu_sys *sys, char type, double 
 /* sep_force_x0 with sep_spring_x0 (source/sepmisc.c:167-181, 645-670): harmonic tether of one type to SEPGPU_F_X0 */
 int sepgpu_force_x0(sepgpu_ctx *ctx, const sepgpu_sys *sys, char type, double kspring);
 
+/* sep_fp (source/sepintgr.c:235-293) and sep_langevinGJF (:89-146).  noise4: HOST array, four doubles per atom
+ * {g0, g1, g2, ldiff}: the Gaussian numbers of this step in the reference's drawing order (atom-major, component-
+ * minor) and the atom's seppart.ldiff (used by sep_fp only). */
+int sepgpu_fp(sepgpu_ctx *ctx, const sepgpu_sys *sys, double temp, const double *noise4);
+int sepgpu_langevin_gjf(sepgpu_ctx *ctx, const sepgpu_sys *sys, double temp, double alpha, const double *noise4);
+
 /* ---- results -------------------------------------------------------------------------------------- */
 /* stream-synchronising read of the scalar block */
 int sepgpu_read_scalars(sepgpu_ctx *ctx, sepgpu_scalars *out);

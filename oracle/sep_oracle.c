@@ -652,3 +652,83 @@ void orc_berendsen(int n, double *x, double Pd, double beta, double p, double dt
             lsub[k] = len[k] / nsub[k];
         }
 }
+
+/* ---- stochastic integrators ------------------------------------------------------------------------------------ */
+static int randn_cached = 0;
+static double randn_spare = 0.0;
+
+void orc_randn_reset(void) { randn_cached = 0; }
+
+double orc_randn(void)
+{
+    if (randn_cached) { randn_cached = 0; return randn_spare; }
+    double x1, x2, w;
+    do {
+        x1 = 2.0 * (rand() / (RAND_MAX + 1.0)) - 1.0;          /* sep_rand(), include/sepmisc.h:63 */
+        x2 = 2.0 * (rand() / (RAND_MAX + 1.0)) - 1.0;
+        w = x1 * x1 + x2 * x2;
+    } while (w >= 1.0 || w == 0.0);
+    w = sqrt((-2.0 * log(w)) / w);
+    randn_spare = x2 * w;
+    randn_cached = 1;
+    return x1 * w;
+}
+
+int orc_fp(int n, double *x, double *v, const double *f, const double *m, const double *ldiff, double *xn,
+           int *cross_neighb, int *crossings, const double len[3], double dt, double temp, double skin,
+           double *max_dist2, orc_ret *ret)
+{
+    const double fac = sqrt(1.0 / 12.0);
+    double sumekin = 0.0;
+    for (int i = 0; i < n; i++) {
+        double d2 = 0.0;
+        const double im = 1.0 / m[i];
+        const double fric = temp / ldiff[i];
+        const double gaussfac = sqrt(24 * temp * fric / dt);
+        for (int k = 0; k < 3; k++) {
+            const int q = 3 * i + k;
+            const double a = orc_randn() * fac * gaussfac;
+            x[q] += dt * v[q];
+            v[q] += im * dt * (f[q] - fric * v[q] + a);
+            if (x[q] > len[k]) { x[q] -= len[k]; cross_neighb[q]++; crossings[q]++; }
+            else if (x[q] < 0.0) { x[q] += len[k]; cross_neighb[q]--; crossings[q]--; }
+            sumekin += v[q] * v[q] * m[i];
+            const double ri = (x[q] + cross_neighb[q] * len[k]) - xn[q];
+            d2 += ri * ri;
+        }
+        if (d2 > *max_dist2) *max_dist2 = d2;
+        for (int k = 0; k < 3; k++)
+            for (int kk = 0; kk < 3; kk++) ret->kin_P[3 * k + kk] += v[3 * i + k] * v[3 * i + kk] * m[i];
+    }
+    ret->ekin += 0.5 * sumekin;
+    return trigger(n, x, xn, cross_neighb, skin, *max_dist2);
+}
+
+int orc_langevin_gjf(int n, double *x, double *v, const double *f, const double *m, double *a, double *prevf, double *randn,
+                     double *xn, int *cross_neighb, int *crossings, const double len[3], double dt, double temp,
+                     double alpha, double skin, double *max_dist2, orc_ret *ret)
+{
+    const double cc = exp(-alpha * dt);
+    double sumekin = 0.0;
+    for (int i = 0; i < n; i++) {
+        const double mass = m[i], imass = 1.0 / mass, imass2 = 0.5 * imass;
+        const double fac = sqrt(temp * (1.0 - cc * cc));
+        const double c = alpha * dt * imass2;
+        const double ca = (1.0 - c) / (1.0 + c), cb = 1.0 / (1.0 + c);
+        for (int k = 0; k < 3; k++) {
+            const int q = 3 * i + k;
+            v[q] = ca * v[q] + dt * imass2 * (ca * prevf[q] + f[q]) + cb * imass * randn[q];
+            a[q] = f[q] * imass;
+            prevf[q] = f[q];
+            sumekin += v[q] * v[q] * mass;
+            randn[q] = fac * orc_randn();
+            x[q] += cb * dt * v[q] + cb * dt * dt * imass2 * f[q] + cb * dt * imass2 * randn[q];
+        }
+        const double d2 = periodic(&x[3 * i], &xn[3 * i], &cross_neighb[3 * i], &crossings[3 * i], len);
+        if (d2 > *max_dist2) *max_dist2 = d2;
+        for (int k = 0; k < 3; k++)
+            for (int kk = 0; kk < 3; kk++) ret->kin_P[3 * k + kk] += v[3 * i + k] * v[3 * i + kk] * mass;
+    }
+    ret->ekin += 0.5 * sumekin;
+    return trigger(n, x, xn, cross_neighb, skin, *max_dist2);
+}

@@ -133,6 +133,19 @@ int orc_compress_box(int n, double *x, double rhoD, double xi, double len[3], in
 void orc_berendsen(int n, double *x, double Pd, double beta, double p, double dt, int iso, double len[3],
                    int nsub[3], double lsub[3], double *volume, double cf, int list_mode);
 
+/* sep_randn (source/sepmisc.c:1131-1160): polar Box-Muller on glibc rand(), second deviate cached.
+ * orc_randn_reset() drops the cached deviate (a fresh process in the reference). */
+double orc_randn(void);
+void orc_randn_reset(void);
+/* sep_fp, source/sepintgr.c:235-293 (state as orc_leapfrog; ldiff[n]; draws 3n numbers from orc_randn) */
+int orc_fp(int n, double *x, double *v, const double *f, const double *m, const double *ldiff, double *xn,
+           int *cross_neighb, int *crossings, const double len[3], double dt, double temp, double skin,
+           double *max_dist2, orc_ret *ret);
+/* sep_langevinGJF, source/sepintgr.c:89-146 (prevf[3n], randn[3n] carried between calls) */
+int orc_langevin_gjf(int n, double *x, double *v, const double *f, const double *m, double *a, double *prevf, double *randn,
+                     double *xn, int *cross_neighb, int *crossings, const double len[3], double dt, double temp,
+                     double alpha, double skin, double *max_dist2, orc_ret *ret);
+
 /* sep_dpdforce_neighb (source/sepprfrc.c:1007-1133) with the reference's glibc rand() stream
  * replaced by the product's counter-based pair generator (see orc_dpd_uniform); the reference's
  * stream cannot be reproduced by any parallel evaluation order. */

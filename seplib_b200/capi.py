@@ -128,7 +128,7 @@ SEPGPU_SYMBOLS = [
     "sepgpu_read_scalars", "sepgpu_sync", "sepgpu_get_pairs", "sepgpu_request_rebuild",
     "sepgpu_set_option", "sepgpu_timer_start", "sepgpu_timer_stop", "sepgpu_kernel_time",
     "sepgpu_peak_fp64", "sepgpu_peak_copy", "sepgpu_flush_l2",
-    "sepgpu_fij_enable", "sepgpu_fij_reset", "sepgpu_fij_get", "sepgpu_scale_box", "sepgpu_relax_temp", "sepgpu_force_x0",
+    "sepgpu_fij_enable", "sepgpu_fij_reset", "sepgpu_fij_get", "sepgpu_scale_box", "sepgpu_relax_temp", "sepgpu_force_x0", "sepgpu_fp", "sepgpu_langevin_gjf",
     "sepgpu_dd_unique_id", "sepgpu_dd_init", "sepgpu_dd_set_owned", "sepgpu_dd_layers",
 ]
 
@@ -155,6 +155,7 @@ SEP_SYMBOLS = [
     "sep_gpu_handle", "sep_gpu_set_dpd_seed",
     "sep_compress_box_dir", "sep_compress_box_dir_length", "sep_berendsen", "sep_berendsen_iso", "sep_relax_temp",
     "sep_spring_x0", "sep_force_x0", "sep_mol_eval_xtrue", "sep_mol_spin", "sep_mol_dipoles",
+    "sep_randn", "sep_fp", "sep_langevinGJF", "sep_set_ldiff",
 ]
 
 
@@ -201,6 +202,9 @@ def declare_sep_api(lib):
     lib.sep_relax_temp.argtypes = [P, C.c_char, C.c_double, C.c_double, S]
     lib.sep_force_x0.argtypes = [P, C.c_char, C.c_void_p, S]
     lib.sep_set_x0.argtypes = [P, C.c_int]
+    lib.sep_fp.argtypes = [P, C.c_double, S, R]
+    lib.sep_langevinGJF.argtypes = [P, C.c_double, C.c_double, S, R]
+    lib.sep_randn.restype = C.c_double
     lib.sep_reset_momentum.argtypes = [P, C.c_char, S]
     lib.sep_set_skin.argtypes = [S, C.c_double]
     lib.sep_set_omp.argtypes = [C.c_uint, S]
@@ -264,6 +268,8 @@ def load():
     lib.sepgpu_scale_box.argtypes = [ctx, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.sepgpu_relax_temp.argtypes = [ctx, C.POINTER(GpuSys), C.c_char, C.c_double, C.c_double, C.POINTER(C.c_double)]
     lib.sepgpu_force_x0.argtypes = [ctx, C.POINTER(GpuSys), C.c_char, C.c_double]
+    lib.sepgpu_fp.argtypes = [ctx, C.POINTER(GpuSys), C.c_double, C.c_void_p]
+    lib.sepgpu_langevin_gjf.argtypes = [ctx, C.POINTER(GpuSys), C.c_double, C.c_double, C.c_void_p]
     lib.sepgpu_fij_enable.argtypes = [ctx, C.c_int]
     lib.sepgpu_fij_reset.argtypes = [ctx]
     lib.sepgpu_fij_get.argtypes = [ctx, C.c_void_p]

@@ -82,6 +82,7 @@ struct sepgpu_ctx {
 
     d4 *x4, *v4, *f4, *xn4, *pv4, *pa4;
     d4 *x0;                // tether positions (sep_set_x0), allocated on first upload
+    d4 *prevf4, *randn4;   // sep_langevinGJF: previous force and previous noise per atom, allocated on first use
     i4 *cr4;
     int *crossings;        // 3n
     double *z;             // charges

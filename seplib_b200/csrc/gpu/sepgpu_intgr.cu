@@ -358,6 +358,162 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     return 0;
 }
 
+// ---- stochastic integrators ---------------------------------------------------------
+// sep_fp (Brownian dynamics at the Fokker-Planck level, source/sepintgr.c:235-293) and sep_langevinGJF
+// (Gronbech-Jensen/Farago Langevin integrator, :89-146).  Both draw one Gaussian number per atom and component from
+// the reference's serial generator (sep_randn on glibc rand(), source/sepmisc.c:1131-1160); the HOST layer produces
+// that stream in the reference's order and hands it over as four doubles per atom {g0, g1, g2, ldiff}, so the
+// device arithmetic sees exactly the numbers the reference would (32 B per atom per step over PCIe -- these
+// integrators are for small systems).  GJF keeps its previous force and previous noise per atom on the device.
+template <bool GJF>
+__global__ void __launch_bounds__(INTGR_BLOCK)
+k_integrate_stoch(d4 *__restrict__ x4, d4 *__restrict__ v4, const d4 *__restrict__ f4, const d4 *__restrict__ xn4,
+                  i4 *__restrict__ cr4, int *__restrict__ crossings, const int *__restrict__ rank, d4 *__restrict__ xs,
+                  const d4 *__restrict__ noise, d4 *__restrict__ prevf4, d4 *__restrict__ randn4,
+                  IntgrParams P, double temp, double alpha, double *__restrict__ partial)
+{
+    __shared__ double red[SEPGPU_NPART_I * (INTGR_BLOCK / 32)];
+    double acc[SEPGPU_NPART_I];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_I; q++) acc[q] = 0.0;
+    const double dt = P.dt;
+    const double cc = exp(-alpha * dt);
+
+    for (int i = blockIdx.x * INTGR_BLOCK + threadIdx.x; i < P.n; i += gridDim.x * INTGR_BLOCK) {
+        d4 x = x4[i], v = v4[i], f;
+        if (P.f_zero) { f.x = f.y = f.z = f.w = 0.0; } else f = f4[i];
+        const double m = v.w;
+        const d4 g = noise[i];
+        i4 cr = cr4[i];
+        const d4 xn = xn4[i];
+        int clx, cly, clz; unpack_cl(cr.w, clx, cly, clz);
+        int tx = 0, ty = 0, tz = 0; bool changed = false;
+        double d2 = 0.0;
+        if (!GJF) {
+            const double im = 1.0 / m;
+            const double fric = temp / g.w;                              // :245  (g.w = ldiff)
+            const double gaussfac = sqrt(24 * temp * fric / dt);         // :246
+            const double fac = sqrt(1.0 / 12.0);
+            const double ax = g.x * fac * gaussfac, ay = g.y * fac * gaussfac, az = g.z * fac * gaussfac;   // :252
+            x.x += dt * v.x; v.x += im * dt * (f.x - fric * v.x + ax);   // :254-255
+            d2 += periodic_1d(x.x, P.Lx, cr.x, clx, tx, changed, xn.x);
+            x.y += dt * v.y; v.y += im * dt * (f.y - fric * v.y + ay);
+            d2 += periodic_1d(x.y, P.Ly, cr.y, cly, ty, changed, xn.y);
+            x.z += dt * v.z; v.z += im * dt * (f.z - fric * v.z + az);
+            d2 += periodic_1d(x.z, P.Lz, cr.z, clz, tz, changed, xn.z);
+        } else {
+            const double imass = 1.0 / m, imass2 = 0.5 * imass;
+            const double fac = sqrt(temp * (1.0 - cc * cc));             // :100
+            const double c_ = alpha * dt * imass2;
+            const double a = (1.0 - c_) / (1.0 + c_), b = 1.0 / (1.0 + c_);
+            d4 pf = prevf4[i], rn = randn4[i];
+            v.x = a * v.x + dt * imass2 * (a * pf.x + f.x) + b * imass * rn.x;     // :108
+            v.y = a * v.y + dt * imass2 * (a * pf.y + f.y) + b * imass * rn.y;
+            v.z = a * v.z + dt * imass2 * (a * pf.z + f.z) + b * imass * rn.z;
+            pf.x = f.x; pf.y = f.y; pf.z = f.z;                                    // :111
+            rn.x = fac * g.x; rn.y = fac * g.y; rn.z = fac * g.z;                   // :115
+            x.x += b * dt * v.x + b * dt * dt * imass2 * f.x + b * dt * imass2 * rn.x;   // :117
+            x.y += b * dt * v.y + b * dt * dt * imass2 * f.y + b * dt * imass2 * rn.y;
+            x.z += b * dt * v.z + b * dt * dt * imass2 * f.z + b * dt * imass2 * rn.z;
+            prevf4[i] = pf; randn4[i] = rn;
+            d2 += periodic_1d(x.x, P.Lx, cr.x, clx, tx, changed, xn.x);
+            d2 += periodic_1d(x.y, P.Ly, cr.y, cly, ty, changed, xn.y);
+            d2 += periodic_1d(x.z, P.Lz, cr.z, clz, tz, changed, xn.z);
+        }
+        acc[0] += v.x * v.x * m; acc[0] += v.y * v.y * m; acc[0] += v.z * v.z * m;     // :258 / :113
+        acc[1] += v.x * v.x * m; acc[2] += v.x * v.y * m; acc[3] += v.x * v.z * m;
+        acc[4] += v.y * v.y * m; acc[5] += v.y * v.z * m; acc[6] += v.z * v.z * m;
+        acc[7] = fmax(acc[7], d2);
+        acc[8] += (v.x * v.x + v.y * v.y + v.z * v.z) * m;
+        acc[9] += v.x * m; acc[10] += v.y * m; acc[11] += v.z * m;
+        x4[i] = x; v4[i] = v;
+        if (changed) {
+            cr.w = pack_cl(clx, cly, clz);
+            cr4[i] = cr;
+            if (tx) crossings[3 * i] += tx;
+            if (ty) crossings[3 * i + 1] += ty;
+            if (tz) crossings[3 * i + 2] += tz;
+        }
+        if (P.write_xs) {
+            d4 u; u.x = x.x + clx * P.Lx; u.y = x.y + cly * P.Ly; u.z = x.z + clz * P.Lz; u.w = x.w;
+            xs[rank[i]] = u;
+        }
+    }
+    const double mymax = acc[7];
+    acc[7] = 0.0;
+    block_sum<SEPGPU_NPART_I, INTGR_BLOCK>(acc, red);
+    __syncthreads();
+    double wm = warp_max(mymax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int w = 0; w < INTGR_BLOCK / 32; w++) mx = fmax(mx, red[w]);
+        acc[7] = mx;
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_I; q++) partial[blockIdx.x * SEPGPU_NPART_I + q] = acc[q];
+    }
+}
+
+// noise4: host array, 4 doubles per atom {g0, g1, g2, ldiff}
+static int run_stochastic(sepgpu_ctx *c, const sepgpu_sys *sys, bool gjf, double temp, double alpha, const double *noise4)
+{
+    if (c->dd) { sepgpu_set_error("stochastic integrators are not available in decomposed runs"); return SEPGPU_ESTATE; }
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = sepgpu_apply_pending(c);
+    if (rc) return rc;
+    const size_t bytes = sizeof(d4) * (size_t)c->n_own;
+    if ((rc = sepgpu_ensure_stage(c, bytes))) return rc;
+    memcpy(c->stage, noise4, bytes);
+    CUDA_TRY(cudaMemcpyAsync(c->dstage, c->stage, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (gjf && !c->prevf4) {
+        CUDA_TRY(cudaMalloc((void **)&c->prevf4, sizeof(d4) * (size_t)c->ncap));
+        CUDA_TRY(cudaMalloc((void **)&c->randn4, sizeof(d4) * (size_t)c->ncap));
+        CUDA_TRY(cudaMemsetAsync(c->prevf4, 0, sizeof(d4) * (size_t)c->ncap, c->stream));   // sep_init zeroes both, source/sepinit.c:45-46
+        CUDA_TRY(cudaMemsetAsync(c->randn4, 0, sizeof(d4) * (size_t)c->ncap, c->stream));
+    }
+    IntgrParams P;
+    P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
+    P.dt = sys->dt; P.skin = sys->skin; P.n = c->n_own;
+    P.alpha_slot = -1; P.alpha_type = -1;
+    P.f_zero = c->f_zero ? 1 : 0;
+    P.write_xs = (sys->neighb_update != 0 && c->list_valid) ? 1 : 0;
+    long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
+    const int grid = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
+    if (gjf)
+        k_integrate_stoch<true><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings, c->rank, c->xs,
+            (const d4 *)c->dstage, c->prevf4, c->randn4, P, temp, alpha, c->partial);
+    else
+        k_integrate_stoch<false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings, c->rank, c->xs,
+            (const d4 *)c->dstage, NULL, NULL, P, temp, alpha, c->partial);
+    const int resets = (c->ret_reset_pending ? 1 : 0) | (c->maxd_reset_pending ? 2 : 0);
+    c->ret_reset_pending = false; c->maxd_reset_pending = false;
+    k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 0, NULL, resets, 0, 1);
+    KERNEL_CHECK();
+    c->mv2_valid = true;
+    if (!P.write_xs) c->xs_current = false;
+    CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->scal_host->neighb_flag) {
+        k_set_xn<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n_own);
+        KERNEL_CHECK();
+        c->list_valid = false;
+    }
+    return 0;
+}
+
+extern "C" int sepgpu_fp(sepgpu_ctx *c, const sepgpu_sys *sys, double temp, const double *noise4)
+{
+    if (!c || !sys || !noise4) return SEPGPU_EINVAL;
+    return run_stochastic(c, sys, false, temp, 0.0, noise4);
+}
+
+extern "C" int sepgpu_langevin_gjf(sepgpu_ctx *c, const sepgpu_sys *sys, double temp, double alpha, const double *noise4)
+{
+    if (!c || !sys || !noise4) return SEPGPU_EINVAL;
+    return run_stochastic(c, sys, true, temp, alpha, noise4);
+}
+
 extern "C" int sepgpu_leapfrog(sepgpu_ctx *c, const sepgpu_sys *sys)
 {
     if (!c || !sys) return SEPGPU_EINVAL;

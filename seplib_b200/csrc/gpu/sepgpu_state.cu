@@ -120,6 +120,8 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->fij) cudaFree(c->fij);
     if (c->cls) cudaFree(c->cls);
     if (c->x0) cudaFree(c->x0);
+    if (c->prevf4) cudaFree(c->prevf4);
+    if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
                     c->rank, c->cell_of, c->cell_cnt, c->cell_start, c->tmp_slot, c->nbr, c->cnt,

@@ -126,7 +126,7 @@ void sepb_unregister(seppart *atoms)
             sep_binding *b = *pp;
             *pp = b->next;
             if (b->gpu) sepgpu_destroy(b->gpu);
-            free(b->blengths_host); free(b->angles_host); free(b->dihedrals_host);
+            free(b->blengths_host); free(b->angles_host); free(b->dihedrals_host); free(b->noise);
             free(b);
             return;
         }

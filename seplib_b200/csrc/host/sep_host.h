@@ -36,6 +36,7 @@ typedef struct sep_binding {
     int dpd_state_on_device;
     int fij_on;                  /* device molecule-molecule force table enabled */
     int x0_on_device;            /* tether positions (seppart.x0) are mirrored on the device */
+    double *noise; size_t noise_cap;   /* per-step Gaussian numbers for sep_fp / sep_langevinGJF */
     double *alpha_ptr[4];       /* caller-owned thermostat multipliers mapped to device slots */
     double alpha_seen[4];
     unsigned long long dpd_calls;

@@ -68,6 +68,11 @@ def oracle():
     lib.orc_leapfrog.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, vp, C.POINTER(OrcRet)]
     lib.orc_verlet_dpd.restype = i32
     lib.orc_verlet_dpd.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, i32, dbl, vp, C.POINTER(OrcRet)]
+    lib.orc_randn.restype = dbl
+    lib.orc_fp.restype = i32
+    lib.orc_fp.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, vp, C.POINTER(OrcRet)]
+    lib.orc_langevin_gjf.restype = i32
+    lib.orc_langevin_gjf.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, C.POINTER(OrcRet)]
     lib.orc_relax_temp.restype = dbl
     lib.orc_relax_temp.argtypes = [i32, vp, vp, vp, C.c_char, dbl, dbl, dbl]
     lib.orc_force_x0.argtypes = [i32, vp, vp, vp, C.c_char, vp, vp]
@@ -516,4 +521,52 @@ def oracle_slit(x, v, L, steps=30):
         o.orc.orc_relax_temp(o.n, ptr(o.v), ptr(o.m), ptr(o.types), b"W", 1.4, 0.01, o.dt)
         tr.append((o.ret.epot, o.ret.ekin))
     rec = o.record(); rec["traj"] = np.array(tr); rec["types"] = types
+    return rec
+
+
+# ---- stochastic integrators (section 8f rank 3): sep_fp (prg9's loop) and sep_langevinGJF --------------------------
+_libc = C.CDLL(None)
+STOCH_SEED = 20261017
+
+
+def drive_stochastic(lib, x, v, L, which, steps=30):
+    """prg9's loop (reference prgs/prg9.c:41-63): brute-force pair forces with cutoff SEP_WCACF, then sep_fp -- or
+    sep_langevinGJF with friction 1.0 -- at T = 1.12.  The C library's rand() is seeded right before the loop; the
+    library under test draws its Gaussian numbers from it."""
+    cf = 1.12246204830937
+    s = ApiSystem(lib, x, L, cf, 0.001, v=v, update=capi.SEP_BRUTE, nneighb=0)
+    fun = s.fun("sep_lj_shift")
+    _libc.srand(STOCH_SEED)
+    tr = []
+    for n in range(steps):
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+        if which == "fp":
+            lib.sep_fp(s.atoms, 1.12, s.S, s.R)
+        else:
+            lib.sep_langevinGJF(s.atoms, 1.12, 1.0, s.S, s.R)
+        tr.append((s.ret.epot, s.ret.ekin, s.sys.tnow))
+    rec = _final(s, {"traj": np.array(tr)})
+    s.close()
+    return rec
+
+
+def oracle_stochastic(x, v, L, which, steps=30):
+    cf = 1.12246204830937
+    o = OracleLoop(x, v, L, cf, 0.001, list_mode=False)
+    ldiff = np.ones(o.n); prevf = np.zeros((o.n, 3)); randn = np.zeros((o.n, 3))
+    o.orc.orc_randn_reset()
+    _libc.srand(STOCH_SEED)
+    tr, tnow = [], 0.0
+    for n in range(steps):
+        o.reset(); o.pair_force(b"AA", cf, POT_LJ_SHIFT)
+        if which == "fp":
+            o.orc.orc_fp(o.n, ptr(o.x), ptr(o.v), ptr(o.f), ptr(o.m), ptr(ldiff), ptr(o.xn), ptr(o.cn), ptr(o.cr), ptr(o.len),
+                         o.dt, 1.12, o.skin, C.byref(o.maxd2), C.byref(o.ret))
+        else:
+            o.orc.orc_langevin_gjf(o.n, ptr(o.x), ptr(o.v), ptr(o.f), ptr(o.m), ptr(o.a), ptr(prevf), ptr(randn), ptr(o.xn), ptr(o.cn),
+                                   ptr(o.cr), ptr(o.len), o.dt, 1.12, 1.0, o.skin, C.byref(o.maxd2), C.byref(o.ret))
+            tnow += o.dt
+        tr.append((o.ret.epot, o.ret.ekin, tnow))
+    rec = o.record(); rec["traj"] = np.array(tr)
     return rec

@@ -297,6 +297,11 @@ def next_rows_fixture(lib):
         out["ber_" + k] = val
     for k, val in cm.drive_slit(lib, x, v, L).items():
         out["slit_" + k] = val
+    # stochastic integrators: each in its own process-like state -- the reference's sep_randn caches a deviate, so
+    # the two runs draw an even number of deviates (3 * 216 * 30) and leave the cache empty for the next
+    for which in ("fp", "gjf"):
+        for k, val in cm.drive_stochastic(lib, xb, vb, Lb, which).items():
+            out[which + "_" + k] = val
     np.savez_compressed(os.path.join(HERE, "next_rows.npz"), **out)
     print("next_rows: compress L", out["compress_traj"][0, 2], "->", out["compress_traj"][-1, 2], "cells", out["compress_traj"][0, 3], "->",
           out["compress_traj"][-1, 3], "| berendsen Lz", out["ber_traj"][0, 3], "->", out["ber_traj"][-1, 3], "p", out["ber_traj"][-1, 2],

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs one of the section-8f loops of tests/common.py on libsep.so in its own process and saves what it recorded:
-    python tests/next_driver.py <compress|ber|beriso|slit> <sync mode 0|1> <out.npz>
+    python tests/next_driver.py <compress|ber|beriso|slit|fp|gjf> <sync mode 0|1> <out.npz>
 A separate process because the sep_* API reports errors the way the reference does -- sep_error() prints and
 exit()s -- which must fail one test, not end the pytest run."""
 import os
@@ -28,6 +28,8 @@ def main():
         rec = cm.drive_berendsen(lib, g["c_x0"], g["c_v0"], float(g["c_L"]), steps=12, iso=True, update=capi.SEP_LLIST_NEIGHBLIST)
     elif what == "slit":
         rec = cm.drive_slit(lib, g["c_x0"], g["c_v0"], float(g["c_L"]))
+    elif what in ("fp", "gjf"):
+        rec = cm.drive_stochastic(lib, g["b_x0"], g["b_v0"], float(g["b_L"]), what)
     else:
         raise SystemExit("unknown scenario " + what)
     np.savez(out, **rec)

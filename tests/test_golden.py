@@ -406,3 +406,30 @@ def test_oracle_next_rows_golden():
         assert np.abs(rec["x"] - g[name + "_x"]).max() <= 1e-10, (name, np.abs(rec["x"] - g[name + "_x"]).max())
         assert np.abs(rec["v"] - g[name + "_v"]).max() <= 1e-10, name
         assert np.array_equal(rec["nsubbox"], g[name + "_nsubbox"]) and abs(rec["volume"] - float(g[name + "_volume"])) <= 1e-12 * rec["volume"]
+
+
+def test_oracle_stochastic_integrators_golden():
+    """sep_fp and sep_langevinGJF on the oracle (orc_fp, orc_langevin_gjf, orc_randn on the same glibc rand() stream)
+    against the reference's recorded 30-step loops: identical noise, so the trajectories agree to rounding."""
+    g = load("next_rows.npz")
+    for which in ("fp", "gjf"):
+        rec = cm.oracle_stochastic(g["b_x0"], g["b_v0"], float(g["b_L"]), which)
+        ref = g[which + "_traj"]
+        scale = np.maximum(np.abs(ref).max(axis=0), 1e-300)
+        assert (np.abs(rec["traj"] - ref).max(axis=0) <= 1e-11 * scale).all(), (which, np.abs(rec["traj"] - ref).max(axis=0) / scale)
+        assert np.abs(rec["x"] - g[which + "_x"]).max() <= 1e-11, which
+        assert np.abs(rec["v"] - g[which + "_v"]).max() <= 1e-11, which
+
+
+def test_host_randn_stream_equals_the_reference():
+    """libsep.so's sep_randn (host, feeds the device integrators) reproduces the reference's Gaussian stream"""
+    ref = cm.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/libsep_ref.so not built")
+    ours = capi.load()
+    ref.sep_randn.restype = C.c_double
+    ours.sep_randn.restype = C.c_double
+    libc = C.CDLL(None)
+    libc.srand(99); a = [ref.sep_randn() for _ in range(2000)]
+    libc.srand(99); b = [ours.sep_randn() for _ in range(2000)]
+    assert a == b
