@@ -12,7 +12,7 @@ on a lattice-initialised Lennard-Jones fluid (prg1-style NVT, SURVEY.md section 
             scalars EVERY step, and the final download into the host array
   roofline  the pair-force kernel (dominant): algorithmic bytes / CUDA-event time vs measured HBM peak,
             plus its FP64 rate vs an FMA-chain peak measured on this box (the kernel is bound by neither: the L1
-            tag stage of the neighbour gathers is)
+            data pipe serving the scattered neighbour gathers is)
   cpu_baseline  the reference's own OpenMP CPU path (oracle/_ref, compiled from its unmodified sources)
             on the box's host cores, bounded sample of the same workload
 
@@ -813,7 +813,7 @@ def main():
                 "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_atom_step": alg_bytes, "avg_launch_ms": force_ms, "launches": f_cnt,
                 "share_of_step": f_ms / (t_sec * 1e3),
-                "fp64": {"note": "neither HBM nor the FP64 pipe binds this kernel: the L1 tag stage does (each warp-wide neighbour gather touches ~22 distinct 128-B lines; ncu l1tex 83 %, profiles/r01_k_lj_list_ncu_full.txt)",
+                "fp64": {"note": "neither HBM nor the FP64 pipe binds this kernel: the L1 data pipe does (each warp-wide neighbour gather touches ~22 distinct 128-B lines = 22 wavefronts instead of 8; ncu l1tex data pipe 79 %, profiles/r01_k_lj_list_ncu_full.txt)",
                          "algorithmic_flops_per_atom_step": alg_flops, "achieved_tflops": achieved_tf,
                          "peak_tflops_fma_chain_measured_here": fp64_peak.value,
                          "frac": achieved_tf / fp64_peak.value if fp64_peak.value else None}}

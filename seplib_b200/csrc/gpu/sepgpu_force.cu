@@ -100,9 +100,9 @@ __device__ __forceinline__ void virial_add(double *v, double gx, double gy, doub
 // chains of two pairs.  r2 of a real pair is finite and non-zero, so the masked values stay finite.
 //
 // The pair body is 20 FP64 instructions (32 in the first version).  Measured on B200 the kernel time did
-// NOT follow (0.268 -> 0.265 ms at 1e6 atoms): the binding unit is the L1 tag stage -- the 32 lanes of one
-// neighbour gather touch ~22 different 128-byte lines (ncu: l1tex throughput 83 %, 23 cycles per warp
-// gather), the FP64 pipe needs ~10.  The leaner body is kept because it frees issue slots and power:
+// NOT follow (0.268 -> 0.265 ms at 1e6 atoms): the binding unit is the L1 data pipe -- the 32 lanes of one
+// neighbour gather touch ~22 different 128-byte lines, one wavefront each (ncu: l1tex data pipe 79 %, 19
+// wavefronts per load request), the FP64 pipe needs ~10 cycles.  The leaner body is kept because it frees issue slots and power:
 //  * the cutoff test is a 64-bit INTEGER compare of the bit patterns (both sides are non-negative doubles);
 //  * the prefactor 48 eps is applied once per atom, not per pair;
 //  * the virial is NOT accumulated per pair.  With a full list every pair is seen from both ends with
