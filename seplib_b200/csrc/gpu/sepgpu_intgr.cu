@@ -10,6 +10,7 @@
 // multiplier update is a one-thread kernel, and f -= alpha m v is applied inside the next integrator
 // kernel -- one streaming pass over the atoms per time step (HBM-bound: 144 B read + 128 B written).
 #include "sepgpu_internal.cuh"
+#include "sepgpu_intgr_atom.cuh"
 
 #define INTGR_BLOCK 256
 #define INTGR_MAX_GRID (148 * 8)
@@ -23,22 +24,6 @@ struct IntgrParams {
     int f_zero;         // force array logically zero
     int write_xs;       // maintain the cell-sorted copy
 };
-
-__device__ __forceinline__ int pack_cl(int cx, int cy, int cz) { return (cx + 512) | ((cy + 512) << 10) | ((cz + 512) << 20); }
-__device__ __forceinline__ void unpack_cl(int w, int &cx, int &cy, int &cz)
-{
-    if (w == 0) { cx = cy = cz = 0; return; }
-    cx = (w & 1023) - 512; cy = ((w >> 10) & 1023) - 512; cz = ((w >> 20) & 1023) - 512;
-}
-
-// one component of sep_periodic (source/sepintgr.c:21-35); returns the squared displacement term
-__device__ __forceinline__ double periodic_1d(double &x, double L, int &cn, int &cl, int &cross_total, bool &changed, double xn)
-{
-    if (x > L) { x -= L; cn++; cl++; cross_total = 1; changed = true; }
-    else if (x < 0.0) { x += L; cn--; cl--; cross_total = -1; changed = true; }
-    const double ri = (x + cn * L) - xn;
-    return ri * ri;
-}
 
 template <bool DPD>
 __global__ void __launch_bounds__(INTGR_BLOCK)
@@ -386,40 +371,13 @@ k_integrate_stoch(d4 *__restrict__ x4, d4 *__restrict__ v4, const d4 *__restrict
         const d4 g = noise[i];
         i4 cr = cr4[i];
         const d4 xn = xn4[i];
-        int clx, cly, clz; unpack_cl(cr.w, clx, cly, clz);
-        int tx = 0, ty = 0, tz = 0; bool changed = false;
-        double d2 = 0.0;
-        if (!GJF) {
-            const double im = 1.0 / m;
-            const double fric = temp / g.w;                              // :245  (g.w = ldiff)
-            const double gaussfac = sqrt(24 * temp * fric / dt);         // :246
-            const double fac = sqrt(1.0 / 12.0);
-            const double ax = g.x * fac * gaussfac, ay = g.y * fac * gaussfac, az = g.z * fac * gaussfac;   // :252
-            x.x += dt * v.x; v.x += im * dt * (f.x - fric * v.x + ax);   // :254-255
-            d2 += periodic_1d(x.x, P.Lx, cr.x, clx, tx, changed, xn.x);
-            x.y += dt * v.y; v.y += im * dt * (f.y - fric * v.y + ay);
-            d2 += periodic_1d(x.y, P.Ly, cr.y, cly, ty, changed, xn.y);
-            x.z += dt * v.z; v.z += im * dt * (f.z - fric * v.z + az);
-            d2 += periodic_1d(x.z, P.Lz, cr.z, clz, tz, changed, xn.z);
-        } else {
-            const double imass = 1.0 / m, imass2 = 0.5 * imass;
-            const double fac = sqrt(temp * (1.0 - cc * cc));             // :100
-            const double c_ = alpha * dt * imass2;
-            const double a = (1.0 - c_) / (1.0 + c_), b = 1.0 / (1.0 + c_);
-            d4 pf = prevf4[i], rn = randn4[i];
-            v.x = a * v.x + dt * imass2 * (a * pf.x + f.x) + b * imass * rn.x;     // :108
-            v.y = a * v.y + dt * imass2 * (a * pf.y + f.y) + b * imass * rn.y;
-            v.z = a * v.z + dt * imass2 * (a * pf.z + f.z) + b * imass * rn.z;
-            pf.x = f.x; pf.y = f.y; pf.z = f.z;                                    // :111
-            rn.x = fac * g.x; rn.y = fac * g.y; rn.z = fac * g.z;                   // :115
-            x.x += b * dt * v.x + b * dt * dt * imass2 * f.x + b * dt * imass2 * rn.x;   // :117
-            x.y += b * dt * v.y + b * dt * dt * imass2 * f.y + b * dt * imass2 * rn.y;
-            x.z += b * dt * v.z + b * dt * dt * imass2 * f.z + b * dt * imass2 * rn.z;
-            prevf4[i] = pf; randn4[i] = rn;
-            d2 += periodic_1d(x.x, P.Lx, cr.x, clx, tx, changed, xn.x);
-            d2 += periodic_1d(x.y, P.Ly, cr.y, cly, ty, changed, xn.y);
-            d2 += periodic_1d(x.z, P.Lz, cr.z, clz, tz, changed, xn.z);
-        }
+        int cl[3]; unpack_cl(cr.w, cl[0], cl[1], cl[2]);
+        int t[3] = {0, 0, 0}; bool changed = false;
+        d4 pf, rn;
+        if (GJF) { pf = prevf4[i]; rn = randn4[i]; } else { pf.x = pf.y = pf.z = pf.w = 0.0; rn = pf; }
+        const double d2 = stoch_atom<GJF>(x, v, f, g, pf, rn, xn, cr, cl, t, changed, P.Lx, P.Ly, P.Lz, dt, temp, alpha, cc);
+        if (GJF) { prevf4[i] = pf; randn4[i] = rn; }
+        const int clx = cl[0], cly = cl[1], clz = cl[2], tx = t[0], ty = t[1], tz = t[2];
         acc[0] += v.x * v.x * m; acc[0] += v.y * v.y * m; acc[0] += v.z * v.z * m;     // :258 / :113
         acc[1] += v.x * v.x * m; acc[2] += v.x * v.y * m; acc[3] += v.x * v.z * m;
         acc[4] += v.y * v.y * m; acc[5] += v.y * v.z * m; acc[6] += v.z * v.z * m;
