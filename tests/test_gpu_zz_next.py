@@ -69,26 +69,6 @@ def test_slit_pore_relax_temp_and_tethers(sync, tmp_path):
     _check(rec, "slit", scalar_cols=(0, 1))
 
 
-@pytest.mark.parametrize("which", ["fp", "gjf"])
-def test_stochastic_integrators_follow_the_reference_noise(which, tmp_path):
-    """sep_fp (prg9's integrator) and sep_langevinGJF: the host draws the reference's Gaussian stream (same rand()
-    seed), the device applies it -- 30 steps against the reference's recorded loop.  Columns: epot, ekin, tnow."""
-    rec = _run(which, 1, tmp_path)
-    _check(rec, which, scalar_cols=(0, 1), exact_cols=())
-    assert np.abs(rec["traj"][:, 2] - G[which + "_traj"][:, 2]).max() <= 1e-12      # sep_fp leaves sys.tnow alone, GJF advances it
-
-
-def test_prg9_brownian_dynamics(tmp_path):
-    """prg9 (reference prgs/prg9.c), unchanged: WCA fluid under sep_fp, seeded with sep_set_vel_seed(42), so the run
-    is reproducible.  Columns: n  T  x y z of atom 10.  The first lines to printed precision, then the temperature
-    the integrator is there to hold (reference prg9.c:5 "Tests the temperature")."""
-    got, _ = run_prg("prg9", tmp_path=tmp_path)
-    ref = golden("prg9.ref.out")
-    assert got.shape == ref.shape
-    assert np.allclose(got[:2], ref[:2], rtol=0, atol=2e-5)                  # steps 0 and 100: same noise, same trajectory
-    assert abs(got[10:, 1].mean() - ref[10:, 1].mean()) < 0.15              # T (two printed decimals, sample std 0.13)
-
-
 def test_prg7_berendsen_npt(tmp_path):
     """columns: n t epot/N ekin/N T etot/N sum_p p volume   (reference prgs/prg7.c:60-64): brute LJ + Nose-Hoover +
     sep_berendsen every step.  Step-0 lattice energy to printed precision, then the state point the barostat/thermostat hold."""
@@ -121,3 +101,25 @@ def test_prg8_slit_pore_runs(tmp_path):
     assert len(got) == 100 and np.isfinite(got).all()
     assert 0.8 < got[20:, 1].mean() < 2.0                                    # wall thermostat at 1.4 carries the fluid along
     assert os.path.exists(tmp_path / "slitpore.xyz")
+
+
+# ---- written after the round's GPU budget was spent: not yet run on hardware (kept last, so that -x cannot hide the
+# ---- verified tests above).  CPU side: tests/test_golden.py (oracle), tests/test_cpu_kernels.py (per-atom arithmetic).
+@pytest.mark.parametrize("which", ["fp", "gjf"])
+def test_stochastic_integrators_follow_the_reference_noise(which, tmp_path):
+    """sep_fp (prg9's integrator) and sep_langevinGJF: the host draws the reference's Gaussian stream (same rand()
+    seed), the device applies it -- 30 steps against the reference's recorded loop.  Columns: epot, ekin, tnow."""
+    rec = _run(which, 1, tmp_path)
+    _check(rec, which, scalar_cols=(0, 1), exact_cols=())
+    assert np.abs(rec["traj"][:, 2] - G[which + "_traj"][:, 2]).max() <= 1e-12      # sep_fp leaves sys.tnow alone, GJF advances it
+
+
+def test_prg9_brownian_dynamics(tmp_path):
+    """prg9 (reference prgs/prg9.c), unchanged: WCA fluid under sep_fp, seeded with sep_set_vel_seed(42), so the run
+    is reproducible.  Columns: n  T  x y z of atom 10.  The first lines to printed precision, then the temperature
+    the integrator is there to hold (reference prg9.c:5 "Tests the temperature")."""
+    got, _ = run_prg("prg9", tmp_path=tmp_path)
+    ref = golden("prg9.ref.out")
+    assert got.shape == ref.shape
+    assert np.allclose(got[:2], ref[:2], rtol=0, atol=2e-5)                  # steps 0 and 100: same noise, same trajectory
+    assert abs(got[10:, 1].mean() - ref[10:, 1].mean()) < 0.15              # T (two printed decimals, sample std 0.13)
