@@ -1,0 +1,171 @@
+"""The HOST layer (seplib_b200/csrc/host/sep_*.c) on the CPU.  The unchanged host sources are linked with a stand-in
+device layer that keeps its state in host memory and computes with the oracle (tests/mock_device/sepgpu_mock.c --
+test infrastructure, never part of libsep.so), and the same sep_* loops the GPU tests run are driven through it:
+dispatch and control flow (brute / list, rebuild flag, epot assign vs accumulate over several typed calls), the
+bookkeeping of the box-changing routines, per-type relaxation and tethers, the Gaussian stream handed to the
+stochastic integrators, and the step / lazy coherence modes -- all against the reference's recorded loops."""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common as cm
+from seplib_b200 import capi
+from test_gpu_zz_next import _check
+
+BUILD = os.path.join(cm.ROOT, "tests", "_build")
+G = np.load(os.path.join(cm.GOLDEN, "next_rows.npz"))
+
+
+@pytest.fixture(scope="module")
+def mock():
+    so = os.path.join(BUILD, "libsep_hostmock.so")
+    srcs = sorted(glob.glob(os.path.join(cm.ROOT, "seplib_b200", "csrc", "host", "*.c"))) + [
+        os.path.join(cm.ROOT, "tests", "mock_device", "sepgpu_mock.c"), os.path.join(cm.ROOT, "oracle", "sep_oracle.c")]
+    deps = srcs + glob.glob(os.path.join(cm.ROOT, "include", "*.h")) + glob.glob(os.path.join(cm.ROOT, "seplib_b200", "csrc", "host", "*.h"))
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in deps):
+        os.makedirs(BUILD, exist_ok=True)
+        subprocess.check_call(["gcc", "-shared", "-fPIC", "-O1", "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-ffp-contract=off",
+                               "-I" + os.path.join(cm.ROOT, "include"), "-I" + os.path.join(cm.ROOT, "oracle"),
+                               "-I" + os.path.join(cm.ROOT, "seplib_b200", "csrc", "host"), *srcs, "-Wl,--no-undefined", "-lm", "-o", so])
+    lib = C.CDLL(so, mode=C.RTLD_LOCAL)
+    capi.declare_sep_api(lib)
+    return lib
+
+
+@pytest.mark.parametrize("sync", [1, 0, 2])          # step, lazy, full
+def test_lj_loop_matches_reference_golden(mock, sync):
+    """the prg1 loop of tests/test_gpu_more.py::test_sep_api_lj_loop_matches_reference_golden, on the mock"""
+    g = np.load(os.path.join(cm.GOLDEN, "lj_n1000.npz"))
+    mock.sep_gpu_set_sync(sync)
+    s = cm.ApiSystem(mock, g["x0"], float(g["L"]), float(g["cf"]), float(g["dt"]), v=g["v0"], nneighb=0)
+    s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+    alpha = C.c_double(float(g["alpha0"]))
+    fun = s.fun("sep_lj_shift")
+    mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+    mock.sep_force_pairs(s.atoms, b"AA", float(g["cf"]), fun, s.S, s.R, 1)
+    mock.sep_gpu_sync(s.atoms)
+    assert cm.rel_force_err(s.view["f"], g["f_pairs"]) <= 1e-11
+    if sync != 0:
+        assert abs(s.ret.epot - float(g["epot"])) <= 1e-11 * abs(float(g["epot"]))
+    mock.sep_nosehoover(s.atoms, float(g["temp"]), C.byref(alpha), float(g["tau"]), s.S)
+    mock.sep_leapfrog(s.atoms, s.S, s.R)
+    mock.sep_gpu_sync(s.atoms)
+    assert np.abs(s.view["x"] - g["x1"]).max() <= 1e-12 and np.abs(s.view["v"] - g["v1"]).max() <= 1e-12
+    assert abs(alpha.value - float(g["alpha1"])) <= 1e-12
+    assert abs(s.ret.ekin - float(g["ekin"])) <= 1e-11 * float(g["ekin"])
+    assert np.array_equal(s.view["crossings"], g["cr1"]) and np.array_equal(s.view["cross_neighb"], g["cn1"])
+    assert int(s.sys.neighb_flag) == int(g["neighb_flag1"]) and abs(s.sys.tnow - float(g["dt"])) <= 1e-15
+    # 40 more steps: the reference's aggregate trajectory and its list-rebuild count
+    nup0 = int(s.sys.nupdate_neighb)
+    traj = g["traj"]
+    for k in range(40):
+        mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+        mock.sep_force_pairs(s.atoms, b"AA", float(g["cf"]), fun, s.S, s.R, 1)
+        mock.sep_nosehoover(s.atoms, float(g["temp"]), C.byref(alpha), float(g["tau"]), s.S)
+        mock.sep_leapfrog(s.atoms, s.S, s.R)
+        mock.sep_pressure_tensor(s.R, s.S)
+        assert abs(s.ret.epot - traj[k, 0]) <= 1e-9 * abs(traj[k, 0]) and abs(s.ret.ekin - traj[k, 1]) <= 1e-9 * traj[k, 1]
+        assert abs(s.ret.p - traj[k, 2]) <= 1e-8 * abs(traj[k, 2]) and abs(alpha.value - traj[k, 3]) <= 1e-9 * abs(traj[k, 3])
+        if k == 0:
+            nup0 = int(s.sys.nupdate_neighb)
+    assert int(s.sys.nupdate_neighb) - nup0 == int(traj[-1, 4] - traj[0, 4])      # rebuilds over the last 39 steps
+    s.close()
+    mock.sep_gpu_set_sync(1)
+
+
+@pytest.mark.parametrize("sync", [1, 0])
+def test_box_changing_callers(mock, sync):
+    mock.sep_gpu_set_sync(sync)
+    _check(cm.drive_compress(mock, G["c_x0"], G["c_v0"], float(G["c_L"])), "compress", scalar_cols=(0, 1, 2, 4), exact_cols=(3,), xtol=1e-9)
+    _check(cm.drive_berendsen(mock, G["b_x0"], G["b_v0"], float(G["b_L"])), "ber", scalar_cols=(0, 1, 2, 3, 4), exact_cols=(5,), xtol=1e-9)
+    _check(cm.drive_berendsen(mock, G["c_x0"], G["c_v0"], float(G["c_L"]), steps=12, iso=True, update=capi.SEP_LLIST_NEIGHBLIST),
+           "beriso", scalar_cols=(0, 1, 2, 3, 4), exact_cols=(5,), xtol=1e-9)
+    mock.sep_gpu_set_sync(1)
+
+
+@pytest.mark.parametrize("sync", [1, 0])
+def test_slit_pore_three_typed_calls_relax_temp_tethers(mock, sync):
+    mock.sep_gpu_set_sync(sync)
+    rec = cm.drive_slit(mock, G["c_x0"], G["c_v0"], float(G["c_L"]))
+    mock.sep_gpu_set_sync(1)
+    assert np.array_equal(rec["types"], G["slit_types"])
+    _check(rec, "slit", scalar_cols=(0, 1), xtol=1e-9)
+
+
+def test_stochastic_integrators_get_the_reference_noise(mock):
+    for which in ("fp", "gjf"):
+        rec = cm.drive_stochastic(mock, G["b_x0"], G["b_v0"], float(G["b_L"]), which)
+        _check(rec, which, scalar_cols=(0, 1), xtol=1e-9)
+        assert np.abs(rec["traj"][:, 2] - G[which + "_traj"][:, 2]).max() <= 1e-12
+
+
+def _top_file(g, tmp_path, name):
+    top = str(tmp_path / name)
+    with open(top, "w") as fh:
+        fh.write("[ bonds ]\n;generated\n")
+        for (a, b, t) in g["blist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {t}\n")
+        fh.write("\n[ angles ]\n;generated\n")
+        for (a, b, c, t) in g["alist"]:
+            fh.write(f"{g['molindex'][a]} {a} {b} {c} {t}\n")
+        if len(g["dlist"]):
+            fh.write("\n[ dihedrals ]\n;generated\n")
+            for (a, b, c, d, t) in g["dlist"]:
+                fh.write(f"{g['molindex'][a]} {a} {b} {c} {d} {t}\n")
+    return top
+
+
+@pytest.mark.parametrize("sync", [1, 0])
+def test_butane_and_water_steps(mock, sync, tmp_path):
+    """prg2 (list mode, same-molecule exclusion, bond / angle / Ryckaert torsion) and prg3 (brute LJ, cos^2 angles,
+    shifted-force Coulomb) force sequences, then thermostat + leapfrog, against the reference's recorded step"""
+    mock.sep_gpu_set_sync(sync)
+    g = np.load(os.path.join(cm.GOLDEN, "butane_n4000.npz"))
+    n = len(g["x0"])
+    s = cm.ApiSystem(mock, g["x0"], g["L"], 2.5, float(g["dt"]), v=g["v0"], types=np.full(n, ord("C"), dtype=np.uint8), nneighb=0)
+    s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+    mock.sep_read_topology_file(s.atoms, _top_file(g, tmp_path, "b.top").encode(), s.S, b"q")
+    rb = (C.c_double * 6)(*g["rb"])
+    alpha = C.c_double(float(g["alpha0"]))
+    mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+    mock.sep_force_pairs(s.atoms, b"CC", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+    mock.sep_stretch_harmonic(s.atoms, 0, 0.407, 2074.0, s.S, s.R)
+    mock.sep_angle_harmonic(s.atoms, 0, 1.90, 400.0, s.S, s.R)
+    mock.sep_torsion_Ryckaert(s.atoms, 0, rb, s.S, s.R)
+    mock.sep_gpu_sync_scalars(s.atoms, s.S, s.R)
+    assert abs(s.ret.epot - float(g["epot_torsion"])) <= 1e-11 * abs(float(g["epot_torsion"]))
+    mock.sep_gpu_sync(s.atoms)
+    assert cm.rel_force_err(s.view["f"], g["f_torsion"]) <= 1e-11
+    mock.sep_nosehoover(s.atoms, float(g["temp"]), C.byref(alpha), 0.1, s.S)
+    mock.sep_leapfrog(s.atoms, s.S, s.R)
+    mock.sep_gpu_sync(s.atoms)
+    assert np.abs(s.view["x"] - g["x1"]).max() <= 1e-12 and np.abs(s.view["v"] - g["v1"]).max() <= 1e-11
+    assert abs(s.ret.ekin - float(g["ekin"])) <= 1e-11 * float(g["ekin"])
+    s.close()
+
+    g = np.load(os.path.join(cm.GOLDEN, "water_n648.npz"))
+    s = cm.ApiSystem(mock, g["x0"], g["L"], float(g["cf"]), float(g["dt"]), update=capi.SEP_BRUTE, v=g["v0"], types=g["type"],
+                     m=g["m"], z=g["z"], nneighb=0)
+    s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+    mock.sep_read_topology_file(s.atoms, _top_file(g, tmp_path, "w.top").encode(), s.S, b"q")
+    alpha3 = (C.c_double * 3)(float(g["alpha0"]), 0.0, 0.0)
+    mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+    mock.sep_force_pairs(s.atoms, b"OO", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+    mock.sep_stretch_harmonic(s.atoms, 0, 0.316, 68421.0, s.S, s.R)
+    mock.sep_angle_cossq(s.atoms, 0, 1.97, 490.0, s.S, s.R)
+    mock.sep_coulomb_sf(s.atoms, float(g["cf"]), s.S, s.R, 3)
+    mock.sep_gpu_sync_scalars(s.atoms, s.S, s.R)
+    mock.sep_gpu_sync(s.atoms)
+    assert cm.rel_force_err(s.view["f"], g["f_coul"]) <= 1e-11
+    assert abs(s.ret.epot - float(g["epot_coul"])) <= 1e-11 * abs(float(g["epot_coul"]))
+    assert abs(s.ret.ecoul - float(g["ecoul"])) <= 1e-11 * abs(float(g["ecoul"]))
+    mock.sep_nosehoover(s.atoms, float(g["temp"]), alpha3, 0.01, s.S)
+    mock.sep_leapfrog(s.atoms, s.S, s.R)
+    mock.sep_gpu_sync(s.atoms)
+    assert np.abs(s.view["x"] - g["x1"]).max() <= 1e-12 and np.abs(s.view["v"] - g["v1"]).max() <= 1e-10
+    s.close()
+    mock.sep_gpu_set_sync(1)
