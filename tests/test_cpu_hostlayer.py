@@ -169,3 +169,21 @@ def test_butane_and_water_steps(mock, sync, tmp_path):
     assert np.abs(s.view["x"] - g["x1"]).max() <= 1e-12 and np.abs(s.view["v"] - g["v1"]).max() <= 1e-10
     s.close()
     mock.sep_gpu_set_sync(1)
+
+
+@pytest.mark.parametrize("prg", ["prg0", "prg9"])
+def test_reference_program_on_the_mock_reproduces_the_reference_output(mock, prg, tmp_path):
+    """The reference's example program, unchanged, compiled against include/sep.h and linked with the host layer +
+    mock device, prints exactly what it prints when linked with the reference (tests/golden/<prg>.ref.out): 10 000
+    steps of prg0 (brute LJ, NVE) and of prg9 (sep_set_vel_seed's rand() stream continuing into sep_fp's noise).
+    Needs the reference sources (build container only)."""
+    src = f"/root/reference/prgs/{prg}.c"
+    if not os.path.exists(src):
+        pytest.skip("reference sources not present")
+    exe = str(tmp_path / prg)
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-w", "-I" + os.path.join(cm.ROOT, "include"), src, "-L" + BUILD,
+                           "-lsep_hostmock", "-lm", "-Wl,-rpath," + BUILD, "-o", exe])
+    out = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0
+    want = open(os.path.join(cm.GOLDEN, f"{prg}.ref.out")).read()
+    assert out.stdout == want
