@@ -171,11 +171,12 @@ def test_butane_and_water_steps(mock, sync, tmp_path):
     mock.sep_gpu_set_sync(1)
 
 
-@pytest.mark.parametrize("prg", ["prg0", "prg9"])
-def test_reference_program_on_the_mock_reproduces_the_reference_output(mock, prg, tmp_path):
+@pytest.mark.parametrize("prg,args", [("prg0", ()), ("prg9", ()), ("prg1", ()), ("prg4", ("1",))])
+def test_reference_program_on_the_mock_reproduces_the_reference_output(mock, prg, args, tmp_path):
     """The reference's example program, unchanged, compiled against include/sep.h and linked with the host layer +
     mock device, prints exactly what it prints when linked with the reference (tests/golden/<prg>.ref.out): 10 000
-    steps of prg0 (brute LJ, NVE) and of prg9 (sep_set_vel_seed's rand() stream continuing into sep_fp's noise).
+    steps of prg0 (brute LJ, NVE) and of prg9 (sep_set_vel_seed's rand() stream continuing into sep_fp's noise),
+    prg1 (list mode, Nose-Hoover, samplers attached) and prg4 (skin reset to 1.0 after setup, the reference's quirk).
     Needs the reference sources (build container only)."""
     src = f"/root/reference/prgs/{prg}.c"
     if not os.path.exists(src):
@@ -183,7 +184,7 @@ def test_reference_program_on_the_mock_reproduces_the_reference_output(mock, prg
     exe = str(tmp_path / prg)
     subprocess.check_call(["gcc", "-std=c99", "-O2", "-w", "-I" + os.path.join(cm.ROOT, "include"), src, "-L" + BUILD,
                            "-lsep_hostmock", "-lm", "-Wl,-rpath," + BUILD, "-o", exe])
-    out = subprocess.run([exe], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, *args], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0
     want = open(os.path.join(cm.GOLDEN, f"{prg}.ref.out")).read()
     assert out.stdout == want
