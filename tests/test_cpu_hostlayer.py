@@ -188,3 +188,26 @@ def test_reference_program_on_the_mock_reproduces_the_reference_output(mock, prg
     assert out.returncode == 0
     want = open(os.path.join(cm.GOLDEN, f"{prg}.ref.out")).read()
     assert out.stdout == want
+
+
+def test_dpd_loop_is_independent_of_the_coherence_mode(mock):
+    """prg6's loop (sep_force_dpd + sep_verlet_dpd, predictor state pv/pa mirrored on the device): the step, lazy and
+    full modes must give the same trajectory -- what differs between them is only when atoms[] is refreshed."""
+    x, L = cm.lattice(6, 3.0, jitter=0.3, seed=51)
+    v = cm.velocities(len(x), 1.0, seed=52)
+    results = []
+    for sync in (1, 0, 2):
+        mock.sep_gpu_set_sync(sync)
+        s = cm.ApiSystem(mock, x, L, 1.0, 0.02, v=v, nneighb=0)
+        for n in range(25):
+            mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+            mock.sep_force_dpd(s.atoms, b"AA", 1.0, 25.0, 1.0, 3.0, s.S, s.R, 1)
+            mock.sep_verlet_dpd(s.atoms, 0.5, n, s.S, s.R)
+        mock.sep_gpu_sync(s.atoms)
+        results.append((s.view["x"].copy(), s.view["v"].copy(), s.view["pv"].copy(), s.ret.ekin, int(s.sys.neighb_flag)))
+        s.close()
+    mock.sep_gpu_set_sync(1)
+    for r in results[1:]:
+        assert np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1]) and np.array_equal(r[2], results[0][2])
+        assert r[3] == results[0][3] and r[4] == results[0][4]
+    assert np.isfinite(results[0][0]).all() and abs(results[0][3] / len(x) - 1.5) < 0.5
