@@ -1,0 +1,251 @@
+// emu_rt.cpp -- fiber scheduler and runtime stubs of the CPU kernel emulator.  TEST INFRASTRUCTURE ONLY.
+//
+// One CUDA block at a time; each thread of the block is a ucontext fiber.  A fiber runs until it reaches a
+// rendezvous (__syncthreads, a *_sync warp primitive) or returns.  The scheduler releases
+//   * a block barrier when every thread that has not returned waits at it (CUDA's rule), and
+//   * a warp exchange when every live lane named in the mask has arrived with the same mask;
+// if neither is possible and nobody can run, the kernel has a divergent barrier: the emulator says so and aborts.
+// "Device" memory is host memory filled with 0xCD at allocation, so a kernel that relies on zeroed allocations
+// computes garbage here too.
+#include "cuda_runtime.h"
+
+#include <stdio.h>
+#include <sys/mman.h>
+#include <ucontext.h>
+
+#include <mutex>
+#include <vector>
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+namespace {
+enum { READY = 0, AT_BARRIER = 1, AT_WARP = 2, DONE = 3 };
+struct Fiber {
+    ucontext_t ctx;
+    int state;
+    unsigned wmask;
+    uint64_t deposit;
+    uint64_t snap[32];
+    uint3 tid;
+    int lin;
+};
+const size_t STACK_BYTES = 256 * 1024;
+const int MAX_THREADS = 1024;
+char *g_stacks = nullptr;
+std::vector<Fiber> g_fibers;
+ucontext_t g_sched;
+Fiber *g_cur = nullptr;
+const std::function<void()> *g_body = nullptr;
+const char *g_kernel = "?";
+std::vector<unsigned char> g_dyn;
+std::recursive_mutex g_lock;
+long long g_launches = 0;
+
+void fiber_main()
+{
+    (*g_body)();
+    g_cur->state = DONE;
+    // returning resumes uc_link == g_sched
+}
+
+void yield_to_scheduler()
+{
+    Fiber *me = g_cur;
+    swapcontext(&me->ctx, &g_sched);
+    // resumed: the scheduler has restored threadIdx and g_cur
+}
+
+void run_block(int nthreads)
+{
+    int alive = nthreads;
+    for (;;) {
+        bool ran = false;
+        for (int t = 0; t < nthreads; t++) {
+            Fiber &f = g_fibers[t];
+            if (f.state != READY) continue;
+            threadIdx = f.tid;
+            g_cur = &f;
+            swapcontext(&g_sched, &f.ctx);
+            ran = true;
+            if (f.state == DONE) alive--;
+        }
+        if (alive == 0) return;
+        // block barrier
+        int at_bar = 0;
+        for (int t = 0; t < nthreads; t++) at_bar += g_fibers[t].state == AT_BARRIER;
+        bool released = false;
+        if (at_bar == alive) {
+            for (int t = 0; t < nthreads; t++)
+                if (g_fibers[t].state == AT_BARRIER) g_fibers[t].state = READY;
+            released = true;
+        }
+        // warp exchanges
+        for (int w0 = 0; w0 < nthreads; w0 += 32) {
+            const int wn = nthreads - w0 < 32 ? nthreads - w0 : 32;
+            unsigned live = 0;
+            for (int l = 0; l < wn; l++)
+                if (g_fibers[w0 + l].state != DONE) live |= 1u << l;
+            for (int l = 0; l < wn; l++) {
+                Fiber &f = g_fibers[w0 + l];
+                if (f.state != AT_WARP) continue;
+                const unsigned need = f.wmask & live;
+                bool ok = true;
+                for (int m = 0; m < wn && ok; m++)
+                    if (need >> m & 1u) ok = g_fibers[w0 + m].state == AT_WARP && g_fibers[w0 + m].wmask == f.wmask;
+                if (!ok) continue;
+                for (int m = 0; m < wn; m++) {
+                    if (!(need >> m & 1u)) continue;
+                    Fiber &g = g_fibers[w0 + m];
+                    for (int q = 0; q < 32; q++)
+                        g.snap[q] = (q < wn && (need >> q & 1u)) ? g_fibers[w0 + q].deposit : g.deposit;
+                }
+                for (int m = 0; m < wn; m++)
+                    if (need >> m & 1u) g_fibers[w0 + m].state = READY;
+                released = true;
+            }
+        }
+        if (!ran && !released) {
+            int nb = 0, nw = 0;
+            for (int t = 0; t < nthreads; t++) { nb += g_fibers[t].state == AT_BARRIER; nw += g_fibers[t].state == AT_WARP; }
+            fprintf(stderr, "emu: DEADLOCK in kernel %s, block (%u,%u,%u): %d threads alive, %d at __syncthreads, %d at a warp "
+                            "primitive -- divergent barrier or a mask naming lanes that never arrive\n",
+                    g_kernel, blockIdx.x, blockIdx.y, blockIdx.z, alive, nb, nw);
+            abort();
+        }
+    }
+}
+}  // namespace
+
+namespace emu {
+dim3 d3(dim3 v) { return v; }
+
+void *dyn_smem() { return g_dyn.data(); }
+
+int lane_id() { return g_cur->lin & 31; }
+
+void sync_block()
+{
+    g_cur->state = AT_BARRIER;
+    yield_to_scheduler();
+}
+
+void warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32])
+{
+    Fiber *me = g_cur;
+    me->state = AT_WARP;
+    me->wmask = mask;
+    me->deposit = mine;
+    yield_to_scheduler();
+    for (int q = 0; q < 32; q++) out[q] = me->snap[q];
+}
+
+void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
+{
+    std::lock_guard<std::recursive_mutex> guard(g_lock);
+    const int nthreads = (int)(block.x * block.y * block.z);
+    if (nthreads <= 0 || nthreads > MAX_THREADS || grid.x == 0 || grid.y == 0 || grid.z == 0) {
+        fprintf(stderr, "emu: invalid launch configuration for %s: grid (%u,%u,%u) block (%u,%u,%u)\n", name, grid.x, grid.y,
+                grid.z, block.x, block.y, block.z);
+        abort();
+    }
+    if (smem > 227 * 1024) { fprintf(stderr, "emu: %s asks for %zu bytes of shared memory (> 227 KB)\n", name, smem); abort(); }
+    if (!g_stacks) {
+        g_stacks = (char *)mmap(nullptr, STACK_BYTES * MAX_THREADS, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (g_stacks == (char *)MAP_FAILED) { perror("emu: mmap"); abort(); }
+        g_fibers.resize(MAX_THREADS);
+    }
+    g_launches++;
+    g_kernel = name;
+    g_body = &body;
+    blockDim = block;
+    gridDim = grid;
+    g_dyn.assign(smem + 128, 0xCD);
+    for (unsigned bz = 0; bz < grid.z; bz++)
+        for (unsigned by = 0; by < grid.y; by++)
+            for (unsigned bx = 0; bx < grid.x; bx++) {
+                blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                if (smem) memset(g_dyn.data(), 0xCD, smem);
+                int t = 0;
+                for (unsigned tz = 0; tz < block.z; tz++)
+                    for (unsigned ty = 0; ty < block.y; ty++)
+                        for (unsigned tx = 0; tx < block.x; tx++, t++) {
+                            Fiber &f = g_fibers[t];
+                            getcontext(&f.ctx);
+                            f.ctx.uc_stack.ss_sp = g_stacks + (size_t)t * STACK_BYTES;
+                            f.ctx.uc_stack.ss_size = STACK_BYTES;
+                            f.ctx.uc_link = &g_sched;
+                            makecontext(&f.ctx, fiber_main, 0);
+                            f.state = READY;
+                            f.tid.x = tx; f.tid.y = ty; f.tid.z = tz;
+                            f.lin = t;
+                        }
+                run_block(nthreads);
+            }
+    g_cur = nullptr;
+}
+}  // namespace emu
+
+extern "C" long long sepgpu_emu_launches(void) { return g_launches; }
+
+// ---- runtime ------------------------------------------------------------------------------------------------------------
+struct emuStream { int dummy; };
+struct emuEvent { double t_ms; };
+
+static double now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t e)
+{
+    switch (e) {
+    case cudaSuccess: return "no error";
+    case cudaErrorInvalidValue: return "invalid argument";
+    case cudaErrorMemoryAllocation: return "out of memory";
+    case cudaErrorNotSupported: return "operation not supported (kernel emulator)";
+    default: return "unknown error";
+    }
+}
+cudaError_t cudaMalloc(void **p, size_t bytes)
+{
+    void *q = nullptr;
+    if (posix_memalign(&q, 256, bytes ? bytes : 256)) return cudaErrorMemoryAllocation;
+    memset(q, 0xCD, bytes);
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void **p, size_t bytes)
+{
+    void *q = nullptr;
+    if (posix_memalign(&q, 256, bytes ? bytes : 256)) return cudaErrorMemoryAllocation;
+    memset(q, 0xCD, bytes);
+    *p = q;
+    return cudaSuccess;
+}
+cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t bytes, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaMemset(void *p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
+cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = new emuStream(); return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emuStream(); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent(); (*e)->t_ms = 0; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = now_ms(); return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }

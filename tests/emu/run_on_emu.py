@@ -1,0 +1,25 @@
+"""Runs pytest with the ctypes bindings pointed at tests/_build/libsep_emu.so (the library's own kernels executed by
+the CPU kernel emulator) instead of libsep.so.  TEST INFRASTRUCTURE ONLY: the redirection lives here, in the test
+runner -- seplib_b200/capi.py has no switch for it, and libsep.so has no CPU path.
+
+    python tests/emu/run_on_emu.py tests/test_gpu_lj.py -m gpu -x -q
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, HERE)
+
+import build_emu  # noqa: E402
+from seplib_b200 import capi  # noqa: E402
+
+capi.LIB_PATH = build_emu.build()
+os.environ["SEPGPU_EMULATED"] = "1"        # tests that need real hardware (full-size runs, linked prgs) skip on it
+sys.stderr.write("seplib-b200 TEST RUN ON THE CPU KERNEL EMULATOR: %s\n" % capi.LIB_PATH)
+
+import pytest  # noqa: E402
+
+sys.exit(pytest.main(sys.argv[1:]))
