@@ -17,7 +17,11 @@ import build_emu  # noqa: E402
 from seplib_b200 import capi  # noqa: E402
 
 capi.LIB_PATH = build_emu.build()
-os.environ["SEPGPU_EMULATED"] = "1"        # tests that need real hardware (full-size runs, linked prgs) skip on it
+os.environ["SEPGPU_EMU_LIB"] = capi.LIB_PATH   # subprocess drivers (tests/next_driver.py, linked prgs) follow it
+_d = os.path.join(os.path.dirname(capi.LIB_PATH), "emu_lib")
+os.makedirs(_d, exist_ok=True)
+if not os.path.lexists(os.path.join(_d, "libsep.so")):
+    os.symlink(capi.LIB_PATH, os.path.join(_d, "libsep.so"))
 sys.stderr.write("seplib-b200 TEST RUN ON THE CPU KERNEL EMULATOR: %s\n" % capi.LIB_PATH)
 
 import pytest  # noqa: E402

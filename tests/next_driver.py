@@ -18,6 +18,8 @@ from seplib_b200 import capi  # noqa: E402
 def main():
     what, sync, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
     g = np.load(os.path.join(cm.GOLDEN, "next_rows.npz"))
+    if os.environ.get("SEPGPU_EMU_LIB"):          # test run on the CPU kernel emulator (tests/emu/run_on_emu.py)
+        capi.LIB_PATH = os.environ["SEPGPU_EMU_LIB"]
     lib = capi.load()
     lib.sep_gpu_set_sync(sync)
     if what == "compress":

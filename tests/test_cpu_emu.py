@@ -1,0 +1,38 @@
+"""The library's own CUDA kernels, executed on the CPU by the kernel emulator (tests/emu/): the unchanged .cu sources
+are compiled with g++, every CUDA thread of a block runs as a fiber and __syncthreads / the *_sync warp primitives are
+rendezvous points of the fiber scheduler.  The `-m gpu` parity tests then run against that build.
+
+What this proves: the kernels' logic (indexing, list layout, masks, scans, reductions, control flow of the C ABI around
+them) against the oracle, on every CPU round.  What it cannot prove: memory-model races, alignment faults, resource
+limits and speed -- those stay with the hardware run.  The emulated library is test infrastructure: libsep.so contains
+none of it and has no CPU path (tests/test_cpu_host.py::test_no_cpu_fallback_without_device).
+"""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUNNER = os.path.join(ROOT, "tests", "emu", "run_on_emu.py")
+
+# the long trajectories and the linked example programs (thousands of steps) are left to the hardware run
+FAST = ("not prg and not md_trajectory and not lj_loop and not molecular_pressure and not fij_list "
+        "and not compress_box and not berendsen and not slit_pore")
+
+
+def _run(args, timeout=1500):
+    r = subprocess.run([sys.executable, RUNNER, *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m, tail
+    assert "failed" not in r.stdout and "error" not in r.stdout.lower().replace("test_error_paths", ""), tail
+    return int(m.group(1))
+
+
+def test_gpu_parity_tests_pass_on_the_emulated_kernels():
+    n = _run(["tests/test_gpu_lj.py", "tests/test_gpu_more.py", "tests/test_gpu_zz_next.py", "-m", "gpu", "-q", "-x",
+              "-k", FAST, "-p", "no:cacheprovider"])
+    assert n >= 20, n

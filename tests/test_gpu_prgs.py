@@ -24,7 +24,10 @@ def run_prg(name, args=(), tmp_path=None, timeout=600):
     if not os.path.exists(exe):
         pytest.skip(f"{exe} not built (scripts/build_prgs.sh needs the reference sources)")
     env = dict(os.environ)
-    env["LD_LIBRARY_PATH"] = os.path.join(cm.ROOT, "seplib_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    libdir = os.path.join(cm.ROOT, "seplib_b200")
+    if env.get("SEPGPU_EMU_LIB"):                 # test run on the CPU kernel emulator (tests/emu/run_on_emu.py):
+        libdir = os.path.join(os.path.dirname(env["SEPGPU_EMU_LIB"]), "emu_lib")      # holds libsep.so -> libsep_emu.so
+    env["LD_LIBRARY_PATH"] = libdir + ":" + env.get("LD_LIBRARY_PATH", "")
     out = subprocess.run([exe, *args], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=timeout)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     rows = [ln.split() for ln in out.stdout.splitlines() if ln and ln[0].isdigit()]
