@@ -466,11 +466,90 @@ static LJDev make_lj(const sepgpu_ljparam *p, const char types[2])
     return d;
 }
 
+// ---- typed sub-lists (option typed_sublist) -------------------------------------------------------------------------
+// A typed call such as prg3's sep_force_pairs(atoms, "OO", ...) on water walks every entry of the full list only to
+// find that 8 of 9 partners have the wrong type (reference source/sepprfrc.c:126-127 tests the types per pair as well).
+// With the option on, the first typed call after a list build copies the matching entries of every row into a second
+// list of the same chunked layout (one thread per atom, 128-bit streaming reads of the row, types from a one-byte
+// array in sorted order); the force kernel then runs unchanged on that list.  Same pairs, same order -> same sums.
+__global__ void k_sorted_types(const d4 *__restrict__ xs, unsigned char *__restrict__ tsort, int n)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) tsort[s] = (unsigned char)tag_type(xs[s].w);
+}
+
+__global__ void __launch_bounds__(128)
+k_typed_sublist(const unsigned *__restrict__ nbr, const int *__restrict__ cnt, const unsigned char *__restrict__ tsort,
+                unsigned *__restrict__ nbr_t, int *__restrict__ cnt_t, int n, int npad, int t0, int t1)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int ti = tsort[s];
+    int m = 0;
+    if (ti == t0 || ti == t1) {                                   // source/sepprfrc.c:164-165
+        const int mfull = cnt[s];
+        const int nch = (mfull + 3) >> 2;
+        const uint4 *row = reinterpret_cast<const uint4 *>(nbr) + s;
+        for (int c = 0; c < nch; c++) {
+            const uint4 ch = __ldcs(row + (size_t)c * npad);
+            const unsigned e[4] = {ch.x, ch.y, ch.z, ch.w};
+            const int left = mfull - 4 * c;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (q < left) {
+                    const int tj = tsort[e[q] & SEPGPU_INDEX_MASK];
+                    if ((ti == t0 && tj == t1) || (ti == t1 && tj == t0)) {        // :171-172
+                        nbr_t[nbr_index(m, s, npad)] = e[q];
+                        m++;
+                    }
+                }
+            }
+        }
+    }
+    cnt_t[s] = m;
+}
+
+// returns the sub-list for the type pair in *nbr_out / *cnt_out (building it when the list is newer than the slot)
+static int typed_sublist_get(sepgpu_ctx *c, const char types[2], const unsigned **nbr_out, const int **cnt_out)
+{
+    const int a = (unsigned char)types[0], b = (unsigned char)types[1];
+    const int key = (a < b ? a | (b << 8) : b | (a << 8)) | (1 << 16);
+    int k = -1;
+    for (int q = 0; q < SEPGPU_NSUB; q++) if (c->sub_key[q] == key) k = q;
+    if (k < 0) for (int q = 0; q < SEPGPU_NSUB && k < 0; q++) if (c->sub_key[q] == 0) k = q;
+    if (k < 0) {                                                  // all slots taken: reuse the stalest one
+        k = 0;
+        for (int q = 1; q < SEPGPU_NSUB; q++) if (c->sub_gen[q] < c->sub_gen[k]) k = q;
+    }
+    if (c->sub_key[k] != key) { c->sub_key[k] = key; c->sub_gen[k] = -1; }
+    if (!c->nbr_t[k] || c->sub_cap[k] != c->cap) {
+        if (c->nbr_t[k]) cudaFree(c->nbr_t[k]);
+        c->nbr_t[k] = NULL;
+        CUDA_TRY(cudaMalloc((void **)&c->nbr_t[k], sizeof(unsigned) * (size_t)c->cap * c->npad));
+        if (!c->cnt_t[k]) CUDA_TRY(cudaMalloc((void **)&c->cnt_t[k], sizeof(int) * (size_t)c->npad));
+        c->sub_cap[k] = c->cap;
+        c->sub_gen[k] = -1;
+    }
+    if (c->sub_gen[k] != c->list_gen) {
+        if (!c->tsort) CUDA_TRY(cudaMalloc((void **)&c->tsort, (size_t)c->ncap));
+        if (c->tsort_gen != c->list_gen) {
+            k_sorted_types<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->xs, c->tsort, c->n);
+            c->tsort_gen = c->list_gen;
+        }
+        k_typed_sublist<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->tsort, c->nbr_t[k], c->cnt_t[k], c->n, c->npad, a, b);
+        KERNEL_CHECK();
+        c->sub_gen[k] = c->list_gen;
+    }
+    *nbr_out = c->nbr_t[k];
+    *cnt_out = c->cnt_t[k];
+    return 0;
+}
+
 template <int TPA, bool FIJ>
 static void launch_lj_list_f(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
-                             double *part, const unsigned char *cls, int want)
+                             double *part, const unsigned char *cls, int want, const unsigned *nbr, const int *cnt)
 {
-#define LJ_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, part, c->fij, c->nmol, cls, want
+#define LJ_ARGS c->xs, nbr, cnt, c->order, c->f4, c->n, c->npad, apc, P, B, part, c->fij, c->nmol, cls, want
     if (typed) {
         if (store) k_lj_list<TPA, true, true, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
         else       k_lj_list<TPA, true, false, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
@@ -483,20 +562,21 @@ static void launch_lj_list_f(sepgpu_ctx *c, int grid, int apc, bool typed, bool 
 
 template <int TPA>
 static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
-                           double *part, const unsigned char *cls, int want)
+                           double *part, const unsigned char *cls, int want, const unsigned *nbr, const int *cnt)
 {
-    if (c->fij) launch_lj_list_f<TPA, true>(c, grid, apc, typed, store, P, B, part, cls, want);
-    else launch_lj_list_f<TPA, false>(c, grid, apc, typed, store, P, B, part, cls, want);
+    if (c->fij) launch_lj_list_f<TPA, true>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt);
+    else launch_lj_list_f<TPA, false>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt);
 }
 
 static void launch_lj_list_tpa(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
-                               double *part, const unsigned char *cls, int want)
+                               double *part, const unsigned char *cls, int want, const unsigned *nbr = NULL, const int *cnt = NULL)
 {
+    if (!nbr) { nbr = c->nbr; cnt = c->cnt; }
     switch (c->tpa) {
-    case 1: launch_lj_list<1>(c, grid, apc, typed, store, P, B, part, cls, want); break;
-    case 2: launch_lj_list<2>(c, grid, apc, typed, store, P, B, part, cls, want); break;
-    case 4: launch_lj_list<4>(c, grid, apc, typed, store, P, B, part, cls, want); break;
-    default: launch_lj_list<8>(c, grid, apc, typed, store, P, B, part, cls, want); break;
+    case 1: launch_lj_list<1>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt); break;
+    case 2: launch_lj_list<2>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt); break;
+    case 4: launch_lj_list<4>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt); break;
+    default: launch_lj_list<8>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt); break;
     }
 }
 
@@ -560,8 +640,11 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
             ktimer_end(c, &c->t_force);
         }
     } else {
+        const unsigned *nbr = NULL;
+        const int *cnt = NULL;
+        if (typed && c->typed_sublist && (rc = typed_sublist_get(c, types, &nbr, &cnt))) return rc;
         ktimer_begin(c, &c->t_force);
-        launch_lj_list_tpa(c, grid, apc, typed, store, P, B, c->partial, NULL, 0);
+        launch_lj_list_tpa(c, grid, apc, typed, store, P, B, c->partial, NULL, 0, nbr, cnt);
         ktimer_end(c, &c->t_force);
     }
     KERNEL_CHECK();

@@ -114,6 +114,148 @@ k_coulomb_list(const d4 *__restrict__ xs, const double *__restrict__ zs, const u
         for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
 }
 
+// ---- Coulomb, Verlet list, second kernel (option coulomb_kernel = 2) ---------------------------------------------------
+// Same sums as k_coulomb_list, organised like the Lennard-Jones list kernel (sepgpu_force.cu):
+//  * the charge rides in .w of a per-call copy xq[s] = {x, y, z, z_s} of the sorted coordinates, so a pair costs ONE
+//    32-byte gather instead of a position gather plus a charge gather (k_make_xq: 64 B/atom per call);
+//  * four list entries per 128-bit streaming load, issued one chunk ahead;
+//  * two pairs per straight-line block, branch-free: out-of-range pairs run the same arithmetic with the partner
+//    charge selected to zero (the reference's |z| < DBL_EPSILON skip, source/sepcoulomb.c:106, removes exact zeros);
+//  * 1/r from the MUFU seed and ONE third-order step (5 FP64 operations instead of 12);
+//  * z_i is applied once per atom, and the virial comes from the full-list identity
+//        sum_ij g_ij (x) d_ij = 2 sum_i F_i (x) x_i - sum_ij g_ij (x) S_ij      (see lj_pair in sepgpu_force.cu).
+// No molecule-pair table here: contexts that carry Fij stay on k_coulomb_list.
+struct CoulDev { double cf2, icf2, twoicf; };
+
+__device__ __forceinline__ double rsqrt_3rd(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // x y^2 = 1 - e  =>  1/sqrt(x) = y (1 + e/2 + 3 e^2/8 + O(e^3));  |e| <= 2^-19 leaves < 2^-58
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5) * e;
+    return fma(y, p, y);
+}
+
+struct CoulAcc {
+    double fx, fy, fz, ua;                   // per atom, in units of z_i
+    double v[6];                             // per thread
+};
+
+__device__ __forceinline__ void coul_virial(double *v, double gx, double gy, double gz, double sx, double sy, double sz)
+{
+    v[0] = fma(gx, sx, v[0]); v[1] = fma(gx, sy, v[1]); v[2] = fma(gx, sz, v[2]);
+    v[3] = fma(gy, sy, v[3]); v[4] = fma(gy, sz, v[4]); v[5] = fma(gz, sz, v[5]);
+}
+
+__device__ __forceinline__ void coul_pair2(const d4 &pi, const d4 &p0, const d4 &p1, unsigned e0, unsigned e1, bool valid1,
+                                           const CoulDev &P, const BoxC &B, CoulAcc &A)
+{
+    double dx0 = pi.x - p0.x, dy0 = pi.y - p0.y, dz0 = pi.z - p0.z;
+    double dx1 = pi.x - p1.x, dy1 = pi.y - p1.y, dz1 = pi.z - p1.z;
+    const int c0 = (int)(e0 >> SEPGPU_SHIFT_BITS), c1 = valid1 ? (int)(e1 >> SEPGPU_SHIFT_BITS) : 13;
+    const bool shifted = (c0 != 13) | (c1 != 13);
+    if (shifted) { apply_image_c(c0, B, dx0, dy0, dz0); apply_image_c(c1, B, dx1, dy1, dz1); }
+    const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+    const double r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+    const bool in0 = __double_as_longlong(r20) < __double_as_longlong(P.cf2);                 // r2 < cf2, :118
+    const bool in1 = (__double_as_longlong(r21) < __double_as_longlong(P.cf2)) && valid1;
+    const double q0 = in0 ? p0.w : 0.0, q1 = in1 ? p1.w : 0.0;                               // partner charge, masked
+    const double y0 = rsqrt_3rd(r20), y1 = rsqrt_3rd(r21);
+    const double f0 = q0 * (fma(y0, y0, -P.icf2) * y0);             // z_j (1/r^2 - 1/cf^2)/r, :121
+    const double f1 = q1 * (fma(y1, y1, -P.icf2) * y1);
+    const double ra = r20 * y0, rb = r21 * y1;                      // r
+    const double u0 = q0 * (y0 + fma(ra, P.icf2, -P.twoicf));       // z_j (1/r + (r - cf)/cf^2 - 1/cf), :150
+    const double u1 = q1 * (y1 + fma(rb, P.icf2, -P.twoicf));
+    A.fx = fma(f0, dx0, A.fx); A.fy = fma(f0, dy0, A.fy); A.fz = fma(f0, dz0, A.fz);
+    A.fx = fma(f1, dx1, A.fx); A.fy = fma(f1, dy1, A.fy); A.fz = fma(f1, dz1, A.fz);
+    A.ua += u0; A.ua += u1;
+    if (shifted) {                                                  // boundary-crossing pairs: - g (x) S
+        const double zi = pi.w;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        apply_image_c(c0, B, sx, sy, sz);
+        double g = zi * f0;
+        coul_virial(A.v, g * dx0, g * dy0, g * dz0, sx, sy, sz);
+        sx = sy = sz = 0.0;
+        apply_image_c(c1, B, sx, sy, sz);
+        g = zi * f1;
+        coul_virial(A.v, g * dx1, g * dy1, g * dz1, sx, sy, sz);
+    }
+}
+
+__global__ void k_make_xq(const d4 *__restrict__ xs, const double *__restrict__ z, const int *__restrict__ order,
+                          d4 *__restrict__ xq, int n)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    d4 p = xs[s];
+    p.w = z[order[s]];
+    xq[s] = p;
+}
+
+#define COUL2_MIN_CTAS 5
+template <bool STORE>
+__global__ void __launch_bounds__(FORCE_BLOCK, COUL2_MIN_CTAS)
+k_coulomb_list2(const d4 *__restrict__ xq, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
+                const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int atoms_per_cta,
+                CoulDev P, BoxC B, double *__restrict__ partial)
+{
+    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
+    CoulAcc A;
+#pragma unroll
+    for (int q = 0; q < 6; q++) A.v[q] = 0.0;
+    double usum = 0.0;
+    const int first = blockIdx.x * atoms_per_cta;
+    const int last = min(n, first + atoms_per_cta);
+    const uint4 *nbrv = reinterpret_cast<const uint4 *>(nbr);
+
+    for (int s = first + (int)threadIdx.x; s < last; s += FORCE_BLOCK) {
+        const d4 pi = xq[s];
+        const int m = cnt[s];
+        const int nch = (m + 3) >> 2;
+        const uint4 *row = nbrv + s;
+        A.fx = A.fy = A.fz = 0.0; A.ua = 0.0;
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        if (nch > 0) cur = __ldcs(row);
+        for (int c = 0; c < nch; c++) {
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (c + 1 < nch) nxt = __ldcs(row + (size_t)(c + 1) * npad);
+            const int left = m - 4 * c;                          // >= 1 valid entries in this chunk
+            {
+                const bool v1 = left > 1;
+                const d4 p0 = xq[cur.x & SEPGPU_INDEX_MASK];
+                const d4 p1 = xq[(v1 ? cur.y : cur.x) & SEPGPU_INDEX_MASK];
+                coul_pair2(pi, p0, p1, cur.x, cur.y, v1, P, B, A);
+            }
+            if (left > 2) {
+                const bool v3 = left > 3;
+                const d4 p2 = xq[cur.z & SEPGPU_INDEX_MASK];
+                const d4 p3 = xq[(v3 ? cur.w : cur.z) & SEPGPU_INDEX_MASK];
+                coul_pair2(pi, p2, p3, cur.z, cur.w, v3, P, B, A);
+            }
+            cur = nxt;
+        }
+        const double zi = pi.w;
+        const double fx = zi * A.fx, fy = zi * A.fy, fz = zi * A.fz;
+        usum = fma(zi, A.ua, usum);
+        const int i = order[s];
+        if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0; f4[i] = o; }
+        else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
+        coul_virial(A.v, fx + fx, fy + fy, fz + fz, pi.x, pi.y, pi.z);      // 2 F_i (x) x_i
+    }
+    double acc[SEPGPU_NPART_F];
+    acc[0] = 0.0;
+    acc[1] = usum;
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc[2 + q] = A.v[q];
+    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
+    }
+}
+
 __device__ __forceinline__ int share_tab_c(const int *__restrict__ tab, int width, int a, int b)
 {
     for (int k = 0; k < width; k++) {
@@ -229,6 +371,23 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
     if (!c->list_valid) {
         sepgpu_set_error("coulomb_sf: no neighbour list (call sep_force_pairs first, as the reference requires)");
         return SEPGPU_ESTATE;
+    }
+    if (c->coulomb_kernel == 2 && !c->fij && !c->dd) {
+        if (!c->xq) CUDA_TRY(cudaMalloc((void **)&c->xq, sizeof(d4) * (size_t)c->ncap));
+        CoulDev P; P.cf2 = cf * cf; P.icf2 = 1.0 / P.cf2; P.twoicf = 2.0 / cf;
+        // contiguous ranges of the sorted atoms per CTA, as in the Lennard-Jones list kernel
+        int grid = 148 * 64;
+        int apc = (c->n + grid - 1) / grid;
+        apc = ((apc + FORCE_BLOCK - 1) / FORCE_BLOCK) * FORCE_BLOCK;
+        grid = (c->n + apc - 1) / apc;
+        ktimer_begin(c, &c->t_coul);
+        k_make_xq<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->xs, c->z, c->order, c->xq, c->n);
+        if (store) k_coulomb_list2<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial);
+        else       k_coulomb_list2<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial);
+        ktimer_end(c, &c->t_coul);
+        KERNEL_CHECK();
+        c->f_zero = false;
+        return sepgpu_finalize_force(c, grid, 0.5, 4);
     }
     if (!c->zs) CUDA_TRY(cudaMalloc((void **)&c->zs, sizeof(double) * (size_t)c->n));
     k_sort_charges<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->z, c->order, c->zs, c->n);

@@ -39,6 +39,7 @@ struct __align__(16) i4 { int x, y, z, w; };
 #define SEPGPU_NPART_F 8      // force kernels : e, ecoul, 6 virial
 #define SEPGPU_NPART_I 12     // integrators   : sum m vh^2, 6 kin_P, max d2, sum m v^2, 3 momentum
 #define SEPGPU_MAX_BLOCKS_PARTIAL 65536
+#define SEPGPU_NSUB 4         // typed sub-lists kept per list build
 
 // device-resident scalar block (one per context)
 struct DevScalars {
@@ -113,6 +114,18 @@ struct sepgpu_ctx {
     bool list_valid;
     unsigned list_opt;
     bool sorted_identity;  // brute mode: xs is x4 in original order
+    long long list_gen;    // bumped by every successful list build (keys the derived lists below)
+
+    // typed sub-lists (option typed_sublist): for a typed Lennard-Jones call ("OO" in water) the entries of the
+    // full list whose partner has the wanted type, same chunked layout, rebuilt lazily once per list build
+    unsigned *nbr_t[SEPGPU_NSUB];
+    int *cnt_t[SEPGPU_NSUB];
+    int sub_key[SEPGPU_NSUB];        // t0 | t1 << 8 with t0 <= t1; 0 = slot unused
+    long long sub_gen[SEPGPU_NSUB];  // list_gen the slot was filled for
+    int sub_cap[SEPGPU_NSUB];        // rows allocated (== cap at allocation time)
+    unsigned char *tsort;            // type char per sorted slot
+    long long tsort_gen;
+    d4 *xq;                          // coulomb_kernel 2: {continuous x, y, z, charge} per sorted slot, refreshed per call
 
     // topology
     unsigned *blist, *alist, *dlist;
@@ -151,6 +164,8 @@ struct sepgpu_ctx {
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
     int force_grid;              // CTAs of the list force kernel (0 = default)
     int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
+    int coulomb_kernel;          // 1: first list Coulomb kernel (hardware-verified default); 2: k_coulomb_list2
+    int typed_sublist;           // typed Lennard-Jones calls walk a per-type sub-list (0 = off, default)
     int overlap;                 // decomposed runs: halo refresh beside an interior-only force pass (default 0: measured slower,
                                  // the boundary pass is a nearly empty wave that costs more than the 20 us refresh)
 

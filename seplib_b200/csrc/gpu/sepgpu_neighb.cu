@@ -631,6 +631,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (c->scal_host->max_neighb <= c->cap) {
             c->list_valid = true; c->list_opt = opt; c->sorted_identity = false; c->xs_current = true;
             c->zs_valid = false;
+            c->list_gen++;
             c->grid_n[0] = nx; c->grid_n[1] = ny; c->grid_n[2] = nz;
             return 0;
         }

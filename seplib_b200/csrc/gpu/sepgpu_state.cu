@@ -82,6 +82,8 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->prefilter = 1;
     c->overlap = 0;
     c->single_type = 'A';
+    c->coulomb_kernel = 1;
+    c->typed_sublist = 0;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
     const size_t n = npart;
@@ -100,6 +102,19 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     KERNEL_CHECK();
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->f_zero = true;
+    // SEPGPU_OPTS="name=value,name=value": options for programs that only see the sep_* API (prgs/*.c)
+    const char *opts = getenv("SEPGPU_OPTS");
+    if (opts && *opts) {
+        char buf[512];
+        strncpy(buf, opts, sizeof buf - 1); buf[sizeof buf - 1] = 0;
+        for (char *tok = strtok(buf, ","); tok; tok = strtok(NULL, ",")) {
+            char *eq = strchr(tok, '=');
+            if (!eq) { sepgpu_set_error("SEPGPU_OPTS: '%s' is not name=value", tok); sepgpu_destroy(c); return SEPGPU_EINVAL; }
+            *eq = 0;
+            const int rc = sepgpu_set_option(c, tok, atoll(eq + 1));
+            if (rc) { sepgpu_destroy(c); return rc; }
+        }
+    }
     *out = c;
     return 0;
 }
@@ -121,6 +136,9 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->cls) cudaFree(c->cls);
     if (c->x0) cudaFree(c->x0);
     if (c->prevf4) cudaFree(c->prevf4);
+    for (int k = 0; k < SEPGPU_NSUB; k++) { if (c->nbr_t[k]) cudaFree(c->nbr_t[k]); if (c->cnt_t[k]) cudaFree(c->cnt_t[k]); }
+    if (c->tsort) cudaFree(c->tsort);
+    if (c->xq) cudaFree(c->xq);
     if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
@@ -678,6 +696,8 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
+    if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
+    if (!strcmp(name, "typed_sublist")) { c->typed_sublist = value != 0; return 0; }
     if (!strcmp(name, "force_grid")) { c->force_grid = value > 0 && value <= SEPGPU_MAX_BLOCKS_PARTIAL ? (int)value : 0; return 0; }
     if (!strcmp(name, "time_kernels")) {
         if (value) { if (ktimer_enable(&c->t_force) || ktimer_enable(&c->t_build) || ktimer_enable(&c->t_intgr) ||

@@ -22,8 +22,9 @@ FAST = ("not prg and not md_trajectory and not lj_loop and not molecular_pressur
         "and not compress_box and not berendsen and not slit_pore")
 
 
-def _run(args, timeout=1500):
-    r = subprocess.run([sys.executable, RUNNER, *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+def _run(args, timeout=1500, env=None):
+    r = subprocess.run([sys.executable, RUNNER, *args], capture_output=True, text=True, timeout=timeout, cwd=ROOT,
+                       env=dict(os.environ, **(env or {})))
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
@@ -36,3 +37,11 @@ def test_gpu_parity_tests_pass_on_the_emulated_kernels():
     n = _run(["tests/test_gpu_lj.py", "tests/test_gpu_more.py", "tests/test_gpu_zz_next.py", "-m", "gpu", "-q", "-x",
               "-k", FAST, "-p", "no:cacheprovider"])
     assert n >= 20, n
+
+
+def test_optin_kernels_pass_on_the_emulator():
+    """coulomb_kernel=2 and typed_sublist=1 (tests/test_gpu_zzz_options.py): skipped on hardware until a GPU run has
+    confirmed them, exercised here on every CPU round."""
+    n = _run(["tests/test_gpu_zzz_options.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
+             env={"SEPGPU_TEST_UNVERIFIED": "1"})
+    assert n >= 6, n

@@ -1,0 +1,153 @@
+"""Opt-in kernels (sepgpu_set_option / SEPGPU_OPTS): the second list Coulomb kernel (coulomb_kernel=2) and typed
+sub-lists (typed_sublist=1).  Same parity bar as the default kernels they stand in for: forces 1e-10 of the oracle,
+sums 1e-10, and -- because they walk the same pairs -- agreement with the default kernels to rounding.
+
+Status: written without access to hardware.  Their logic is verified on the CPU kernel emulator
+(tests/test_cpu_emu.py runs this file with SEPGPU_TEST_UNVERIFIED=1); on a GPU box they are skipped until a hardware
+run has confirmed them -- set SEPGPU_TEST_UNVERIFIED=1 to run them there.  The options default to off, so nothing the
+default suite or bench.py measures goes through these kernels.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import common as cm
+from seplib_b200 import capi
+from test_gpu_more import tiled_water
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SEPGPU_TEST_UNVERIFIED") != "1",
+                                 reason="opt-in kernels verified on the CPU emulator only; SEPGPU_TEST_UNVERIFIED=1 runs them")]
+
+FT = 1e-10
+
+
+def _water_system(reps, opts):
+    x, types, z, m, mol, L, _ = tiled_water(reps)
+    n = len(x)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_TYPE, types); s.put(capi.F_Z, z); s.put(capi.F_M, m); s.put(capi.F_MOLINDEX, mol)
+    for k, v in opts.items():
+        s.call("sepgpu_set_option", k.encode(), v)
+    return s, x, types, z, mol, L
+
+
+def _water_forces(s, L, cf, skin, lj=True, coulomb=True):
+    sys_ = capi.make_sys(L, cf, 5e-4, skin=skin)
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.EXCL_SAME_MOL)
+    p = capi.lj_param(2.5, kind="lj_shift")
+    if lj:
+        s.call("sepgpu_force_lj", C.byref(sys_), b"OO", C.byref(p), cm.EXCL_SAME_MOL, 1)
+    if coulomb:
+        s.call("sepgpu_coulomb_sf", C.byref(sys_), cf, cm.EXCL_SAME_MOL)
+    return s.get(capi.F_F), s.scalars()
+
+
+@pytest.mark.parametrize("opts", [{"coulomb_kernel": 2}, {"typed_sublist": 1}, {"coulomb_kernel": 2, "typed_sublist": 1}],
+                         ids=["coulomb2", "sublist", "both"])
+def test_water_forces_with_optin_kernels_match_oracle(opts):
+    """prg3-style water step (typed 'OO' Lennard-Jones + shifted-force Coulomb on the same list) against the oracle
+    (reference source/sepprfrc.c:94-224, source/sepcoulomb.c:96-160)."""
+    cf, skin = 2.9, 0.25
+    s, x, types, z, mol, L = _water_system(2, opts)
+    n = len(x)
+    t = cm.Topo(n); t.molindex[:] = mol
+    pairs = np.ascontiguousarray(cm.oracle_pairs(x, L, cf, skin, opt=cm.EXCL_SAME_MOL, topo=t, max_pairs=4_000_000), dtype=np.int32)
+    orc = cm.oracle(); length = cm.dvec3(L)
+    fref = np.zeros((n, 3)); rref = cm.OrcRet()
+    orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pairs), len(pairs), b"OO", 2.5,
+                             cm.POT_LJ_SHIFT, None, cm.ptr(fref), C.byref(rref))
+    orc.orc_coulomb_sf_list(n, cm.ptr(x), cm.ptr(z), cm.ptr(length), cm.ptr(pairs), len(pairs), cf, cm.ptr(fref), C.byref(rref))
+    f, sc = _water_forces(s, L, cf, skin)
+    assert cm.rel_force_err(f, fref) <= FT
+    assert abs(sc.ecoul - rref.ecoul) <= FT * abs(rref.ecoul)
+    assert abs(sc.epot - rref.epot) <= FT * abs(rref.epot)
+    assert np.abs(np.array(sc.pot_P[:]) - np.array(rref.pot_P[:])).max() <= FT * np.abs(np.array(rref.pot_P[:])).max()
+    s.close()
+
+
+def test_optin_kernels_agree_with_the_default_ones_over_steps():
+    """The same water system stepped with the default kernels and with both options on: per-step forces and sums agree
+    to rounding while the list is rebuilt along the way (the sub-list must follow every rebuild)."""
+    cf, skin, dt = 2.9, 0.25, 5e-4
+    runs = []
+    for opts in ({}, {"coulomb_kernel": 2, "typed_sublist": 1}):
+        s, x, types, z, mol, L = _water_system(2, opts)
+        rng = np.random.default_rng(3)
+        s.put(capi.F_M, np.full(len(x), 1e6))                       # no bonded terms here: very heavy atoms, near-ballistic motion
+        s.put(capi.F_V, rng.normal(0.0, 40.0, size=x.shape))        # fast atoms: a rebuild every ~3 steps
+        sys_ = capi.make_sys(L, cf, dt, skin=skin)
+        p = capi.lj_param(2.5, kind="lj_shift")
+        rec = []
+        for step in range(12):
+            s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+            if step == 0 or s.scalars().neighb_flag:
+                s.call("sepgpu_neighb_build", C.byref(sys_), cm.EXCL_SAME_MOL)
+            s.call("sepgpu_force_lj", C.byref(sys_), b"OO", C.byref(p), cm.EXCL_SAME_MOL, 1)
+            s.call("sepgpu_coulomb_sf", C.byref(sys_), cf, cm.EXCL_SAME_MOL)
+            f = s.get(capi.F_F); sc = s.scalars()
+            rec.append((f.copy(), sc.epot, sc.ecoul, np.array(sc.pot_P[:]), sc.nbuild))
+            s.call("sepgpu_leapfrog", C.byref(sys_))
+        runs.append(rec)
+        s.close()
+    assert runs[0][-1][4] >= 3, "the test is meant to cross several rebuilds"
+    for (f0, e0, c0, p0, b0), (f1, e1, c1, p1, b1) in zip(*runs):
+        assert b0 == b1
+        assert cm.rel_force_err(f1, f0) <= 1e-9
+        assert abs(e1 - e0) <= 1e-9 * abs(e0) and abs(c1 - c0) <= 1e-9 * abs(c0)
+        assert np.abs(p1 - p0).max() <= 1e-9 * np.abs(p0).max()
+
+
+def test_typed_sublists_for_three_type_pairs():
+    """Two species, AA / AB / BB calls with different cutoffs and potentials (prg8-style): every call walks its own
+    sub-list; epot is assigned by each list call (reference source/sepprfrc.c:222)."""
+    x, L = cm.lattice(10, 0.8, jitter=0.1, seed=11)
+    n = len(x)
+    cf, skin = 2.5, 0.25
+    rng = np.random.default_rng(5)
+    types = np.where(rng.random(n) < 0.4, ord("B"), ord("A")).astype(np.uint8)
+    pp = np.ascontiguousarray(cm.oracle_pairs(x, L, cf, skin), dtype=np.int32)
+    orc = cm.oracle()
+    fref = np.zeros((n, 3)); rref = cm.OrcRet(); length = cm.dvec3([L] * 3)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_TYPE, types)
+    s.call("sepgpu_set_option", b"typed_sublist", 1)
+    sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
+    for rep in range(2):                                             # second round reuses the cached sub-lists
+        fref[:] = 0.0
+        s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+        rref = cm.OrcRet()
+        for tsel, rc_, pot, kind in ((b"AA", 2.5, cm.POT_LJ_SHIFT, "lj_shift"), (b"AB", 2.0, cm.POT_LJ, "lj"),
+                                     (b"BB", 2 ** (1 / 6), cm.POT_WCA, "wca")):
+            orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pp), len(pp), tsel, rc_, pot,
+                                     None, cm.ptr(fref), C.byref(rref))
+            p = capi.lj_param(rc_, kind=kind)
+            s.call("sepgpu_force_lj", C.byref(sys_), tsel, C.byref(p), cm.ALL, 1)
+        f = s.get(capi.F_F); sc = s.scalars()
+        assert cm.rel_force_err(f, fref) <= FT
+        assert abs(sc.epot - rref.epot) <= 1e-10 * max(abs(rref.epot), 1.0)
+        P = np.array(sc.pot_P[:]); Pref = np.array(rref.pot_P[:])
+        assert np.abs(P - Pref).max() <= 1e-10 * np.abs(Pref).max()
+    s.close()
+
+
+def test_options_through_the_environment(tmp_path):
+    """SEPGPU_OPTS carries the options to programs that only see the sep_* API; an unknown name is an error."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import os\n"
+            "from seplib_b200 import capi\n"
+            "if os.environ.get('SEPGPU_EMU_LIB'): capi.LIB_PATH = os.environ['SEPGPU_EMU_LIB']\n"
+            "try:\n"
+            "    s = capi.System(64)\n"
+            "    print('created')\n"
+            "except Exception as e:\n"
+            "    print('refused', e)\n") % (cm.ROOT, os.path.join(cm.ROOT, "tests"))
+    for opts, want in (("coulomb_kernel=2,typed_sublist=1", "created"), ("no_such_option=1", "refused")):
+        env = dict(os.environ); env["SEPGPU_OPTS"] = opts
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert want in r.stdout, (opts, r.stdout, r.stderr)
