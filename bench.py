@@ -453,7 +453,7 @@ def run_molecular(args, emit, local_rank):
                    "box": list(map(float, w["L"])), "cells": list(gsys.nsubbox[:]), "skin": args.skin, "dt": P["dt"],
                    "parallelism": "single GPU", "l2": "inputs larger than L2 (Verlet list %.0f MB)" % (n * full_entries * 4 / 1e6),
                    "list_rebuilds_in_timed_region": nbuild, "half_pairs_per_atom": full_entries / 2.0,
-                   "epot_per_atom": epotN, "ekin_per_atom": ekinN},
+                   "epot_per_atom": epotN, "ekin_per_atom": ekinN, "sepgpu_opts": os.environ.get("SEPGPU_OPTS", "")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": K * per_step + nbuild * 11, "clocks": clocks,
         "kernel_ms": {k: {"total_ms": a, "launches": b} for k, (a, b) in kt.items()},
     })
@@ -846,7 +846,7 @@ def main():
                    "rank0_owned_halo_atoms": list(own_halo),
                    "l2": "inputs larger than L2 (xs 32 MB + Verlet list %.0f MB + state > 126 MB per GPU)" % (own_halo[0] * pairs_per_atom * 8 / 1e6),
                    "list_rebuilds_in_timed_region": nbuild, "half_pairs_per_atom": pairs_per_atom,
-                   "epot_per_atom": epotN, "ekin_per_atom": ekinN},
+                   "epot_per_atom": epotN, "ekin_per_atom": ekinN, "sepgpu_opts": os.environ.get("SEPGPU_OPTS", "")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "kernel_ms": {k: {"total_ms": a, "launches": b} for k, (a, b) in kt.items()},
     }

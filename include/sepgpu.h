@@ -194,6 +194,15 @@ long long sepgpu_get_pairs(sepgpu_ctx *ctx, int *pairs, long long max_pairs);
 int sepgpu_request_rebuild(sepgpu_ctx *ctx);
 /* tuning: lanes cooperating on one atom in the list force kernels (1,2,4,8,16,32; 0 = default) */
 int sepgpu_set_option(sepgpu_ctx *ctx, const char *name, long long value);
+/* Options (also through the environment, SEPGPU_OPTS="name=value,..." read by sepgpu_create):
+ *   tpa, prefilter, overlap, force_grid, time_kernels, neighb_cap      tuning / measurement
+ *   coulomb_kernel = 1 | 2     list Coulomb kernel: first version | charge-in-record, branch-free (default 1)
+ *   typed_sublist  = 0 | 1     typed Lennard-Jones calls walk a per-type sub-list (default 0)
+ *   cell_order     = 0 | 1     slots inside a cell by atom index | along a Morton curve of 4^3 sub-cells (default 0)
+ *   pair_tile      = 0 | 1     lists hold rows per PAIR of sorted atoms, served by k_lj_pairtile; uncharged single-GPU
+ *                              systems only -- Coulomb and DPD need per-atom rows (default 0)
+ * sepgpu_get_option also answers "list_pair" (1 when the current list is in pair-tile format). */
+int sepgpu_get_option(sepgpu_ctx *ctx, const char *name, long long *value);
 
 /* ---- spatial domain decomposition over the GPUs of one box (no reference counterpart: the reference
  * is single-address-space OpenMP).  One process per GPU; slabs of whole cell layers along z; halo

@@ -126,7 +126,7 @@ SEPGPU_SYMBOLS = [
     "sepgpu_torsion_ryckaert", "sepgpu_nosehoover", "sepgpu_nosehoover_type", "sepgpu_set_alpha",
     "sepgpu_leapfrog", "sepgpu_verlet_dpd", "sepgpu_reset_momentum", "sepgpu_scale_positions",
     "sepgpu_read_scalars", "sepgpu_sync", "sepgpu_get_pairs", "sepgpu_request_rebuild",
-    "sepgpu_set_option", "sepgpu_timer_start", "sepgpu_timer_stop", "sepgpu_kernel_time",
+    "sepgpu_set_option", "sepgpu_get_option", "sepgpu_timer_start", "sepgpu_timer_stop", "sepgpu_kernel_time",
     "sepgpu_peak_fp64", "sepgpu_peak_copy", "sepgpu_flush_l2",
     "sepgpu_fij_enable", "sepgpu_fij_reset", "sepgpu_fij_get", "sepgpu_scale_box", "sepgpu_relax_temp", "sepgpu_force_x0", "sepgpu_fp", "sepgpu_langevin_gjf",
     "sepgpu_dd_unique_id", "sepgpu_dd_init", "sepgpu_dd_set_owned", "sepgpu_dd_layers",
@@ -259,6 +259,7 @@ def load():
     lib.sepgpu_get_pairs.argtypes = [ctx, C.c_void_p, C.c_longlong]
     lib.sepgpu_request_rebuild.argtypes = [ctx]
     lib.sepgpu_set_option.argtypes = [ctx, C.c_char_p, C.c_longlong]
+    lib.sepgpu_get_option.argtypes = [ctx, C.c_char_p, C.POINTER(C.c_longlong)]
     lib.sepgpu_timer_start.argtypes = [ctx]
     lib.sepgpu_timer_stop.argtypes = [ctx, C.POINTER(C.c_float)]
     lib.sepgpu_kernel_time.argtypes = [ctx, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]

@@ -315,6 +315,161 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
     }
 }
 
+// ---- Lennard-Jones, pair-tile list (option pair_tile) ------------------------------------------------------------------
+// k_lj_list is bound by the L1 data pipe: every listed neighbour is a 32-byte gather from a line no other lane shares
+// (~22 wavefronts per warp-wide gather where 8 would do).  Here one THREAD owns the two sorted atoms (2t, 2t+1) and walks
+// the union of their neighbour rows (built by k_build_tile2<SEP_ALL, true>): one gather serves two atoms, and the two
+// dependent FP64 chains of a step belong to the two atoms.  Entries carry membership flags, so each atom still sums
+// exactly its own list; a pair split over two list-build tiles walks its two single rows one after the other.
+struct PairAcc2 {
+    double fxa, fya, fza, fxb, fyb, fzb;    // per pair of atoms, in units of 48 eps
+    double u;                               // per thread
+    int nin;
+    double v[6];
+};
+
+template <bool TYPED>
+__device__ __forceinline__ void lj_tile_step(const d4 &pa, const d4 &pb, const d4 &pj, unsigned e, int ta, int tb,
+                                             const LJDev &P, const BoxDev &B, PairAcc2 &A)
+{
+    double dxa = pa.x - pj.x, dya = pa.y - pj.y, dza = pa.z - pj.z;
+    double dxb = pb.x - pj.x, dyb = pb.y - pj.y, dzb = pb.z - pj.z;
+    const int code = (int)SEPGPU_PT_CODE(e);
+    if (code != 13) { apply_image(code, B, dxa, dya, dza); apply_image(code, B, dxb, dyb, dzb); }
+    double r2a = fma(dza, dza, fma(dya, dya, dxa * dxa));
+    double r2b = fma(dzb, dzb, fma(dyb, dyb, dxb * dxb));
+    bool ina = (__double_as_longlong(r2a) < __double_as_longlong(P.cf2)) && !(e & SEPGPU_PT_SKIP_A);
+    bool inb = (__double_as_longlong(r2b) < __double_as_longlong(P.cf2)) && !(e & SEPGPU_PT_SKIP_B);
+    if (TYPED) {
+        const int tj = tag_type(pj.w);
+        ina = ina && ((ta == P.t0 && tj == P.t1) || (ta == P.t1 && tj == P.t0));     // source/sepprfrc.c:171-172
+        inb = inb && ((tb == P.t0 && tj == P.t1) || (tb == P.t1 && tj == P.t0));
+    }
+    // an entry that is the partner atom itself has r2 == 0 for it (and its skip flag set): keep the arithmetic finite
+    r2a = ina ? r2a : 1.0;
+    r2b = inb ? r2b : 1.0;
+    const double a0 = P.sig2 * fast_rcp3(r2a), a1 = P.sig2 * fast_rcp3(r2b);
+    double b0 = a0 * a0 * a0, b1 = a1 * a1 * a1;
+    double f0 = b0 * (b0 - P.awh) * a0, f1 = b1 * (b1 - P.awh) * a1;     // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
+    const double u0 = b0 - P.aw, u1 = b1 - P.aw;
+    f0 = ina ? f0 : 0.0; f1 = inb ? f1 : 0.0;
+    b0 = ina ? b0 : 0.0; b1 = inb ? b1 : 0.0;
+    A.fxa = fma(f0, dxa, A.fxa); A.fya = fma(f0, dya, A.fya); A.fza = fma(f0, dza, A.fza);
+    A.fxb = fma(f1, dxb, A.fxb); A.fyb = fma(f1, dyb, A.fyb); A.fzb = fma(f1, dzb, A.fzb);
+    A.u = fma(b0, u0, A.u);
+    A.u = fma(b1, u1, A.u);
+    A.nin += (ina ? 1 : 0) + (inb ? 1 : 0);
+    if (code != 13) {                                               // boundary-crossing pairs: - g (x) S (see lj_pair)
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        apply_image(code, B, sx, sy, sz);
+        double g = P.eps48 * f0;
+        virial_add(A.v, g * dxa, g * dya, g * dza, sx, sy, sz);
+        g = P.eps48 * f1;
+        virial_add(A.v, g * dxb, g * dyb, g * dzb, sx, sy, sz);
+    }
+}
+
+#define PT_MIN_CTAS 5
+template <bool TYPED, bool STORE>
+__global__ void __launch_bounds__(FORCE_BLOCK, PT_MIN_CTAS)
+k_lj_pairtile(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
+              const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int pairs_per_cta,
+              LJDev P, BoxDev B, double *__restrict__ partial)
+{
+    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
+    PairAcc2 A;
+    A.u = 0.0;
+    A.nin = 0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) A.v[q] = 0.0;
+    const int npairs = (n + 1) >> 1;
+    const int first = blockIdx.x * pairs_per_cta;
+    const int last = min(npairs, first + pairs_per_cta);
+    const uint4 *nbrv = reinterpret_cast<const uint4 *>(nbr);
+
+    for (int t = first + (int)threadIdx.x; t < last; t += FORCE_BLOCK) {
+        const int sa = 2 * t, sb = 2 * t + 1;
+        const bool have_b = sb < n;
+        const d4 pa = xs[sa];
+        const d4 pb = xs[have_b ? sb : sa];
+        const int cb = have_b ? cnt[sb] : 0;
+        const bool paired = cb < 0;
+        int ta = 0, tb = 0;
+        if (TYPED) { ta = tag_type(pa.w); tb = tag_type(pb.w); }
+        A.fxa = A.fya = A.fza = A.fxb = A.fyb = A.fzb = 0.0;
+        // pass 0: row sa (both atoms when paired, else atom a alone); pass 1 (split pair only): row sb for atom b alone.
+        // A single row carries no flags and its owner plays the entry's "first atom", so pass 1 runs the same step with
+        // b in the first role (accumulators swapped around it) and the second role masked.
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1 && (paired || !have_b)) break;
+            const int s = pass == 0 ? sa : sb;
+            const int m = pass == 0 ? cnt[sa] : cb;
+            const unsigned kill = (pass == 0 && paired) ? 0u : SEPGPU_PT_SKIP_B;
+            const d4 p1 = pass == 0 ? pa : pb;
+            const d4 p2 = pb;
+            const int t1 = pass == 0 ? ta : tb;
+            if (pass == 1) {
+                double w;
+                w = A.fxa; A.fxa = A.fxb; A.fxb = w; w = A.fya; A.fya = A.fyb; A.fyb = w; w = A.fza; A.fza = A.fzb; A.fzb = w;
+            }
+            const int nch = (m + 3) >> 2;
+            const uint4 *row = nbrv + s;
+            uint4 cur = make_uint4(0, 0, 0, 0);
+            if (nch > 0) cur = __ldcs(row);
+            for (int c = 0; c < nch; c++) {
+                uint4 nxt = make_uint4(0, 0, 0, 0);
+                if (c + 1 < nch) nxt = __ldcs(row + (size_t)(c + 1) * npad);
+                const int left = m - 4 * c;                      // >= 1 valid entries in this chunk
+                {
+                    const d4 pj = xs[cur.x & SEPGPU_PT_INDEX_MASK];
+                    lj_tile_step<TYPED>(p1, p2, pj, cur.x | kill, t1, tb, P, B, A);
+                }
+                if (left > 1) {
+                    const d4 pj = xs[cur.y & SEPGPU_PT_INDEX_MASK];
+                    lj_tile_step<TYPED>(p1, p2, pj, cur.y | kill, t1, tb, P, B, A);
+                }
+                if (left > 2) {
+                    const d4 pj = xs[cur.z & SEPGPU_PT_INDEX_MASK];
+                    lj_tile_step<TYPED>(p1, p2, pj, cur.z | kill, t1, tb, P, B, A);
+                }
+                if (left > 3) {
+                    const d4 pj = xs[cur.w & SEPGPU_PT_INDEX_MASK];
+                    lj_tile_step<TYPED>(p1, p2, pj, cur.w | kill, t1, tb, P, B, A);
+                }
+                cur = nxt;
+            }
+            if (pass == 1) {
+                double w;
+                w = A.fxa; A.fxa = A.fxb; A.fxb = w; w = A.fya; A.fya = A.fyb; A.fyb = w; w = A.fza; A.fza = A.fzb; A.fzb = w;
+            }
+        }
+        {
+            const int i = order[sa];
+            const double fx = P.eps48 * A.fxa, fy = P.eps48 * A.fya, fz = P.eps48 * A.fza;
+            if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0; f4[i] = o; }
+            else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
+            virial_add(A.v, fx + fx, fy + fy, fz + fz, pa.x, pa.y, pa.z);      // 2 F_i (x) x_i
+        }
+        if (have_b) {
+            const int i = order[sb];
+            const double fx = P.eps48 * A.fxb, fy = P.eps48 * A.fyb, fz = P.eps48 * A.fzb;
+            if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0; f4[i] = o; }
+            else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
+            virial_add(A.v, fx + fx, fy + fy, fz + fz, pb.x, pb.y, pb.z);
+        }
+    }
+    double acc[SEPGPU_NPART_F];
+    acc[0] = P.eps4 * A.u - P.shift * (double)A.nin;
+    acc[1] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc[2 + q] = A.v[q];
+    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
+    }
+}
+
 // ---- Lennard-Jones, all pairs (SEP_BRUTE) ------------------------------------------------------------------
 // exact reference arithmetic for the separation (wrapped x, sep_Wrap branches)
 __device__ __forceinline__ int share_tab_f(const int *__restrict__ tab, int width, int a, int b)
@@ -610,6 +765,28 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     }
     // the type test is compiled out when every atom carries the one requested type
     const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
+    if (c->list_pair) {                                  // option pair_tile: rows per pair of sorted atoms
+        if (c->dd || c->fij) { sepgpu_set_error("force_lj: pair-tile lists serve single-GPU runs without the Fij table"); return SEPGPU_ESTATE; }
+        const int npairs = (c->n + 1) / 2;
+        int grid = c->force_grid > 0 ? c->force_grid : FORCE_MAX_GRID;
+        int ppc = (npairs + grid - 1) / grid;
+        ppc = ((ppc + FORCE_BLOCK - 1) / FORCE_BLOCK) * FORCE_BLOCK;
+        grid = (npairs + ppc - 1) / ppc;
+        ktimer_begin(c, &c->t_force);
+#define PT_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, ppc, P, B, c->partial
+        if (typed) {
+            if (store) k_lj_pairtile<true, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
+            else       k_lj_pairtile<true, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
+        } else {
+            if (store) k_lj_pairtile<false, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
+            else       k_lj_pairtile<false, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
+        }
+#undef PT_ARGS
+        ktimer_end(c, &c->t_force);
+        KERNEL_CHECK();
+        c->f_zero = false;
+        return sepgpu_finalize_force(c, grid, 0.5, epot_assign ? 1 : 0);
+    }
     const int tpa = c->tpa;
     // contiguous ranges of the sorted atoms per CTA; several CTAs per SM, a few waves for load balance
     const int groups = FORCE_BLOCK / tpa;

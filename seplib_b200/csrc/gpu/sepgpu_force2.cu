@@ -372,6 +372,13 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
         sepgpu_set_error("coulomb_sf: no neighbour list (call sep_force_pairs first, as the reference requires)");
         return SEPGPU_ESTATE;
     }
+    if (c->list_pair) {
+        // option pair_tile and a consumer of per-atom rows: this context stays on per-atom rows from now on; the list is
+        // rebuilt in that format at the current positions (a superset of what the older list still guarantees)
+        c->need_atom_rows = true;
+        int rcb = sepgpu_neighb_build(c, sys, c->list_opt);
+        if (rcb) return rcb;
+    }
     if (c->coulomb_kernel == 2 && !c->fij && !c->dd) {
         if (!c->xq) CUDA_TRY(cudaMalloc((void **)&c->xq, sizeof(d4) * (size_t)c->ncap));
         CoulDev P; P.cf2 = cf * cf; P.icf2 = 1.0 / P.cf2; P.twoicf = 2.0 / cf;
@@ -517,7 +524,8 @@ extern "C" int sepgpu_force_dpd(sepgpu_ctx *c, const sepgpu_sys *sys, const char
         c->f_zero = false;
         return sepgpu_finalize_force(c, grid, 0.5, 0);        // brute: epot += (source/sepprfrc.c:1196)
     }
-    if (!c->list_valid && (rc = sepgpu_neighb_build(c, sys, opt))) return rc;    // :1021-1031
+    c->need_atom_rows = true;                                                    // (option pair_tile: DPD walks per-atom rows)
+    if ((!c->list_valid || c->list_pair) && (rc = sepgpu_neighb_build(c, sys, opt))) return rc;    // :1021-1031
     if (store) k_dpd<0, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
     else       k_dpd<0, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
     KERNEL_CHECK();

@@ -34,6 +34,12 @@ struct __align__(16) i4 { int x, y, z, w; };
 #define SEPGPU_SHIFT_BITS 26
 #define SEPGPU_INDEX_MASK ((1u << SEPGPU_SHIFT_BITS) - 1u)
 #define SEPGPU_MAX_ATOMS  (1u << SEPGPU_SHIFT_BITS)
+// pair-tile lists (option pair_tile): 25-bit index, bit 25 / bit 31 = the entry is NOT a neighbour of the pair's
+// first / second atom; the image code stays in bits 26..30
+#define SEPGPU_PT_SKIP_A     (1u << 25)
+#define SEPGPU_PT_SKIP_B     (1u << 31)
+#define SEPGPU_PT_INDEX_MASK ((1u << 25) - 1u)
+#define SEPGPU_PT_CODE(e)    (((e) >> SEPGPU_SHIFT_BITS) & 31u)
 
 // number of doubles one block writes as its partial result
 #define SEPGPU_NPART_F 8      // force kernels : e, ecoul, 6 virial
@@ -58,6 +64,7 @@ struct DevScalars {
     int max_half;              // longest reference-style half list at the last build
     int aliased_seen;          // list build: an atom outside [0,L) was filed under an aliased cell (reference behaviour)
     int pad;
+    long long row_entries;     // entries written to list rows at the last build (pair-tile format: union rows)
 };
 
 struct KernelTimer {
@@ -114,6 +121,8 @@ struct sepgpu_ctx {
     bool list_valid;
     unsigned list_opt;
     bool sorted_identity;  // brute mode: xs is x4 in original order
+    bool need_atom_rows;   // a consumer of per-atom rows (Coulomb, DPD) has been seen: pair_tile stays off for this context
+    bool list_pair;        // the list is in pair-tile format (rows per pair of sorted atoms; LJ kernels and export only)
     long long list_gen;    // bumped by every successful list build (keys the derived lists below)
 
     // typed sub-lists (option typed_sublist): for a typed Lennard-Jones call ("OO" in water) the entries of the
@@ -164,6 +173,9 @@ struct sepgpu_ctx {
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
     int force_grid;              // CTAs of the list force kernel (0 = default)
     int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
+    int cell_order;              // slots inside a cell: 0 by atom index (default), 1 along a Morton curve of 4^3 sub-cells
+    unsigned char *subkey;       // [ncap] sub-cell code per atom (cell_order = 1)
+    int pair_tile;               // SEP_ALL lists in pair-tile format + k_lj_pairtile (0 = off, default)
     int coulomb_kernel;          // 1: first list Coulomb kernel (hardware-verified default); 2: k_coulomb_list2
     int typed_sublist;           // typed Lennard-Jones calls walk a per-type sub-list (0 = off, default)
     int overlap;                 // decomposed runs: halo refresh beside an interior-only force pass (default 0: measured slower,

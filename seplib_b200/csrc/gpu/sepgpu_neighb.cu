@@ -47,13 +47,22 @@ __host__ __device__ __forceinline__ void key_cell(int key, const CellGrid &G, in
 
 // ---- binning ------------------------------------------------------------------------------------------
 __global__ void k_cell_count(const d4 *__restrict__ x4, int n, double lsx, double lsy, double lsz,
-                             CellGrid G, int *__restrict__ cell_of, int *__restrict__ cell_cnt, DevScalars *scal)
+                             CellGrid G, int *__restrict__ cell_of, int *__restrict__ cell_cnt, DevScalars *scal,
+                             unsigned char *__restrict__ subkey)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     d4 p = x4[i];
     // source/sepprfrc.c:404-406, IEEE division then truncation
     int cx = (int)__ddiv_rn(p.x, lsx), cy = (int)__ddiv_rn(p.y, lsy), cz = (int)__ddiv_rn(p.z, lsz);
+    if (subkey) {
+        // option cell_order = 1: Morton code of the atom's place inside its cell (4 x 4 x 4 sub-cells); atoms of a cell
+        // are then laid out along that curve, so neighbouring slots are neighbours in space
+        const int ux = min(3, max(0, (int)((__ddiv_rn(p.x, lsx) - cx) * 4.0)));
+        const int uy = min(3, max(0, (int)((__ddiv_rn(p.y, lsy) - cy) * 4.0)));
+        const int uz = min(3, max(0, (int)((__ddiv_rn(p.z, lsz) - cz) * 4.0)));
+        subkey[i] = (unsigned char)((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2) | ((ux & 2) << 2) | ((uy & 2) << 3) | ((uz & 2) << 4));
+    }
     const int nzg = G.dd ? G.nzg : G.nz;
     if (cx < 0 || cx >= G.nx || cy < 0 || cy >= G.ny || cz < 0 || cz >= nzg || !(p.x == p.x)) {
         // The reference does not clamp: it forms the linear index cx + cy*nx + cz*nx*ny and, while that
@@ -174,7 +183,7 @@ __global__ void k_cell_finalize(const int *__restrict__ tmp_slot, const int *__r
                                 const int *__restrict__ cell_start, const d4 *__restrict__ x4,
                                 int n, int *__restrict__ order, int *__restrict__ rank,
                                 d4 *__restrict__ xs, float4 *__restrict__ xf, i4 *__restrict__ cr4,
-                                unsigned char *__restrict__ cls, CellGrid G)
+                                unsigned char *__restrict__ cls, CellGrid G, const unsigned char *__restrict__ subkey)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -182,6 +191,13 @@ __global__ void k_cell_finalize(const int *__restrict__ tmp_slot, const int *__r
     int c = cell_of[i];
     int b = cell_start[c], e = cell_start[c + 1];
     int r = 0;
+    if (subkey) {                                   // option cell_order = 1: (sub-cell Morton code, atom index)
+        const int ki = subkey[i];
+        for (int q = b; q < e; q++) {
+            const int iq = tmp_slot[q], kq = subkey[iq];
+            r += (kq < ki) || (kq == ki && iq < i);
+        }
+    } else
     for (int q = b; q < e; q++) r += tmp_slot[q] < i;
     int s = b + r;
     order[s] = i;
@@ -216,6 +232,7 @@ struct BuildParams {
     int n, npad, cap;
     unsigned opt;
     int prefilter;
+    int spatial_order;      // option cell_order = 1: slots of a cell follow a space-filling curve, not the atom index
 };
 
 // exact reference test; returns accept and the image code chosen by the sep_Wrap branches
@@ -487,7 +504,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 
 #include "sepgpu_neighb_tile.cuh"
 
-__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->stage_needed = 0; s->aliased_seen = 0; }
+__global__ void k_build_begin(DevScalars *s) { s->row_entries = 0; s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->stage_needed = 0; s->aliased_seen = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
 int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local);
@@ -541,23 +558,34 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         c->ncell_cap = nkey;
     }
     int *block_sum = c->cell_cnt + nkey + 1;
-    if (c->cap == 0) c->cap = estimate_cap(c, sys);
+    if (c->cap == 0) {
+        c->cap = estimate_cap(c, sys);
+        if (c->pair_tile) c->cap = (c->cap * 8 / 5 + 7) & ~7;      // a pair's row holds the union of two lists
+    }
 
     const int B = 256, Gn = (c->n + B - 1) / B;
     bool force_exact = false;
     for (int attempt = 0; attempt < 8; attempt++) {
         if (!c->nbr) CUDA_TRY(cudaMalloc((void **)&c->nbr, sizeof(unsigned) * (size_t)c->cap * c->npad));
 
+        unsigned char *subkey = NULL;
+        if (c->cell_order) {
+            if (!c->subkey) CUDA_TRY(cudaMalloc((void **)&c->subkey, (size_t)c->ncap));
+            subkey = c->subkey;
+        }
+        // pair-tile format (option pair_tile): plain Lennard-Jones systems on one GPU only
+        const bool pair_format = c->pair_tile && !c->need_atom_rows && !c->dd && !c->fij && !c->have_charge && (unsigned)c->n <= SEPGPU_PT_INDEX_MASK;
+        bool built_pair = false;
         ktimer_begin(c, &c->t_build);
         CUDA_TRY(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * ((size_t)nkey + 1), c->stream));
         k_build_begin<<<1, 1, 0, c->stream>>>(c->scal);
         k_cell_count<<<Gn, B, 0, c->stream>>>(c->x4, c->n, sys->lsubbox[0], sys->lsubbox[1], sys->lsubbox[2],
-                                              G, c->cell_of, c->cell_cnt, c->scal);
+                                              G, c->cell_of, c->cell_cnt, c->scal, subkey);
         if (sepgpu_exclusive_scan(c->stream, c->cell_cnt, c->cell_start, block_sum, nkey)) return SEPGPU_ECUDA;
         k_cell_scatter<<<Gn, B, 0, c->stream>>>(c->cell_of, c->n, c->cell_start, c->cell_cnt, c->tmp_slot);
         if (c->dd && !c->cls) CUDA_TRY(cudaMalloc((void **)&c->cls, (size_t)c->ncap));
         k_cell_finalize<<<Gn, B, 0, c->stream>>>(c->tmp_slot, c->cell_of, c->cell_start, c->x4, c->n,
-                                                 c->order, c->rank, c->xs, c->xf, c->cr4, c->dd ? c->cls : NULL, G);
+                                                 c->order, c->rank, c->xs, c->xf, c->cr4, c->dd ? c->cls : NULL, G, subkey);
         BuildParams P;
         P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
         const double cut = sys->cf + sys->skin;
@@ -565,6 +593,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         P.fLx = (float)P.Lx; P.fLy = (float)P.Ly; P.fLz = (float)P.Lz;
         P.G = G;
         P.n = c->n; P.npad = c->npad; P.cap = c->cap; P.opt = opt;
+        P.spatial_order = subkey != NULL;
         // FP32 prefilter: |r2_f32 - r2_exact| <= 2*sqrt(3)*cut * 4*Lmax*2^-24 (+ accumulation rounding);
         // the band below is 5x that bound.  It also needs cell image == minimum image, which holds when
         // every dimension has >= 4 cells and cut < 2 cells (< L/2).
@@ -585,16 +614,26 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             const size_t smem = (size_t)(stage_cap + TILE2_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
             if (smem > 200 * 1024) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
 #define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, stage_cap
-            if (opt == SEPGPU_ALL) {
-                CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<SEPGPU_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_build_tile2<SEPGPU_ALL><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);
+#define TILE_LAUNCH(O, PR, SP)                                                                                                   \
+    do {                                                                                                                         \
+        CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<O, PR, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        k_build_tile2<O, PR, SP><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);                                          \
+    } while (0)
+            const bool sp = subkey != NULL;
+            if (pair_format) {
+                // membership flags are each atom's own accepted set, so the exclusion rules carry over unchanged
+                if (opt == SEPGPU_ALL) { if (sp) TILE_LAUNCH(SEPGPU_ALL, true, true); else TILE_LAUNCH(SEPGPU_ALL, true, false); }
+                else if (opt == SEPGPU_EXCL_SAME_MOL) { if (sp) TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, true, true); else TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, true, false); }
+                else { if (sp) TILE_LAUNCH(SEPGPU_EXCL_BONDED, true, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, true, false); }
+                built_pair = true;
+            } else if (opt == SEPGPU_ALL) {
+                if (sp) TILE_LAUNCH(SEPGPU_ALL, false, true); else TILE_LAUNCH(SEPGPU_ALL, false, false);
             } else if (opt == SEPGPU_EXCL_SAME_MOL) {
-                CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<SEPGPU_EXCL_SAME_MOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_build_tile2<SEPGPU_EXCL_SAME_MOL><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);
+                if (sp) TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, false, true); else TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, false, false);
             } else {
-                CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<SEPGPU_EXCL_BONDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_build_tile2<SEPGPU_EXCL_BONDED><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);
+                if (sp) TILE_LAUNCH(SEPGPU_EXCL_BONDED, false, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, false, false);
             }
+#undef TILE_LAUNCH
 #undef TILE_ARGS
         } else {
             k_build_list<<<(c->n + BUILD_WARPS - 1) / BUILD_WARPS, BUILD_WARPS * 32, 0, c->stream>>>(
@@ -631,6 +670,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (c->scal_host->max_neighb <= c->cap) {
             c->list_valid = true; c->list_opt = opt; c->sorted_identity = false; c->xs_current = true;
             c->zs_valid = false;
+            c->list_pair = built_pair;
             c->list_gen++;
             c->grid_n[0] = nx; c->grid_n[1] = ny; c->grid_n[2] = nz;
             return 0;
@@ -666,6 +706,31 @@ __global__ void k_export_pairs(const unsigned *__restrict__ nbr, const int *__re
     }
 }
 
+// pair-tile format: row s belongs to atom s alone (flags clear) or to the pair (s, s+1) with per-atom membership flags
+__global__ void k_export_pairs_pt(const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
+                                  const int *__restrict__ order, int n, int npad, int *__restrict__ out,
+                                  long long max_pairs, unsigned long long *counter)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int m = cnt[s];
+    if (m < 0) return;                           // second atom of a pair: served by row s - 1
+    const bool both = !(s & 1) && s + 1 < n && cnt[s + 1] < 0;
+    const int ia = order[s], ib = both ? order[s + 1] : -1;
+    for (int k = 0; k < m; k++) {
+        const unsigned e = nbr[nbr_index(k, s, npad)];
+        const int j = order[e & SEPGPU_PT_INDEX_MASK];
+        if (!(e & SEPGPU_PT_SKIP_A) && ia < j) {
+            unsigned long long p = atomicAdd(counter, 1ULL);
+            if ((long long)p < max_pairs) { out[2 * p] = ia; out[2 * p + 1] = j; }
+        }
+        if (both && !(e & SEPGPU_PT_SKIP_B) && ib < j) {
+            unsigned long long p = atomicAdd(counter, 1ULL);
+            if ((long long)p < max_pairs) { out[2 * p] = ib; out[2 * p + 1] = j; }
+        }
+    }
+}
+
 extern "C" long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_pairs)
 {
     if (!c || !pairs || max_pairs <= 0) return SEPGPU_EINVAL;
@@ -675,7 +740,8 @@ extern "C" long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_p
     if (cudaMalloc((void **)&dout, sizeof(int) * 2 * (size_t)max_pairs) != cudaSuccess) return SEPGPU_ECUDA;
     if (cudaMalloc((void **)&dcount, sizeof(unsigned long long)) != cudaSuccess) { cudaFree(dout); return SEPGPU_ECUDA; }
     cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), c->stream);
-    k_export_pairs<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
+    if (c->list_pair) k_export_pairs_pt<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount);
+    else k_export_pairs<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);

@@ -18,8 +18,25 @@
 #define TILE2_PAD 32
 #define TILE2_NCELL (9 * (TILE2_MAXCX + 2))
 
-template <unsigned OPT>
-__global__ void __launch_bounds__(TILE2_THREADS)
+// bits [max(lo,0), min(hi,32)) of a 32-bit mask
+__device__ __forceinline__ unsigned bit_range(int lo, int hi)
+{
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > 32 ? 32 : hi;
+    if (hi <= lo) return 0u;
+    const unsigned upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+    return upto & ~((1u << lo) - 1u);
+}
+
+// PAIR (option pair_tile): rows are written for PAIRS of sorted atoms (2t, 2t+1) instead of
+// atoms -- row 2t holds the union of both atoms' neighbours, each entry flagged with the atom(s) it does NOT
+// belong to (SEPGPU_PT_SKIP_A / _B), and cnt[2t+1] = -1.  The pair-tile force kernel (k_lj_pairtile) gathers
+// every listed neighbour once for two atoms.  A pair whose atoms fall into different x-runs (different CTAs here)
+// stays two single rows.  Membership flags are each atom's own accepted set, so per-atom pair sets -- and the
+// reference's half-list length -- are exactly those of the per-atom list.
+// SPATIAL (option cell_order = 1): slots of a cell follow a space-filling curve instead of the atom index.
+template <unsigned OPT, bool PAIR, bool SPATIAL>
+__global__ void __launch_bounds__(TILE2_THREADS, (PAIR ? 6 : 9))      // 40 registers for the per-atom variants, as measured in round 1
 k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int *__restrict__ order,
               const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
               const int *__restrict__ excl_angle, const int *__restrict__ excl_dihed,
@@ -104,12 +121,29 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
     }
     __syncthreads();
 
-    int blk_max = 0, blk_half = 0, blk_sum = 0;
-    for (int ab = 0; ab < nhome; ab += TILE2_THREADS) {
-        const int s = a0 + ab + threadIdx.x;
-        if (s < a0 + nhome) {
+    int blk_max = 0, blk_half = 0, blk_sum = 0, blk_rows = 0;
+    // PAIR: the thread <-> atom mapping starts at the even slot at or below a0, so that the two atoms of a globally
+    // aligned pair sit in neighbouring lanes (even, odd) of one warp
+    const int a_base = PAIR ? (a0 & ~1) : a0;
+    const int span = a0 + nhome - a_base;
+    for (int ab = 0; ab < span; ab += TILE2_THREADS) {
+        const int s = a_base + ab + threadIdx.x;
+        if (s >= a0 && s < a0 + nhome) {
             int h = 0;                                   // my home cell inside the tile
             for (int q = 1; q < ncx; q++) h += (s >= s_home[q]);
+            bool paired = false;                         // PAIR: my partner s ^ 1 is a home atom of this tile too
+            int h_lo = h, h_hi = h;
+            if (PAIR) {
+                const int sp = s ^ 1;
+                paired = sp >= a0 && sp < a0 + nhome;
+                if (paired) {
+                    int hp = 0;
+                    for (int q = 1; q < ncx; q++) hp += (sp >= s_home[q]);
+                    h_lo = min(h, hp); h_hi = max(h, hp);
+                }
+            }
+            const unsigned pm = 3u << (threadIdx.x & 30);           // the two lanes of my pair
+            int own_total = 0;
             const float4 fi = xf[s];
             const int mol_i = __float_as_int(fi.w);
             int count = 0, half_count = 0;
@@ -122,8 +156,10 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
                 const int wlo = s_off[c0], whi = s_off[c0 + 3];
                 const int cut_a = s_off[c0 + 1];
                 const int self_q = centre_row ? cut_a + (s - s_beg[c0 + 1]) : -1;
+                // PAIR: both lanes of a pair sweep the union of their two windows in the same 32-candidate steps
+                const int plo = PAIR ? s_off[r * ncc + h_lo] : wlo, phi = PAIR ? s_off[r * ncc + h_hi + 3] : whi;
 #pragma unroll 1
-                for (int q0 = wlo; q0 < whi; q0 += 32) {
+                for (int q0 = plo; q0 < phi; q0 += 32) {
                     unsigned mask = 0, band = 0;
 #pragma unroll
                     for (int b = 0; b < 32; b++) {
@@ -133,8 +169,12 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
                         if (r2 <= P.fcut_hi) mask |= 1u << b;
                         if (r2 >= P.fcut_lo) band |= 1u << b;
                     }
-                    const int nvalid = whi - q0;
-                    if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+                    if (PAIR) {
+                        mask &= bit_range(wlo - q0, whi - q0);          // my own 3-cell stencil only
+                    } else {
+                        const int nvalid = whi - q0;
+                        if (nvalid < 32) mask &= (1u << nvalid) - 1u;
+                    }
                     if ((unsigned)(self_q - q0) < 32u) mask &= ~(1u << (self_q - q0));
                     band &= mask;
                     // rare slow filters first, so that the append loop below is branch-light:
@@ -161,9 +201,42 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
                     // reference half-list length: cells of the half stencil, or (centre row) everything
                     // stored after my own position -- my own cell with j2 > j1 and the ox = +1 cell
                     if (half_row) half_count += __popc(mask);
-                    else if (centre_row) {
+                    else if (SPATIAL && centre_row) {
+                        // slots of a cell are not in index order: the ox = +1 cell counts whole, my own cell by atom index
+                        const int cut_b = s_off[c0 + 2];
+                        half_count += __popc(mask & bit_range(cut_b - q0, whi - q0));
+                        unsigned own = mask & bit_range(cut_a - q0, cut_b - q0);
+                        const int my_i = order[s];
+                        while (own) {
+                            const int b = __ffs(own) - 1;
+                            own &= own - 1;
+                            half_count += order[__float_as_uint(cand[q0 + b].w) & SEPGPU_INDEX_MASK] > my_i;
+                        }
+                    } else if (centre_row) {
                         const int d = self_q + 1 - q0;                   // first bit that counts
                         half_count += __popc(d <= 0 ? mask : (d >= 32 ? 0u : mask & ~((1u << d) - 1u)));
+                    }
+                    if (PAIR) own_total += __popc(mask);
+                    if (PAIR && paired) {
+                        const unsigned other = __shfl_xor_sync(pm, mask, 1);
+                        if (!(threadIdx.x & 1)) {                        // the even atom owns the pair's row
+                            unsigned u = mask | other;
+                            const int nacc = __popc(u);
+                            if (count + nacc <= P.cap) {
+                                while (u) {
+                                    const int b = __ffs(u) - 1;
+                                    u &= u - 1;
+                                    unsigned e = __float_as_uint(cand[q0 + b].w);
+                                    if (!(mask >> b & 1u)) e |= SEPGPU_PT_SKIP_A;
+                                    if (!(other >> b & 1u)) e |= SEPGPU_PT_SKIP_B;
+                                    nbr[nbr_index(count, s, P.npad)] = e;
+                                    count++;
+                                }
+                            } else {
+                                count += nacc;
+                            }
+                        }
+                        continue;
                     }
                     const int nacc = __popc(mask);
                     if (count + nacc <= P.cap) {
@@ -178,8 +251,10 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
                     }
                 }
             }
-            cnt[s] = min(count, P.cap);
-            blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += count;
+            if (PAIR && paired && (threadIdx.x & 1)) cnt[s] = -1;        // second atom of a pair: its entries live in row s - 1
+            else cnt[s] = min(count, P.cap);
+            blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += PAIR ? own_total : count;
+            if (PAIR) blk_rows += count;
         }
     }
     // block statistics: warp reduce, then shared atomics, then three global atomics per CTA
@@ -196,5 +271,9 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
         atomicMax(&scal->max_neighb, s_red[0]);
         atomicMax(&scal->max_half, s_red[1]);
         atomicAdd((unsigned long long *)&scal->npairs_listed, (unsigned long long)s_red[2]);
+    }
+    if (PAIR) {                                  // statistics only: entries actually stored (union rows)
+        for (int o = 16; o > 0; o >>= 1) blk_rows += __shfl_xor_sync(0xffffffffu, blk_rows, o);
+        if ((threadIdx.x & 31) == 0 && blk_rows) atomicAdd((unsigned long long *)&scal->row_entries, (unsigned long long)blk_rows);
     }
 }

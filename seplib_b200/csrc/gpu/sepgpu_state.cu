@@ -139,6 +139,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     for (int k = 0; k < SEPGPU_NSUB; k++) { if (c->nbr_t[k]) cudaFree(c->nbr_t[k]); if (c->cnt_t[k]) cudaFree(c->cnt_t[k]); }
     if (c->tsort) cudaFree(c->tsort);
     if (c->xq) cudaFree(c->xq);
+    if (c->subkey) cudaFree(c->subkey);
     if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
@@ -696,6 +697,8 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
+    if (!strcmp(name, "cell_order")) { if (value != 0 && value != 1) return SEPGPU_EINVAL; c->cell_order = (int)value; c->list_valid = false; return 0; }
+    if (!strcmp(name, "pair_tile")) { c->pair_tile = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
     if (!strcmp(name, "typed_sublist")) { c->typed_sublist = value != 0; return 0; }
     if (!strcmp(name, "force_grid")) { c->force_grid = value > 0 && value <= SEPGPU_MAX_BLOCKS_PARTIAL ? (int)value : 0; return 0; }
@@ -713,6 +716,25 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     }
     sepgpu_set_error("sepgpu_set_option: unknown option '%s'", name);
     return SEPGPU_EINVAL;
+}
+
+extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *value)
+{
+    if (!c || !name || !value) return SEPGPU_EINVAL;
+    if (!strcmp(name, "tpa")) *value = c->tpa;
+    else if (!strcmp(name, "prefilter")) *value = c->prefilter;
+    else if (!strcmp(name, "overlap")) *value = c->overlap;
+    else if (!strcmp(name, "force_grid")) *value = c->force_grid;
+    else if (!strcmp(name, "neighb_cap")) *value = c->cap;
+    else if (!strcmp(name, "coulomb_kernel")) *value = c->coulomb_kernel;
+    else if (!strcmp(name, "typed_sublist")) *value = c->typed_sublist;
+    else if (!strcmp(name, "pair_tile")) *value = c->pair_tile;
+    else if (!strcmp(name, "cell_order")) *value = c->cell_order;
+    else if (!strcmp(name, "list_pair")) *value = c->list_valid && c->list_pair ? 1 : 0;
+    else if (!strcmp(name, "max_half")) *value = c->scal_host->max_half;            // longest reference-style half list, last build
+    else if (!strcmp(name, "row_entries")) *value = c->scal_host->row_entries;      // as of the last list build (pair-tile format)
+    else { sepgpu_set_error("sepgpu_get_option: unknown option '%s'", name); return SEPGPU_EINVAL; }
+    return 0;
 }
 
 extern "C" int sepgpu_kernel_time(sepgpu_ctx *c, const char *which, float *ms_total, int *launches)

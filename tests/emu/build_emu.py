@@ -9,8 +9,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 GPU_SRC = os.path.join(ROOT, "seplib_b200", "csrc", "gpu")
 HOST_SRC = os.path.join(ROOT, "seplib_b200", "csrc", "host")
-OUT = os.path.join(ROOT, "tests", "_build", "emu")
-LIB = os.path.join(ROOT, "tests", "_build", "libsep_emu.so")
+# SEPGPU_EMU_SANITIZE=1: a second build with UBSan's alignment / bounds / null checks.  The CUDA vector types keep their
+# device alignment here (d4 32 bytes, uint4 / float4 / double2 16 bytes), so a misaligned 128- or 256-bit access -- a
+# fault on the GPU, silent on x86 -- aborts the test instead.
+SANITIZE = os.environ.get("SEPGPU_EMU_SANITIZE") == "1"
+OUT = os.path.join(ROOT, "tests", "_build", "emu_ubsan" if SANITIZE else "emu")
+LIB = os.path.join(ROOT, "tests", "_build", "libsep_emu_ubsan.so" if SANITIZE else "libsep_emu.so")
 
 sys.path.insert(0, HERE)
 import prep  # noqa: E402
@@ -30,6 +34,8 @@ def build(force=False, verbose=False):
     inc = ["-I" + HERE, "-I" + OUT, "-I" + os.path.join(ROOT, "include")]
     # -ffp-contract=off: no implicit FMA (explicit fma() calls use the hardware instruction through -mfma)
     cxx = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-mfma", "-ffp-contract=off", "-fno-strict-aliasing", "-w"] + inc
+    if SANITIZE:
+        cxx += ["-fsanitize=alignment,bounds,null", "-fno-sanitize-recover=all"]
     cc = ["gcc", "-std=c99", "-O2", "-fPIC", "-D_POSIX_C_SOURCE=200809L", "-I" + os.path.join(ROOT, "include")]
     objs = []
     jobs = []
@@ -51,7 +57,8 @@ def build(force=False, verbose=False):
         if verbose and out.strip():
             print(out)
         objs.append(o)
-    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + ["-lm", "-ldl", "-lpthread"])
+    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + (["-fsanitize=alignment,bounds,null"] if SANITIZE else [])
+                          + ["-lm", "-ldl", "-lpthread"])
     return LIB
 
 

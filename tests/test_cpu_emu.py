@@ -40,8 +40,8 @@ def test_gpu_parity_tests_pass_on_the_emulated_kernels():
 
 
 def test_optin_kernels_pass_on_the_emulator():
-    """coulomb_kernel=2 and typed_sublist=1 (tests/test_gpu_zzz_options.py): skipped on hardware until a GPU run has
+    """coulomb_kernel=2, typed_sublist=1, pair_tile=1, cell_order=1 (tests/test_gpu_zzz_options.py): skipped on hardware until a GPU run has
     confirmed them, exercised here on every CPU round."""
     n = _run(["tests/test_gpu_zzz_options.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
              env={"SEPGPU_TEST_UNVERIFIED": "1"})
-    assert n >= 6, n
+    assert n >= 18, n

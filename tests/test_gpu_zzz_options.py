@@ -151,3 +151,202 @@ def test_options_through_the_environment(tmp_path):
         env = dict(os.environ); env["SEPGPU_OPTS"] = opts
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert want in r.stdout, (opts, r.stdout, r.stderr)
+
+
+# ---- pair_tile: rows per pair of sorted atoms + k_lj_pairtile ------------------------------------------------------
+def _opt(s, name):
+    v = C.c_longlong(-1)
+    s.call("sepgpu_get_option", name.encode(), C.byref(v))
+    return v.value
+
+def _lj(ncell, seed=3, jitter=0.12):
+    x, L = cm.lattice(ncell, 0.8, jitter=jitter, seed=seed)
+    return x, L
+
+
+@pytest.mark.parametrize("skin", [0.25, 1.0])
+def test_pair_tile_list_holds_exactly_the_reference_pair_set(skin):
+    """Per-atom membership flags of the pair rows reproduce the reference's pair set bit for bit -- also with the
+    skin-1.0 quirk, where one atom of a pair may see a neighbour the other atom's cells do not reach."""
+    x, L = _lj(14)
+    cf = 2.5
+    ref_pairs = cm.pair_set(cm.oracle_pairs(x, L, cf, skin))
+    s = capi.System(len(x))
+    s.put(capi.F_X, x)
+    s.call("sepgpu_set_option", b"pair_tile", 1)
+    sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+    assert _opt(s, "list_pair") == 1
+    got = cm.pair_set(s.pairs())
+    assert got.shape == ref_pairs.shape and np.array_equal(got, ref_pairs)
+    assert s.scalars().npairs_listed == 2 * len(ref_pairs)
+    s.close()
+
+
+@pytest.mark.parametrize("typed,skin", [(False, 0.25), (True, 0.25), (False, 1.0)])
+def test_pair_tile_forces_match_oracle(typed, skin):
+    x, L = _lj(12, seed=9)
+    n = len(x)
+    cf = 2.5
+    rng = np.random.default_rng(5)
+    types = (np.where(rng.random(n) < 0.4, ord("B"), ord("A")) if typed else np.full(n, ord("A"))).astype(np.uint8)
+    pp = np.ascontiguousarray(cm.oracle_pairs(x, L, cf, skin), dtype=np.int32)
+    orc = cm.oracle(); length = cm.dvec3([L] * 3)
+    fref = np.zeros((n, 3)); rref = cm.OrcRet()
+    calls = ((b"AA", 2.5, cm.POT_LJ_SHIFT, "lj_shift"), (b"AB", 2.0, cm.POT_LJ, "lj"), (b"BB", 2 ** (1 / 6), cm.POT_WCA, "wca")) \
+        if typed else ((b"AA", 2.5, cm.POT_LJ_SHIFT, "lj_shift"),)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_TYPE, types)
+    s.call("sepgpu_set_option", b"pair_tile", 1)
+    sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    for tsel, rc_, pot, kind in calls:
+        orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pp), len(pp), tsel, rc_, pot,
+                                 None, cm.ptr(fref), C.byref(rref))
+        p = capi.lj_param(rc_, kind=kind)
+        s.call("sepgpu_force_lj", C.byref(sys_), tsel, C.byref(p), cm.ALL, 1)
+    assert _opt(s, "list_pair") == 1
+    f = s.get(capi.F_F); sc = s.scalars()
+    assert cm.rel_force_err(f, fref) <= FT
+    assert abs(sc.epot - rref.epot) <= 1e-10 * max(abs(rref.epot), 1.0)
+    P = np.array(sc.pot_P[:]); Pref = np.array(rref.pot_P[:])
+    assert np.abs(P - Pref).max() <= 1e-10 * np.abs(Pref).max()
+    s.close()
+
+
+def test_pair_tile_trajectory_follows_the_default_kernels():
+    """24 NVT steps (prg1-style loop through the C ABI) with and without pair_tile: same rebuild steps, energies equal
+    to rounding growth."""
+    x, L = _lj(12, seed=21, jitter=0.05)
+    n = len(x)
+    v = cm.velocities(n, 3.0, seed=22)
+    cf, skin, dt = 2.5, 0.25, 0.005
+    runs = []
+    for on in (0, 1):
+        s = capi.System(n)
+        s.put(capi.F_X, x); s.put(capi.F_V, v)
+        s.call("sepgpu_set_option", b"pair_tile", on)
+        sys_ = capi.make_sys([L] * 3, cf, dt, skin=skin)
+        p = capi.lj_param(cf, kind="lj_shift")
+        s.call("sepgpu_set_alpha", 0, 0.0)
+        rec = []
+        for step in range(24):
+            s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+            if step == 0 or s.scalars().neighb_flag:
+                s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+                assert _opt(s, "list_pair") == on
+            s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
+            s.call("sepgpu_nosehoover", C.byref(sys_), 3.0, 0, 0.1)
+            s.call("sepgpu_leapfrog", C.byref(sys_))
+            sc = s.scalars()
+            rec.append((sc.epot, sc.ekin, np.array(sc.pot_P[:]), sc.nbuild))
+        runs.append((rec, s.get(capi.F_X)))
+        s.close()
+    (r0, x0), (r1, x1) = runs
+    assert r0[-1][3] >= 3
+    for k, ((e0, k0, p0, b0), (e1, k1, p1, b1)) in enumerate(zip(r0, r1)):
+        assert b0 == b1, k
+        assert abs(e1 - e0) <= 1e-9 * (k + 1) * abs(e0) and abs(k1 - k0) <= 1e-9 * (k + 1) * abs(k0)
+        assert np.abs(p1 - p0).max() <= 1e-9 * (k + 1) * np.abs(p0).max()
+    d = x1 - x0
+    d -= L * np.round(d / L)
+    assert np.abs(d).max() <= 1e-8
+
+
+def test_pair_tile_falls_back_to_per_atom_rows_for_coulomb_and_dpd():
+    """Coulomb and DPD walk per-atom rows: a charged system never gets pair rows, and a DPD call on a context that
+    holds pair rows rebuilds the list per atom -- results equal the default path."""
+    # water: charges present -> per-atom rows although the option is on
+    s, x, types, z, mol, L = _water_system(2, {"pair_tile": 1})
+    f1, sc1 = _water_forces(s, L, 2.9, 0.25)
+    assert _opt(s, "list_pair") == 0
+    s.close()
+    s, *_ = _water_system(2, {})
+    f0, sc0 = _water_forces(s, L, 2.9, 0.25)
+    s.close()
+    assert np.array_equal(f0, f1) and sc0.epot == sc1.epot
+    # DPD after a Lennard-Jones call that built pair rows
+    x, Lb = cm.lattice(12, 3.0, jitter=0.35, seed=13)
+    n = len(x)
+    pv = cm.velocities(n, 1.0, seed=14)
+    res = []
+    for on in (0, 1):
+        s = capi.System(n)
+        s.put(capi.F_X, x); s.put(capi.F_PV, pv)
+        s.call("sepgpu_set_option", b"pair_tile", on)
+        sys_ = capi.make_sys([Lb] * 3, 1.0, 0.02, skin=0.25)
+        s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+        p = capi.lj_param(1.0, kind="lj")
+        s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
+        assert _opt(s, "list_pair") == on
+        s.call("sepgpu_force_dpd", C.byref(sys_), b"AA", 1.0, 25.0, 1.0, 3.0, cm.ALL, 7, 3)
+        assert _opt(s, "list_pair") == 0
+        res.append((s.get(capi.F_F), s.scalars().epot))
+        s.close()
+    assert cm.rel_force_err(res[1][0], res[0][0]) <= 1e-12 and abs(res[1][1] - res[0][1]) <= 1e-12 * abs(res[0][1])
+
+
+@pytest.mark.parametrize("cell_order", [0, 1])
+def test_pair_tile_with_exclusions_butane_golden(cell_order):
+    """prg2-style butane against what the REFERENCE computed (tests/golden/butane_n4000.npz): same-molecule and
+    bonded-partner exclusions -- the membership flags of the pair rows carry each atom's own exclusions
+    (reference source/sepprfrc.c:517-700, 703-740)."""
+    import test_golden as tg
+    g = tg.load("butane_n4000.npz")
+    n = len(g["x0"])
+    t = tg.topo_from(g, n)
+    s = capi.System(n)
+    s.put(capi.F_X, g["x0"]); s.put(capi.F_TYPE, np.full(n, ord("C"), dtype=np.uint8))
+    tg.gpu_put_topology(s, t)
+    s.call("sepgpu_set_option", b"pair_tile", 1)
+    s.call("sepgpu_set_option", b"cell_order", cell_order)
+    sys_ = tg.gpu_sys(g, n)
+    p = capi.lj_param(float(g["cf"]), kind="lj_shift")
+    for opt, pairs, fkey, ekey in ((cm.EXCL_SAME_MOL, "pairs_same_mol", "f_lj", "epot_lj"), (cm.EXCL_BONDED, "pairs_nonbonded", "f_lj_nonbonded", None)):
+        s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+        s.call("sepgpu_neighb_build", C.byref(sys_), opt)
+        assert _opt(s, "list_pair") == 1
+        assert np.array_equal(cm.pair_set(s.pairs()), g[pairs])
+        s.call("sepgpu_force_lj", C.byref(sys_), b"CC", C.byref(p), opt, 1)
+        assert cm.rel_force_err(s.get(capi.F_F), g[fkey]) <= FT
+        if ekey:
+            assert abs(s.scalars().epot - float(g[ekey])) <= FT * abs(float(g[ekey]))
+            assert tg.relerr(np.array(s.scalars().pot_P[:]), g["pot_P_lj"]) <= FT
+    s.close()
+
+
+# ---- cell_order: slots of a cell along a space-filling curve ---------------------------------------------------------
+@pytest.mark.parametrize("pair_tile,skin", [(0, 0.25), (1, 0.25), (1, 1.0)])
+def test_cell_order_keeps_pair_set_forces_and_half_list_length(pair_tile, skin):
+    """The in-cell slot order changes neither the pair set nor the forces, and the reference-style half-list length
+    (the SEP_NEIGHB = 3000 error condition, source/sepprfrc.c:499-501) is still counted by atom index."""
+    x, L = _lj(14, seed=4)
+    x = np.ascontiguousarray(x[np.random.default_rng(8).permutation(len(x))])     # index order unrelated to position
+    n = len(x)
+    cf = 2.5
+    pp = np.ascontiguousarray(cm.oracle_pairs(x, L, cf, skin), dtype=np.int32)
+    types = np.full(n, ord("A"), dtype=np.uint8)
+    orc = cm.oracle(); length = cm.dvec3([L] * 3)
+    fref = np.zeros((n, 3)); rref = cm.OrcRet()
+    orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pp), len(pp), b"AA", cf, cm.POT_LJ_SHIFT,
+                             None, cm.ptr(fref), C.byref(rref))
+    half = {}
+    for order in (0, 1):
+        s = capi.System(n)
+        s.put(capi.F_X, x)
+        s.call("sepgpu_set_option", b"cell_order", order)
+        s.call("sepgpu_set_option", b"pair_tile", pair_tile)
+        sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
+        s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+        s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+        assert _opt(s, "list_pair") == pair_tile
+        assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(pp))
+        half[order] = _opt(s, "max_half")
+        p = capi.lj_param(cf, kind="lj_shift")
+        s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
+        f = s.get(capi.F_F); sc = s.scalars()
+        assert cm.rel_force_err(f, fref) <= FT
+        assert abs(sc.epot - rref.epot) <= 1e-10 * abs(rref.epot)
+        s.close()
+    assert half[0] == half[1]
+    assert half[0] >= 1
