@@ -173,6 +173,7 @@ struct sepgpu_ctx {
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
     int force_grid;              // CTAs of the list force kernel (0 = default)
     int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
+    int build_prune;             // tiled list builder skips candidate cells beyond the cutoff (0 = off, default)
     int cell_order;              // slots inside a cell: 0 by atom index (default), 1 along a Morton curve of 4^3 sub-cells
     unsigned char *subkey;       // [ncap] sub-cell code per atom (cell_order = 1)
     int pair_tile;               // SEP_ALL lists in pair-tile format + k_lj_pairtile (0 = off, default)

@@ -228,6 +228,7 @@ struct BuildParams {
     double Lx, Ly, Lz;
     double cut2;
     float fLx, fLy, fLz, fcut_lo, fcut_hi;
+    float flsx, flsy, flsz;  // cell widths (option build_prune)
     CellGrid G;
     int n, npad, cap;
     unsigned opt;
@@ -591,6 +592,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         const double cut = sys->cf + sys->skin;
         P.cut2 = cut * cut;                              // sep_Sq(sys->cf + sys->skin), :432
         P.fLx = (float)P.Lx; P.fLy = (float)P.Ly; P.fLz = (float)P.Lz;
+        P.flsx = (float)sys->lsubbox[0]; P.flsy = (float)sys->lsubbox[1]; P.flsz = (float)sys->lsubbox[2];
         P.G = G;
         P.n = c->n; P.npad = c->npad; P.cap = c->cap; P.opt = opt;
         P.spatial_order = subkey != NULL;
@@ -614,12 +616,14 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             const size_t smem = (size_t)(stage_cap + TILE2_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
             if (smem > 200 * 1024) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
 #define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, stage_cap
-#define TILE_LAUNCH(O, PR, SP)                                                                                                   \
+#define TILE_LAUNCH4(O, PR, SP, PN)                                                                                              \
     do {                                                                                                                         \
-        CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<O, PR, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        k_build_tile2<O, PR, SP><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);                                          \
+        CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<O, PR, SP, PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        k_build_tile2<O, PR, SP, PN><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);                                      \
     } while (0)
+#define TILE_LAUNCH(O, PR, SP) do { if (prune) TILE_LAUNCH4(O, PR, SP, true); else TILE_LAUNCH4(O, PR, SP, false); } while (0)
             const bool sp = subkey != NULL;
+            const bool prune = c->build_prune && !c->dd;       // slab runs keep the plain sweep (local/global layer bookkeeping)
             if (pair_format) {
                 // membership flags are each atom's own accepted set, so the exclusion rules carry over unchanged
                 if (opt == SEPGPU_ALL) { if (sp) TILE_LAUNCH(SEPGPU_ALL, true, true); else TILE_LAUNCH(SEPGPU_ALL, true, false); }
@@ -633,6 +637,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             } else {
                 if (sp) TILE_LAUNCH(SEPGPU_EXCL_BONDED, false, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, false, false);
             }
+#undef TILE_LAUNCH4
 #undef TILE_LAUNCH
 #undef TILE_ARGS
         } else {

@@ -35,7 +35,8 @@ __device__ __forceinline__ unsigned bit_range(int lo, int hi)
 // stays two single rows.  Membership flags are each atom's own accepted set, so per-atom pair sets -- and the
 // reference's half-list length -- are exactly those of the per-atom list.
 // SPATIAL (option cell_order = 1): slots of a cell follow a space-filling curve instead of the atom index.
-template <unsigned OPT, bool PAIR, bool SPATIAL>
+// PRUNE (option build_prune = 1): candidate cells whose nearest point is beyond the cutoff are not swept.
+template <unsigned OPT, bool PAIR, bool SPATIAL, bool PRUNE>
 __global__ void __launch_bounds__(TILE2_THREADS, (PAIR ? 6 : 9))      // 40 registers for the per-atom variants, as measured in round 1
 k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int *__restrict__ order,
               const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
@@ -153,13 +154,40 @@ k_build_tile2(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const in
                 const bool half_row = (oz == 1) || (oz == 0 && oy == 1);
                 const bool centre_row = (oz == 0 && oy == 0);
                 const int c0 = r * ncc + h;              // candidate cells c0 (ox=-1), c0+1 (own column), c0+2 (ox=+1)
-                const int wlo = s_off[c0], whi = s_off[c0 + 3];
+                int wlo = s_off[c0], whi = s_off[c0 + 3];
                 const int cut_a = s_off[c0 + 1];
                 const int self_q = centre_row ? cut_a + (s - s_beg[c0 + 1]) : -1;
+                if (PRUNE) {
+                    // Nearest point of the row's cells, from my distances to the faces of my own cell (FP32, clamped at 0).
+                    // Conservative: the limit carries a 1e-3 margin, far above FP32 rounding of positions and faces, so a
+                    // dropped cell cannot hold a candidate the mask pass would have accepted.
+                    const float dyl = fmaxf(fi.y - cy * P.flsy, 0.f), dyh = fmaxf((cy + 1) * P.flsy - fi.y, 0.f);
+                    const float dzl = fmaxf(fi.z - cz * P.flsz, 0.f), dzh = fmaxf((cz + 1) * P.flsz - fi.z, 0.f);
+                    const float dy = oy == 0 ? 0.f : (oy > 0 ? dyh : dyl), dz = oz == 0 ? 0.f : (oz > 0 ? dzh : dzl);
+                    const float dyz2 = dy * dy + dz * dz;
+                    const float lim = P.fcut_hi * 1.001f;
+                    const float dxl = fmaxf(fi.x - (x0 + h) * P.flsx, 0.f), dxh = fmaxf((x0 + h + 1) * P.flsx - fi.x, 0.f);
+                    if (dyz2 > lim) { whi = wlo; }                                        // whole row out of reach
+                    else {
+                        if (dyz2 + dxl * dxl > lim) wlo = cut_a;                              // ox = -1 cell out of reach
+                        if (dyz2 + dxh * dxh > lim) whi = s_off[c0 + 2];                      // ox = +1 cell out of reach
+                    }
+                }
                 // PAIR: both lanes of a pair sweep the union of their two windows in the same 32-candidate steps
-                const int plo = PAIR ? s_off[r * ncc + h_lo] : wlo, phi = PAIR ? s_off[r * ncc + h_hi + 3] : whi;
+                int plo = PAIR ? s_off[r * ncc + h_lo] : wlo, phi = PAIR ? s_off[r * ncc + h_hi + 3] : whi;
+                if (PAIR && PRUNE) {
+                    plo = wlo; phi = whi;
+                    if (paired) {
+                        const int olo = __shfl_xor_sync(pm, wlo, 1), ohi = __shfl_xor_sync(pm, whi, 1);
+                        if (whi <= wlo) { plo = olo; phi = ohi; }                  // my range is empty: follow my partner's
+                        else if (ohi > olo) { plo = min(wlo, olo); phi = max(whi, ohi); }
+                    }
+                }
 #pragma unroll 1
                 for (int q0 = plo; q0 < phi; q0 += 32) {
+#ifdef SEPGPU_EMU
+                    sepgpu_emu_counter[0] += 32;         // CPU kernel emulator only: candidates tested (work statistics)
+#endif
                     unsigned mask = 0, band = 0;
 #pragma unroll
                     for (int b = 0; b < 32; b++) {

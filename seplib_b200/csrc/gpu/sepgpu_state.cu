@@ -697,6 +697,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
+    if (!strcmp(name, "build_prune")) { c->build_prune = value != 0; return 0; }
     if (!strcmp(name, "cell_order")) { if (value != 0 && value != 1) return SEPGPU_EINVAL; c->cell_order = (int)value; c->list_valid = false; return 0; }
     if (!strcmp(name, "pair_tile")) { c->pair_tile = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
@@ -730,6 +731,7 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "typed_sublist")) *value = c->typed_sublist;
     else if (!strcmp(name, "pair_tile")) *value = c->pair_tile;
     else if (!strcmp(name, "cell_order")) *value = c->cell_order;
+    else if (!strcmp(name, "build_prune")) *value = c->build_prune;
     else if (!strcmp(name, "list_pair")) *value = c->list_valid && c->list_pair ? 1 : 0;
     else if (!strcmp(name, "max_half")) *value = c->scal_host->max_half;            // longest reference-style half list, last build
     else if (!strcmp(name, "row_entries")) *value = c->scal_host->row_entries;      // as of the last list build (pair-tile format)

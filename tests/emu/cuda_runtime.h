@@ -54,6 +54,7 @@ static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 
+extern "C" long long sepgpu_emu_counter[8];      // work statistics kernels may bump under #ifdef SEPGPU_EMU
 extern uint3 threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
 static const int warpSize = 32;

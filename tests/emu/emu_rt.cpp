@@ -187,6 +187,7 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
 }  // namespace emu
 
 extern "C" long long sepgpu_emu_launches(void) { return g_launches; }
+extern "C" { long long sepgpu_emu_counter[8]; }
 
 // ---- runtime ------------------------------------------------------------------------------------------------------------
 struct emuStream { int dummy; };

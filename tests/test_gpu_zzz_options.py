@@ -350,3 +350,37 @@ def test_cell_order_keeps_pair_set_forces_and_half_list_length(pair_tile, skin):
         s.close()
     assert half[0] == half[1]
     assert half[0] >= 1
+
+
+# ---- build_prune: the tiled builder skips candidate cells beyond the cutoff ----------------------------------------
+@pytest.mark.parametrize("pair_tile,cell_order,skin", [(0, 0, 0.25), (0, 0, 1.0), (1, 0, 0.25), (1, 1, 0.25), (1, 1, 1.0)])
+def test_build_prune_changes_nothing_but_the_work(pair_tile, cell_order, skin):
+    """Pair set bit-exact against the oracle, half-list length and entry count equal to the unpruned build."""
+    x, L = _lj(14, seed=6, jitter=0.3)
+    ref_pairs = cm.pair_set(cm.oracle_pairs(x, L, 2.5, skin))
+    stats = []
+    for prune in (0, 1):
+        s = capi.System(len(x))
+        s.put(capi.F_X, x)
+        for k, v in (("build_prune", prune), ("pair_tile", pair_tile), ("cell_order", cell_order)):
+            s.call("sepgpu_set_option", k.encode(), v)
+        sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=skin)
+        s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+        assert _opt(s, "list_pair") == pair_tile
+        assert np.array_equal(cm.pair_set(s.pairs()), ref_pairs)
+        sc = s.scalars()
+        stats.append((sc.npairs_listed, sc.max_neighb, _opt(s, "max_half"), _opt(s, "row_entries")))
+        s.close()
+    assert stats[0] == stats[1]
+    assert stats[0][0] == 2 * len(ref_pairs)
+
+
+def test_build_prune_with_exclusions_water():
+    s, x, types, z, mol, L = _water_system(2, {"build_prune": 1, "cell_order": 1})
+    n = len(x)
+    t = cm.Topo(n); t.molindex[:] = mol
+    pairs = cm.oracle_pairs(x, L, 2.9, 0.25, opt=cm.EXCL_SAME_MOL, topo=t, max_pairs=4_000_000)
+    sys_ = capi.make_sys(L, 2.9, 5e-4, skin=0.25)
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.EXCL_SAME_MOL)
+    assert np.array_equal(cm.pair_set(s.pairs(4_000_000)), cm.pair_set(pairs))
+    s.close()
