@@ -766,7 +766,8 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     // the type test is compiled out when every atom carries the one requested type
     const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
     if (c->list_pair) {                                  // option pair_tile: rows per pair of sorted atoms
-        if (c->dd || c->fij) { sepgpu_set_error("force_lj: pair-tile lists serve single-GPU runs without the Fij table"); return SEPGPU_ESTATE; }
+        if (c->fij) { sepgpu_set_error("force_lj: pair-tile lists do not fill the Fij table"); return SEPGPU_ESTATE; }
+        if (c->dd && (rc = sepgpu_dd_halo_update(c, sys))) return rc;     // neighbours' boundary atoms moved too
         const int npairs = (c->n + 1) / 2;
         int grid = c->force_grid > 0 ? c->force_grid : FORCE_MAX_GRID;
         int ppc = (npairs + grid - 1) / grid;

@@ -574,8 +574,8 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             if (!c->subkey) CUDA_TRY(cudaMalloc((void **)&c->subkey, (size_t)c->ncap));
             subkey = c->subkey;
         }
-        // pair-tile format (option pair_tile): plain Lennard-Jones systems on one GPU only
-        const bool pair_format = c->pair_tile && !c->need_atom_rows && !c->dd && !c->fij && !c->have_charge && (unsigned)c->n <= SEPGPU_PT_INDEX_MASK;
+        // pair-tile format (option pair_tile): uncharged systems; in slab runs the halo atoms own empty single rows
+        const bool pair_format = c->pair_tile && !c->need_atom_rows && !(c->dd && c->overlap) && !c->fij && !c->have_charge && (unsigned)c->n <= SEPGPU_PT_INDEX_MASK;
         bool built_pair = false;
         ktimer_begin(c, &c->t_build);
         CUDA_TRY(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * ((size_t)nkey + 1), c->stream));
@@ -714,22 +714,26 @@ __global__ void k_export_pairs(const unsigned *__restrict__ nbr, const int *__re
 // pair-tile format: row s belongs to atom s alone (flags clear) or to the pair (s, s+1) with per-atom membership flags
 __global__ void k_export_pairs_pt(const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
                                   const int *__restrict__ order, int n, int npad, int *__restrict__ out,
-                                  long long max_pairs, unsigned long long *counter)
+                                  long long max_pairs, unsigned long long *counter, const int *__restrict__ gid, int n_own)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int m = cnt[s];
     if (m < 0) return;                           // second atom of a pair: served by row s - 1
     const bool both = !(s & 1) && s + 1 < n && cnt[s + 1] < 0;
-    const int ia = order[s], ib = both ? order[s + 1] : -1;
+    int ia = order[s], ib = both ? order[s + 1] : -1;
+    // decomposed run: halo atoms own no pairs; global ids (a cross-rank pair is emitted by one rank only)
+    const bool use_a = ia < n_own, use_b = both && ib < n_own;
+    if (gid) { ia = gid[ia]; if (both) ib = gid[ib]; }
     for (int k = 0; k < m; k++) {
         const unsigned e = nbr[nbr_index(k, s, npad)];
-        const int j = order[e & SEPGPU_PT_INDEX_MASK];
-        if (!(e & SEPGPU_PT_SKIP_A) && ia < j) {
+        int j = order[e & SEPGPU_PT_INDEX_MASK];
+        if (gid) j = gid[j];
+        if (use_a && !(e & SEPGPU_PT_SKIP_A) && ia < j) {
             unsigned long long p = atomicAdd(counter, 1ULL);
             if ((long long)p < max_pairs) { out[2 * p] = ia; out[2 * p + 1] = j; }
         }
-        if (both && !(e & SEPGPU_PT_SKIP_B) && ib < j) {
+        if (use_b && !(e & SEPGPU_PT_SKIP_B) && ib < j) {
             unsigned long long p = atomicAdd(counter, 1ULL);
             if ((long long)p < max_pairs) { out[2 * p] = ib; out[2 * p + 1] = j; }
         }
@@ -745,7 +749,7 @@ extern "C" long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_p
     if (cudaMalloc((void **)&dout, sizeof(int) * 2 * (size_t)max_pairs) != cudaSuccess) return SEPGPU_ECUDA;
     if (cudaMalloc((void **)&dcount, sizeof(unsigned long long)) != cudaSuccess) { cudaFree(dout); return SEPGPU_ECUDA; }
     cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), c->stream);
-    if (c->list_pair) k_export_pairs_pt<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount);
+    if (c->list_pair) k_export_pairs_pt<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     else k_export_pairs<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream);

@@ -43,8 +43,9 @@ def build(force=False, verbose=False):
         if f.endswith(".cpp"):
             o = os.path.join(OUT, f[:-4] + ".o")
             jobs.append((cxx + ["-c", os.path.join(OUT, f), "-o", o], o))
-    o = os.path.join(OUT, "emu_rt.o")
-    jobs.append((cxx + ["-c", os.path.join(HERE, "emu_rt.cpp"), "-o", o], o))
+    for src in ("emu_rt", "fake_nccl"):
+        o = os.path.join(OUT, src + ".o")
+        jobs.append((cxx + ["-D_GNU_SOURCE", "-c", os.path.join(HERE, src + ".cpp"), "-o", o], o))
     for f in sorted(os.listdir(HOST_SRC)):
         if f.endswith(".c"):
             o = os.path.join(OUT, "host_" + f[:-2] + ".o")

@@ -68,6 +68,7 @@ static inline dim3 d3(unsigned v) { return dim3(v, 1, 1); }
 static inline dim3 d3(size_t v) { return dim3((unsigned)v, 1, 1); }
 void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
 void *dyn_smem();
+const char *self_path();         // file name of the emulated library (dladdr), for the NCCL stand-in
 void sync_block();
 // every lane named in mask deposits 8 bytes and receives all 32 deposits (slots of lanes that did not take part hold
 // the caller's own value)

@@ -9,6 +9,7 @@
 // computes garbage here too.
 #include "cuda_runtime.h"
 
+#include <dlfcn.h>
 #include <stdio.h>
 #include <sys/mman.h>
 #include <ucontext.h>
@@ -121,6 +122,13 @@ namespace emu {
 dim3 d3(dim3 v) { return v; }
 
 void *dyn_smem() { return g_dyn.data(); }
+
+const char *self_path()
+{
+    static Dl_info info;
+    if (!info.dli_fname) dladdr((void *)&self_path, &info);
+    return info.dli_fname ? info.dli_fname : "";
+}
 
 int lane_id() { return g_cur->lin & 31; }
 

@@ -8,6 +8,7 @@ syntax and inline PTX.  This script copies the sources to an output directory wi
   asm("rsqrt.approx.ftz.f64 ...")    ->  y = emu::rsqrt_approx(x)
   st.release / ld.acquire (sys)      ->  volatile store / load
   extern __shared__ T name[];        ->  T *name = (T *)emu::dyn_smem();
+  dlopen("libnccl.so.2")             ->  dlopen(the emulated library itself), which carries tests/emu/fake_nccl.cpp
 
 and nothing else: the kernel bodies compile unchanged against tests/emu/cuda_runtime.h.
 Anything it does not recognise is an error, not a guess.
@@ -124,6 +125,9 @@ def rewrite(text, fname):
     for rx, rep in ASM_RULES:
         text = rx.sub(rep, text)
     text = DYN_SMEM.sub(r"\1 *\2 = (\1 *)emu::dyn_smem();", text)
+    # the product opens libnccl.so.2 at run time; the emulated build opens itself, where tests/emu/fake_nccl.cpp lives
+    text = text.replace('const char *names[] = {"libnccl.so.2", "libnccl.so"};',
+                        'const char *names[] = {emu::self_path(), emu::self_path()};')
     # whatever inline assembly is left would reach the x86 assembler: refuse
     code = re.sub(r"//[^\n]*", "", text)
     if re.search(r"\basm\b", code):

@@ -45,3 +45,13 @@ def test_optin_kernels_pass_on_the_emulator():
     n = _run(["tests/test_gpu_zzz_options.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
              env={"SEPGPU_TEST_UNVERIFIED": "1"})
     assert n >= 24, n
+
+
+@pytest.mark.parametrize("opts", ["", "pair_tile=1,cell_order=1"], ids=["default", "pair_tile"])
+def test_two_rank_decomposition_on_the_emulator(opts):
+    """Slab decomposition with two ranks as two threads on the emulated kernels (tests/emu/dd_threads.py; exchanges through
+    tests/emu/fake_nccl.cpp): union of the ranks' pair sets == single-domain set, per-step sums, trigger steps, final
+    positions, atom conservation over five rebuilds with migration -- the checks tests/dd_check.py makes on two GPUs."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "20", opts],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0 and "-> OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
