@@ -384,3 +384,61 @@ def test_build_prune_with_exclusions_water():
     s.call("sepgpu_neighb_build", C.byref(sys_), cm.EXCL_SAME_MOL)
     assert np.array_equal(cm.pair_set(s.pairs(4_000_000)), cm.pair_set(pairs))
     s.close()
+
+
+# ---- corner cases of the opt-in list formats -------------------------------------------------------------------------
+def test_pair_tile_capacity_growth_odd_count_and_small_grids():
+    """A deliberately tiny row capacity grows transparently (union rows are longer than per-atom rows); an odd atom
+    count leaves the last atom a single row; a 3-cell grid takes the exact builder and therefore per-atom rows."""
+    x, L = _lj(13, seed=12)                                   # 2197 atoms: odd
+    assert len(x) % 2 == 1
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    s.call("sepgpu_set_option", b"pair_tile", 1)
+    s.call("sepgpu_set_option", b"neighb_cap", 8)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+    assert _opt(s, "list_pair") == 1 and _opt(s, "neighb_cap") > 8
+    pp = np.ascontiguousarray(cm.oracle_pairs(x, L, 2.5, 0.25), dtype=np.int32)
+    assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(pp))
+    types = np.full(len(x), ord("A"), dtype=np.uint8)
+    fref = np.zeros((len(x), 3)); rref = cm.OrcRet(); length = cm.dvec3([L] * 3)
+    cm.oracle().orc_force_pairs_list(len(x), cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pp), len(pp), b"AA", 2.5,
+                                     cm.POT_LJ_SHIFT, None, cm.ptr(fref), C.byref(rref))
+    p = capi.lj_param(2.5, kind="lj_shift")
+    s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
+    assert cm.rel_force_err(s.get(capi.F_F), fref) <= FT
+    assert abs(s.scalars().epot - rref.epot) <= FT * abs(rref.epot)
+    s.close()
+    # 3 cells per side: exact warp-per-atom builder, per-atom rows, default kernel
+    x, L = cm.lattice(9, 0.7, jitter=0.2, seed=8)
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    for k in (b"pair_tile", b"cell_order", b"build_prune"):
+        s.call("sepgpu_set_option", k, 1)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    assert sys_.nsubbox[0] == 3
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+    assert _opt(s, "list_pair") == 0
+    assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(cm.oracle_pairs(x, L, 2.5, 0.25)))
+    s.close()
+
+
+def test_typed_sublist_follows_capacity_growth():
+    x, L = _lj(12, seed=2)
+    n = len(x)
+    types = np.where(np.random.default_rng(1).random(n) < 0.5, ord("B"), ord("A")).astype(np.uint8)
+    pp = np.ascontiguousarray(cm.oracle_pairs(x, L, 2.5, 0.25), dtype=np.int32)
+    fref = np.zeros((n, 3)); rref = cm.OrcRet(); length = cm.dvec3([L] * 3)
+    cm.oracle().orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pp), len(pp), b"AB", 2.5,
+                                     cm.POT_LJ_SHIFT, None, cm.ptr(fref), C.byref(rref))
+    s = capi.System(n); s.put(capi.F_X, x); s.put(capi.F_TYPE, types)
+    s.call("sepgpu_set_option", b"typed_sublist", 1)
+    s.call("sepgpu_set_option", b"neighb_cap", 8)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
+    p = capi.lj_param(2.5, kind="lj_shift")
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    s.call("sepgpu_force_lj", C.byref(sys_), b"AB", C.byref(p), cm.ALL, 1)          # builds (and grows) the list itself
+    assert _opt(s, "neighb_cap") > 8
+    assert cm.rel_force_err(s.get(capi.F_F), fref) <= FT
+    assert abs(s.scalars().epot - rref.epot) <= FT * abs(rref.epot)
+    s.close()
