@@ -324,6 +324,7 @@ bool sepgpu_dd_gather_next(sepgpu_ctx *c, GatherDev *g)
     g->seq = d->gseq; g->rank = d->rank; g->nranks = d->nranks;
     return true;
 }
+int sepgpu_dd_uses_p2p(sepgpu_ctx *c) { return c->dd && c->dd->p2p ? 1 : 0; }
 void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks) { *rank = c->dd->rank; *nranks = c->dd->nranks; }
 
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax)

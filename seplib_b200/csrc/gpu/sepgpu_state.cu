@@ -719,6 +719,8 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     return SEPGPU_EINVAL;
 }
 
+int sepgpu_dd_uses_p2p(sepgpu_ctx *c);
+
 extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *value)
 {
     if (!c || !name || !value) return SEPGPU_EINVAL;
@@ -733,6 +735,7 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "cell_order")) *value = c->cell_order;
     else if (!strcmp(name, "build_prune")) *value = c->build_prune;
     else if (!strcmp(name, "list_pair")) *value = c->list_valid && c->list_pair ? 1 : 0;
+    else if (!strcmp(name, "dd_p2p")) *value = sepgpu_dd_uses_p2p(c);               // decomposed run on the peer-memory path
     else if (!strcmp(name, "max_half")) *value = c->scal_host->max_half;            // longest reference-style half list, last build
     else if (!strcmp(name, "row_entries")) *value = c->scal_host->row_entries;      // as of the last list build (pair-tile format)
     else { sepgpu_set_error("sepgpu_get_option: unknown option '%s'", name); return SEPGPU_EINVAL; }

@@ -28,7 +28,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__ static
+#define __shared__ static thread_local     // one block at a time PER HOST THREAD (ranks of a decomposed run are threads)
 #define __constant__ static
 
 // ---- vector types ----------------------------------------------------------------------------------------------
@@ -55,8 +55,8 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 
 extern "C" long long sepgpu_emu_counter[8];      // work statistics kernels may bump under #ifdef SEPGPU_EMU
-extern uint3 threadIdx, blockIdx;
-extern dim3 blockDim, gridDim;
+extern thread_local uint3 threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
 static const int warpSize = 32;
 
 // ---- the fiber scheduler ----------------------------------------------------------------------------------------
@@ -200,15 +200,40 @@ template <class T> static inline T __ldca(const T *p) { return *p; }
 template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 template <class T> static inline void __stcg(T *p, T v) { *p = v; }
 
-// atomics: one host thread runs all fibers, and a fiber is only switched out at a rendezvous
-template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
-template <class T> static inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }
-template <class T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
-template <class T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
-template <class T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
-template <class T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
-template <class T> static inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
-template <class T> static inline T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+// atomics: the fibers of a block share one host thread and are only switched at a rendezvous, but kernels of different
+// host threads (ranks of a decomposed run) run concurrently and may meet in peer-mapped memory
+template <class T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline double atomicAdd(double *p, double v)
+{
+    unsigned long long *q = (unsigned long long *)p, o = __atomic_load_n(q, __ATOMIC_SEQ_CST), n;
+    double od;
+    do { memcpy(&od, &o, 8); const double nd = od + v; memcpy(&n, &nd, 8); } while (!__atomic_compare_exchange_n(q, &o, n, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    return od;
+}
+static inline float atomicAdd(float *p, float v)
+{
+    unsigned *q = (unsigned *)p, o = __atomic_load_n(q, __ATOMIC_SEQ_CST), n;
+    float of;
+    do { memcpy(&of, &o, 4); const float nf = of + v; memcpy(&n, &nf, 4); } while (!__atomic_compare_exchange_n(q, &o, n, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+    return of;
+}
+template <class T> static inline T atomicSub(T *p, T v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicMax(T *p, T v)
+{
+    T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
+template <class T> static inline T atomicMin(T *p, T v)
+{
+    T o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
+template <class T> static inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicAnd(T *p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+template <class T> static inline T atomicCAS(T *p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 
 // ---- runtime API --------------------------------------------------------------------------------------------------------
 typedef int cudaError_t;

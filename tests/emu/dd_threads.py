@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Two-rank slab decomposition on the CPU kernel emulator: the ranks are two THREADS of this process, each driving its
-own sepgpu context; tests/emu/fake_nccl.cpp carries their exchanges (peer memory is not available here, so the library
-takes its NCCL path: halo send/recv every step, migration at rebuilds, all-reduced integrator sums).  Same checks as
+own sepgpu context.  Default: the library's peer-memory path (halo pushed into the neighbour's buffer with release/acquire
+flags, integrator sums all-gathered through the peer blocks) -- the emulator hands out in-process "IPC" handles and the
+two ranks' kernels run concurrently; SEPGPU_EMU_NO_IPC=1 (or SEPGPU_DD_P2P=0): the NCCL path (tests/emu/fake_nccl.cpp:
+halo send/recv every step, all-reduced sums).  Migration at rebuilds goes through the NCCL stand-in in both.  Same checks as
 tests/dd_check.py on hardware: union of the ranks' pair sets == single-domain pair set at compared rebuilds, per-step
 epot / ekin / alpha / max displacement equal to 1e-9 relative, trigger steps equal, final positions by global id equal
 to 1e-7, atom count conserved across migration.
@@ -67,6 +69,8 @@ def main():
                     lp = C.c_longlong(-1)
                     s.call("sepgpu_get_option", b"list_pair", C.byref(lp))
                     shared["list_pair"] = lp.value
+                    s.call("sepgpu_get_option", b"dd_p2p", C.byref(lp))
+                    shared["p2p"] = lp.value
                 pr = None
                 if step in check_steps:
                     pr = cm.pair_set(s.pairs(max_pairs=int(sc.npairs_listed) + 16))
@@ -135,8 +139,9 @@ def main():
     builds = ref.scalars().nbuild
     ref.close()
     ok = ok and err <= 1e-7 and builds >= 3 and shared.get("list_pair") == int(opts.get("pair_tile", 0))
+    ok = ok and shared.get("p2p") == (0 if os.environ.get("SEPGPU_EMU_NO_IPC") == "1" or os.environ.get("SEPGPU_DD_P2P") == "0" else 1)
     print(f"dd_threads: world={WORLD} n={n} steps={nsteps} layers={nz} builds={builds} pair-set checks={checked} "
-          f"max|dx|={err:.2e} list_pair={shared.get('list_pair')} own/halo(rank0)={shared['final'][0][2]}/{shared['final'][0][3]} opts={opts} -> {'OK' if ok else 'FAIL'}")
+          f"max|dx|={err:.2e} list_pair={shared.get('list_pair')} p2p={shared.get('p2p')} own/halo(rank0)={shared['final'][0][2]}/{shared['final'][0][3]} opts={opts} -> {'OK' if ok else 'FAIL'}")
     return 0 if ok else 1
 
 

@@ -17,8 +17,10 @@
 #include <mutex>
 #include <vector>
 
-uint3 threadIdx, blockIdx;
-dim3 blockDim, gridDim;
+// All scheduler state is per HOST thread: the ranks of an emulated decomposed run are threads that launch kernels
+// concurrently (a kernel of one rank may spin on a flag that a kernel of another rank raises in peer-mapped memory).
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
 
 namespace {
 enum { READY = 0, AT_BARRIER = 1, AT_WARP = 2, DONE = 3 };
@@ -33,14 +35,13 @@ struct Fiber {
 };
 const size_t STACK_BYTES = 256 * 1024;
 const int MAX_THREADS = 1024;
-char *g_stacks = nullptr;
-std::vector<Fiber> g_fibers;
-ucontext_t g_sched;
-Fiber *g_cur = nullptr;
-const std::function<void()> *g_body = nullptr;
-const char *g_kernel = "?";
-std::vector<unsigned char> g_dyn;
-std::recursive_mutex g_lock;
+thread_local char *g_stacks = nullptr;
+thread_local std::vector<Fiber> g_fibers;
+thread_local ucontext_t g_sched;
+thread_local Fiber *g_cur = nullptr;
+thread_local const std::function<void()> *g_body = nullptr;
+thread_local const char *g_kernel = "?";
+thread_local std::vector<unsigned char> g_dyn;
 long long g_launches = 0;
 
 void fiber_main()
@@ -150,7 +151,6 @@ void warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32])
 
 void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
 {
-    std::lock_guard<std::recursive_mutex> guard(g_lock);
     const int nthreads = (int)(block.x * block.y * block.z);
     if (nthreads <= 0 || nthreads > MAX_THREADS || grid.x == 0 || grid.y == 0 || grid.z == 0) {
         fprintf(stderr, "emu: invalid launch configuration for %s: grid (%u,%u,%u) block (%u,%u,%u)\n", name, grid.x, grid.y,
@@ -163,7 +163,7 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
         if (g_stacks == (char *)MAP_FAILED) { perror("emu: mmap"); abort(); }
         g_fibers.resize(MAX_THREADS);
     }
-    g_launches++;
+    __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED);
     g_kernel = name;
     g_body = &body;
     blockDim = block;
@@ -255,6 +255,15 @@ cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t_ms = now_ms(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t_ms - a->t_ms); return cudaSuccess; }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+// "Inter-process" handles inside one process: the handle carries the pointer (ranks are threads of this process).
+// SEPGPU_EMU_NO_IPC=1 makes the export fail, which sends the library down its NCCL-only path.
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+    const char *no = getenv("SEPGPU_EMU_NO_IPC");
+    if (no && no[0] == '1') return cudaErrorNotSupported;
+    memset(h, 0, sizeof *h);
+    memcpy(h->reserved, &p, sizeof p);
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

@@ -47,11 +47,14 @@ def test_optin_kernels_pass_on_the_emulator():
     assert n >= 26, n
 
 
-@pytest.mark.parametrize("opts", ["", "pair_tile=1,cell_order=1"], ids=["default", "pair_tile"])
-def test_two_rank_decomposition_on_the_emulator(opts):
-    """Slab decomposition with two ranks as two threads on the emulated kernels (tests/emu/dd_threads.py; exchanges through
-    tests/emu/fake_nccl.cpp): union of the ranks' pair sets == single-domain set, per-step sums, trigger steps, final
-    positions, atom conservation over five rebuilds with migration -- the checks tests/dd_check.py makes on two GPUs."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "20", opts],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+@pytest.mark.parametrize("opts,no_ipc", [("", "0"), ("pair_tile=1,cell_order=1", "0"), ("", "1")],
+                         ids=["peer-memory", "peer-memory+pair_tile", "nccl-path"])
+def test_two_rank_decomposition_on_the_emulator(opts, no_ipc):
+    """Slab decomposition with two ranks as two THREADS on the emulated kernels (tests/emu/dd_threads.py): union of the
+    ranks' pair sets == single-domain set, per-step sums, trigger steps, final positions, atom conservation over several
+    rebuilds with migration -- the checks tests/dd_check.py makes on two GPUs.  Both transport paths: peer memory (the
+    emulator hands out in-process IPC handles; the two ranks' kernels run concurrently and meet at release/acquire
+    flags) and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "14", opts],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc))
     assert r.returncode == 0 and "-> OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
