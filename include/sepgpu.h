@@ -202,6 +202,7 @@ int sepgpu_set_option(sepgpu_ctx *ctx, const char *name, long long value);
  *   cell_order     = 0 | 1     slots inside a cell by atom index | along a Morton curve of 4^3 sub-cells (default 0)
  *   pair_tile      = 0 | 1     lists hold rows per PAIR of sorted atoms, served by k_lj_pairtile; uncharged single-GPU
  *                              systems only -- Coulomb and DPD need per-atom rows (default 0)
+ *   pt_ctas, coul2_ctas = 4 | 5 | 6   register budget (CTAs per SM) of k_lj_pairtile / k_coulomb_list2 (default 5)
  * sepgpu_get_option also answers "list_pair" (1 when the current list is in pair-tile format). */
 int sepgpu_get_option(sepgpu_ctx *ctx, const char *name, long long *value);
 

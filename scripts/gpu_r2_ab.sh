@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 opener (1 GPU, ~12 min): the opt-in kernels were brought up on the CPU kernel emulator in round 1 and have not
+# Round-2 opener (1 GPU, ~15 min): the opt-in kernels were brought up on the CPU kernel emulator in round 1 and have not
 # run on hardware.  (1) their parity tests on the GPU, (2) A/B of every option on the configuration it targets.
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_r2_ab.sh'
 # Reads: gpurun_out/r2_ab.txt (one line per run), gpurun_out/r2_ab_*.json (full bench lines).
@@ -32,6 +32,10 @@ run lj_cellorder      lj "cell_order=1" $S
 run lj_pairtile       lj "pair_tile=1" $S
 run lj_pairtile_co    lj "pair_tile=1,cell_order=1" $S
 run lj_all            lj "pair_tile=1,cell_order=1,build_prune=1" $S
+run lj_all_ctas4      lj "pair_tile=1,cell_order=1,build_prune=1,pt_ctas=4" $S
+run lj_all_ctas6      lj "pair_tile=1,cell_order=1,build_prune=1,pt_ctas=6" $S
+run lj_all_grid2368   lj "pair_tile=1,cell_order=1,build_prune=1,force_grid=2368" $S
+run lj_default_g2368  lj "force_grid=2368" $S
 echo "== C2: butane 864k atoms" | tee -a gpurun_out/r2_ab.txt
 S="--steps 300 --warmup 50"
 run butane_default    butane "" $S
@@ -41,3 +45,5 @@ run water_default     water "" $S
 run water_coul2       water "coulomb_kernel=2" $S
 run water_sublist     water "typed_sublist=1" $S
 run water_all         water "coulomb_kernel=2,typed_sublist=1,build_prune=1" $S
+run water_all_ctas4   water "coulomb_kernel=2,typed_sublist=1,build_prune=1,coul2_ctas=4" $S
+run water_all_ctas6   water "coulomb_kernel=2,typed_sublist=1,build_prune=1,coul2_ctas=6" $S

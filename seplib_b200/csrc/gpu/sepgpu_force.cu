@@ -369,9 +369,10 @@ __device__ __forceinline__ void lj_tile_step(const d4 &pa, const d4 &pb, const d
     }
 }
 
-#define PT_MIN_CTAS 5
-template <bool TYPED, bool STORE>
-__global__ void __launch_bounds__(FORCE_BLOCK, PT_MIN_CTAS)
+// MINB: CTAs per SM the register budget is cut for (option pt_ctas: 4 = 128 registers, 5 = 96 and a few spilled bytes,
+// 6 = 80) -- the occupancy / spill trade is to be settled on hardware
+template <bool TYPED, bool STORE, int MINB>
+__global__ void __launch_bounds__(FORCE_BLOCK, MINB)
 k_lj_pairtile(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
               const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int pairs_per_cta,
               LJDev P, BoxDev B, double *__restrict__ partial)
@@ -775,13 +776,18 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
         grid = (npairs + ppc - 1) / ppc;
         ktimer_begin(c, &c->t_force);
 #define PT_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, ppc, P, B, c->partial
-        if (typed) {
-            if (store) k_lj_pairtile<true, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
-            else       k_lj_pairtile<true, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
-        } else {
-            if (store) k_lj_pairtile<false, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
-            else       k_lj_pairtile<false, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);
-        }
+#define PT_LAUNCH(MB)                                                                                       \
+        do {                                                                                                \
+            if (typed) {                                                                                    \
+                if (store) k_lj_pairtile<true, true, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);     \
+                else       k_lj_pairtile<true, false, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);    \
+            } else {                                                                                        \
+                if (store) k_lj_pairtile<false, true, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);    \
+                else       k_lj_pairtile<false, false, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);   \
+            }                                                                                               \
+        } while (0)
+        if (c->pt_ctas == 4) PT_LAUNCH(4); else if (c->pt_ctas == 6) PT_LAUNCH(6); else PT_LAUNCH(5);
+#undef PT_LAUNCH
 #undef PT_ARGS
         ktimer_end(c, &c->t_force);
         KERNEL_CHECK();

@@ -194,9 +194,9 @@ __global__ void k_make_xq(const d4 *__restrict__ xs, const double *__restrict__ 
     xq[s] = p;
 }
 
-#define COUL2_MIN_CTAS 5
-template <bool STORE>
-__global__ void __launch_bounds__(FORCE_BLOCK, COUL2_MIN_CTAS)
+// MINB: CTAs per SM the register budget is cut for (option coul2_ctas = 4 | 5 | 6), to be settled on hardware
+template <bool STORE, int MINB>
+__global__ void __launch_bounds__(FORCE_BLOCK, MINB)
 k_coulomb_list2(const d4 *__restrict__ xq, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
                 const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int atoms_per_cta,
                 CoulDev P, BoxC B, double *__restrict__ partial)
@@ -389,8 +389,13 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
         grid = (c->n + apc - 1) / apc;
         ktimer_begin(c, &c->t_coul);
         k_make_xq<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->xs, c->z, c->order, c->xq, c->n);
-        if (store) k_coulomb_list2<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial);
-        else       k_coulomb_list2<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial);
+#define C2_LAUNCH(MB)                                                                                                                                            \
+        do {                                                                                                                                                     \
+            if (store) k_coulomb_list2<true, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial);  \
+            else       k_coulomb_list2<false, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial); \
+        } while (0)
+        if (c->coul2_ctas == 4) C2_LAUNCH(4); else if (c->coul2_ctas == 6) C2_LAUNCH(6); else C2_LAUNCH(5);
+#undef C2_LAUNCH
         ktimer_end(c, &c->t_coul);
         KERNEL_CHECK();
         c->f_zero = false;

@@ -176,6 +176,7 @@ struct sepgpu_ctx {
     int build_prune;             // tiled list builder skips candidate cells beyond the cutoff (0 = off, default)
     int cell_order;              // slots inside a cell: 0 by atom index (default), 1 along a Morton curve of 4^3 sub-cells
     unsigned char *subkey;       // [ncap] sub-cell code per atom (cell_order = 1)
+    int pt_ctas, coul2_ctas;     // register budget of k_lj_pairtile / k_coulomb_list2: CTAs per SM (4, 5 or 6; 0 = 5)
     int pair_tile;               // SEP_ALL lists in pair-tile format + k_lj_pairtile (0 = off, default)
     int coulomb_kernel;          // 1: first list Coulomb kernel (hardware-verified default); 2: k_coulomb_list2
     int typed_sublist;           // typed Lennard-Jones calls walk a per-type sub-list (0 = off, default)

@@ -697,6 +697,11 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
+    if (!strcmp(name, "pt_ctas") || !strcmp(name, "coul2_ctas")) {
+        if (value != 0 && value != 4 && value != 5 && value != 6) return SEPGPU_EINVAL;
+        if (name[0] == 'p') c->pt_ctas = (int)value; else c->coul2_ctas = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "build_prune")) { c->build_prune = value != 0; return 0; }
     if (!strcmp(name, "cell_order")) { if (value != 0 && value != 1) return SEPGPU_EINVAL; c->cell_order = (int)value; c->list_valid = false; return 0; }
     if (!strcmp(name, "pair_tile")) { c->pair_tile = value != 0; c->list_valid = false; return 0; }
