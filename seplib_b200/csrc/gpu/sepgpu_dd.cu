@@ -552,26 +552,6 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
 }
 
 // ---- every step: refresh the halo coordinates ---------------------------------------------------------------
-__global__ void k_dd_pack_xu(const d4 *__restrict__ x4, const i4 *__restrict__ cr4, const int *__restrict__ idx, int n,
-                             double Lx, double Ly, double Lz, d4 *__restrict__ out)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int i = idx[k];
-    d4 x = x4[i];
-    const int w = cr4[i].w;                              // crossings since the list was built (packed, see sepgpu_intgr.cu)
-    if (w != 0) {
-        x.x += ((w & 1023) - 512) * Lx; x.y += (((w >> 10) & 1023) - 512) * Ly; x.z += (((w >> 20) & 1023) - 512) * Lz;
-    }
-    out[k] = x;
-}
-
-__global__ void k_dd_unpack_xu(const d4 *__restrict__ in, int n, int first_local, const int *__restrict__ rank, d4 *__restrict__ xs)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    xs[rank[first_local + k]] = in[k];
-}
 
 // both directions in one launch
 __global__ void k_dd_pack_xu2(const d4 *__restrict__ x4, const i4 *__restrict__ cr4, const int *__restrict__ idx0, int n0,

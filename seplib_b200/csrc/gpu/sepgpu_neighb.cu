@@ -332,176 +332,10 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
     }
 }
 
-// ---- tiled build: the fast path ------------------------------------------------------------------------------
-// One CTA owns one x-run of a brick (G.bx consecutive home cells of one x-row; their atoms are
-// contiguous in the sorted array) and one THREAD owns one home atom.  For each of the 9 (dy,dz) rows
-// the G.bx+2 candidate cells are staged once into shared memory as FP32 positions already shifted to
-// the right periodic image, with the finished list entry (sorted index | image code) in .w; a thread
-// then sweeps the 3 cells around its own cell in two passes: a branch-free pass that tests 32
-// candidates into a bit mask, and a pass over the set bits that appends entries.  Every candidate is
-// read from HBM once per CTA instead of once per atom and all lanes work on different atoms.
-// Candidates inside the FP32 error band of the cutoff take the exact FP64 test (pair_exact).
+// ---- tiled build: the fast path is k_build_tile2 (sepgpu_neighb_tile.cuh) --------------------------------------------
+// brick / tile geometry shared with the host-side choice of G.bx
 #define TILE_MAXCX 8
 #define TILE_THREADS 160
-#define TILE_STAGE 768
-#define TILE_PAD 32
-
-template <unsigned OPT>
-__global__ void __launch_bounds__(TILE_THREADS)
-k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int *__restrict__ order,
-             const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
-             const int *__restrict__ excl_angle, const int *__restrict__ excl_dihed,
-             unsigned *__restrict__ nbr, int *__restrict__ cnt, DevScalars *scal, BuildParams P)
-{
-    __shared__ float4 cand[TILE_STAGE + TILE_PAD];
-    __shared__ int cand_mol[OPT == SEPGPU_EXCL_SAME_MOL ? TILE_STAGE + TILE_PAD : 1];
-    __shared__ int s_off[TILE_MAXCX + 3];      // staged offset of candidate cell cc (cc = 0..ncx+1), +1 end marker
-    __shared__ int s_jbase[TILE_MAXCX + 2];    // sorted index of a candidate = staged position + s_jbase[cc]
-    __shared__ int s_wx[TILE_MAXCX + 2];       // x image of candidate cell cc
-    __shared__ int s_home[TILE_MAXCX + 1];     // sorted-index boundaries of the home cells
-    __shared__ int s_red[3];
-
-    const CellGrid G = P.G;
-    int x0, cy, cz;
-    key_cell(blockIdx.x * G.bx, G, x0, cy, cz);
-    if (x0 >= G.nx || cy >= G.ny || cz >= G.nz) return;          // padding of the brick grid
-    const int ncx = min(G.bx, G.nx - x0);
-    const int key0 = blockIdx.x * G.bx;
-    if (threadIdx.x <= ncx) s_home[threadIdx.x] = cell_start[key0 + threadIdx.x];
-    if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
-    __syncthreads();
-    const int a0 = s_home[0], nhome = s_home[ncx] - a0;
-    if (nhome == 0) return;
-    int blk_max = 0, blk_half = 0, blk_sum = 0;
-
-    for (int ab = 0; ab < nhome; ab += TILE_THREADS) {
-        const int s = a0 + ab + threadIdx.x;
-        const bool active = s < a0 + nhome;
-        int h = 0;                                   // my home cell inside the tile
-        float4 fi = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-            for (int q = 1; q < ncx; q++) h += (s >= s_home[q]);
-            fi = xf[s];
-        }
-        const int mol_i = __float_as_int(fi.w);
-        int count = 0, half_count = 0;
-
-        for (int r = 0; r < 9; r++) {
-            const int oy = r % 3 - 1, oz = r / 3 - 1;
-            int my = cy + oy, wy = 0, mz = cz + oz, wz = 0;
-            if (my == G.ny) { my = 0; wy = 1; } else if (my == -1) { my = G.ny - 1; wy = -1; }
-            if (mz == G.nz) { mz = 0; wz = 1; } else if (mz == -1) { mz = G.nz - 1; wz = -1; }
-            __syncthreads();                         // previous row fully consumed
-            if (threadIdx.x < ncx + 2) {
-                const int cc = threadIdx.x;
-                int mx = x0 - 1 + cc, wx = 0;
-                if (mx >= G.nx) { mx -= G.nx; wx = 1; } else if (mx < 0) { mx += G.nx; wx = -1; }
-                const int key = cell_key(mx, my, mz, G);
-                s_jbase[cc] = cell_start[key];           // temporarily: begin
-                s_off[cc] = cell_start[key + 1] - s_jbase[cc];   // temporarily: length
-                s_wx[cc] = wx;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int off = 0;
-                for (int cc = 0; cc < ncx + 2; cc++) {
-                    const int len = s_off[cc];
-                    s_off[cc] = off; s_jbase[cc] -= off;
-                    off += len;
-                }
-                s_off[ncx + 2] = off;
-            }
-            __syncthreads();
-            const int total = s_off[ncx + 2];
-            const float shy = wy * P.fLy, shz = wz * P.fLz;
-            const bool half_row = (oz == 1) || (oz == 0 && oy == 1);
-            const bool centre_row = (oz == 0 && oy == 0);
-            const unsigned code_yz = 3u * (wy + 1) + 9u * (wz + 1);
-
-            for (int base = 0; base < total; base += TILE_STAGE) {
-                const int lim = min(total - base, TILE_STAGE);
-                if (base > 0) __syncthreads();
-                for (int q = threadIdx.x; q < lim + TILE_PAD; q += TILE_THREADS) {
-                    float4 f = make_float4(1e18f, 1e18f, 1e18f, 0.f);         // padding: never in range
-                    if (q < lim) {
-                        const int g = base + q;
-                        int cc = 0;
-                        for (int t = 1; t < ncx + 2; t++) cc += (g >= s_off[t]);
-                        const int j = g + s_jbase[cc];
-                        f = xf[j];
-                        if (OPT == SEPGPU_EXCL_SAME_MOL) cand_mol[q] = __float_as_int(f.w);
-                        f.x += s_wx[cc] * P.fLx; f.y += shy; f.z += shz;
-                        f.w = __uint_as_float((unsigned)j | (((unsigned)(s_wx[cc] + 1) + code_yz) << SEPGPU_SHIFT_BITS));
-                    }
-                    cand[q] = f;
-                }
-                __syncthreads();
-                if (active) {
-                    // my window: candidate cells h, h+1, h+2 -- contiguous in the staged row
-                    const int wlo = max(s_off[h], base) - base, whi = min(s_off[h + 3], base + lim) - base;
-                    // positions that split the window for the reference half-list count
-                    const int cut_a = min(max(s_off[h + 1] - base, wlo), whi);      // start of my own cell (ox = 0)
-                    const int cut_b = min(max(s_off[h + 2] - base, wlo), whi);      // start of cell ox = +1
-                    const int self_q = (centre_row ? s - s_jbase[h + 1] : -1) - base; // my own staged position
-                    for (int q0 = wlo; q0 < whi; q0 += 32) {
-                        unsigned mask = 0, band = 0;
-#pragma unroll
-                        for (int b = 0; b < 32; b++) {
-                            const float4 fj = cand[q0 + b];
-                            const float dx = fi.x - fj.x, dy = fi.y - fj.y, dz = fi.z - fj.z;
-                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            if (r2 <= P.fcut_hi) mask |= 1u << b;
-                            if (r2 >= P.fcut_lo) band |= 1u << b;
-                        }
-                        const int nvalid = whi - q0;
-                        if (nvalid < 32) mask &= (1u << nvalid) - 1u;
-                        if ((unsigned)(self_q - q0) < 32u) mask &= ~(1u << (self_q - q0));
-                        band &= mask;
-                        while (mask) {
-                            const int b = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const int q = q0 + b;
-                            unsigned entry = __float_as_uint(cand[q].w);
-                            const int j = (int)(entry & SEPGPU_INDEX_MASK);
-                            if ((band >> b) & 1u) {                                   // inside the FP32 error band
-                                int code;
-                                if (!pair_exact(xs[s], xs[j], P, code)) continue;
-                                entry = (unsigned)j | ((unsigned)code << SEPGPU_SHIFT_BITS);
-                            }
-                            if (OPT != SEPGPU_ALL &&
-                                excluded<OPT>(mol_i, OPT == SEPGPU_EXCL_SAME_MOL ? cand_mol[q] : 0, s, j, order,
-                                              excl_bond, excl_angle, excl_dihed)) continue;
-                            if (count < P.cap) nbr[nbr_index(count, s, P.npad)] = entry;
-                            count++;
-                            // reference half list: cells of the half stencil, or my own cell with j2 > j1
-                            const bool in_half = half_row || (centre_row && (q >= cut_b || (q >= cut_a && j > s)));
-                            half_count += in_half ? 1 : 0;
-                        }
-                    }
-                }
-            }
-        }
-        if (active) {
-            cnt[s] = min(count, P.cap);
-            blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += count;
-        }
-    }
-    // block statistics: warp reduce, then shared atomics, then three global atomics per CTA
-    for (int o = 16; o > 0; o >>= 1) {
-        blk_max = max(blk_max, __shfl_xor_sync(0xffffffffu, blk_max, o));
-        blk_half = max(blk_half, __shfl_xor_sync(0xffffffffu, blk_half, o));
-        blk_sum += __shfl_xor_sync(0xffffffffu, blk_sum, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&s_red[0], blk_max); atomicMax(&s_red[1], blk_half); atomicAdd(&s_red[2], blk_sum);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        atomicMax(&scal->max_neighb, s_red[0]);
-        atomicMax(&scal->max_half, s_red[1]);
-        atomicAdd((unsigned long long *)&scal->npairs_listed, (unsigned long long)s_red[2]);
-    }
-}
 
 #include "sepgpu_neighb_tile.cuh"
 

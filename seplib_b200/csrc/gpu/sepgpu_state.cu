@@ -44,11 +44,6 @@ __global__ void k_init_tags(d4 *x4, d4 *v4, int n)
     v4[i].w = 1.0;
 }
 
-__global__ void k_fill_int(int *p, int v, size_t n)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 
 extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
 {
