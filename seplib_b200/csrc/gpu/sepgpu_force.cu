@@ -264,12 +264,16 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
                 } else {
                     {
                         const bool v1 = left > 1;
+                        SEPGPU_EMU_GATHER(&xs[cur.x & SEPGPU_INDEX_MASK]);
+                        SEPGPU_EMU_GATHER(&xs[(v1 ? cur.y : cur.x) & SEPGPU_INDEX_MASK]);
                         const d4 p0 = xs[cur.x & SEPGPU_INDEX_MASK];
                         const d4 p1 = xs[(v1 ? cur.y : cur.x) & SEPGPU_INDEX_MASK];
                         lj_pair2<TYPED>(pi, p0, p1, cur.x, cur.y, v1, ti, P, B, A);
                     }
                     if (left > 2) {
                         const bool v3 = left > 3;
+                        SEPGPU_EMU_GATHER(&xs[cur.z & SEPGPU_INDEX_MASK]);
+                        SEPGPU_EMU_GATHER(&xs[(v3 ? cur.w : cur.z) & SEPGPU_INDEX_MASK]);
                         const d4 p2 = xs[cur.z & SEPGPU_INDEX_MASK];
                         const d4 p3 = xs[(v3 ? cur.w : cur.z) & SEPGPU_INDEX_MASK];
                         lj_pair2<TYPED>(pi, p2, p3, cur.z, cur.w, v3, ti, P, B, A);
@@ -422,18 +426,22 @@ k_lj_pairtile(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const
                 if (c + 1 < nch) nxt = __ldcs(row + (size_t)(c + 1) * npad);
                 const int left = m - 4 * c;                      // >= 1 valid entries in this chunk
                 {
+                    SEPGPU_EMU_GATHER(&xs[cur.x & SEPGPU_PT_INDEX_MASK]);
                     const d4 pj = xs[cur.x & SEPGPU_PT_INDEX_MASK];
                     lj_tile_step<TYPED>(p1, p2, pj, cur.x | kill, t1, tb, P, B, A);
                 }
                 if (left > 1) {
+                    SEPGPU_EMU_GATHER(&xs[cur.y & SEPGPU_PT_INDEX_MASK]);
                     const d4 pj = xs[cur.y & SEPGPU_PT_INDEX_MASK];
                     lj_tile_step<TYPED>(p1, p2, pj, cur.y | kill, t1, tb, P, B, A);
                 }
                 if (left > 2) {
+                    SEPGPU_EMU_GATHER(&xs[cur.z & SEPGPU_PT_INDEX_MASK]);
                     const d4 pj = xs[cur.z & SEPGPU_PT_INDEX_MASK];
                     lj_tile_step<TYPED>(p1, p2, pj, cur.z | kill, t1, tb, P, B, A);
                 }
                 if (left > 3) {
+                    SEPGPU_EMU_GATHER(&xs[cur.w & SEPGPU_PT_INDEX_MASK]);
                     const d4 pj = xs[cur.w & SEPGPU_PT_INDEX_MASK];
                     lj_tile_step<TYPED>(p1, p2, pj, cur.w | kill, t1, tb, P, B, A);
                 }

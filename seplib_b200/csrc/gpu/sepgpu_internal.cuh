@@ -189,6 +189,14 @@ struct sepgpu_ctx {
     void *flush_buf; size_t flush_bytes;
 };
 
+// CPU kernel emulator (tests/emu): scattered loads marked with this macro are counted as warp-wide requests and the
+// 128-byte lines they touch; compiles to nothing in the product
+#ifdef SEPGPU_EMU
+#define SEPGPU_EMU_GATHER(p) emu::record_gather(p)
+#else
+#define SEPGPU_EMU_GATHER(p) ((void)0)
+#endif
+
 // ---- error plumbing -------------------------------------------------------------------------------
 void sepgpu_set_error(const char *fmt, ...);
 #define CUDA_TRY(call)                                                                      \

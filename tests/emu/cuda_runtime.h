@@ -74,6 +74,11 @@ void sync_block();
 // the caller's own value)
 void warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32]);
 int lane_id();
+// gather statistics (SEPGPU_EMU_GATHER_STATS=1): kernels mark their scattered loads with SEPGPU_EMU_GATHER(ptr); the k-th
+// marked load of every lane of a warp is taken as one warp-wide request, and the distinct 128-byte lines it touches are
+// counted -- the L1 wavefront count the force kernels are bound by.  sepgpu_emu_counter[1] += requests, [2] += lines,
+// [3] += lane loads, per launch.
+void record_gather(const void *p);
 static inline double rcp_approx(double x) { return (double)(1.0f / (float)x); }
 static inline double rsqrt_approx(double x) { return (double)(1.0f / sqrtf((float)x)); }
 }  // namespace emu

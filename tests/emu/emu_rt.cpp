@@ -14,6 +14,7 @@
 #include <sys/mman.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -32,6 +33,7 @@ struct Fiber {
     uint64_t snap[32];
     uint3 tid;
     int lin;
+    int gseq;             // marked gathers issued so far (gather statistics)
 };
 const size_t STACK_BYTES = 256 * 1024;
 const int MAX_THREADS = 1024;
@@ -43,6 +45,24 @@ thread_local const std::function<void()> *g_body = nullptr;
 thread_local const char *g_kernel = "?";
 thread_local std::vector<unsigned char> g_dyn;
 long long g_launches = 0;
+// gather statistics of the block being run: (warp << 32 | sequence number, 128-byte line)
+thread_local std::vector<std::pair<unsigned long long, unsigned long long>> g_gathers;
+int g_gather_stats = -1;
+
+void flush_gathers()
+{
+    if (g_gathers.empty()) return;
+    std::sort(g_gathers.begin(), g_gathers.end());
+    long long requests = 0, lines = 0;
+    for (size_t k = 0; k < g_gathers.size(); k++) {
+        if (k == 0 || g_gathers[k].first != g_gathers[k - 1].first) { requests++; lines++; }
+        else if (g_gathers[k].second != g_gathers[k - 1].second) lines++;
+    }
+    __atomic_fetch_add(&sepgpu_emu_counter[1], requests, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&sepgpu_emu_counter[2], lines, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&sepgpu_emu_counter[3], (long long)g_gathers.size(), __ATOMIC_RELAXED);
+    g_gathers.clear();
+}
 
 void fiber_main()
 {
@@ -133,6 +153,14 @@ const char *self_path()
 
 int lane_id() { return g_cur->lin & 31; }
 
+void record_gather(const void *p)
+{
+    if (g_gather_stats < 0) { const char *e = getenv("SEPGPU_EMU_GATHER_STATS"); g_gather_stats = e && e[0] == '1'; }
+    if (!g_gather_stats) return;
+    Fiber *me = g_cur;
+    g_gathers.emplace_back(((unsigned long long)(me->lin >> 5) << 32) | (unsigned)me->gseq++, (unsigned long long)(uintptr_t)p >> 7);
+}
+
 void sync_block()
 {
     g_cur->state = AT_BARRIER;
@@ -187,8 +215,10 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
                             f.state = READY;
                             f.tid.x = tx; f.tid.y = ty; f.tid.z = tz;
                             f.lin = t;
+                            f.gseq = 0;
                         }
                 run_block(nthreads);
+                flush_gathers();
             }
     g_cur = nullptr;
 }
