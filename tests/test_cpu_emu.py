@@ -19,7 +19,7 @@ RUNNER = os.path.join(ROOT, "tests", "emu", "run_on_emu.py")
 
 # the long trajectories and the linked example programs (thousands of steps) are left to the hardware run
 FAST = ("not prg and not md_trajectory and not lj_loop and not molecular_pressure and not fij_list "
-        "and not compress_box and not berendsen and not slit_pore")
+        "and not compress_box and not berendsen and not slit_pore and not lj_golden and not lj_trajectory_golden")
 
 
 def _run(args, timeout=1500, env=None):
@@ -34,9 +34,10 @@ def _run(args, timeout=1500, env=None):
 
 
 def test_gpu_parity_tests_pass_on_the_emulated_kernels():
-    n = _run(["tests/test_gpu_lj.py", "tests/test_gpu_more.py", "tests/test_gpu_zz_next.py", "-m", "gpu", "-q", "-x",
-              "-k", FAST, "-p", "no:cacheprovider"])
-    assert n >= 20, n
+    # tests/test_golden.py: the reference's own recorded butane / water / DPD vectors against the emulated kernels
+    n = _run(["tests/test_gpu_lj.py", "tests/test_gpu_more.py", "tests/test_gpu_zz_next.py", "tests/test_golden.py", "-m", "gpu",
+              "-q", "-x", "-k", FAST, "-p", "no:cacheprovider"])
+    assert n >= 24, n
 
 
 def test_optin_kernels_pass_on_the_emulator():
