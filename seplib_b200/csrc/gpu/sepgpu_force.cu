@@ -600,9 +600,78 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_end(sepgpu_ctx *c);
 
+// Option fin_multi: the same reduction spread over several CTAs.  CTA b sums a fixed chunk of rows into stage row b;
+// the CTA that draws the last ticket adds the stage rows in index order and applies the result -- fixed chunks and a
+// fixed final order, so the sums are as deterministic as the single-CTA kernel's (not bit-identical to it: the
+// association differs).  One launch, parallel row loads instead of one CTA's serial latency chain.
+#define FIN2_THREADS 256
+#define FIN2_MAX_CTAS 64
+__global__ void __launch_bounds__(FIN2_THREADS)
+k_finalize_force_multi(const double *__restrict__ partial, int nrows, double *__restrict__ stage, unsigned *ticket,
+                       DevScalars *scal, double scale, int flags)
+{
+    __shared__ double red[SEPGPU_NPART_F * (FIN2_THREADS / 32)];
+    __shared__ double tot[SEPGPU_NPART_F];
+    __shared__ int s_last;
+    const int chunk = (nrows + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * chunk, r1 = min(nrows, r0 + chunk);
+    double v[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) v[q] = 0.0;
+    for (int r = r0 + (int)threadIdx.x; r < r1; r += FIN2_THREADS) {
+        const double4 a = *reinterpret_cast<const double4 *>(partial + (size_t)r * SEPGPU_NPART_F);
+        const double4 b = *reinterpret_cast<const double4 *>(partial + (size_t)r * SEPGPU_NPART_F + 4);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    block_sum<SEPGPU_NPART_F, FIN2_THREADS>(v, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_F; q++) stage[blockIdx.x * SEPGPU_NPART_F + q] = v[q];
+        __threadfence();                                            // stage row visible before the ticket is drawn
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < SEPGPU_NPART_F) {
+        double a = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) a += __ldcg(stage + b * SEPGPU_NPART_F + threadIdx.x);
+        tot[threadIdx.x] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0;                                                // ready for the next launch on this stream
+        if (flags & 8) reset_ret_block(scal);
+        const double e = tot[0] * scale, ec = tot[1] * scale;
+        if (flags & 1) scal->epot = e; else scal->epot += e;
+        if (flags & 4) { scal->epot += ec; scal->ecoul += ec; }
+        const double xx = tot[2] * scale, xy = tot[3] * scale, xz = tot[4] * scale;
+        const double yy = tot[5] * scale, yz = tot[6] * scale, zz = tot[7] * scale;
+        const double P[9] = {xx, xy, xz, xy, yy, yz, xz, yz, zz};
+        for (int k = 0; k < 9; k++) {
+            scal->pot_P[k] += P[k];
+            if (flags & 2) scal->pot_P_bond[k] += P[k];
+        }
+    }
+}
+
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
 {
     if (c->ret_reset_pending) { flags |= 8; c->ret_reset_pending = false; }
+    if (c->fin_multi) {
+        if (!c->fin_ticket) {
+            CUDA_TRY(cudaMalloc((void **)&c->fin_ticket, sizeof(unsigned)));
+            CUDA_TRY(cudaMemsetAsync(c->fin_ticket, 0, sizeof(unsigned), c->stream));
+        }
+        int per = (nrows + FIN2_MAX_CTAS - 1) / FIN2_MAX_CTAS;           // rows per CTA: at least 8, at most 64 CTAs
+        if (per < 8) per = 8;
+        const int ctas = nrows > 0 ? (nrows + per - 1) / per : 1;
+        // stage rows live behind the largest possible set of force rows of the partial buffer
+        double *stage = c->partial + (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * SEPGPU_NPART_F;
+        k_finalize_force_multi<<<ctas, FIN2_THREADS, 0, c->stream>>>(c->partial, nrows, stage, c->fin_ticket, c->scal, scale, flags);
+        KERNEL_CHECK();
+        return 0;
+    }
     k_finalize_force<<<1, FIN_THREADS, 0, c->stream>>>(c->partial, nrows, c->scal, scale, flags);
     KERNEL_CHECK();
     return 0;

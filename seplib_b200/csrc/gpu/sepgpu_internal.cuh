@@ -173,6 +173,8 @@ struct sepgpu_ctx {
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
     int force_grid;              // CTAs of the list force kernel (0 = default)
     int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
+    int fin_multi;               // multi-CTA final reduction of the force partial rows (0 = off, default)
+    unsigned *fin_ticket;        // its ticket counter
     int build_prune;             // tiled list builder skips candidate cells beyond the cutoff (0 = off, default)
     int cell_order;              // slots inside a cell: 0 by atom index (default), 1 along a Morton curve of 4^3 sub-cells
     unsigned char *subkey;       // [ncap] sub-cell code per atom (cell_order = 1)

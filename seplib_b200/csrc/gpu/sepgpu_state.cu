@@ -135,6 +135,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->tsort) cudaFree(c->tsort);
     if (c->xq) cudaFree(c->xq);
     if (c->subkey) cudaFree(c->subkey);
+    if (c->fin_ticket) cudaFree(c->fin_ticket);
     if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
@@ -697,6 +698,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
         if (name[0] == 'p') c->pt_ctas = (int)value; else c->coul2_ctas = (int)value;
         return 0;
     }
+    if (!strcmp(name, "fin_multi")) { c->fin_multi = value != 0; return 0; }
     if (!strcmp(name, "build_prune")) { c->build_prune = value != 0; return 0; }
     if (!strcmp(name, "cell_order")) { if (value != 0 && value != 1) return SEPGPU_EINVAL; c->cell_order = (int)value; c->list_valid = false; return 0; }
     if (!strcmp(name, "pair_tile")) { c->pair_tile = value != 0; c->list_valid = false; return 0; }
@@ -734,6 +736,7 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "pair_tile")) *value = c->pair_tile;
     else if (!strcmp(name, "cell_order")) *value = c->cell_order;
     else if (!strcmp(name, "build_prune")) *value = c->build_prune;
+    else if (!strcmp(name, "fin_multi")) *value = c->fin_multi;
     else if (!strcmp(name, "list_pair")) *value = c->list_valid && c->list_pair ? 1 : 0;
     else if (!strcmp(name, "dd_p2p")) *value = sepgpu_dd_uses_p2p(c);               // decomposed run on the peer-memory path
     else if (!strcmp(name, "max_half")) *value = c->scal_host->max_half;            // longest reference-style half list, last build

@@ -442,3 +442,22 @@ def test_typed_sublist_follows_capacity_growth():
     assert cm.rel_force_err(s.get(capi.F_F), fref) <= FT
     assert abs(s.scalars().epot - rref.epot) <= FT * abs(rref.epot)
     s.close()
+
+
+def test_multi_cta_finalisation_of_the_force_sums():
+    """fin_multi: epot / virial / ecoul of a water step (five force routines, assign and accumulate flags) equal the
+    single-CTA finalisation to rounding, repeatedly (the ticket counter must re-arm)."""
+    res = []
+    for on in (0, 1):
+        s, x, types, z, mol, L = _water_system(2, {"fin_multi": on})
+        out = []
+        for rep in range(3):
+            f, sc = _water_forces(s, L, 2.9, 0.25)
+            out.append((sc.epot, sc.ecoul, np.array(sc.pot_P[:])))
+        res.append((f, out))
+        s.close()
+    assert np.array_equal(res[0][0], res[1][0])                      # forces do not pass through the finaliser
+    for (e0, c0, p0), (e1, c1, p1) in zip(res[0][1], res[1][1]):
+        assert abs(e1 - e0) <= 1e-12 * abs(e0) and abs(c1 - c0) <= 1e-12 * abs(c0)
+        assert np.abs(p1 - p0).max() <= 1e-12 * np.abs(p0).max()
+    assert res[1][1][0][0] == res[1][1][2][0]                        # same input, same sums, call after call
