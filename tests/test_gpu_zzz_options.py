@@ -215,8 +215,8 @@ def test_pair_tile_forces_match_oracle(typed, skin):
 
 
 def test_pair_tile_trajectory_follows_the_default_kernels():
-    """24 NVT steps (prg1-style loop through the C ABI) with and without pair_tile: same rebuild steps, energies equal
-    to rounding growth."""
+    """24 NVT steps (prg1-style loop through the C ABI) with the default kernels and with pair_tile, cell_order,
+    build_prune and fin_multi all on: same rebuild steps, energies equal to rounding growth."""
     x, L = _lj(12, seed=21, jitter=0.05)
     n = len(x)
     v = cm.velocities(n, 3.0, seed=22)
@@ -225,7 +225,8 @@ def test_pair_tile_trajectory_follows_the_default_kernels():
     for on in (0, 1):
         s = capi.System(n)
         s.put(capi.F_X, x); s.put(capi.F_V, v)
-        s.call("sepgpu_set_option", b"pair_tile", on)
+        for k in (b"pair_tile", b"cell_order", b"build_prune", b"fin_multi"):     # everything scripts/gpu_r2_ab.sh calls "lj_all"
+            s.call("sepgpu_set_option", k, on)
         sys_ = capi.make_sys([L] * 3, cf, dt, skin=skin)
         p = capi.lj_param(cf, kind="lj_shift")
         s.call("sepgpu_set_alpha", 0, 0.0)
