@@ -198,6 +198,8 @@ int sepgpu_set_option(sepgpu_ctx *ctx, const char *name, long long value);
  *   tpa, prefilter, overlap, force_grid, time_kernels, neighb_cap      tuning / measurement
  *   coulomb_kernel = 1 | 2     list Coulomb kernel: first version | charge-in-record, branch-free (default 1)
  *   typed_sublist  = 0 | 1     typed Lennard-Jones calls walk a per-type sub-list (default 0)
+ *   step_fold      = 0 | 1     the step's last force reduction and the Nose-Hoover multiplier update are folded into the
+ *                              integrator's kernels (3 launches per Lennard-Jones step instead of 5; single GPU; default 0)
  *   fin_multi      = 0 | 1     final reduction of the force partial rows on several CTAs with a last-block pass (default 0)
  *   build_prune    = 0 | 1     the tiled list builder skips candidate cells whose nearest point is beyond the cutoff (default 0)
  *   cell_order     = 0 | 1     slots inside a cell by atom index | along a Morton curve of 4^3 sub-cells (default 0)

@@ -235,7 +235,7 @@ extern "C" int sepgpu_set_topology(sepgpu_ctx *c, const unsigned *blist, unsigne
 {
     if (!c) return SEPGPU_EINVAL;
     if (nb >= (1u << 29) || na >= (1u << 29) || nd >= (1u << 29)) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     int rc;
     c->nb = nb; c->na = na; c->nd = nd;
@@ -261,7 +261,7 @@ extern "C" int sepgpu_set_topology(sepgpu_ctx *c, const unsigned *blist, unsigne
 extern "C" int sepgpu_get_bonded_values(sepgpu_ctx *c, double *blengths, double *angles, double *dihedrals)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (blengths && c->nb) CUDA_TRY(cudaMemcpy(blengths, c->blengths, sizeof(double) * c->nb, cudaMemcpyDeviceToHost));
     if (angles && c->na) CUDA_TRY(cudaMemcpy(angles, c->angles, sizeof(double) * c->na, cudaMemcpyDeviceToHost));
@@ -281,7 +281,7 @@ extern "C" int sepgpu_stretch_harmonic(sepgpu_ctx *c, const sepgpu_sys *sys, int
 {
     if (!c || !sys) return SEPGPU_EINVAL;
     if (!c->atom_bond_ptr) { sepgpu_set_error("stretch_harmonic: no topology on the device"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
     ktimer_begin(c, &c->t_bonded);
     k_bond<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->blist, c->atom_bond_ptr, c->atom_bond_idx,
@@ -296,7 +296,7 @@ static int run_angle(sepgpu_ctx *c, const sepgpu_sys *sys, int type, double angl
 {
     if (!c || !sys) return SEPGPU_EINVAL;
     if (!c->atom_angle_ptr) { sepgpu_set_error("angle force: no topology on the device"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
     const double cCon = cos(SEPGPU_PI - angle0);        // host libm, as the reference (source/sepmol.c:422)
     ktimer_begin(c, &c->t_bonded);
@@ -326,7 +326,7 @@ extern "C" int sepgpu_torsion_ryckaert(sepgpu_ctx *c, const sepgpu_sys *sys, int
 {
     if (!c || !sys || !g) return SEPGPU_EINVAL;
     if (!c->atom_dihed_ptr) { sepgpu_set_error("torsion force: no topology on the device"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
     RBCoef G; for (int k = 0; k < 6; k++) G.g[k] = g[k];
     ktimer_begin(c, &c->t_bonded);

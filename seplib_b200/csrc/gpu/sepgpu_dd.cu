@@ -228,7 +228,7 @@ extern "C" int sepgpu_dd_init(sepgpu_ctx *c, int rank, int nranks, const void *i
     if (c->dd) { sepgpu_set_error("dd_init: already decomposed"); return SEPGPU_ESTATE; }
     int rc = nccl_load();
     if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const int nzg = sys->nsubbox[2];
     if (nzg < 2 * nranks || nzg < 4) {
         sepgpu_set_error("dd_init: %d cell layers along z cannot be split over %d ranks", nzg, nranks);

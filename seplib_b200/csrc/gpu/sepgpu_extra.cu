@@ -37,7 +37,7 @@ extern "C" int sepgpu_scale_box(sepgpu_ctx *c, const double scale[3], const doub
 {
     if (!c || !scale || !new_length) return SEPGPU_EINVAL;
     if (c->dd) { sepgpu_set_error("scale_box: not available in decomposed runs"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const int write_xs = (c->list_valid && !c->sorted_identity) ? 1 : 0;
     k_scale_box<<<(c->n_own + XB - 1) / XB, XB, 0, c->stream>>>(c->x4, c->cr4, c->rank, c->xs, c->n_own, scale[0], scale[1], scale[2],
                                                                new_length[0], new_length[1], new_length[2], write_xs);
@@ -94,7 +94,7 @@ extern "C" int sepgpu_relax_temp(sepgpu_ctx *c, const sepgpu_sys *sys, char type
 {
     if (!c || !sys || tau == 0.0) return SEPGPU_EINVAL;
     if (c->dd) { sepgpu_set_error("relax_temp: not available in decomposed runs"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     long long want = ((long long)c->n_own + XB - 1) / XB;
     const int nrows = (int)(want < X_MAX_GRID ? want : X_MAX_GRID);
     const int t = (unsigned char)type;
@@ -143,7 +143,7 @@ extern "C" int sepgpu_force_x0(sepgpu_ctx *c, const sepgpu_sys *sys, char type, 
     if (!c || !sys) return SEPGPU_EINVAL;
     if (!c->x0) { sepgpu_set_error("force_x0: no tether positions on the device (put SEPGPU_F_X0 first)"); return SEPGPU_ESTATE; }
     if (c->dd) { sepgpu_set_error("force_x0: not available in decomposed runs"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     k_force_x0<<<(c->n_own + XB - 1) / XB, XB, 0, c->stream>>>(c->x4, c->x0, c->f4, c->n_own, (unsigned char)type, -kspring,
                                                               sys->length[0], sys->length[1], sys->length[2], c->f_zero ? 1 : 0);
     KERNEL_CHECK();

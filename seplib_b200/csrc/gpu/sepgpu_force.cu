@@ -655,9 +655,36 @@ k_finalize_force_multi(const double *__restrict__ partial, int nrows, double *__
     }
 }
 
+static int launch_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags);
+
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
 {
     if (c->ret_reset_pending) { flags |= 8; c->ret_reset_pending = false; }
+    if (c->step_fold && !c->dd) {
+        // option step_fold: leave the reduction to whoever comes next -- the integrator folds it into its own final
+        // kernel, every other entry point launches it first (SEPGPU_ENTER).  The rows stay in c->partial until then.
+        if (c->fin_pending.active) { int rc = launch_finalize_force(c, c->fin_pending.nrows, c->fin_pending.scale, c->fin_pending.flags); if (rc) return rc; }
+        c->fin_pending.active = true; c->fin_pending.nrows = nrows; c->fin_pending.scale = scale; c->fin_pending.flags = flags;
+        return 0;
+    }
+    return launch_finalize_force(c, nrows, scale, flags);
+}
+
+int sepgpu_nh_update_now(sepgpu_ctx *c);       // sepgpu_intgr.cu
+
+int sepgpu_settle(sepgpu_ctx *c)
+{
+    if (c->fin_pending.active) {
+        c->fin_pending.active = false;
+        int rc = launch_finalize_force(c, c->fin_pending.nrows, c->fin_pending.scale, c->fin_pending.flags);
+        if (rc) return rc;
+    }
+    if (c->nh_pending.active) return sepgpu_nh_update_now(c);
+    return 0;
+}
+
+static int launch_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
+{
     if (c->fin_multi) {
         if (!c->fin_ticket) {
             CUDA_TRY(cudaMalloc((void **)&c->fin_ticket, sizeof(unsigned)));
@@ -817,7 +844,7 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
                                const sepgpu_ljparam *p, unsigned opt, int epot_assign)
 {
     if (!c || !sys || !types || !p) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const LJDev P = make_lj(p, types);
     BoxDev B; B.Lx = sys->length[0]; B.Ly = sys->length[1]; B.Lz = sys->length[2];
     const bool store = c->f_zero;

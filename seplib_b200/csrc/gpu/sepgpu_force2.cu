@@ -349,7 +349,7 @@ static void launch_coulomb(sepgpu_ctx *c, int grid, bool store, double cf, const
 extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf, unsigned opt)
 {
     if (!c || !sys) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     BoxC B; B.Lx = sys->length[0]; B.Ly = sys->length[1]; B.Lz = sys->length[2];
     const bool store = c->f_zero;
     if (sys->neighb_update == 0) {
@@ -510,7 +510,7 @@ extern "C" int sepgpu_force_dpd(sepgpu_ctx *c, const sepgpu_sys *sys, const char
                                 unsigned long long seed, unsigned long long step)
 {
     if (!c || !sys || !types) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     int rc = sepgpu_ensure_dpd(c);
     if (rc) return rc;
     DpdParams P;

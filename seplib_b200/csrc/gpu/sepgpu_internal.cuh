@@ -173,6 +173,13 @@ struct sepgpu_ctx {
     int prefilter;               // FP32 prefilter in list build (1) or exact FP64 everywhere (0)
     int force_grid;              // CTAs of the list force kernel (0 = default)
     int tile_stage_cap;          // candidates the tiled list builder can stage per CTA (grows on demand)
+    // option step_fold: the final reduction of the last force routine of a step and the Nose-Hoover multiplier update are
+    // not launched on their own but folded into the integrator (k_integrate<.., NHFOLD> + k_finalize_both): 3 kernels per
+    // Lennard-Jones step instead of 5.  Anything else that enters the library first settles what is pending.
+    int step_fold;
+    struct { bool active; int nrows; double scale; int flags; } fin_pending;
+    struct { bool active; int slot; double temp0, tau; } nh_pending;
+    double nh_dt;
     int fin_multi;               // multi-CTA final reduction of the force partial rows (0 = off, default)
     unsigned *fin_ticket;        // its ticket counter
     int build_prune;             // tiled list builder skips candidate cells beyond the cutoff (0 = off, default)
@@ -211,6 +218,17 @@ void sepgpu_set_error(const char *fmt, ...);
         }                                                                                   \
     } while (0)
 #define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+// entry points: select the device and, with option step_fold, launch whatever an earlier call left pending
+int sepgpu_settle(sepgpu_ctx *c);
+int sepgpu_nh_update_now(sepgpu_ctx *c);
+#define SEPGPU_ENTER(c)                                                                     \
+    do {                                                                                    \
+        CUDA_TRY(cudaSetDevice((c)->device));                                               \
+        if ((c)->fin_pending.active || (c)->nh_pending.active) {                            \
+            int _rs = sepgpu_settle(c);                                                     \
+            if (_rs) return _rs;                                                            \
+        }                                                                                   \
+    } while (0)
 
 // ---- small device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ long long tag_bits(double w) { return __double_as_longlong(w); }

@@ -25,18 +25,30 @@ struct IntgrParams {
     int write_xs;       // maintain the cell-sorted copy
 };
 
-template <bool DPD>
+// sep_nosehoover's multiplier update (source/sepintgr.c:157-161) as one function with pinned rounding: with option
+// step_fold every thread of k_integrate<.., true> evaluates it on the same inputs and k_finalize_both stores the same value
+struct NhFold { double temp0, tau, npart; };
+__device__ __forceinline__ double nh_alpha_next(double alpha, double sum_mv2, const NhFold &N, double dt)
+{
+    const double ekin = __ddiv_rn(__dmul_rn(0.5, sum_mv2), N.npart);
+    const double temp = __dmul_rn(0.666667, ekin);
+    const double rate = __ddiv_rn(dt, __dmul_rn(N.tau, N.tau));
+    return __dadd_rn(alpha, __dmul_rn(rate, __dsub_rn(__ddiv_rn(temp, N.temp0), 1.0)));
+}
+
+template <bool DPD, bool NHFOLD>
 __global__ void __launch_bounds__(INTGR_BLOCK)
 k_integrate(d4 *__restrict__ x4, d4 *__restrict__ v4, d4 *__restrict__ f4, const d4 *__restrict__ xn4,
             i4 *__restrict__ cr4, int *__restrict__ crossings, const int *__restrict__ rank,
             d4 *__restrict__ xs, d4 *__restrict__ pv4, d4 *__restrict__ pa4, const DevScalars *__restrict__ scal,
-            IntgrParams P, double lambda, int stepnow, double *__restrict__ partial)
+            IntgrParams P, double lambda, int stepnow, double *__restrict__ partial, NhFold N)
 {
     __shared__ double red[SEPGPU_NPART_I * (INTGR_BLOCK / 32)];
     double acc[SEPGPU_NPART_I];
 #pragma unroll
     for (int q = 0; q < SEPGPU_NPART_I; q++) acc[q] = 0.0;
-    const double alpha = P.alpha_slot >= 0 ? scal->alpha[P.alpha_slot] : 0.0;
+    double alpha = P.alpha_slot >= 0 ? scal->alpha[P.alpha_slot] : 0.0;
+    if (NHFOLD) alpha = nh_alpha_next(alpha, scal->sum_mv2, N, P.dt);
     const double dt = P.dt;
 
     for (int i = blockIdx.x * INTGR_BLOCK + threadIdx.x; i < P.n; i += gridDim.x * INTGR_BLOCK) {
@@ -178,6 +190,71 @@ k_finalize_intgr(const double *__restrict__ partial, int nrows, DevScalars *scal
     }
 }
 
+// Option step_fold, single GPU: the step's last force reduction (k_finalize_force), the Nose-Hoover multiplier update
+// (k_nh_update) and the integrator's own reduction (k_finalize_intgr, mode 0) in ONE kernel, applied in that order.
+// fflags < 0: no force reduction pending; nh_slot < 0: no multiplier update pending.
+#define FIN_BOTH_THREADS 1024
+__global__ void __launch_bounds__(FIN_BOTH_THREADS)
+k_finalize_both(const double *__restrict__ fpartial, int fnrows, double fscale, int fflags,
+                const double *__restrict__ ipartial, int inrows, DevScalars *scal, double skin, int resets,
+                int nh_slot, NhFold N, double dt)
+{
+    __shared__ double red[SEPGPU_NPART_I * (FIN_BOTH_THREADS / 32)];
+    // ---- force rows (source/sepprfrc.c:222 and friends; see k_finalize_force) ----
+    double f[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) f[q] = 0.0;
+    if (fflags >= 0) {
+        for (int r = threadIdx.x; r < fnrows; r += FIN_BOTH_THREADS) {
+#pragma unroll
+            for (int q = 0; q < SEPGPU_NPART_F; q++) f[q] += fpartial[(size_t)r * SEPGPU_NPART_F + q];
+        }
+        block_sum<SEPGPU_NPART_F, FIN_BOTH_THREADS>(f, red);
+        __syncthreads();
+    }
+    // ---- integrator rows ----
+    double v[SEPGPU_NPART_I];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_I; q++) v[q] = 0.0;
+    double mx = 0.0;
+    for (int r = threadIdx.x; r < inrows; r += FIN_BOTH_THREADS) {
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_I; q++)
+            if (q != 7) v[q] += ipartial[r * SEPGPU_NPART_I + q];
+        mx = fmax(mx, ipartial[r * SEPGPU_NPART_I + 7]);
+    }
+    block_sum<SEPGPU_NPART_I, FIN_BOTH_THREADS>(v, red);
+    __syncthreads();
+    const double wm = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < FIN_BOTH_THREADS / 32; w++) mx = fmax(mx, red[w]);
+        if (fflags >= 0) {                                             // what k_finalize_force does
+            if (fflags & 8) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
+            const double e = f[0] * fscale, ec = f[1] * fscale;
+            if (fflags & 1) scal->epot = e; else scal->epot += e;
+            if (fflags & 4) { scal->epot += ec; scal->ecoul += ec; }
+            const double xx = f[2] * fscale, xy = f[3] * fscale, xz = f[4] * fscale;
+            const double yy = f[5] * fscale, yz = f[6] * fscale, zz = f[7] * fscale;
+            const double Pm[9] = {xx, xy, xz, xy, yy, yz, xz, yz, zz};
+            for (int k = 0; k < 9; k++) { scal->pot_P[k] += Pm[k]; if (fflags & 2) scal->pot_P_bond[k] += Pm[k]; }
+        }
+        if (nh_slot >= 0)                                              // what k_nh_update (mode 0) does, before sum_mv2 moves on
+            scal->alpha[nh_slot] = nh_alpha_next(scal->alpha[nh_slot], scal->sum_mv2, N, dt);
+        // what k_finalize_intgr (mode 0) does
+        if (resets & 1) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
+        if (resets & 2) scal->max_dist2 = 0.0;
+        scal->ekin += 0.5 * v[0];
+        const double K[9] = {v[1], v[2], v[3], v[2], v[4], v[5], v[3], v[5], v[6]};
+        for (int k = 0; k < 9; k++) scal->kin_P[k] += K[k];
+        if (mx > scal->max_dist2) scal->max_dist2 = mx;
+        scal->sum_mv2 = v[8];
+        scal->mom[0] = v[9]; scal->mom[1] = v[10]; scal->mom[2] = v[11];
+        scal->neighb_flag = sqrt(scal->max_dist2) > skin * 0.5 ? 1 : 0;
+    }
+}
+
 // Decomposed run with peer memory: ONE kernel reduces this rank's partial rows, stores the 12 sums into every
 // rank's gather table over NVLink (slot = seq & 1, row = my rank), raises the per-sender flag, waits for all
 // senders' flags and then adds the rows in rank order -- every rank computes bit-identical totals and so takes
@@ -296,17 +373,35 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     P.write_xs = (sys->neighb_update != 0 && c->list_valid) ? 1 : 0;
     long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
     const int grid = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
+    // option step_fold (single GPU, leapfrog): what the force routine and sep_nosehoover left pending is folded in here
+    NhFold N; N.temp0 = 1.0; N.tau = 1.0; N.npart = 1.0;
+    const bool fold = !dpd && !c->dd && (c->fin_pending.active || c->nh_pending.active);
+    if (!fold && (c->fin_pending.active || c->nh_pending.active)) { int rs = sepgpu_settle(c); if (rs) return rs; }
+    const bool fold_nh = fold && c->nh_pending.active && c->nh_pending.slot == c->pending_alpha_slot && c->pending_alpha_type < 0;
+    if (fold && c->nh_pending.active && !fold_nh) { int rs = sepgpu_nh_update_now(c); if (rs) return rs; }
+    if (fold_nh) { N.temp0 = c->nh_pending.temp0; N.tau = c->nh_pending.tau; N.npart = (double)c->n_global; }
+    // the integrator's partial rows must not land on force rows that are still waiting for their reduction
+    double *ipartial = fold ? c->partial + (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * SEPGPU_NPART_F + 1024 : c->partial;
     ktimer_begin(c, &c->t_intgr);
     if (dpd)
-        k_integrate<true><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
-            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial);
+        k_integrate<true, false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial, N);
+    else if (fold_nh)
+        k_integrate<false, true><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, ipartial, N);
     else
-        k_integrate<false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
-            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial);
+        k_integrate<false, false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, ipartial, N);
     const int resets = (c->ret_reset_pending ? 1 : 0) | (c->maxd_reset_pending ? 2 : 0);
     c->ret_reset_pending = false; c->maxd_reset_pending = false;
     GatherDev gd;
-    if (c->dd && sepgpu_dd_gather_next(c, &gd)) {
+    if (fold) {
+        const bool ff = c->fin_pending.active;
+        k_finalize_both<<<1, FIN_BOTH_THREADS, 0, c->stream>>>(c->partial, ff ? c->fin_pending.nrows : 0, ff ? c->fin_pending.scale : 0.0,
+            ff ? c->fin_pending.flags : -1, ipartial, grid, c->scal, sys->skin, resets, fold_nh ? c->nh_pending.slot : -1, N, sys->dt);
+        c->fin_pending.active = false;
+        c->nh_pending.active = false;
+    } else if (c->dd && sepgpu_dd_gather_next(c, &gd)) {
         k_finalize_intgr_p2p<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, resets, gd);
     } else if (c->dd) {
         double *comm = sepgpu_dd_comm(c);
@@ -417,7 +512,7 @@ k_integrate_stoch(d4 *__restrict__ x4, d4 *__restrict__ v4, const d4 *__restrict
 static int run_stochastic(sepgpu_ctx *c, const sepgpu_sys *sys, bool gjf, double temp, double alpha, const double *noise4)
 {
     if (c->dd) { sepgpu_set_error("stochastic integrators are not available in decomposed runs"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     int rc = sepgpu_apply_pending(c);
     if (rc) return rc;
     const size_t bytes = sizeof(d4) * (size_t)c->n_own;
@@ -527,6 +622,14 @@ k_nh_update(const double *__restrict__ partial, int nrows, DevScalars *scal, int
     }
 }
 
+__global__ void k_nh_update_fold(DevScalars *scal, int slot, double temp0, double tau, double dt, double npart)
+{
+    NhFold N; N.temp0 = temp0; N.tau = tau; N.npart = npart;
+    scal->alpha[slot] = nh_alpha_next(scal->alpha[slot], scal->sum_mv2, N, dt);
+}
+
+int sepgpu_nh_update_now(sepgpu_ctx *c);
+
 extern "C" int sepgpu_nosehoover(sepgpu_ctx *c, const sepgpu_sys *sys, double temp0, int slot, double tau)
 {
     if (!c || !sys || slot < 0 || slot > 3) return SEPGPU_EINVAL;
@@ -535,6 +638,7 @@ extern "C" int sepgpu_nosehoover(sepgpu_ctx *c, const sepgpu_sys *sys, double te
     if (rc) return rc;
     int nrows = 0;
     if (!c->mv2_valid) {
+        if (c->fin_pending.active && (rc = sepgpu_settle(c))) return rc;      // k_sum_mv2 writes into c->partial
         long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
         nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
         k_sum_mv2<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n_own, -1, c->partial);
@@ -546,10 +650,28 @@ extern "C" int sepgpu_nosehoover(sepgpu_ctx *c, const sepgpu_sys *sys, double te
             nrows = 0;
         }
     }
-    k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, slot, 0, temp0, tau, sys->dt, (double)c->n_global, 0, 0, 0);
-    KERNEL_CHECK();
+    if (c->step_fold && !c->dd && nrows == 0 && !c->nh_pending.active) {
+        // option step_fold: sum m v^2 of the last integrator call is current, so the update needs no pass of its own --
+        // the integrator evaluates it (k_integrate<.., true>) and k_finalize_both stores it
+        c->nh_pending.active = true; c->nh_pending.slot = slot; c->nh_pending.temp0 = temp0; c->nh_pending.tau = tau;
+        c->nh_dt = sys->dt;
+    } else {
+        if (c->nh_pending.active && (rc = sepgpu_nh_update_now(c))) return rc;
+        k_nh_update<<<1, 256, 0, c->stream>>>(c->partial, nrows, c->scal, slot, 0, temp0, tau, sys->dt, (double)c->n_global, 0, 0, 0);
+        KERNEL_CHECK();
+    }
     c->pending_alpha_slot = slot;
     c->pending_alpha_type = -1;
+    return 0;
+}
+
+// the pending multiplier update as a launch of its own (somebody needs alpha, or the force, before the integrator runs)
+int sepgpu_nh_update_now(sepgpu_ctx *c)
+{
+    if (!c->nh_pending.active) return 0;
+    c->nh_pending.active = false;
+    k_nh_update_fold<<<1, 1, 0, c->stream>>>(c->scal, c->nh_pending.slot, c->nh_pending.temp0, c->nh_pending.tau, c->nh_dt, (double)c->n_global);
+    KERNEL_CHECK();
     return 0;
 }
 
@@ -557,7 +679,7 @@ extern "C" int sepgpu_nosehoover_type(sepgpu_ctx *c, const sepgpu_sys *sys, char
                                       double alpha3[3], double Q)
 {
     if (!c || !sys || !alpha3) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     int rc = sepgpu_apply_pending(c);
     if (rc) return rc;
     long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
@@ -593,6 +715,7 @@ __global__ void k_apply_alpha(d4 *__restrict__ f4, const d4 *__restrict__ v4, co
 int sepgpu_apply_pending(sepgpu_ctx *c)
 {
     if (c->pending_alpha_slot < 0) return 0;
+    if (c->nh_pending.active) { int rs = sepgpu_nh_update_now(c); if (rs) return rs; }     // the multiplier about to be applied
     k_apply_alpha<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->f4, c->v4, c->x4, c->scal, c->pending_alpha_slot,
                                                             c->pending_alpha_type, c->n_own, c->f_zero ? 1 : 0);
     KERNEL_CHECK();
@@ -639,7 +762,7 @@ __global__ void k_sub_mom(d4 *__restrict__ v4, const d4 *__restrict__ x4, int n,
 extern "C" int sepgpu_reset_momentum(sepgpu_ctx *c, char type)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     long long want = ((long long)c->n_own + INTGR_BLOCK - 1) / INTGR_BLOCK;
     const int nrows = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
     k_sum_mom<<<nrows, INTGR_BLOCK, 0, c->stream>>>(c->v4, c->x4, c->n_own, (unsigned char)type, c->partial);
@@ -661,7 +784,7 @@ __global__ void k_scale_x(d4 *__restrict__ x4, d4 *__restrict__ xs, int n, doubl
 extern "C" int sepgpu_scale_positions(sepgpu_ctx *c, double xi)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     k_scale_x<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xs, c->n_own, xi, c->list_valid ? 1 : 0);
     KERNEL_CHECK();
     return 0;

@@ -357,7 +357,7 @@ static int estimate_cap(const sepgpu_ctx *c, const sepgpu_sys *sys)
 extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigned opt)
 {
     if (!c || !sys) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const int nx = sys->nsubbox[0], ny = sys->nsubbox[1], nz = sys->nsubbox[2];
     if (nx < 1 || ny < 1 || nz < 1) { sepgpu_set_error("neighb_build: empty cell grid"); return SEPGPU_EINVAL; }
     if (opt < SEPGPU_ALL || opt > SEPGPU_EXCL_SAME_MOL) { sepgpu_set_error("neighb_build: bad opt %u", opt); return SEPGPU_EINVAL; }

@@ -377,7 +377,7 @@ extern "C" int sepgpu_put_fields(sepgpu_ctx *c, const void *base, size_t stride,
                                  const int *fields, const size_t *offsets)
 {
     if (!c || !base || nfields <= 0 || nfields > SEPGPU_MAX_FIELDS || !fields) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const size_t n = (size_t)c->n_own;
     size_t row[SEPGPU_MAX_FIELDS], off[SEPGPU_MAX_FIELDS], hoff[SEPGPU_MAX_FIELDS], total = 0;
     for (int f = 0; f < nfields; f++) {
@@ -467,7 +467,7 @@ extern "C" int sepgpu_get_fields(sepgpu_ctx *c, void *base, size_t stride, int n
                                  const int *fields, const size_t *offsets)
 {
     if (!c || !base || nfields <= 0 || nfields > SEPGPU_MAX_FIELDS || !fields) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const size_t n = (size_t)c->n_own;
     size_t row[SEPGPU_MAX_FIELDS], off[SEPGPU_MAX_FIELDS], hoff[SEPGPU_MAX_FIELDS], total = 0;
     for (int f = 0; f < nfields; f++) {
@@ -510,7 +510,7 @@ extern "C" int sepgpu_fij_enable(sepgpu_ctx *c, int nmol)
 {
     if (!c || nmol <= 0) return SEPGPU_EINVAL;
     if (c->dd) { sepgpu_set_error("fij_enable: not available in decomposed runs"); return SEPGPU_ESTATE; }
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     if (c->fij && c->nmol == nmol) return 0;
     if (c->fij) { cudaFree(c->fij); c->fij = NULL; }
     CUDA_TRY(cudaMalloc((void **)&c->fij, sizeof(double) * 3 * (size_t)nmol * nmol));
@@ -522,7 +522,7 @@ extern "C" int sepgpu_fij_enable(sepgpu_ctx *c, int nmol)
 extern "C" int sepgpu_fij_reset(sepgpu_ctx *c)
 {
     if (!c || !c->fij) return SEPGPU_ESTATE;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     CUDA_TRY(cudaMemsetAsync(c->fij, 0, sizeof(double) * 3 * (size_t)c->nmol * c->nmol, c->stream));
     return 0;
 }
@@ -537,7 +537,7 @@ __global__ void k_fij_to_float(const double *__restrict__ in, float *__restrict_
 extern "C" int sepgpu_fij_get(sepgpu_ctx *c, float *out)
 {
     if (!c || !out || !c->fij) return SEPGPU_ESTATE;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     const size_t cnt = 3 * (size_t)c->nmol * c->nmol;
     int rc = sepgpu_ensure_stage(c, cnt * sizeof(float));
     if (rc) return rc;
@@ -572,7 +572,7 @@ __global__ void k_reset_maxdist(DevScalars *s) { s->max_dist2 = 0.0; }
 extern "C" int sepgpu_reset_force(sepgpu_ctx *c)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     // f <- 0 is not written out: the first force kernel after this call stores instead of adding.
     c->f_zero = true;
     c->pending_alpha_slot = -1;       // a pending f -= alpha m v dies with the force it would modify
@@ -591,7 +591,7 @@ int sepgpu_flush_resets(sepgpu_ctx *c)
 extern "C" int sepgpu_read_scalars(sepgpu_ctx *c, sepgpu_scalars *out)
 {
     if (!c || !out) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     { int rcf = sepgpu_flush_resets(c); if (rcf) return rcf; }
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -619,7 +619,7 @@ extern "C" int sepgpu_read_scalars(sepgpu_ctx *c, sepgpu_scalars *out)
 extern "C" int sepgpu_sync(sepgpu_ctx *c)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -629,7 +629,7 @@ __global__ void k_set_alpha(DevScalars *s, int slot, double a) { s->alpha[slot] 
 extern "C" int sepgpu_set_alpha(sepgpu_ctx *c, int slot, double alpha)
 {
     if (!c || slot < 0 || slot > 3) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     k_set_alpha<<<1, 1, 0, c->stream>>>(c->scal, slot, alpha);
     KERNEL_CHECK();
     return 0;
@@ -640,7 +640,7 @@ __global__ void k_set_flag(DevScalars *s) { s->neighb_flag = 1; }
 extern "C" int sepgpu_request_rebuild(sepgpu_ctx *c)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     c->list_valid = false;
     k_set_flag<<<1, 1, 0, c->stream>>>(c->scal);
     KERNEL_CHECK();
@@ -698,6 +698,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
         if (name[0] == 'p') c->pt_ctas = (int)value; else c->coul2_ctas = (int)value;
         return 0;
     }
+    if (!strcmp(name, "step_fold")) { if (!value) { int rs = sepgpu_settle(c); if (rs) return rs; } c->step_fold = value != 0; return 0; }
     if (!strcmp(name, "fin_multi")) { c->fin_multi = value != 0; return 0; }
     if (!strcmp(name, "build_prune")) { c->build_prune = value != 0; return 0; }
     if (!strcmp(name, "cell_order")) { if (value != 0 && value != 1) return SEPGPU_EINVAL; c->cell_order = (int)value; c->list_valid = false; return 0; }
@@ -737,6 +738,7 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "cell_order")) *value = c->cell_order;
     else if (!strcmp(name, "build_prune")) *value = c->build_prune;
     else if (!strcmp(name, "fin_multi")) *value = c->fin_multi;
+    else if (!strcmp(name, "step_fold")) *value = c->step_fold;
     else if (!strcmp(name, "list_pair")) *value = c->list_valid && c->list_pair ? 1 : 0;
     else if (!strcmp(name, "dd_p2p")) *value = sepgpu_dd_uses_p2p(c);               // decomposed run on the peer-memory path
     else if (!strcmp(name, "max_half")) *value = c->scal_host->max_half;            // longest reference-style half list, last build
@@ -753,7 +755,7 @@ extern "C" int sepgpu_kernel_time(sepgpu_ctx *c, const char *which, float *ms_to
                    : !strcmp(which, "bonded") ? &c->t_bonded : !strcmp(which, "halo") ? &c->t_halo
                    : !strcmp(which, "migrate") ? &c->t_migr : NULL;
     if (!t || !t->enabled) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     ktimer_drain(t);
     if (ms_total) *ms_total = t->total_ms;
     if (launches) *launches = t->launches;
@@ -764,7 +766,7 @@ extern "C" int sepgpu_kernel_time(sepgpu_ctx *c, const char *which, float *ms_to
 extern "C" int sepgpu_timer_start(sepgpu_ctx *c)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
     return 0;
 }
@@ -772,7 +774,7 @@ extern "C" int sepgpu_timer_start(sepgpu_ctx *c)
 extern "C" int sepgpu_timer_stop(sepgpu_ctx *c, float *ms)
 {
     if (!c || !ms) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev1));
     CUDA_TRY(cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -789,7 +791,7 @@ __global__ void k_flush(double *p, size_t n)
 extern "C" int sepgpu_flush_l2(sepgpu_ctx *c)
 {
     if (!c) return SEPGPU_EINVAL;
-    CUDA_TRY(cudaSetDevice(c->device));
+    SEPGPU_ENTER(c);
     if (!c->flush_buf) {
         c->flush_bytes = (size_t)256 << 20;           // 256 MiB > 126 MB L2
         CUDA_TRY(cudaMalloc(&c->flush_buf, c->flush_bytes));

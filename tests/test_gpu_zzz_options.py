@@ -462,3 +462,119 @@ def test_multi_cta_finalisation_of_the_force_sums():
         assert abs(e1 - e0) <= 1e-12 * abs(e0) and abs(c1 - c0) <= 1e-12 * abs(c0)
         assert np.abs(p1 - p0).max() <= 1e-12 * np.abs(p0).max()
     assert res[1][1][0][0] == res[1][1][2][0]                        # same input, same sums, call after call
+
+
+# ---- step_fold: last force reduction + Nose-Hoover update folded into the integrator's kernels -------------------
+def _nvt_loop(opts, nsteps, peek):
+    """prg1-style loop through the C ABI; peek: read the scalar block / the forces between the force call and the
+    integrator on some steps (which must settle whatever is pending)"""
+    x, L = _lj(12, seed=31, jitter=0.05)
+    n = len(x)
+    v = cm.velocities(n, 2.5, seed=32)
+    rng = np.random.default_rng(4)
+    types = np.where(rng.random(n) < 0.5, ord("B"), ord("A")).astype(np.uint8)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_V, v); s.put(capi.F_TYPE, types)
+    for k, val in opts.items():
+        s.call("sepgpu_set_option", k.encode(), val)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
+    s.call("sepgpu_set_alpha", 0, 0.05)
+    rec = []
+    for step in range(nsteps):
+        s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+        for tsel, rc_, kind in ((b"AA", 2.5, "lj_shift"), (b"AB", 2.0, "lj"), (b"BB", 2 ** (1 / 6), "wca")):
+            p = capi.lj_param(rc_, kind=kind)
+            s.call("sepgpu_force_lj", C.byref(sys_), tsel, C.byref(p), cm.ALL, 1)
+        mid = None
+        if peek and step % 3 == 1:
+            mid = (s.scalars().epot, None)                      # scalars before the thermostat
+        s.call("sepgpu_nosehoover", C.byref(sys_), 2.5, 0, 0.05)
+        if peek and step % 3 == 2:
+            sc = s.scalars()
+            mid = (sc.epot, sc.alpha[0], s.get(capi.F_F).copy())   # multiplier and thermostatted forces before the integrator
+        s.call("sepgpu_leapfrog", C.byref(sys_))
+        sc = s.scalars()
+        rec.append((sc.epot, sc.ekin, sc.alpha[0], np.array(sc.pot_P[:]), np.array(sc.kin_P[:]), sc.max_dist2, sc.neighb_flag, sc.nbuild, mid))
+    xf, vf, ff = s.get(capi.F_X), s.get(capi.F_V), s.get(capi.F_F)
+    s.close()
+    return rec, xf, vf, ff
+
+
+@pytest.mark.parametrize("peek", [False, True])
+def test_step_fold_equals_the_unfolded_step(peek):
+    """20 NVT steps with three typed force calls per step: every scalar, the multiplier, the rebuild steps and the final
+    state equal the default sequence of kernels to rounding; reading scalars or forces between the calls settles what is
+    pending and sees the same values."""
+    a = _nvt_loop({}, 20, peek)
+    b = _nvt_loop({"step_fold": 1, "fin_multi": 1 if peek else 0}, 20, peek)
+    assert a[0][-1][7] >= 3
+    for k, (ra, rb) in enumerate(zip(a[0], b[0])):
+        tol = 1e-11 * (k + 1)
+        assert ra[6] == rb[6] and ra[7] == rb[7], k
+        assert abs(ra[0] - rb[0]) <= tol * abs(ra[0]) and abs(ra[1] - rb[1]) <= tol * abs(ra[1]), k
+        assert abs(ra[2] - rb[2]) <= tol * max(abs(ra[2]), 1e-3), k
+        assert np.abs(ra[3] - rb[3]).max() <= tol * np.abs(ra[3]).max() and np.abs(ra[4] - rb[4]).max() <= tol * np.abs(ra[4]).max()
+        assert abs(ra[5] - rb[5]) <= tol * ra[5]
+        if ra[8] is not None:
+            assert abs(ra[8][0] - rb[8][0]) <= tol * abs(ra[8][0])
+            if ra[8][1] is not None:
+                assert abs(ra[8][1] - rb[8][1]) <= tol * max(abs(ra[8][1]), 1e-3)
+                assert cm.rel_force_err(rb[8][2], ra[8][2]) <= 1e-10
+    assert np.abs(a[1] - b[1]).max() <= 1e-9 and np.abs(a[2] - b[2]).max() <= 1e-9
+    assert cm.rel_force_err(b[3], a[3]) <= 1e-9
+
+
+def test_step_fold_water_step_and_option_switch_off():
+    """prg3-style step (typed LJ, bond, angle, Coulomb, thermostat, leapfrog) with step_fold; switching the option off
+    settles what is pending."""
+    res = []
+    for on in (0, 1):
+        s, x, types, z, mol, L = _water_system(2, {"step_fold": on})
+        sys_ = capi.make_sys(L, 2.9, 5e-4, skin=0.25)
+        rng = np.random.default_rng(2)
+        s.put(capi.F_V, rng.normal(0.0, 1.0, size=x.shape))
+        s.call("sepgpu_set_alpha", 0, 0.0)
+        out = []
+        for step in range(4):
+            s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+            p = capi.lj_param(2.5, kind="lj_shift")
+            s.call("sepgpu_force_lj", C.byref(sys_), b"OO", C.byref(p), cm.EXCL_SAME_MOL, 1)
+            s.call("sepgpu_coulomb_sf", C.byref(sys_), 2.9, cm.EXCL_SAME_MOL)
+            s.call("sepgpu_nosehoover", C.byref(sys_), 3.8, 0, 0.01)
+            if step == 3 and on:
+                s.call("sepgpu_set_option", b"step_fold", 0)        # settles the pending reduction and multiplier update
+            s.call("sepgpu_leapfrog", C.byref(sys_))
+            sc = s.scalars()
+            out.append((sc.epot, sc.ecoul, sc.ekin, sc.alpha[0]))
+        res.append(out)
+        s.close()
+    for k, (ra, rb) in enumerate(zip(*res)):
+        for va, vb in zip(ra, rb):
+            assert abs(va - vb) <= 1e-11 * (k + 1) * max(abs(va), 1e-3), (k, ra, rb)
+
+
+def test_step_fold_launches_three_kernels_per_lennard_jones_step():
+    """Counted by the CPU kernel emulator (the symbol does not exist in libsep.so): 5 launches per steady-state step by
+    default -- force, its reduction, multiplier update, integrator, its reduction -- and 3 with step_fold."""
+    lib = capi.load()
+    if not hasattr(lib, "sepgpu_emu_launches"):
+        pytest.skip("launch counter of the CPU kernel emulator")
+    lib.sepgpu_emu_launches.restype = C.c_longlong
+    x, L = _lj(12, seed=3, jitter=0.05)
+    v = cm.velocities(len(x), 1.0, seed=4)
+    per_step = {}
+    for on in (0, 1):
+        s = capi.System(len(x)); s.put(capi.F_X, x); s.put(capi.F_V, v)
+        s.call("sepgpu_set_option", b"step_fold", on)
+        sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
+        p = capi.lj_param(2.5, kind="lj_shift")
+        s.call("sepgpu_set_alpha", 0, 0.1)
+        for step in range(5):
+            n0 = lib.sepgpu_emu_launches()
+            s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+            s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
+            s.call("sepgpu_nosehoover", C.byref(sys_), 1.0, 0, 0.1)
+            s.call("sepgpu_leapfrog", C.byref(sys_))
+            per_step[on] = lib.sepgpu_emu_launches() - n0
+        s.close()
+    assert per_step == {0: 5, 1: 3}, per_step
