@@ -25,6 +25,15 @@ def _newest(paths):
 
 
 def build(force=False, verbose=False):
+    """build (if stale) under a file lock: test processes that start side by side must not compile into the same files"""
+    import fcntl
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build(force, verbose)
+
+
+def _build(force, verbose):
     srcs = [os.path.join(d, f) for d in (GPU_SRC, HOST_SRC, HERE, os.path.join(ROOT, "include")) for f in os.listdir(d)
             if f.endswith((".cu", ".cuh", ".c", ".h", ".cpp", ".py"))]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest(srcs):

@@ -16,6 +16,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RUNNER = os.path.join(ROOT, "tests", "emu", "run_on_emu.py")
+WORKERS = str(max(1, min(4, (os.cpu_count() or 2) // 2)))       # the emulator is one busy thread per test process
 
 # the long trajectories and the linked example programs (thousands of steps) are left to the hardware run
 FAST = ("not prg and not md_trajectory and not lj_loop and not molecular_pressure and not fij_list "
@@ -36,26 +37,30 @@ def _run(args, timeout=1500, env=None):
 def test_gpu_parity_tests_pass_on_the_emulated_kernels():
     # tests/test_golden.py: the reference's own recorded butane / water / DPD vectors against the emulated kernels
     n = _run(["tests/test_gpu_lj.py", "tests/test_gpu_more.py", "tests/test_gpu_zz_next.py", "tests/test_golden.py", "-m", "gpu",
-              "-q", "-x", "-k", FAST, "-p", "no:cacheprovider"])
+              "-q", "-n", WORKERS, "-k", FAST, "-p", "no:cacheprovider"])
     assert n >= 24, n
 
 
 def test_optin_kernels_pass_on_the_emulator():
     """coulomb_kernel=2, typed_sublist=1, pair_tile=1, cell_order=1 (tests/test_gpu_zzz_options.py): skipped on hardware until a GPU run has
     confirmed them, exercised here on every CPU round."""
-    n = _run(["tests/test_gpu_zzz_options.py", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"],
+    n = _run(["tests/test_gpu_zzz_options.py", "-m", "gpu", "-q", "-n", WORKERS, "-p", "no:cacheprovider"],
              env={"SEPGPU_TEST_UNVERIFIED": "1"})
     assert n >= 31, n
 
 
-@pytest.mark.parametrize("opts,no_ipc", [("", "0"), ("pair_tile=1,cell_order=1", "0"), ("", "1")],
-                         ids=["peer-memory", "peer-memory+pair_tile", "nccl-path"])
-def test_two_rank_decomposition_on_the_emulator(opts, no_ipc):
+def test_two_rank_decomposition_on_the_emulator():
     """Slab decomposition with two ranks as two THREADS on the emulated kernels (tests/emu/dd_threads.py): union of the
     ranks' pair sets == single-domain set, per-step sums, trigger steps, final positions, atom conservation over several
     rebuilds with migration -- the checks tests/dd_check.py makes on two GPUs.  Both transport paths: peer memory (the
     emulator hands out in-process IPC handles; the two ranks' kernels run concurrently and meet at release/acquire
-    flags) and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp)."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "14", opts],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc))
-    assert r.returncode == 0 and "-> OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    flags), also with pair-tile lists, and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp).  The three runs go side
+    by side."""
+    cases = {"peer-memory": ("", "0"), "peer-memory+pair_tile": ("pair_tile=1,cell_order=1", "0"), "nccl-path": ("", "1")}
+    procs = {k: subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "14", opts],
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
+                                 env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc))
+             for k, (opts, no_ipc) in cases.items()}
+    for k, p in procs.items():
+        out, err = p.communicate(timeout=900)
+        assert p.returncode == 0 and "-> OK" in out, (k, out[-2000:], err[-2000:])

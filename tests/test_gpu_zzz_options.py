@@ -502,12 +502,12 @@ def _nvt_loop(opts, nsteps, peek):
 
 @pytest.mark.parametrize("peek", [False, True])
 def test_step_fold_equals_the_unfolded_step(peek):
-    """20 NVT steps with three typed force calls per step: every scalar, the multiplier, the rebuild steps and the final
+    """12 NVT steps with three typed force calls per step: every scalar, the multiplier, the rebuild steps and the final
     state equal the default sequence of kernels to rounding; reading scalars or forces between the calls settles what is
     pending and sees the same values."""
-    a = _nvt_loop({}, 20, peek)
-    b = _nvt_loop({"step_fold": 1, "fin_multi": 1 if peek else 0}, 20, peek)
-    assert a[0][-1][7] >= 3
+    a = _nvt_loop({}, 12, peek)
+    b = _nvt_loop({"step_fold": 1, "fin_multi": 1 if peek else 0}, 12, peek)
+    assert a[0][-1][7] >= 2
     for k, (ra, rb) in enumerate(zip(a[0], b[0])):
         tol = 1e-11 * (k + 1)
         assert ra[6] == rb[6] and ra[7] == rb[7], k
