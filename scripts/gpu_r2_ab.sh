@@ -53,4 +53,4 @@ run water_all         water "coulomb_kernel=2,typed_sublist=1,build_prune=1" $S
 run water_all_ctas4   water "coulomb_kernel=2,typed_sublist=1,build_prune=1,coul2_ctas=4" $S
 run water_all_ctas6   water "coulomb_kernel=2,typed_sublist=1,build_prune=1,coul2_ctas=6" $S
 echo "== whole default suite with every option on (SEPGPU_OPTS reaches every context the tests create)" | tee -a gpurun_out/r2_ab.txt
-SEPGPU_OPTS="step_fold=1,fin_multi=1,build_prune=1,cell_order=1,pair_tile=1,coulomb_kernel=2,typed_sublist=1" timeout 900 python -m pytest tests -m gpu -q -k "not dd" 2>&1 | tail -6 | tee -a gpurun_out/r2_ab.txt
+SEPGPU_OPTS="step_fold=1,fin_multi=1,build_prune=1,cell_order=1,pair_tile=1,coulomb_kernel=2,typed_sublist=1" timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee -a gpurun_out/r2_ab.txt

@@ -660,7 +660,7 @@ static int launch_finalize_force(sepgpu_ctx *c, int nrows, double scale, int fla
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
 {
     if (c->ret_reset_pending) { flags |= 8; c->ret_reset_pending = false; }
-    if (c->step_fold && !c->dd) {
+    if (c->step_fold && (!c->dd || sepgpu_dd_uses_p2p(c))) {
         // option step_fold: leave the reduction to whoever comes next -- the integrator folds it into its own final
         // kernel, every other entry point launches it first (SEPGPU_ENTER).  The rows stay in c->partial until then.
         if (c->fin_pending.active) { int rc = launch_finalize_force(c, c->fin_pending.nrows, c->fin_pending.scale, c->fin_pending.flags); if (rc) return rc; }
@@ -670,7 +670,6 @@ int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags)
     return launch_finalize_force(c, nrows, scale, flags);
 }
 
-int sepgpu_nh_update_now(sepgpu_ctx *c);       // sepgpu_intgr.cu
 
 int sepgpu_settle(sepgpu_ctx *c)
 {

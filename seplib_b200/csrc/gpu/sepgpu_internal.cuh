@@ -221,6 +221,7 @@ void sepgpu_set_error(const char *fmt, ...);
 // entry points: select the device and, with option step_fold, launch whatever an earlier call left pending
 int sepgpu_settle(sepgpu_ctx *c);
 int sepgpu_nh_update_now(sepgpu_ctx *c);
+int sepgpu_dd_uses_p2p(sepgpu_ctx *c);             // sepgpu_dd.cu: decomposed run on the peer-memory path
 #define SEPGPU_ENTER(c)                                                                     \
     do {                                                                                    \
         CUDA_TRY(cudaSetDevice((c)->device));                                               \

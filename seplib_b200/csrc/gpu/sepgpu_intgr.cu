@@ -260,11 +260,41 @@ k_finalize_both(const double *__restrict__ fpartial, int fnrows, double fscale, 
 // senders' flags and then adds the rows in rank order -- every rank computes bit-identical totals and so takes
 // the same rebuild decision.  Replaces finalize(phase A) + NCCL all-reduce + finalize(phase B).
 // Slot reuse is safe: nobody can be two refreshes ahead of a rank whose contribution it still needs.
+// FOLD (option step_fold): the step's last force reduction and the Nose-Hoover multiplier update ride along, applied in
+// the order the separate kernels would (force sums, multiplier, then the integrator's sums).
+struct FoldArgs { const double *fpartial; int fnrows; double fscale; int fflags; int nh_slot; NhFold N; double dt; };
+
+template <bool FOLD>
 __global__ void __launch_bounds__(256)
-k_finalize_intgr_p2p(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int resets, GatherDev G)
+k_finalize_intgr_p2p(const double *__restrict__ partial, int nrows, DevScalars *scal, double skin, int resets, GatherDev G, FoldArgs F)
 {
     __shared__ double red[SEPGPU_NPART_I * 8];
     __shared__ double mine[SEPGPU_NPART_I];
+    if (FOLD) {
+        if (F.fflags >= 0) {
+            double f[SEPGPU_NPART_F];
+#pragma unroll
+            for (int q = 0; q < SEPGPU_NPART_F; q++) f[q] = 0.0;
+            for (int r = threadIdx.x; r < F.fnrows; r += 256) {
+#pragma unroll
+                for (int q = 0; q < SEPGPU_NPART_F; q++) f[q] += F.fpartial[(size_t)r * SEPGPU_NPART_F + q];
+            }
+            block_sum<SEPGPU_NPART_F, 256>(f, red);
+            if (threadIdx.x == 0) {
+                if (F.fflags & 8) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
+                const double e = f[0] * F.fscale, ec = f[1] * F.fscale;
+                if (F.fflags & 1) scal->epot = e; else scal->epot += e;
+                if (F.fflags & 4) { scal->epot += ec; scal->ecoul += ec; }
+                const double xx = f[2] * F.fscale, xy = f[3] * F.fscale, xz = f[4] * F.fscale;
+                const double yy = f[5] * F.fscale, yz = f[6] * F.fscale, zz = f[7] * F.fscale;
+                const double Pm[9] = {xx, xy, xz, xy, yy, yz, xz, yz, zz};
+                for (int k = 0; k < 9; k++) { scal->pot_P[k] += Pm[k]; if (F.fflags & 2) scal->pot_P_bond[k] += Pm[k]; }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0 && F.nh_slot >= 0)            // sum_mv2 is still the previous step's global value here
+            scal->alpha[F.nh_slot] = nh_alpha_next(scal->alpha[F.nh_slot], scal->sum_mv2, F.N, F.dt);
+    }
     if (threadIdx.x == 0) {
         if (resets & 1) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
         if (resets & 2) scal->max_dist2 = 0.0;
@@ -349,6 +379,7 @@ void sepgpu_dd_positions_moved(sepgpu_ctx *c);
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax);
 void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks);
 bool sepgpu_dd_gather_next(sepgpu_ctx *c, GatherDev *g);
+int sepgpu_dd_uses_p2p(sepgpu_ctx *c);
 
 __global__ void k_partial2_to_comm(const double *__restrict__ partial, int nrows, double *comm)
 {
@@ -375,7 +406,8 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     const int grid = (int)(want < INTGR_MAX_GRID ? want : INTGR_MAX_GRID);
     // option step_fold (single GPU, leapfrog): what the force routine and sep_nosehoover left pending is folded in here
     NhFold N; N.temp0 = 1.0; N.tau = 1.0; N.npart = 1.0;
-    const bool fold = !dpd && !c->dd && (c->fin_pending.active || c->nh_pending.active);
+    // decomposed runs fold into the peer-memory finaliser only (the NCCL path keeps its three kernels)
+    const bool fold = !dpd && (!c->dd || sepgpu_dd_uses_p2p(c)) && (c->fin_pending.active || c->nh_pending.active);
     if (!fold && (c->fin_pending.active || c->nh_pending.active)) { int rs = sepgpu_settle(c); if (rs) return rs; }
     const bool fold_nh = fold && c->nh_pending.active && c->nh_pending.slot == c->pending_alpha_slot && c->pending_alpha_type < 0;
     if (fold && c->nh_pending.active && !fold_nh) { int rs = sepgpu_nh_update_now(c); if (rs) return rs; }
@@ -395,14 +427,24 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     const int resets = (c->ret_reset_pending ? 1 : 0) | (c->maxd_reset_pending ? 2 : 0);
     c->ret_reset_pending = false; c->maxd_reset_pending = false;
     GatherDev gd;
-    if (fold) {
+    if (fold && c->dd) {
+        if (!sepgpu_dd_gather_next(c, &gd)) { sepgpu_set_error("step_fold: the peer-memory path went away"); return SEPGPU_ESTATE; }
+        const bool ff = c->fin_pending.active;
+        FoldArgs F;
+        F.fpartial = c->partial; F.fnrows = ff ? c->fin_pending.nrows : 0; F.fscale = ff ? c->fin_pending.scale : 0.0;
+        F.fflags = ff ? c->fin_pending.flags : -1; F.nh_slot = fold_nh ? c->nh_pending.slot : -1; F.N = N; F.dt = sys->dt;
+        k_finalize_intgr_p2p<true><<<1, 256, 0, c->stream>>>(ipartial, grid, c->scal, sys->skin, resets, gd, F);
+        c->fin_pending.active = false;
+        c->nh_pending.active = false;
+    } else if (fold) {
         const bool ff = c->fin_pending.active;
         k_finalize_both<<<1, FIN_BOTH_THREADS, 0, c->stream>>>(c->partial, ff ? c->fin_pending.nrows : 0, ff ? c->fin_pending.scale : 0.0,
             ff ? c->fin_pending.flags : -1, ipartial, grid, c->scal, sys->skin, resets, fold_nh ? c->nh_pending.slot : -1, N, sys->dt);
         c->fin_pending.active = false;
         c->nh_pending.active = false;
     } else if (c->dd && sepgpu_dd_gather_next(c, &gd)) {
-        k_finalize_intgr_p2p<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, resets, gd);
+        FoldArgs F0; F0.fpartial = NULL; F0.fnrows = 0; F0.fscale = 0.0; F0.fflags = -1; F0.nh_slot = -1; F0.N = N; F0.dt = 0.0;
+        k_finalize_intgr_p2p<false><<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, resets, gd, F0);
     } else if (c->dd) {
         double *comm = sepgpu_dd_comm(c);
         int drank = 0, dn = 1;
@@ -650,7 +692,7 @@ extern "C" int sepgpu_nosehoover(sepgpu_ctx *c, const sepgpu_sys *sys, double te
             nrows = 0;
         }
     }
-    if (c->step_fold && !c->dd && nrows == 0 && !c->nh_pending.active) {
+    if (c->step_fold && (!c->dd || sepgpu_dd_uses_p2p(c)) && nrows == 0 && !c->nh_pending.active) {
         // option step_fold: sum m v^2 of the last integrator call is current, so the update needs no pass of its own --
         // the integrator evaluates it (k_integrate<.., true>) and k_finalize_both stores it
         c->nh_pending.active = true; c->nh_pending.slot = slot; c->nh_pending.temp0 = temp0; c->nh_pending.tau = tau;

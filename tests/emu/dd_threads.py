@@ -64,20 +64,20 @@ def main():
             for step in range(nsteps):
                 s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
                 s.call("sepgpu_force_lj", C.byref(gsys), b"AA", C.byref(p), 1, 1)
-                sc = s.scalars()                               # collective
+                pr = None
+                if step in check_steps:                        # mid-step reads only here: the other steps run unobserved
+                    sc = s.scalars()                           # (collective) -- what option step_fold leaves pending stays pending
+                    pr = cm.pair_set(s.pairs(max_pairs=int(sc.npairs_listed) + 16))
                 if step == 0:
                     lp = C.c_longlong(-1)
                     s.call("sepgpu_get_option", b"list_pair", C.byref(lp))
                     shared["list_pair"] = lp.value
                     s.call("sepgpu_get_option", b"dd_p2p", C.byref(lp))
                     shared["p2p"] = lp.value
-                pr = None
-                if step in check_steps:
-                    pr = cm.pair_set(s.pairs(max_pairs=int(sc.npairs_listed) + 16))
                 s.call("sepgpu_nosehoover", C.byref(gsys), temp, 0, tau)
                 s.call("sepgpu_leapfrog", C.byref(gsys))
-                sc2 = s.scalars()
-                rec.append((sc.epot, sc2.ekin, sc2.alpha[0], sc2.max_dist2, sc.pot_P[0], sc2.neighb_flag, sc.nbuild, pr))
+                sc2 = s.scalars()                              # epot and the virial of this step's force call are still in the block
+                rec.append((sc2.epot, sc2.ekin, sc2.alpha[0], sc2.max_dist2, sc2.pot_P[0], sc2.neighb_flag, sc2.nbuild, pr))
             _, _, n_own, n_halo = s.dd_layers()
             shared["final"][rank] = (s.get(capi.F_X)[:n_own].copy(), s.get(capi.F_GID)[:n_own].copy(), n_own, n_halo)
             shared["rec"][rank] = rec

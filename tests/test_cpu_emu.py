@@ -54,9 +54,10 @@ def test_two_rank_decomposition_on_the_emulator():
     ranks' pair sets == single-domain set, per-step sums, trigger steps, final positions, atom conservation over several
     rebuilds with migration -- the checks tests/dd_check.py makes on two GPUs.  Both transport paths: peer memory (the
     emulator hands out in-process IPC handles; the two ranks' kernels run concurrently and meet at release/acquire
-    flags), also with pair-tile lists, and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp).  The three runs go side
+    flags), also with pair-tile lists and the folded step, and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp).  The three runs go side
     by side."""
-    cases = {"peer-memory": ("", "0"), "peer-memory+pair_tile": ("pair_tile=1,cell_order=1", "0"), "nccl-path": ("", "1")}
+    cases = {"peer-memory": ("", "0"), "peer-memory+options": ("step_fold=1,pair_tile=1,cell_order=1,fin_multi=1", "0"),
+             "nccl-path": ("step_fold=1", "1")}
     procs = {k: subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "14", opts],
                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
                                  env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc))
