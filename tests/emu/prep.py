@@ -149,7 +149,6 @@ def main(src_dir, out_dir):
         total += nl
         out = name[:-3] + ".cpp" if name.endswith(".cu") else name
         with open(os.path.join(out_dir, out), "w") as fh:
-            fh.write(f'#line 1 "{os.path.join(src_dir, name)}"\n' if False else "")
             fh.write(text)
     return total
 
