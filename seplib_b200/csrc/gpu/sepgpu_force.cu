@@ -322,7 +322,7 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
 // ---- Lennard-Jones, pair-tile list (option pair_tile) ------------------------------------------------------------------
 // k_lj_list is bound by the L1 data pipe: every listed neighbour is a 32-byte gather from a line no other lane shares
 // (~22 wavefronts per warp-wide gather where 8 would do).  Here one THREAD owns the two sorted atoms (2t, 2t+1) and walks
-// the union of their neighbour rows (built by k_build_tile2<SEP_ALL, true>): one gather serves two atoms, and the two
+// the union of their neighbour rows (built by k_build_tile2<.., PAIR = true>): one gather serves two atoms, and the two
 // dependent FP64 chains of a step belong to the two atoms.  Entries carry membership flags, so each atom still sums
 // exactly its own list; a pair split over two list-build tiles walks its two single rows one after the other.
 struct PairAcc2 {
@@ -373,7 +373,7 @@ __device__ __forceinline__ void lj_tile_step(const d4 &pa, const d4 &pb, const d
     }
 }
 
-// MINB: CTAs per SM the register budget is cut for (option pt_ctas: 4 = 128 registers, 5 = 96 and a few spilled bytes,
+// MINB: CTAs per SM the register budget is cut for (option pt_ctas: 4 = 117 registers, 5 = 96 and a few spilled bytes,
 // 6 = 80) -- the occupancy / spill trade is to be settled on hardware
 template <bool TYPED, bool STORE, int MINB>
 __global__ void __launch_bounds__(FORCE_BLOCK, MINB)
