@@ -38,7 +38,8 @@ run lj_all_grid2368   lj "pair_tile=1,cell_order=1,build_prune=1,force_grid=2368
 run lj_default_g2368  lj "force_grid=2368" $S
 run lj_finmulti       lj "fin_multi=1" $S
 run lj_stepfold       lj "step_fold=1" $S
-run lj_everything     lj "pair_tile=1,cell_order=1,build_prune=1,step_fold=1" $S
+run lj_stepfold_multi lj "step_fold=1,fin_multi=1" $S
+run lj_everything     lj "pair_tile=1,cell_order=1,build_prune=1,step_fold=1,fin_multi=1" $S
 echo "== C2: butane 864k atoms" | tee -a gpurun_out/r2_ab.txt
 S="--steps 300 --warmup 50"
 run butane_default    butane "" $S

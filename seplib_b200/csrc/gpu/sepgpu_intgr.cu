@@ -255,6 +255,101 @@ k_finalize_both(const double *__restrict__ fpartial, int fnrows, double fscale, 
     }
 }
 
+// k_finalize_both on several CTAs (options step_fold + fin_multi): CTA b sums fixed chunks of the force rows and of the
+// integrator rows into stage row b (8 + 12 doubles), the CTA that draws the last ticket adds the stage rows in index
+// order and applies them exactly as k_finalize_both does.  Fixed chunks, fixed final order: deterministic.
+#define FBM_THREADS 256
+#define FBM_MAX_CTAS 64
+#define FBM_W (SEPGPU_NPART_F + SEPGPU_NPART_I)
+__global__ void __launch_bounds__(FBM_THREADS)
+k_finalize_both_multi(const double *__restrict__ fpartial, int fnrows, double fscale, int fflags,
+                      const double *__restrict__ ipartial, int inrows, double *__restrict__ stage, unsigned *ticket,
+                      DevScalars *scal, double skin, int resets, int nh_slot, NhFold N, double dt)
+{
+    __shared__ double red[SEPGPU_NPART_I * (FBM_THREADS / 32)];
+    __shared__ double tot[FBM_W];
+    __shared__ int s_last;
+    const int G = gridDim.x;
+    double f[SEPGPU_NPART_F];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_F; q++) f[q] = 0.0;
+    if (fflags >= 0) {
+        const int chunk = (fnrows + G - 1) / G, r0 = blockIdx.x * chunk, r1 = min(fnrows, r0 + chunk);
+        for (int r = r0 + (int)threadIdx.x; r < r1; r += FBM_THREADS) {
+#pragma unroll
+            for (int q = 0; q < SEPGPU_NPART_F; q++) f[q] += fpartial[(size_t)r * SEPGPU_NPART_F + q];
+        }
+        block_sum<SEPGPU_NPART_F, FBM_THREADS>(f, red);
+        __syncthreads();
+    }
+    double v[SEPGPU_NPART_I];
+#pragma unroll
+    for (int q = 0; q < SEPGPU_NPART_I; q++) v[q] = 0.0;
+    double mx = 0.0;
+    {
+        const int chunk = (inrows + G - 1) / G, r0 = blockIdx.x * chunk, r1 = min(inrows, r0 + chunk);
+        for (int r = r0 + (int)threadIdx.x; r < r1; r += FBM_THREADS) {
+#pragma unroll
+            for (int q = 0; q < SEPGPU_NPART_I; q++)
+                if (q != 7) v[q] += ipartial[r * SEPGPU_NPART_I + q];
+            mx = fmax(mx, ipartial[r * SEPGPU_NPART_I + 7]);
+        }
+    }
+    block_sum<SEPGPU_NPART_I, FBM_THREADS>(v, red);
+    __syncthreads();
+    const double wm = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < FBM_THREADS / 32; w++) mx = fmax(mx, red[w]);
+        v[7] = mx;
+        double *row = stage + (size_t)blockIdx.x * FBM_W;
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_F; q++) row[q] = f[q];
+#pragma unroll
+        for (int q = 0; q < SEPGPU_NPART_I; q++) row[SEPGPU_NPART_F + q] = v[q];
+        __threadfence();                                            // stage row visible before the ticket is drawn
+        s_last = atomicAdd(ticket, 1u) == (unsigned)G - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < FBM_W) {
+        const int q = threadIdx.x;
+        double a = 0.0;
+        for (int b = 0; b < G; b++) {
+            const double x = __ldcg(stage + (size_t)b * FBM_W + q);
+            if (q == SEPGPU_NPART_F + 7) a = fmax(a, x); else a += x;
+        }
+        tot[q] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+        const double *F = tot, *V = tot + SEPGPU_NPART_F;
+        if (fflags >= 0) {
+            if (fflags & 8) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
+            const double e = F[0] * fscale, ec = F[1] * fscale;
+            if (fflags & 1) scal->epot = e; else scal->epot += e;
+            if (fflags & 4) { scal->epot += ec; scal->ecoul += ec; }
+            const double xx = F[2] * fscale, xy = F[3] * fscale, xz = F[4] * fscale;
+            const double yy = F[5] * fscale, yz = F[6] * fscale, zz = F[7] * fscale;
+            const double Pm[9] = {xx, xy, xz, xy, yy, yz, xz, yz, zz};
+            for (int k = 0; k < 9; k++) { scal->pot_P[k] += Pm[k]; if (fflags & 2) scal->pot_P_bond[k] += Pm[k]; }
+        }
+        if (nh_slot >= 0) scal->alpha[nh_slot] = nh_alpha_next(scal->alpha[nh_slot], scal->sum_mv2, N, dt);
+        if (resets & 1) { scal->epot = 0; scal->ecoul = 0; scal->ekin = 0; for (int k = 0; k < 9; k++) { scal->pot_P[k] = 0; scal->kin_P[k] = 0; scal->pot_P_bond[k] = 0; } }
+        if (resets & 2) scal->max_dist2 = 0.0;
+        scal->ekin += 0.5 * V[0];
+        const double K[9] = {V[1], V[2], V[3], V[2], V[4], V[5], V[3], V[5], V[6]};
+        for (int k = 0; k < 9; k++) scal->kin_P[k] += K[k];
+        if (V[7] > scal->max_dist2) scal->max_dist2 = V[7];
+        scal->sum_mv2 = V[8];
+        scal->mom[0] = V[9]; scal->mom[1] = V[10]; scal->mom[2] = V[11];
+        scal->neighb_flag = sqrt(scal->max_dist2) > skin * 0.5 ? 1 : 0;
+    }
+}
+
 // Decomposed run with peer memory: ONE kernel reduces this rank's partial rows, stores the 12 sums into every
 // rank's gather table over NVLink (slot = seq & 1, row = my rank), raises the per-sender flag, waits for all
 // senders' flags and then adds the rows in rank order -- every rank computes bit-identical totals and so takes
@@ -413,7 +508,7 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     if (fold && c->nh_pending.active && !fold_nh) { int rs = sepgpu_nh_update_now(c); if (rs) return rs; }
     if (fold_nh) { N.temp0 = c->nh_pending.temp0; N.tau = c->nh_pending.tau; N.npart = (double)c->n_global; }
     // the integrator's partial rows must not land on force rows that are still waiting for their reduction
-    double *ipartial = fold ? c->partial + (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * SEPGPU_NPART_F + 1024 : c->partial;
+    double *ipartial = fold ? c->partial + (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * SEPGPU_NPART_F + 2048 : c->partial;
     ktimer_begin(c, &c->t_intgr);
     if (dpd)
         k_integrate<true, false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
@@ -438,6 +533,20 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
         c->nh_pending.active = false;
     } else if (fold) {
         const bool ff = c->fin_pending.active;
+        if (c->fin_multi) {
+            if (!c->fin_ticket) {
+                CUDA_TRY(cudaMalloc((void **)&c->fin_ticket, sizeof(unsigned)));
+                CUDA_TRY(cudaMemsetAsync(c->fin_ticket, 0, sizeof(unsigned), c->stream));
+            }
+            const int most = ff && c->fin_pending.nrows > grid ? c->fin_pending.nrows : grid;
+            int per = (most + FBM_MAX_CTAS - 1) / FBM_MAX_CTAS;
+            if (per < 8) per = 8;
+            const int ctas = (most + per - 1) / per;
+            double *stage = c->partial + (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * SEPGPU_NPART_F;      // 64 x 20 doubles, below ipartial
+            k_finalize_both_multi<<<ctas, FBM_THREADS, 0, c->stream>>>(c->partial, ff ? c->fin_pending.nrows : 0, ff ? c->fin_pending.scale : 0.0,
+                ff ? c->fin_pending.flags : -1, ipartial, grid, stage, c->fin_ticket, c->scal, sys->skin, resets,
+                fold_nh ? c->nh_pending.slot : -1, N, sys->dt);
+        } else
         k_finalize_both<<<1, FIN_BOTH_THREADS, 0, c->stream>>>(c->partial, ff ? c->fin_pending.nrows : 0, ff ? c->fin_pending.scale : 0.0,
             ff ? c->fin_pending.flags : -1, ipartial, grid, c->scal, sys->skin, resets, fold_nh ? c->nh_pending.slot : -1, N, sys->dt);
         c->fin_pending.active = false;
