@@ -65,3 +65,15 @@ def test_two_rank_decomposition_on_the_emulator():
     for k, p in procs.items():
         out, err = p.communicate(timeout=900)
         assert p.returncode == 0 and "-> OK" in out, (k, out[-2000:], err[-2000:])
+
+
+def test_smoke_entry_point_on_the_emulator():
+    """__graft_entry__.smoke() -- the one-step check the driver runs on cuda:0 -- against the emulated kernels."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import build_emu\n"
+            "from seplib_b200 import capi\n"
+            "capi.LIB_PATH = build_emu.build()\n"
+            "import __graft_entry__ as g\n"
+            "g.smoke()\n") % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
