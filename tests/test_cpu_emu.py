@@ -77,3 +77,19 @@ def test_smoke_entry_point_on_the_emulator():
             "g.smoke()\n") % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_work_model_numbers_quoted_in_the_design_document():
+    """tests/emu/model_check.py: the emulator's gather model reproduces the ~20 distinct lines per warp-wide gather that ncu
+    measured for k_lj_list on B200 (profiles/r01_k_lj_list_ncu_full.txt), and gives the work reductions DESIGN.md section 3a
+    quotes for the pair-tile list and the pruned list build."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "model_check.py")], capture_output=True, text=True,
+                       timeout=900, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    m = json.loads(r.stdout.strip().splitlines()[-1])
+    assert 18.0 <= m["per_atom"]["lines_per_request"] <= 24.0
+    assert m["pair_tile"]["wavefronts_per_atom"] <= 0.85 * m["per_atom"]["wavefronts_per_atom"]
+    assert m["pair_tile"]["lane_loads_per_atom"] <= 0.75 * m["per_atom"]["lane_loads_per_atom"]
+    assert m["pruned"]["candidates_per_atom"] <= 0.85 * m["per_atom"]["candidates_per_atom"]
+    assert m["pruned"]["wavefronts_per_atom"] == m["per_atom"]["wavefronts_per_atom"]        # same list, same gathers
