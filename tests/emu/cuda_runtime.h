@@ -70,9 +70,9 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
 void *dyn_smem();
 const char *self_path();         // file name of the emulated library (dladdr), for the NCCL stand-in
 void sync_block();
-// every lane named in mask deposits 8 bytes and receives all 32 deposits (slots of lanes that did not take part hold
-// the caller's own value)
-void warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32]);
+// every lane named in mask deposits 8 bytes; returns the warp's 32 deposit slots and, in *part, which lanes took part in
+// this exchange (slots of other lanes are stale)
+const uint64_t *warp_exchange(unsigned mask, uint64_t mine, unsigned *part);
 int lane_id();
 // gather statistics (SEPGPU_EMU_GATHER_STATS=1): kernels mark their scattered loads with SEPGPU_EMU_GATHER(ptr); the k-th
 // marked load of every lane of a warp is taken as one warp-wide request, and the distinct 128-byte lines it touches are
@@ -84,7 +84,7 @@ static inline double rsqrt_approx(double x) { return (double)(1.0f / sqrtf((floa
 }  // namespace emu
 
 static inline void __syncthreads() { emu::sync_block(); }
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { uint64_t t[32]; emu::warp_exchange(mask, 0, t); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { unsigned part; emu::warp_exchange(mask, 0, &part); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __threadfence_system() {}
@@ -99,52 +99,52 @@ static inline long long clock64()
 template <class T> static inline uint64_t emu_pack(T v) { uint64_t u = 0; static_assert(sizeof(T) <= 8, "8-byte shuffles only"); memcpy(&u, &v, sizeof(T)); return u; }
 template <class T> static inline T emu_unpack(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
 
+// a source lane that did not take part (exited, or not named in the mask) yields the caller's own value
+template <class T> static inline T emu_pick(const uint64_t *slots, unsigned part, int src, T own)
+{
+    return (src >= 0 && src < 32 && (part >> src & 1u)) ? emu_unpack<T>(slots[src]) : own;
+}
 template <class T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
 {
-    uint64_t all[32];
-    emu::warp_exchange(mask, emu_pack(v), all);
+    unsigned part;
+    const uint64_t *slots = emu::warp_exchange(mask, emu_pack(v), &part);
     const int lane = emu::lane_id();
-    const int base = lane & ~(width - 1);
-    return emu_unpack<T>(all[base + (src & (width - 1))]);
+    return emu_pick(slots, part, (lane & ~(width - 1)) + (src & (width - 1)), v);
 }
 template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32)
 {
-    uint64_t all[32];
-    emu::warp_exchange(mask, emu_pack(v), all);
+    unsigned part;
+    const uint64_t *slots = emu::warp_exchange(mask, emu_pack(v), &part);
     const int lane = emu::lane_id();
     const int src = lane ^ lanemask;
     if ((src & ~(width - 1)) != (lane & ~(width - 1))) return v;
-    return emu_unpack<T>(all[src]);
+    return emu_pick(slots, part, src, v);
 }
 template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
 {
-    uint64_t all[32];
-    emu::warp_exchange(mask, emu_pack(v), all);
+    unsigned part;
+    const uint64_t *slots = emu::warp_exchange(mask, emu_pack(v), &part);
     const int lane = emu::lane_id();
     const int src = lane - (int)delta;
     if (src < (lane & ~(width - 1))) return v;
-    return emu_unpack<T>(all[src]);
+    return emu_pick(slots, part, src, v);
 }
 template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
 {
-    uint64_t all[32];
-    emu::warp_exchange(mask, emu_pack(v), all);
+    unsigned part;
+    const uint64_t *slots = emu::warp_exchange(mask, emu_pack(v), &part);
     const int lane = emu::lane_id();
     const int src = lane + (int)delta;
     if (src > (lane | (width - 1))) return v;
-    return emu_unpack<T>(all[src]);
+    return emu_pick(slots, part, src, v);
 }
-// ballots: lanes that did not take part deposit nothing -> their slot holds the caller's own value, so each lane marks
-// its deposit with a tag bit and only tagged slots of other lanes count
 static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
-    uint64_t all[32];
-    const int lane = emu::lane_id();
-    const uint64_t mine = ((uint64_t)(pred ? 1 : 0)) | ((uint64_t)(lane + 1) << 8);
-    emu::warp_exchange(mask, mine, all);
+    unsigned part;
+    const uint64_t *slots = emu::warp_exchange(mask, pred ? 1 : 0, &part);
     unsigned r = 0;
     for (int l = 0; l < 32; l++)
-        if ((mask >> l & 1u) && (all[l] >> 8) == (uint64_t)(l + 1) && (all[l] & 1u)) r |= 1u << l;
+        if ((part >> l & 1u) && (mask >> l & 1u) && slots[l]) r |= 1u << l;
     return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }

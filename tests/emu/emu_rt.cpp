@@ -23,14 +23,50 @@
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
 
+// Context switch.  x86-64: a dozen instructions (callee-saved registers pushed on the outgoing stack, stack pointers
+// exchanged) -- swapcontext() makes two signal-mask system calls per switch, and a 1024-thread reduction kernel switches
+// ~50 000 times.  Elsewhere: ucontext.
+#if defined(__x86_64__) && !defined(EMU_UCONTEXT)
+#define EMU_FAST_SWITCH 1
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+    .text
+    .globl emu_switch
+    .type emu_switch, @function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size emu_switch, .-emu_switch
+)");
+#else
+#define EMU_FAST_SWITCH 0
+#endif
+
 namespace {
 enum { READY = 0, AT_BARRIER = 1, AT_WARP = 2, DONE = 3 };
 struct Fiber {
+#if EMU_FAST_SWITCH
+    void *sp;             // saved stack pointer (callee-saved registers sit on the fiber's own stack)
+#else
     ucontext_t ctx;
+#endif
     int state;
     unsigned wmask;
     uint64_t deposit;
-    uint64_t snap[32];
+    unsigned part;        // lanes that took part in the exchange this fiber was just released from
     uint3 tid;
     int lin;
     int gseq;             // marked gathers issued so far (gather statistics)
@@ -39,11 +75,17 @@ const size_t STACK_BYTES = 256 * 1024;
 const int MAX_THREADS = 1024;
 thread_local char *g_stacks = nullptr;
 thread_local std::vector<Fiber> g_fibers;
+#if EMU_FAST_SWITCH
+thread_local void *g_sched_sp = nullptr;
+#else
 thread_local ucontext_t g_sched;
+#endif
 thread_local Fiber *g_cur = nullptr;
 thread_local const std::function<void()> *g_body = nullptr;
 thread_local const char *g_kernel = "?";
 thread_local std::vector<unsigned char> g_dyn;
+thread_local uint64_t g_wslots[32][32];          // per warp: the deposits of the last released exchange
+thread_local int g_at_warp[32];                   // per warp: fibers waiting at a warp primitive
 long long g_launches = 0;
 // gather statistics of the block being run: (warp << 32 | sequence number, 128-byte line)
 thread_local std::vector<std::pair<unsigned long long, unsigned long long>> g_gathers;
@@ -64,6 +106,36 @@ void flush_gathers()
     g_gathers.clear();
 }
 
+#if EMU_FAST_SWITCH
+void fiber_main()
+{
+    (*g_body)();
+    g_cur->state = DONE;
+    emu_switch(&g_cur->sp, g_sched_sp);          // never resumed
+    __builtin_trap();
+}
+
+void yield_to_scheduler()
+{
+    Fiber *me = g_cur;
+    emu_switch(&me->sp, g_sched_sp);
+    // resumed: the scheduler has restored threadIdx and g_cur
+}
+
+void fiber_init(Fiber &f, char *stack, size_t bytes)
+{
+    // a fresh stack that emu_switch can "return" into: six zeroed callee-saved registers, then fiber_main as the return
+    // address; after that ret the stack pointer is 8 mod 16, as at any function entry
+    uintptr_t top = ((uintptr_t)stack + bytes) & ~(uintptr_t)15;
+    void **sp = (void **)top;
+    *--sp = nullptr;                             // where fiber_main would return to (it never does)
+    *--sp = (void *)fiber_main;
+    for (int k = 0; k < 6; k++) *--sp = nullptr;
+    f.sp = sp;
+}
+
+inline void resume(Fiber &f) { emu_switch(&g_sched_sp, f.sp); }
+#else
 void fiber_main()
 {
     (*g_body)();
@@ -78,9 +150,22 @@ void yield_to_scheduler()
     // resumed: the scheduler has restored threadIdx and g_cur
 }
 
+void fiber_init(Fiber &f, char *stack, size_t bytes)
+{
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = stack;
+    f.ctx.uc_stack.ss_size = bytes;
+    f.ctx.uc_link = &g_sched;
+    makecontext(&f.ctx, fiber_main, 0);
+}
+
+inline void resume(Fiber &f) { swapcontext(&g_sched, &f.ctx); }
+#endif
+
 void run_block(int nthreads)
 {
     int alive = nthreads;
+    for (int w = 0; w < 32; w++) g_at_warp[w] = 0;
     for (;;) {
         bool ran = false;
         for (int t = 0; t < nthreads; t++) {
@@ -88,7 +173,7 @@ void run_block(int nthreads)
             if (f.state != READY) continue;
             threadIdx = f.tid;
             g_cur = &f;
-            swapcontext(&g_sched, &f.ctx);
+            resume(f);
             ran = true;
             if (f.state == DONE) alive--;
         }
@@ -102,28 +187,38 @@ void run_block(int nthreads)
                 if (g_fibers[t].state == AT_BARRIER) g_fibers[t].state = READY;
             released = true;
         }
-        // warp exchanges
-        for (int w0 = 0; w0 < nthreads; w0 += 32) {
+        // warp exchanges: a group (lanes waiting with the same mask) is released when every live lane it names has arrived
+        for (int w0 = 0, w = 0; w0 < nthreads; w0 += 32, w++) {
+            if (g_at_warp[w] == 0) continue;
             const int wn = nthreads - w0 < 32 ? nthreads - w0 : 32;
-            unsigned live = 0;
-            for (int l = 0; l < wn; l++)
-                if (g_fibers[w0 + l].state != DONE) live |= 1u << l;
+            unsigned live = 0, waiting = 0;
             for (int l = 0; l < wn; l++) {
-                Fiber &f = g_fibers[w0 + l];
-                if (f.state != AT_WARP) continue;
-                const unsigned need = f.wmask & live;
-                bool ok = true;
-                for (int m = 0; m < wn && ok; m++)
-                    if (need >> m & 1u) ok = g_fibers[w0 + m].state == AT_WARP && g_fibers[w0 + m].wmask == f.wmask;
-                if (!ok) continue;
-                for (int m = 0; m < wn; m++) {
-                    if (!(need >> m & 1u)) continue;
-                    Fiber &g = g_fibers[w0 + m];
-                    for (int q = 0; q < 32; q++)
-                        g.snap[q] = (q < wn && (need >> q & 1u)) ? g_fibers[w0 + q].deposit : g.deposit;
+                const int st = g_fibers[w0 + l].state;
+                if (st != DONE) live |= 1u << l;
+                if (st == AT_WARP) waiting |= 1u << l;
+            }
+            unsigned todo = waiting;
+            while (todo) {
+                const int l = __builtin_ctz(todo);
+                const unsigned m = g_fibers[w0 + l].wmask;
+                const unsigned need = m & live & (wn == 32 ? 0xffffffffu : ((1u << wn) - 1u));
+                unsigned same = 0;                                   // waiting lanes with this very mask
+                for (unsigned t = waiting; t; t &= t - 1) {
+                    const int q = __builtin_ctz(t);
+                    if (g_fibers[w0 + q].wmask == m) same |= 1u << q;
                 }
-                for (int m = 0; m < wn; m++)
-                    if (need >> m & 1u) g_fibers[w0 + m].state = READY;
+                todo &= ~same;
+                if ((need & same) != need) continue;                 // somebody named in the mask is still on the way
+                for (unsigned t = need; t; t &= t - 1) {
+                    const int q = __builtin_ctz(t);
+                    g_wslots[w][q] = g_fibers[w0 + q].deposit;
+                }
+                for (unsigned t = need; t; t &= t - 1) {
+                    Fiber &g = g_fibers[w0 + __builtin_ctz(t)];
+                    g.part = need;
+                    g.state = READY;
+                }
+                g_at_warp[w] -= __builtin_popcount(need);
                 released = true;
             }
         }
@@ -167,14 +262,16 @@ void sync_block()
     yield_to_scheduler();
 }
 
-void warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32])
+const uint64_t *warp_exchange(unsigned mask, uint64_t mine, unsigned *part)
 {
     Fiber *me = g_cur;
     me->state = AT_WARP;
     me->wmask = mask;
     me->deposit = mine;
+    g_at_warp[me->lin >> 5]++;
     yield_to_scheduler();
-    for (int q = 0; q < 32; q++) out[q] = me->snap[q];
+    *part = me->part;
+    return g_wslots[me->lin >> 5];
 }
 
 void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
@@ -207,11 +304,7 @@ void launch(const char *name, dim3 grid, dim3 block, size_t smem, const std::fun
                     for (unsigned ty = 0; ty < block.y; ty++)
                         for (unsigned tx = 0; tx < block.x; tx++, t++) {
                             Fiber &f = g_fibers[t];
-                            getcontext(&f.ctx);
-                            f.ctx.uc_stack.ss_sp = g_stacks + (size_t)t * STACK_BYTES;
-                            f.ctx.uc_stack.ss_size = STACK_BYTES;
-                            f.ctx.uc_link = &g_sched;
-                            makecontext(&f.ctx, fiber_main, 0);
+                            fiber_init(f, g_stacks + (size_t)t * STACK_BYTES, STACK_BYTES);
                             f.state = READY;
                             f.tid.x = tx; f.tid.y = ty; f.tid.z = tz;
                             f.lin = t;
