@@ -1,11 +1,15 @@
-"""Opt-in kernels (sepgpu_set_option / SEPGPU_OPTS): the second list Coulomb kernel (coulomb_kernel=2) and typed
-sub-lists (typed_sublist=1).  Same parity bar as the default kernels they stand in for: forces 1e-10 of the oracle,
-sums 1e-10, and -- because they walk the same pairs -- agreement with the default kernels to rounding.
+"""Opt-in kernels (sepgpu_set_option / SEPGPU_OPTS):
+  coulomb_kernel=2   second list Coulomb kernel          typed_sublist=1   per-type sub-lists for typed Lennard-Jones calls
+  pair_tile=1        list rows per pair of sorted atoms + k_lj_pairtile     cell_order=1   Morton slot order inside a cell
+  build_prune=1      list builder skips unreachable candidate cells         fin_multi=1    multi-CTA final reductions
+  step_fold=1        force reduction + Nose-Hoover update folded into the integrator's kernels
+Same parity bar as the default kernels they stand in for: forces 1e-10 of the oracle / the reference's golden vectors,
+pair sets bit-exact, sums 1e-10, and agreement with the default kernels to rounding over runs with many rebuilds.
 
 Status: written without access to hardware.  Their logic is verified on the CPU kernel emulator
-(tests/test_cpu_emu.py runs this file with SEPGPU_TEST_UNVERIFIED=1); on a GPU box they are skipped until a hardware
-run has confirmed them -- set SEPGPU_TEST_UNVERIFIED=1 to run them there.  The options default to off, so nothing the
-default suite or bench.py measures goes through these kernels.
+(tests/test_cpu_emu.py runs this file with SEPGPU_TEST_UNVERIFIED=1, also under UBSan); on a GPU box they are skipped
+until a hardware run has confirmed them -- set SEPGPU_TEST_UNVERIFIED=1 to run them there (scripts/gpu_r2_ab.sh does).
+The options default to off, so nothing the default suite or bench.py measures goes through these kernels.
 """
 import ctypes as C
 import os
