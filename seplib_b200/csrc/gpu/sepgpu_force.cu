@@ -869,8 +869,12 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     }
     // the type test is compiled out when every atom carries the one requested type
     const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
+    if (c->list_pair && c->fij) {
+        // the molecule-pair table was switched on after a pair-tile list had been built: per-atom rows from now on
+        c->need_atom_rows = true;
+        if ((rc = sepgpu_neighb_build(c, sys, c->list_opt))) return rc;
+    }
     if (c->list_pair) {                                  // option pair_tile: rows per pair of sorted atoms
-        if (c->fij) { sepgpu_set_error("force_lj: pair-tile lists do not fill the Fij table"); return SEPGPU_ESTATE; }
         if (c->dd && (rc = sepgpu_dd_halo_update(c, sys))) return rc;     // neighbours' boundary atoms moved too
         const int npairs = (c->n + 1) / 2;
         int grid = c->force_grid > 0 ? c->force_grid : FORCE_MAX_GRID;
