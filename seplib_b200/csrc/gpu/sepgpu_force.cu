@@ -15,6 +15,7 @@
 // The periodic image of a pair is fixed at list-build time and stored in the top bits of the list
 // entry, which removes the 9 FP64 compare/adjust operations of sep_Wrap from the inner loop.
 #include "sepgpu_internal.cuh"
+#include "sepgpu_pair.cuh"
 
 #include <math.h>
 
@@ -23,76 +24,6 @@
 #ifndef LJ_MIN_CTAS
 #define LJ_MIN_CTAS 7          // 72 registers per thread; forcing 8 CTAs (64 registers) spills and measured 11 % slower
 #endif
-
-struct LJDev {
-    double cf2, sig2, eps48, eps4, aw, awh, shift;
-    int t0, t1;
-};
-
-struct BoxDev { double Lx, Ly, Lz; };
-
-// 1/x to ~1 ulp: MUFU.RCP64H seed (relative error <= 2^-23) + two Newton steps (4 DFMA) instead of the
-// IEEE division sequence; inputs are r^2 of in-range pairs, far from denormals/inf.
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
-}
-
-// Same seed, ONE third-order step: y1 = y0 (1 + e + e^2), e = 1 - x y0.  The error goes 2^-23 -> 2^-69,
-// below double rounding, in 3 DFMA instead of 4.
-__device__ __forceinline__ double fast_rcp3(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, 1.0);
-    const double e2 = fma(e, e, e);
-    return fma(y, e2, y);
-}
-
-__device__ __forceinline__ double fast_rsqrt(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    // Newton: y <- y + y*(0.5 - 0.5*x*y*y)
-#pragma unroll
-    for (int it = 0; it < 2; it++) {
-        double h = 0.5 * y;
-        double e = fma(-x * y, h, 0.5);
-        y = fma(y, e, y);
-    }
-    // one more correction step for full double accuracy
-    double h = 0.5 * y;
-    double e = fma(-x * y, h, 0.5);
-    y = fma(y, e, y);
-    return y;
-}
-
-__device__ __forceinline__ void apply_image(int code, const BoxDev &B, double &dx, double &dy, double &dz)
-{
-    // code = (sx+1) + 3(sy+1) + 9(sz+1); s = +1 means the reference's sep_Wrap subtracted L
-    const int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
-    dx -= sx * B.Lx; dy -= sy * B.Ly; dz -= sz * B.Lz;
-}
-
-// ---- Lennard-Jones, Verlet list ------------------------------------------------------------------------
-struct PairAcc {
-    double fx, fy, fz;                       // per atom, in units of 48 eps
-    double u;                                // per thread
-    int nin;
-    double v[6];                             // per thread: xx xy xz yy yz zz, touched once per atom + on boundary pairs
-};
-
-__device__ __forceinline__ void virial_add(double *v, double gx, double gy, double gz, double sx, double sy, double sz)
-{
-    v[0] = fma(gx, sx, v[0]); v[1] = fma(gx, sy, v[1]); v[2] = fma(gx, sz, v[2]);
-    v[3] = fma(gy, sy, v[3]); v[4] = fma(gy, sz, v[4]); v[5] = fma(gz, sz, v[5]);
-}
 
 // One listed pair, branch-free: out-of-range (or wrong-type) pairs run the same arithmetic with the
 // force factor selected to zero.  In a warp some lane is almost always in range, so the branchy form
@@ -319,166 +250,6 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
     }
 }
 
-// ---- Lennard-Jones, pair-tile list (option pair_tile) ------------------------------------------------------------------
-// k_lj_list is bound by the L1 data pipe: every listed neighbour is a 32-byte gather from a line no other lane shares
-// (~22 wavefronts per warp-wide gather where 8 would do).  Here one THREAD owns the two sorted atoms (2t, 2t+1) and walks
-// the union of their neighbour rows (built by k_build_tile2<.., PAIR = true>): one gather serves two atoms, and the two
-// dependent FP64 chains of a step belong to the two atoms.  Entries carry membership flags, so each atom still sums
-// exactly its own list; a pair split over two list-build tiles walks its two single rows one after the other.
-struct PairAcc2 {
-    double fxa, fya, fza, fxb, fyb, fzb;    // per pair of atoms, in units of 48 eps
-    double u;                               // per thread
-    int nin;
-    double v[6];
-};
-
-template <bool TYPED>
-__device__ __forceinline__ void lj_tile_step(const d4 &pa, const d4 &pb, const d4 &pj, unsigned e, int ta, int tb,
-                                             const LJDev &P, const BoxDev &B, PairAcc2 &A)
-{
-    double dxa = pa.x - pj.x, dya = pa.y - pj.y, dza = pa.z - pj.z;
-    double dxb = pb.x - pj.x, dyb = pb.y - pj.y, dzb = pb.z - pj.z;
-    const int code = (int)SEPGPU_PT_CODE(e);
-    if (code != 13) { apply_image(code, B, dxa, dya, dza); apply_image(code, B, dxb, dyb, dzb); }
-    double r2a = fma(dza, dza, fma(dya, dya, dxa * dxa));
-    double r2b = fma(dzb, dzb, fma(dyb, dyb, dxb * dxb));
-    bool ina = (__double_as_longlong(r2a) < __double_as_longlong(P.cf2)) && !(e & SEPGPU_PT_SKIP_A);
-    bool inb = (__double_as_longlong(r2b) < __double_as_longlong(P.cf2)) && !(e & SEPGPU_PT_SKIP_B);
-    if (TYPED) {
-        const int tj = tag_type(pj.w);
-        ina = ina && ((ta == P.t0 && tj == P.t1) || (ta == P.t1 && tj == P.t0));     // source/sepprfrc.c:171-172
-        inb = inb && ((tb == P.t0 && tj == P.t1) || (tb == P.t1 && tj == P.t0));
-    }
-    // an entry that is the partner atom itself has r2 == 0 for it (and its skip flag set): keep the arithmetic finite
-    r2a = ina ? r2a : 1.0;
-    r2b = inb ? r2b : 1.0;
-    const double a0 = P.sig2 * fast_rcp3(r2a), a1 = P.sig2 * fast_rcp3(r2b);
-    double b0 = a0 * a0 * a0, b1 = a1 * a1 * a1;
-    double f0 = b0 * (b0 - P.awh) * a0, f1 = b1 * (b1 - P.awh) * a1;     // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
-    const double u0 = b0 - P.aw, u1 = b1 - P.aw;
-    f0 = ina ? f0 : 0.0; f1 = inb ? f1 : 0.0;
-    b0 = ina ? b0 : 0.0; b1 = inb ? b1 : 0.0;
-    A.fxa = fma(f0, dxa, A.fxa); A.fya = fma(f0, dya, A.fya); A.fza = fma(f0, dza, A.fza);
-    A.fxb = fma(f1, dxb, A.fxb); A.fyb = fma(f1, dyb, A.fyb); A.fzb = fma(f1, dzb, A.fzb);
-    A.u = fma(b0, u0, A.u);
-    A.u = fma(b1, u1, A.u);
-    A.nin += (ina ? 1 : 0) + (inb ? 1 : 0);
-    if (code != 13) {                                               // boundary-crossing pairs: - g (x) S (see lj_pair)
-        double sx = 0.0, sy = 0.0, sz = 0.0;
-        apply_image(code, B, sx, sy, sz);
-        double g = P.eps48 * f0;
-        virial_add(A.v, g * dxa, g * dya, g * dza, sx, sy, sz);
-        g = P.eps48 * f1;
-        virial_add(A.v, g * dxb, g * dyb, g * dzb, sx, sy, sz);
-    }
-}
-
-// MINB: CTAs per SM the register budget is cut for (option pt_ctas: 4 = 117 registers, 5 = 96 and a few spilled bytes,
-// 6 = 80) -- the occupancy / spill trade is to be settled on hardware
-template <bool TYPED, bool STORE, int MINB>
-__global__ void __launch_bounds__(FORCE_BLOCK, MINB)
-k_lj_pairtile(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
-              const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int pairs_per_cta,
-              LJDev P, BoxDev B, double *__restrict__ partial)
-{
-    __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
-    PairAcc2 A;
-    A.u = 0.0;
-    A.nin = 0;
-#pragma unroll
-    for (int q = 0; q < 6; q++) A.v[q] = 0.0;
-    const int npairs = (n + 1) >> 1;
-    const int first = blockIdx.x * pairs_per_cta;
-    const int last = min(npairs, first + pairs_per_cta);
-    const uint4 *nbrv = reinterpret_cast<const uint4 *>(nbr);
-
-    for (int t = first + (int)threadIdx.x; t < last; t += FORCE_BLOCK) {
-        const int sa = 2 * t, sb = 2 * t + 1;
-        const bool have_b = sb < n;
-        const d4 pa = xs[sa];
-        const d4 pb = xs[have_b ? sb : sa];
-        const int cb = have_b ? cnt[sb] : 0;
-        const bool paired = cb < 0;
-        int ta = 0, tb = 0;
-        if (TYPED) { ta = tag_type(pa.w); tb = tag_type(pb.w); }
-        A.fxa = A.fya = A.fza = A.fxb = A.fyb = A.fzb = 0.0;
-        // pass 0: row sa (both atoms when paired, else atom a alone); pass 1 (split pair only): row sb for atom b alone.
-        // A single row carries no flags and its owner plays the entry's "first atom", so pass 1 runs the same step with
-        // b in the first role (accumulators swapped around it) and the second role masked.
-        for (int pass = 0; pass < 2; pass++) {
-            if (pass == 1 && (paired || !have_b)) break;
-            const int s = pass == 0 ? sa : sb;
-            const int m = pass == 0 ? cnt[sa] : cb;
-            const unsigned kill = (pass == 0 && paired) ? 0u : SEPGPU_PT_SKIP_B;
-            const d4 p1 = pass == 0 ? pa : pb;
-            const d4 p2 = pb;
-            const int t1 = pass == 0 ? ta : tb;
-            if (pass == 1) {
-                double w;
-                w = A.fxa; A.fxa = A.fxb; A.fxb = w; w = A.fya; A.fya = A.fyb; A.fyb = w; w = A.fza; A.fza = A.fzb; A.fzb = w;
-            }
-            const int nch = (m + 3) >> 2;
-            const uint4 *row = nbrv + s;
-            uint4 cur = make_uint4(0, 0, 0, 0);
-            if (nch > 0) cur = __ldcs(row);
-            for (int c = 0; c < nch; c++) {
-                uint4 nxt = make_uint4(0, 0, 0, 0);
-                if (c + 1 < nch) nxt = __ldcs(row + (size_t)(c + 1) * npad);
-                const int left = m - 4 * c;                      // >= 1 valid entries in this chunk
-                {
-                    SEPGPU_EMU_GATHER(&xs[cur.x & SEPGPU_PT_INDEX_MASK]);
-                    const d4 pj = xs[cur.x & SEPGPU_PT_INDEX_MASK];
-                    lj_tile_step<TYPED>(p1, p2, pj, cur.x | kill, t1, tb, P, B, A);
-                }
-                if (left > 1) {
-                    SEPGPU_EMU_GATHER(&xs[cur.y & SEPGPU_PT_INDEX_MASK]);
-                    const d4 pj = xs[cur.y & SEPGPU_PT_INDEX_MASK];
-                    lj_tile_step<TYPED>(p1, p2, pj, cur.y | kill, t1, tb, P, B, A);
-                }
-                if (left > 2) {
-                    SEPGPU_EMU_GATHER(&xs[cur.z & SEPGPU_PT_INDEX_MASK]);
-                    const d4 pj = xs[cur.z & SEPGPU_PT_INDEX_MASK];
-                    lj_tile_step<TYPED>(p1, p2, pj, cur.z | kill, t1, tb, P, B, A);
-                }
-                if (left > 3) {
-                    SEPGPU_EMU_GATHER(&xs[cur.w & SEPGPU_PT_INDEX_MASK]);
-                    const d4 pj = xs[cur.w & SEPGPU_PT_INDEX_MASK];
-                    lj_tile_step<TYPED>(p1, p2, pj, cur.w | kill, t1, tb, P, B, A);
-                }
-                cur = nxt;
-            }
-            if (pass == 1) {
-                double w;
-                w = A.fxa; A.fxa = A.fxb; A.fxb = w; w = A.fya; A.fya = A.fyb; A.fyb = w; w = A.fza; A.fza = A.fzb; A.fzb = w;
-            }
-        }
-        {
-            const int i = order[sa];
-            const double fx = P.eps48 * A.fxa, fy = P.eps48 * A.fya, fz = P.eps48 * A.fza;
-            if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0; f4[i] = o; }
-            else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
-            virial_add(A.v, fx + fx, fy + fy, fz + fz, pa.x, pa.y, pa.z);      // 2 F_i (x) x_i
-        }
-        if (have_b) {
-            const int i = order[sb];
-            const double fx = P.eps48 * A.fxb, fy = P.eps48 * A.fyb, fz = P.eps48 * A.fzb;
-            if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0.0; f4[i] = o; }
-            else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
-            virial_add(A.v, fx + fx, fy + fy, fz + fz, pb.x, pb.y, pb.z);
-        }
-    }
-    double acc[SEPGPU_NPART_F];
-    acc[0] = P.eps4 * A.u - P.shift * (double)A.nin;
-    acc[1] = 0.0;
-#pragma unroll
-    for (int q = 0; q < 6; q++) acc[2 + q] = A.v[q];
-    block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
-    }
-}
-
 // ---- Lennard-Jones, all pairs (SEP_BRUTE) ------------------------------------------------------------------
 // exact reference arithmetic for the separation (wrapped x, sep_Wrap branches)
 __device__ __forceinline__ int share_tab_f(const int *__restrict__ tab, int width, int a, int b)
@@ -599,6 +370,8 @@ k_finalize_force(const double *__restrict__ partial, int nrows, DevScalars *scal
 int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_end(sepgpu_ctx *c);
+int sepgpu_need_global_rows(sepgpu_ctx *c, const sepgpu_sys *sys);
+int sepgpu_lj_tile_launch(sepgpu_ctx *c, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows);
 
 // Option fin_multi: the same reduction spread over several CTAs.  CTA b sums a fixed chunk of rows into stage row b;
 // the CTA that draws the last ticket adds the stage rows in index order and applies the result -- fixed chunks and a
@@ -869,37 +642,19 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
     }
     // the type test is compiled out when every atom carries the one requested type
     const bool typed = !(types[0] == types[1] && c->single_type == (unsigned char)types[0]);
-    if (c->list_pair && c->fij) {
-        // the molecule-pair table was switched on after a pair-tile list had been built: per-atom rows from now on
-        c->need_atom_rows = true;
-        if ((rc = sepgpu_neighb_build(c, sys, c->list_opt))) return rc;
+    if (c->list_f16 && c->fij) {
+        // the molecule-pair table was switched on after a tile-format list had been built: global-index rows from now on
+        if ((rc = sepgpu_need_global_rows(c, sys))) return rc;
     }
-    if (c->list_pair) {                                  // option pair_tile: rows per pair of sorted atoms
+    if (c->list_f16) {                                   // rows of 16-bit tile slots: shared-memory staged tile kernel
         if (c->dd && (rc = sepgpu_dd_halo_update(c, sys))) return rc;     // neighbours' boundary atoms moved too
-        const int npairs = (c->n + 1) / 2;
-        int grid = c->force_grid > 0 ? c->force_grid : FORCE_MAX_GRID;
-        int ppc = (npairs + grid - 1) / grid;
-        ppc = ((ppc + FORCE_BLOCK - 1) / FORCE_BLOCK) * FORCE_BLOCK;
-        grid = (npairs + ppc - 1) / ppc;
+        int nrows = 0;
         ktimer_begin(c, &c->t_force);
-#define PT_ARGS c->xs, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, ppc, P, B, c->partial
-#define PT_LAUNCH(MB)                                                                                       \
-        do {                                                                                                \
-            if (typed) {                                                                                    \
-                if (store) k_lj_pairtile<true, true, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);     \
-                else       k_lj_pairtile<true, false, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);    \
-            } else {                                                                                        \
-                if (store) k_lj_pairtile<false, true, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);    \
-                else       k_lj_pairtile<false, false, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(PT_ARGS);   \
-            }                                                                                               \
-        } while (0)
-        if (c->pt_ctas == 4) PT_LAUNCH(4); else if (c->pt_ctas == 6) PT_LAUNCH(6); else PT_LAUNCH(5);
-#undef PT_LAUNCH
-#undef PT_ARGS
+        rc = sepgpu_lj_tile_launch(c, P, B, typed, store, &nrows);
         ktimer_end(c, &c->t_force);
-        KERNEL_CHECK();
+        if (rc) return rc;
         c->f_zero = false;
-        return sepgpu_finalize_force(c, grid, 0.5, epot_assign ? 1 : 0);
+        return sepgpu_finalize_force(c, nrows, 0.5, epot_assign ? 1 : 0);
     }
     const int tpa = c->tpa;
     // contiguous ranges of the sorted atoms per CTA; several CTAs per SM, a few waves for load balance

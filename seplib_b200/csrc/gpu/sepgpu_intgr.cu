@@ -467,6 +467,13 @@ __global__ void k_set_xn(const d4 *__restrict__ x4, d4 *__restrict__ xn4, i4 *__
     cr4[i] = c;
 }
 
+int sepgpu_reset_xn(sepgpu_ctx *c)
+{
+    k_set_xn<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n_own);
+    KERNEL_CHECK();
+    return 0;
+}
+
 int sepgpu_ensure_dpd(sepgpu_ctx *c);
 // domain-decomposition hooks (sepgpu_dd.cu)
 double *sepgpu_dd_comm(sepgpu_ctx *c);
@@ -571,6 +578,7 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     c->pending_alpha_slot = -1;
     c->pending_alpha_type = -1;
     c->mv2_valid = true;
+    c->moved_since_build = true;
     if (!P.write_xs) c->xs_current = false;
     sepgpu_dd_positions_moved(c);
 
@@ -695,6 +703,7 @@ static int run_stochastic(sepgpu_ctx *c, const sepgpu_sys *sys, bool gjf, double
     k_finalize_intgr<<<1, 256, 0, c->stream>>>(c->partial, grid, c->scal, sys->skin, 0, NULL, resets, 0, 1);
     KERNEL_CHECK();
     c->mv2_valid = true;
+    c->moved_since_build = true;
     if (!P.write_xs) c->xs_current = false;
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));

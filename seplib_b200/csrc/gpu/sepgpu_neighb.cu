@@ -15,54 +15,19 @@
 // only band candidates pay for the exact FP64 test.
 #include "sepgpu_internal.cuh"
 
+#include "sepgpu_tile.cuh"
+
 #define BUILD_WARPS 8
-#define BRICK_YZ 4
-
-struct CellGrid {
-    int nx, ny, nz;         // reference cell grid (sys->nsubbox)
-    int bx;                 // brick extent along x (1,2,4,8); y and z extents are BRICK_YZ
-    int nbx, nby, nbz;      // bricks per direction
-    // slab decomposition along z (sepgpu_dd.cu): nz above is the number of LOCAL layers (owned layers
-    // plus one halo layer on each side); local layer l holds global layer zoff + l (mod nzg)
-    int dd, zoff, nzg;
-};
-
-__host__ __device__ __forceinline__ int cell_key(int cx, int cy, int cz, const CellGrid &G)
-{
-    const int bxi = cx / G.bx, lx = cx % G.bx;
-    const int byi = cy / BRICK_YZ, ly = cy % BRICK_YZ;
-    const int bzi = cz / BRICK_YZ, lz = cz % BRICK_YZ;
-    return (((bzi * G.nby + byi) * G.nbx + bxi) * (BRICK_YZ * BRICK_YZ) + lz * BRICK_YZ + ly) * G.bx + lx;
-}
-
-__host__ __device__ __forceinline__ void key_cell(int key, const CellGrid &G, int &cx, int &cy, int &cz)
-{
-    const int lx = key % G.bx; key /= G.bx;
-    const int ly = key % BRICK_YZ; key /= BRICK_YZ;
-    const int lz = key % BRICK_YZ; key /= BRICK_YZ;
-    const int bxi = key % G.nbx; key /= G.nbx;
-    const int byi = key % G.nby; const int bzi = key / G.nby;
-    cx = bxi * G.bx + lx; cy = byi * BRICK_YZ + ly; cz = bzi * BRICK_YZ + lz;
-}
 
 // ---- binning ------------------------------------------------------------------------------------------
 __global__ void k_cell_count(const d4 *__restrict__ x4, int n, double lsx, double lsy, double lsz,
-                             CellGrid G, int *__restrict__ cell_of, int *__restrict__ cell_cnt, DevScalars *scal,
-                             unsigned char *__restrict__ subkey)
+                             CellGrid G, int *__restrict__ cell_of, int *__restrict__ cell_cnt, DevScalars *scal)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     d4 p = x4[i];
     // source/sepprfrc.c:404-406, IEEE division then truncation
     int cx = (int)__ddiv_rn(p.x, lsx), cy = (int)__ddiv_rn(p.y, lsy), cz = (int)__ddiv_rn(p.z, lsz);
-    if (subkey) {
-        // option cell_order = 1: Morton code of the atom's place inside its cell (4 x 4 x 4 sub-cells); atoms of a cell
-        // are then laid out along that curve, so neighbouring slots are neighbours in space
-        const int ux = min(3, max(0, (int)((__ddiv_rn(p.x, lsx) - cx) * 4.0)));
-        const int uy = min(3, max(0, (int)((__ddiv_rn(p.y, lsy) - cy) * 4.0)));
-        const int uz = min(3, max(0, (int)((__ddiv_rn(p.z, lsz) - cz) * 4.0)));
-        subkey[i] = (unsigned char)((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2) | ((ux & 2) << 2) | ((uy & 2) << 3) | ((uz & 2) << 4));
-    }
     const int nzg = G.dd ? G.nzg : G.nz;
     if (cx < 0 || cx >= G.nx || cy < 0 || cy >= G.ny || cz < 0 || cz >= nzg || !(p.x == p.x)) {
         // The reference does not clamp: it forms the linear index cx + cy*nx + cz*nx*ny and, while that
@@ -183,7 +148,7 @@ __global__ void k_cell_finalize(const int *__restrict__ tmp_slot, const int *__r
                                 const int *__restrict__ cell_start, const d4 *__restrict__ x4,
                                 int n, int *__restrict__ order, int *__restrict__ rank,
                                 d4 *__restrict__ xs, float4 *__restrict__ xf, i4 *__restrict__ cr4,
-                                unsigned char *__restrict__ cls, CellGrid G, const unsigned char *__restrict__ subkey)
+                                unsigned char *__restrict__ cls, CellGrid G)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -191,13 +156,6 @@ __global__ void k_cell_finalize(const int *__restrict__ tmp_slot, const int *__r
     int c = cell_of[i];
     int b = cell_start[c], e = cell_start[c + 1];
     int r = 0;
-    if (subkey) {                                   // option cell_order = 1: (sub-cell Morton code, atom index)
-        const int ki = subkey[i];
-        for (int q = b; q < e; q++) {
-            const int iq = tmp_slot[q], kq = subkey[iq];
-            r += (kq < ki) || (kq == ki && iq < i);
-        }
-    } else
     for (int q = b; q < e; q++) r += tmp_slot[q] < i;
     int s = b + r;
     order[s] = i;
@@ -228,12 +186,10 @@ struct BuildParams {
     double Lx, Ly, Lz;
     double cut2;
     float fLx, fLy, fLz, fcut_lo, fcut_hi;
-    float flsx, flsy, flsz;  // cell widths (option build_prune)
     CellGrid G;
     int n, npad, cap;
     unsigned opt;
     int prefilter;
-    int spatial_order;      // option cell_order = 1: slots of a cell follow a space-filling curve, not the atom index
 };
 
 // exact reference test; returns accept and the image code chosen by the sep_Wrap branches
@@ -332,14 +288,10 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
     }
 }
 
-// ---- tiled build: the fast path is k_build_tile2 (sepgpu_neighb_tile.cuh) --------------------------------------------
-// brick / tile geometry shared with the host-side choice of G.bx
-#define TILE_MAXCX 8
-#define TILE_THREADS 160
-
+// ---- tiled build: the fast path is k_build_tile (sepgpu_neighb_tile.cuh) ---------------------------------------------
 #include "sepgpu_neighb_tile.cuh"
 
-__global__ void k_build_begin(DevScalars *s) { s->row_entries = 0; s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->stage_needed = 0; s->aliased_seen = 0; }
+__global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->stage_needed = 0; s->stage_used = 0; s->aliased_seen = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
 int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local);
@@ -352,6 +304,19 @@ static int estimate_cap(const sepgpu_ctx *c, const sepgpu_sys *sys)
     int cap = (int)(expect * 1.5) + 24;
     if (cap > c->n_global) cap = (int)c->n_global;
     return (cap + 7) & ~7;
+}
+
+// Tile shape for a mean cell occupancy: brick x-extent bx (1, 2, 4, 8) and x-runs per tile R (1, 2, 4), as many home
+// atoms as one pass of TILE_THREADS threads takes, within the staging limits (16-bit slots, shared memory).
+static void choose_tile(double mean_per_cell, int nx, int ny, int *bx_out, int *R_out)
+{
+    const double budget = 0.94 * TILE_THREADS;
+    int bx = 1;
+    while (bx < TILE_MAXBX && 2 * bx * mean_per_cell <= budget && 2 * bx <= nx) bx *= 2;
+    int R = 1;
+    while (R < TILE_MAXR && 2 * R * bx * mean_per_cell <= budget && 2 * R <= ny &&
+           3.0 * (2 * R + 2) * (bx + 2) * mean_per_cell * 1.3 <= 0.8 * TILE_MAX_SLOTS) R *= 2;
+    *bx_out = bx; *R_out = R;
 }
 
 extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigned opt)
@@ -374,10 +339,10 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (rcd) return rcd;
         G.dd = 1;
     }
-    // brick x-extent: as many cells as keep one x-run of home atoms within one pass of the tile kernel
     const double mean_per_cell = (double)c->n / ((double)nx * ny * G.nz);
-    G.bx = 1;
-    while (G.bx < TILE_MAXCX && 2 * G.bx * mean_per_cell <= 0.9 * TILE_THREADS && 2 * G.bx <= nx) G.bx *= 2;
+    int R = 1;
+    choose_tile(mean_per_cell, nx, ny, &G.bx, &R);
+    if (c->tile_R_max > 0) while (R > c->tile_R_max) R /= 2;       // a tile overflowed the slot range earlier: smaller tiles
     G.nbx = (nx + G.bx - 1) / G.bx; G.nby = (ny + BRICK_YZ - 1) / BRICK_YZ; G.nbz = (G.nz + BRICK_YZ - 1) / BRICK_YZ;
     const long long nkey_ll = (long long)G.nbx * G.nby * G.nbz * G.bx * BRICK_YZ * BRICK_YZ;
     if (nkey_ll > (1LL << 30)) { sepgpu_set_error("neighb_build: too many cells"); return SEPGPU_EINVAL; }
@@ -393,43 +358,34 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         c->ncell_cap = nkey;
     }
     int *block_sum = c->cell_cnt + nkey + 1;
-    if (c->cap == 0) {
-        c->cap = estimate_cap(c, sys);
-        if (c->pair_tile) c->cap = (c->cap * 8 / 5 + 7) & ~7;      // a pair's row holds the union of two lists
-    }
+    if (c->cap == 0) c->cap = estimate_cap(c, sys);
 
     const int B = 256, Gn = (c->n + B - 1) / B;
     bool force_exact = false;
     for (int attempt = 0; attempt < 8; attempt++) {
         if (!c->nbr) CUDA_TRY(cudaMalloc((void **)&c->nbr, sizeof(unsigned) * (size_t)c->cap * c->npad));
 
-        unsigned char *subkey = NULL;
-        if (c->cell_order) {
-            if (!c->subkey) CUDA_TRY(cudaMalloc((void **)&c->subkey, (size_t)c->ncap));
-            subkey = c->subkey;
-        }
-        // pair-tile format (option pair_tile): uncharged systems; in slab runs the halo atoms own empty single rows
-        const bool pair_format = c->pair_tile && !c->need_atom_rows && !(c->dd && c->overlap) && !c->fij && !c->have_charge && (unsigned)c->n <= SEPGPU_PT_INDEX_MASK;
-        bool built_pair = false;
+        // Rows of 16-bit tile slots for the tile force kernels unless a consumer of global-index rows has been seen
+        // (DPD, the molecule-pair table) or the context asks for them (option tile_list = 0)
+        const bool f16 = c->tile_list && !c->need_atom_rows && !c->fij && !c->have_charge;
+        bool built_f16 = false;
         ktimer_begin(c, &c->t_build);
         CUDA_TRY(cudaMemsetAsync(c->cell_cnt, 0, sizeof(int) * ((size_t)nkey + 1), c->stream));
         k_build_begin<<<1, 1, 0, c->stream>>>(c->scal);
         k_cell_count<<<Gn, B, 0, c->stream>>>(c->x4, c->n, sys->lsubbox[0], sys->lsubbox[1], sys->lsubbox[2],
-                                              G, c->cell_of, c->cell_cnt, c->scal, subkey);
+                                              G, c->cell_of, c->cell_cnt, c->scal);
         if (sepgpu_exclusive_scan(c->stream, c->cell_cnt, c->cell_start, block_sum, nkey)) return SEPGPU_ECUDA;
         k_cell_scatter<<<Gn, B, 0, c->stream>>>(c->cell_of, c->n, c->cell_start, c->cell_cnt, c->tmp_slot);
         if (c->dd && !c->cls) CUDA_TRY(cudaMalloc((void **)&c->cls, (size_t)c->ncap));
         k_cell_finalize<<<Gn, B, 0, c->stream>>>(c->tmp_slot, c->cell_of, c->cell_start, c->x4, c->n,
-                                                 c->order, c->rank, c->xs, c->xf, c->cr4, c->dd ? c->cls : NULL, G, subkey);
+                                                 c->order, c->rank, c->xs, c->xf, c->cr4, c->dd ? c->cls : NULL, G);
         BuildParams P;
         P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
         const double cut = sys->cf + sys->skin;
         P.cut2 = cut * cut;                              // sep_Sq(sys->cf + sys->skin), :432
         P.fLx = (float)P.Lx; P.fLy = (float)P.Ly; P.fLz = (float)P.Lz;
-        P.flsx = (float)sys->lsubbox[0]; P.flsy = (float)sys->lsubbox[1]; P.flsz = (float)sys->lsubbox[2];
         P.G = G;
         P.n = c->n; P.npad = c->npad; P.cap = c->cap; P.opt = opt;
-        P.spatial_order = subkey != NULL;
         // FP32 prefilter: |r2_f32 - r2_exact| <= 2*sqrt(3)*cut * 4*Lmax*2^-24 (+ accumulation rounding);
         // the band below is 5x that bound.  It also needs cell image == minimum image, which holds when
         // every dimension has >= 4 cells and cut < 2 cells (< L/2).
@@ -440,38 +396,25 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (c->dd && !P.prefilter) { sepgpu_set_error("neighb_build: decomposed runs need >= 4 cells per direction"); return SEPGPU_EINVAL; }
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
+        const int ntile = nkey / (G.bx * R);
         if (P.prefilter) {
-            const int grid = nkey / G.bx;
             if (c->tile_stage_cap == 0) {
-                // 9 rows x (bx+2) cells x mean occupancy, with head-room for density fluctuations
-                c->tile_stage_cap = ((int)(9.0 * (G.bx + 2) * mean_per_cell * 1.3) + 96 + 31) & ~31;
+                // 3 x (R+2) rows x (bx+2) cells x mean occupancy, with head-room for density fluctuations
+                c->tile_stage_cap = ((int)(3.0 * (R + 2) * (G.bx + 2) * mean_per_cell * 1.3) + 96 + 31) & ~31;
             }
             const int stage_cap = c->tile_stage_cap;
-            const size_t smem = (size_t)(stage_cap + TILE2_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
+            const size_t smem = (size_t)(stage_cap + TILE_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
             if (smem > 200 * 1024) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
-#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, stage_cap
-#define TILE_LAUNCH4(O, PR, SP, PN)                                                                                              \
+#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, R, stage_cap
+#define TILE_LAUNCH(O, F)                                                                                                        \
     do {                                                                                                                         \
-        CUDA_TRY(cudaFuncSetAttribute(k_build_tile2<O, PR, SP, PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-        k_build_tile2<O, PR, SP, PN><<<grid, TILE2_THREADS, smem, c->stream>>>(TILE_ARGS);                                      \
+        CUDA_TRY(cudaFuncSetAttribute(k_build_tile<O, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        k_build_tile<O, F><<<ntile, TILE_THREADS, smem, c->stream>>>(TILE_ARGS);                                                 \
     } while (0)
-#define TILE_LAUNCH(O, PR, SP) do { if (prune) TILE_LAUNCH4(O, PR, SP, true); else TILE_LAUNCH4(O, PR, SP, false); } while (0)
-            const bool sp = subkey != NULL;
-            const bool prune = c->build_prune && !c->dd;       // slab runs keep the plain sweep (local/global layer bookkeeping)
-            if (pair_format) {
-                // membership flags are each atom's own accepted set, so the exclusion rules carry over unchanged
-                if (opt == SEPGPU_ALL) { if (sp) TILE_LAUNCH(SEPGPU_ALL, true, true); else TILE_LAUNCH(SEPGPU_ALL, true, false); }
-                else if (opt == SEPGPU_EXCL_SAME_MOL) { if (sp) TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, true, true); else TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, true, false); }
-                else { if (sp) TILE_LAUNCH(SEPGPU_EXCL_BONDED, true, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, true, false); }
-                built_pair = true;
-            } else if (opt == SEPGPU_ALL) {
-                if (sp) TILE_LAUNCH(SEPGPU_ALL, false, true); else TILE_LAUNCH(SEPGPU_ALL, false, false);
-            } else if (opt == SEPGPU_EXCL_SAME_MOL) {
-                if (sp) TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, false, true); else TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, false, false);
-            } else {
-                if (sp) TILE_LAUNCH(SEPGPU_EXCL_BONDED, false, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, false, false);
-            }
-#undef TILE_LAUNCH4
+            if (opt == SEPGPU_ALL) { if (f16) TILE_LAUNCH(SEPGPU_ALL, true); else TILE_LAUNCH(SEPGPU_ALL, false); }
+            else if (opt == SEPGPU_EXCL_SAME_MOL) { if (f16) TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, true); else TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, false); }
+            else { if (f16) TILE_LAUNCH(SEPGPU_EXCL_BONDED, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, false); }
+            built_f16 = f16;
 #undef TILE_LAUNCH
 #undef TILE_ARGS
         } else {
@@ -500,8 +443,14 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             CUDA_TRY(cudaMemcpyAsync(&c->scal->nbuild, &c->scal_host->nbuild, sizeof(int), cudaMemcpyHostToDevice, c->stream));
             continue;
         }
-        if (c->scal_host->stage_needed > 0) {       // a tile needed a larger staging buffer: grow, rebuild
-            c->tile_stage_cap = (c->scal_host->stage_needed * 5 / 4 + 63) & ~31;
+        if (c->scal_host->stage_needed > 0) {       // a tile needed a larger staging buffer: grow (or shrink the tile), rebuild
+            if (c->scal_host->stage_needed > TILE_MAX_SLOTS) {
+                if (R == 1) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
+                R /= 2; c->tile_R_max = R; c->tile_stage_cap = 0;
+            } else {
+                c->tile_stage_cap = (c->scal_host->stage_needed * 5 / 4 + 63) & ~31;
+                if (c->tile_stage_cap > TILE_MAX_SLOTS) c->tile_stage_cap = TILE_MAX_SLOTS;
+            }
             c->scal_host->nbuild -= 1;
             CUDA_TRY(cudaMemcpyAsync(&c->scal->nbuild, &c->scal_host->nbuild, sizeof(int), cudaMemcpyHostToDevice, c->stream));
             continue;
@@ -509,7 +458,10 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (c->scal_host->max_neighb <= c->cap) {
             c->list_valid = true; c->list_opt = opt; c->sorted_identity = false; c->xs_current = true;
             c->zs_valid = false;
-            c->list_pair = built_pair;
+            c->list_f16 = built_f16;
+            c->tile_grid = G; c->tile_R = R; c->tile_count = ntile;
+            c->tile_stage_used = (c->scal_host->stage_used + 31) & ~31;
+            c->moved_since_build = false;
             c->list_gen++;
             c->grid_n[0] = nx; c->grid_n[1] = ny; c->grid_n[2] = nz;
             return 0;
@@ -522,6 +474,23 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
     }
     sepgpu_set_error("neighb_build: neighbour capacity did not converge");
     return SEPGPU_ENEIGHB;
+}
+
+// A consumer of global-index rows (list Coulomb, DPD, the molecule-pair table) met a list of tile slots: this context
+// builds global-index rows from now on, and the current list is rebuilt in that format.  When atoms have moved since
+// the list was built, the rebuild point also becomes the reference point of the skin trigger (xn <- x, cross_neighb <- 0,
+// what the reference does at a rebuild, source/sepintgr.c:76-82): a list built here must be valid until every atom has
+// moved skin/2 from HERE.
+int sepgpu_reset_xn(sepgpu_ctx *c);
+int sepgpu_need_global_rows(sepgpu_ctx *c, const sepgpu_sys *sys)
+{
+    c->need_atom_rows = true;
+    if (!c->list_valid || !c->list_f16) return 0;
+    const bool moved = c->moved_since_build;
+    int rc = sepgpu_neighb_build(c, sys, c->list_opt);
+    if (rc) return rc;
+    if (moved) return sepgpu_reset_xn(c);
+    return 0;
 }
 
 // ---- pair export -----------------------------------------------------------------------------------------------
@@ -545,31 +514,34 @@ __global__ void k_export_pairs(const unsigned *__restrict__ nbr, const int *__re
     }
 }
 
-// pair-tile format: row s belongs to atom s alone (flags clear) or to the pair (s, s+1) with per-atom membership flags
-__global__ void k_export_pairs_pt(const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
-                                  const int *__restrict__ order, int n, int npad, int *__restrict__ out,
-                                  long long max_pairs, unsigned long long *counter, const int *__restrict__ gid, int n_own)
+// rows of 16-bit tile slots: one CTA per tile rebuilds the tile's staging order and maps slots back to sorted indices
+__global__ void __launch_bounds__(TILE_THREADS)
+k_export_pairs_tile(const unsigned short *__restrict__ nbr16, const int *__restrict__ cnt, const int *__restrict__ order,
+                    const int *__restrict__ cell_start, CellGrid G, int R, int npad, int *__restrict__ out,
+                    long long max_pairs, unsigned long long *counter, const int *__restrict__ gid, int n_own)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const int m = cnt[s];
-    if (m < 0) return;                           // second atom of a pair: served by row s - 1
-    const bool both = !(s & 1) && s + 1 < n && cnt[s + 1] < 0;
-    int ia = order[s], ib = both ? order[s + 1] : -1;
-    // decomposed run: halo atoms own no pairs; global ids (a cross-rank pair is emitted by one rank only)
-    const bool use_a = ia < n_own, use_b = both && ib < n_own;
-    if (gid) { ia = gid[ia]; if (both) ib = gid[ib]; }
-    for (int k = 0; k < m; k++) {
-        const unsigned e = nbr[nbr_index(k, s, npad)];
-        int j = order[e & SEPGPU_PT_INDEX_MASK];
-        if (gid) j = gid[j];
-        if (use_a && !(e & SEPGPU_PT_SKIP_A) && ia < j) {
-            unsigned long long p = atomicAdd(counter, 1ULL);
-            if ((long long)p < max_pairs) { out[2 * p] = ia; out[2 * p + 1] = j; }
-        }
-        if (use_b && !(e & SEPGPU_PT_SKIP_B) && ib < j) {
-            unsigned long long p = atomicAdd(counter, 1ULL);
-            if ((long long)p < max_pairs) { out[2 * p] = ib; out[2 * p + 1] = j; }
+    __shared__ TileLayout T;
+    if (G.dd) {
+        int x0, cy0, cz;
+        key_cell(blockIdx.x * R * G.bx, G, x0, cy0, cz);
+        if (cz == 0 || cz == G.nz - 1) return;
+    }
+    if (!tile_layout(T, G, R, cell_start)) return;
+    for (int ab = threadIdx.x; ab < T.nhome; ab += TILE_THREADS) {
+        const int s = T.a0 + ab;
+        int i = order[s];
+        if (i >= n_own) continue;
+        if (gid) i = gid[i];
+        const int m = cnt[s];
+        for (int k = 0; k < m; k++) {
+            const int q = nbr16[nbr16_index(k, s, npad)] & TILE_SLOT_MASK;
+            const int cc = tile_cell_of_slot(T, q);
+            int j = order[T.beg[cc] + (q - T.off[cc])];
+            if (gid) j = gid[j];
+            if (i < j) {
+                unsigned long long p = atomicAdd(counter, 1ULL);
+                if ((long long)p < max_pairs) { out[2 * p] = i; out[2 * p + 1] = j; }
+            }
         }
     }
 }
@@ -583,7 +555,7 @@ extern "C" long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_p
     if (cudaMalloc((void **)&dout, sizeof(int) * 2 * (size_t)max_pairs) != cudaSuccess) return SEPGPU_ECUDA;
     if (cudaMalloc((void **)&dcount, sizeof(unsigned long long)) != cudaSuccess) { cudaFree(dout); return SEPGPU_ECUDA; }
     cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), c->stream);
-    if (c->list_pair) k_export_pairs_pt<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
+    if (c->list_f16) k_export_pairs_tile<<<c->tile_count, TILE_THREADS, 0, c->stream>>>(reinterpret_cast<const unsigned short *>(c->nbr), c->cnt, c->order, c->cell_start, c->tile_grid, c->tile_R, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     else k_export_pairs<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream);

@@ -79,6 +79,7 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->single_type = 'A';
     c->coulomb_kernel = 1;
     c->typed_sublist = 0;
+    c->tile_list = 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
     const size_t n = npart;
@@ -134,7 +135,6 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     for (int k = 0; k < SEPGPU_NSUB; k++) { if (c->nbr_t[k]) cudaFree(c->nbr_t[k]); if (c->cnt_t[k]) cudaFree(c->cnt_t[k]); }
     if (c->tsort) cudaFree(c->tsort);
     if (c->xq) cudaFree(c->xq);
-    if (c->subkey) cudaFree(c->subkey);
     if (c->fin_ticket) cudaFree(c->fin_ticket);
     if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
@@ -693,16 +693,9 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     }
     if (!strcmp(name, "prefilter")) { c->prefilter = value != 0; return 0; }
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
-    if (!strcmp(name, "pt_ctas") || !strcmp(name, "coul2_ctas")) {
-        if (value != 0 && value != 4 && value != 5 && value != 6) return SEPGPU_EINVAL;
-        if (name[0] == 'p') c->pt_ctas = (int)value; else c->coul2_ctas = (int)value;
-        return 0;
-    }
     if (!strcmp(name, "step_fold")) { if (!value) { int rs = sepgpu_settle(c); if (rs) return rs; } c->step_fold = value != 0; return 0; }
     if (!strcmp(name, "fin_multi")) { c->fin_multi = value != 0; return 0; }
-    if (!strcmp(name, "build_prune")) { c->build_prune = value != 0; return 0; }
-    if (!strcmp(name, "cell_order")) { if (value != 0 && value != 1) return SEPGPU_EINVAL; c->cell_order = (int)value; c->list_valid = false; return 0; }
-    if (!strcmp(name, "pair_tile")) { c->pair_tile = value != 0; c->list_valid = false; return 0; }
+    if (!strcmp(name, "tile_list")) { c->tile_list = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
     if (!strcmp(name, "typed_sublist")) { c->typed_sublist = value != 0; return 0; }
     if (!strcmp(name, "force_grid")) { c->force_grid = value > 0 && value <= SEPGPU_MAX_BLOCKS_PARTIAL ? (int)value : 0; return 0; }
@@ -734,15 +727,14 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "neighb_cap")) *value = c->cap;
     else if (!strcmp(name, "coulomb_kernel")) *value = c->coulomb_kernel;
     else if (!strcmp(name, "typed_sublist")) *value = c->typed_sublist;
-    else if (!strcmp(name, "pair_tile")) *value = c->pair_tile;
-    else if (!strcmp(name, "cell_order")) *value = c->cell_order;
-    else if (!strcmp(name, "build_prune")) *value = c->build_prune;
+    else if (!strcmp(name, "tile_list")) *value = c->tile_list;
     else if (!strcmp(name, "fin_multi")) *value = c->fin_multi;
     else if (!strcmp(name, "step_fold")) *value = c->step_fold;
-    else if (!strcmp(name, "list_pair")) *value = c->list_valid && c->list_pair ? 1 : 0;
+    else if (!strcmp(name, "list_f16")) *value = c->list_valid && c->list_f16 ? 1 : 0;       // rows of 16-bit tile slots
+    else if (!strcmp(name, "tile_R")) *value = c->tile_R;
+    else if (!strcmp(name, "tile_stage")) *value = c->tile_stage_used;
     else if (!strcmp(name, "dd_p2p")) *value = sepgpu_dd_uses_p2p(c);               // decomposed run on the peer-memory path
     else if (!strcmp(name, "max_half")) *value = c->scal_host->max_half;            // longest reference-style half list, last build
-    else if (!strcmp(name, "row_entries")) *value = c->scal_host->row_entries;      // as of the last list build (pair-tile format)
     else { sepgpu_set_error("sepgpu_get_option: unknown option '%s'", name); return SEPGPU_EINVAL; }
     return 0;
 }

@@ -1,15 +1,11 @@
-"""Opt-in kernels (sepgpu_set_option / SEPGPU_OPTS):
-  coulomb_kernel=2   second list Coulomb kernel          typed_sublist=1   per-type sub-lists for typed Lennard-Jones calls
-  pair_tile=1        list rows per pair of sorted atoms + k_lj_pairtile     cell_order=1   Morton slot order inside a cell
-  build_prune=1      list builder skips unreachable candidate cells         fin_multi=1    multi-CTA final reductions
-  step_fold=1        force reduction + Nose-Hoover update folded into the integrator's kernels
-Same parity bar as the default kernels they stand in for: forces 1e-10 of the oracle / the reference's golden vectors,
-pair sets bit-exact, sums 1e-10, and agreement with the default kernels to rounding over runs with many rebuilds.
-
-Status: written without access to hardware.  Their logic is verified on the CPU kernel emulator
-(tests/test_cpu_emu.py runs this file with SEPGPU_TEST_UNVERIFIED=1, also under UBSan); on a GPU box they are skipped
-until a hardware run has confirmed them -- set SEPGPU_TEST_UNVERIFIED=1 to run them there (scripts/gpu_r2_ab.sh does).
-The options default to off, so nothing the default suite or bench.py measures goes through these kernels.
+"""Kernel options (sepgpu_set_option / SEPGPU_OPTS) and the list formats behind them:
+  tile_list=1 (default)  rows of 16-bit tile slots + the shared-memory staged tile kernel; 0 = global-index rows + gather kernel
+  coulomb_kernel=2       second list Coulomb kernel          typed_sublist=1   per-type sub-lists for typed Lennard-Jones calls
+  fin_multi=1            multi-CTA final reductions          step_fold=1       force reduction + Nose-Hoover update folded
+                                                                               into the integrator's kernels
+Same parity bar everywhere: forces 1e-10 of the oracle / the reference's golden vectors, pair sets bit-exact, sums 1e-10,
+and agreement between alternative kernels to rounding over runs with many rebuilds.  All of these ran on a B200
+(round 2, scripts/gpu_r2_ab.sh); the CPU suite runs the same file on the kernel emulator (tests/test_cpu_emu.py).
 """
 import ctypes as C
 import os
@@ -21,9 +17,7 @@ import common as cm
 from seplib_b200 import capi
 from test_gpu_more import tiled_water
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SEPGPU_TEST_UNVERIFIED") != "1",
-                                 reason="opt-in kernels verified on the CPU emulator only; SEPGPU_TEST_UNVERIFIED=1 runs them")]
+pytestmark = [pytest.mark.gpu]
 
 FT = 1e-10
 
@@ -157,7 +151,7 @@ def test_options_through_the_environment(tmp_path):
         assert want in r.stdout, (opts, r.stdout, r.stderr)
 
 
-# ---- pair_tile: rows per pair of sorted atoms + k_lj_pairtile ------------------------------------------------------
+# ---- tile lists: rows of 16-bit tile slots + the shared-memory staged tile kernel (the default Lennard-Jones path) ---
 def _opt(s, name):
     v = C.c_longlong(-1)
     s.call("sepgpu_get_option", name.encode(), C.byref(v))
@@ -169,18 +163,18 @@ def _lj(ncell, seed=3, jitter=0.12):
 
 
 @pytest.mark.parametrize("skin", [0.25, 1.0])
-def test_pair_tile_list_holds_exactly_the_reference_pair_set(skin):
-    """Per-atom membership flags of the pair rows reproduce the reference's pair set bit for bit -- also with the
-    skin-1.0 quirk, where one atom of a pair may see a neighbour the other atom's cells do not reach."""
-    x, L = _lj(14)
+@pytest.mark.parametrize("ncell", [14, 18])
+def test_tile_list_holds_exactly_the_reference_pair_set(skin, ncell):
+    """Slots decode to the reference's pair set bit for bit -- also with the skin-1.0 quirk (cells narrower than the
+    list cutoff) and on grids whose size is not a multiple of the brick (padding tiles, clipped tiles)."""
+    x, L = _lj(ncell)
     cf = 2.5
     ref_pairs = cm.pair_set(cm.oracle_pairs(x, L, cf, skin))
     s = capi.System(len(x))
     s.put(capi.F_X, x)
-    s.call("sepgpu_set_option", b"pair_tile", 1)
     sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
     s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
-    assert _opt(s, "list_pair") == 1
+    assert _opt(s, "list_f16") == 1
     got = cm.pair_set(s.pairs())
     assert got.shape == ref_pairs.shape and np.array_equal(got, ref_pairs)
     assert s.scalars().npairs_listed == 2 * len(ref_pairs)
@@ -188,7 +182,7 @@ def test_pair_tile_list_holds_exactly_the_reference_pair_set(skin):
 
 
 @pytest.mark.parametrize("typed,skin", [(False, 0.25), (True, 0.25), (False, 1.0)])
-def test_pair_tile_forces_match_oracle(typed, skin):
+def test_tile_forces_match_oracle(typed, skin):
     x, L = _lj(12, seed=9)
     n = len(x)
     cf = 2.5
@@ -201,7 +195,6 @@ def test_pair_tile_forces_match_oracle(typed, skin):
         if typed else ((b"AA", 2.5, cm.POT_LJ_SHIFT, "lj_shift"),)
     s = capi.System(n)
     s.put(capi.F_X, x); s.put(capi.F_TYPE, types)
-    s.call("sepgpu_set_option", b"pair_tile", 1)
     sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
     s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
     for tsel, rc_, pot, kind in calls:
@@ -209,7 +202,7 @@ def test_pair_tile_forces_match_oracle(typed, skin):
                                  None, cm.ptr(fref), C.byref(rref))
         p = capi.lj_param(rc_, kind=kind)
         s.call("sepgpu_force_lj", C.byref(sys_), tsel, C.byref(p), cm.ALL, 1)
-    assert _opt(s, "list_pair") == 1
+    assert _opt(s, "list_f16") == 1
     f = s.get(capi.F_F); sc = s.scalars()
     assert cm.rel_force_err(f, fref) <= FT
     assert abs(sc.epot - rref.epot) <= 1e-10 * max(abs(rref.epot), 1.0)
@@ -218,9 +211,9 @@ def test_pair_tile_forces_match_oracle(typed, skin):
     s.close()
 
 
-def test_pair_tile_trajectory_follows_the_default_kernels():
-    """24 NVT steps (prg1-style loop through the C ABI) with the default kernels and with pair_tile, cell_order,
-    build_prune and fin_multi all on: same rebuild steps, energies equal to rounding growth."""
+def test_tile_trajectory_follows_the_global_row_kernels():
+    """24 NVT steps (prg1-style loop through the C ABI) with the tile kernels (default) and with global-index rows +
+    the gather kernel (tile_list = 0): same rebuild steps, energies equal to rounding growth."""
     x, L = _lj(12, seed=21, jitter=0.05)
     n = len(x)
     v = cm.velocities(n, 3.0, seed=22)
@@ -229,8 +222,7 @@ def test_pair_tile_trajectory_follows_the_default_kernels():
     for on in (0, 1):
         s = capi.System(n)
         s.put(capi.F_X, x); s.put(capi.F_V, v)
-        for k in (b"pair_tile", b"cell_order", b"build_prune", b"fin_multi"):     # everything scripts/gpu_r2_ab.sh calls "lj_all"
-            s.call("sepgpu_set_option", k, on)
+        s.call("sepgpu_set_option", b"tile_list", on)
         sys_ = capi.make_sys([L] * 3, cf, dt, skin=skin)
         p = capi.lj_param(cf, kind="lj_shift")
         s.call("sepgpu_set_alpha", 0, 0.0)
@@ -239,7 +231,7 @@ def test_pair_tile_trajectory_follows_the_default_kernels():
             s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
             if step == 0 or s.scalars().neighb_flag:
                 s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
-                assert _opt(s, "list_pair") == on
+                assert _opt(s, "list_f16") == on
             s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
             s.call("sepgpu_nosehoover", C.byref(sys_), 3.0, 0, 0.1)
             s.call("sepgpu_leapfrog", C.byref(sys_))
@@ -258,19 +250,19 @@ def test_pair_tile_trajectory_follows_the_default_kernels():
     assert np.abs(d).max() <= 1e-8
 
 
-def test_pair_tile_falls_back_to_per_atom_rows_for_coulomb_and_dpd():
-    """Coulomb and DPD walk per-atom rows: a charged system never gets pair rows, and a DPD call on a context that
-    holds pair rows rebuilds the list per atom -- results equal the default path."""
-    # water: charges present -> per-atom rows although the option is on
-    s, x, types, z, mol, L = _water_system(2, {"pair_tile": 1})
+def test_tile_list_falls_back_to_global_rows_for_coulomb_and_dpd():
+    """List Coulomb and DPD walk global-index rows: a charged system never gets tile rows, and a DPD call on a context
+    that holds tile rows rebuilds the list -- results equal the tile_list = 0 path."""
+    # water: charges present -> global-index rows although the option is on
+    s, x, types, z, mol, L = _water_system(2, {"tile_list": 1})
     f1, sc1 = _water_forces(s, L, 2.9, 0.25)
-    assert _opt(s, "list_pair") == 0
+    assert _opt(s, "list_f16") == 0
     s.close()
-    s, *_ = _water_system(2, {})
+    s, *_ = _water_system(2, {"tile_list": 0})
     f0, sc0 = _water_forces(s, L, 2.9, 0.25)
     s.close()
     assert np.array_equal(f0, f1) and sc0.epot == sc1.epot
-    # DPD after a Lennard-Jones call that built pair rows
+    # DPD after a Lennard-Jones call that built tile rows
     x, Lb = cm.lattice(12, 3.0, jitter=0.35, seed=13)
     n = len(x)
     pv = cm.velocities(n, 1.0, seed=14)
@@ -278,23 +270,22 @@ def test_pair_tile_falls_back_to_per_atom_rows_for_coulomb_and_dpd():
     for on in (0, 1):
         s = capi.System(n)
         s.put(capi.F_X, x); s.put(capi.F_PV, pv)
-        s.call("sepgpu_set_option", b"pair_tile", on)
+        s.call("sepgpu_set_option", b"tile_list", on)
         sys_ = capi.make_sys([Lb] * 3, 1.0, 0.02, skin=0.25)
         s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
         p = capi.lj_param(1.0, kind="lj")
         s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
-        assert _opt(s, "list_pair") == on
+        assert _opt(s, "list_f16") == on
         s.call("sepgpu_force_dpd", C.byref(sys_), b"AA", 1.0, 25.0, 1.0, 3.0, cm.ALL, 7, 3)
-        assert _opt(s, "list_pair") == 0
+        assert _opt(s, "list_f16") == 0
         res.append((s.get(capi.F_F), s.scalars().epot))
         s.close()
-    assert cm.rel_force_err(res[1][0], res[0][0]) <= 1e-12 and abs(res[1][1] - res[0][1]) <= 1e-12 * abs(res[0][1])
+    assert cm.rel_force_err(res[1][0], res[0][0]) <= 1e-10 and abs(res[1][1] - res[0][1]) <= 1e-10 * abs(res[0][1])
 
 
-@pytest.mark.parametrize("cell_order", [0, 1])
-def test_pair_tile_with_exclusions_butane_golden(cell_order):
+def test_tile_list_with_exclusions_butane_golden():
     """prg2-style butane against what the REFERENCE computed (tests/golden/butane_n4000.npz): same-molecule and
-    bonded-partner exclusions -- the membership flags of the pair rows carry each atom's own exclusions
+    bonded-partner exclusions through the tile builder and the tile kernel
     (reference source/sepprfrc.c:517-700, 703-740)."""
     import test_golden as tg
     g = tg.load("butane_n4000.npz")
@@ -303,14 +294,12 @@ def test_pair_tile_with_exclusions_butane_golden(cell_order):
     s = capi.System(n)
     s.put(capi.F_X, g["x0"]); s.put(capi.F_TYPE, np.full(n, ord("C"), dtype=np.uint8))
     tg.gpu_put_topology(s, t)
-    s.call("sepgpu_set_option", b"pair_tile", 1)
-    s.call("sepgpu_set_option", b"cell_order", cell_order)
     sys_ = tg.gpu_sys(g, n)
     p = capi.lj_param(float(g["cf"]), kind="lj_shift")
     for opt, pairs, fkey, ekey in ((cm.EXCL_SAME_MOL, "pairs_same_mol", "f_lj", "epot_lj"), (cm.EXCL_BONDED, "pairs_nonbonded", "f_lj_nonbonded", None)):
         s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
         s.call("sepgpu_neighb_build", C.byref(sys_), opt)
-        assert _opt(s, "list_pair") == 1
+        assert _opt(s, "list_f16") == 1
         assert np.array_equal(cm.pair_set(s.pairs()), g[pairs])
         s.call("sepgpu_force_lj", C.byref(sys_), b"CC", C.byref(p), opt, 1)
         assert cm.rel_force_err(s.get(capi.F_F), g[fkey]) <= FT
@@ -320,15 +309,13 @@ def test_pair_tile_with_exclusions_butane_golden(cell_order):
     s.close()
 
 
-# ---- cell_order: slots of a cell along a space-filling curve ---------------------------------------------------------
-@pytest.mark.parametrize("pair_tile,skin", [(0, 0.25), (1, 0.25), (1, 1.0)])
-def test_cell_order_keeps_pair_set_forces_and_half_list_length(pair_tile, skin):
-    """The in-cell slot order changes neither the pair set nor the forces, and the reference-style half-list length
-    (the SEP_NEIGHB = 3000 error condition, source/sepprfrc.c:499-501) is still counted by atom index."""
+def test_tile_list_index_order_unrelated_to_position_and_half_list_length():
+    """Atom indices shuffled against positions: pair set and forces unchanged, and the reference-style half-list length
+    (the SEP_NEIGHB = 3000 error condition, source/sepprfrc.c:499-501) is the same in both list formats."""
     x, L = _lj(14, seed=4)
-    x = np.ascontiguousarray(x[np.random.default_rng(8).permutation(len(x))])     # index order unrelated to position
+    x = np.ascontiguousarray(x[np.random.default_rng(8).permutation(len(x))])
     n = len(x)
-    cf = 2.5
+    cf, skin = 2.5, 0.25
     pp = np.ascontiguousarray(cm.oracle_pairs(x, L, cf, skin), dtype=np.int32)
     types = np.full(n, ord("A"), dtype=np.uint8)
     orc = cm.oracle(); length = cm.dvec3([L] * 3)
@@ -336,17 +323,16 @@ def test_cell_order_keeps_pair_set_forces_and_half_list_length(pair_tile, skin):
     orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pp), len(pp), b"AA", cf, cm.POT_LJ_SHIFT,
                              None, cm.ptr(fref), C.byref(rref))
     half = {}
-    for order in (0, 1):
+    for on in (0, 1):
         s = capi.System(n)
         s.put(capi.F_X, x)
-        s.call("sepgpu_set_option", b"cell_order", order)
-        s.call("sepgpu_set_option", b"pair_tile", pair_tile)
+        s.call("sepgpu_set_option", b"tile_list", on)
         sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
         s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
         s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
-        assert _opt(s, "list_pair") == pair_tile
+        assert _opt(s, "list_f16") == on
         assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(pp))
-        half[order] = _opt(s, "max_half")
+        half[on] = _opt(s, "max_half")
         p = capi.lj_param(cf, kind="lj_shift")
         s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
         f = s.get(capi.F_F); sc = s.scalars()
@@ -357,31 +343,9 @@ def test_cell_order_keeps_pair_set_forces_and_half_list_length(pair_tile, skin):
     assert half[0] >= 1
 
 
-# ---- build_prune: the tiled builder skips candidate cells beyond the cutoff ----------------------------------------
-@pytest.mark.parametrize("pair_tile,cell_order,skin", [(0, 0, 0.25), (0, 0, 1.0), (1, 0, 0.25), (1, 1, 0.25), (1, 1, 1.0)])
-def test_build_prune_changes_nothing_but_the_work(pair_tile, cell_order, skin):
-    """Pair set bit-exact against the oracle, half-list length and entry count equal to the unpruned build."""
-    x, L = _lj(14, seed=6, jitter=0.3)
-    ref_pairs = cm.pair_set(cm.oracle_pairs(x, L, 2.5, skin))
-    stats = []
-    for prune in (0, 1):
-        s = capi.System(len(x))
-        s.put(capi.F_X, x)
-        for k, v in (("build_prune", prune), ("pair_tile", pair_tile), ("cell_order", cell_order)):
-            s.call("sepgpu_set_option", k.encode(), v)
-        sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=skin)
-        s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
-        assert _opt(s, "list_pair") == pair_tile
-        assert np.array_equal(cm.pair_set(s.pairs()), ref_pairs)
-        sc = s.scalars()
-        stats.append((sc.npairs_listed, sc.max_neighb, _opt(s, "max_half"), _opt(s, "row_entries")))
-        s.close()
-    assert stats[0] == stats[1]
-    assert stats[0][0] == 2 * len(ref_pairs)
-
-
-def test_build_prune_with_exclusions_water():
-    s, x, types, z, mol, L = _water_system(2, {"build_prune": 1, "cell_order": 1})
+def test_tile_list_with_exclusions_water():
+    s, x, types, z, mol, L = _water_system(2, {})
+    s.put(capi.F_Z, np.zeros(len(x)))                         # uncharged copy: tile rows
     n = len(x)
     t = cm.Topo(n); t.molindex[:] = mol
     pairs = cm.oracle_pairs(x, L, 2.9, 0.25, opt=cm.EXCL_SAME_MOL, topo=t, max_pairs=4_000_000)
@@ -391,19 +355,17 @@ def test_build_prune_with_exclusions_water():
     s.close()
 
 
-# ---- corner cases of the opt-in list formats -------------------------------------------------------------------------
-def test_pair_tile_capacity_growth_odd_count_and_small_grids():
-    """A deliberately tiny row capacity grows transparently (union rows are longer than per-atom rows); an odd atom
-    count leaves the last atom a single row; a 3-cell grid takes the exact builder and therefore per-atom rows."""
-    x, L = _lj(13, seed=12)                                   # 2197 atoms: odd
-    assert len(x) % 2 == 1
+# ---- corner cases of the list formats ----------------------------------------------------------------------------------
+def test_tile_list_capacity_growth_and_small_grids():
+    """A deliberately tiny row capacity grows transparently; a 3-cell grid takes the exact builder and therefore
+    global-index rows and the gather kernel."""
+    x, L = _lj(13, seed=12)
     s = capi.System(len(x)); s.put(capi.F_X, x)
-    s.call("sepgpu_set_option", b"pair_tile", 1)
     s.call("sepgpu_set_option", b"neighb_cap", 8)
     sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
     s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
     s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
-    assert _opt(s, "list_pair") == 1 and _opt(s, "neighb_cap") > 8
+    assert _opt(s, "list_f16") == 1 and _opt(s, "neighb_cap") > 8
     pp = np.ascontiguousarray(cm.oracle_pairs(x, L, 2.5, 0.25), dtype=np.int32)
     assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(pp))
     types = np.full(len(x), ord("A"), dtype=np.uint8)
@@ -415,16 +377,26 @@ def test_pair_tile_capacity_growth_odd_count_and_small_grids():
     assert cm.rel_force_err(s.get(capi.F_F), fref) <= FT
     assert abs(s.scalars().epot - rref.epot) <= FT * abs(rref.epot)
     s.close()
-    # 3 cells per side: exact warp-per-atom builder, per-atom rows, default kernel
+    # 3 cells per side: exact warp-per-atom builder, global-index rows, gather kernel
     x, L = cm.lattice(9, 0.7, jitter=0.2, seed=8)
     s = capi.System(len(x)); s.put(capi.F_X, x)
-    for k in (b"pair_tile", b"cell_order", b"build_prune"):
-        s.call("sepgpu_set_option", k, 1)
     sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
     assert sys_.nsubbox[0] == 3
     s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
-    assert _opt(s, "list_pair") == 0
+    assert _opt(s, "list_f16") == 0
     assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(cm.oracle_pairs(x, L, 2.5, 0.25)))
+    s.close()
+
+
+def test_tile_list_dense_cells_shrink_the_tile():
+    """High density (DPD-like, 3 atoms per unit volume, cells of 1.25): more atoms per cell -> smaller bricks / tiles,
+    same pair set."""
+    x, Lb = cm.lattice(14, 3.0, jitter=0.35, seed=17)
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    sys_ = capi.make_sys([Lb] * 3, 1.0, 0.02, skin=0.25)
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+    assert _opt(s, "list_f16") == 1
+    assert np.array_equal(cm.pair_set(s.pairs()), cm.pair_set(cm.oracle_pairs(x, Lb, 1.0, 0.25)))
     s.close()
 
 
