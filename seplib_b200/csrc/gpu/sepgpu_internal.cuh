@@ -46,7 +46,7 @@ struct DevScalars {
     double pot_P[9], kin_P[9], pot_P_bond[9];
     double max_dist2;
     double sum_mv2;
-    double alpha[4];
+    double alpha[8];           // 0..3: sep_nosehoover multipliers (host slots); 4..6: history of _sep_nosehoover_type
     double mom[4];             // sum m v (3) + sum m, per sepgpu_reset_momentum
     int neighb_flag;           // skin trigger fired in the LAST integrator call
     int nbuild;
@@ -124,9 +124,15 @@ struct sepgpu_ctx {
     bool sorted_identity;  // brute mode: xs is x4 in original order
     bool need_atom_rows;   // a consumer of global-index rows (list Coulomb, DPD, the molecule-pair table) has been seen
     bool list_f16;         // the list holds rows of 16-bit tile slots (sepgpu_tile.cuh) for the tile force kernels
+    int ljt_ctas;          // option: register budget of k_lj_tile, CTAs per SM (3 or 4)
+    int row_sched;         // option: bank-conflict-aware order of the tile rows (k_row_schedule)
     int tile_list;         // option: build 16-bit tile rows when no consumer needs global-index rows (default 1)
     CellGrid tile_grid;    // grid / tile shape of the current list (every build, both formats)
     int tile_R, tile_count, tile_stage_used, tile_R_max;
+    int4 *tile_hdr;        // per tile: first home atom (sorted index), home atoms, staged atoms, image flag
+    unsigned *tile_src;    // per tile and slot: sorted index | image code << 26 (the staging order), stride tile_stride
+    size_t tile_hdr_cap, tile_src_cap;
+    int tile_stride;
     bool moved_since_build; // an integrator ran since the list was built
     long long list_gen;    // bumped by every successful list build (keys the derived lists below)
 

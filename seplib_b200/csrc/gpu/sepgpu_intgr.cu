@@ -774,10 +774,11 @@ k_nh_update(const double *__restrict__ partial, int nrows, DevScalars *scal, int
             scal->alpha[slot] = scal->alpha[slot] + dt / (tau_or_Q * tau_or_Q) * (temp / temp0 - 1.0);
         } else {
             const double g = 3.0 * v[1] - 3.0;
-            // history shift: alpha[0]<-alpha[1], alpha[1]<-alpha[2], alpha[2]<-old alpha[0] + ...
-            scal->alpha[0] = a1;
-            scal->alpha[1] = a2;
-            scal->alpha[2] = a0 + 2.0 * dt * (sum - g * temp0) / tau_or_Q;
+            // history shift: alpha[0]<-alpha[1], alpha[1]<-alpha[2], alpha[2]<-old alpha[0] + ...   (slots 4..6: the
+            // caller's sep_nosehoover multipliers live in slots 0..3 and must not be touched)
+            scal->alpha[4] = a1;
+            scal->alpha[5] = a2;
+            scal->alpha[6] = a0 + 2.0 * dt * (sum - g * temp0) / tau_or_Q;
         }
     }
 }
@@ -851,8 +852,8 @@ extern "C" int sepgpu_nosehoover_type(sepgpu_ctx *c, const sepgpu_sys *sys, char
     // the history is host-visible state of the caller: read it back (3 doubles)
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    alpha3[0] = c->scal_host->alpha[0]; alpha3[1] = c->scal_host->alpha[1]; alpha3[2] = c->scal_host->alpha[2];
-    c->pending_alpha_slot = 1;                 // the multiplier applied is alpha[1] (source/sepintgr.c:193)
+    alpha3[0] = c->scal_host->alpha[4]; alpha3[1] = c->scal_host->alpha[5]; alpha3[2] = c->scal_host->alpha[6];
+    c->pending_alpha_slot = 5;                 // the multiplier applied is alpha[1] of the history (source/sepintgr.c:193)
     c->pending_alpha_type = (unsigned char)type;
     return 0;
 }

@@ -291,6 +291,50 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 // ---- tiled build: the fast path is k_build_tile (sepgpu_neighb_tile.cuh) ---------------------------------------------
 #include "sepgpu_neighb_tile.cuh"
 
+// ---- bank-conflict-aware row order (option row_sched) ------------------------------------------------------------------
+// The tile force kernel fetches a neighbour with one LDS.128 (x, y: 16-byte columns, 8 per 128-byte row of shared memory)
+// and one LDS.64 (z: 8-byte columns, 16 per row).  With rows in slot order the 32 lanes of a warp hit random columns:
+// measured 8.3 / 4.7 wavefronts per instruction where 4 / 2 would do (ncu, round 2) -- the L1 data pipe, not the FP64
+// pipe, paces the kernel.  Here every row is re-ordered so that entry k of the thread in lane l names a slot of class
+// (l + k) mod 16 whenever the row still has one: the 16 lanes of a half-warp then read 16 different columns in the same
+// step.  Steps whose class has run out take a left-over entry of another class.  The pair set is unchanged; only the
+// order in which a thread visits its neighbours (and with it the rounding of its sums) changes.
+#define SCHED_MAXROW 512
+__global__ void __launch_bounds__(TILE_THREADS)
+k_row_schedule(unsigned short *__restrict__ nbr16, const int *__restrict__ cnt, const int *__restrict__ cell_start,
+               CellGrid G, int R, int npad)
+{
+    const int key0 = blockIdx.x * R * G.bx;
+    const int a0 = cell_start[key0], nhome = cell_start[key0 + R * G.bx] - a0;
+    for (int ab = threadIdx.x; ab < nhome; ab += TILE_THREADS) {
+        const int s = a0 + ab, l = ab & 15;
+        const int m = cnt[s];
+        if (m <= 16 || m > SCHED_MAXROW) continue;
+        unsigned short ent[SCHED_MAXROW], out[SCHED_MAXROW];
+        int n[16], start[17], cur[16];
+        for (int c = 0; c < 16; c++) n[c] = 0;
+        for (int k = 0; k < m; k++) { ent[k] = nbr16[nbr16_index(k, s, npad)]; n[ent[k] & 15]++; }
+        start[0] = 0;
+        for (int c = 0; c < 16; c++) { start[c + 1] = start[c] + n[c]; cur[c] = start[c]; }
+        unsigned short sorted[SCHED_MAXROW];
+        for (int k = 0; k < m; k++) sorted[cur[ent[k] & 15]++] = ent[k];
+        // scheduled steps
+        for (int c = 0; c < 16; c++) cur[c] = start[c];
+        for (int k = 0; k < m; k++) {
+            const int c = (l + k) & 15;
+            if (cur[c] < start[c + 1]) out[k] = sorted[cur[c]++]; else out[k] = 0xffff;     // hole
+        }
+        // left-over entries fill the holes, longest class first so that the tail stays mixed
+        int cc = 0;
+        for (int k = 0; k < m; k++) {
+            if (out[k] != 0xffff) continue;
+            while (cur[cc] >= start[cc + 1]) cc++;
+            out[k] = sorted[cur[cc]++];
+        }
+        for (int k = 0; k < m; k++) nbr16[nbr16_index(k, s, npad)] = out[k];
+    }
+}
+
 __global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->stage_needed = 0; s->stage_used = 0; s->aliased_seen = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
@@ -403,9 +447,21 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
                 c->tile_stage_cap = ((int)(3.0 * (R + 2) * (G.bx + 2) * mean_per_cell * 1.3) + 96 + 31) & ~31;
             }
             const int stage_cap = c->tile_stage_cap;
+            if ((size_t)ntile > c->tile_hdr_cap) {
+                if (c->tile_hdr) cudaFree(c->tile_hdr);
+                c->tile_hdr = NULL;
+                CUDA_TRY(cudaMalloc((void **)&c->tile_hdr, sizeof(int4) * (size_t)ntile));
+                c->tile_hdr_cap = (size_t)ntile;
+            }
+            if ((size_t)ntile * stage_cap > c->tile_src_cap) {
+                if (c->tile_src) cudaFree(c->tile_src);
+                c->tile_src = NULL;
+                CUDA_TRY(cudaMalloc((void **)&c->tile_src, sizeof(unsigned) * (size_t)ntile * stage_cap));
+                c->tile_src_cap = (size_t)ntile * stage_cap;
+            }
             const size_t smem = (size_t)(stage_cap + TILE_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
             if (smem > 200 * 1024) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
-#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, R, stage_cap
+#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, R, stage_cap, c->tile_hdr, c->tile_src
 #define TILE_LAUNCH(O, F)                                                                                                        \
     do {                                                                                                                         \
         CUDA_TRY(cudaFuncSetAttribute(k_build_tile<O, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
@@ -415,6 +471,8 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             else if (opt == SEPGPU_EXCL_SAME_MOL) { if (f16) TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, true); else TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, false); }
             else { if (f16) TILE_LAUNCH(SEPGPU_EXCL_BONDED, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, false); }
             built_f16 = f16;
+            if (f16 && c->row_sched)
+                k_row_schedule<<<ntile, TILE_THREADS, 0, c->stream>>>(reinterpret_cast<unsigned short *>(c->nbr), c->cnt, c->cell_start, G, R, c->npad);
 #undef TILE_LAUNCH
 #undef TILE_ARGS
         } else {
@@ -461,6 +519,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             c->list_f16 = built_f16;
             c->tile_grid = G; c->tile_R = R; c->tile_count = ntile;
             c->tile_stage_used = (c->scal_host->stage_used + 31) & ~31;
+            c->tile_stride = c->tile_stage_cap;
             c->moved_since_build = false;
             c->list_gen++;
             c->grid_n[0] = nx; c->grid_n[1] = ny; c->grid_n[2] = nz;
@@ -514,29 +573,23 @@ __global__ void k_export_pairs(const unsigned *__restrict__ nbr, const int *__re
     }
 }
 
-// rows of 16-bit tile slots: one CTA per tile rebuilds the tile's staging order and maps slots back to sorted indices
+// rows of 16-bit tile slots: the tile's staging table maps slots back to sorted indices
 __global__ void __launch_bounds__(TILE_THREADS)
 k_export_pairs_tile(const unsigned short *__restrict__ nbr16, const int *__restrict__ cnt, const int *__restrict__ order,
-                    const int *__restrict__ cell_start, CellGrid G, int R, int npad, int *__restrict__ out,
-                    long long max_pairs, unsigned long long *counter, const int *__restrict__ gid, int n_own)
+                    const int4 *__restrict__ tile_hdr, const unsigned *__restrict__ tile_src, int stride, int npad,
+                    int *__restrict__ out, long long max_pairs, unsigned long long *counter, const int *__restrict__ gid, int n_own)
 {
-    __shared__ TileLayout T;
-    if (G.dd) {
-        int x0, cy0, cz;
-        key_cell(blockIdx.x * R * G.bx, G, x0, cy0, cz);
-        if (cz == 0 || cz == G.nz - 1) return;
-    }
-    if (!tile_layout(T, G, R, cell_start)) return;
-    for (int ab = threadIdx.x; ab < T.nhome; ab += TILE_THREADS) {
-        const int s = T.a0 + ab;
+    const int4 hdr = tile_hdr[blockIdx.x];
+    const unsigned *src = tile_src + (size_t)blockIdx.x * stride;
+    for (int ab = threadIdx.x; ab < hdr.y; ab += TILE_THREADS) {
+        const int s = hdr.x + ab;
         int i = order[s];
         if (i >= n_own) continue;
         if (gid) i = gid[i];
         const int m = cnt[s];
         for (int k = 0; k < m; k++) {
             const int q = nbr16[nbr16_index(k, s, npad)] & TILE_SLOT_MASK;
-            const int cc = tile_cell_of_slot(T, q);
-            int j = order[T.beg[cc] + (q - T.off[cc])];
+            int j = order[src[q] & SEPGPU_INDEX_MASK];
             if (gid) j = gid[j];
             if (i < j) {
                 unsigned long long p = atomicAdd(counter, 1ULL);
@@ -555,7 +608,7 @@ extern "C" long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_p
     if (cudaMalloc((void **)&dout, sizeof(int) * 2 * (size_t)max_pairs) != cudaSuccess) return SEPGPU_ECUDA;
     if (cudaMalloc((void **)&dcount, sizeof(unsigned long long)) != cudaSuccess) { cudaFree(dout); return SEPGPU_ECUDA; }
     cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), c->stream);
-    if (c->list_f16) k_export_pairs_tile<<<c->tile_count, TILE_THREADS, 0, c->stream>>>(reinterpret_cast<const unsigned short *>(c->nbr), c->cnt, c->order, c->cell_start, c->tile_grid, c->tile_R, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
+    if (c->list_f16) k_export_pairs_tile<<<c->tile_count, TILE_THREADS, 0, c->stream>>>(reinterpret_cast<const unsigned short *>(c->nbr), c->cnt, c->order, c->tile_hdr, c->tile_src, c->tile_stride, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     else k_export_pairs<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->nbr, c->cnt, c->order, c->n, c->npad, dout, max_pairs, dcount, c->dd ? c->gid : NULL, c->n_own);
     unsigned long long h = 0;
     cudaMemcpyAsync(&h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream);

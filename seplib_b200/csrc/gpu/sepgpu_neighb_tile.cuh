@@ -19,6 +19,18 @@
 
 #include "sepgpu_tile.cuh"
 
+#include <cuda_pipeline.h>
+
+// bits [max(lo,0), min(hi,32)) of a 32-bit mask
+__device__ __forceinline__ unsigned bit_range(int lo, int hi)
+{
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > 32 ? 32 : hi;
+    if (hi <= lo) return 0u;
+    const unsigned upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+    return upto & ~((1u << lo) - 1u);
+}
+
 template <bool F16>
 struct RowWriter {
     unsigned long long lo, hi;
@@ -61,7 +73,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4)
 k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int *__restrict__ order,
              const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
              const int *__restrict__ excl_angle, const int *__restrict__ excl_dihed,
-             unsigned *__restrict__ nbr, int *__restrict__ cnt, DevScalars *scal, BuildParams P, int R, int stage_cap)
+             unsigned *__restrict__ nbr, int *__restrict__ cnt, DevScalars *scal, BuildParams P, int R, int stage_cap,
+             int4 *__restrict__ tile_hdr, unsigned *__restrict__ tile_src)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *cand = reinterpret_cast<float4 *>(smem_raw);                       // [stage_cap + TILE_PAD]
@@ -77,31 +90,51 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             const int key0 = blockIdx.x * R * G.bx;
             const int b = cell_start[key0], e = cell_start[key0 + R * G.bx];
             for (int q = b + threadIdx.x; q < e; q += TILE_THREADS) cnt[q] = 0;
+            if (threadIdx.x == 0) tile_hdr[blockIdx.x] = make_int4(0, 0, 0, 0);
             return;
         }
     }
     if (threadIdx.x < 3) s_red[threadIdx.x] = 0;
-    if (!tile_layout(T, G, R, cell_start)) return;
+    if (!tile_layout(T, G, R, cell_start)) {
+        if (threadIdx.x == 0) tile_hdr[blockIdx.x] = make_int4(0, 0, 0, 0);
+        return;
+    }
     const int total = T.total;
     if (total > stage_cap || total > TILE_MAX_SLOTS) {             // host grows the staging buffer (or shrinks the tile) and relaunches
         if (threadIdx.x == 0) atomicMax(&scal->stage_needed, total);
         return;
     }
-    if (threadIdx.x == 0) atomicMax(&scal->stage_used, total);
-    // ---- stage every candidate of the tile once ----
-    for (int q = threadIdx.x; q < total + TILE_PAD; q += TILE_THREADS) {
-        float4 f = make_float4(1e18f, 1e18f, 1e18f, 0.f);         // padding: never in range
-        if (q < total) {
-            const int c = tile_cell_of_slot(T, q);
-            const int j = T.beg[c] + (q - T.off[c]);
-            f = xf[j];
-            if (OPT == SEPGPU_EXCL_SAME_MOL) cand_mol[q] = __float_as_int(f.w);
+    if (threadIdx.x == 0) {
+        atomicMax(&scal->stage_used, total);
+        // what the force kernels need to know about this tile: home atoms [a0, a0 + nhome), staged atoms, image flag
+        tile_hdr[blockIdx.x] = make_int4(T.a0, T.nhome, total, T.any_image);
+    }
+    // ---- stage every candidate of the tile once: warps take cells, lanes take atoms; cp.async copies (all of a thread's
+    // loads in flight at once), then every thread finishes the slots it copied: image shift, list entry in .w ----
+    {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int c = wid; c < T.ncell; c += TILE_THREADS / 32) {
+            const int q0 = T.off[c], len = T.off[c + 1] - q0, j0 = T.beg[c];
+            for (int k = lane; k < len; k += 32) __pipeline_memcpy_async(&cand[q0 + k], &xf[j0 + k], 16);
+        }
+        __pipeline_commit();
+        if (threadIdx.x < TILE_PAD) cand[total + threadIdx.x] = make_float4(1e18f, 1e18f, 1e18f, 0.f);   // padding: never in range
+        __pipeline_wait_prior(0);
+        for (int c = wid; c < T.ncell; c += TILE_THREADS / 32) {
+            const int q0 = T.off[c], len = T.off[c + 1] - q0, j0 = T.beg[c];
             const unsigned code = T.code[c];
             const int wx = (int)(code % 3u) - 1, wy = (int)((code / 3u) % 3u) - 1, wz = (int)(code / 9u) - 1;
-            f.x += wx * P.fLx; f.y += wy * P.fLy; f.z += wz * P.fLz;
-            f.w = __uint_as_float((unsigned)j | (code << SEPGPU_SHIFT_BITS));
+            for (int k = lane; k < len; k += 32) {
+                float4 f = cand[q0 + k];
+                if (OPT == SEPGPU_EXCL_SAME_MOL) cand_mol[q0 + k] = __float_as_int(f.w);
+                f.x += wx * P.fLx; f.y += wy * P.fLy; f.z += wz * P.fLz;
+                const unsigned ent = (unsigned)(j0 + k) | (code << SEPGPU_SHIFT_BITS);
+                f.w = __uint_as_float(ent);
+                cand[q0 + k] = f;
+                // the staging order of this tile, for the force kernels: slot -> sorted index | image code
+                tile_src[(size_t)blockIdx.x * stage_cap + q0 + k] = ent;
+            }
         }
-        cand[q] = f;
     }
     __syncthreads();
 
@@ -115,8 +148,11 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             const float4 fi = xf[s];
             const int mol_i = __float_as_int(fi.w);
             int count = 0, half_count = 0;
-            RowWriter<F16> W;
-            W.init((unsigned)total);
+            RowWriter<false> W;
+            W.init(0u);
+            // F16: entries leave one by one as 16-bit stores into the row's current 128-bit chunk
+            unsigned short *row16 = reinterpret_cast<unsigned short *>(nbr) + (size_t)s * 8;
+            const bool img_tile = F16 && T.any_image != 0;
 #pragma unroll 1
             for (int r = 0; r < 9; r++) {
                 const int oy = r % 3 - 1, oz = r / 3 - 1;
@@ -126,6 +162,8 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                 const int wlo = T.off[c0], whi = T.off[c0 + 3];
                 const int cut_a = T.off[c0 + 1];
                 const int self_q = centre_row ? cut_a + (s - T.beg[c0 + 1]) : -1;
+                const int cut_b = T.off[c0 + 2];
+                const bool im0 = img_tile && T.code[c0] != 13, im1 = img_tile && T.code[c0 + 1] != 13, im2 = img_tile && T.code[c0 + 2] != 13;
 #pragma unroll 1
                 for (int q0 = wlo; q0 < whi; q0 += 32) {
 #ifdef SEPGPU_EMU
@@ -174,21 +212,37 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                     }
                     const int nacc = __popc(mask);
                     if (count + nacc <= P.cap) {
-                        while (mask) {
-                            const int b = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const unsigned g = __float_as_uint(cand[q0 + b].w);
-                            unsigned e = g;
-                            if (F16) e = (unsigned)(q0 + b) | ((g >> SEPGPU_SHIFT_BITS) != 13u ? TILE_SLOT_IMAGE : 0u);
-                            W.push(e, count, s, P.npad, nbr);
-                            count++;
+                        if (F16) {
+                            unsigned imgbits = 0;                        // candidates of this block that sit in a periodic image
+                            if (img_tile) {
+                                if (im0) imgbits |= bit_range(wlo - q0, cut_a - q0);
+                                if (im1) imgbits |= bit_range(cut_a - q0, cut_b - q0);
+                                if (im2) imgbits |= bit_range(cut_b - q0, whi - q0);
+                            }
+                            while (mask) {
+                                const int b = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                *row16 = (unsigned short)((unsigned)(q0 + b) | (((imgbits >> b) & 1u) << 15));
+                                count++;
+                                row16 += (count & 7) ? 1 : P.npad * 8 - 7;
+                            }
+                        } else {
+                            while (mask) {
+                                const int b = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                W.push(__float_as_uint(cand[q0 + b].w), count, s, P.npad, nbr);
+                                count++;
+                            }
                         }
                     } else {
                         count += nacc;                                   // overflow: the host grows the list and rebuilds
                     }
                 }
             }
-            if (count <= P.cap) W.finish(count, s, P.npad, nbr);
+            if (count <= P.cap) {
+                if (F16) { for (int k = count; k & 7; k++) *row16++ = (unsigned short)total; }   // pad the last chunk with the far-away slot
+                else W.finish(count, s, P.npad, nbr);
+            }
             cnt[s] = min(count, P.cap);
             blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += count;
         }

@@ -136,6 +136,8 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->tsort) cudaFree(c->tsort);
     if (c->xq) cudaFree(c->xq);
     if (c->fin_ticket) cudaFree(c->fin_ticket);
+    if (c->tile_hdr) cudaFree(c->tile_hdr);
+    if (c->tile_src) cudaFree(c->tile_src);
     if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
@@ -695,6 +697,8 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
     if (!strcmp(name, "step_fold")) { if (!value) { int rs = sepgpu_settle(c); if (rs) return rs; } c->step_fold = value != 0; return 0; }
     if (!strcmp(name, "fin_multi")) { c->fin_multi = value != 0; return 0; }
+    if (!strcmp(name, "ljt_ctas")) { if (value != 3 && value != 4) return SEPGPU_EINVAL; c->ljt_ctas = (int)value; return 0; }
+    if (!strcmp(name, "row_sched")) { c->row_sched = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "tile_list")) { c->tile_list = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
     if (!strcmp(name, "typed_sublist")) { c->typed_sublist = value != 0; return 0; }
@@ -728,6 +732,7 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "coulomb_kernel")) *value = c->coulomb_kernel;
     else if (!strcmp(name, "typed_sublist")) *value = c->typed_sublist;
     else if (!strcmp(name, "tile_list")) *value = c->tile_list;
+    else if (!strcmp(name, "row_sched")) *value = c->row_sched;
     else if (!strcmp(name, "fin_multi")) *value = c->fin_multi;
     else if (!strcmp(name, "step_fold")) *value = c->step_fold;
     else if (!strcmp(name, "list_f16")) *value = c->list_valid && c->list_f16 ? 1 : 0;       // rows of 16-bit tile slots

@@ -130,6 +130,37 @@ def test_nosehoover_type_and_momentum_reset():
     s.close()
 
 
+def test_nosehoover_and_type_thermostat_in_the_same_step():
+    """sep_nosehoover's multiplier (device slot 0..3) must survive a _sep_nosehoover_type call in the same step: the
+    type thermostat keeps its 3-value history in slots of its own (reference source/sepintgr.c:149-198)."""
+    x, L = cm.lattice(8, 0.8, jitter=0.1, seed=3)
+    n = len(x)
+    rng = np.random.default_rng(14)
+    types = np.where(rng.random(n) < 0.5, ord("B"), ord("A")).astype(np.uint8)
+    m = np.where(types == ord("B"), 2.5, 1.0)
+    v = cm.velocities(n, 1.3, seed=15, m=m)
+    f0 = rng.normal(size=(n, 3))
+    orc = cm.oracle()
+    fref = f0.copy(); hist = np.array([0.05, 0.07, 0.02])
+    a_ref = orc.orc_nosehoover(n, cm.ptr(v), cm.ptr(m), cm.ptr(fref), 1.0, 0.3, 0.1, 0.005)
+    orc.orc_nosehoover_type(n, cm.ptr(v), cm.ptr(m), cm.ptr(types), b"B", cm.ptr(fref), 1.1, cm.ptr(hist), 10.0, 0.005)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_V, v); s.put(capi.F_TYPE, types); s.put(capi.F_M, m)
+    s.call("sepgpu_reset_force"); s.put(capi.F_F, f0)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    s.call("sepgpu_set_alpha", 0, 0.3)
+    s.call("sepgpu_set_alpha", 1, 0.77)                    # a second caller-owned multiplier, not used in this step
+    s.call("sepgpu_nosehoover", C.byref(sys_), 1.0, 0, 0.1)
+    a3 = (C.c_double * 3)(0.05, 0.07, 0.02)
+    s.call("sepgpu_nosehoover_type", C.byref(sys_), b"B", 1.1, a3, 10.0)
+    assert np.abs(np.array(a3[:]) - hist).max() <= 1e-13 * np.abs(hist).max()
+    assert np.abs(s.get(capi.F_F) - fref).max() <= 1e-12 * np.abs(fref).max()
+    sc = s.scalars()
+    assert abs(sc.alpha[0] - a_ref) <= 1e-13 * abs(a_ref)
+    assert sc.alpha[1] == 0.77
+    s.close()
+
+
 def test_error_paths():
     """Atom outside [0,L) -> the reference's 'Index larger than array length' class of error; bonded
     exclusion without partner tables; list force without anything to build from is fine (auto build)."""
