@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsep.so")
+LIB_PATH = os.environ.get("SEPLIB_SO") or os.path.join(HERE, "libsep.so")      # SEPLIB_SO: A/B builds of the same library (scripts/)
 
 SEP_BOND, SEP_ANGLE, SEP_DIHED = 10, 10, 20
 SEP_ALL, SEP_EXCL_BONDED, SEP_EXCL_SAME_MOL = 1, 2, 3

@@ -94,7 +94,7 @@ template <bool TYPED, bool STORE, int MINB>
 __global__ void __launch_bounds__(TILE_THREADS, MINB)
 k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, const int4 *__restrict__ tile_hdr, const unsigned *__restrict__ tile_src,
-          d4 *__restrict__ f4, int stride, int npad, int stage_cap, LJDev P, BoxDev B, double isig,
+          const int *__restrict__ row_perm, d4 *__restrict__ f4, int stride, int npad, int stage_cap, LJDev P, BoxDev B, double isig,
           double *__restrict__ partial)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,7 +160,7 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
         for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
         const int ab = base + threadIdx.x;
         if (ab < nhome) {
-            const int s = a0 + ab;
+            const int s = row_perm[a0 + ab];                         // atoms of the tile by decreasing row length
             const d4 pi = xs[s];
             int m = cnt[s];
             int ti = 0;
@@ -219,7 +219,7 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const LJDev &P, const BoxDev &B, bool t
     do {                                                                                                                         \
         CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k_lj_tile<TY, ST, MB><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt,   \
-            c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial);             \
+            c->order, c->tile_hdr, c->tile_src, c->row_perm, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial);             \
     } while (0)
 #define LJT_LAUNCH(TY, ST) do { if (c->ljt_ctas == 4) LJT_LAUNCH3(TY, ST, 4); else LJT_LAUNCH3(TY, ST, 3); } while (0)
     if (typed) { if (store) LJT_LAUNCH(true, true); else LJT_LAUNCH(true, false); }

@@ -77,8 +77,11 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->prefilter = 1;
     c->overlap = 0;
     c->single_type = 'A';
-    c->coulomb_kernel = 1;
-    c->typed_sublist = 0;
+    // defaults settled on a B200 in round 2 (scripts/gpu_r2_ab.sh, profiles/r02_optin_ab.txt)
+    c->coulomb_kernel = 2;
+    c->typed_sublist = 1;
+    c->step_fold = 1;
+    c->fin_multi = 1;
     c->tile_list = 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 
@@ -138,6 +141,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->fin_ticket) cudaFree(c->fin_ticket);
     if (c->tile_hdr) cudaFree(c->tile_hdr);
     if (c->tile_src) cudaFree(c->tile_src);
+    if (c->row_perm) cudaFree(c->row_perm);
     if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,

@@ -70,8 +70,8 @@ def main():
                     pr = cm.pair_set(s.pairs(max_pairs=int(sc.npairs_listed) + 16))
                 if step == 0:
                     lp = C.c_longlong(-1)
-                    s.call("sepgpu_get_option", b"list_pair", C.byref(lp))
-                    shared["list_pair"] = lp.value
+                    s.call("sepgpu_get_option", b"list_f16", C.byref(lp))
+                    shared["list_f16"] = lp.value
                     s.call("sepgpu_get_option", b"dd_p2p", C.byref(lp))
                     shared["p2p"] = lp.value
                 s.call("sepgpu_nosehoover", C.byref(gsys), temp, 0, tau)
@@ -138,10 +138,10 @@ def main():
     err = np.abs(full - ref.get(capi.F_X)).max()
     builds = ref.scalars().nbuild
     ref.close()
-    ok = ok and err <= 1e-7 and builds >= 3 and shared.get("list_pair") == int(opts.get("pair_tile", 0))
+    ok = ok and err <= 1e-7 and builds >= 3 and shared.get("list_f16") == int(opts.get("tile_list", 1))
     ok = ok and shared.get("p2p") == (0 if os.environ.get("SEPGPU_EMU_NO_IPC") == "1" or os.environ.get("SEPGPU_DD_P2P") == "0" else 1)
     print(f"dd_threads: world={WORLD} n={n} steps={nsteps} layers={nz} builds={builds} pair-set checks={checked} "
-          f"max|dx|={err:.2e} list_pair={shared.get('list_pair')} p2p={shared.get('p2p')} own/halo(rank0)={shared['final'][0][2]}/{shared['final'][0][3]} opts={opts} -> {'OK' if ok else 'FAIL'}")
+          f"max|dx|={err:.2e} list_f16={shared.get('list_f16')} p2p={shared.get('p2p')} own/halo(rank0)={shared['final'][0][2]}/{shared['final'][0][3]} opts={opts} -> {'OK' if ok else 'FAIL'}")
     return 0 if ok else 1
 
 

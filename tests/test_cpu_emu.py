@@ -41,12 +41,11 @@ def test_gpu_parity_tests_pass_on_the_emulated_kernels():
     assert n >= 40, n
 
 
-def test_optin_kernels_pass_on_the_emulator():
-    """coulomb_kernel=2, typed_sublist=1, pair_tile=1, cell_order=1 (tests/test_gpu_zzz_options.py): skipped on hardware until a GPU run has
-    confirmed them, exercised here on every CPU round."""
-    n = _run(["tests/test_gpu_zzz_options.py", "-m", "gpu", "-q", "-n", WORKERS, "-p", "no:cacheprovider"],
-             env={"SEPGPU_TEST_UNVERIFIED": "1"})
-    assert n >= 31, n
+def test_kernel_options_pass_on_the_emulator():
+    """The kernel options and list formats (tests/test_gpu_zzz_options.py): tile rows against global-index rows, the
+    alternative Coulomb / sub-list / finalisation kernels against the ones they replaced."""
+    n = _run(["tests/test_gpu_zzz_options.py", "-m", "gpu", "-q", "-n", WORKERS, "-p", "no:cacheprovider"])
+    assert n >= 25, n
 
 
 def test_two_rank_decomposition_on_the_emulator():
@@ -54,10 +53,10 @@ def test_two_rank_decomposition_on_the_emulator():
     ranks' pair sets == single-domain set, per-step sums, trigger steps, final positions, atom conservation over several
     rebuilds with migration -- the checks tests/dd_check.py makes on two GPUs.  Both transport paths: peer memory (the
     emulator hands out in-process IPC handles; the two ranks' kernels run concurrently and meet at release/acquire
-    flags), also with pair-tile lists and the folded step, and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp).  The three runs go side
-    by side."""
-    cases = {"peer-memory": ("", "0"), "peer-memory+options": ("step_fold=1,pair_tile=1,cell_order=1,fin_multi=1", "0"),
-             "nccl-path": ("step_fold=1", "1")}
+    flags), also with global-index rows and the unfolded step, and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp).
+    The three runs go side by side."""
+    cases = {"peer-memory": ("", "0"), "peer-memory+old-kernels": ("step_fold=0,tile_list=0,fin_multi=0", "0"),
+             "nccl-path": ("", "1")}
     procs = {k: subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "14", opts],
                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
                                  env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc))
@@ -77,19 +76,3 @@ def test_smoke_entry_point_on_the_emulator():
             "g.smoke()\n") % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "smoke ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
-
-
-def test_work_model_numbers_quoted_in_the_design_document():
-    """tests/emu/model_check.py: the emulator's gather model reproduces the ~20 distinct lines per warp-wide gather that ncu
-    measured for k_lj_list on B200 (profiles/r01_k_lj_list_ncu_full.txt), and gives the work reductions DESIGN.md section 3a
-    quotes for the pair-tile list and the pruned list build."""
-    import json
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "model_check.py")], capture_output=True, text=True,
-                       timeout=900, cwd=ROOT)
-    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
-    m = json.loads(r.stdout.strip().splitlines()[-1])
-    assert 18.0 <= m["per_atom"]["lines_per_request"] <= 24.0
-    assert m["pair_tile"]["wavefronts_per_atom"] <= 0.85 * m["per_atom"]["wavefronts_per_atom"]
-    assert m["pair_tile"]["lane_loads_per_atom"] <= 0.75 * m["per_atom"]["lane_loads_per_atom"]
-    assert m["pruned"]["candidates_per_atom"] <= 0.85 * m["per_atom"]["candidates_per_atom"]
-    assert m["pruned"]["wavefronts_per_atom"] == m["per_atom"]["wavefronts_per_atom"]        # same list, same gathers

@@ -44,8 +44,9 @@ def _water_forces(s, L, cf, skin, lj=True, coulomb=True):
     return s.get(capi.F_F), s.scalars()
 
 
-@pytest.mark.parametrize("opts", [{"coulomb_kernel": 2}, {"typed_sublist": 1}, {"coulomb_kernel": 2, "typed_sublist": 1}],
-                         ids=["coulomb2", "sublist", "both"])
+@pytest.mark.parametrize("opts", [{"coulomb_kernel": 1, "typed_sublist": 0}, {"coulomb_kernel": 2, "typed_sublist": 0},
+                                  {"coulomb_kernel": 1, "typed_sublist": 1}, {"coulomb_kernel": 2, "typed_sublist": 1}],
+                         ids=["first-kernels", "coulomb2", "sublist", "both"])
 def test_water_forces_with_optin_kernels_match_oracle(opts):
     """prg3-style water step (typed 'OO' Lennard-Jones + shifted-force Coulomb on the same list) against the oracle
     (reference source/sepprfrc.c:94-224, source/sepcoulomb.c:96-160)."""
@@ -72,7 +73,7 @@ def test_optin_kernels_agree_with_the_default_ones_over_steps():
     to rounding while the list is rebuilt along the way (the sub-list must follow every rebuild)."""
     cf, skin, dt = 2.9, 0.25, 5e-4
     runs = []
-    for opts in ({}, {"coulomb_kernel": 2, "typed_sublist": 1}):
+    for opts in ({"coulomb_kernel": 1, "typed_sublist": 0}, {"coulomb_kernel": 2, "typed_sublist": 1}):
         s, x, types, z, mol, L = _water_system(2, opts)
         rng = np.random.default_rng(3)
         s.put(capi.F_M, np.full(len(x), 1e6))                       # no bonded terms here: very heavy atoms, near-ballistic motion
@@ -481,7 +482,7 @@ def test_step_fold_equals_the_unfolded_step(peek):
     """12 NVT steps with three typed force calls per step: every scalar, the multiplier, the rebuild steps and the final
     state equal the default sequence of kernels to rounding; reading scalars or forces between the calls settles what is
     pending and sees the same values."""
-    a = _nvt_loop({}, 12, peek)
+    a = _nvt_loop({"step_fold": 0, "fin_multi": 0}, 12, peek)
     b = _nvt_loop({"step_fold": 1, "fin_multi": 1 if peek else 0}, 12, peek)
     assert a[0][-1][7] >= 2
     for k, (ra, rb) in enumerate(zip(a[0], b[0])):
