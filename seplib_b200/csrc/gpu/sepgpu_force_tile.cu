@@ -30,8 +30,8 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 template <bool TYPED, bool IMAGE>
 __device__ __forceinline__ void lj_tile_pair(double xi, double yi, double zi, int ti, const double2 *__restrict__ XY,
                                              const double *__restrict__ Z, const unsigned char *__restrict__ CODE,
-                                             const unsigned char *__restrict__ TYPE, unsigned e, const LJDev &P,
-                                             const BoxDev &B, double &fx, double &fy, double &fz, double &u, int &nin, double *v)
+                                             const unsigned char *__restrict__ TYPE, const double *__restrict__ SHIFT,
+                                             unsigned e, const LJDev &P, double &fx, double &fy, double &fz, double &u, int &nin, double *v)
 {
     const unsigned j = IMAGE ? (e & TILE_SLOT_MASK) : e;
     const double2 a = XY[j];
@@ -52,10 +52,9 @@ __device__ __forceinline__ void lj_tile_pair(double xi, double yi, double zi, in
     fx = fma(f, dx, fx); fy = fma(f, dy, fy); fz = fma(f, dz, fz);
     if (IMAGE) {
         if (e & TILE_SLOT_IMAGE) {                                   // boundary-crossing pair: - g (x) S
-            double sx = 0.0, sy = 0.0, sz = 0.0;
-            apply_image(CODE[j], B, sx, sy, sz);                     // s = -S
+            const double *sh = SHIFT + 3 * CODE[j];                  // -S of the partner's image, from the CTA's 27-entry table
             const double g = P.eps48 * f;                            // (eps48 carries the 1/sigma of the scaled coordinates)
-            virial_add(v, g * dx, g * dy, g * dz, sx, sy, sz);
+            virial_add(v, g * dx, g * dy, g * dz, sh[0], sh[1], sh[2]);
         }
     }
 }
@@ -65,7 +64,7 @@ template <bool TYPED, bool IMAGE>
 __device__ __forceinline__ void lj_tile_row(double xi, double yi, double zi, int ti, int m, const uint4 *__restrict__ row, int npad,
                                             const double2 *__restrict__ XY, const double *__restrict__ Z,
                                             const unsigned char *__restrict__ CODE, const unsigned char *__restrict__ TYPE,
-                                            const LJDev &P, const BoxDev &B, double &fx, double &fy, double &fz, double &u, int &nin, double *v)
+                                            const double *__restrict__ SHIFT, const LJDev &P, double &fx, double &fy, double &fz, double &u, int &nin, double *v)
 {
     // rows are padded to whole chunks of 8 with the tile's far-away pad slot: no tail handling
     const int nch = (m + 7) >> 3;
@@ -75,7 +74,7 @@ __device__ __forceinline__ void lj_tile_row(double xi, double yi, double zi, int
     for (int c = 0; c < nch; c++) {
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (c + 1 < nch) nxt = __ldcs(row + (size_t)(c + 1) * npad);
-#define LJT_PAIR(E) lj_tile_pair<TYPED, IMAGE>(xi, yi, zi, ti, XY, Z, CODE, TYPE, (E), P, B, fx, fy, fz, u, nin, v)
+#define LJT_PAIR(E) lj_tile_pair<TYPED, IMAGE>(xi, yi, zi, ti, XY, Z, CODE, TYPE, SHIFT, (E), P, fx, fy, fz, u, nin, v)
         LJT_PAIR(cur.x & 0xffffu); LJT_PAIR(cur.x >> 16);
         LJT_PAIR(cur.y & 0xffffu); LJT_PAIR(cur.y >> 16);
         LJT_PAIR(cur.z & 0xffffu); LJT_PAIR(cur.z >> 16);
@@ -94,7 +93,7 @@ template <bool TYPED, bool STORE, int MINB>
 __global__ void __launch_bounds__(TILE_THREADS, MINB)
 k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, const int4 *__restrict__ tile_hdr, const unsigned *__restrict__ tile_src,
-          const int *__restrict__ row_perm, d4 *__restrict__ f4, int stride, int npad, int stage_cap, LJDev P, BoxDev B, double isig,
+          d4 *__restrict__ f4, int stride, int npad, int stage_cap, LJDev P, BoxDev B, double isig,
           double *__restrict__ partial)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -104,6 +103,7 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
     unsigned char *CODE = reinterpret_cast<unsigned char *>(Z + nslot);           // [nslot]
     unsigned char *TYPE = CODE + nslot;                                           // [nslot] (typed calls only)
     __shared__ double red[SEPGPU_NPART_F * (TILE_THREADS / 32)];
+    __shared__ double SHIFT[27 * 3];                                              // -S per image code
 
     const int4 hdr = tile_hdr[blockIdx.x];
     const int a0 = hdr.x, nhome = hdr.y, total = hdr.z;
@@ -141,6 +141,11 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
                 }
             }
         }
+        if (threadIdx.x < 27) {
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            apply_image((int)threadIdx.x, B, sx, sy, sz);
+            SHIFT[3 * threadIdx.x] = sx; SHIFT[3 * threadIdx.x + 1] = sy; SHIFT[3 * threadIdx.x + 2] = sz;
+        }
         if (threadIdx.x < TILE_PAD) {                                // pad slots: far away, never in range
             XY[total + threadIdx.x] = make_double2(1e9, 1e9);
             Z[total + threadIdx.x] = 1e9;
@@ -160,7 +165,7 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
         for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
         const int ab = base + threadIdx.x;
         if (ab < nhome) {
-            const int s = row_perm[a0 + ab];                         // atoms of the tile by decreasing row length
+            const int s = a0 + ab;
             const d4 pi = xs[s];
             int m = cnt[s];
             int ti = 0;
@@ -171,8 +176,8 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
             const double xi = pi.x * isig, yi = pi.y * isig, zi = pi.z * isig;
             double fx = 0.0, fy = 0.0, fz = 0.0, u = 0.0;
             int nin = 0;
-            if (image) lj_tile_row<TYPED, true>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, P, B, fx, fy, fz, u, nin, acc + 2);
-            else       lj_tile_row<TYPED, false>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, P, B, fx, fy, fz, u, nin, acc + 2);
+            if (image) lj_tile_row<TYPED, true>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, SHIFT, P, fx, fy, fz, u, nin, acc + 2);
+            else       lj_tile_row<TYPED, false>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, SHIFT, P, fx, fy, fz, u, nin, acc + 2);
             const int i = order[s];
             fx *= P.eps48; fy *= P.eps48; fz *= P.eps48;
             if (STORE) {
@@ -219,7 +224,7 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const LJDev &P, const BoxDev &B, bool t
     do {                                                                                                                         \
         CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k_lj_tile<TY, ST, MB><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt,   \
-            c->order, c->tile_hdr, c->tile_src, c->row_perm, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial);             \
+            c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial);             \
     } while (0)
 #define LJT_LAUNCH(TY, ST) do { if (c->ljt_ctas == 4) LJT_LAUNCH3(TY, ST, 4); else LJT_LAUNCH3(TY, ST, 3); } while (0)
     if (typed) { if (store) LJT_LAUNCH(true, true); else LJT_LAUNCH(true, false); }

@@ -133,7 +133,6 @@ struct sepgpu_ctx {
     unsigned *tile_src;    // per tile and slot: sorted index | image code << 26 (the staging order), stride tile_stride
     size_t tile_hdr_cap, tile_src_cap;
     int tile_stride;
-    int *row_perm;         // [npad] thread order of the tile force kernels inside each tile: atoms by decreasing row length
     bool moved_since_build; // an integrator ran since the list was built
     long long list_gen;    // bumped by every successful list build (keys the derived lists below)
 

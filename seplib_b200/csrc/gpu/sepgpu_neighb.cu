@@ -459,10 +459,9 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
                 CUDA_TRY(cudaMalloc((void **)&c->tile_src, sizeof(unsigned) * (size_t)ntile * stage_cap));
                 c->tile_src_cap = (size_t)ntile * stage_cap;
             }
-            if (!c->row_perm) CUDA_TRY(cudaMalloc((void **)&c->row_perm, sizeof(int) * (size_t)c->npad));
             const size_t smem = (size_t)(stage_cap + TILE_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
             if (smem > 200 * 1024) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
-#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, R, stage_cap, c->tile_hdr, c->tile_src, c->row_perm
+#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, R, stage_cap, c->tile_hdr, c->tile_src
 #define TILE_LAUNCH(O, F)                                                                                                        \
     do {                                                                                                                         \
         CUDA_TRY(cudaFuncSetAttribute(k_build_tile<O, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \

@@ -77,14 +77,13 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
              const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
              const int *__restrict__ excl_angle, const int *__restrict__ excl_dihed,
              unsigned *__restrict__ nbr, int *__restrict__ cnt, DevScalars *scal, BuildParams P, int R, int stage_cap,
-             int4 *__restrict__ tile_hdr, unsigned *__restrict__ tile_src, int *__restrict__ row_perm)
+             int4 *__restrict__ tile_hdr, unsigned *__restrict__ tile_src)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *cand = reinterpret_cast<float4 *>(smem_raw);                       // [stage_cap + TILE_PAD]
     int *cand_mol = reinterpret_cast<int *>(cand + stage_cap + TILE_PAD);      // [stage_cap + TILE_PAD] (SAME_MOL only)
     __shared__ TileLayout T;
     __shared__ int s_red[3];
-    __shared__ int s_cnt[TILE_THREADS];
 
     const CellGrid G = P.G;
     {
@@ -146,7 +145,6 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
     int blk_max = 0, blk_half = 0, blk_sum = 0;
     for (int ab = 0; ab < nhome; ab += TILE_THREADS) {
         const int s = a0 + ab + threadIdx.x;
-        int my_count = -1;
         if (s < a0 + nhome) {
             const int h = tile_home_cell(T, s, nh);                // my home cell inside the tile
             const int hx = h % G.bx, hy = h / G.bx;
@@ -249,22 +247,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                 else W.finish(count, s, P.npad, nbr);
             }
             cnt[s] = min(count, P.cap);
-            my_count = count;
             blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += count;
-        }
-        // Thread order of the force kernels: the atoms of this pass by decreasing row length (ties by position), so that
-        // the 32 lanes of a warp walk rows of nearly the same length.  row_perm[a0 + ab + rank] = sorted index.
-        __syncthreads();
-        s_cnt[threadIdx.x] = my_count;
-        __syncthreads();
-        if (my_count >= 0) {
-            const int npass = min(TILE_THREADS, nhome - ab);
-            int rank = 0;
-            for (int j = 0; j < npass; j++) {
-                const int cj = s_cnt[j];
-                rank += (cj > my_count) || (cj == my_count && j < (int)threadIdx.x);
-            }
-            row_perm[a0 + ab + rank] = s;
         }
     }
     // block statistics: warp reduce, then shared atomics, then three global atomics per CTA

@@ -141,7 +141,6 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->fin_ticket) cudaFree(c->fin_ticket);
     if (c->tile_hdr) cudaFree(c->tile_hdr);
     if (c->tile_src) cudaFree(c->tile_src);
-    if (c->row_perm) cudaFree(c->row_perm);
     if (c->randn4) cudaFree(c->randn4);
     void *ptrs[] = {c->x4, c->v4, c->f4, c->xn4, c->pv4, c->pa4, c->cr4, c->crossings, c->z, c->type,
                     c->molindex, c->excl_bond, c->excl_angle, c->excl_dihed, c->zs, c->xs, c->xf, c->order,
