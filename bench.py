@@ -134,6 +134,23 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation on the host cores
 # ---------------------------------------------------------------------------------------------------
+def raise_stack_limit():
+    """The reference keeps per-atom scratch in variable-length stack arrays (e.g. the neighbour builder's index[npart],
+    source/sepprfrc.c:428); at 1 M atoms that overflows the default 8 MB stack.  Raise the soft limit of this process (and
+    of the OpenMP workers the reference will start) before its library is loaded."""
+    import resource
+    try:
+        soft, hard = resource.getrlimit(resource.RLIMIT_STACK)
+        want = 1 << 30
+        if hard != resource.RLIM_INFINITY:
+            want = min(want, hard)
+        if soft != resource.RLIM_INFINITY and soft < want:
+            resource.setrlimit(resource.RLIMIT_STACK, (want, hard))
+    except (ValueError, OSError) as e:
+        log("could not raise the stack limit:", e)
+    os.environ.setdefault("OMP_STACKSIZE", "512M")
+
+
 def cpu_reference_arm(ncell, rho, rc, skin, dt, temp, tau, target_seconds, threads):
     """Runs the prg1/prg4-style loop through the reference API (oracle/_ref/libsep_ref_fast.so, built from
     the unmodified reference sources with its shipped flags -Ofast -fopenmp).  Falls back to the C port
@@ -220,6 +237,71 @@ def cpu_reference_arm(ncell, rho, rc, skin, dt, temp, tau, target_seconds, threa
                       f"in {el:.1f} s, epot/N={epot:.4f}",
             "seconds": el, "steps": steps, "natoms": n}
     return value, info
+
+
+def cpu_arm_child(kind, **kw):
+    """Runs one CPU arm (the reference's own code on the host cores) in a CHILD process whose stack limit is raised before
+    exec: the reference keeps per-atom scratch in variable-length stack arrays (source/sepprfrc.c:428), 1 M atoms overflow
+    the default 8 MB, and a limit raised inside a process that already mapped CUDA / torch cannot grow the main stack."""
+    import resource
+
+    def big_stack():
+        try:
+            soft, hard = resource.getrlimit(resource.RLIMIT_STACK)
+            want = resource.RLIM_INFINITY if hard == resource.RLIM_INFINITY else hard
+            resource.setrlimit(resource.RLIMIT_STACK, (want, hard))
+        except (ValueError, OSError):
+            pass
+
+    env = dict(os.environ)
+    env.setdefault("OMP_STACKSIZE", "512M")
+    req = json.dumps(dict(kind=kind, **kw))
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-arm-json", req], capture_output=True, text=True,
+                       preexec_fn=big_stack, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("CPU arm failed (rc %d): %s" % (r.returncode, (r.stdout + r.stderr)[-400:]))
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def cpu_arm_main(req):
+    """child side of cpu_arm_child"""
+    q = json.loads(req)
+    if q.pop("kind") == "lj":
+        _, info = cpu_reference_arm(**q)
+    else:
+        _, info = mol_cpu_arm(**q)
+    print(json.dumps(info))
+    return 0
+
+
+def cpu_matrix(rho, rc, dt, temp, tau, seconds_each, skip_big):
+    """SURVEY.md section 8d / BASELINE.md section 3: the reference's OpenMP build, prg4-style LJ at N = 10 648 / 110 592 /
+    1 000 000, one thread and all cores, skin 0.25 and 1.0 (prg4's setting), plus prg5-style butane.  Bounded samples."""
+    rows = []
+    allc = host_cores()
+    plan = [(22, 1, 0.25), (22, allc, 0.25), (22, allc, 1.0), (48, 1, 0.25), (48, 1, 1.0), (48, allc, 0.25), (48, allc, 1.0)]
+    if not skip_big:
+        plan.append((100, allc, 1.0))
+    for ncell, thr, skin in plan:
+        try:
+            info = cpu_arm_child("lj", ncell=ncell, rho=rho, rc=rc, skin=skin, dt=dt, temp=temp, tau=tau,
+                                 target_seconds=seconds_each, threads=thr)
+            rows.append({"workload": "lj", "natoms": info["natoms"], "threads": thr, "skin": skin, "value": info["value"],
+                         "steps": info["steps"], "seconds": info["seconds"], "kind": info["kind"]})
+        except Exception as e:      # noqa: BLE001
+            rows.append({"workload": "lj", "natoms": ncell ** 3, "threads": thr, "skin": skin, "value": None, "error": repr(e)})
+    for thr in (1, allc):
+        try:
+            info = cpu_arm_child("mol", name="butane", skin=0.25, target_seconds=seconds_each, threads=thr)
+            rows.append({"workload": "butane (prg2/prg5 force sequence)", "natoms": info["natoms"], "threads": thr, "skin": 0.25,
+                         "value": info["value"], "steps": info["steps"], "seconds": info["seconds"], "kind": info["kind"]})
+        except Exception as e:      # noqa: BLE001
+            rows.append({"workload": "butane", "threads": thr, "value": None, "error": repr(e)})
+    return rows
+
+
+def h2d_bytes_lj(n):
+    return n * (24 * 3 + 8 * 2 + 1 + 4 + 12 * 2)            # x, v, xn, m, z, type, molindex, cross_neighb, crossings
 
 
 def host_cores():
@@ -437,7 +519,7 @@ def run_molecular(args, emit, local_rank):
     cpu = None
     if not args.no_cpu:
         try:
-            _, info = mol_cpu_arm(name, args.skin, args.cpu_seconds, host_cores())
+            info = cpu_arm_child("mol", name=name, skin=args.skin, target_seconds=args.cpu_seconds, threads=host_cores())
             cpu = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:      # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
@@ -518,7 +600,11 @@ def main():
     ap.add_argument("--force-grid", type=int, default=0)
     ap.add_argument("--overlap", type=int, default=-1, help="decomposed runs: 0 = halo exchange before the force pass, 1 = beside it (default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--cpu-ncell", type=int, default=48)
+    ap.add_argument("--cpu-ncell", type=int, default=100, help="CPU arms: lattice side (100 = the 1 M-atom configuration itself)")
+    ap.add_argument("--cpu-arm-json", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-matrix", action="store_true", help="skip the section-8d matrix of smaller CPU samples")
+    ap.add_argument("--no-other", action="store_true", help="skip the short C2 (butane) / C3 (water) runs appended as other_workloads")
+    ap.add_argument("--equilibrate", type=int, default=300, help="untimed steps from the lattice before the warm-up (thermalisation)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of domain decomposition")
@@ -526,6 +612,8 @@ def main():
                     help="lj = C1/C4 (the BASELINE metric, default); butane = C2; water = C3 (single GPU)")
     ap.add_argument("--reps", type=int, default=0, help="molecular workloads: unit cells per side (default 6 / 12)")
     args = ap.parse_args()
+    if args.cpu_arm_json:
+        return cpu_arm_main(args.cpu_arm_json)
 
     # stdout carries exactly ONE line (the JSON): libraries that print banners to fd 1 (NCCL version line,
     # the reference's sep-warning) are sent to stderr for the duration of the run.
@@ -546,7 +634,8 @@ def main():
         if rank != 0:
             return 0
         if args.impl == "reference":
-            value, info = mol_cpu_arm(args.workload, args.skin, max(args.cpu_seconds, 5.0) * 2, host_cores())
+            info = cpu_arm_child("mol", name=args.workload, skin=args.skin, target_seconds=max(args.cpu_seconds, 5.0) * 2, threads=host_cores())
+            value = info["value"]
             emit({"impl": "reference", "metric": METRIC.replace("LJ, rc=2.5", args.workload), "value": value, "unit": UNIT,
                   "n_gpus": args.gpus, "steps": info["steps"], "warmup": 5, "ms_per_step": 1e3 * info["seconds"] / info["steps"],
                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -560,14 +649,18 @@ def main():
         if rank != 0:
             return 0
         threads = host_cores()
-        value, info = cpu_reference_arm(args.cpu_ncell, args.rho, rc, args.skin, dt, temp, tau,
-                                        max(args.cpu_seconds, 5.0) * 2, threads)
+        info = cpu_arm_child("lj", ncell=args.cpu_ncell, rho=args.rho, rc=rc, skin=args.skin, dt=dt, temp=temp, tau=tau,
+                             target_seconds=max(args.cpu_seconds, 5.0) * 2, threads=threads)
+        value = info["value"]
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": info["steps"], "warmup": 5, "ms_per_step": 1e3 * info["seconds"] / info["steps"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "prg1-style LJ NVT (rc=2.5, NH) bounded CPU sample", "natoms": info["natoms"],
-                           "rho": args.rho, "skin": args.skin, "l2": "n/a (host)"},
+                "config": {"workload": "prg1-style LJ NVT: sep_force_pairs(sep_lj_shift, rc=2.5) + sep_nosehoover + sep_leapfrog"
+                                       + (" (C1, 1M atoms)" if info["natoms"] == 1000000 else " bounded CPU sample"),
+                           "natoms": info["natoms"], "natoms_total": info["natoms"], "rho": args.rho, "skin": args.skin,
+                           "dt": dt, "T0": temp, "tau": tau, "lattice": "sc %dx%dx%d" % ((args.cpu_ncell,) * 3),
+                           "parallelism": "%d OpenMP threads (reference's own sep_set_omp path)" % threads, "l2": "n/a (host)"},
                 "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -652,9 +745,18 @@ def main():
         return step
 
     # ---------------- device-resident arm -------------------------------------------------------
+    dd_check = None
+    if decomposed:
+        # decomposed vs single-GPU run of a small system (pair sets, sums, final positions), before anything is timed
+        import dd_check as ddc
+        dd_check = ddc.run(rank, world, local_rank, 40, max(28, 5 * world), verbose=(rank == 0))
+        if not dd_check["ok"]:
+            raise RuntimeError("bench.py: the decomposed run does not reproduce the single-GPU run: %r" % (dd_check,))
     s = new_system()
     upload(s)
     step_dev = make_step(s)
+    for _ in range(max(0, args.equilibrate - W)):      # leave the lattice behind before anything counts
+        step_dev()
     for _ in range(W):
         step_dev()
     nb0 = s.scalars().nbuild
@@ -739,6 +841,29 @@ def main():
             log("e2e breakdown: first step incl. upload %.1f ms, %d steps %.1f ms, download %.1f ms"
                 % (1e3 * (t_up - t0), Ke - 1, 1e3 * (t_st - t_up), 1e3 * (time.perf_counter() - t_st)))
             e_epot = ret.epot / n
+            # the same loop in the DEFAULT coherence mode (SEP_SYNC=step: atoms[] refreshed after every integrator call --
+            # what an unchanged program gets without setting anything), fewer steps
+            e2e_step_mode = None
+            try:
+                Ks = max(5, min(Ke, 40))
+                lib.sep_gpu_set_sync(1)
+                view["x"][:] = x; view["v"][:] = v; view["xn"][:] = 0.0
+                view["cross_neighb"][:] = 0; view["crossings"][:] = 0
+                lib.sep_gpu_invalidate(atoms)
+                hsys.neighb_flag = 1
+                torch.cuda.synchronize()
+                t0s = time.perf_counter()
+                for _ in range(Ks):
+                    step_api()
+                lib.sep_gpu_sync(atoms)
+                torch.cuda.synchronize()
+                els = time.perf_counter() - t0s
+                e2e_step_mode = {"value": n * Ks / els, "unit": UNIT, "steps": Ks, "ms_per_step": 1e3 * els / Ks,
+                                 "h2d_bytes_per_step": h2d_bytes_lj(n) / Ks, "d2h_bytes_per_step": 416 + n * (24 * 4 + 12 * 2 + 24),
+                                 "path": "sep_* API, SEP_SYNC=step (default): x, v, f, a, counters D2H into seppart[] after every sep_leapfrog"}
+            except Exception as e:      # noqa: BLE001
+                e2e_step_mode = {"value": None, "error": repr(e)}
+            lib.sep_gpu_set_sync(0)
             lib.sep_close(atoms, n)
             how = ("sep_* API (include/sep.h), SEP_SYNC=lazy: sepret/sepsys scalars D2H every step; seppart[] uploaded at "
                    "step 0 and downloaded after the last step, both inside the timed region")
@@ -781,6 +906,8 @@ def main():
         e2e = {"value": total_atoms * Ke / el, "unit": UNIT,
                "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": scal_bytes + d2h_final / Ke,
                "steps": Ke, "path": how, "epot_per_atom": e_epot}
+        if not decomposed:
+            e2e["sync_step_mode"] = e2e_step_mode
 
     if rank != 0:
         if world > 1:
@@ -809,11 +936,13 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:      # noqa: BLE001
             traffic = None
-    roofline = {"kernel": "k_lj_list", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"kernel": "k_lj_tile", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_atom_step": alg_bytes, "avg_launch_ms": force_ms, "launches": f_cnt,
                 "share_of_step": f_ms / (t_sec * 1e3),
-                "fp64": {"note": "neither HBM nor the FP64 pipe binds this kernel: the L1 data pipe does (each warp-wide neighbour gather touches ~22 distinct 128-B lines = 22 wavefronts instead of 8; ncu l1tex data pipe 79 %, profiles/r01_k_lj_list_ncu_full.txt)",
+                "fp64": {"note": "SURVEY 8d names the FP64 pipe as this kernel's bound; the peak is an FMA-chain probe run on this GPU in this process "
+                                 "(sepgpu_peak_fp64, 2 flop per DFMA).  ncu (profiles/r02_k_lj_tile_ncu.txt): FP64 pipe 46 %, shared-memory data pipe 73 %, "
+                                 "issue slots 55 % -- the kernel is latency / phase bound (staging + end-of-tile barrier), see DESIGN.md section 3",
                          "algorithmic_flops_per_atom_step": alg_flops, "achieved_tflops": achieved_tf,
                          "peak_tflops_fma_chain_measured_here": fp64_peak.value,
                          "frac": achieved_tf / fp64_peak.value if fp64_peak.value else None}}
@@ -821,14 +950,36 @@ def main():
     cpu = None
     if not args.no_cpu and world == 1:
         try:
-            _, info = cpu_reference_arm(args.cpu_ncell, args.rho, rc, args.skin, dt, temp, tau, args.cpu_seconds, host_cores())
+            info = cpu_arm_child("lj", ncell=args.cpu_ncell, rho=args.rho, rc=rc, skin=args.skin, dt=dt, temp=temp, tau=tau,
+                                 target_seconds=args.cpu_seconds, threads=host_cores())
             cpu = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:      # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        if not args.no_cpu_matrix:
+            cpu["matrix"] = cpu_matrix(args.rho, rc, dt, temp, tau, 2.5, skip_big=False)
+    other = None
+    if world == 1 and not args.no_other:
+        # short runs of the C2 / C3 configurations (device loop only), so that the driver's record carries them too
+        import copy
+        other = []
+        for wname, ksteps in (("butane", 200), ("water", 100)):
+            a2 = copy.copy(args)
+            a2.workload, a2.steps, a2.warmup, a2.no_e2e, a2.no_cpu, a2.reps = wname, ksteps, 40, True, True, 0
+            got = []
+            try:
+                run_molecular(a2, got.append, local_rank)
+                g = got[0]
+                other.append({"workload": g["config"]["workload"], "natoms": g["config"]["natoms_total"], "value": g["value"],
+                              "unit": UNIT, "ms_per_step": g["ms_per_step"], "steps": ksteps, "warmup": 40,
+                              "list_rebuilds": g["config"]["list_rebuilds_in_timed_region"],
+                              "epot_per_atom": g["config"]["epot_per_atom"], "roofline": g["roofline"],
+                              "kernel_ms": g["kernel_ms"]})
+            except Exception as e:      # noqa: BLE001
+                other.append({"workload": wname, "value": None, "error": repr(e)})
 
     # kernels of this rank in the timed region: force, finalize, nh_update, integrate, finalize (+ lazy resets);
     # decomposed: + halo push and wait/unpack (peer-memory path); per rebuild: set_xn + 10 build kernels (+ ~25 migration/halo)
-    per_step = 7 + (2 if decomposed else 0)
+    per_step = 3 + (2 if decomposed else 0)      # force, integrate, folded finaliser (+ halo push / unpack)
     per_build = 11 + (25 if decomposed else 0)
     launches = (K * per_step + nbuild * per_build) * (world if decomposed else 1)
     if decomposed:
@@ -850,6 +1001,10 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "kernel_ms": {k: {"total_ms": a, "launches": b} for k, (a, b) in kt.items()},
     }
+    if other is not None:
+        line["other_workloads"] = other
+    if dd_check is not None:
+        line["dd_check"] = dd_check
     emit(line)
     if world > 1:
         dist.destroy_process_group()

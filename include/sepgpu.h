@@ -134,7 +134,11 @@ int sepgpu_force_lj(sepgpu_ctx *ctx, const sepgpu_sys *sys, const char types[2],
                     const sepgpu_ljparam *p, unsigned opt, int epot_assign);
 /* sep_coulomb_sf (source/sepcoulomb.c:5-18) */
 int sepgpu_coulomb_sf(sepgpu_ctx *ctx, const sepgpu_sys *sys, double cf, unsigned opt);
-/* sep_force_dpd (source/sepprfrc.c:278-301); counter-based pair noise keyed on (seed, step) */
+/* sep_force_dpd (source/sepprfrc.c:278-301); counter-based pair noise keyed on (seed, step).
+ * seed == SEPGPU_DPD_SEED_FIXED: every pair draws u = 0.75 -- what the reference computes when its rand() is interposed to
+ * return 3*2^29 (sep_rand() = rand()/(RAND_MAX+1), include/sepmisc.h:60); used to pin the dissipative and random terms to
+ * the reference itself (tests/golden/dpd_force_n512.npz). */
+#define SEPGPU_DPD_SEED_FIXED 0xFFFFFFFFFFFFFFFFULL
 int sepgpu_force_dpd(sepgpu_ctx *ctx, const sepgpu_sys *sys, const char types[2], double cf,
                      double aij, double temp, double sigma, unsigned opt,
                      unsigned long long seed, unsigned long long step);

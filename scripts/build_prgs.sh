@@ -14,7 +14,7 @@ for p in prg0 prg1 prg2 prg3 prg4 prg6 prg7 prg8 prg9; do
   echo "built $p against seplib-b200"
 done
 if [ -f "$ROOT/oracle/_ref/libsep_ref.so" ]; then
-  for p in prg0 prg1 prg4 prg7 prg9; do
+  for p in prg0 prg1 prg2 prg3 prg4 prg7 prg9; do
     gcc -std=c99 -O2 -w -DCOMPLEX -fopenmp -I"$REF/include" "$REF/prgs/$p.c" "$ROOT/oracle/_ref/libsep_ref.so" -lm \
         -Wl,-rpath,'$ORIGIN/..' -o "$OUT/${p}_ref"
     echo "built ${p}_ref against the reference"

@@ -435,6 +435,7 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z)
 __device__ __forceinline__ double dpd_uniform(unsigned long long seed, unsigned long long step, unsigned i, unsigned j)
 {
     const unsigned lo = i < j ? i : j, hi = i < j ? j : i;
+    if (seed == SEPGPU_DPD_SEED_FIXED) return 0.75;      // parity fixture: the reference with rand() interposed to a constant
     unsigned long long h = mix64(seed ^ (step * 0xD1342543DE82EF95ULL));
     h = mix64(h ^ (((unsigned long long)lo << 32) | hi));
     return (double)(h >> 11) * (1.0 / 9007199254740992.0);

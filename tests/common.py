@@ -570,3 +570,52 @@ def oracle_stochastic(x, v, L, which, steps=30):
         tr.append((o.ret.epot, o.ret.ekin, tnow))
     rec = o.record(); rec["traj"] = np.array(tr)
     return rec
+
+
+def write_molecular_start_files(dirpath):
+    """prg2 reads prg1.xyz / prg1.top, prg3 reads prg2.xyz / prg2.top (reference naming, prgs/prg2.c:30, prg3.c:39):
+    written from the recorded butane / water states (tests/golden/*.npz) in the reference's own file formats."""
+    for stem, fix, tname in (("prg1", "butane_n4000.npz", "C"), ("prg2", "water_n648.npz", None)):
+        g = np.load(os.path.join(GOLDEN, fix))
+        L = np.atleast_1d(g["L"]).astype(float)
+        n = len(g["x0"])
+        types = g["type"] if tname is None else np.full(n, ord(tname), dtype=np.uint8)
+        m = g["m"] if "m" in g else np.ones(n)
+        z = g["z"] if "z" in g else np.zeros(n)
+        with open(os.path.join(str(dirpath), f"{stem}.xyz"), "w") as fh:
+            fh.write(f"{n}\n{L[0]:.6f} {L[1]:.6f} {L[2]:.6f}\n")
+            for i in range(n):
+                fh.write("%c %.15f %.15f %.15f %.15f %.15f %.15f %.15f %.15f\n" % (
+                    chr(types[i]), *g["x0"][i], *g["v0"][i], m[i], z[i]))
+        with open(os.path.join(str(dirpath), f"{stem}.top"), "w") as fh:
+            fh.write("[ bonds ]\n;generated\n")
+            for (a, b, t) in g["blist"]:
+                fh.write(f"{g['molindex'][a]} {a} {b} {t}\n")
+            fh.write("\n[ angles ]\n;generated\n")
+            for (a, b, c, t) in g["alist"]:
+                fh.write(f"{g['molindex'][a]} {a} {b} {c} {t}\n")
+            if len(g["dlist"]):
+                fh.write("\n[ dihedrals ]\n;generated\n")
+                for (a, b, c, d, t) in g["dlist"]:
+                    fh.write(f"{g['molindex'][a]} {a} {b} {c} {d} {t}\n")
+
+
+def drive_nvt_1000(lib, x, v, L, nsteps=1000, every=100, cf=2.5, dt=0.005, temp=1.0, tau=0.1, sync_lazy=False):
+    """prg1-style NVT loop through the sep_* API (reference prgs/prg1.c:52-83 with the metric's rc = 2.5) on `lib` -- the
+    compiled reference when the fixture is recorded, libsep.so on the GPU when it is checked.  Every `every` steps:
+    [step, epot/N, ekin/N, T, p, nupdate_neighb] exactly as prg1 derives them (sep_pressure_tensor, ekin*2/3N)."""
+    s = ApiSystem(lib, x, L, cf, dt, v=v, nneighb=3000 if not hasattr(lib, "sep_gpu_sync") else 0)
+    alpha = C.c_double(0.1)
+    fun = s.fun("sep_lj_shift")
+    rows = []
+    n = s.n
+    for step in range(nsteps + 1):
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+        lib.sep_nosehoover(s.atoms, temp, C.byref(alpha), tau, s.S)
+        lib.sep_leapfrog(s.atoms, s.S, s.R)
+        if step % every == 0:
+            lib.sep_pressure_tensor(s.R, s.S)
+            rows.append([step, s.ret.epot / n, s.ret.ekin / n, s.ret.ekin * 2.0 / (3.0 * n), s.ret.p, s.sys.nupdate_neighb])
+    s.close()
+    return np.array(rows)

@@ -33,6 +33,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = run(rank, world, local, NSTEPS, NCELL)
+    dist.destroy_process_group()
+    return 0 if res["ok"] else 1
+
+
+def run(rank, world, local, nsteps, ncell, verbose=True):
+    """The check itself, for a process group that is already initialised (bench.py --gpus N runs it before its timed
+    region, so that the driver's scaling record carries a decomposed-vs-single-GPU comparison).  Collective."""
+    NSTEPS, NCELL = nsteps, ncell
     rho, rc, skin, dt, temp, tau = 0.8, 2.5, 0.25, 0.005, 1.0, 0.1
     x, L = cm.lattice(NCELL, rho, jitter=0.08, seed=5)
     n = len(x)
@@ -123,20 +132,25 @@ def main():
     full = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
     full[torch.from_numpy(go.astype(np.int64)).cuda()] = torch.from_numpy(xo).cuda()
     dist.all_reduce(full)
+    res = {"world": world, "natoms": n, "steps": NSTEPS, "cell_layers": int(nz)}
     if rank == 0:
         xr = ref.get(capi.F_X)
         err = np.abs(full.cpu().numpy() - xr).max()
-        print(f"dd_check: world={world} n={n} steps={NSTEPS} layers={nz} builds={rs2.nbuild} "
-              f"pair-set checks={pairs_checked} max|dx|={err:.2e} own/halo(rank0)={n_own}/{n_halo} -> {'OK' if ok and err <= 1e-7 else 'FAIL'}", flush=True)
+        if verbose:
+            print(f"dd_check: world={world} n={n} steps={NSTEPS} layers={nz} builds={rs2.nbuild} "
+                  f"pair-set checks={pairs_checked} max|dx|={err:.2e} own/halo(rank0)={n_own}/{n_halo} -> {'OK' if ok and err <= 1e-7 else 'FAIL'}",
+                  file=sys.stderr, flush=True)
         ok = ok and err <= 1e-7
+        res.update({"list_rebuilds": int(rs2.nbuild), "pair_set_comparisons": pairs_checked, "max_abs_dx_vs_single_gpu": float(err),
+                    "epot_per_atom_decomposed": sc.epot / n, "epot_per_atom_single_gpu": rs.epot / n})
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
     s.close()
     if ref is not None:
         ref.close()
-    dist.destroy_process_group()
-    return 0 if int(flag.item()) == 1 else 1
+    res["ok"] = int(flag.item()) == 1
+    return res
 
 
 if __name__ == "__main__":

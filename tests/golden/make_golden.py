@@ -228,6 +228,46 @@ def dpd_fixture(lib):
     print("dpd_n512 ok")
 
 
+def dpd_force_fixture(lib):
+    """sep_force_dpd of the REFERENCE with rand() interposed to a constant (tests/golden/rand_shim.c, LD_PRELOAD): every
+    pair draws sep_rand() = 0.75.  Pins the conservative, dissipative and random terms (list and brute variants,
+    source/sepprfrc.c:1007-1231) to the reference itself; the device and the oracle reproduce the draw with
+    SEPGPU_DPD_SEED_FIXED.  Re-executes this script under the shim."""
+    import subprocess
+    if os.environ.get("SEP_GOLDEN_SHIM") != "1":
+        shim = os.path.join(os.path.dirname(HERE), "_build", "librandshim.so")
+        os.makedirs(os.path.dirname(shim), exist_ok=True)
+        subprocess.check_call(["gcc", "-shared", "-fPIC", "-O2", "-o", shim, os.path.join(HERE, "rand_shim.c")])
+        env = dict(os.environ, LD_PRELOAD=shim, SEP_GOLDEN_SHIM="1")
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "dpd_force"], env=env)
+        return
+    assert C.CDLL(None).rand() == 1610612736, "rand() shim not active"
+    cf, dt, aij, temp, sigma = 1.0, 0.02, 25.0, 1.0, 3.0
+    out = dict(cf=cf, dt=dt, aij=aij, temp=temp, sigma=sigma)
+    for tag, ncell, update in (("list", 8, capi.SEP_LLIST_NEIGHBLIST), ("brute", 6, capi.SEP_BRUTE)):
+        x, L = cm.lattice(ncell, 3.0, jitter=0.35, seed=41)
+        n = len(x)
+        pv = cm.velocities(n, 1.0, seed=42)
+        s = cm.ApiSystem(lib, x, L, cf, dt, update=update)
+        s.view["pv"][:] = pv
+        lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+        lib.sep_force_dpd(s.atoms, b"AA", cf, aij, temp, sigma, s.S, s.R, 1)
+        out.update({f"{tag}_x": x, f"{tag}_pv": pv, f"{tag}_L": L, f"{tag}_f": s.view["f"].copy(), f"{tag}_epot": s.ret.epot})
+        s.close()
+    np.savez_compressed(os.path.join(HERE, "dpd_force_n512.npz"), **out)
+    print("dpd_force_n512: list epot", out["list_epot"], "brute epot", out["brute_epot"], "|f|max", np.abs(out["list_f"]).max())
+
+
+def nvt1000_fixture(lib):
+    """1000 steps of the prg1-style NVT loop on the reference (N = 4096, rho 0.8, rc 2.5): epot/N, ekin/N, T, p and the
+    list-update counter every 100 steps (trajectories compare on aggregates)."""
+    x, L = cm.lattice(16, 0.8, jitter=0.05, seed=61)
+    v = cm.velocities(len(x), 1.0, seed=62)
+    rows = cm.drive_nvt_1000(lib, x, v, L)
+    np.savez_compressed(os.path.join(HERE, "nvt1000_n4096.npz"), x0=x, v0=v, L=L, rows=rows)
+    print("nvt1000_n4096:", rows[0], rows[-1])
+
+
 def fij_array(s):
     """sys->molptr->Fij (float ***) as an (nmol, nmol, 3) float32 array."""
     mp = s.sys.molptr.contents
@@ -312,8 +352,8 @@ if __name__ == "__main__":
     lib = cm.ref()
     if lib is None:
         sys.exit("oracle/_ref/libsep_ref.so missing: run `make -C oracle ref` first")
-    which = sys.argv[1:] or ["lj", "butane", "water", "dpd", "molpress", "water_dense", "next_rows"]
+    which = sys.argv[1:] or ["lj", "butane", "water", "dpd", "dpd_force", "nvt1000", "molpress", "water_dense", "next_rows"]
     for name in which:
-        {"lj": lj_fixture, "butane": butane_fixture, "water": water_fixture, "dpd": dpd_fixture,
+        {"lj": lj_fixture, "butane": butane_fixture, "water": water_fixture, "dpd": dpd_fixture, "dpd_force": dpd_force_fixture, "nvt1000": nvt1000_fixture,
          "molpress": molpress_fixture, "water_dense": lambda l: water_fixture(l, dense=True),
          "next_rows": next_rows_fixture}[name](lib)

@@ -20,7 +20,7 @@ RUNNER = os.path.join(ROOT, "tests", "emu", "run_on_emu.py")
 WORKERS = str(max(1, min(4, (os.cpu_count() or 2) // 2)))       # the emulator is one busy thread per test process
 
 # the linked example programs (10^4 steps, minutes each on the emulator) are left to the hardware run
-FAST = "not prg"
+FAST = "not prg and not nvt_1000"      # (and the 1000-step trajectory: 160 s on the emulator)
 
 
 def _run(args, timeout=1500, env=None):

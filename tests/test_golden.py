@@ -166,6 +166,34 @@ def test_oracle_verlet_dpd_golden():
         assert abs(ret.ekin - float(g[f"ekin{step + 1}"])) <= EXACT * ret.ekin
 
 
+SEED_FIXED = 0xFFFFFFFFFFFFFFFF          # SEPGPU_DPD_SEED_FIXED: every pair draws u = 0.75 (include/sepgpu.h)
+
+
+def _dpd_pairs(x, L, cf, tag):
+    n = len(x); length = cm.dvec3([L] * 3)
+    if tag == "list":
+        return np.ascontiguousarray(cm.oracle_pairs(x, L, cf, 0.25), dtype=np.int32)
+    buf = np.empty((n * n, 2), dtype=np.int32); tp = cm.OrcTopo()
+    k = cm.oracle().orc_neighb_pairs_n2(n, cm.ptr(x), cm.ptr(length), cf, cm.ALL, C.byref(tp), cm.ptr(buf), n * n)
+    return np.ascontiguousarray(buf[:k])
+
+
+@pytest.mark.parametrize("tag", ["list", "brute"])
+def test_oracle_dpd_force_golden(tag):
+    """sep_force_dpd as the REFERENCE computes it when its rand() is interposed to a constant (tests/golden/rand_shim.c):
+    conservative + dissipative + random terms of sep_dpdforce_neighb / _brute (source/sepprfrc.c:1007-1231)."""
+    g = load("dpd_force_n512.npz")
+    x = np.ascontiguousarray(g[tag + "_x"]); pv = np.ascontiguousarray(g[tag + "_pv"]); L = float(g[tag + "_L"]); n = len(x)
+    types = np.full(n, ord("A"), dtype=np.uint8); length = cm.dvec3([L] * 3)
+    pairs = _dpd_pairs(x, L, float(g["cf"]), tag)
+    f = np.zeros((n, 3)); ret = cm.OrcRet()
+    cm.oracle().orc_dpd_force_list(n, cm.ptr(x), cm.ptr(pv), cm.ptr(types), cm.ptr(length), cm.ptr(pairs), len(pairs), b"AA",
+                                   float(g["cf"]), float(g["aij"]), float(g["temp"]), float(g["sigma"]), float(g["dt"]),
+                                   SEED_FIXED, 0, cm.ptr(f), C.byref(ret))
+    assert cm.rel_force_err(f, g[tag + "_f"]) <= 1e-12
+    assert abs(ret.epot - float(g[tag + "_epot"])) <= 1e-12 * abs(ret.epot)
+
+
 # ====================================================================================================
 # GPU: CUDA path vs reference golden vectors
 # ====================================================================================================
@@ -387,6 +415,47 @@ def test_gpu_verlet_dpd_golden():
         assert sc.neighb_flag == int(g[f"flag{step + 1}"])
         assert abs(sc.ekin - float(g[f"ekin{step + 1}"])) <= FT * sc.ekin
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["list", "brute"])
+def test_gpu_dpd_force_golden(tag):
+    """k_dpd against the reference's own sep_force_dpd (rand() interposed to a constant; SEPGPU_DPD_SEED_FIXED draws the
+    same number on the device): conservative, dissipative and random terms, list and brute variants."""
+    g = load("dpd_force_n512.npz")
+    x = g[tag + "_x"]; pv = g[tag + "_pv"]; L = float(g[tag + "_L"]); n = len(x)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_PV, pv)
+    sys_ = capi.make_sys([L] * 3, float(g["cf"]), float(g["dt"]),
+                         neighb_update=capi.SEP_LLIST_NEIGHBLIST if tag == "list" else capi.SEP_BRUTE)
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    s.call("sepgpu_force_dpd", C.byref(sys_), b"AA", float(g["cf"]), float(g["aij"]), float(g["temp"]), float(g["sigma"]),
+           cm.ALL, SEED_FIXED, 0)
+    assert cm.rel_force_err(s.get(capi.F_F), g[tag + "_f"]) <= FT
+    assert abs(s.scalars().epot - float(g[tag + "_epot"])) <= FT * abs(float(g[tag + "_epot"]))
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_nvt_1000_steps_follow_the_reference():
+    """1000 steps of the prg1-style NVT loop through the sep_* API of libsep.so against the REFERENCE's own run of the same
+    loop (tests/golden/nvt1000_n4096.npz): epot/N, T and p every 100 steps.  Bounds from SURVEY.md section 8c -- the
+    reference's own -O2 and -Ofast builds differ by 3.6e-6 in epot at step 1000: 1e-5 relative up to step 500, 1e-4 at
+    step 1000 (p: of its thermal scale rho*T), and the list-update counter equal over the first 200 steps."""
+    g = load("nvt1000_n4096.npz")
+    lib = capi.load()
+    rows = cm.drive_nvt_1000(lib, np.ascontiguousarray(g["x0"]), np.ascontiguousarray(g["v0"]), float(g["L"]))
+    ref = g["rows"]
+    assert rows.shape == ref.shape
+    for got, want in zip(rows, ref):
+        step = int(want[0])
+        tol = 1e-5 if step <= 500 else 1e-4
+        assert abs(got[1] - want[1]) <= tol * abs(want[1]), (step, got, want)            # epot/N
+        assert abs(got[3] - want[3]) <= tol * abs(want[3]), (step, got, want)            # T
+        assert abs(got[4] - want[4]) <= 10 * tol * 0.8, (step, got, want)                # p (fluctuates around 1.6; scale rho*T)
+        if step <= 200:
+            assert got[5] == want[5], (step, got, want)                                  # nupdate_neighb
+    assert abs(rows[-1, 5] - ref[-1, 5]) <= 2
 
 
 def test_oracle_next_rows_golden():
