@@ -474,7 +474,7 @@ def run_molecular(args, emit, local_rank):
     e2e = None
     if not args.no_e2e:
         Ke = max(10, min(K, 200))
-        lib.sep_gpu_set_sync(0)
+        lib.sep_gpu_set_sync(3)          # the default coherence mode (auto)
         atoms, view, hsys = mol_api_system(lib, capi, w, P, capi.SEP_LLIST_NEIGHBLIST, 0, args.skin)
         ret = capi.SepRet(); alpha = C.c_double(0.1)
         step_api = mol_api_step(lib, capi, name, P, atoms, hsys, ret, alpha)
@@ -498,8 +498,8 @@ def run_molecular(args, emit, local_rank):
         d2h_final = n * (24 * 4 + 12 * 2 + 24)
         e2e = {"value": n * Ke / el, "unit": UNIT, "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": 416 + d2h_final / Ke,
                "steps": Ke, "epot_per_atom": e_epot,
-               "path": "sep_* API (include/sep.h), SEP_SYNC=lazy: scalars D2H every step; seppart[] uploaded at step 0 and "
-                       "downloaded after the last step, both inside the timed region"}
+               "path": "sep_* API (include/sep.h), default coherence mode SEP_SYNC=auto: scalars D2H after every hot call; seppart[] "
+                       "uploaded at step 0 and downloaded after the last step, both inside the timed region"}
 
     # roofline of the dominant pair kernel (k_lj_list for butane, k_coulomb_list for water): list + own row + force row
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -799,76 +799,71 @@ def main():
     if not args.no_e2e:
         Ke = max(10, min(K, 300))
         if not decomposed:
-            # the reference-facing sep_* API of include/sep.h on a host seppart[] array
-            lib.sep_gpu_set_sync(0)          # SEP_SYNC_LAZY: scalars every step, atoms[] at the end
-            atoms = lib.sep_init(n, 0)
-            view = capi.atoms_view(atoms, n)
-            view["x"][:] = x
-            view["v"][:] = v
-            hsys = lib.sep_sys_setup(Lvec[0], Lvec[1], Lvec[2], rc, dt, n, capi.SEP_LLIST_NEIGHBLIST)
-            lib.sep_set_skin(C.byref(hsys), args.skin)
-            ret = capi.SepRet()
-            alpha = C.c_double(0.1)
-            fun = C.cast(lib.sep_lj_shift, C.c_void_p)
+            # the reference-facing sep_* API of include/sep.h on a host seppart[] array, in the library's DEFAULT coherence
+            # mode (SEP_SYNC=auto: what an unchanged program gets) -- and, for comparison, in lazy and step mode
+            fun = None
 
-            def step_api():
-                lib.sep_reset_retval(C.byref(ret))
-                lib.sep_reset_force(atoms, C.byref(hsys))
-                lib.sep_force_pairs(atoms, b"AA", rc, fun, C.byref(hsys), C.byref(ret), capi.SEP_ALL)
-                lib.sep_nosehoover(atoms, temp, C.byref(alpha), tau, C.byref(hsys))
-                lib.sep_leapfrog(atoms, C.byref(hsys), C.byref(ret))
+            def api_run(mode, nsteps, label):
+                lib.sep_gpu_set_sync(mode)
+                atoms = lib.sep_init(n, 0)
+                view = capi.atoms_view(atoms, n)
+                view["x"][:] = x
+                view["v"][:] = v
+                hsys = lib.sep_sys_setup(Lvec[0], Lvec[1], Lvec[2], rc, dt, n, capi.SEP_LLIST_NEIGHBLIST)
+                lib.sep_set_skin(C.byref(hsys), args.skin)
+                ret = capi.SepRet()
+                alpha = C.c_double(0.1)
+                fun = C.cast(lib.sep_lj_shift, C.c_void_p)
 
-            for _ in range(max(3, min(W, 20))):          # warm-up (both directions), then restore the host arrays and re-upload
-                step_api()
-            lib.sep_gpu_sync(atoms)
-            view["x"][:] = x
-            view["v"][:] = v
-            view["xn"][:] = 0.0
-            view["cross_neighb"][:] = 0
-            view["crossings"][:] = 0
-            lib.sep_gpu_invalidate(atoms)
-            hsys.neighb_flag = 1
-            barrier()
-            t0 = time.perf_counter()
-            step_api()                       # first call uploads x,v,m,z,type,... from the host array
-            t_up = time.perf_counter()
-            for _ in range(Ke - 1):
-                step_api()
-            t_st = time.perf_counter()
-            lib.sep_gpu_sync(atoms)          # final state back into atoms[]
-            torch.cuda.synchronize()
-            el = time.perf_counter() - t0
-            log("e2e breakdown: first step incl. upload %.1f ms, %d steps %.1f ms, download %.1f ms"
-                % (1e3 * (t_up - t0), Ke - 1, 1e3 * (t_st - t_up), 1e3 * (time.perf_counter() - t_st)))
-            e_epot = ret.epot / n
-            # the same loop in the DEFAULT coherence mode (SEP_SYNC=step: atoms[] refreshed after every integrator call --
-            # what an unchanged program gets without setting anything), fewer steps
-            e2e_step_mode = None
-            try:
-                Ks = max(5, min(Ke, 40))
-                lib.sep_gpu_set_sync(1)
-                view["x"][:] = x; view["v"][:] = v; view["xn"][:] = 0.0
-                view["cross_neighb"][:] = 0; view["crossings"][:] = 0
+                def step_api():
+                    lib.sep_reset_retval(C.byref(ret))
+                    lib.sep_reset_force(atoms, C.byref(hsys))
+                    lib.sep_force_pairs(atoms, b"AA", rc, fun, C.byref(hsys), C.byref(ret), capi.SEP_ALL)
+                    lib.sep_nosehoover(atoms, temp, C.byref(alpha), tau, C.byref(hsys))
+                    lib.sep_leapfrog(atoms, C.byref(hsys), C.byref(ret))
+
+                for _ in range(max(3, min(W, 20))):      # warm-up (both directions), then restore the host arrays: they are
+                    step_api()                           # uploaded again inside the timed region
+                lib.sep_gpu_sync(atoms)
+                view["x"][:] = x
+                view["v"][:] = v
+                view["xn"][:] = 0.0
+                view["cross_neighb"][:] = 0
+                view["crossings"][:] = 0
                 lib.sep_gpu_invalidate(atoms)
                 hsys.neighb_flag = 1
-                torch.cuda.synchronize()
-                t0s = time.perf_counter()
-                for _ in range(Ks):
+                barrier()
+                t0 = time.perf_counter()
+                step_api()                       # first call uploads x,v,m,z,type,... from the host array
+                t_up = time.perf_counter()
+                for _ in range(nsteps - 1):
                     step_api()
-                lib.sep_gpu_sync(atoms)
+                t_st = time.perf_counter()
+                lib.sep_gpu_sync(atoms)          # final state back into atoms[]
                 torch.cuda.synchronize()
-                els = time.perf_counter() - t0s
-                e2e_step_mode = {"value": n * Ks / els, "unit": UNIT, "steps": Ks, "ms_per_step": 1e3 * els / Ks,
-                                 "h2d_bytes_per_step": h2d_bytes_lj(n) / Ks, "d2h_bytes_per_step": 416 + n * (24 * 4 + 12 * 2 + 24),
-                                 "path": "sep_* API, SEP_SYNC=step (default): x, v, f, a, counters D2H into seppart[] after every sep_leapfrog"}
-            except Exception as e:      # noqa: BLE001
-                e2e_step_mode = {"value": None, "error": repr(e)}
-            lib.sep_gpu_set_sync(0)
-            lib.sep_close(atoms, n)
-            how = ("sep_* API (include/sep.h), SEP_SYNC=lazy: sepret/sepsys scalars D2H every step; seppart[] uploaded at "
-                   "step 0 and downloaded after the last step, both inside the timed region")
-            h2d = n * (24 * 3 + 8 * 2 + 1 + 4 + 12 * 2)            # x, v, xn, m, z, type, molindex, cross_neighb, crossings
+                el_ = time.perf_counter() - t0
+                log("e2e %s: first step incl. upload %.1f ms, %d steps %.1f ms, download %.1f ms"
+                    % (label, 1e3 * (t_up - t0), nsteps - 1, 1e3 * (t_st - t_up), 1e3 * (time.perf_counter() - t_st)))
+                ep = ret.epot / n
+                lib.sep_close(atoms, n)
+                return el_, ep
+
+            h2d = h2d_bytes_lj(n)
             d2h_final = n * (24 * 4 + 12 * 2 + 24)                 # x, v, f, a, counters, xn
+            el, e_epot = api_run(3, Ke, "SEP_SYNC=auto")
+            e2e_modes = {}
+            for mode, label, ks in ((0, "lazy", Ke), (1, "step", max(5, min(Ke, 40)))):
+                try:
+                    el_m, _ = api_run(mode, ks, "SEP_SYNC=" + label)
+                    e2e_modes[label] = {"value": n * ks / el_m, "unit": UNIT, "steps": ks, "ms_per_step": 1e3 * el_m / ks,
+                                        "d2h_bytes_per_step": 416 + (d2h_final if mode == 1 else d2h_final / ks)}
+                except Exception as e:      # noqa: BLE001
+                    e2e_modes[label] = {"value": None, "error": repr(e)}
+            lib.sep_gpu_set_sync(3)
+            e2e_step_mode = e2e_modes
+            how = ("sep_* API (include/sep.h) in the default coherence mode SEP_SYNC=auto (atoms[] page-protected while the device "
+                   "copy is newer): sepret/sepsys scalars D2H after every hot call; seppart[] uploaded at step 0 and downloaded "
+                   "after the last step, both inside the timed region")
         else:
             # decomposed: the sepgpu_* C ABI with host numpy buffers (the sep_* API is one process / one GPU)
             # (the context is reused after the warm-up: a fresh NCCL communicator would put its lazy connection
@@ -907,7 +902,7 @@ def main():
                "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": scal_bytes + d2h_final / Ke,
                "steps": Ke, "path": how, "epot_per_atom": e_epot}
         if not decomposed:
-            e2e["sync_step_mode"] = e2e_step_mode
+            e2e["other_sync_modes"] = e2e_step_mode
 
     if rank != 0:
         if world > 1:

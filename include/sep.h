@@ -1,7 +1,9 @@
 /* sep.h -- the seplib C99 API, as served by seplib-b200 (B200 / sm_100a device path).
  *
  * This header is the drop-in boundary: programs written against the reference's include/sep.h
- * (prgs/prg0.c ... prg6.c) compile against it unchanged and link with -lsep.  Type names, field
+ * (prgs/prg0-4.c, prg6-9.c) compile against it unchanged and link with -lsep.  Not provided: the OpenMP
+ * tasking model II of prg5 (sep_omp_bond / sep_omp_angle / sep_omp_torsion, source/sepomp.c -- a CPU
+ * idiom with nothing to do on a device) and the sep_matrix_* helpers it uses.  Type names, field
  * names, field order, constants and prototypes follow the reference so that user code which reads
  * atoms[i].x/v/f, sys.nupdate_neighb or ret.epot directly keeps working; each block cites the
  * reference header it mirrors (paths relative to the reference root).
@@ -12,13 +14,21 @@
  * with sep_error().
  *
  * Host/device coherence (env SEP_SYNC, or sep_gpu_set_sync):
- *   step (default)  atoms[] is refreshed from the device at the end of every integrator call;
+ *   auto (default)  atoms[] lives in pages the library protects while the device copy is newer.  The first READ of any
+ *                   atoms[i] member by user code faults, the library brings the array up to date and the read continues;
+ *                   the first WRITE marks the array as changed by the host and it is uploaded before the next hot call.
+ *                   Programs that leave atoms[] alone inside the loop pay nothing; programs that read or write it
+ *                   (reference prgs/prg0.c:64 prints atoms[0].f, prgs/prg5.c writes forces) stay correct without any
+ *                   change.  sepret / sepsys scalars are refreshed after every hot call.  Arrays that did not come from
+ *                   sep_init / sep_init_xyz cannot be protected and are handled as in "step".
+ *   step            atoms[] is refreshed from the device at the end of every integrator call;
  *                   sepret / sepsys scalars after every hot call.
  *   lazy            atoms[] is refreshed only by library calls that read it (sep_eval_mom,
  *                   sep_save_xyz, ...), by sep_gpu_sync() and by sep_close(); scalars after
  *                   integrator calls.
  *   full            like step, plus forces are written back after every force call.
- * Writing into atoms[] from user code between hot calls needs sep_gpu_invalidate(atoms).
+ * In step / lazy / full mode, writing into atoms[] from user code between hot calls needs sep_gpu_invalidate(atoms);
+ * in auto mode the library notices by itself.
  */
 #ifndef SEP_B200_SEP_H
 #define SEP_B200_SEP_H
@@ -305,6 +315,7 @@ void sep_close_sampler(sepsampler *ptr);
 #define SEP_SYNC_LAZY 0
 #define SEP_SYNC_STEP 1
 #define SEP_SYNC_FULL 2
+#define SEP_SYNC_AUTO 3
 void sep_gpu_set_sync(int mode);                 /* overrides env SEP_SYNC                              */
 void sep_gpu_sync(seppart *ptr);                 /* device -> atoms[] (everything that changed)         */
 void sep_gpu_invalidate(seppart *ptr);           /* atoms[] was edited by the caller: re-upload         */

@@ -370,8 +370,15 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
     // list mode: the reference neither builds nor checks the list here and ignores opt
     // (source/sepcoulomb.c:8-16); it reuses whatever the preceding sep_force_pairs left behind.
     if (!c->list_valid) {
-        sepgpu_set_error("coulomb_sf: no neighbour list (call sep_force_pairs first, as the reference requires)");
-        return SEPGPU_ESTATE;
+        // The reference walks whatever list the last sep_force_pairs left behind, however stale (a program may call
+        // sep_coulomb_sf before sep_force_pairs in a step).  Here the skin trigger has already invalidated that list: build
+        // a fresh one with the exclusion rule of the last build -- a superset of what the stale list still guarantees.
+        if (c->list_gen == 0) {
+            sepgpu_set_error("coulomb_sf: no neighbour list (call sep_force_pairs first, as the reference requires)");
+            return SEPGPU_ESTATE;
+        }
+        int rcb = sepgpu_neighb_build(c, sys, c->list_opt);
+        if (rcb) return rcb;
     }
     if (c->list_f16) {                      // the list kernels below walk global-index rows
         int rcb = sepgpu_need_global_rows(c, sys);

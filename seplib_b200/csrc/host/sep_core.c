@@ -5,10 +5,14 @@
  * the parts of source/sepmisc.c that the example programs use; each cites its counterpart.  They
  * never compute forces or integrate: that is the device layer's job (include/sepgpu.h).
  */
+#define _DEFAULT_SOURCE
 #include "sep_host.h"
 #include <float.h>
 
 #include <ctype.h>
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 /* ---------------------------------------------------------------------------------------------------
  * error reporting (source/sepmisc.c:16-113): mini-printf to stdout, then exit for errors
@@ -66,24 +70,114 @@ static sep_binding *g_bindings = NULL;
 static int g_sync_mode = -1;
 static unsigned long long g_dpd_seed = 0x5EB11B200ULL;
 
+/* ---------------------------------------------------------------------------------------------------
+ * SEP_SYNC=auto: page protection of atoms[].  The reference exposes seppart as a public
+ * struct (include/sepstrct.h:23-61) that callers read and write between library calls; with the state resident on the
+ * device the library has to notice.  The array is an anonymous mapping of its own:
+ *   PROT_NONE   the device copy is newer (after any hot call)
+ *   PROT_READ   host and device agree; a write faults once more and marks the host copy as changed
+ *   READ|WRITE  the host copy may have changed: everything is uploaded before the next hot call
+ * A fault elsewhere goes to whoever handled SIGSEGV before.
+ * ------------------------------------------------------------------------------------------------- */
+static struct sigaction g_old_segv;
+static int g_segv_installed = 0;
+
+static void sepb_set_prot(sep_binding *b, int prot)
+{
+    if (!b->managed || b->prot == prot) return;
+    if (mprotect(b->map_base, b->map_bytes, prot) != 0) sep_error("%s: mprotect failed", (char *)__func__);
+    b->prot = prot;
+}
+
+void sepb_unprotect_all(sep_binding *b)
+{
+    if (!b->managed || b->prot == (PROT_READ | PROT_WRITE)) return;
+    const int was = b->prot;
+    sepb_set_prot(b, PROT_READ | PROT_WRITE);
+    if (was == PROT_NONE && b->gpu) sepb_download(b, ~0u);
+}
+
+static void sep_segv_handler(int sig, siginfo_t *si, void *uctx)
+{
+    const char *addr = (const char *)si->si_addr;
+    for (sep_binding *b = sepb_first(); b; b = b->next) {
+        if (!b->managed || addr < (const char *)b->map_base || addr >= (const char *)b->map_base + b->map_bytes) continue;
+        if (b->prot == PROT_NONE) {                      /* first touch since the device moved on: bring atoms[] up to date */
+            sepb_set_prot(b, PROT_READ | PROT_WRITE);
+            if (b->gpu) sepb_download(b, ~0u);
+            sepb_set_prot(b, PROT_READ);
+            return;
+        }
+        if (b->prot == PROT_READ) {                      /* a write: the host copy is the newer one from here on */
+            sepb_set_prot(b, PROT_READ | PROT_WRITE);
+            b->host_dirty |= SEPB_ALL_STATE | SEPB_EXCL;
+            if (b->dpd_state_on_device) b->host_dirty |= SEPB_PV | SEPB_PA;
+            if (b->x0_on_device) b->host_dirty |= SEPB_X0;
+            b->dev_dirty = 0;
+            return;
+        }
+        break;                                           /* already writable: a genuine fault */
+    }
+    /* not ours: previous handler, or the default action */
+    if (g_old_segv.sa_flags & SA_SIGINFO) {
+        if (g_old_segv.sa_sigaction) { g_old_segv.sa_sigaction(sig, si, uctx); return; }
+    } else if (g_old_segv.sa_handler != SIG_DFL && g_old_segv.sa_handler != SIG_IGN && g_old_segv.sa_handler) {
+        g_old_segv.sa_handler(sig);
+        return;
+    }
+    signal(SIGSEGV, SIG_DFL);
+    raise(SIGSEGV);
+}
+
+static void sep_install_segv(void)
+{
+    if (g_segv_installed) return;
+    struct sigaction sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sa_sigaction = sep_segv_handler;
+    sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+    sigemptyset(&sa.sa_mask);
+    if (sigaction(SIGSEGV, &sa, &g_old_segv) == 0) g_segv_installed = 1;
+}
+
+void sepb_dev_newer(sep_binding *b, unsigned bits)
+{
+    b->dev_dirty |= bits;
+    if (b->managed && sep_sync_mode() == SEP_SYNC_AUTO) {
+        /* what the host changed and has not uploaded yet must not be lost: those fields stay the host's */
+        if (b->host_dirty == 0) sepb_set_prot(b, PROT_NONE);
+    }
+}
+
 int sep_sync_mode(void)
 {
     if (g_sync_mode < 0) {
         const char *e = getenv("SEP_SYNC");
-        g_sync_mode = SEP_SYNC_STEP;
+        g_sync_mode = SEP_SYNC_AUTO;
         if (e) {
             if (!strcmp(e, "lazy")) g_sync_mode = SEP_SYNC_LAZY;
             else if (!strcmp(e, "full")) g_sync_mode = SEP_SYNC_FULL;
             else if (!strcmp(e, "step")) g_sync_mode = SEP_SYNC_STEP;
-            else sep_warning("SEP_SYNC=%s not understood (lazy|step|full); using step", (char *)e);
+            else if (!strcmp(e, "auto")) g_sync_mode = SEP_SYNC_AUTO;
+            else sep_warning("SEP_SYNC=%s not understood (auto|lazy|step|full); using auto", (char *)e);
         }
     }
     return g_sync_mode;
 }
 
+void sepb_unprotect_all(sep_binding *b);
+
 void sep_gpu_set_sync(int mode)
 {
-    if (mode == SEP_SYNC_LAZY || mode == SEP_SYNC_STEP || mode == SEP_SYNC_FULL) g_sync_mode = mode;
+    if (mode == SEP_SYNC_LAZY || mode == SEP_SYNC_STEP || mode == SEP_SYNC_FULL || mode == SEP_SYNC_AUTO) g_sync_mode = mode;
+    if (mode != SEP_SYNC_AUTO)           /* leaving auto mode: nothing stays protected */
+        for (sep_binding *b = sepb_first(); b; b = b->next) sepb_unprotect_all(b);
+}
+
+int sepb_eager(const sep_binding *b)
+{
+    const int mode = sep_sync_mode();
+    return mode == SEP_SYNC_STEP || mode == SEP_SYNC_FULL || (mode == SEP_SYNC_AUTO && !(b && b->managed));
 }
 
 void sep_gpu_set_dpd_seed(unsigned long long seed) { g_dpd_seed = seed; }
@@ -244,7 +338,7 @@ void sepb_pull_scalars(sep_binding *b, sepsys *sys, sepret *ret, sepgpu_scalars 
 
 void sepb_after_force(sep_binding *b, sepsys *sys, sepret *ret)
 {
-    b->dev_dirty |= SEPB_F | SEPB_A;
+    sepb_dev_newer(b, SEPB_F | SEPB_A);
     b->last_ret = ret;
     const int mode = sep_sync_mode();
     if (mode != SEP_SYNC_LAZY) sepb_pull_scalars(b, sys, ret, NULL);
@@ -254,7 +348,14 @@ void sepb_after_force(sep_binding *b, sepsys *sys, sepret *ret)
 void sep_gpu_sync(seppart *ptr)
 {
     sep_binding *b = sepb_find(ptr);
-    if (b && b->gpu) sepb_download(b, ~0u);
+    if (!b || !b->gpu) return;
+    if (b->managed && b->prot == PROT_NONE) {
+        sepb_set_prot(b, PROT_READ | PROT_WRITE);
+        sepb_download(b, ~0u);
+        sepb_set_prot(b, PROT_READ);
+    } else {
+        sepb_download(b, ~0u);
+    }
 }
 
 void sep_gpu_invalidate(seppart *ptr)
@@ -264,6 +365,7 @@ void sep_gpu_invalidate(seppart *ptr)
     b->host_dirty |= SEPB_ALL_STATE | SEPB_EXCL;
     if (b->dpd_state_on_device) b->host_dirty |= SEPB_PV | SEPB_PA;
     b->dev_dirty = 0;
+    sepb_set_prot(b, PROT_READ | PROT_WRITE);
 }
 
 void sep_gpu_sync_scalars(seppart *ptr, sepsys *sys, sepret *ret)
@@ -293,7 +395,17 @@ seppart *sep_init(size_t npart, size_t nneighb)
 {
     /* zero-filled so that xn starts at 0 (the reference leaves it uninitialised; fresh heap pages
      * make it 0 in practice and the first leapfrog then requests a rebuild) */
-    seppart *p = calloc(npart ? npart : 1, sizeof(seppart));
+    seppart *p = NULL;
+    size_t map_bytes = 0;
+    const size_t want = (npart ? npart : 1) * sizeof(seppart);
+    if (sep_sync_mode() == SEP_SYNC_AUTO) {
+        /* a mapping of its own (whole pages, zero-filled) whose protection the library can switch */
+        const size_t pg = (size_t)sysconf(_SC_PAGESIZE);
+        map_bytes = (want + pg - 1) / pg * pg;
+        void *m = mmap(NULL, map_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) map_bytes = 0; else p = m;
+    }
+    if (!p) p = calloc(npart ? npart : 1, sizeof(seppart));
     if (!p) sep_error("%s at line %d: Couldn't allocate memory\n", (char *)__func__, __LINE__);
     /* The reference gives every atom an int[nneighb] row (12 kB/atom at SEP_NEIGHB).  The device owns
      * the list here; rows are not materialised (1 M atoms would need 12 GB of host memory). */
@@ -308,7 +420,11 @@ seppart *sep_init(size_t npart, size_t nneighb)
         for (int k = 0; k < SEP_ANGLE; k++) p[n].angle[k] = -1;
         for (int k = 0; k < SEP_DIHED; k++) p[n].dihed[k] = -1;
     }
-    sepb_register(p, npart);
+    sep_binding *b = sepb_register(p, npart);
+    if (map_bytes) {
+        b->managed = 1; b->map_base = p; b->map_bytes = map_bytes; b->prot = PROT_READ | PROT_WRITE;
+        sep_install_segv();
+    }
     return p;
 }
 
@@ -316,9 +432,13 @@ void sep_close(seppart *ptr, size_t npart)
 {
     (void)npart;
     sep_binding *b = sepb_find(ptr);
-    if (b && b->gpu) sepb_download(b, ~0u);     /* final state visible to anyone still holding a copy */
+    void *map_base = NULL; size_t map_bytes = 0;
+    if (b) {
+        if (b->managed) { sepb_set_prot(b, PROT_READ | PROT_WRITE); map_base = b->map_base; map_bytes = b->map_bytes; }
+        if (b->gpu) sepb_download(b, ~0u);      /* final state visible to anyone still holding a copy */
+    }
     sepb_unregister(ptr);
-    free(ptr);
+    if (map_base) munmap(map_base, map_bytes); else free(ptr);
 }
 
 /* source/sepinit.c:69-109 */
@@ -529,11 +649,11 @@ void sep_reset_force(seppart *ptr, sepsys *sys)
     sepb_check(sepgpu_reset_force(b->gpu), "sep_reset_force");
     sys->max_dist2 = 0.0;
     b->host_dirty &= ~SEPB_F;
-    if (sep_sync_mode() != SEP_SYNC_LAZY) {
+    if (sepb_eager(b)) {
         for (long n = 0; n < sys->npart; n++) ptr[n].f[0] = ptr[n].f[1] = ptr[n].f[2] = 0.0;
         b->dev_dirty &= ~(SEPB_F | SEPB_A);
     } else {
-        b->dev_dirty |= SEPB_F | SEPB_A;
+        sepb_dev_newer(b, SEPB_F | SEPB_A);
     }
 }
 
@@ -695,8 +815,8 @@ void sep_reset_momentum(seppart *ptr, const char type, sepsys *sys)
 {
     sep_binding *b = sepb_prepare(ptr, sys);
     sepb_check(sepgpu_reset_momentum(b->gpu, type), "sep_reset_momentum");
-    b->dev_dirty |= SEPB_V;
-    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_V);
+    sepb_dev_newer(b, SEPB_V);
+    if (sepb_eager(b)) sepb_download(b, SEPB_V);
 }
 
 /* source/sepmisc.c:994-1026 */
@@ -709,8 +829,8 @@ static void scale_box_on_device(sepatom *ptr, sepsys *sys, double sx, double sy,
     sep_binding *b = sepb_prepare(ptr, sys);
     const double sc[3] = {sx, sy, sz};
     sepb_check(sepgpu_scale_box(b->gpu, sc, sys->length), who);
-    b->dev_dirty |= SEPB_X;
-    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_X);
+    sepb_dev_newer(b, SEPB_X);
+    if (sepb_eager(b)) sepb_download(b, SEPB_X);
 }
 
 static void resize_subbox(sepsys *sys, int k, double skin, const char *who)
@@ -799,8 +919,8 @@ void sep_relax_temp(seppart *ptr, char type, double Td, double tau, sepsys *sys)
     sepb_check(sepgpu_relax_temp(b->gpu, &gs, type, Td, tau, &ekin), "sep_relax_temp");
     if (ekin < DBL_EPSILON)
         sep_warning("sep_relax_temp: Zero kinetic energy - check your the types.");
-    b->dev_dirty |= SEPB_V;
-    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, SEPB_V);
+    sepb_dev_newer(b, SEPB_V);
+    if (sepb_eager(b)) sepb_download(b, SEPB_V);
 }
 
 double sep_spring_x0(double r2, char opt)
@@ -825,6 +945,6 @@ void sep_force_x0(seppart *ptr, char type, double (*fun)(double, char), sepsys *
     sepgpu_sys gs;
     sepb_fill_sys(sys, &gs);
     sepb_check(sepgpu_force_x0(b->gpu, &gs, type, -fun(0.0, 'f')), "sep_force_x0");
-    b->dev_dirty |= SEPB_F | SEPB_A;
+    sepb_dev_newer(b, SEPB_F | SEPB_A);
     if (sep_sync_mode() == SEP_SYNC_FULL) sepb_download(b, SEPB_F);
 }

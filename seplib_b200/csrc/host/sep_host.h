@@ -42,6 +42,10 @@ typedef struct sep_binding {
     unsigned long long dpd_calls;
     sepret *last_ret;
     double *blengths_host, *angles_host, *dihedrals_host;
+    /* SEP_SYNC=auto: atoms[] is an mmap'ed region whose protection tracks which side is newer */
+    int managed;                 /* 1: allocated by sep_init in auto mode */
+    void *map_base; size_t map_bytes;
+    int prot;                    /* current protection of the region (PROT_NONE / PROT_READ / PROT_READ|PROT_WRITE) */
     struct sep_binding *next;
 } sep_binding;
 
@@ -61,6 +65,10 @@ void sepb_pull_scalars(sep_binding *b, sepsys *sys, sepret *ret, sepgpu_scalars 
 void sepb_mark_host_dirty(seppart *atoms, unsigned fields);
 void sepb_after_force(sep_binding *b, sepsys *sys, sepret *ret);
 int sep_sync_mode(void);
+/* atoms[] refreshed eagerly after integrator calls (step / full, or auto on an array the library cannot protect) */
+int sepb_eager(const sep_binding *b);
+/* the device copy of `bits` is newer than atoms[] from now on (auto mode: protects the array) */
+void sepb_dev_newer(sep_binding *b, unsigned bits);
 void sepb_check(int rc, const char *where);
 unsigned long long sep_dpd_seed(void);
 

@@ -27,7 +27,7 @@ void sep_nosehoover(sepatom *ptr, double temp0, double *alpha, const double tau,
     sepgpu_sys gs;
     sepb_fill_sys(sys, &gs);
     sepb_check(sepgpu_nosehoover(b->gpu, &gs, temp0, slot, tau), "sep_nosehoover");
-    b->dev_dirty |= SEPB_F | SEPB_A;
+    sepb_dev_newer(b, SEPB_F | SEPB_A);
     if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_pull_scalars(b, sys, NULL, NULL);   /* refreshes *alpha */
     if (sep_sync_mode() == SEP_SYNC_FULL) sepb_download(b, SEPB_F);
 }
@@ -38,7 +38,7 @@ void _sep_nosehoover_type(seppart *ptr, char type, double Td, double *alpha, con
     sepgpu_sys gs;
     sepb_fill_sys(sys, &gs);
     sepb_check(sepgpu_nosehoover_type(b->gpu, &gs, type, Td, alpha, Q), "_sep_nosehoover_type");
-    b->dev_dirty |= SEPB_F | SEPB_A;
+    sepb_dev_newer(b, SEPB_F | SEPB_A);
     if (sep_sync_mode() == SEP_SYNC_FULL) sepb_download(b, SEPB_F);
 }
 
@@ -47,13 +47,13 @@ static void after_integrator(sep_binding *b, sepsys *sys, sepret *ret, int count
     sepgpu_scalars s;
     b->last_ret = ret;
     sepb_pull_scalars(b, sys, ret, &s);
-    b->dev_dirty |= SEPB_X | SEPB_V | SEPB_F | SEPB_A | SEPB_CN | SEPB_CR;
+    sepb_dev_newer(b, SEPB_X | SEPB_V | SEPB_F | SEPB_A | SEPB_CN | SEPB_CR);
     if (s.neighb_flag) {                                  /* source/sepintgr.c:72-84 */
         sys->neighb_flag = 1;
         if (count_update) sys->nupdate_neighb++;
         b->dev_dirty |= SEPB_XN;
     }
-    if (sep_sync_mode() != SEP_SYNC_LAZY) sepb_download(b, ~0u);
+    if (sepb_eager(b)) sepb_download(b, ~0u);
 }
 
 void sep_leapfrog(seppart *ptr, sepsys *sys, sepret *retval)
@@ -74,7 +74,7 @@ void sep_verlet_dpd(seppart *ptr, double lambda, int stepnow, sepsys *sys, sepre
     sepgpu_sys gs;
     sepb_fill_sys(sys, &gs);
     sepb_check(sepgpu_verlet_dpd(b->gpu, &gs, lambda, stepnow), "sep_verlet_dpd");
-    b->dev_dirty |= SEPB_PV | SEPB_PA;
+    sepb_dev_newer(b, SEPB_PV | SEPB_PA);
     after_integrator(b, sys, retval, 0);                  /* does not count list updates (:336-342) */
 }
 

@@ -400,6 +400,10 @@ void sep_reset_force_mol(sepsys *sys)
     sys->fun_cstate = 0;
     if (sys->molptr->flag_Fij == 0)
         sep_error("%s: Tried to reset mol force, but flag is zero", (char *)__func__);
+    /* the host copy too (source/sepmisc.c:418-422): it is what callers read before any device call has bound the table */
+    for (unsigned i = 0; i < sys->molptr->num_mols; i++)
+        for (unsigned j = 0; j < sys->molptr->num_mols; j++)
+            for (int k = 0; k < 3; k++) sys->molptr->Fij[i][j][k] = 0.0f;
     sep_binding *b = sepb_find_mol(sys->molptr);
     if (b && b->gpu) {
         sepb_check(sepgpu_fij_enable(b->gpu, (int)sys->molptr->num_mols), "sep_reset_force_mol");
@@ -440,10 +444,20 @@ void sep_eval_mol_pressure_tensor(sepatom *atoms, sepmol *mols, sepret *ret, sep
             for (int k = 0; k < 3; k++)
                 for (int kk = 0; kk < 3; kk++) ret->pot_P_mol[k][kk] += Fij[i][j][k] * rij[kk];
         }
+    /* P_mol and p_mol are filled here as well (source/sepmol.c:950-961) */
+    const double ivol = 1.0 / sys->volume;
+    ret->p_mol = 0.0;
+    for (int k = 0; k < 3; k++) {
+        for (int kk = 0; kk < 3; kk++) ret->P_mol[k][kk] = (ret->kin_P_mol[k][kk] + ret->pot_P_mol[k][kk]) * ivol;
+        ret->p_mol += ret->P_mol[k][k];
+    }
+    ret->p_mol /= 3.0;
 }
 
 void sep_mol_pressure_tensor(sepatom *atoms, sepmol *mols, sepret *ret, sepsys *sys)
 {
+    /* source/sepret.c:85-102: evaluated again here, also when the table is switched off (then from whatever the
+     * kinetic / potential parts hold) */
     const double ivol = 1.0 / sys->volume;
     sep_eval_mol_pressure_tensor(atoms, mols, ret, sys);
     ret->p_mol = 0.0;

@@ -36,7 +36,7 @@ def mock():
     return lib
 
 
-@pytest.mark.parametrize("sync", [1, 0, 2])          # step, lazy, full
+@pytest.mark.parametrize("sync", [1, 0, 2, 3])          # step, lazy, full, auto
 def test_lj_loop_matches_reference_golden(mock, sync):
     """the prg1 loop of tests/test_gpu_more.py::test_sep_api_lj_loop_matches_reference_golden, on the mock"""
     g = np.load(os.path.join(cm.GOLDEN, "lj_n1000.npz"))
@@ -74,6 +74,53 @@ def test_lj_loop_matches_reference_golden(mock, sync):
             nup0 = int(s.sys.nupdate_neighb)
     assert int(s.sys.nupdate_neighb) - nup0 == int(traj[-1, 4] - traj[0, 4])      # rebuilds over the last 39 steps
     s.close()
+    mock.sep_gpu_set_sync(1)
+
+
+def test_auto_mode_notices_host_reads_and_writes(mock):
+    """SEP_SYNC=auto (the default): atoms[] is page-protected while the device copy is newer.  Reading a member right after
+    a hot call -- no sep_gpu_sync -- sees the fresh state; writing members between calls -- no sep_gpu_invalidate -- is
+    picked up by the next hot call (reference callers do both: prgs/prg0.c:64 prints atoms[0].f, prgs/prg5.c writes f)."""
+    g = np.load(os.path.join(cm.GOLDEN, "lj_n1000.npz"))
+    cf, dt = float(g["cf"]), float(g["dt"])
+
+    def system(mode):
+        mock.sep_gpu_set_sync(mode)
+        s = cm.ApiSystem(mock, g["x0"], float(g["L"]), cf, dt, v=g["v0"], nneighb=0)
+        s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+        return s, C.c_double(float(g["alpha0"])), s.fun("sep_lj_shift")
+
+    def step(s, alpha, fun):
+        mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+        mock.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+        mock.sep_nosehoover(s.atoms, float(g["temp"]), C.byref(alpha), float(g["tau"]), s.S)
+        mock.sep_leapfrog(s.atoms, s.S, s.R)
+
+    s, alpha, fun = system(3)
+    mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+    mock.sep_force_pairs(s.atoms, b"AA", cf, fun, s.S, s.R, 1)
+    assert cm.rel_force_err(s.view["f"].copy(), g["f_pairs"]) <= 1e-11          # read after a force call: no sync call
+    mock.sep_nosehoover(s.atoms, float(g["temp"]), C.byref(alpha), float(g["tau"]), s.S)
+    mock.sep_leapfrog(s.atoms, s.S, s.R)
+    assert np.abs(s.view["x"].copy() - g["x1"]).max() <= 1e-12 and np.abs(s.view["v"].copy() - g["v1"]).max() <= 1e-12
+    for _ in range(3):                                                          # untouched steps in between
+        step(s, alpha, fun)
+    s.view["v"][:] = s.view["v"] * 0.5                                          # user code writes velocities: no invalidate
+    s.view["f"][:, 0] += 0.0
+    for _ in range(3):
+        step(s, alpha, fun)
+    xa, va, ea = s.view["x"].copy(), s.view["v"].copy(), s.ret.ekin
+    s.close()
+    # the same protocol in step mode with the explicit calls
+    t, alpha, fun = system(1)
+    for _ in range(4):
+        step(t, alpha, fun)
+    t.view["v"][:] = t.view["v"] * 0.5
+    mock.sep_gpu_invalidate(t.atoms)
+    for _ in range(3):
+        step(t, alpha, fun)
+    assert np.array_equal(xa, t.view["x"]) and np.array_equal(va, t.view["v"]) and ea == t.ret.ekin
+    t.close()
     mock.sep_gpu_set_sync(1)
 
 
