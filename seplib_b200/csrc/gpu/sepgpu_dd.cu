@@ -103,6 +103,9 @@ struct DDState {
     size_t peer_cap[2];               // atoms the lo / hi neighbour's buffers hold
     unsigned long long seq;           // halo refreshes so far (identical on all ranks)
     unsigned int *done_ctr;
+    // migration through the same blocks (peer-memory path): count mailboxes and "records delivered" flags in the header
+    size_t mig_off;                   // MigBox box[2] (written by the hi / lo neighbour), then u64 flag2[2]
+    unsigned long long mseq;          // rebuilds so far (identical on all ranks)
     // all ranks' blocks (for the all-gather of the integrator sums)
     void *peer_all[64];
     unsigned char **bases_dev;
@@ -145,6 +148,7 @@ static int p2p_setup(sepgpu_ctx *c)
     d->ipc_flag_off = 0;
     d->gather_off = 256;
     d->gflag_off = d->gather_off + sizeof(double) * 2 * 64 * SEPGPU_GATHER_W;
+    d->mig_off = 20480;                                   // behind the gather table and its flags (end at 17664)
     const size_t hdr = 32768;
     const size_t total = hdr + 2 * buf_bytes;
     cudaIpcMemHandle_t mine;
@@ -470,6 +474,235 @@ static int exchange(sepgpu_ctx *c, const void *send_lo, size_t n_lo, const void 
     return 0;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---- migration and halo membership through peer memory (no NCCL call, one host read per rebuild) ----------------
+// Round 1: every rank classifies its atoms, counts who leaves towards which neighbour and who stays in a boundary layer,
+// and stores those two numbers into the neighbour's mailbox; it then waits for the neighbours' numbers.  By the time a
+// neighbour has posted its counts it has finished the previous step, so its receive buffers are free.
+// Round 2: one kernel compacts the stayers, writes the leavers' full records and the boundary stayers' (position, id)
+// STRAIGHT INTO the neighbours' receive buffers over NVLink and raises their "delivered" flags; a second kernel waits for
+// both neighbours' flags and unpacks.  The atoms a rank has just sent away are exactly the halo atoms it still needs from
+// that side, so they are appended to its halo locally and never travel back.
+struct MigBox { unsigned long long seq; int n_mig, n_bnd; int pad[4]; };      // 32 bytes
+
+__global__ void k_dd_classify2(const d4 *__restrict__ x4, int n_own, double lsz, int nzg, int z0, int z1,
+                               int *f_stay, int *f_lo, int *f_hi, int *f_blo, int *f_bhi, DevScalars *scal)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_own) return;
+    const int cz = (int)__ddiv_rn(x4[i].z, lsz);                 // reference binning (source/sepprfrc.c:406)
+    int stay = 0, lo = 0, hi = 0;
+    if (cz >= z0 && cz < z1) stay = 1;
+    else if (cz == (z0 - 1 + nzg) % nzg) lo = 1;
+    else if (cz == z1 % nzg) hi = 1;
+    else scal->error = SEPGPU_ECELL;                             // moved more than one layer, or left the box
+    f_stay[i] = stay; f_lo[i] = lo; f_hi[i] = hi;
+    f_blo[i] = stay && cz == z0; f_bhi[i] = stay && cz == z1 - 1;
+}
+
+// counts_dev: [0] stay [1] to_lo [2] to_hi [3] bnd_lo [4] bnd_hi | from the hi neighbour: [5] migrants [6] boundary stayers |
+//             from the lo neighbour: [7] migrants [8] boundary stayers
+__global__ void k_dd_post_counts(const int *p_stay, const int *p_lo, const int *p_hi, const int *p_blo, const int *p_bhi, int n,
+                                 MigBox *lo_box_from_above, MigBox *hi_box_from_below, const MigBox *my_boxes,
+                                 unsigned long long seq, int *counts, DevScalars *scal)
+{
+    if (threadIdx.x != 0) return;
+    counts[0] = p_stay[n]; counts[1] = p_lo[n]; counts[2] = p_hi[n]; counts[3] = p_blo[n]; counts[4] = p_bhi[n];
+    lo_box_from_above->n_mig = counts[1]; lo_box_from_above->n_bnd = counts[3];
+    hi_box_from_below->n_mig = counts[2]; hi_box_from_below->n_bnd = counts[4];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&lo_box_from_above->seq), "l"(seq) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&hi_box_from_below->seq), "l"(seq) : "memory");
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&my_boxes[0].seq) < seq || ld_acquire_sys(&my_boxes[1].seq) < seq) {
+        if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+        __nanosleep(100);
+    }
+    const volatile MigBox *b = my_boxes;
+    counts[5] = b[0].n_mig; counts[6] = b[0].n_bnd; counts[7] = b[1].n_mig; counts[8] = b[1].n_bnd;
+}
+
+// peer_lo / peer_hi: the neighbours' receive buffers: [n_to * REC_D4 migrant records][n_bnd * 2 boundary records]
+// keep_lo / keep_hi: (position, id) of my own leavers, which stay with me as halo atoms from that side
+__global__ void k_dd_split2(const d4 *__restrict__ x4, const d4 *__restrict__ v4, const d4 *__restrict__ xn4,
+                            const i4 *__restrict__ cr4, const int *__restrict__ crossings, const int *__restrict__ gid,
+                            int n_own, const int *__restrict__ pos_stay, const int *__restrict__ pos_lo,
+                            const int *__restrict__ pos_hi, const int *__restrict__ pos_blo, const int *__restrict__ pos_bhi,
+                            d4 *x4b, d4 *v4b, d4 *xn4b, i4 *cr4b, int *crossb, int *gidb,
+                            d4 *peer_lo, d4 *peer_hi, int n_to_lo, int n_to_hi, d4 *keep_lo, d4 *keep_hi,
+                            int *send_idx_lo, int *send_idx_hi,
+                            unsigned long long *flag_lo, unsigned long long *flag_hi, unsigned long long seq, unsigned int *done)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_own) {
+        const int ps = pos_stay[i];
+        if (pos_stay[i + 1] > ps) {
+            const d4 x = x4[i];
+            x4b[ps] = x; v4b[ps] = v4[i]; xn4b[ps] = xn4[i]; cr4b[ps] = cr4[i];
+            crossb[3 * ps] = crossings[3 * i]; crossb[3 * ps + 1] = crossings[3 * i + 1]; crossb[3 * ps + 2] = crossings[3 * i + 2];
+            const int g = gid[i];
+            gidb[ps] = g;
+            d4 a; a.x = __longlong_as_double((long long)g); a.y = a.z = a.w = 0.0;
+            const int bl = pos_blo[i], bh = pos_bhi[i];
+            if (pos_blo[i + 1] > bl) {                   // boundary layer towards lo: halo atom of the lo neighbour
+                d4 *rec = peer_lo + (size_t)n_to_lo * REC_D4 + 2 * (size_t)bl;
+                rec[0] = x; rec[1] = a;
+                send_idx_lo[bl] = ps;
+            }
+            if (pos_bhi[i + 1] > bh) {
+                d4 *rec = peer_hi + (size_t)n_to_hi * REC_D4 + 2 * (size_t)bh;
+                rec[0] = x; rec[1] = a;
+                send_idx_hi[bh] = ps;
+            }
+        } else {
+            const int pl = pos_lo[i];
+            const bool to_lo = pos_lo[i + 1] > pl;
+            const int p = to_lo ? pl : pos_hi[i];
+            d4 *rec = (to_lo ? peer_lo : peer_hi) + (size_t)p * REC_D4;
+            const d4 x = x4[i];
+            const int g = gid[i];
+            rec[0] = x; rec[1] = v4[i]; rec[2] = xn4[i];
+            rec[3] = pack_aux(cr4[i], crossings + 3 * i, g);
+            d4 *kp = (to_lo ? keep_lo : keep_hi) + 2 * (size_t)p;
+            d4 a; a.x = __longlong_as_double((long long)g); a.y = a.z = a.w = 0.0;
+            kp[0] = x; kp[1] = a;
+        }
+    }
+    // every block publishes its stores system-wide, the last one to finish raises both neighbours' flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(done, 1u);
+        if (t == gridDim.x - 1) {
+            *done = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_lo), "l"(seq) : "memory");
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_hi), "l"(seq) : "memory");
+        }
+    }
+}
+
+__device__ __forceinline__ d4 ld_peer_d4(const d4 *p)             // written by another GPU: never through L1
+{
+    const double2 *s = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldcg(s), b = __ldcg(s + 1);
+    d4 v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
+    return v;
+}
+
+// Work items: [migrants from hi][migrants from lo][halo from hi: its boundary stayers, my leavers to hi][halo from lo: ...]
+__global__ void k_dd_unpack2(const d4 *from_hi, const d4 *from_lo, const d4 *__restrict__ keep_lo, const d4 *__restrict__ keep_hi,
+                             int n_stay, int m_hi, int m_lo, int b_hi, int b_lo, int n_to_hi, int n_to_lo, int nb_lo, int nb_hi,
+                             d4 *x4, d4 *v4, d4 *xn4, i4 *cr4, int *crossings, int *gid, int *send_idx_lo, int *send_idx_hi,
+                             const unsigned long long *flags2, unsigned long long seq, DevScalars *scal)
+{
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags2) < seq || ld_acquire_sys(flags2 + 1) < seq) {
+            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_own = n_stay + m_hi + m_lo;
+    if (k < m_hi + m_lo) {                                        // migrants: full records
+        const bool lo = k >= m_hi;
+        const int q = lo ? k - m_hi : k;
+        const d4 *rec = (lo ? from_lo : from_hi) + (size_t)q * REC_D4;
+        const int i = n_stay + k;
+        x4[i] = ld_peer_d4(rec); v4[i] = ld_peer_d4(rec + 1); xn4[i] = ld_peer_d4(rec + 2);
+        i4 cr; int g;
+        unpack_aux(ld_peer_d4(rec + 3), cr, crossings + 3 * i, g);
+        cr4[i] = cr; gid[i] = g;
+        // an atom that arrived from below sits in my lowest layer: the lo neighbour needs it as halo (and likewise above)
+        if (lo) send_idx_lo[nb_lo + q] = i; else send_idx_hi[nb_hi + q] = i;
+        return;
+    }
+    k -= m_hi + m_lo;
+    const int h_hi = b_hi + n_to_hi, h_lo = b_lo + n_to_lo;
+    if (k >= h_hi + h_lo) return;
+    const bool lo = k >= h_hi;
+    const int q = lo ? k - h_hi : k;
+    const int nb = lo ? b_lo : b_hi;
+    d4 x, a;
+    if (q < nb) {                                                 // the neighbour's boundary stayers
+        const d4 *rec = (lo ? from_lo + (size_t)m_lo * REC_D4 : from_hi + (size_t)m_hi * REC_D4) + 2 * (size_t)q;
+        x = ld_peer_d4(rec); a = ld_peer_d4(rec + 1);
+    } else {                                                      // the atoms I have just handed to that neighbour
+        const d4 *rec = (lo ? keep_lo : keep_hi) + 2 * (size_t)(q - nb);
+        x = rec[0]; a = rec[1];
+    }
+    const int i = n_own + k;
+    x4[i] = x;
+    gid[i] = (int)__double_as_longlong(a.x);
+    d4 v; v.x = v.y = v.z = 0.0; v.w = 1.0; v4[i] = v;
+    i4 z; z.x = z.y = z.z = z.w = 0; cr4[i] = z;
+}
+
+static int before_build_p2p(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local)
+{
+    DDState *d = c->dd;
+    const double lsz = sys->lsubbox[2];
+    const int B = 256;
+    int n_own = c->n_own;
+    const int G = n_own ? (n_own + B - 1) / B : 1;
+    int rc;
+    d->mseq++;
+    MigBox *my_boxes = (MigBox *)(d->ipc_base + d->mig_off);
+    MigBox *lo_box = (MigBox *)((unsigned char *)d->peer_base[0] + d->mig_off);            // lo neighbour's "from above" box
+    MigBox *hi_box = (MigBox *)((unsigned char *)d->peer_base[1] + d->mig_off) + 1;        // hi neighbour's "from below" box
+    unsigned long long *my_flags2 = (unsigned long long *)(d->ipc_base + d->mig_off + 2 * sizeof(MigBox));
+    unsigned long long *lo_flag2 = (unsigned long long *)((unsigned char *)d->peer_base[0] + d->mig_off + 2 * sizeof(MigBox));
+    unsigned long long *hi_flag2 = (unsigned long long *)((unsigned char *)d->peer_base[1] + d->mig_off + 2 * sizeof(MigBox)) + 1;
+    ktimer_begin(c, &c->t_migr);
+    k_dd_classify2<<<G, B, 0, c->stream>>>(c->x4, n_own, lsz, d->nzg, d->z0, d->z1, d->flag[0], d->flag[1], d->flag[2], d->flag[3], d->flag[4], c->scal);
+    for (int k = 0; k < 5; k++)
+        if ((rc = sepgpu_exclusive_scan(c->stream, d->flag[k], d->pos[k], d->scan_scratch, n_own))) return rc;
+    k_dd_post_counts<<<1, 32, 0, c->stream>>>(d->pos[0], d->pos[1], d->pos[2], d->pos[3], d->pos[4], n_own, lo_box, hi_box, my_boxes,
+                                             d->mseq, d->counts_dev, c->scal);
+    if ((rc = read_counts(c, 9))) return rc;
+    const int *h = d->counts_host;
+    const int n_stay = h[0], n_to_lo = h[1], n_to_hi = h[2], nb_lo = h[3], nb_hi = h[4];
+    const int m_hi = h[5], b_hi = h[6], m_lo = h[7], b_lo = h[8];          // arriving from hi / lo: migrants, boundary stayers
+    const size_t need_lo = (size_t)n_to_lo * REC_D4 + 2 * (size_t)nb_lo, need_hi = (size_t)n_to_hi * REC_D4 + 2 * (size_t)nb_hi;
+    const int n_new = n_stay + m_hi + m_lo;
+    const int n_halo = b_hi + n_to_hi + b_lo + n_to_lo;
+    if (need_lo > d->peer_cap[0] || need_hi > d->peer_cap[1] || (size_t)(nb_lo + m_lo) > d->bufcap || (size_t)(nb_hi + m_hi) > d->bufcap ||
+        2 * (size_t)n_to_lo > d->bufcap * REC_D4 || 2 * (size_t)n_to_hi > d->bufcap * REC_D4 || n_new + n_halo > c->ncap) {
+        sepgpu_set_error("decomposed rebuild: migration / halo exceeds the buffers (stay %d, out %d/%d, in %d/%d, halo %d, cap %d)",
+                         n_stay, n_to_lo, n_to_hi, m_hi, m_lo, n_halo, c->ncap);
+        return SEPGPU_EINVAL;
+    }
+    k_dd_split2<<<G, B, 0, c->stream>>>(c->x4, c->v4, c->xn4, c->cr4, c->crossings, c->gid, n_own, d->pos[0], d->pos[1], d->pos[2],
+        d->pos[3], d->pos[4], d->x4b, d->v4b, d->xn4b, d->cr4b, d->crossb, d->gidb, d->peer_dst[0], d->peer_dst[1], n_to_lo, n_to_hi,
+        d->send[0], d->send[1], d->send_idx[0], d->send_idx[1], lo_flag2, hi_flag2, d->mseq, d->done_ctr);
+    { d4 *t; i4 *ti; int *tn;
+      t = c->x4; c->x4 = d->x4b; d->x4b = t;  t = c->v4; c->v4 = d->v4b; d->v4b = t;  t = c->xn4; c->xn4 = d->xn4b; d->xn4b = t;
+      ti = c->cr4; c->cr4 = d->cr4b; d->cr4b = ti;  tn = c->crossings; c->crossings = d->crossb; d->crossb = tn;
+      tn = c->gid; c->gid = d->gidb; d->gidb = tn; }
+    const int nwork = m_hi + m_lo + n_halo;
+    k_dd_unpack2<<<nwork ? (nwork + B - 1) / B : 1, B, 0, c->stream>>>(d->p2p_recv[0], d->p2p_recv[1], d->send[0], d->send[1],
+        n_stay, m_hi, m_lo, b_hi, b_lo, n_to_hi, n_to_lo, nb_lo, nb_hi, c->x4, c->v4, c->xn4, c->cr4, c->crossings, c->gid,
+        d->send_idx[0], d->send_idx[1], my_flags2, d->mseq, c->scal);
+    ktimer_end(c, &c->t_migr);
+    KERNEL_CHECK();
+    d->n_send[0] = nb_lo + m_lo; d->n_send[1] = nb_hi + m_hi;
+    d->n_recv[0] = b_hi + n_to_hi; d->n_recv[1] = b_lo + n_to_lo;           // from hi, from lo
+    c->n_own = n_new;
+    c->n = n_new + n_halo;
+    d->halo_current = true;
+    *zoff = d->z0 - 1;
+    *nz_local = (d->z1 - d->z0) + 2;
+    return 0;
+}
+
 int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local)
 {
     DDState *d = c->dd;
@@ -479,6 +712,7 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
         return SEPGPU_ESTATE;
     }
     if (sys->nsubbox[2] != d->nzg) { sepgpu_set_error("decomposed run: the cell grid along z changed"); return SEPGPU_ESTATE; }
+    if (d->p2p) return before_build_p2p(c, sys, zoff, nz_local);
     const double lsz = sys->lsubbox[2];
     const int B = 256;
     int n_own = c->n_own;
@@ -609,13 +843,6 @@ __global__ void k_dd_push_xu2(const d4 *__restrict__ x4, const i4 *__restrict__ 
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag1), "l"(seq) : "memory");
         }
     }
-}
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
 }
 
 // waits until both neighbours have delivered refresh number `seq`, then scatters into the halo slots of xs.

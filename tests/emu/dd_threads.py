@@ -26,7 +26,7 @@ from seplib_b200 import capi  # noqa: E402
 capi.LIB_PATH = build_emu.build()
 import common as cm  # noqa: E402
 
-WORLD = 2
+WORLD = int(os.environ.get("DD_WORLD", "2"))
 
 
 def main():
@@ -102,14 +102,14 @@ def main():
     ref.call("sepgpu_set_alpha", 0, 0.1)
     ok = True
     checked = 0
-    r0, r1 = shared["rec"]
+    recs = shared["rec"]
     for step in range(nsteps):
         ref.call("sepgpu_reset_ret"); ref.call("sepgpu_reset_force")
         ref.call("sepgpu_force_lj", C.byref(gsys), b"AA", C.byref(p), 1, 1)
         rs = ref.scalars()
         if step in check_steps:
             want = cm.pair_set(ref.pairs())
-            got = cm.pair_set(np.concatenate([r0[step][7], r1[step][7]]))
+            got = cm.pair_set(np.concatenate([r[step][7] for r in recs]))
             checked += 1
             if not np.array_equal(got, want):
                 print(f"step {step}: pair sets differ: dd {len(got)} vs single {len(want)}")
@@ -118,7 +118,7 @@ def main():
         ref.call("sepgpu_leapfrog", C.byref(gsys))
         rs2 = ref.scalars()
         tol = 1e-9 * (step + 1)
-        for rk, rec in enumerate((r0, r1)):
+        for rk, rec in enumerate(recs):
             e, k, a, md, vir, flag, nb, _ = rec[step]
             for name, got_v, want_v in (("epot", e, rs.epot), ("ekin", k, rs2.ekin), ("alpha", a, rs2.alpha[0]),
                                         ("maxd2", md, rs2.max_dist2), ("virial", vir, rs.pot_P[0])):

@@ -55,12 +55,12 @@ def test_two_rank_decomposition_on_the_emulator():
     emulator hands out in-process IPC handles; the two ranks' kernels run concurrently and meet at release/acquire
     flags), also with global-index rows and the unfolded step, and NCCL send/recv + all-reduce (tests/emu/fake_nccl.cpp).
     The three runs go side by side."""
-    cases = {"peer-memory": ("", "0"), "peer-memory+old-kernels": ("step_fold=0,tile_list=0,fin_multi=0", "0"),
-             "nccl-path": ("", "1")}
-    procs = {k: subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "14", "14", opts],
+    cases = {"peer-memory": ("", "0", "2", "14"), "peer-memory+old-kernels": ("step_fold=0,tile_list=0,fin_multi=0", "0", "2", "14"),
+             "nccl-path": ("", "1", "2", "14"), "peer-memory-3-ranks": ("", "0", "3", "18")}
+    procs = {k: subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), ncell, "14", opts],
                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
-                                 env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc))
-             for k, (opts, no_ipc) in cases.items()}
+                                 env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc, DD_WORLD=world))
+             for k, (opts, no_ipc, world, ncell) in cases.items()}
     for k, p in procs.items():
         out, err = p.communicate(timeout=900)
         assert p.returncode == 0 and "-> OK" in out, (k, out[-2000:], err[-2000:])

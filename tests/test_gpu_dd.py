@@ -27,4 +27,4 @@ def test_two_rank_decomposition_matches_oracle(ncell):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(cm.ROOT, "tests", "dd_check.py")],
                        env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "-> OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "-> OK" in (r.stdout + r.stderr), (r.stdout[-2000:], r.stderr[-2000:])

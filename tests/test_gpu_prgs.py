@@ -71,7 +71,9 @@ def test_prg1_nvt_list(tmp_path):
     assert got.shape == ref.shape
     assert np.allclose(got[0, 2:6], ref[0, 2:6], rtol=0, atol=2e-6)
     assert abs(got[5:, 4].mean() - ref[5:, 4].mean()) < 0.01                 # thermostatted temperature
-    assert abs(got[5:, 2].mean() - ref[5:, 2].mean()) < 0.01                 # epot/N
+    # epot/N: 95 printed samples of a 1000-atom system scatter by ~0.03 each (independent at this print interval), so the
+    # two means differ by ~0.005 rms once the trajectories have decorrelated; 4 sigma
+    assert abs(got[5:, 2].mean() - ref[5:, 2].mean()) < 0.02
     assert abs(got[5:, 7].mean() - ref[5:, 7].mean()) < 0.05                 # pressure
     assert np.allclose(got[5:, 8].mean(), ref[5:, 8].mean(), rtol=0.03)      # steps per list rebuild
 
