@@ -749,7 +749,7 @@ def main():
     if decomposed:
         # decomposed vs single-GPU run of a small system (pair sets, sums, final positions), before anything is timed
         import dd_check as ddc
-        dd_check = ddc.run(rank, world, local_rank, 40, max(28, 5 * world), verbose=(rank == 0))
+        dd_check = ddc.run(rank, world, local_rank, 40, max(28, 6 * world), verbose=(rank == 0))      # >= 2 cell layers per rank
         if not dd_check["ok"]:
             raise RuntimeError("bench.py: the decomposed run does not reproduce the single-GPU run: %r" % (dd_check,))
     s = new_system()

@@ -936,7 +936,33 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys)
     return rc;
 }
 
-void sepgpu_dd_positions_moved(sepgpu_ctx *c) { if (c->dd) c->dd->halo_current = false; }
+void sepgpu_dd_positions_moved(sepgpu_ctx *c)
+{
+    if (!c->dd) return;
+    c->dd->halo_current = false;
+    if (c->dd->p2p) c->dd->halo_inflight = false;        // a pushed refresh nobody unpacked is simply obsolete now
+}
+
+// The tile force kernels consume the neighbours' boundary coordinates straight from the receive buffers: push mine
+// (if this step's refresh has not gone out yet) and tell the kernel where to wait and read.  Returns 1 when `out` is
+// valid, 0 when the caller has to refresh xs the ordinary way (not decomposed on the peer-memory path), < 0 on error.
+int sepgpu_dd_halo_args(sepgpu_ctx *c, const sepgpu_sys *sys, HaloArgs *out)
+{
+    memset(out, 0, sizeof *out);
+    DDState *d = c->dd;
+    if (!d || !d->p2p) return 0;
+    if (!d->halo_current) {
+        ktimer_begin(c, &c->t_halo);
+        const int rc = sepgpu_dd_halo_begin(c, sys);      // no-op when this step's push is already under way
+        ktimer_end(c, &c->t_halo);
+        if (rc < 0) return rc;
+        out->seq = d->seq;                                // halo_current: the list build has just placed the halo in xs itself
+    }
+    out->in0 = d->p2p_recv[0]; out->in1 = d->p2p_recv[1];
+    out->n0 = d->n_recv[0]; out->n_own = c->n_own;
+    out->flags = d->p2p_flag;
+    return 1;
+}
 
 // ---- scalars: force-derived sums are kept per rank and summed when read -----------------------------------
 __global__ void k_dd_gather_force_scalars(const DevScalars *s, double *comm)

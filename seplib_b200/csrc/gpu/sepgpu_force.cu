@@ -371,7 +371,7 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_end(sepgpu_ctx *c);
 int sepgpu_need_global_rows(sepgpu_ctx *c, const sepgpu_sys *sys);
-int sepgpu_lj_tile_launch(sepgpu_ctx *c, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows);
+int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows);
 
 // Option fin_multi: the same reduction spread over several CTAs.  CTA b sums a fixed chunk of rows into stage row b;
 // the CTA that draws the last ticket adds the stage rows in index order and applies the result -- fixed chunks and a
@@ -647,10 +647,9 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
         if ((rc = sepgpu_need_global_rows(c, sys))) return rc;
     }
     if (c->list_f16) {                                   // rows of 16-bit tile slots: shared-memory staged tile kernel
-        if (c->dd && (rc = sepgpu_dd_halo_update(c, sys))) return rc;     // neighbours' boundary atoms moved too
         int nrows = 0;
         ktimer_begin(c, &c->t_force);
-        rc = sepgpu_lj_tile_launch(c, P, B, typed, store, &nrows);
+        rc = sepgpu_lj_tile_launch(c, sys, P, B, typed, store, &nrows);
         ktimer_end(c, &c->t_force);
         if (rc) return rc;
         c->f_zero = false;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
 k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, const int4 *__restrict__ tile_hdr, const unsigned *__restrict__ tile_src,
           d4 *__restrict__ f4, int stride, int npad, int stage_cap, LJDev P, BoxDev B, double isig,
-          double *__restrict__ partial)
+          double *__restrict__ partial, HaloArgs H, DevScalars *scal)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nslot = stage_cap + TILE_PAD;
@@ -107,10 +107,28 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
 
     const int4 hdr = tile_hdr[blockIdx.x];
     const int a0 = hdr.x, nhome = hdr.y, total = hdr.z;
-    const bool image = hdr.w != 0;
+    const bool image = (hdr.w & 1) != 0;
+    // slab runs on the peer-memory path: the neighbours store their boundary coordinates straight into this rank's
+    // receive buffers every step and raise a flag.  Only tiles next to a halo layer wait for it -- every other CTA of
+    // this launch computes while the transfer is still on its way -- and they read the halo atoms from those buffers.
+    const bool halo = (hdr.w & 2) != 0 && H.seq != 0;
     if (nhome == 0 || total > stage_cap) {                           // (the second cannot happen: the builder sized stage_cap)
         if (threadIdx.x < SEPGPU_NPART_F) partial[blockIdx.x * SEPGPU_NPART_F + threadIdx.x] = 0.0;
         return;
+    }
+    if (halo) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            unsigned long long f0, f1;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f0) : "l"(H.flags) : "memory");
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f1) : "l"(H.flags + 1) : "memory");
+                if (f0 >= H.seq && f1 >= H.seq) break;
+                if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+                __nanosleep(100);
+            } while (true);
+        }
+        __syncthreads();
     }
     // ---- stage the current coordinates of every candidate of the tile once; four independent loads in flight per
     // thread, image shift and 1/sigma on the way ----
@@ -126,7 +144,19 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
                 e[u] = q < total ? __ldg(src + q) : 0xffffffffu;
             }
 #pragma unroll
-            for (int u = 0; u < UN; u++) if (e[u] != 0xffffffffu) p[u] = xs[e[u] & SEPGPU_INDEX_MASK];
+            for (int u = 0; u < UN; u++) {
+                if (e[u] == 0xffffffffu) continue;
+                const int j = (int)(e[u] & SEPGPU_INDEX_MASK);
+                int k = -1;
+                if (halo) k = order[j] - H.n_own;                 // >= 0: a halo atom, k-th in arrival order
+                if (k >= 0) {
+                    const double2 *sp = reinterpret_cast<const double2 *>(k < H.n0 ? H.in0 + k : H.in1 + (k - H.n0));
+                    const double2 a = __ldcg(sp), b = __ldcg(sp + 1);       // written by another GPU: never through L1
+                    p[u].x = a.x; p[u].y = a.y; p[u].z = b.x; p[u].w = b.y;
+                } else {
+                    p[u] = xs[j];
+                }
+            }
 #pragma unroll
             for (int u = 0; u < UN; u++) {
                 if (e[u] != 0xffffffffu) {
@@ -211,8 +241,17 @@ size_t sepgpu_tile_force_smem(int stage_cap)
 }
 
 // Launches the tile kernel on the context's current tile-format list; returns the number of partial rows.
-int sepgpu_lj_tile_launch(sepgpu_ctx *c, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows)
+int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows)
 {
+    // decomposed run: peer-memory path -> the kernel waits for and reads the neighbours' coordinates itself;
+    // otherwise refresh the halo entries of xs first
+    HaloArgs H;
+    memset(&H, 0, sizeof H);
+    if (c->dd) {
+        int rh = sepgpu_dd_halo_args(c, sys, &H);
+        if (rh < 0) return rh;
+        if (rh == 0 && (rh = sepgpu_dd_halo_update(c, sys))) return rh;
+    }
     const int grid = c->tile_count;
     const int stage_cap = c->tile_stage_used;
     const size_t smem = sepgpu_tile_force_smem(stage_cap);
@@ -224,7 +263,7 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const LJDev &P, const BoxDev &B, bool t
     do {                                                                                                                         \
         CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         k_lj_tile<TY, ST, MB><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt,   \
-            c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial);             \
+            c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);    \
     } while (0)
 #define LJT_LAUNCH(TY, ST) do { if (c->ljt_ctas == 4) LJT_LAUNCH3(TY, ST, 4); else LJT_LAUNCH3(TY, ST, 3); } while (0)
     if (typed) { if (store) LJT_LAUNCH(true, true); else LJT_LAUNCH(true, false); }

@@ -308,6 +308,16 @@ struct GatherDev {
     int rank, nranks;
 };
 
+// decomposed runs on the peer-memory path: where a kernel finds the neighbours' freshly pushed boundary coordinates
+// (sepgpu_dd.cu fills it; the tile force kernels wait on the flags themselves and read the buffers directly)
+struct HaloArgs {
+    const d4 *in0, *in1;                 // my from-hi / from-lo receive buffers (written by the neighbours over NVLink)
+    int n0, n_own;                       // halo atoms from hi (the ones from lo follow); local atoms n_own.. are the halo
+    const unsigned long long *flags;     // [0] raised by the hi neighbour, [1] by the lo neighbour
+    unsigned long long seq;              // refresh number to wait for; 0 = nothing to wait for (not decomposed)
+};
+int sepgpu_dd_halo_args(sepgpu_ctx *c, const sepgpu_sys *sys, HaloArgs *out);
+
 // internal cross-file entry points
 int sepgpu_ensure_stage(sepgpu_ctx *c, size_t bytes);
 int sepgpu_apply_pending(sepgpu_ctx *c);          // flush a deferred thermostat update into f4

@@ -110,7 +110,8 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
     if (threadIdx.x == 0) {
         atomicMax(&scal->stage_used, total);
         // what the force kernels need to know about this tile: home atoms [a0, a0 + nhome), staged atoms, image flag
-        tile_hdr[blockIdx.x] = make_int4(T.a0, T.nhome, total, T.any_image);
+        // flags: bit 0 some candidate is a periodic image, bit 1 (slab runs) some candidate is a halo atom
+        tile_hdr[blockIdx.x] = make_int4(T.a0, T.nhome, total, T.any_image | ((G.dd && (T.cz == 1 || T.cz == G.nz - 2)) ? 2 : 0));
     }
     // ---- stage every candidate of the tile once: warps take cells, lanes take atoms; cp.async copies (all of a thread's
     // loads in flight at once), then every thread finishes the slots it copied: image shift, list entry in .w ----
