@@ -104,8 +104,6 @@ struct DDState {
     unsigned long long seq;           // halo refreshes so far (identical on all ranks)
     unsigned int *done_ctr;
     // migration through the same blocks (peer-memory path): count mailboxes and "records delivered" flags in the header
-    int2 *halo_slot;                  // [ncap] per owned atom: slot in the lo / hi neighbour's receive buffer or -1 (rebuilt with the list)
-    bool slots_valid;
     size_t mig_off;                   // MigBox box[2] (written by the hi / lo neighbour), then u64 flag2[2]
     unsigned long long mseq;          // rebuilds so far (identical on all ranks)
     // all ranks' blocks (for the all-gather of the integrator sums)
@@ -251,8 +249,7 @@ extern "C" int sepgpu_dd_init(sepgpu_ctx *c, int rank, int nranks, const void *i
     NCCL_TRY(g_nccl.CommInitRank(&d->comm, nranks, id, rank));
     const size_t cap = (size_t)c->ncap;
     // a boundary layer holds about n_own / (owned layers); leave generous head-room
-    // (the per-step coordinate refresh is double-buffered inside these buffers: each half must hold one boundary layer)
-    d->bufcap = cap / (size_t)(d->z1 - d->z0) * 3 + 8192;
+    d->bufcap = cap / (size_t)(d->z1 - d->z0) * 2 + 4096;
     if (d->bufcap > cap) d->bufcap = cap;
     if (nranks > 64) { sepgpu_set_error("dd_init: at most 64 ranks"); return SEPGPU_EINVAL; }
     if (dmalloc(&d->comm_buf, 160)) return SEPGPU_ECUDA;
@@ -306,7 +303,6 @@ void sepgpu_dd_destroy(sepgpu_ctx *c)
     if (d->bases_dev) cudaFree(d->bases_dev);
     if (d->ipc_base) cudaFree(d->ipc_base);
     if (d->done_ctr) cudaFree(d->done_ctr);
-    if (d->halo_slot) cudaFree(d->halo_slot);
     if (d->ev_ready) cudaEventDestroy(d->ev_ready);
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     if (d->comm) g_nccl.CommDestroy(d->comm);
@@ -650,18 +646,6 @@ __global__ void k_dd_unpack2(const d4 *from_hi, const d4 *from_lo, const d4 *__r
     i4 z; z.x = z.y = z.z = z.w = 0; cr4[i] = z;
 }
 
-__global__ void k_dd_clear_slots(int2 *slot, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) slot[i] = make_int2(-1, -1);
-}
-__global__ void k_dd_fill_slots(int2 *slot, const int *__restrict__ idx0, int n0, const int *__restrict__ idx1, int n1)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n0) slot[idx0[k]].x = k;
-    else if (k < n0 + n1) slot[idx1[k - n0]].y = k - n0;
-}
-
 static int before_build_p2p(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int *nz_local)
 {
     DDState *d = c->dd;
@@ -690,9 +674,7 @@ static int before_build_p2p(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int
     const size_t need_lo = (size_t)n_to_lo * REC_D4 + 2 * (size_t)nb_lo, need_hi = (size_t)n_to_hi * REC_D4 + 2 * (size_t)nb_hi;
     const int n_new = n_stay + m_hi + m_lo;
     const int n_halo = b_hi + n_to_hi + b_lo + n_to_lo;
-    if ((size_t)(nb_lo + m_lo) > d->peer_cap[0] / 2 || (size_t)(nb_hi + m_hi) > d->peer_cap[1] / 2 ||
-        (size_t)(b_hi + n_to_hi) > d->bufcap / 2 || (size_t)(b_lo + n_to_lo) > d->bufcap / 2 ||
-        need_lo > d->peer_cap[0] || need_hi > d->peer_cap[1] || (size_t)(nb_lo + m_lo) > d->bufcap || (size_t)(nb_hi + m_hi) > d->bufcap ||
+    if (need_lo > d->peer_cap[0] || need_hi > d->peer_cap[1] || (size_t)(nb_lo + m_lo) > d->bufcap || (size_t)(nb_hi + m_hi) > d->bufcap ||
         2 * (size_t)n_to_lo > d->bufcap * REC_D4 || 2 * (size_t)n_to_hi > d->bufcap * REC_D4 || n_new + n_halo > c->ncap) {
         sepgpu_set_error("decomposed rebuild: migration / halo exceeds the buffers (stay %d, out %d/%d, in %d/%d, halo %d, cap %d)",
                          n_stay, n_to_lo, n_to_hi, m_hi, m_lo, n_halo, c->ncap);
@@ -709,12 +691,6 @@ static int before_build_p2p(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int
     k_dd_unpack2<<<nwork ? (nwork + B - 1) / B : 1, B, 0, c->stream>>>(d->p2p_recv[0], d->p2p_recv[1], d->send[0], d->send[1],
         n_stay, m_hi, m_lo, b_hi, b_lo, n_to_hi, n_to_lo, nb_lo, nb_hi, c->x4, c->v4, c->xn4, c->cr4, c->crossings, c->gid,
         d->send_idx[0], d->send_idx[1], my_flags2, d->mseq, c->scal);
-    // per-atom send slots for the integrator's fused push
-    if (!d->halo_slot) CUDA_TRY(cudaMalloc((void **)&d->halo_slot, sizeof(int2) * (size_t)c->ncap));
-    k_dd_clear_slots<<<n_new ? (n_new + B - 1) / B : 1, B, 0, c->stream>>>(d->halo_slot, n_new);
-    { const int ns = nb_lo + m_lo + nb_hi + m_hi;
-      k_dd_fill_slots<<<ns ? (ns + B - 1) / B : 1, B, 0, c->stream>>>(d->halo_slot, d->send_idx[0], nb_lo + m_lo, d->send_idx[1], nb_hi + m_hi); }
-    d->slots_valid = true;
     ktimer_end(c, &c->t_migr);
     KERNEL_CHECK();
     d->n_send[0] = nb_lo + m_lo; d->n_send[1] = nb_hi + m_hi;
@@ -722,7 +698,6 @@ static int before_build_p2p(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int
     c->n_own = n_new;
     c->n = n_new + n_halo;
     d->halo_current = true;
-    if (d->p2p) d->halo_inflight = false;       // a refresh pushed before this rebuild is obsolete (its buffer now holds migration records)
     *zoff = d->z0 - 1;
     *nz_local = (d->z1 - d->z0) + 2;
     return 0;
@@ -783,7 +758,7 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
     d->n_send[0] = d->counts_host[8]; d->n_send[1] = d->counts_host[9];
     d->n_recv[0] = d->counts_host[10]; d->n_recv[1] = d->counts_host[11];          // from hi, from lo
     const int n_halo = d->n_recv[0] + d->n_recv[1];
-    if (d->p2p && ((size_t)d->n_send[0] > d->peer_cap[0] / 2 || (size_t)d->n_send[1] > d->peer_cap[1] / 2)) {
+    if (d->p2p && ((size_t)d->n_send[0] > d->peer_cap[0] || (size_t)d->n_send[1] > d->peer_cap[1])) {
         sepgpu_set_error("decomposed rebuild: halo (%d / %d atoms) exceeds a neighbour's receive buffer", d->n_send[0], d->n_send[1]);
         return SEPGPU_EINVAL;
     }
@@ -805,7 +780,6 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
     c->n_own = n_own;
     c->n = n_own + n_halo;
     d->halo_current = true;
-    if (d->p2p) d->halo_inflight = false;       // a refresh pushed before this rebuild is obsolete (its buffer now holds migration records)
     *zoff = d->z0 - 1;
     *nz_local = (d->z1 - d->z0) + 2;
     return 0;
@@ -908,8 +882,7 @@ int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys)
         d->seq++;
         const int nsend = d->n_send[0] + d->n_send[1];
         k_dd_push_xu2<<<nsend ? (nsend + B - 1) / B : 1, B, 0, c->stream>>>(c->x4, c->cr4, d->send_idx[0], d->n_send[0],
-            d->send_idx[1], d->n_send[1], sys->length[0], sys->length[1], sys->length[2],
-            d->peer_dst[0] + (d->seq & 1) * (d->peer_cap[0] / 2), d->peer_dst[1] + (d->seq & 1) * (d->peer_cap[1] / 2),
+            d->send_idx[1], d->n_send[1], sys->length[0], sys->length[1], sys->length[2], d->peer_dst[0], d->peer_dst[1],
             d->peer_flag[0], d->peer_flag[1], d->seq, d->done_ctr);
         KERNEL_CHECK();
         d->halo_inflight = true;
@@ -942,8 +915,8 @@ int sepgpu_dd_halo_end(sepgpu_ctx *c)
     if (d->p2p) {
         const int B = 256;
         const int nrecv = d->n_recv[0] + d->n_recv[1];
-        k_dd_wait_unpack_xu2<<<nrecv ? (nrecv + B - 1) / B : 1, B, 0, c->stream>>>(d->p2p_recv[0] + (d->seq & 1) * (d->bufcap / 2), d->n_recv[0],
-            d->p2p_recv[1] + (d->seq & 1) * (d->bufcap / 2), d->n_recv[1], c->n_own, c->rank, c->xs, d->p2p_flag, d->seq, c->scal);
+        k_dd_wait_unpack_xu2<<<nrecv ? (nrecv + B - 1) / B : 1, B, 0, c->stream>>>(d->p2p_recv[0], d->n_recv[0], d->p2p_recv[1],
+            d->n_recv[1], c->n_own, c->rank, c->xs, d->p2p_flag, d->seq, c->scal);
         KERNEL_CHECK();
     } else {
         CUDA_TRY(cudaStreamWaitEvent(c->stream, d->ev_halo, 0));
@@ -970,24 +943,6 @@ void sepgpu_dd_positions_moved(sepgpu_ctx *c)
     if (c->dd->p2p) c->dd->halo_inflight = false;        // a pushed refresh nobody unpacked is simply obsolete now
 }
 
-// The integrator pushes the boundary atoms' new coordinates itself (PushArgs): one refresh number per integrator call.
-int sepgpu_dd_push_args(sepgpu_ctx *c, PushArgs *out)
-{
-    memset(out, 0, sizeof *out);
-    DDState *d = c->dd;
-    if (!d || !d->p2p || !d->slots_valid || !c->list_valid) return 0;
-    d->seq++;
-    out->slot = d->halo_slot;
-    // Refreshes alternate between the two halves of the neighbours' buffers: a neighbour may still be reading refresh n
-    // in its force kernel while refresh n + 1 is written from here (two ahead is impossible: the integrator's all-gather
-    // of the step in between needs that neighbour's contribution, which follows its force kernel).
-    out->out0 = d->peer_dst[0] + (d->seq & 1) * (d->peer_cap[0] / 2); out->out1 = d->peer_dst[1] + (d->seq & 1) * (d->peer_cap[1] / 2);
-    out->flag0 = d->peer_flag[0]; out->flag1 = d->peer_flag[1];
-    out->seq = d->seq; out->done = d->done_ctr;
-    return 1;
-}
-void sepgpu_dd_pushed(sepgpu_ctx *c) { if (c->dd) c->dd->halo_inflight = true; }     // call after sepgpu_dd_positions_moved
-
 // The tile force kernels consume the neighbours' boundary coordinates straight from the receive buffers: push mine
 // (if this step's refresh has not gone out yet) and tell the kernel where to wait and read.  Returns 1 when `out` is
 // valid, 0 when the caller has to refresh xs the ordinary way (not decomposed on the peer-memory path), < 0 on error.
@@ -1003,7 +958,7 @@ int sepgpu_dd_halo_args(sepgpu_ctx *c, const sepgpu_sys *sys, HaloArgs *out)
         if (rc < 0) return rc;
         out->seq = d->seq;                                // halo_current: the list build has just placed the halo in xs itself
     }
-    out->in0 = d->p2p_recv[0] + (d->seq & 1) * (d->bufcap / 2); out->in1 = d->p2p_recv[1] + (d->seq & 1) * (d->bufcap / 2);
+    out->in0 = d->p2p_recv[0]; out->in1 = d->p2p_recv[1];
     out->n0 = d->n_recv[0]; out->n_own = c->n_own;
     out->flags = d->p2p_flag;
     return 1;

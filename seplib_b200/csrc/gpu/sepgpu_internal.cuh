@@ -317,17 +317,6 @@ struct HaloArgs {
     unsigned long long seq;              // refresh number to wait for; 0 = nothing to wait for (not decomposed)
 };
 int sepgpu_dd_halo_args(sepgpu_ctx *c, const sepgpu_sys *sys, HaloArgs *out);
-// ... and where the integrator stores the boundary atoms' new coordinates: straight into the neighbours' receive
-// buffers, from the kernel that has just computed them (no separate pack/push kernel)
-struct PushArgs {
-    const int2 *slot;                    // per owned atom: position in the lo / hi neighbour's buffer, or -1; NULL = no push
-    d4 *out0, *out1;
-    unsigned long long *flag0, *flag1;
-    unsigned long long seq;
-    unsigned int *done;
-};
-int sepgpu_dd_push_args(sepgpu_ctx *c, PushArgs *out);
-void sepgpu_dd_pushed(sepgpu_ctx *c);
 
 // internal cross-file entry points
 int sepgpu_ensure_stage(sepgpu_ctx *c, size_t bytes);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(INTGR_BLOCK)
 k_integrate(d4 *__restrict__ x4, d4 *__restrict__ v4, d4 *__restrict__ f4, const d4 *__restrict__ xn4,
             i4 *__restrict__ cr4, int *__restrict__ crossings, const int *__restrict__ rank,
             d4 *__restrict__ xs, d4 *__restrict__ pv4, d4 *__restrict__ pa4, const DevScalars *__restrict__ scal,
-            IntgrParams P, double lambda, int stepnow, double *__restrict__ partial, NhFold N, PushArgs PA)
+            IntgrParams P, double lambda, int stepnow, double *__restrict__ partial, NhFold N)
 {
     __shared__ double red[SEPGPU_NPART_I * (INTGR_BLOCK / 32)];
     double acc[SEPGPU_NPART_I];
@@ -107,28 +107,9 @@ k_integrate(d4 *__restrict__ x4, d4 *__restrict__ v4, d4 *__restrict__ f4, const
             if (ty) crossings[3 * i + 1] += ty;
             if (tz) crossings[3 * i + 2] += tz;
         }
-        if (P.write_xs || PA.slot) {
+        if (P.write_xs) {
             d4 u; u.x = x.x + clx * P.Lx; u.y = x.y + cly * P.Ly; u.z = x.z + clz * P.Lz; u.w = x.w;
-            if (P.write_xs) xs[rank[i]] = u;
-            if (PA.slot) {                               // slab run: boundary atoms go straight into the neighbours' buffers
-                const int2 sl = PA.slot[i];
-                if (sl.x >= 0) PA.out0[sl.x] = u;
-                if (sl.y >= 0) PA.out1[sl.y] = u;
-            }
-        }
-    }
-    if (PA.slot) {
-        // every block publishes its remote stores system-wide, the last one to finish raises both neighbours' flags
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int t = atomicAdd(PA.done, 1u);
-            if (t == gridDim.x - 1) {
-                *PA.done = 0;
-                __threadfence_system();
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(PA.flag0), "l"(PA.seq) : "memory");
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(PA.flag1), "l"(PA.seq) : "memory");
-            }
+            xs[rank[i]] = u;
         }
     }
     // block reduction: sums for all but slot 7 (max)
@@ -535,18 +516,16 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     if (fold_nh) { N.temp0 = c->nh_pending.temp0; N.tau = c->nh_pending.tau; N.npart = (double)c->n_global; }
     // the integrator's partial rows must not land on force rows that are still waiting for their reduction
     double *ipartial = fold ? c->partial + (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * SEPGPU_NPART_F + 2048 : c->partial;
-    PushArgs PA;
-    const int pushing = sepgpu_dd_push_args(c, &PA);
     ktimer_begin(c, &c->t_intgr);
     if (dpd)
         k_integrate<true, false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
-            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial, N, PA);
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, c->partial, N);
     else if (fold_nh)
         k_integrate<false, true><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
-            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, ipartial, N, PA);
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, ipartial, N);
     else
         k_integrate<false, false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
-            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, ipartial, N, PA);
+            c->rank, c->xs, c->pv4, c->pa4, c->scal, P, lambda, stepnow, ipartial, N);
     const int resets = (c->ret_reset_pending ? 1 : 0) | (c->maxd_reset_pending ? 2 : 0);
     c->ret_reset_pending = false; c->maxd_reset_pending = false;
     GatherDev gd;
@@ -602,7 +581,6 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     c->moved_since_build = true;
     if (!P.write_xs) c->xs_current = false;
     sepgpu_dd_positions_moved(c);
-    if (pushing) sepgpu_dd_pushed(c);
 
     // the trigger is needed by the host before the next force call: small D2H + stream sync per step
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
