@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 int sepgpu_exclusive_scan(cudaStream_t st, int *cnt, int *start, int *scratch, int n);
+int sepgpu_dd_before_positions_change(sepgpu_ctx *c);
 
 struct NcclApi {
     void *lib;
@@ -89,6 +90,7 @@ struct DDState {
     cudaStream_t stream2;
     cudaEvent_t ev_ready, ev_halo;
     bool halo_inflight;
+    bool push_pending;          // a push kernel on stream2 may still be reading x4 / cr4
     // peer-memory halo push (NVLink P2P through CUDA IPC).  Every rank owns one block
     //   [from-hi buffer: bufcap d4][from-lo buffer: bufcap d4][flags: 2 x u64]
     // that both neighbours map; the pack kernel of a neighbour stores straight into it and then raises the flag.
@@ -491,19 +493,112 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // that side, so they are appended to its halo locally and never travel back.
 struct MigBox { unsigned long long seq; int n_mig, n_bnd; int pad[4]; };      // 32 bytes
 
-__global__ void k_dd_classify2(const d4 *__restrict__ x4, int n_own, double lsz, int nzg, int z0, int z1,
-                               int *f_stay, int *f_lo, int *f_hi, int *f_blo, int *f_bhi, DevScalars *scal)
+// Classification and the five exclusive prefix sums it feeds (stayers, leavers to lo / hi, boundary stayers lo / hi) in
+// three launches: every thread classifies its atoms on the fly, five warp scans run side by side.
+#define S5_BLOCK 512
+#define S5_ITEMS 2
+struct Pos5 { int *p[5]; };
+
+__device__ __forceinline__ void dd_classify(const d4 *__restrict__ x4, int i, double lsz, int nzg, int z0, int z1, int f[5], DevScalars *scal)
+{
+    const int cz = (int)__ddiv_rn(x4[i].z, lsz);                 // reference binning (source/sepprfrc.c:406)
+    f[0] = f[1] = f[2] = 0;
+    if (cz >= z0 && cz < z1) f[0] = 1;
+    else if (cz == (z0 - 1 + nzg) % nzg) f[1] = 1;
+    else if (cz == z1 % nzg) f[2] = 1;
+    else scal->error = SEPGPU_ECELL;                             // moved more than one layer, or left the box
+    f[3] = f[0] && cz == z0; f[4] = f[0] && cz == z1 - 1;
+}
+
+__global__ void __launch_bounds__(S5_BLOCK)
+k_dd_scan5_local(const d4 *__restrict__ x4, int n, double lsz, int nzg, int z0, int z1, Pos5 P, int *__restrict__ block_sum,
+                 int nblocks, DevScalars *scal)
+{
+    __shared__ int wsum[5][S5_BLOCK / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int base = (blockIdx.x * S5_BLOCK + threadIdx.x) * S5_ITEMS;
+    int f[S5_ITEMS][5], tot[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < S5_ITEMS; q++) {
+        if (base + q < n) dd_classify(x4, base + q, lsz, nzg, z0, z1, f[q], scal);
+        else f[q][0] = f[q][1] = f[q][2] = f[q][3] = f[q][4] = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) tot[k] += f[q][k];
+    }
+    int incl[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        int v = tot[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        incl[k] = v;
+        if (lane == 31) wsum[k][wid] = v;
+    }
+    __syncthreads();
+    if (wid < 5) {                                               // warp k scans the warp totals of array k
+        const int w = lane < S5_BLOCK / 32 ? wsum[wid][lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        if (lane < S5_BLOCK / 32) wsum[wid][lane] = wi - w;
+        if (lane == S5_BLOCK / 32 - 1) block_sum[wid * (nblocks + 1) + blockIdx.x] = wi;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        int run = wsum[k][wid] + incl[k] - tot[k];
+#pragma unroll
+        for (int q = 0; q < S5_ITEMS; q++)
+            if (base + q < n) { P.p[k][base + q] = run; run += f[q][k]; }
+    }
+}
+
+// one block: exclusive scan of the block totals of each of the five arrays (<= 1024 blocks per pass), grand totals at [nblocks]
+__global__ void __launch_bounds__(1024) k_dd_scan5_blocks(int *__restrict__ block_sum, int nblocks)
+{
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = 0; k < 5; k++) {
+        int *bs = block_sum + k * (nblocks + 1);
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (int base = 0; base < nblocks; base += 1024) {
+            const int idx = base + threadIdx.x;
+            const int v = idx < nblocks ? bs[idx] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) wsum[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                const int w = wsum[lane];
+                int wi = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+                wsum[lane] = wi - w;
+            }
+            __syncthreads();
+            const int excl = carry + wsum[wid] + incl - v;
+            if (idx < nblocks) bs[idx] = excl;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = excl + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) bs[nblocks] = carry;
+        __syncthreads();
+    }
+}
+
+__global__ void k_dd_scan5_apply(Pos5 P, const int *__restrict__ block_sum, int n, int nblocks)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_own) return;
-    const int cz = (int)__ddiv_rn(x4[i].z, lsz);                 // reference binning (source/sepprfrc.c:406)
-    int stay = 0, lo = 0, hi = 0;
-    if (cz >= z0 && cz < z1) stay = 1;
-    else if (cz == (z0 - 1 + nzg) % nzg) lo = 1;
-    else if (cz == z1 % nzg) hi = 1;
-    else scal->error = SEPGPU_ECELL;                             // moved more than one layer, or left the box
-    f_stay[i] = stay; f_lo[i] = lo; f_hi[i] = hi;
-    f_blo[i] = stay && cz == z0; f_bhi[i] = stay && cz == z1 - 1;
+    if (i < n) {
+        const int b = i / (S5_BLOCK * S5_ITEMS);
+#pragma unroll
+        for (int k = 0; k < 5; k++) P.p[k][i] += block_sum[k * (nblocks + 1) + b];
+    }
+    if (i < 5) P.p[i][n] = block_sum[i * (nblocks + 1) + nblocks];
 }
 
 // counts_dev: [0] stay [1] to_lo [2] to_hi [3] bnd_lo [4] bnd_hi | from the hi neighbour: [5] migrants [6] boundary stayers |
@@ -574,10 +669,11 @@ __global__ void k_dd_split2(const d4 *__restrict__ x4, const d4 *__restrict__ v4
             kp[0] = x; kp[1] = a;
         }
     }
-    // every block publishes its stores system-wide, the last one to finish raises both neighbours' flags
-    __threadfence_system();
+    // The block's stores are ordered before thread 0's system-scope fence by the barrier (cumulativity): one fence per
+    // block publishes them; the last block to finish raises both neighbours' flags
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int t = atomicAdd(done, 1u);
         if (t == gridDim.x - 1) {
             *done = 0;
@@ -662,9 +758,15 @@ static int before_build_p2p(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int
     unsigned long long *lo_flag2 = (unsigned long long *)((unsigned char *)d->peer_base[0] + d->mig_off + 2 * sizeof(MigBox));
     unsigned long long *hi_flag2 = (unsigned long long *)((unsigned char *)d->peer_base[1] + d->mig_off + 2 * sizeof(MigBox)) + 1;
     ktimer_begin(c, &c->t_migr);
-    k_dd_classify2<<<G, B, 0, c->stream>>>(c->x4, n_own, lsz, d->nzg, d->z0, d->z1, d->flag[0], d->flag[1], d->flag[2], d->flag[3], d->flag[4], c->scal);
-    for (int k = 0; k < 5; k++)
-        if ((rc = sepgpu_exclusive_scan(c->stream, d->flag[k], d->pos[k], d->scan_scratch, n_own))) return rc;
+    {
+        Pos5 P5;
+        for (int k = 0; k < 5; k++) P5.p[k] = d->pos[k];
+        const int nb5 = n_own ? (n_own + S5_BLOCK * S5_ITEMS - 1) / (S5_BLOCK * S5_ITEMS) : 1;
+        int *bs = d->flag[0];                                    // the flag arrays are free on this path: scratch for 5 x (nb5 + 1) block totals
+        k_dd_scan5_local<<<nb5, S5_BLOCK, 0, c->stream>>>(c->x4, n_own, lsz, d->nzg, d->z0, d->z1, P5, bs, nb5, c->scal);
+        k_dd_scan5_blocks<<<1, 1024, 0, c->stream>>>(bs, nb5);
+        k_dd_scan5_apply<<<(n_own + 255) / 256 + 1, 256, 0, c->stream>>>(P5, bs, n_own, nb5);
+    }
     k_dd_post_counts<<<1, 32, 0, c->stream>>>(d->pos[0], d->pos[1], d->pos[2], d->pos[3], d->pos[4], n_own, lo_box, hi_box, my_boxes,
                                              d->mseq, d->counts_dev, c->scal);
     if ((rc = read_counts(c, 9))) return rc;
@@ -712,6 +814,7 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
         return SEPGPU_ESTATE;
     }
     if (sys->nsubbox[2] != d->nzg) { sepgpu_set_error("decomposed run: the cell grid along z changed"); return SEPGPU_ESTATE; }
+    { int rw = sepgpu_dd_before_positions_change(c); if (rw) return rw; }
     if (d->p2p) return before_build_p2p(c, sys, zoff, nz_local);
     const double lsz = sys->lsubbox[2];
     const int B = 256;
@@ -831,10 +934,11 @@ __global__ void k_dd_push_xu2(const d4 *__restrict__ x4, const i4 *__restrict__ 
         }
         (second ? out1 : out0)[k] = x;
     }
-    // every block publishes its stores system-wide, the last one to finish raises both flags
-    __threadfence_system();
+    // The block's stores are ordered before thread 0's system-scope fence by the barrier (cumulativity): one fence per
+    // block publishes them; the last block to finish raises both flags
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int t = atomicAdd(done, 1u);
         if (t == gridDim.x - 1) {
             *done = 0;
@@ -878,13 +982,21 @@ int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys)
     if (d->halo_current || d->halo_inflight) return 0;
     const int B = 256;
     if (d->p2p) {
-        // same stream, no hand-shake: remote stores and the flag travel while the caller's next kernels run
+        // The push runs on the second stream, launched BEFORE the force kernel that follows on the main stream: both
+        // are on the device at once, my remote stores and the flag travel while my own force tiles already compute.
+        // (The next integrator waits for it: sepgpu_dd_before_positions_change.)
         d->seq++;
         const int nsend = d->n_send[0] + d->n_send[1];
-        k_dd_push_xu2<<<nsend ? (nsend + B - 1) / B : 1, B, 0, c->stream>>>(c->x4, c->cr4, d->send_idx[0], d->n_send[0],
+        if (cudaEventRecord(d->ev_ready, c->stream) != cudaSuccess || cudaStreamWaitEvent(d->stream2, d->ev_ready, 0) != cudaSuccess) {
+            sepgpu_set_error("halo refresh: stream hand-over failed");
+            return SEPGPU_ECUDA;
+        }
+        k_dd_push_xu2<<<nsend ? (nsend + B - 1) / B : 1, B, 0, d->stream2>>>(c->x4, c->cr4, d->send_idx[0], d->n_send[0],
             d->send_idx[1], d->n_send[1], sys->length[0], sys->length[1], sys->length[2], d->peer_dst[0], d->peer_dst[1],
             d->peer_flag[0], d->peer_flag[1], d->seq, d->done_ctr);
         KERNEL_CHECK();
+        CUDA_TRY(cudaEventRecord(d->ev_halo, d->stream2));
+        d->push_pending = true;
         d->halo_inflight = true;
         return 1;
     }
@@ -934,6 +1046,16 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys)
     rc = sepgpu_dd_halo_end(c);
     ktimer_end(c, &c->t_halo);
     return rc;
+}
+
+// before anything on the main stream overwrites positions (integrators, migration): the push kernel must have read them
+int sepgpu_dd_before_positions_change(sepgpu_ctx *c)
+{
+    DDState *d = c->dd;
+    if (!d || !d->push_pending) return 0;
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, d->ev_halo, 0));
+    d->push_pending = false;
+    return 0;
 }
 
 void sepgpu_dd_positions_moved(sepgpu_ctx *c)

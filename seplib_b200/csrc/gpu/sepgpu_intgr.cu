@@ -478,6 +478,7 @@ int sepgpu_ensure_dpd(sepgpu_ctx *c);
 // domain-decomposition hooks (sepgpu_dd.cu)
 double *sepgpu_dd_comm(sepgpu_ctx *c);
 void sepgpu_dd_positions_moved(sepgpu_ctx *c);
+int sepgpu_dd_before_positions_change(sepgpu_ctx *c);
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax);
 void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks);
 bool sepgpu_dd_gather_next(sepgpu_ctx *c, GatherDev *g);
@@ -516,6 +517,7 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     if (fold_nh) { N.temp0 = c->nh_pending.temp0; N.tau = c->nh_pending.tau; N.npart = (double)c->n_global; }
     // the integrator's partial rows must not land on force rows that are still waiting for their reduction
     double *ipartial = fold ? c->partial + (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * SEPGPU_NPART_F + 2048 : c->partial;
+    if (c->dd) { int rw = sepgpu_dd_before_positions_change(c); if (rw) return rw; }
     ktimer_begin(c, &c->t_intgr);
     if (dpd)
         k_integrate<true, false><<<grid, INTGR_BLOCK, 0, c->stream>>>(c->x4, c->v4, c->f4, c->xn4, c->cr4, c->crossings,
