@@ -4,7 +4,7 @@
 // (reference source/sepprfrc.c:394-415, 419-513, 517-603, 606-700).  The reference walks a linked
 // cell list serially and stores each pair once (half list); here
 //   1. atoms are binned with the reference's exact FP64 expression (int)(x/lsubbox) and
-//      counting-sorted by cell; inside a cell the order is ascending atom index (deterministic),
+//      counting-sorted by cell; inside a cell the order is ascending x, ties by atom index (deterministic),
 //      and cells are laid out brick-major (bricks of BX x 4 x 4 cells, x fastest inside a brick) so
 //      that atoms close in space are close in memory in all three directions,
 //   2. a tiled kernel sweeps the 27 surrounding cells and writes a transposed FULL list.
@@ -143,31 +143,66 @@ __global__ void k_cell_scatter(const int *__restrict__ cell_of, int n, const int
     tmp_slot[cell_start[c] + atomicAdd(&cell_cnt[c], 1)] = i;
 }
 
-// rank inside the cell by atom index (removes the atomic arrival order), then write the sorted copies
-__global__ void k_cell_finalize(const int *__restrict__ tmp_slot, const int *__restrict__ cell_of,
-                                const int *__restrict__ cell_start, const d4 *__restrict__ x4,
-                                int n, int *__restrict__ order, int *__restrict__ rank,
-                                d4 *__restrict__ xs, float4 *__restrict__ xf, i4 *__restrict__ cr4,
-                                unsigned char *__restrict__ cls, CellGrid G)
+// Order inside a cell: ascending x (FP32 image of the coordinate, ties by atom index) -- deterministic, independent of the
+// atomic arrival order, and it makes every x-row of cells a list sorted along x, which lets the tiled builder restrict
+// its sweep of a row to the window |x_j - x_i| <= reach (sepgpu_neighb_tile.cuh).  One warp per cell: keys staged in
+// shared memory, rank by counting; then the sorted copies are written.
+#define FIN_WARPS 8
+#define FIN_CAP 256            // atoms of one cell ranked from shared memory; fuller cells take the global loop
+__global__ void __launch_bounds__(FIN_WARPS * 32)
+k_cell_finalize(const int *__restrict__ tmp_slot, const int *__restrict__ cell_start, const d4 *__restrict__ x4,
+                int nkey, int *__restrict__ order, int *__restrict__ rank,
+                d4 *__restrict__ xs, float4 *__restrict__ xf, i4 *__restrict__ cr4,
+                unsigned char *__restrict__ cls, CellGrid G)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    int i = tmp_slot[t];
-    int c = cell_of[i];
-    int b = cell_start[c], e = cell_start[c + 1];
-    int r = 0;
-    for (int q = b; q < e; q++) r += tmp_slot[q] < i;
-    int s = b + r;
-    order[s] = i;
-    rank[i] = s;
-    d4 p = x4[i];
-    xs[s] = p;
-    xf[s] = make_float4((float)p.x, (float)p.y, (float)p.z, __int_as_float(tag_mol(p.w)));
-    cr4[i].w = 0;          // crossings since list build
-    if (cls) {             // slab decomposition: does this atom's neighbourhood reach into a halo layer?
+    __shared__ unsigned s_kx[FIN_WARPS][FIN_CAP];
+    __shared__ int s_ki[FIN_WARPS][FIN_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int key = blockIdx.x * FIN_WARPS + w;
+    if (key >= nkey) return;
+    const int b = cell_start[key], m = cell_start[key + 1] - b;
+    if (m == 0) return;
+    const bool staged = m <= FIN_CAP;
+    if (staged) {
+        for (int k = lane; k < m; k += 32) {
+            const int i = tmp_slot[b + k];
+            s_ki[w][k] = i;
+            s_kx[w][k] = __float_as_uint((float)x4[i].x);        // x >= 0: the bit pattern orders like the value
+        }
+        __syncwarp();
+    }
+    unsigned char cl = 0;
+    if (cls) {             // slab decomposition: does this cell's neighbourhood reach into a halo layer?
         int cx, cy, cz;
-        key_cell(c, G, cx, cy, cz);
-        cls[s] = (cz == 0 || cz == G.nz - 1) ? 2 : ((cz == 1 || cz == G.nz - 2) ? 1 : 0);
+        key_cell(key, G, cx, cy, cz);
+        cl = (cz == 0 || cz == G.nz - 1) ? 2 : ((cz == 1 || cz == G.nz - 2) ? 1 : 0);
+    }
+    for (int k = lane; k < m; k += 32) {
+        int i, r = 0;
+        if (staged) {
+            i = s_ki[w][k];
+            const unsigned kx = s_kx[w][k];
+            for (int q = 0; q < m; q++) {
+                const unsigned kq = s_kx[w][q];
+                r += (kq < kx) || (kq == kx && s_ki[w][q] < i);
+            }
+        } else {
+            i = tmp_slot[b + k];
+            const unsigned kx = __float_as_uint((float)x4[i].x);
+            for (int q = 0; q < m; q++) {
+                const int iq = tmp_slot[b + q];
+                const unsigned kq = __float_as_uint((float)x4[iq].x);
+                r += (kq < kx) || (kq == kx && iq < i);
+            }
+        }
+        const int s = b + r;
+        order[s] = i;
+        rank[i] = s;
+        const d4 p = x4[i];
+        xs[s] = p;
+        xf[s] = make_float4((float)p.x, (float)p.y, (float)p.z, __int_as_float(tag_mol(p.w)));
+        cr4[i].w = 0;          // crossings since list build
+        if (cls) cls[s] = cl;
     }
 }
 
@@ -186,6 +221,9 @@ struct BuildParams {
     double Lx, Ly, Lz;
     double cut2;
     float fLx, fLy, fLz, fcut_lo, fcut_hi;
+    float flsy, flsz;       // cell widths along y and z (window of the tiled builder)
+    int zcell0;             // global cell layer of local layer 0 (slab runs: zoff, else 0)
+    int xwindow;            // tiled builder: restrict each row to the x window within reach (cells at least as wide as the cutoff)
     CellGrid G;
     int n, npad, cap;
     unsigned opt;
@@ -272,9 +310,8 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                     count += __popc(mask);
                     if (in_half) half_count += __popc(mask);
                     else if (same_cell) {
-                        // same cell: the reference keeps j2 > j1 (original indices); sorted order inside a
-                        // cell is ascending in the original index, so j > s is the same condition
-                        half_count += __popc(__ballot_sync(0xffffffffu, ok && j > s));
+                        // same cell: the reference keeps j2 > j1 (original indices)
+                        half_count += __popc(__ballot_sync(0xffffffffu, ok && order[j < je ? j : s] > i_orig));
                     }
                 }
             }
@@ -421,7 +458,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (sepgpu_exclusive_scan(c->stream, c->cell_cnt, c->cell_start, block_sum, nkey)) return SEPGPU_ECUDA;
         k_cell_scatter<<<Gn, B, 0, c->stream>>>(c->cell_of, c->n, c->cell_start, c->cell_cnt, c->tmp_slot);
         if (c->dd && !c->cls) CUDA_TRY(cudaMalloc((void **)&c->cls, (size_t)c->ncap));
-        k_cell_finalize<<<Gn, B, 0, c->stream>>>(c->tmp_slot, c->cell_of, c->cell_start, c->x4, c->n,
+        k_cell_finalize<<<(nkey + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, c->stream>>>(c->tmp_slot, c->cell_start, c->x4, nkey,
                                                  c->order, c->rank, c->xs, c->xf, c->cr4, c->dd ? c->cls : NULL, G);
         BuildParams P;
         P.Lx = sys->length[0]; P.Ly = sys->length[1]; P.Lz = sys->length[2];
@@ -429,6 +466,8 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         P.cut2 = cut * cut;                              // sep_Sq(sys->cf + sys->skin), :432
         P.fLx = (float)P.Lx; P.fLy = (float)P.Ly; P.fLz = (float)P.Lz;
         P.G = G;
+        P.flsy = (float)sys->lsubbox[1]; P.flsz = (float)sys->lsubbox[2];
+        P.zcell0 = G.dd ? G.zoff : 0;
         P.n = c->n; P.npad = c->npad; P.cap = c->cap; P.opt = opt;
         // FP32 prefilter: |r2_f32 - r2_exact| <= 2*sqrt(3)*cut * 4*Lmax*2^-24 (+ accumulation rounding);
         // the band below is 5x that bound.  It also needs cell image == minimum image, which holds when
@@ -438,6 +477,9 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         const double band = 4.2e-6 * cut * Lmax + 2e-6 * P.cut2;
         P.prefilter = c->prefilter && !force_exact && nx >= 4 && ny >= 4 && nz >= 4 && cut < 1.95 * wmin && band < 0.05 * P.cut2;
         if (c->dd && !P.prefilter) { sepgpu_set_error("neighb_build: decomposed runs need >= 4 cells per direction"); return SEPGPU_EINVAL; }
+        // the window argument needs every candidate within the cutoff to sit in the 27 cells around the atom anyway: cells
+        // at least as wide as the cutoff (not the case after sep_set_skin enlarged the skin past the cell width)
+        P.xwindow = c->build_window && cut <= wmin ? 1 : 0;
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
         const int ntile = nkey / (G.bx * R);

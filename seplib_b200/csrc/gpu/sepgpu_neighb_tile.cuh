@@ -163,11 +163,30 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                 const bool half_row = (oz == 1) || (oz == 0 && oy == 1);
                 const bool centre_row = (oz == 0 && oy == 0);
                 const int c0 = ((oz + 1) * nry + (hy + oy + 1)) * ncc + hx;   // candidate cells c0 (ox=-1), c0+1 (own column), c0+2 (ox=+1)
-                const int wlo = T.off[c0], whi = T.off[c0 + 3];
+                int wlo = T.off[c0], whi = T.off[c0 + 3];
                 const int cut_a = T.off[c0 + 1];
                 const int self_q = centre_row ? cut_a + (s - T.beg[c0 + 1]) : -1;
                 const int cut_b = T.off[c0 + 2];
                 const bool im0 = img_tile && T.code[c0] != 13, im1 = img_tile && T.code[c0 + 1] != 13, im2 = img_tile && T.code[c0 + 2] != 13;
+                if (P.xwindow) {
+                    // Cells are sorted along x inside (k_cell_finalize), so the three cells of a row are ONE list ascending
+                    // in the staged x.  Only candidates with |x_j - x_i| <= reach can be within the list cutoff, where
+                    // reach^2 = cut^2 - (distance to the row's y slab)^2 - (distance to its z slab)^2; both ends of that
+                    // window are found by bisection.  All in FP32 with a margin far above its rounding (1e-3 in reach^2
+                    // plus 1e-3 in x against a band of ~1e-4): a dropped candidate could not have passed the mask test.
+                    const float dy = oy == 0 ? 0.f : (oy > 0 ? fmaxf((T.cy0 + hy + 1) * P.flsy - fi.y, 0.f) : fmaxf(fi.y - (T.cy0 + hy) * P.flsy, 0.f));
+                    const float dz = oz == 0 ? 0.f : (oz > 0 ? fmaxf((P.zcell0 + T.cz + 1) * P.flsz - fi.z, 0.f) : fmaxf(fi.z - (P.zcell0 + T.cz) * P.flsz, 0.f));
+                    const float reach2 = P.fcut_hi * 1.001f - dy * dy - dz * dz;
+                    if (reach2 <= 0.f) continue;
+                    const float reach = sqrtf(reach2) + 1e-3f;
+                    const float xlo = fi.x - reach, xhi = fi.x + reach;
+                    int lo = wlo, hi = whi;                       // first candidate with x >= xlo
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cand[mid].x < xlo) lo = mid + 1; else hi = mid; }
+                    wlo = lo;
+                    hi = whi;                                     // first candidate with x > xhi
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cand[mid].x <= xhi) lo = mid + 1; else hi = mid; }
+                    whi = lo;
+                }
 #pragma unroll 1
                 for (int q0 = wlo; q0 < whi; q0 += 32) {
 #ifdef SEPGPU_EMU
@@ -211,8 +230,17 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                     // stored after my own position -- my own cell with j2 > j1 and the ox = +1 cell
                     if (half_row) half_count += __popc(mask);
                     else if (centre_row) {
-                        const int d = self_q + 1 - q0;                   // first bit that counts
-                        half_count += __popc(d <= 0 ? mask : (d >= 32 ? 0u : mask & ~((1u << d) - 1u)));
+                        // the ox = +1 cell counts whole, my own cell by atom index (slots of a cell are ordered along x)
+                        half_count += __popc(mask & bit_range(cut_b - q0, 32));
+                        unsigned own = mask & bit_range(cut_a - q0, cut_b - q0);
+                        if (own) {
+                            const int my_i = order[s];
+                            while (own) {
+                                const int b = __ffs(own) - 1;
+                                own &= own - 1;
+                                half_count += order[__float_as_uint(cand[q0 + b].w) & SEPGPU_INDEX_MASK] > my_i;
+                            }
+                        }
                     }
                     const int nacc = __popc(mask);
                     if (count + nacc <= P.cap) {
