@@ -479,7 +479,10 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         if (c->dd && !P.prefilter) { sepgpu_set_error("neighb_build: decomposed runs need >= 4 cells per direction"); return SEPGPU_EINVAL; }
         // the window argument needs every candidate within the cutoff to sit in the 27 cells around the atom anyway: cells
         // at least as wide as the cutoff (not the case after sep_set_skin enlarged the skin past the cell width)
-        P.xwindow = c->build_window && cut <= wmin ? 1 : 0;
+        // Measured on B200 (profiles/r02_build_window_ab.txt): the per-lane windows halve the candidate tests but cost the
+        // warp its shared (broadcast) candidate reads; that pays from ~24 atoms per cell on (water -13 %, butane -6 %) and
+        // loses 3 % at 17 atoms per cell (the 1 M-atom Lennard-Jones fluid).  build_window = 2 forces it on.
+        P.xwindow = cut <= wmin && (c->build_window == 2 || (c->build_window == 1 && mean_per_cell >= 24.0)) ? 1 : 0;
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
         const int ntile = nkey / (G.bx * R);
