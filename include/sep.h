@@ -254,6 +254,9 @@ void sep_warning(char *str, ...);
 double sep_lj(double r2, char opt);
 double sep_lj_shift(double r2, char opt);
 double sep_wca(double r2, char opt);
+/* Extension: sep_force_pairs samples a pair function of the caller's own once per (function, cutoff) -- see
+ * INTEGRATION.md "Pair functions of your own".  Call this after changing parameters that function reads. */
+void sep_pairs_retabulate(void);
 void sep_reset_force(seppart *ptr, sepsys *sys);
 void sep_reset_force_mol(sepsys *sys);
 int sep_nsubbox(double cf, double delta, double lbox);

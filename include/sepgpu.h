@@ -29,6 +29,7 @@ typedef struct sepgpu_ctx sepgpu_ctx;
 #define SEPGPU_ENEIGHB    -5   /* "Too many neighbours" (source/sepprfrc.c:499): a half list reached SEP_NEIGHB */
 #define SEPGPU_ESTATE     -6   /* call order problem (e.g. list force without a list) */
 #define SEPGPU_ENCCL      -7   /* NCCL failure (domain decomposition) */
+#define SEPGPU_ETABLE     -8   /* a pair came closer than a tabulated pair function reaches */
 
 /* per-atom fields for sepgpu_put / sepgpu_get.  Host element = what the reference keeps in seppart
  * (include/sepstrct.h:23-61): 3 doubles for vectors, 1 double for scalars, 3 ints for counters. */
@@ -132,6 +133,11 @@ int sepgpu_neighb_build(sepgpu_ctx *ctx, const sepgpu_sys *sys, unsigned opt);
  * epot_assign=1 reproduces "retval->epot = epot" (:222), 0 accumulates (:64, :922). */
 int sepgpu_force_lj(sepgpu_ctx *ctx, const sepgpu_sys *sys, const char types[2],
                     const sepgpu_ljparam *p, unsigned opt, int epot_assign);
+/* sep_force_pairs with a pair function of the caller's own (include/sepprfrc.h:49-51: double (*fun)(double r2, char opt)):
+ * the host layer samples fun(r2,'f') and fun(r2,'u') on n uniform points of r^2 in [r2_lo, cf^2]; tab_fu holds the n pairs
+ * {f, u}.  The device interpolates with a cubic through the four surrounding samples.  Tile lists and SEP_BRUTE. */
+int sepgpu_force_table(sepgpu_ctx *ctx, const sepgpu_sys *sys, const char types[2], double cf, const double *tab_fu, int n,
+                       double r2_lo, unsigned opt, int epot_assign);
 /* sep_coulomb_sf (source/sepcoulomb.c:5-18) */
 int sepgpu_coulomb_sf(sepgpu_ctx *ctx, const sepgpu_sys *sys, double cf, unsigned opt);
 /* sep_force_dpd (source/sepprfrc.c:278-301); counter-based pair noise keyed on (seed, step).

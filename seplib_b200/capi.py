@@ -121,7 +121,7 @@ def atoms_view(ptr, n):
 SEPGPU_SYMBOLS = [
     "sepgpu_create", "sepgpu_destroy", "sepgpu_last_error", "sepgpu_device_count", "sepgpu_put",
     "sepgpu_get", "sepgpu_put_fields", "sepgpu_get_fields", "sepgpu_set_topology", "sepgpu_get_bonded_values", "sepgpu_reset_ret",
-    "sepgpu_reset_force", "sepgpu_neighb_build", "sepgpu_force_lj", "sepgpu_coulomb_sf",
+    "sepgpu_reset_force", "sepgpu_neighb_build", "sepgpu_force_lj", "sepgpu_force_table", "sepgpu_coulomb_sf",
     "sepgpu_force_dpd", "sepgpu_stretch_harmonic", "sepgpu_angle_harmonic", "sepgpu_angle_cossq",
     "sepgpu_torsion_ryckaert", "sepgpu_nosehoover", "sepgpu_nosehoover_type", "sepgpu_set_alpha",
     "sepgpu_leapfrog", "sepgpu_verlet_dpd", "sepgpu_reset_momentum", "sepgpu_scale_positions",
@@ -144,7 +144,7 @@ SEP_SYMBOLS = [
     "sep_torsion_Ryckaert", "sep_mol_cm", "sep_mol_velcm", "sep_eval_mol_pressure_tensor",
     "sep_average_bondlengths", "sep_reset_retval", "sep_get_pressure", "sep_get_temperature",
     "sep_pressure_tensor", "sep_mol_pressure_tensor", "sep_error", "sep_warning", "sep_lj",
-    "sep_lj_shift", "sep_wca", "sep_reset_force", "sep_reset_force_mol", "sep_nsubbox",
+    "sep_lj_shift", "sep_wca", "sep_pairs_retabulate", "sep_reset_force", "sep_reset_force_mol", "sep_nsubbox",
     "sep_box_length", "sep_count_type", "sep_set_x0", "sep_set_xn", "sep_save_xyz", "sep_eval_mom",
     "sep_eval_mom_type", "sep_compress_box", "sep_set_charge", "sep_set_mass", "sep_set_type",
     "sep_set_omp", "sep_set_skin", "sep_set_ndof", "sep_reset_momentum", "sep_dist_ij",
@@ -239,6 +239,8 @@ def load():
     lib.sepgpu_reset_force.argtypes = [ctx]
     lib.sepgpu_neighb_build.argtypes = [ctx, C.POINTER(GpuSys), C.c_uint]
     lib.sepgpu_force_lj.argtypes = [ctx, C.POINTER(GpuSys), C.c_char_p, C.POINTER(GpuLJ), C.c_uint, C.c_int]
+    lib.sepgpu_force_table.argtypes = [ctx, C.POINTER(GpuSys), C.c_char_p, C.c_double, C.POINTER(C.c_double), C.c_int, C.c_double,
+                                       C.c_uint, C.c_int]
     lib.sepgpu_coulomb_sf.argtypes = [ctx, C.POINTER(GpuSys), C.c_double, C.c_uint]
     lib.sepgpu_force_dpd.argtypes = [ctx, C.POINTER(GpuSys), C.c_char_p, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_uint, C.c_ulonglong, C.c_ulonglong]

@@ -60,22 +60,32 @@ __device__ __forceinline__ void lj_pair(const d4 &pi, const d4 &pj, unsigned e, 
         const int tj = tag_type(pj.w);
         in = in && ((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0));   // source/sepprfrc.c:171-172
     }
-    const double rri = P.sig2 * fast_rcp3(r2);
-    double rri3 = rri * rri * rri;
-    double ft = rri3 * (rri3 - P.awh) * rri;                       // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
-    const double uu = rri3 - P.aw;
-    ft = in ? ft : 0.0;
-    rri3 = in ? rri3 : 0.0;
+    double ft;
+    if (FIJ && P.tab) {                                            // (the FIJ instantiation is the general-purpose one)
+        // user pair function sampled by the host layer (sepgpu_force_table): force factor and energy from the table
+        bool below;
+        const double2 fu = table_eval(P, in ? r2 : P.cf2, below);
+        if (in && below) A.nin |= 0x40000000;
+        ft = in ? fu.x : 0.0;
+        A.u += in ? fu.y : 0.0;
+    } else {
+        const double rri = P.sig2 * fast_rcp3(r2);
+        double rri3 = rri * rri * rri;
+        ft = rri3 * (rri3 - P.awh) * rri;                          // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
+        const double uu = rri3 - P.aw;
+        ft = in ? ft : 0.0;
+        rri3 = in ? rri3 : 0.0;
+        A.u = fma(rri3, uu, A.u);                                  // u/(4 eps) before the shift
+        A.nin += in ? 1 : 0;
+    }
     A.fx = fma(ft, dx, A.fx); A.fy = fma(ft, dy, A.fy); A.fz = fma(ft, dz, A.fz);
-    A.u = fma(rri3, uu, A.u);                                      // u/(4 eps) before the shift
-    A.nin += in ? 1 : 0;
     if (code != 13) {                                              // boundary-crossing pair: - g (x) S
         double sx = 0.0, sy = 0.0, sz = 0.0;
         apply_image(code, B, sx, sy, sz);                          // s = -S
         const double g = P.eps48 * ft;
         virial_add(A.v, g * dx, g * dy, g * dz, sx, sy, sz);
     }
-    if (FIJ && in) {
+    if (FIJ && in && fij) {
         const int mi = tag_mol(pi.w), mj = tag_mol(pj.w);
         if (mi != -1 && mj != -1 && mi != mj) {
             const double g = P.eps48 * ft;
@@ -141,7 +151,7 @@ __global__ void __launch_bounds__(FORCE_BLOCK, LJ_MIN_CTAS)
 k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, d4 *__restrict__ f4, int n, int npad, int atoms_per_cta,
           LJDev P, BoxDev B, double *__restrict__ partial, double *fij, int nmol,
-          const unsigned char *__restrict__ cls, int want)
+          const unsigned char *__restrict__ cls, int want, DevScalars *scal)
 {
     __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
     const int sub = threadIdx.x % TPA;
@@ -239,7 +249,12 @@ k_lj_list(const d4 *__restrict__ xs, const unsigned *__restrict__ nbr, const int
         }
     }
     double acc[SEPGPU_NPART_F];
-    acc[0] = P.eps4 * A.u - P.shift * (double)A.nin;
+    if (FIJ && P.tab) {
+        acc[0] = A.u;
+        if (A.nin & 0x40000000) scal->error = SEPGPU_ETABLE;
+    } else {
+        acc[0] = P.eps4 * A.u - P.shift * (double)A.nin;
+    }
     acc[1] = 0.0;
 #pragma unroll
     for (int q = 0; q < 6; q++) acc[2 + q] = A.v[q];
@@ -265,7 +280,7 @@ __device__ __forceinline__ int share_tab_f(const int *__restrict__ tab, int widt
 template <bool STORE>
 __global__ void __launch_bounds__(FORCE_BLOCK)
 k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDev B, unsigned opt,
-           const int *__restrict__ excl_bond, double *__restrict__ partial, double *fij, int nmol)
+           const int *__restrict__ excl_bond, double *__restrict__ partial, double *fij, int nmol, DevScalars *scal)
 {
     __shared__ d4 tile[FORCE_BLOCK];
     __shared__ double red[SEPGPU_NPART_F * (FORCE_BLOCK / 32)];
@@ -280,6 +295,7 @@ k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDe
 #pragma unroll
     for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
     int nin = 0;
+    bool below_seen = false;
     for (int j0 = 0; j0 < n; j0 += FORCE_BLOCK) {
         __syncthreads();
         if (j0 + threadIdx.x < n) tile[threadIdx.x] = x4[j0 + threadIdx.x];
@@ -299,13 +315,22 @@ k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDe
             const double dz = wrap_exact(pi.z - pj.z, B.Lz, hz);
             const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
             if (r2 < P.cf2) {
-                const double rri = P.sig2 / r2;
-                const double rri3 = rri * rri * rri;
-                const double ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;
+                double ft;
+                if (P.tab) {                                     // user pair function (tabulated by the host layer)
+                    bool below;
+                    const double2 fu = table_eval(P, r2, below);
+                    if (below) below_seen = true;
+                    ft = fu.x;
+                    acc[1] += fu.y;                              // energy, moved to slot 0 below
+                } else {
+                    const double rri = P.sig2 / r2;
+                    const double rri3 = rri * rri * rri;
+                    ft = P.eps48 * rri3 * (rri3 - P.awh) * rri;
+                    acc[0] = fma(rri3, rri3 - P.aw, acc[0]);
+                    nin++;
+                }
                 const double gx = ft * dx, gy = ft * dy, gz = ft * dz;
                 fx += gx; fy += gy; fz += gz;
-                acc[0] = fma(rri3, rri3 - P.aw, acc[0]);
-                nin++;
                 acc[2] = fma(gx, dx, acc[2]); acc[3] = fma(gx, dy, acc[3]); acc[4] = fma(gx, dz, acc[4]);
                 acc[5] = fma(gy, dy, acc[5]); acc[6] = fma(gy, dz, acc[6]); acc[7] = fma(gz, dz, acc[7]);
                 if (fij) {                                   // source/sepprfrc.c:70-80: both molecules known
@@ -322,7 +347,8 @@ k_lj_brute(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, LJDev P, BoxDe
         if (STORE) { d4 o; o.x = fx; o.y = fy; o.z = fz; o.w = 0; f4[i] = o; }
         else { d4 o = f4[i]; o.x += fx; o.y += fy; o.z += fz; f4[i] = o; }
     }
-    acc[0] = P.eps4 * acc[0] - P.shift * (double)nin;
+    if (P.tab) { acc[0] = acc[1]; acc[1] = 0.0; if (below_seen) scal->error = SEPGPU_ETABLE; }
+    else acc[0] = P.eps4 * acc[0] - P.shift * (double)nin;
     block_sum<SEPGPU_NPART_F, FORCE_BLOCK>(acc, red);
     if (threadIdx.x == 0)
         for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
@@ -495,6 +521,7 @@ static LJDev make_lj(const sepgpu_ljparam *p, const char types[2])
     d.shift = p->shift;
     d.t0 = (unsigned char)types[0];
     d.t1 = (unsigned char)types[1];
+    d.tab = NULL; d.t_lo = 0.0; d.t_inv = 0.0; d.t_n = 0;
     return d;
 }
 
@@ -581,7 +608,7 @@ template <int TPA, bool FIJ>
 static void launch_lj_list_f(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
                              double *part, const unsigned char *cls, int want, const unsigned *nbr, const int *cnt)
 {
-#define LJ_ARGS c->xs, nbr, cnt, c->order, c->f4, c->n, c->npad, apc, P, B, part, c->fij, c->nmol, cls, want
+#define LJ_ARGS c->xs, nbr, cnt, c->order, c->f4, c->n, c->npad, apc, P, B, part, c->fij, c->nmol, cls, want, c->scal
     if (typed) {
         if (store) k_lj_list<TPA, true, true, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
         else       k_lj_list<TPA, true, false, FIJ><<<grid, FORCE_BLOCK, 0, c->stream>>>(LJ_ARGS);
@@ -596,7 +623,7 @@ template <int TPA>
 static void launch_lj_list(sepgpu_ctx *c, int grid, int apc, bool typed, bool store, const LJDev &P, const BoxDev &B,
                            double *part, const unsigned char *cls, int want, const unsigned *nbr, const int *cnt)
 {
-    if (c->fij) launch_lj_list_f<TPA, true>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt);
+    if (c->fij || P.tab) launch_lj_list_f<TPA, true>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt);
     else launch_lj_list_f<TPA, false>(c, grid, apc, typed, store, P, B, part, cls, want, nbr, cnt);
 }
 
@@ -612,12 +639,56 @@ static void launch_lj_list_tpa(sepgpu_ctx *c, int grid, int apc, bool typed, boo
     }
 }
 
+static int force_pairs_dev(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], const LJDev &P, unsigned opt, int epot_assign);
+
 extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2],
                                const sepgpu_ljparam *p, unsigned opt, int epot_assign)
 {
     if (!c || !sys || !types || !p) return SEPGPU_EINVAL;
     SEPGPU_ENTER(c);
-    const LJDev P = make_lj(p, types);
+    return force_pairs_dev(c, sys, types, make_lj(p, types), opt, epot_assign);
+}
+
+// sep_force_pairs with a pair function of the caller's own (reference include/sepprfrc.h:49-51, called at
+// source/sepprfrc.c:140-146): the host layer has sampled it; the table is uploaded when it changes.
+extern "C" int sepgpu_force_table(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], double cf, const double *tab_fu, int n,
+                                  double r2_lo, unsigned opt, int epot_assign)
+{
+    if (!c || !sys || !types || !tab_fu || n < 8 || !(r2_lo >= 0.0) || !(cf * cf > r2_lo)) return SEPGPU_EINVAL;
+    SEPGPU_ENTER(c);
+    // up to SEPGPU_NTAB tables stay resident (one per pair function and cutoff in use); a table is recognised by its
+    // geometry and a hash over 256 of its entries, so a re-sampled function at the same address is uploaded again
+    unsigned long long h = 1469598103934665603ull;
+    for (int q = 0; q < 256; q++) {
+        unsigned long long bits[2];
+        memcpy(bits, tab_fu + 2 * (size_t)((long long)q * (n - 1) / 255), sizeof bits);
+        h = (h ^ bits[0]) * 1099511628211ull; h = (h ^ bits[1]) * 1099511628211ull;
+    }
+    int slot = -1;
+    for (int q = 0; q < SEPGPU_NTAB; q++)
+        if (c->tab[q].dev && c->tab[q].key == tab_fu && c->tab[q].n == n && c->tab[q].lo == r2_lo && c->tab[q].cf == cf && c->tab[q].hash == h) slot = q;
+    if (slot < 0) {
+        slot = (int)(c->tab_next++ % SEPGPU_NTAB);
+        if (c->tab[slot].dev && c->tab[slot].n != n) {
+            CUDA_TRY(cudaStreamSynchronize(c->stream));            // a kernel in flight may still read it
+            cudaFree(c->tab[slot].dev); c->tab[slot].dev = NULL;
+        }
+        if (!c->tab[slot].dev) CUDA_TRY(cudaMalloc((void **)&c->tab[slot].dev, sizeof(double2) * (size_t)n));
+        CUDA_TRY(cudaMemcpyAsync(c->tab[slot].dev, tab_fu, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->tab[slot].key = tab_fu; c->tab[slot].n = n; c->tab[slot].lo = r2_lo; c->tab[slot].cf = cf; c->tab[slot].hash = h;
+    }
+    sepgpu_ljparam p;
+    p.cf = cf; p.eps = 1.0 / 48.0; p.sigma = 1.0; p.aw = 1.0; p.shift = 0.0;       // eps48 = 1: the table holds the force factor itself
+    LJDev P = make_lj(&p, types);
+    P.eps48 = 1.0; P.eps4 = 1.0;
+    P.tab = reinterpret_cast<const double2 *>(c->tab[slot].dev);
+    P.t_lo = r2_lo; P.t_inv = (double)(n - 1) / (cf * cf - r2_lo); P.t_n = n;
+    return force_pairs_dev(c, sys, types, P, opt, epot_assign);
+}
+
+static int force_pairs_dev(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], const LJDev &P, unsigned opt, int epot_assign)
+{
     BoxDev B; B.Lx = sys->length[0]; B.Ly = sys->length[1]; B.Lz = sys->length[2];
     const bool store = c->f_zero;
     int rc;
@@ -629,8 +700,8 @@ extern "C" int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char 
         }
         const int grid = (c->n + FORCE_BLOCK - 1) / FORCE_BLOCK;
         ktimer_begin(c, &c->t_force);
-        if (store) k_lj_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial, c->fij, c->nmol);
-        else       k_lj_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial, c->fij, c->nmol);
+        if (store) k_lj_brute<true><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial, c->fij, c->nmol, c->scal);
+        else       k_lj_brute<false><<<grid, FORCE_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, P, B, opt, c->excl_bond, c->partial, c->fij, c->nmol, c->scal);
         ktimer_end(c, &c->t_force);
         KERNEL_CHECK();
         c->f_zero = false;

@@ -27,7 +27,7 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 // padding) partner continues with r^2 = 1e300, whose inverse cube underflows to exactly zero -- no further selects.
 // No per-pair virial: with a full list  sum g (x) d = 2 sum_i F_i (x) x_i - sum over boundary-crossing pairs g (x) S
 // (see lj_pair in sepgpu_force.cu); IMAGE tiles (those that touch a face of the box) add the second term.
-template <bool TYPED, bool IMAGE>
+template <bool TYPED, bool IMAGE, bool TABLE>
 __device__ __forceinline__ void lj_tile_pair(double xi, double yi, double zi, int ti, const double2 *__restrict__ XY,
                                              const double *__restrict__ Z, const unsigned char *__restrict__ CODE,
                                              const unsigned char *__restrict__ TYPE, const double *__restrict__ SHIFT,
@@ -43,12 +43,21 @@ __device__ __forceinline__ void lj_tile_pair(double xi, double yi, double zi, in
         const int tj = TYPE[j];
         in = in && ((ti == P.t0 && tj == P.t1) || (ti == P.t1 && tj == P.t0));       // source/sepprfrc.c:126-127
     }
-    r2 = in ? r2 : 1e300;
-    nin += in ? 1 : 0;
-    const double q = fast_rcp3(r2);
-    const double b = q * q * q;
-    const double f = b * (b - P.awh) * q;                            // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
-    u = fma(b, b - P.aw, u);
+    double f;
+    if (TABLE) {                                                     // user pair function, sampled by the host layer
+        bool below;
+        const double2 fu = table_eval(P, in ? r2 : P.cf2, below);
+        if (in && below) nin |= 0x40000000;                          // closer than the table reaches: reported by the host
+        f = in ? fu.x : 0.0;
+        u += in ? fu.y : 0.0;
+    } else {
+        r2 = in ? r2 : 1e300;
+        nin += in ? 1 : 0;
+        const double q = fast_rcp3(r2);
+        const double b = q * q * q;
+        f = b * (b - P.awh) * q;                                     // source/sepmisc.c:139, sepprfrc.c:888 (/ 48 eps)
+        u = fma(b, b - P.aw, u);
+    }
     fx = fma(f, dx, fx); fy = fma(f, dy, fy); fz = fma(f, dz, fz);
     if (IMAGE) {
         if (e & TILE_SLOT_IMAGE) {                                   // boundary-crossing pair: - g (x) S
@@ -60,7 +69,7 @@ __device__ __forceinline__ void lj_tile_pair(double xi, double yi, double zi, in
 }
 
 // the whole row of one atom
-template <bool TYPED, bool IMAGE>
+template <bool TYPED, bool IMAGE, bool TABLE>
 __device__ __forceinline__ void lj_tile_row(double xi, double yi, double zi, int ti, int m, const uint4 *__restrict__ row, int npad,
                                             const double2 *__restrict__ XY, const double *__restrict__ Z,
                                             const unsigned char *__restrict__ CODE, const unsigned char *__restrict__ TYPE,
@@ -74,7 +83,7 @@ __device__ __forceinline__ void lj_tile_row(double xi, double yi, double zi, int
     for (int c = 0; c < nch; c++) {
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (c + 1 < nch) nxt = __ldcs(row + (size_t)(c + 1) * npad);
-#define LJT_PAIR(E) lj_tile_pair<TYPED, IMAGE>(xi, yi, zi, ti, XY, Z, CODE, TYPE, SHIFT, (E), P, fx, fy, fz, u, nin, v)
+#define LJT_PAIR(E) lj_tile_pair<TYPED, IMAGE, TABLE>(xi, yi, zi, ti, XY, Z, CODE, TYPE, SHIFT, (E), P, fx, fy, fz, u, nin, v)
         LJT_PAIR(cur.x & 0xffffu); LJT_PAIR(cur.x >> 16);
         LJT_PAIR(cur.y & 0xffffu); LJT_PAIR(cur.y >> 16);
         LJT_PAIR(cur.z & 0xffffu); LJT_PAIR(cur.z >> 16);
@@ -89,7 +98,8 @@ __device__ __forceinline__ void lj_tile_row(double xi, double yi, double zi, int
 // tile_hdr / tile_src: the staging tables the list builder left behind (per tile: home range, staged count, image flag;
 // per slot: sorted index | image code), so that the kernel starts copying at once -- no cell arithmetic here.
 // MINB: CTAs per SM the register budget is cut for (3: 72 registers, 4: 56)
-template <bool TYPED, bool STORE, int MINB>
+// TABLE: the pair function is a table sampled from a user callback (sep_force_pairs with a function of the caller's own)
+template <bool TYPED, bool STORE, int MINB, bool TABLE>
 __global__ void __launch_bounds__(TILE_THREADS, MINB)
 k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *__restrict__ cnt,
           const int *__restrict__ order, const int4 *__restrict__ tile_hdr, const unsigned *__restrict__ tile_src,
@@ -206,8 +216,8 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
             const double xi = pi.x * isig, yi = pi.y * isig, zi = pi.z * isig;
             double fx = 0.0, fy = 0.0, fz = 0.0, u = 0.0;
             int nin = 0;
-            if (image) lj_tile_row<TYPED, true>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, SHIFT, P, fx, fy, fz, u, nin, acc + 2);
-            else       lj_tile_row<TYPED, false>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, SHIFT, P, fx, fy, fz, u, nin, acc + 2);
+            if (image) lj_tile_row<TYPED, true, TABLE>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, SHIFT, P, fx, fy, fz, u, nin, acc + 2);
+            else       lj_tile_row<TYPED, false, TABLE>(xi, yi, zi, ti, m, nbr + s, npad, XY, Z, CODE, TYPE, SHIFT, P, fx, fy, fz, u, nin, acc + 2);
             const int i = order[s];
             fx *= P.eps48; fy *= P.eps48; fz *= P.eps48;
             if (STORE) {
@@ -220,7 +230,12 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
             }
             // per-atom part of the virial: 2 F_i (x) x_i, upper triangle
             virial_add(acc + 2, fx + fx, fy + fy, fz + fz, pi.x, pi.y, pi.z);
-            acc[0] = P.eps4 * u - P.shift * (double)nin;
+            if (TABLE) {
+                if (nin & 0x40000000) scal->error = SEPGPU_ETABLE;
+                acc[0] = u;
+            } else {
+                acc[0] = P.eps4 * u - P.shift * (double)nin;
+            }
         }
         block_sum<SEPGPU_NPART_F, TILE_THREADS>(acc, red);
         if (threadIdx.x == 0) {
@@ -256,13 +271,19 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, 
     const int stage_cap = c->tile_stage_used;
     const size_t smem = sepgpu_tile_force_smem(stage_cap);
     // the kernel works on coordinates divided by sigma: cutoff and force prefactor follow
-    const double sigma = sqrt(P.sig2), isig = 1.0 / sigma;
+    const double sigma = P.tab ? 1.0 : sqrt(P.sig2), isig = 1.0 / sigma;
     LJDev Ps = P;
-    Ps.cf2 = P.cf2 / P.sig2; Ps.sig2 = 1.0; Ps.eps48 = P.eps48 * isig;
+    Ps.cf2 = P.cf2 / (sigma * sigma); Ps.sig2 = 1.0; Ps.eps48 = P.eps48 * isig;
 #define LJT_LAUNCH3(TY, ST, MB)                                                                                                  \
     do {                                                                                                                         \
-        CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-        k_lj_tile<TY, ST, MB><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt,   \
+        if (P.tab) {                                                                                                             \
+            CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            k_lj_tile<TY, ST, 3, true><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt, \
+                c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);    \
+            break;                                                                                                               \
+        }                                                                                                                        \
+        CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        k_lj_tile<TY, ST, MB, false><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt,   \
             c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);    \
     } while (0)
 #define LJT_LAUNCH(TY, ST) do { if (c->ljt_ctas == 4) LJT_LAUNCH3(TY, ST, 4); else LJT_LAUNCH3(TY, ST, 3); } while (0)

@@ -199,6 +199,11 @@ struct sepgpu_ctx {
     int overlap;                 // decomposed runs: halo refresh beside an interior-only force pass (default 0: measured slower,
                                  // the boundary pass is a nearly empty wave that costs more than the 20 us refresh)
 
+    // tabulated pair function (sepgpu_force_table): device copy and what it was made from
+#define SEPGPU_NTAB 4
+    struct { void *dev; const void *key; int n; double lo, cf; unsigned long long hash; } tab[SEPGPU_NTAB];
+    unsigned tab_next;
+
     // measurement
     cudaEvent_t ev0, ev1;
     KernelTimer t_force, t_build, t_intgr, t_coul, t_bonded, t_halo, t_migr;

@@ -591,6 +591,10 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
         sepgpu_set_error("decomposed step: a neighbour's data never arrived (peer-memory wait timed out)");
         return SEPGPU_ENCCL;
     }
+    if (c->scal_host->error == SEPGPU_ETABLE) {
+        sepgpu_set_error("a pair came closer than the tabulated pair function reaches (raise its resolution towards r = 0: SEP_TABLE_RMIN)");
+        return SEPGPU_ETABLE;
+    }
     if (c->scal_host->neighb_flag) {
         k_set_xn<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n_own);
         KERNEL_CHECK();

@@ -9,7 +9,28 @@
 struct LJDev {
     double cf2, sig2, eps48, eps4, aw, awh, shift;
     int t0, t1;
+    // tabulated pair function (user callbacks of sep_force_pairs): n samples {f, u} on a uniform r^2 grid [t_lo, t_lo + (n-1)/t_inv];
+    // NULL = the Lennard-Jones family above
+    const double2 *tab;
+    double t_lo, t_inv;
+    int t_n;
 };
+
+// {force factor, energy} of a tabulated pair function at r2: cubic Lagrange interpolation through the four grid points
+// around r2 (uniform grid in r^2).  Error <= (3/128) h^4 max|d4/d(r2)4|; with the 32768-point table the host layer
+// builds that is < 1e-12 relative for a Lennard-Jones-like function at r >= 0.8 sigma.  *below: r2 under the table's range.
+__device__ __forceinline__ double2 table_eval(const LJDev &P, double r2, bool &below)
+{
+    const double t = (r2 - P.t_lo) * P.t_inv;
+    below = t < 0.0;
+    int k = (int)t;
+    k = k < 1 ? 1 : (k > P.t_n - 3 ? P.t_n - 3 : k);
+    const double w = t - (double)k;
+    const double wm = w - 1.0, wp = w + 1.0, w2 = w - 2.0;
+    const double c0 = -w * wm * w2 * (1.0 / 6.0), c1 = wp * wm * w2 * 0.5, c2 = -wp * w * w2 * 0.5, c3 = wp * w * wm * (1.0 / 6.0);
+    const double2 a = __ldg(P.tab + k - 1), b = __ldg(P.tab + k), c = __ldg(P.tab + k + 1), d = __ldg(P.tab + k + 2);
+    return make_double2(c0 * a.x + c1 * b.x + c2 * c.x + c3 * d.x, c0 * a.y + c1 * b.y + c2 * c.y + c3 * d.y);
+}
 
 struct BoxDev { double Lx, Ly, Lz; };
 

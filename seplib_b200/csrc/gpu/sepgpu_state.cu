@@ -140,6 +140,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->tsort) cudaFree(c->tsort);
     if (c->xq) cudaFree(c->xq);
     if (c->fin_ticket) cudaFree(c->fin_ticket);
+    for (int q = 0; q < SEPGPU_NTAB; q++) if (c->tab[q].dev) cudaFree(c->tab[q].dev);
     if (c->tile_hdr) cudaFree(c->tile_hdr);
     if (c->tile_src) cudaFree(c->tile_src);
     if (c->randn4) cudaFree(c->randn4);
@@ -602,6 +603,10 @@ extern "C" int sepgpu_read_scalars(sepgpu_ctx *c, sepgpu_scalars *out)
     CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     const DevScalars *s = c->scal_host;
+    if (s->error == SEPGPU_ETABLE) {
+        sepgpu_set_error("a pair came closer than the tabulated pair function reaches (SEP_TABLE_RMIN)");
+        return SEPGPU_ETABLE;
+    }
     out->epot = s->epot; out->ecoul = s->ecoul; out->ekin = s->ekin;
     memcpy(out->pot_P, s->pot_P, sizeof out->pot_P);
     memcpy(out->kin_P, s->kin_P, sizeof out->kin_P);

@@ -58,6 +58,7 @@ void sepb_check(int rc, const char *where)
     if (rc == 0) return;
     if (rc == SEPGPU_ENEIGHB) sep_error("%s: Too many neighbours", (char *)where);
     if (rc == SEPGPU_ECELL) sep_error("%s: Index larger than array length", (char *)where);
+    if (rc == SEPGPU_ETABLE) sep_error("%s: a pair came closer than the table of the pair function reaches (SEP_TABLE_RMIN)", (char *)where);
     if (rc == SEPGPU_ENODEV)
         sep_error("%s: no CUDA device -- seplib-b200 has no CPU path (%s)", (char *)where, (char *)sepgpu_last_error());
     sep_error("%s: device layer failed (%d): %s", (char *)where, rc, (char *)sepgpu_last_error());
@@ -221,6 +222,7 @@ void sepb_unregister(seppart *atoms)
             *pp = b->next;
             if (b->gpu) sepgpu_destroy(b->gpu);
             free(b->blengths_host); free(b->angles_host); free(b->dihedrals_host); free(b->noise);
+            for (int q = 0; q < 4; q++) free(b->pairtab[q].fu);
             free(b);
             return;
         }

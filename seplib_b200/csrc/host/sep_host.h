@@ -42,6 +42,9 @@ typedef struct sep_binding {
     unsigned long long dpd_calls;
     sepret *last_ret;
     double *blengths_host, *angles_host, *dihedrals_host;
+    /* sep_force_pairs with a pair function of the caller's own: its table, sampled once per (function, cutoff) */
+    struct sep_pairtab { double (*fun)(double, char); double cf, r2_lo; int n; double *fu; } pairtab[4];
+    unsigned pairtab_next;
     /* SEP_SYNC=auto: atoms[] is an mmap'ed region whose protection tracks which side is newer */
     int managed;                 /* 1: allocated by sep_init in auto mode */
     void *map_base; size_t map_bytes;

@@ -217,6 +217,56 @@ static void add_ret(sepgpu_ctx *c, const orc_ret *t, int epot_assign, int bond_v
     }
 }
 
+/* sep_force_pairs with a caller-made pair function: the same four-point cubic over the r^2 table the device kernels use
+ * (sepgpu_pair.cuh table_eval), written as a plain loop over the pair list */
+static int table_pair(const double *tab, int n, double lo, double inv, double r2, double *ft, double *u)
+{
+    double s = (r2 - lo) * inv;
+    if (s < 0.0) return -1;
+    int k = (int)s;
+    if (k < 1) k = 1;
+    if (k > n - 3) k = n - 3;
+    const double t = s - (double)k;
+    const double w0 = -t * (t - 1.0) * (t - 2.0) / 6.0, w1 = (t + 1.0) * (t - 1.0) * (t - 2.0) / 2.0;
+    const double w2 = -(t + 1.0) * t * (t - 2.0) / 2.0, w3 = (t + 1.0) * t * (t - 1.0) / 6.0;
+    *ft = w0 * tab[2 * (k - 1)] + w1 * tab[2 * k] + w2 * tab[2 * (k + 1)] + w3 * tab[2 * (k + 2)];
+    *u = w0 * tab[2 * (k - 1) + 1] + w1 * tab[2 * k + 1] + w2 * tab[2 * (k + 1) + 1] + w3 * tab[2 * (k + 2) + 1];
+    return 0;
+}
+
+int sepgpu_force_table(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], double cf, const double *tab_fu, int n, double r2_lo,
+                       unsigned opt, int epot_assign)
+{
+    if (!c || !tab_fu || n < 8 || !(cf * cf > r2_lo)) return SEPGPU_EINVAL;
+    if (sys->neighb_update == 0) { set_error("mock device: tabulated pair functions need a neighbour list"); return SEPGPU_EINVAL; }
+    if (!c->list_valid) { int rc = sepgpu_neighb_build(c, sys, opt); if (rc) return rc; }
+    const double inv = (double)(n - 1) / (cf * cf - r2_lo);
+    orc_ret t;
+    memset(&t, 0, sizeof t);
+    for (long p = 0; p < c->npairs; p++) {
+        const int i = c->pairs[2 * p], j = c->pairs[2 * p + 1];
+        const char a = c->type[i], b = c->type[j];
+        if (!((a == types[0] && b == types[1]) || (a == types[1] && b == types[0]))) continue;
+        double r[3], r2 = 0.0, ft, u;
+        for (int k = 0; k < 3; k++) {
+            r[k] = c->x[3 * i + k] - c->x[3 * j + k];
+            if (r[k] > 0.5 * sys->length[k]) r[k] -= sys->length[k];
+            else if (r[k] < -0.5 * sys->length[k]) r[k] += sys->length[k];
+            r2 += r[k] * r[k];
+        }
+        if (!(r2 < cf * cf)) continue;
+        if (table_pair(tab_fu, n, r2_lo, inv, r2, &ft, &u)) { set_error("pair below the table"); return SEPGPU_ETABLE; }
+        for (int k = 0; k < 3; k++) {
+            c->f[3 * i + k] += ft * r[k];
+            c->f[3 * j + k] -= ft * r[k];
+            for (int kk = 0; kk < 3; kk++) t.pot_P[3 * k + kk] += ft * r[k] * r[kk];
+        }
+        t.epot += u;
+    }
+    add_ret(c, &t, epot_assign, 0);
+    return 0;
+}
+
 int sepgpu_force_lj(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], const sepgpu_ljparam *p, unsigned opt, int epot_assign)
 {
     int pot;

@@ -258,3 +258,32 @@ def test_dpd_loop_is_independent_of_the_coherence_mode(mock):
         assert np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1]) and np.array_equal(r[2], results[0][2])
         assert r[3] == results[0][3] and r[4] == results[0][4]
     assert np.isfinite(results[0][0]).all() and abs(results[0][3] / len(x) - 1.5) < 0.5
+
+
+def test_sep_force_pairs_samples_a_callers_own_pair_function(mock):
+    """host layer: a function the library does not know by address is sampled once per (function, cutoff) and handed
+    to sepgpu_force_table; the mock evaluates the table over the oracle's pair list (same cubic as the kernels)."""
+    g = np.load(os.path.join(cm.GOLDEN, "lj_n1000.npz"))
+    mock.sep_gpu_set_sync(1)
+    s = cm.ApiSystem(mock, g["x0"], float(g["L"]), float(g["cf"]), float(g["dt"]), v=g["v0"], nneighb=0)
+    s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+    calls = [0]
+
+    def user_lj_shift(r2, opt):
+        calls[0] += 1
+        rri = 1.0 / r2; rri3 = rri * rri * rri
+        return 48.0 * rri3 * (rri3 - 0.5) * rri if opt == b"f" else 4.0 * rri3 * (rri3 - 1.0) + 0.016316891136
+
+    cb = C.CFUNCTYPE(C.c_double, C.c_double, C.c_char)(user_lj_shift)
+    for rep in range(2):
+        mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+        mock.sep_force_pairs(s.atoms, b"AA", float(g["cf"]), C.cast(cb, C.c_void_p), s.S, s.R, 1)
+        mock.sep_gpu_sync(s.atoms)
+        assert cm.rel_force_err(s.view["f"], g["f_pairs"]) <= 1e-9
+        assert abs(s.ret.epot - float(g["epot"])) <= 1e-9 * abs(float(g["epot"]))
+        assert calls[0] == 2 * 65536                    # sampled once, reused on the second call
+    mock.sep_pairs_retabulate()
+    mock.sep_reset_retval(s.R); mock.sep_reset_force(s.atoms, s.S)
+    mock.sep_force_pairs(s.atoms, b"AA", float(g["cf"]), C.cast(cb, C.c_void_p), s.S, s.R, 1)
+    assert calls[0] == 4 * 65536
+    s.close()

@@ -209,6 +209,78 @@ def test_small_grid_exact_fallback_and_capacity_growth():
 
 
 # ---- the reference-facing API: host seppart[] buffers through libsep.so -----------------------------------
+PAIRFUN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_char)
+
+
+def _user_lj_shift(r2, opt):
+    """what a user would write after source/sepmisc.c:131-145 -- a pair function the library does NOT know by address"""
+    rri = 1.0 / r2; rri3 = rri * rri * rri
+    if opt == b"f":
+        return 48.0 * rri3 * (rri3 - 0.5) * rri
+    return 4.0 * rri3 * (rri3 - 1.0) + 0.016316891136
+
+
+def _user_morse(r2, opt):
+    r = r2 ** 0.5; e = np.exp(-2.0 * (r - 1.1))
+    if opt == b"f":
+        return float(2.0 * 2.0 * 0.7 * e * (e - 1.0) / r)           # -u'(r) / r
+    return float(0.7 * (e - 1.0) ** 2 - 0.7)
+
+
+@pytest.mark.parametrize("update", [capi.SEP_LLIST_NEIGHBLIST, capi.SEP_BRUTE])
+def test_sep_force_pairs_with_a_pair_function_of_the_callers_own(update):
+    """sep_force_pairs takes ANY double fun(double r2, char opt) (reference include/sepprfrc.h:49-51, called per pair at
+    source/sepprfrc.c:140-146).  The library samples it once and interpolates on the device.  (1) a Python re-statement
+    of sep_lj_shift must reproduce the reference's recorded forces / energy of the same step; (2) a Morse function
+    against a numpy sum over the oracle's pair list.  Tolerance 1e-9 relative (cubic interpolation)."""
+    g = np.load(os.path.join(cm.GOLDEN, "lj_n1000.npz"))
+    lib = capi.load()
+    lib.sep_gpu_set_sync(1)
+    L, cf, dt = float(g["L"]), float(g["cf"]), float(g["dt"])
+    s = cm.ApiSystem(lib, g["x0"], L, cf, dt, v=g["v0"], update=update, nneighb=0)
+    s.view["xn"][:] = g["xn0"]; s.view["cross_neighb"][:] = g["cn0"]; s.view["crossings"][:] = g["cr0"]
+    lj, morse = PAIRFUN(_user_lj_shift), PAIRFUN(_user_morse)
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_force_pairs(s.atoms, b"AA", cf, C.cast(lj, C.c_void_p), s.S, s.R, 1)
+    lib.sep_gpu_sync(s.atoms)
+    assert cm.rel_force_err(s.view["f"], g["f_pairs"]) <= 1e-9
+    assert abs(s.ret.epot - float(g["epot"])) <= 1e-9 * abs(float(g["epot"]))
+    # Morse, cut at 2.0: expectation from the positions, in numpy
+    x = g["x0"]
+    d = x[:, None, :] - x[None, :, :]; d -= L * np.round(d / L)
+    r2 = (d * d).sum(axis=2); np.fill_diagonal(r2, 1e30)
+    inr = r2 < 4.0
+    r = np.sqrt(np.where(inr, r2, 1.0)); e = np.exp(-2.0 * (r - 1.1))
+    ft = np.where(inr, 2.0 * 2.0 * 0.7 * e * (e - 1.0) / r, 0.0)
+    f_exp = (ft[:, :, None] * d).sum(axis=1)
+    u_exp = 0.5 * np.where(inr, 0.7 * (e - 1.0) ** 2 - 0.7, 0.0).sum()
+    P_exp = 0.5 * np.einsum("ij,ija,ijb->ab", ft, d, d)
+    lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+    lib.sep_force_pairs(s.atoms, b"AA", 2.0, C.cast(morse, C.c_void_p), s.S, s.R, 1)
+    lib.sep_gpu_sync(s.atoms)
+    assert cm.rel_force_err(s.view["f"], f_exp) <= 1e-9
+    assert abs(s.ret.epot - u_exp) <= 1e-9 * abs(u_exp)
+    assert np.abs(np.array(s.ret.pot_P).reshape(3, 3) - P_exp).max() <= 1e-8 * np.abs(P_exp).max()
+    s.close()
+
+
+def test_pair_closer_than_the_table_is_an_error_not_an_extrapolation():
+    g = np.load(os.path.join(cm.GOLDEN, "lj_n1000.npz"))
+    x = g["x0"].copy(); L = float(g["L"])
+    x[1] = x[0] + np.array([0.2, 0.0, 0.0])                # closer than 0.15 cf
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    n = 4096; lo = (0.15 * 2.5) ** 2
+    r2 = lo + (6.25 - lo) * np.arange(n) / (n - 1)
+    tab = np.empty((n, 2)); tab[:, 0] = 48.0 * r2 ** -7 - 24.0 * r2 ** -4; tab[:, 1] = 4.0 * (r2 ** -6 - r2 ** -3)
+    s.call("sepgpu_neighb_build", C.byref(sys_), 1)
+    rc = s.lib.sepgpu_force_table(s.ctx, C.byref(sys_), b"AA", 2.5, tab.ctypes.data_as(C.POINTER(C.c_double)), n, lo, 1, 1)
+    assert rc == 0
+    sc = capi.GpuScalars()
+    assert s.lib.sepgpu_read_scalars(s.ctx, C.byref(sc)) == -8      # SEPGPU_ETABLE
+    s.close()
+
+
 @pytest.mark.parametrize("sync", [1, 0])        # SEP_SYNC_STEP, SEP_SYNC_LAZY
 def test_sep_api_lj_loop_matches_reference_golden(sync):
     """The prg1 loop written against include/sep.h, run through libsep.so on host buffers, reproduces the

@@ -212,6 +212,64 @@ def test_tile_forces_match_oracle(typed, skin):
     s.close()
 
 
+@pytest.mark.parametrize("typed", [False, True])
+def test_tabulated_pair_function_on_tile_lists(typed):
+    """sepgpu_force_table (what sep_force_pairs calls for a pair function of the caller's own) on a tile-format list:
+    a table sampled from the shifted LJ function and from a Morse function, against the oracle's LJ forces and a numpy
+    sum over the oracle's pairs.  Bound 1e-9: four-point cubic interpolation on 65536 points."""
+    x, L = _lj(12, seed=9)
+    n = len(x)
+    cf = 2.5
+    rng = np.random.default_rng(5)
+    types = (np.where(rng.random(n) < 0.4, ord("B"), ord("A")) if typed else np.full(n, ord("A"))).astype(np.uint8)
+    pp = np.ascontiguousarray(cm.oracle_pairs(x, L, cf, 0.25), dtype=np.int32)
+    orc = cm.oracle(); length = cm.dvec3([L] * 3)
+    fref = np.zeros((n, 3)); rref = cm.OrcRet()
+    tsel = b"AB" if typed else b"AA"
+    orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(length), cm.ptr(pp), len(pp), tsel, cf, cm.POT_LJ_SHIFT,
+                             None, cm.ptr(fref), C.byref(rref))
+    nt = 65536; lo = (0.15 * cf) ** 2
+
+    def table(rc, ffun, ufun):
+        r2 = lo + (rc * rc - lo) * np.arange(nt) / (nt - 1)
+        t = np.empty((nt, 2)); t[:, 0] = ffun(r2); t[:, 1] = ufun(r2)
+        return t
+
+    lj = table(cf, lambda r2: 48.0 * r2 ** -7 - 24.0 * r2 ** -4, lambda r2: 4.0 * (r2 ** -6 - r2 ** -3) + 0.016316891136)
+    s = capi.System(n)
+    s.put(capi.F_X, x); s.put(capi.F_TYPE, types)
+    sys_ = capi.make_sys([L] * 3, cf, 0.005)
+    s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+    s.call("sepgpu_force_table", C.byref(sys_), tsel, cf, lj.ctypes.data_as(C.POINTER(C.c_double)), nt, lo, cm.ALL, 1)
+    assert _opt(s, "list_f16") == 1
+    f = s.get(capi.F_F); sc = s.scalars()
+    assert cm.rel_force_err(f, fref) <= 1e-9
+    assert abs(sc.epot - rref.epot) <= 1e-9 * max(abs(rref.epot), 1.0)
+    P = np.array(sc.pot_P[:]); Pref = np.array(rref.pot_P[:])
+    assert np.abs(P - Pref).max() <= 1e-9 * np.abs(Pref).max()
+    # Morse cut at 2.0 on the same list, accumulated on top (epot_assign = 0): expectation in numpy over the listed pairs
+    D, a, r0, rc = 0.7, 2.0, 1.1, 2.0
+    mo = table(rc, lambda r2: 2 * a * D * np.exp(-a * (np.sqrt(r2) - r0)) * (np.exp(-a * (np.sqrt(r2) - r0)) - 1) / np.sqrt(r2),
+               lambda r2: D * (np.exp(-a * (np.sqrt(r2) - r0)) - 1) ** 2 - D)
+    i, j = pp[:, 0], pp[:, 1]
+    d = x[i] - x[j]; d -= L * np.round(d / L)
+    r2 = (d * d).sum(axis=1)
+    sel = r2 < rc * rc
+    if typed:
+        ti, tj = types[i], types[j]
+        sel &= ((ti == ord("A")) & (tj == ord("B"))) | ((ti == ord("B")) & (tj == ord("A")))
+    r = np.sqrt(r2[sel]); e = np.exp(-a * (r - r0))
+    ft = 2 * a * D * e * (e - 1) / r
+    fexp = fref.copy()
+    np.add.at(fexp, i[sel], ft[:, None] * d[sel]); np.add.at(fexp, j[sel], -ft[:, None] * d[sel])
+    uexp = rref.epot + (D * (e - 1) ** 2 - D).sum()
+    s.call("sepgpu_force_table", C.byref(sys_), tsel, rc, mo.ctypes.data_as(C.POINTER(C.c_double)), nt, lo, cm.ALL, 0)
+    f = s.get(capi.F_F); sc = s.scalars()
+    assert cm.rel_force_err(f, fexp) <= 1e-9
+    assert abs(sc.epot - uexp) <= 1e-9 * max(abs(uexp), 1.0)
+    s.close()
+
+
 def test_tile_trajectory_follows_the_global_row_kernels():
     """24 NVT steps (prg1-style loop through the C ABI) with the tile kernels (default) and with global-index rows +
     the gather kernel (tile_list = 0): same rebuild steps, energies equal to rounding growth."""
@@ -354,6 +412,38 @@ def test_tile_list_with_exclusions_water():
     s.call("sepgpu_neighb_build", C.byref(sys_), cm.EXCL_SAME_MOL)
     assert np.array_equal(cm.pair_set(s.pairs(4_000_000)), cm.pair_set(pairs))
     s.close()
+
+
+@pytest.mark.parametrize("window", [0, 2])
+def test_build_window_changes_nothing_but_the_work(window):
+    """Cells are sorted along x inside; with build_window the builder sweeps each row of cells only inside the x window
+    within reach of the atom (default: from 24 atoms per cell on; 2 forces it).  Pair set bit-exact against the oracle,
+    entry count and the reference-style half-list length equal with and without -- also with same-molecule exclusion."""
+    x, L = _lj(14, seed=6, jitter=0.3)
+    ref_pairs = cm.pair_set(cm.oracle_pairs(x, L, 2.5, 0.25))
+    s = capi.System(len(x)); s.put(capi.F_X, x)
+    s.call("sepgpu_set_option", b"build_window", window)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+    assert np.array_equal(cm.pair_set(s.pairs()), ref_pairs)
+    sc = s.scalars()
+    assert sc.npairs_listed == 2 * len(ref_pairs)
+    half = _opt(s, "max_half")
+    s.close()
+    t = capi.System(len(x)); t.put(capi.F_X, x)
+    t.call("sepgpu_set_option", b"tile_list", 0)
+    t.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+    assert _opt(t, "max_half") == half
+    t.close()
+    # water cell with same-molecule exclusion
+    w, xw, types, z, mol, Lw = _water_system(2, {"build_window": window})
+    n = len(xw)
+    tp = cm.Topo(n); tp.molindex[:] = mol
+    pairs = cm.oracle_pairs(xw, Lw, 2.9, 0.25, opt=cm.EXCL_SAME_MOL, topo=tp, max_pairs=4_000_000)
+    sysw = capi.make_sys(Lw, 2.9, 5e-4, skin=0.25)
+    w.call("sepgpu_neighb_build", C.byref(sysw), cm.EXCL_SAME_MOL)
+    assert np.array_equal(cm.pair_set(w.pairs(4_000_000)), cm.pair_set(pairs))
+    w.close()
 
 
 # ---- corner cases of the list formats ----------------------------------------------------------------------------------
