@@ -95,7 +95,9 @@ def test_prg2_prg3_prg6_run(tmp_path):
     assert np.allclose(got2[1, 2:5], ref2[1, 2:5], rtol=0, atol=5e-5), (got2[1], ref2[1])
     assert abs(got2[1, 7] - ref2[1, 7]) <= 0.03 and abs(got2[1, 8] - ref2[1, 8]) <= 0.03, (got2[1], ref2[1])
     assert abs(got2[10:, 5].mean() - ref2[10:, 5].mean()) < 0.02            # thermostatted temperature (4.0)
-    assert abs(got2[10:, 2].mean() - ref2[10:, 2].mean()) < 0.01            # epot/N
+    # epot/N: the 90 printed samples scatter by 0.07 each, so the means of two decorrelated trajectories differ by
+    # ~0.01 rms (measured 0.002 and 0.016 with two orderings of the same neighbour rows); 4 sigma
+    assert abs(got2[10:, 2].mean() - ref2[10:, 2].mean()) < 0.04
     assert abs(got2[10:, 7].mean() - ref2[10:, 7].mean()) < 0.15            # atomic pressure
     assert abs(got2[10:, 8].mean() - ref2[10:, 8].mean()) < 0.15            # molecular pressure
     got3, txt3 = run_prg("prg3", tmp_path=tmp_path)
