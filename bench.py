@@ -797,7 +797,7 @@ def main():
     # ---------------- e2e arm: host buffers in, host buffers out ------------------------------------
     e2e = None
     if not args.no_e2e:
-        Ke = max(10, min(K, 300))
+        Ke = max(10, K)                  # the same K steps as the device-resident arm
         if not decomposed:
             # the reference-facing sep_* API of include/sep.h on a host seppart[] array, in the library's DEFAULT coherence
             # mode (SEP_SYNC=auto: what an unchanged program gets) -- and, for comparison, in lazy and step mode

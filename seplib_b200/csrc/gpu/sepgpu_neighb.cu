@@ -220,7 +220,7 @@ __device__ __forceinline__ int share_tab(const int *__restrict__ tab, int width,
 struct BuildParams {
     double Lx, Ly, Lz;
     double cut2;
-    float fLx, fLy, fLz, fcut_lo, fcut_hi;
+    float fLx, fLy, fLz, fcut_lo, fcut_hi, fband;       // fband: width of the FP32 error band below fcut_hi
     float flsy, flsz;       // cell widths along y and z (window of the tiled builder)
     int zcell0;             // global cell layer of local layer 0 (slab runs: zoff, else 0)
     int xwindow;            // tiled builder: restrict each row to the x window within reach (cells at least as wide as the cutoff)
@@ -485,6 +485,7 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
         P.xwindow = cut <= wmin && (c->build_window == 2 || (c->build_window == 1 && mean_per_cell >= 24.0)) ? 1 : 0;
         P.fcut_lo = (float)(P.cut2 - band);
         P.fcut_hi = (float)(P.cut2 + band);
+        P.fband = (float)(2.0 * band) * 1.0001f;
         const int ntile = nkey / (G.bx * R);
         if (P.prefilter) {
             if (c->tile_stage_cap == 0) {
@@ -504,9 +505,10 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
                 CUDA_TRY(cudaMalloc((void **)&c->tile_src, sizeof(unsigned) * (size_t)ntile * stage_cap));
                 c->tile_src_cap = (size_t)ntile * stage_cap;
             }
-            const size_t smem = (size_t)(stage_cap + TILE_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0));
+            const int home_cap = stage_cap / 2;
+            const size_t smem = (size_t)(stage_cap + TILE_PAD) * (sizeof(float4) + (opt == SEPGPU_EXCL_SAME_MOL ? sizeof(int) : 0)) + sizeof(int) * (size_t)home_cap;
             if (smem > 200 * 1024) { sepgpu_set_error("neighb_build: cell occupancy too high for the tiled builder"); return SEPGPU_EINVAL; }
-#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, R, stage_cap, c->tile_hdr, c->tile_src
+#define TILE_ARGS c->xs, c->xf, c->order, c->cell_start, c->excl_bond, c->excl_angle, c->excl_dihed, c->nbr, c->cnt, c->scal, P, R, stage_cap, home_cap, c->tile_hdr, c->tile_src
 #define TILE_LAUNCH(O, F)                                                                                                        \
     do {                                                                                                                         \
         CUDA_TRY(cudaFuncSetAttribute(k_build_tile<O, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \

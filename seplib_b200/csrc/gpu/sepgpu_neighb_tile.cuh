@@ -14,7 +14,8 @@
 // F16 = true : rows of 16-bit tile slots (sepgpu_tile.cuh) for the tile force kernels, 8 per 128-bit chunk.
 // F16 = false: rows of 32-bit entries  sorted index | image code << 26, 4 per chunk, for the kernels that
 //              gather from global memory (DPD, the molecule-pair table, small grids).
-// Rows are assembled in registers and leave as whole 128-bit chunks.
+// 16-bit entries leave one by one into the row's current 128-bit chunk (L2 merges the partial sectors); 32-bit rows
+// are assembled in registers and leave as whole chunks.
 #pragma once
 
 #include "sepgpu_tile.cuh"
@@ -30,6 +31,20 @@ __device__ __forceinline__ unsigned bit_range(int lo, int hi)
     const unsigned upto = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
     return upto & ~((1u << lo) - 1u);
 }
+
+// packed FP32 (two lanes of one 64-bit register pair per instruction: FADD2 / FFMA2 on sm_100)
+#ifdef SEPGPU_EMU
+static inline float2 f2_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 f2_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+static inline int imin3(int a, int b, int c) { return a < b ? (a < c ? a : c) : (b < c ? b : c); }
+static inline unsigned shift_in_sign(unsigned m, float d) { return (m << 1) | (__float_as_uint(d) >> 31); }
+#else
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ int imin3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
+// (m << 1) | sign(d): one funnel shift
+__device__ __forceinline__ unsigned shift_in_sign(unsigned m, float d) { return __funnelshift_l(__float_as_uint(d), m, 1); }
+#endif
 
 template <bool F16>
 struct RowWriter {
@@ -77,11 +92,18 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
              const int *__restrict__ cell_start, const int *__restrict__ excl_bond,
              const int *__restrict__ excl_angle, const int *__restrict__ excl_dihed,
              unsigned *__restrict__ nbr, int *__restrict__ cnt, DevScalars *scal, BuildParams P, int R, int stage_cap,
-             int4 *__restrict__ tile_hdr, unsigned *__restrict__ tile_src)
+             int home_cap, int4 *__restrict__ tile_hdr, unsigned *__restrict__ tile_src)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *cand = reinterpret_cast<float4 *>(smem_raw);                       // [stage_cap + TILE_PAD]
-    int *cand_mol = reinterpret_cast<int *>(cand + stage_cap + TILE_PAD);      // [stage_cap + TILE_PAD] (SAME_MOL only)
+    // candidates as four arrays (x, y, z, list entry), so that one 128-bit read brings one coordinate of FOUR candidates
+    // for the packed FP32 tests below; each [stage_cap + TILE_PAD], both multiples of 32
+    const int SC = stage_cap + TILE_PAD;
+    float *candX = reinterpret_cast<float *>(smem_raw);
+    float *candY = candX + SC;
+    float *candZ = candY + SC;
+    unsigned *candW = reinterpret_cast<unsigned *>(candZ + SC);
+    int *home_order = reinterpret_cast<int *>(candW + SC);                     // [home_cap] original index of the home atoms
+    int *cand_mol = home_order + home_cap;                                     // [SC] (SAME_MOL only)
     __shared__ TileLayout T;
     __shared__ int s_red[3];
 
@@ -113,30 +135,44 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
         // flags: bit 0 some candidate is a periodic image, bit 1 (slab runs) some candidate is a halo atom
         tile_hdr[blockIdx.x] = make_int4(T.a0, T.nhome, total, T.any_image | ((G.dd && (T.cz == 1 || T.cz == G.nz - 2)) ? 2 : 0));
     }
-    // ---- stage every candidate of the tile once: warps take cells, lanes take atoms; cp.async copies (all of a thread's
-    // loads in flight at once), then every thread finishes the slots it copied: image shift, list entry in .w ----
+    // ---- stage every candidate of the tile once: thread q takes slots q, q + 288, ...; four loads in flight per
+    // thread, then image shift, list entry, and the scatter into the four arrays ----
     {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int c = wid; c < T.ncell; c += TILE_THREADS / 32) {
-            const int q0 = T.off[c], len = T.off[c + 1] - q0, j0 = T.beg[c];
-            for (int k = lane; k < len; k += 32) __pipeline_memcpy_async(&cand[q0 + k], &xf[j0 + k], 16);
+        if (threadIdx.x < TILE_PAD) {                                          // padding: never in range
+            const int q = total + threadIdx.x;
+            candX[q] = 1e18f; candY[q] = 1e18f; candZ[q] = 1e18f; candW[q] = 0u;
         }
-        __pipeline_commit();
-        if (threadIdx.x < TILE_PAD) cand[total + threadIdx.x] = make_float4(1e18f, 1e18f, 1e18f, 0.f);   // padding: never in range
-        __pipeline_wait_prior(0);
-        for (int c = wid; c < T.ncell; c += TILE_THREADS / 32) {
-            const int q0 = T.off[c], len = T.off[c + 1] - q0, j0 = T.beg[c];
-            const unsigned code = T.code[c];
-            const int wx = (int)(code % 3u) - 1, wy = (int)((code / 3u) % 3u) - 1, wz = (int)(code / 9u) - 1;
-            for (int k = lane; k < len; k += 32) {
-                float4 f = cand[q0 + k];
-                if (OPT == SEPGPU_EXCL_SAME_MOL) cand_mol[q0 + k] = __float_as_int(f.w);
-                f.x += wx * P.fLx; f.y += wy * P.fLy; f.z += wz * P.fLz;
-                const unsigned ent = (unsigned)(j0 + k) | (code << SEPGPU_SHIFT_BITS);
-                f.w = __uint_as_float(ent);
-                cand[q0 + k] = f;
-                // the staging order of this tile, for the force kernels: slot -> sorted index | image code
-                tile_src[(size_t)blockIdx.x * stage_cap + q0 + k] = ent;
+        // (the reference-style half-list length below compares original indices inside the own cell)
+        if (T.nhome <= home_cap)
+            for (int k = threadIdx.x; k < T.nhome; k += TILE_THREADS) home_order[k] = order[T.a0 + k];
+        for (int qb = threadIdx.x; qb < total; qb += 4 * TILE_THREADS) {
+            float4 f[4];
+            unsigned ent[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int q = qb + u * TILE_THREADS;
+                if (q < total) {
+                    const int cc = tile_cell_of_slot(T, q);
+                    const int j = T.beg[cc] + (q - T.off[cc]);
+                    ent[u] = (unsigned)j | ((unsigned)T.code[cc] << SEPGPU_SHIFT_BITS);
+                    f[u] = xf[j];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int q = qb + u * TILE_THREADS;
+                if (q < total) {
+                    const unsigned code = ent[u] >> SEPGPU_SHIFT_BITS;
+                    const int wx = (int)(code % 3u) - 1, wy = (int)((code / 3u) % 3u) - 1, wz = (int)(code / 9u) - 1;
+                    if (OPT == SEPGPU_EXCL_SAME_MOL) {                  // atoms outside molecules (-1) never match anyone
+                        const int mj = __float_as_int(f[u].w);
+                        cand_mol[q] = mj == -1 ? 0x3fffffff : mj;
+                    }
+                    candX[q] = f[u].x + wx * P.fLx; candY[q] = f[u].y + wy * P.fLy; candZ[q] = f[u].z + wz * P.fLz;
+                    candW[q] = ent[u];
+                    // the staging order of this tile, for the force kernels: slot -> sorted index | image code
+                    tile_src[(size_t)blockIdx.x * stage_cap + q] = ent[u];
+                }
             }
         }
     }
@@ -151,11 +187,15 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             const int hx = h % G.bx, hy = h / G.bx;
             const float4 fi = xf[s];
             const int mol_i = __float_as_int(fi.w);
+            const float2 nxi = make_float2(-fi.x, -fi.x), nyi = make_float2(-fi.y, -fi.y), nzi = make_float2(-fi.z, -fi.z);
+            const float2 nhi = make_float2(-P.fcut_hi, -P.fcut_hi);
+            const int band_bits = __float_as_int(P.fband);
+            const int mol_x = mol_i == -1 ? 0x3ffffffe : mol_i;
             int count = 0, half_count = 0;
-            RowWriter<false> W;
-            W.init(0u);
             // F16: entries leave one by one as 16-bit stores into the row's current 128-bit chunk
             unsigned short *row16 = reinterpret_cast<unsigned short *>(nbr) + (size_t)s * 8;
+            RowWriter<false> W;
+            W.init(0u);
             const bool img_tile = F16 && T.any_image != 0;
 #pragma unroll 1
             for (int r = 0; r < 9; r++) {
@@ -181,25 +221,60 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                     const float reach = sqrtf(reach2) + 1e-3f;
                     const float xlo = fi.x - reach, xhi = fi.x + reach;
                     int lo = wlo, hi = whi;                       // first candidate with x >= xlo
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cand[mid].x < xlo) lo = mid + 1; else hi = mid; }
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (candX[mid] < xlo) lo = mid + 1; else hi = mid; }
                     wlo = lo;
                     hi = whi;                                     // first candidate with x > xhi
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cand[mid].x <= xhi) lo = mid + 1; else hi = mid; }
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (candX[mid] <= xhi) lo = mid + 1; else hi = mid; }
                     whi = lo;
                 }
 #pragma unroll 1
-                for (int q0 = wlo; q0 < whi; q0 += 32) {
+                for (int q0 = wlo & ~3; q0 < whi; q0 += 32) {
 #ifdef SEPGPU_EMU
                     sepgpu_emu_counter[0] += 32;         // CPU kernel emulator only: candidates tested (work statistics)
 #endif
-                    unsigned mask = 0, band = 0;
+                    // 32 candidates, eight at a time: d = r^2 - cut_hi in packed FP32 (two candidates per instruction);
+                    // the sign bit of d IS the mask bit (funnel-shifted in), and the smallest signed integer among the
+                    // bit patterns of the d's belongs to the accepted candidate closest to the cutoff -- which tells
+                    // whether anyone sits in the FP32 error band [cut_lo, cut_hi) that needs the exact test.
+                    unsigned mask = 0, band = 0, same = 0;
+                    int dmin = 0x7fffffff, ntest = 0;
 #pragma unroll
-                    for (int b = 0; b < 32; b++) {
-                        const float4 fj = cand[q0 + b];
-                        const float dx = fi.x - fj.x, dy = fi.y - fj.y, dz = fi.z - fj.z;
-                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        if (r2 <= P.fcut_hi) mask |= 1u << b;
-                        if (r2 >= P.fcut_lo) band |= 1u << b;
+                    for (int g = 0; g < 4; g++) {
+                        if (g > 0 && q0 + 8 * g >= whi) break;
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const float4 X = *reinterpret_cast<const float4 *>(candX + q0 + 8 * g + 4 * h);
+                            const float4 Y = *reinterpret_cast<const float4 *>(candY + q0 + 8 * g + 4 * h);
+                            const float4 Z = *reinterpret_cast<const float4 *>(candZ + q0 + 8 * g + 4 * h);
+                            const float2 dx0 = f2_add(make_float2(X.x, X.y), nxi), dx1 = f2_add(make_float2(X.z, X.w), nxi);
+                            const float2 dy0 = f2_add(make_float2(Y.x, Y.y), nyi), dy1 = f2_add(make_float2(Y.z, Y.w), nyi);
+                            const float2 dz0 = f2_add(make_float2(Z.x, Z.y), nzi), dz1 = f2_add(make_float2(Z.z, Z.w), nzi);
+                            const float2 d0 = f2_fma(dz0, dz0, f2_fma(dy0, dy0, f2_fma(dx0, dx0, nhi)));
+                            const float2 d1 = f2_fma(dz1, dz1, f2_fma(dy1, dy1, f2_fma(dx1, dx1, nhi)));
+                            mask = shift_in_sign(mask, d0.x); mask = shift_in_sign(mask, d0.y);
+                            mask = shift_in_sign(mask, d1.x); mask = shift_in_sign(mask, d1.y);
+                            dmin = imin3(dmin, __float_as_int(d0.x), __float_as_int(d0.y));
+                            dmin = imin3(dmin, __float_as_int(d1.x), __float_as_int(d1.y));
+                            if (OPT == SEPGPU_EXCL_SAME_MOL) {               // same molecule <=> (mol_j ^ mol_i) - 1 is negative
+                                const int4 M = *reinterpret_cast<const int4 *>(cand_mol + q0 + 8 * g + 4 * h);
+                                same = shift_in_sign(same, __int_as_float((M.x ^ mol_x) - 1));
+                                same = shift_in_sign(same, __int_as_float((M.y ^ mol_x) - 1));
+                                same = shift_in_sign(same, __int_as_float((M.z ^ mol_x) - 1));
+                                same = shift_in_sign(same, __int_as_float((M.w ^ mol_x) - 1));
+                            }
+                        }
+                        ntest += 8;
+                    }
+                    mask = __brev(mask) >> (32 - ntest);                 // bit b = candidate q0 + b
+                    if (OPT == SEPGPU_EXCL_SAME_MOL) mask &= ~(__brev(same) >> (32 - ntest));      // source/sepprfrc.c:673-674
+                    if (q0 < wlo) mask &= ~((1u << (wlo - q0)) - 1u);    // (the block starts on a multiple of four)
+                    if (dmin < 0 && (dmin & 0x7fffffff) <= band_bits) {
+                        // someone within the error band below cut_hi: find them (rare)
+                        for (int b = 0; b < ntest; b++) {
+                            const float ex = candX[q0 + b] - fi.x, ey = candY[q0 + b] - fi.y, ez = candZ[q0 + b] - fi.z;
+                            const float e = fmaf(ez, ez, fmaf(ey, ey, fmaf(ex, ex, -P.fcut_hi)));
+                            if (e < 0.f && e >= -P.fband) band |= 1u << b;
+                        }
                     }
                     const int nvalid = whi - q0;
                     if (nvalid < 32) mask &= (1u << nvalid) - 1u;
@@ -211,17 +286,17 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                         const int b = __ffs(band) - 1;
                         band &= band - 1;
                         int code;
-                        const int j = (int)(__float_as_uint(cand[q0 + b].w) & SEPGPU_INDEX_MASK);
+                        const int j = (int)(candW[q0 + b] & SEPGPU_INDEX_MASK);
                         // (under the prefilter preconditions the image pair_exact picks equals the cell image)
                         if (!pair_exact(xs[s], xs[j], P, code)) mask &= ~(1u << b);
                     }
                     // ... and the exclusion rules remove their pairs from the mask
-                    if (OPT != SEPGPU_ALL) {
+                    if (OPT == SEPGPU_EXCL_BONDED) {
                         unsigned m2 = mask;
                         while (m2) {
                             const int b = __ffs(m2) - 1;
                             m2 &= m2 - 1;
-                            const int j = (int)(__float_as_uint(cand[q0 + b].w) & SEPGPU_INDEX_MASK);
+                            const int j = (int)(candW[q0 + b] & SEPGPU_INDEX_MASK);
                             if (excluded<OPT>(mol_i, OPT == SEPGPU_EXCL_SAME_MOL ? cand_mol[q0 + b] : 0, s, j, order,
                                               excl_bond, excl_angle, excl_dihed)) mask &= ~(1u << b);
                         }
@@ -234,35 +309,54 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                         half_count += __popc(mask & bit_range(cut_b - q0, 32));
                         unsigned own = mask & bit_range(cut_a - q0, cut_b - q0);
                         if (own) {
-                            const int my_i = order[s];
-                            while (own) {
-                                const int b = __ffs(own) - 1;
-                                own &= own - 1;
-                                half_count += order[__float_as_uint(cand[q0 + b].w) & SEPGPU_INDEX_MASK] > my_i;
+                            if (nhome <= home_cap) {
+                                const int my_i = home_order[s - a0];
+                                while (own) {
+                                    const int b = __ffs(own) - 1;
+                                    own &= own - 1;
+                                    half_count += home_order[(int)(candW[q0 + b] & SEPGPU_INDEX_MASK) - a0] > my_i;
+                                }
+                            } else {
+                                const int my_i = order[s];
+                                while (own) {
+                                    const int b = __ffs(own) - 1;
+                                    own &= own - 1;
+                                    half_count += order[candW[q0 + b] & SEPGPU_INDEX_MASK] > my_i;
+                                }
                             }
                         }
                     }
                     const int nacc = __popc(mask);
                     if (count + nacc <= P.cap) {
                         if (F16) {
-                            unsigned imgbits = 0;                        // candidates of this block that sit in a periodic image
                             if (img_tile) {
+                                unsigned imgbits = 0;                    // candidates of this block that sit in a periodic image
                                 if (im0) imgbits |= bit_range(wlo - q0, cut_a - q0);
                                 if (im1) imgbits |= bit_range(cut_a - q0, cut_b - q0);
                                 if (im2) imgbits |= bit_range(cut_b - q0, whi - q0);
-                            }
-                            while (mask) {
-                                const int b = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                *row16 = (unsigned short)((unsigned)(q0 + b) | (((imgbits >> b) & 1u) << 15));
-                                count++;
-                                row16 += (count & 7) ? 1 : P.npad * 8 - 7;
+                                while (mask) {
+                                    const int b = __ffs(mask) - 1;
+                                    mask &= mask - 1;
+                                    *row16 = (unsigned short)((unsigned)(q0 + b) | (((imgbits >> b) & 1u) << 15));
+                                    count++;
+                                    row16 += (count & 7) ? 1 : P.npad * 8 - 7;
+                                }
+                            } else {
+                                while (mask) {
+                                    const int b = __ffs(mask) - 1;
+                                    mask &= mask - 1;
+                                    *row16 = (unsigned short)(q0 + b);
+                                    count++;
+                                    row16 += (count & 7) ? 1 : P.npad * 8 - 7;
+                                }
                             }
                         } else {
+                            // (32-bit rows are long where they are used -- 400 entries per atom in water -- and leave as whole
+                            //  128-bit chunks: single 4-byte stores were measured 50 % slower there)
                             while (mask) {
                                 const int b = __ffs(mask) - 1;
                                 mask &= mask - 1;
-                                W.push(__float_as_uint(cand[q0 + b].w), count, s, P.npad, nbr);
+                                W.push(candW[q0 + b], count, s, P.npad, nbr);
                                 count++;
                             }
                         }

@@ -182,6 +182,37 @@ def test_tile_list_holds_exactly_the_reference_pair_set(skin, ncell):
     s.close()
 
 
+@pytest.mark.parametrize("opts", ["", "tile_list=0"])
+def test_pairs_at_the_list_cutoff_are_decided_in_double_precision(opts):
+    """The builder tests candidates in packed FP32 and sends everything within the FP32 error band of the list cutoff to
+    the exact FP64 test (reference arithmetic, source/sepprfrc.c:437-452).  600 pairs are placed at (cf + skin)(1 +- eps),
+    eps from 1e-15 to 1e-4: the listed set must still equal the oracle's bit for bit, with pairs on both sides of it."""
+    x, L = _lj(14, seed=31)
+    n = len(x)
+    cf, skin = 2.5, 0.25
+    rng = np.random.default_rng(17)
+    idx = rng.permutation(n)[:1200]
+    eps = 10.0 ** rng.uniform(-15, -4, 600) * rng.choice([-1.0, 1.0], 600)
+    u = rng.normal(size=(600, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    x = x.copy()
+    x[idx[600:]] = x[idx[:600]] + (cf + skin) * (1.0 + eps)[:, None] * u
+    x -= L * np.floor(x / L)
+    ref_pairs = cm.pair_set(cm.oracle_pairs(x, L, cf, skin))
+    planted = {(min(a, b), max(a, b)) for a, b in zip(idx[:600], idx[600:])}
+    listed = {tuple(p) for p in ref_pairs.tolist()}
+    inside = len(planted & listed)
+    assert 200 < inside < 400                      # the oracle itself puts them on both sides
+    s = capi.System(n)
+    s.put(capi.F_X, x)
+    for kv in filter(None, opts.split(",")):
+        k, v = kv.split("="); s.call("sepgpu_set_option", k.encode(), int(v))
+    sys_ = capi.make_sys([L] * 3, cf, 0.005, skin=skin)
+    s.call("sepgpu_neighb_build", C.byref(sys_), cm.ALL)
+    got = cm.pair_set(s.pairs())
+    assert got.shape == ref_pairs.shape and np.array_equal(got, ref_pairs)
+    s.close()
+
+
 @pytest.mark.parametrize("typed,skin", [(False, 0.25), (True, 0.25), (False, 1.0)])
 def test_tile_forces_match_oracle(typed, skin):
     x, L = _lj(12, seed=9)
