@@ -227,6 +227,9 @@ int sepgpu_get_option(sepgpu_ctx *ctx, const char *name, long long *value);
  * every rank with the same id, sepgpu_dd_set_owned(n), sepgpu_put(X, V, GID, ...) for the atoms whose
  * cell layer (int)(z/lsubbox[2]) lies in this rank's range, then the ordinary per-step calls.  All
  * ranks must make the same calls in the same order (they are collective). ---- */
+/* put/get address the host records through rows[i] (i = device atom) instead of i; NULL switches back.  Decomposed runs
+ * behind the sep_* API use it with the global ids so that each process touches only its own atoms of the full array. */
+int sepgpu_set_host_rows(sepgpu_ctx *ctx, const int *rows);
 int sepgpu_dd_unique_id(void *out128);
 int sepgpu_dd_init(sepgpu_ctx *ctx, int rank, int nranks, const void *id128, const sepgpu_sys *sys, long long n_global);
 int sepgpu_dd_set_owned(sepgpu_ctx *ctx, int n_own);

@@ -1,3 +1,8 @@
 #!/bin/bash
-# 2-GPU check of the domain decomposition (run with: gpurun --gpus 2 -- bash scripts/gpu_dd2.sh); uneven layer split
-DD_NCELL=30 timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dd_check.py 2>&1 | grep "dd_check\|differ\|rror" | tail -3
+# 2 GPUs: decomposition tests (C ABI under torchrun, SEP_NGPU through the sep_* API), then the decomposed bench
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_dd.py -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/dd2.txt
+if [ "${DD2_BENCH:-1}" = 1 ]; then
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 300 --warmup 100 --no-cpu 2>gpurun_out/b2.err > gpurun_out/b2.json; python scripts/summ.py "N=2 dd" < gpurun_out/b2.json
+grep -v "^W0\|OMP_NUM\|^\*\*\*\|^$" gpurun_out/b2.err | tail -3
+fi

@@ -204,6 +204,8 @@ struct sepgpu_ctx {
     struct { void *dev; const void *key; int n; double lo, cf; unsigned long long hash; } tab[SEPGPU_NTAB];
     unsigned tab_next;
 
+    const int *host_rows;          // sepgpu_set_host_rows
+
     // measurement
     cudaEvent_t ev0, ev1;
     KernelTimer t_force, t_build, t_intgr, t_coul, t_bonded, t_halo, t_migr;

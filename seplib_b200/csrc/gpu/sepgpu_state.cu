@@ -402,16 +402,26 @@ extern "C" int sepgpu_put_fields(sepgpu_ctx *c, const void *base, size_t stride,
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     const char *src = (const char *)base;
     char *dst = (char *)c->stage;
-    if (nfields == 1 && stride == row[0]) memcpy(dst, src + hoff[0], row[0] * n);
+    const int *rows = c->host_rows;                 // (SEP_NGPU) device atom i lives in host record rows[i]
+    if (!rows && nfields == 1 && stride == row[0]) memcpy(dst, src + hoff[0], row[0] * n);
     else parallel_rows(n, [&](size_t b, size_t e) {
         for (size_t i = b; i < e; i++) {
-            const char *rec = src + i * stride;
+            const char *rec = src + (rows ? (size_t)rows[i] : i) * stride;
             for (int f = 0; f < nfields; f++) memcpy(dst + off[f] + i * row[f], rec + hoff[f], row[f]);
         }
     });
     CUDA_TRY(cudaMemcpyAsync(c->dstage, c->stage, total, cudaMemcpyHostToDevice, c->stream));
     for (int f = 0; f < nfields; f++)
         if ((rc = put_dispatch(c, fields[f], (const char *)c->dstage + off[f], (const char *)c->stage + off[f]))) return rc;
+    return 0;
+}
+
+// Host records are addressed through `rows` from now on (NULL: record i = device atom i).  The array stays the caller's and
+// must hold one entry per owned atom at every later put/get.
+extern "C" int sepgpu_set_host_rows(sepgpu_ctx *c, const int *rows)
+{
+    if (!c) return SEPGPU_EINVAL;
+    c->host_rows = rows;
     return 0;
 }
 
@@ -496,10 +506,11 @@ extern "C" int sepgpu_get_fields(sepgpu_ctx *c, void *base, size_t stride, int n
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     char *dst = (char *)base;
     const char *src = (const char *)c->stage;
-    if (nfields == 1 && stride == row[0]) memcpy(dst + hoff[0], src, row[0] * n);
+    const int *rows = c->host_rows;
+    if (!rows && nfields == 1 && stride == row[0]) memcpy(dst + hoff[0], src, row[0] * n);
     else parallel_rows(n, [&](size_t b, size_t e) {
         for (size_t i = b; i < e; i++) {
-            char *rec = dst + i * stride;
+            char *rec = dst + (rows ? (size_t)rows[i] : i) * stride;
             for (int f = 0; f < nfields; f++) memcpy(rec + hoff[f], src + off[f] + i * row[f], row[f]);
         }
     });

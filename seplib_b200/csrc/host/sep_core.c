@@ -41,6 +41,8 @@ void sep_error(char *str, ...)
     va_end(ap);
     printf("BAILING OUT\n");
     fflush(stdout);
+    if (sepdd_rank() > 0) fprintf(stderr, "sep-error in copy %d of a SEP_NGPU run: %s\n", sepdd_rank(), str);
+    sepdd_mark_failed();
     exit(EXIT_FAILURE);
 }
 
@@ -260,10 +262,12 @@ sep_binding *sepb_prepare(seppart *atoms, sepsys *sys)
         b->npart = (size_t)sys->npart;
     }
     if (!b->gpu) {
-        sepb_check(sepgpu_create(&b->gpu, b->npart, -1), "sepgpu_create");
+        if (sepdd_world() > 1) sepdd_start(b, sys);
+        else sepb_check(sepgpu_create(&b->gpu, b->npart, -1), "sepgpu_create");
         b->host_dirty = ~0u;
         b->dev_dirty = 0;
     }
+    sepdd_guard(b);
     if (sys->molptr) b->molptr = sys->molptr;
     if (sys->molptr && sys->molptr->flag_Fij == 1 && !b->fij_on && sys->molptr->num_mols > 0) {
         sepb_check(sepgpu_fij_enable(b->gpu, (int)sys->molptr->num_mols), "molecular force table");
@@ -282,6 +286,7 @@ sep_binding *sepb_prepare(seppart *atoms, sepsys *sys)
         if (b->dpd_state_on_device) { WANT(SEPB_PV, SEPGPU_F_PV, pv) WANT(SEPB_PA, SEPGPU_F_PA, pa) }
         if (b->x0_on_device) WANT(SEPB_X0, SEPGPU_F_X0, x0)
 #undef WANT
+        if (nf && b->dd) sepdd_before_upload(b);
         if (nf) sepb_check(sepgpu_put_fields(b->gpu, b->atoms, sizeof(seppart), nf, fields, offs), "upload");
     }
     if ((b->host_dirty & SEPB_EXCL) && sys->molptr &&
@@ -314,7 +319,8 @@ void sepb_download(sep_binding *b, unsigned fields)
         PULL(SEPB_XN, SEPGPU_F_XN, xn) PULL(SEPB_CN, SEPGPU_F_CROSS_NEIGHB, cross_neighb) PULL(SEPB_CR, SEPGPU_F_CROSSINGS, crossings)
         PULL(SEPB_PV, SEPGPU_F_PV, pv) PULL(SEPB_PA, SEPGPU_F_PA, pa)
 #undef PULL
-        if (nf) sepb_check(sepgpu_get_fields(b->gpu, b->atoms, sizeof(seppart), nf, fl, offs), "download");
+        if (nf && b->dd) sepdd_download(b, nf, fl, offs);
+        else if (nf) sepb_check(sepgpu_get_fields(b->gpu, b->atoms, sizeof(seppart), nf, fl, offs), "download");
     }
     b->dev_dirty &= ~fields;
 }
@@ -647,6 +653,7 @@ void sep_reset_retval(sepret *r)
 
 void sep_reset_force(seppart *ptr, sepsys *sys)
 {
+    sepdd_allow();
     sep_binding *b = sepb_prepare(ptr, sys);
     sepb_check(sepgpu_reset_force(b->gpu), "sep_reset_force");
     sys->max_dist2 = 0.0;

@@ -85,6 +85,7 @@ int sep_force_pairs(seppart *ptr, const char *types, double cf, double (*fun)(do
         return SEP_FAILURE;
     }
 
+    if (builtin) sepdd_allow();
     sep_binding *b = sepb_prepare(ptr, sys);
     sepgpu_sys gs;
     sepb_fill_sys(sys, &gs);
@@ -110,6 +111,7 @@ void sep_force_lj(seppart *ptr, const char *types, const double *param, sepsys *
     p.cf = cf; p.eps = eps; p.sigma = sigma; p.aw = aw;
     p.shift = 4.0 * eps * (pow(sigma / cf, 12.) - aw * pow(sigma / cf, 6.));
 
+    sepdd_allow();
     sep_binding *b = sepb_prepare(ptr, sys);
     sepgpu_sys gs;
     sepb_fill_sys(sys, &gs);

@@ -5,6 +5,10 @@
 
 #include "sep.h"
 #include "sepgpu.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stddef.h>
 
 /* bits for host_dirty (host newer than device) and dev_dirty (device newer than host) */
 #define SEPB_X      (1u << 0)
@@ -49,6 +53,8 @@ typedef struct sep_binding {
     int managed;                 /* 1: allocated by sep_init in auto mode */
     void *map_base; size_t map_bytes;
     int prot;                    /* current protection of the region (PROT_NONE / PROT_READ / PROT_READ|PROT_WRITE) */
+    int dd;                      /* SEP_NGPU > 1: this process drives one slab of the box (sep_dd.c) */
+    int dd_rows_valid;
     struct sep_binding *next;
 } sep_binding;
 
@@ -74,5 +80,17 @@ int sepb_eager(const sep_binding *b);
 void sepb_dev_newer(sep_binding *b, unsigned bits);
 void sepb_check(int rc, const char *where);
 unsigned long long sep_dpd_seed(void);
+
+/* SEP_NGPU (sep_dd.c) */
+int sepdd_world(void);
+int sepdd_rank(void);
+void sepdd_allow(void);                    /* the next sepb_prepare belongs to a call that runs decomposed */
+void sepdd_guard(const sep_binding *b);
+void sepdd_start(sep_binding *b, sepsys *sys);
+void sepdd_before_upload(sep_binding *b);
+void sepdd_download(sep_binding *b, int nf, const int *fl, const size_t *offs);
+void sepdd_mark_failed(void);
+FILE *sepdd_fopen(const char *path, const char *mode);
+#define fopen(path, mode) sepdd_fopen(path, mode)     /* copies 1..N-1 of a SEP_NGPU run write nothing */
 
 #endif

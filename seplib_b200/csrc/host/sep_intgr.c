@@ -18,6 +18,7 @@ static int alpha_slot(sep_binding *b, double *alpha)
 
 void sep_nosehoover(sepatom *ptr, double temp0, double *alpha, const double tau, sepsys *sys)
 {
+    sepdd_allow();
     sep_binding *b = sepb_prepare(ptr, sys);
     const int slot = alpha_slot(b, alpha);
     if (*alpha != b->alpha_seen[slot]) {                 /* first use, or the caller changed it */
@@ -58,6 +59,7 @@ static void after_integrator(sep_binding *b, sepsys *sys, sepret *ret, int count
 
 void sep_leapfrog(seppart *ptr, sepsys *sys, sepret *retval)
 {
+    sepdd_allow();
     sep_binding *b = sepb_prepare(ptr, sys);
     sepgpu_sys gs;
     sepb_fill_sys(sys, &gs);

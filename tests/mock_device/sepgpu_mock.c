@@ -520,3 +520,19 @@ long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_pairs)
     }
     return c->npairs;
 }
+
+/* SEP_NGPU needs real devices: the mock only satisfies the linker */
+int sepgpu_set_host_rows(sepgpu_ctx *c, const int *rows) { (void)c; return rows ? SEPGPU_ESTATE : 0; }
+int sepgpu_dd_unique_id(void *out128) { (void)out128; set_error("mock device: no decomposition"); return SEPGPU_ESTATE; }
+int sepgpu_dd_init(sepgpu_ctx *c, int rank, int nranks, const void *id128, const sepgpu_sys *sys, long long n_global)
+{
+    (void)c; (void)rank; (void)nranks; (void)id128; (void)sys; (void)n_global;
+    set_error("mock device: no decomposition");
+    return SEPGPU_ESTATE;
+}
+int sepgpu_dd_set_owned(sepgpu_ctx *c, int n_own) { (void)c; (void)n_own; return SEPGPU_ESTATE; }
+int sepgpu_dd_layers(sepgpu_ctx *c, int *z0, int *z1, int *n_own, int *n_halo)
+{
+    (void)c; (void)z0; (void)z1; (void)n_own; (void)n_halo;
+    return SEPGPU_ESTATE;
+}
