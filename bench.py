@@ -512,8 +512,14 @@ def run_molecular(args, emit, local_rank):
     dom_ms = d_ms / max(d_cnt, 1)
     alg_bytes = 4.0 * full_entries / 2.0 + 64.0 + (8.0 if name == "water" else 0.0)     # half-list entries, SURVEY 8d convention
     achieved = alg_bytes * n / (dom_ms * 1e-3) / 1e9
-    roofline = {"kernel": "k_coulomb_list" if name == "water" else "k_lj_list", "bound": "hbm", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+    traffic = None                                   # DRAM bytes per launch of that kernel from the committed ncu capture
+    if name == "water":
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "water_coulomb_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:      # noqa: BLE001
+            traffic = None
+    roofline = {"kernel": "k_coulomb_list2" if name == "water" else "k_lj_list", "bound": "hbm", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_atom_step": alg_bytes, "avg_launch_ms": dom_ms, "launches": d_cnt,
                 "share_of_step": d_ms / (t_sec * 1e3)}
     cpu = None
