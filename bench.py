@@ -134,23 +134,6 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation on the host cores
 # ---------------------------------------------------------------------------------------------------
-def raise_stack_limit():
-    """The reference keeps per-atom scratch in variable-length stack arrays (e.g. the neighbour builder's index[npart],
-    source/sepprfrc.c:428); at 1 M atoms that overflows the default 8 MB stack.  Raise the soft limit of this process (and
-    of the OpenMP workers the reference will start) before its library is loaded."""
-    import resource
-    try:
-        soft, hard = resource.getrlimit(resource.RLIMIT_STACK)
-        want = 1 << 30
-        if hard != resource.RLIM_INFINITY:
-            want = min(want, hard)
-        if soft != resource.RLIM_INFINITY and soft < want:
-            resource.setrlimit(resource.RLIMIT_STACK, (want, hard))
-    except (ValueError, OSError) as e:
-        log("could not raise the stack limit:", e)
-    os.environ.setdefault("OMP_STACKSIZE", "512M")
-
-
 def cpu_reference_arm(ncell, rho, rc, skin, dt, temp, tau, target_seconds, threads):
     """Runs the prg1/prg4-style loop through the reference API (oracle/_ref/libsep_ref_fast.so, built from
     the unmodified reference sources with its shipped flags -Ofast -fopenmp).  Falls back to the C port

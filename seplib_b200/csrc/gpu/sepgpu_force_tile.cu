@@ -286,7 +286,7 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, 
         k_lj_tile<TY, ST, MB, false><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt,   \
             c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);    \
     } while (0)
-#define LJT_LAUNCH(TY, ST) do { if (c->ljt_ctas == 4) LJT_LAUNCH3(TY, ST, 4); else LJT_LAUNCH3(TY, ST, 3); } while (0)
+#define LJT_LAUNCH(TY, ST) LJT_LAUNCH3(TY, ST, 3)        // 3 CTAs per SM (72 registers); 4 spill and were measured slower
     if (typed) { if (store) LJT_LAUNCH(true, true); else LJT_LAUNCH(true, false); }
     else { if (store) LJT_LAUNCH(false, true); else LJT_LAUNCH(false, false); }
 #undef LJT_LAUNCH

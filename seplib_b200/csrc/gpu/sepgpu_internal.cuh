@@ -124,9 +124,7 @@ struct sepgpu_ctx {
     bool sorted_identity;  // brute mode: xs is x4 in original order
     bool need_atom_rows;   // a consumer of global-index rows (list Coulomb, DPD, the molecule-pair table) has been seen
     bool list_f16;         // the list holds rows of 16-bit tile slots (sepgpu_tile.cuh) for the tile force kernels
-    int ljt_ctas;          // option: register budget of k_lj_tile, CTAs per SM (3 or 4)
     int build_window;      // option: x-window sweep in the tiled list builder (default 1)
-    int row_sched;         // option: bank-conflict-aware order of the tile rows (k_row_schedule)
     int tile_list;         // option: build 16-bit tile rows when no consumer needs global-index rows (default 1)
     CellGrid tile_grid;    // grid / tile shape of the current list (every build, both formats)
     int tile_R, tile_count, tile_stage_used, tile_R_max;

@@ -328,50 +328,6 @@ k_build_list(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
 // ---- tiled build: the fast path is k_build_tile (sepgpu_neighb_tile.cuh) ---------------------------------------------
 #include "sepgpu_neighb_tile.cuh"
 
-// ---- bank-conflict-aware row order (option row_sched) ------------------------------------------------------------------
-// The tile force kernel fetches a neighbour with one LDS.128 (x, y: 16-byte columns, 8 per 128-byte row of shared memory)
-// and one LDS.64 (z: 8-byte columns, 16 per row).  With rows in slot order the 32 lanes of a warp hit random columns:
-// measured 8.3 / 4.7 wavefronts per instruction where 4 / 2 would do (ncu, round 2) -- the L1 data pipe, not the FP64
-// pipe, paces the kernel.  Here every row is re-ordered so that entry k of the thread in lane l names a slot of class
-// (l + k) mod 16 whenever the row still has one: the 16 lanes of a half-warp then read 16 different columns in the same
-// step.  Steps whose class has run out take a left-over entry of another class.  The pair set is unchanged; only the
-// order in which a thread visits its neighbours (and with it the rounding of its sums) changes.
-#define SCHED_MAXROW 512
-__global__ void __launch_bounds__(TILE_THREADS)
-k_row_schedule(unsigned short *__restrict__ nbr16, const int *__restrict__ cnt, const int *__restrict__ cell_start,
-               CellGrid G, int R, int npad)
-{
-    const int key0 = blockIdx.x * R * G.bx;
-    const int a0 = cell_start[key0], nhome = cell_start[key0 + R * G.bx] - a0;
-    for (int ab = threadIdx.x; ab < nhome; ab += TILE_THREADS) {
-        const int s = a0 + ab, l = ab & 15;
-        const int m = cnt[s];
-        if (m <= 16 || m > SCHED_MAXROW) continue;
-        unsigned short ent[SCHED_MAXROW], out[SCHED_MAXROW];
-        int n[16], start[17], cur[16];
-        for (int c = 0; c < 16; c++) n[c] = 0;
-        for (int k = 0; k < m; k++) { ent[k] = nbr16[nbr16_index(k, s, npad)]; n[ent[k] & 15]++; }
-        start[0] = 0;
-        for (int c = 0; c < 16; c++) { start[c + 1] = start[c] + n[c]; cur[c] = start[c]; }
-        unsigned short sorted[SCHED_MAXROW];
-        for (int k = 0; k < m; k++) sorted[cur[ent[k] & 15]++] = ent[k];
-        // scheduled steps
-        for (int c = 0; c < 16; c++) cur[c] = start[c];
-        for (int k = 0; k < m; k++) {
-            const int c = (l + k) & 15;
-            if (cur[c] < start[c + 1]) out[k] = sorted[cur[c]++]; else out[k] = 0xffff;     // hole
-        }
-        // left-over entries fill the holes, longest class first so that the tail stays mixed
-        int cc = 0;
-        for (int k = 0; k < m; k++) {
-            if (out[k] != 0xffff) continue;
-            while (cur[cc] >= start[cc + 1]) cc++;
-            out[k] = sorted[cur[cc]++];
-        }
-        for (int k = 0; k < m; k++) nbr16[nbr16_index(k, s, npad)] = out[k];
-    }
-}
-
 __global__ void k_build_begin(DevScalars *s) { s->max_neighb = 0; s->max_half = 0; s->npairs_listed = 0; s->stage_needed = 0; s->stage_used = 0; s->aliased_seen = 0; }
 __global__ void k_build_end(DevScalars *s) { s->nbuild += 1; }
 
@@ -518,8 +474,6 @@ extern "C" int sepgpu_neighb_build(sepgpu_ctx *c, const sepgpu_sys *sys, unsigne
             else if (opt == SEPGPU_EXCL_SAME_MOL) { if (f16) TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, true); else TILE_LAUNCH(SEPGPU_EXCL_SAME_MOL, false); }
             else { if (f16) TILE_LAUNCH(SEPGPU_EXCL_BONDED, true); else TILE_LAUNCH(SEPGPU_EXCL_BONDED, false); }
             built_f16 = f16;
-            if (f16 && c->row_sched)
-                k_row_schedule<<<ntile, TILE_THREADS, 0, c->stream>>>(reinterpret_cast<unsigned short *>(c->nbr), c->cnt, c->cell_start, G, R, c->npad);
 #undef TILE_LAUNCH
 #undef TILE_ARGS
         } else {

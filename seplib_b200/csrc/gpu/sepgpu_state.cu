@@ -717,9 +717,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
     if (!strcmp(name, "step_fold")) { if (!value) { int rs = sepgpu_settle(c); if (rs) return rs; } c->step_fold = value != 0; return 0; }
     if (!strcmp(name, "fin_multi")) { c->fin_multi = value != 0; return 0; }
-    if (!strcmp(name, "ljt_ctas")) { if (value != 3 && value != 4) return SEPGPU_EINVAL; c->ljt_ctas = (int)value; return 0; }
     if (!strcmp(name, "build_window")) { if (value < 0 || value > 2) return SEPGPU_EINVAL; c->build_window = (int)value; return 0; }
-    if (!strcmp(name, "row_sched")) { c->row_sched = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "tile_list")) { c->tile_list = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
     if (!strcmp(name, "typed_sublist")) { c->typed_sublist = value != 0; return 0; }
@@ -753,7 +751,6 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "coulomb_kernel")) *value = c->coulomb_kernel;
     else if (!strcmp(name, "typed_sublist")) *value = c->typed_sublist;
     else if (!strcmp(name, "tile_list")) *value = c->tile_list;
-    else if (!strcmp(name, "row_sched")) *value = c->row_sched;
     else if (!strcmp(name, "build_window")) *value = c->build_window;
     else if (!strcmp(name, "fin_multi")) *value = c->fin_multi;
     else if (!strcmp(name, "step_fold")) *value = c->step_fold;
