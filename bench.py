@@ -9,10 +9,11 @@ on a lattice-initialised Lennard-Jones fluid (prg1-style NVT, SURVEY.md section 
   value     device-resident loop through the sepgpu_* C ABI (inputs already in HBM), CUDA-event timed
   e2e       the same loop through the reference-facing sep_* API with HOST seppart[] buffers; the timed
             region contains the host->device upload, a device->host read of the step's sepret/sepsys
-            scalars EVERY step, and the final download into the host array
+            scalars EVERY step, and the final download into the host array; it runs max(--steps, --e2e-steps)
+            steps (default 1000) so that the one upload and the one download do not dominate a short --steps
   roofline  the pair-force kernel (dominant): algorithmic bytes / CUDA-event time vs measured HBM peak,
-            plus its FP64 rate vs an FMA-chain peak measured on this box (the kernel is bound by neither: the L1
-            data pipe serving the scattered neighbour gathers is)
+            plus its FP64 rate vs an FMA-chain peak measured on this box (the kernel is phase- and latency-limited
+            below both)
   cpu_baseline  the reference's own OpenMP CPU path (oracle/_ref, compiled from its unmodified sources)
             on the box's host cores, bounded sample of the same workload
 
@@ -594,6 +595,7 @@ def main():
     ap.add_argument("--no-cpu-matrix", action="store_true", help="skip the section-8d matrix of smaller CPU samples")
     ap.add_argument("--no-other", action="store_true", help="skip the short C2 (butane) / C3 (water) runs appended as other_workloads")
     ap.add_argument("--equilibrate", type=int, default=300, help="untimed steps from the lattice before the warm-up (thermalisation)")
+    ap.add_argument("--e2e-steps", type=int, default=1000, help="the e2e arm runs max(--steps, this) steps (it carries one upload and one download of atoms[])")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of domain decomposition")
@@ -786,7 +788,9 @@ def main():
     # ---------------- e2e arm: host buffers in, host buffers out ------------------------------------
     e2e = None
     if not args.no_e2e:
-        Ke = max(10, K)                  # the same K steps as the device-resident arm
+        # at least --e2e-steps steps: the array is uploaded once and downloaded once inside this timed region, and a run of
+        # a few dozen steps would time those two transfers (16 ms each at 1 M atoms), not the loop a program spends its time in
+        Ke = max(10, K, args.e2e_steps)
         if not decomposed:
             # the reference-facing sep_* API of include/sep.h on a host seppart[] array, in the library's DEFAULT coherence
             # mode (SEP_SYNC=auto: what an unchanged program gets) -- and, for comparison, in lazy and step mode
