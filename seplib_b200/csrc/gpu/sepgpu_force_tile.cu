@@ -115,6 +115,16 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
     __shared__ double red[SEPGPU_NPART_F * (TILE_THREADS / 32)];
     __shared__ double SHIFT[27 * 3];                                              // -S per image code
 
+    // The first round of staging entries is requested together with the header: they lie inside this tile's stride of
+    // tile_src whatever `total` turns out to be, and the two loads then share one trip to memory instead of two.
+    constexpr int UN = 4, UN2 = 2 * UN;
+    const unsigned *src = tile_src + (size_t)blockIdx.x * stride;
+    unsigned e[UN2];
+#pragma unroll
+    for (int u = 0; u < UN2; u++) {
+        const int q = threadIdx.x + u * TILE_THREADS;
+        e[u] = q < stride ? __ldg(src + q) : 0xffffffffu;
+    }
     const int4 hdr = tile_hdr[blockIdx.x];
     const int a0 = hdr.x, nhome = hdr.y, total = hdr.z;
     const bool image = (hdr.w & 1) != 0;
@@ -140,44 +150,49 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
         }
         __syncthreads();
     }
-    // ---- stage the current coordinates of every candidate of the tile once; four independent loads in flight per
-    // thread, image shift and 1/sigma on the way ----
+    // ---- stage the current coordinates of every candidate of the tile once; eight entries per thread and round, their
+    // coordinates in two groups of four independent loads; image shift and 1/sigma on the way ----
     {
-        const unsigned *src = tile_src + (size_t)blockIdx.x * stride;
-        constexpr int UN = 4;
-        for (int base = threadIdx.x; base < total; base += TILE_THREADS * UN) {
-            unsigned e[UN];
-            d4 p[UN];
+        for (int base = threadIdx.x; base < total; base += TILE_THREADS * UN2) {
+            if (base != (int)threadIdx.x) {
 #pragma unroll
-            for (int u = 0; u < UN; u++) {
-                const int q = base + u * TILE_THREADS;
-                e[u] = q < total ? __ldg(src + q) : 0xffffffffu;
-            }
-#pragma unroll
-            for (int u = 0; u < UN; u++) {
-                if (e[u] == 0xffffffffu) continue;
-                const int j = (int)(e[u] & SEPGPU_INDEX_MASK);
-                int k = -1;
-                if (halo) k = order[j] - H.n_own;                 // >= 0: a halo atom, k-th in arrival order
-                if (k >= 0) {
-                    const double2 *sp = reinterpret_cast<const double2 *>(k < H.n0 ? H.in0 + k : H.in1 + (k - H.n0));
-                    const double2 a = __ldcg(sp), b = __ldcg(sp + 1);       // written by another GPU: never through L1
-                    p[u].x = a.x; p[u].y = a.y; p[u].z = b.x; p[u].w = b.y;
-                } else {
-                    p[u] = xs[j];
+                for (int u = 0; u < UN2; u++) {
+                    const int q = base + u * TILE_THREADS;
+                    e[u] = q < total ? __ldg(src + q) : 0xffffffffu;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < UN; u++) {
-                if (e[u] != 0xffffffffu) {
-                    const int q = base + u * TILE_THREADS;
-                    const int code = (int)(e[u] >> SEPGPU_SHIFT_BITS);
-                    double sx = 0.0, sy = 0.0, sz = 0.0;
-                    if (code != 13) apply_image(code, B, sx, sy, sz);               // s = -S
-                    XY[q] = make_double2((p[u].x - sx) * isig, (p[u].y - sy) * isig);
-                    Z[q] = (p[u].z - sz) * isig;
-                    if (image) CODE[q] = (unsigned char)code;
-                    if (TYPED) TYPE[q] = (unsigned char)tag_type(p[u].w);
+            for (int g = 0; g < 2; g++) {
+                d4 p[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int q = base + (g * UN + u) * TILE_THREADS;
+                    if (q >= total) e[g * UN + u] = 0xffffffffu;
+                    if (e[g * UN + u] == 0xffffffffu) continue;
+                    const int j = (int)(e[g * UN + u] & SEPGPU_INDEX_MASK);
+                    int k = -1;
+                    if (halo) k = order[j] - H.n_own;                 // >= 0: a halo atom, k-th in arrival order
+                    if (k >= 0) {
+                        const double2 *sp = reinterpret_cast<const double2 *>(k < H.n0 ? H.in0 + k : H.in1 + (k - H.n0));
+                        const double2 a = __ldcg(sp), b = __ldcg(sp + 1);       // written by another GPU: never through L1
+                        p[u].x = a.x; p[u].y = a.y; p[u].z = b.x; p[u].w = b.y;
+                    } else {
+                        p[u] = xs[j];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const unsigned ee = e[g * UN + u];
+                    if (ee != 0xffffffffu) {
+                        const int q = base + (g * UN + u) * TILE_THREADS;
+                        const int code = (int)(ee >> SEPGPU_SHIFT_BITS);
+                        double sx = 0.0, sy = 0.0, sz = 0.0;
+                        if (code != 13) apply_image(code, B, sx, sy, sz);               // s = -S
+                        XY[q] = make_double2((p[u].x - sx) * isig, (p[u].y - sy) * isig);
+                        Z[q] = (p[u].z - sz) * isig;
+                        if (image) CODE[q] = (unsigned char)code;
+                        if (TYPED) TYPE[q] = (unsigned char)tag_type(p[u].w);
+                    }
                 }
             }
         }
