@@ -380,6 +380,103 @@ def mol_cpu_arm(name, skin, target_seconds, threads):
                    "seconds": el, "steps": steps, "natoms": n}
 
 
+def run_butane_decomposed(args, emit, local_rank, rank, world, reps):
+    """C2 on N GPUs (weak scaling): the recorded butane cell tiled reps x reps x (reps * N), slabs along z, prg2's force
+    sequence through the C ABI.  Bonded terms are evaluated by every rank that owns one of their atoms, partners read from
+    the halo; the check against the reference's golden vectors is tests/dd_check.py DD_MOL=butane."""
+    import torch
+    import torch.distributed as dist
+    from seplib_b200 import capi
+    from seplib_b200 import workloads as wl
+    P = wl.BUTANE
+    K, W = args.steps, max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = wl.tiled_molecular("butane_n4000.npz", (reps, reps, reps * world))
+    n_total = w["n"]
+    gsys = capi.make_sys(w["L"], P["cf"], P["dt"], skin=args.skin)
+    gs = C.byref(gsys)
+    nz = gsys.nsubbox[2]
+    z0, z1 = capi.dd_slab_range(rank, world, nz)
+    cz = np.clip(np.floor(w["x"][:, 2] / gsys.lsubbox[2]).astype(np.int64), 0, nz - 1)
+    mine = np.nonzero((cz >= z0) & (cz < z1))[0].astype(np.int32)
+    n = len(mine)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(capi.dd_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    s = capi.System(int(1.25 * n_total / world) + int(3.5 * n_total / nz) + 4096, device=local_rank)
+    s.dd_init(rank, world, bytes(idt.cpu().numpy().tobytes()), gsys, n_total)
+    s.dd_set_owned(n)
+    s.put(capi.F_X, w["x"][mine]); s.put(capi.F_V, w["v"][mine]); s.put(capi.F_GID, mine)
+    s.put(capi.F_TYPE, np.ascontiguousarray(w["type"][mine])); s.put(capi.F_M, np.ascontiguousarray(w["m"][mine]))
+    s.put(capi.F_MOLINDEX, np.ascontiguousarray(w["molindex"][mine]))
+    s.set_topology(w["blist"], w["alist"], w["dlist"])
+    s.call("sepgpu_set_alpha", 0, 0.1)
+    ljp = capi.lj_param(P["cf"], kind="lj_shift")
+    ljr = C.byref(ljp)
+    rb = (C.c_double * 6)(*P["rb"])
+    ctx, fn = s.ctx, s.lib
+
+    def step():
+        fn.sepgpu_reset_ret(ctx)
+        fn.sepgpu_reset_force(ctx)
+        r = fn.sepgpu_force_lj(ctx, gs, P["types"], ljr, 3, 1)
+        r |= fn.sepgpu_stretch_harmonic(ctx, gs, 0, P["lbond"], P["kbond"])
+        r |= fn.sepgpu_angle_harmonic(ctx, gs, 0, P["angle"], P["kangle"])
+        r |= fn.sepgpu_torsion_ryckaert(ctx, gs, 0, rb)
+        r |= fn.sepgpu_nosehoover(ctx, gs, P["temp"], 0, P["tau"])
+        r |= fn.sepgpu_leapfrog(ctx, gs)
+        if r:
+            raise RuntimeError("device step failed: " + fn.sepgpu_last_error().decode())
+
+    for _ in range(W):
+        step()
+    nb0 = s.scalars().nbuild
+    s.call("sepgpu_set_option", b"time_kernels", 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    dist.barrier(); torch.cuda.synchronize()
+    t_wall0 = time.time()
+    s.call("sepgpu_timer_start")
+    for _ in range(K):
+        step()
+    ms = C.c_float()
+    s.call("sepgpu_timer_stop", C.byref(ms))
+    dist.barrier(); torch.cuda.synchronize()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    t = torch.tensor([ms.value], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_sec = float(t.item()) * 1e-3
+    sc = s.scalars()
+    kt = {}
+    for which in ("force", "bonded", "build", "intgr", "halo", "migrate"):
+        tot, cnt = C.c_float(), C.c_int()
+        s.call("sepgpu_kernel_time", which.encode(), C.byref(tot), C.byref(cnt))
+        kt[which] = (tot.value, cnt.value)
+    own, halo = s.dd_layers()[2:]
+    s.close()
+    if rank == 0:
+        emit({"metric": METRIC.replace("LJ, rc=2.5", "C2 butane"), "value": n_total * K / t_sec, "unit": UNIT, "n_gpus": world,
+              "steps": K, "warmup": W, "ms_per_step": t_sec * 1e3 / K, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": {"workload": "C2 butane, %d-way slab decomposition: sep_force_pairs(CC, lj_shift, EXCL_SAME_MOL) + stretch + angle + "
+                                     "Ryckaert torsion + NH + leapfrog" % world,
+                         "natoms_total": n_total, "natoms_per_gpu": n_total // world, "tiling": "%d x %d x %d unit cells" % (reps, reps, reps * world),
+                         "box": list(map(float, w["L"])), "cells": list(gsys.nsubbox[:]), "skin": args.skin, "dt": P["dt"],
+                         "parallelism": "%d-way slab domain decomposition along z, bonded partners from the halo" % world,
+                         "rank0_owned_halo_atoms": [own, halo], "list_rebuilds_in_timed_region": sc.nbuild - nb0,
+                         "epot_per_atom": sc.epot / n_total, "ekin_per_atom": sc.ekin / n_total,
+                         "l2": "inputs larger than L2"},
+              "roofline": None, "cpu_baseline": None, "e2e": None, "gpu_launches": K * 13 + (sc.nbuild - nb0) * 20, "clocks": clocks,
+              "kernel_ms": {k: {"total_ms": a, "launches": b} for k, (a, b) in kt.items()}})
+    dist.barrier()
+    return 0
+
+
 def run_molecular(args, emit, local_rank):
     import torch
     from seplib_b200 import capi
@@ -392,6 +489,12 @@ def run_molecular(args, emit, local_rank):
     lib = capi.load()
     if lib.sepgpu_device_count() <= 0:
         raise RuntimeError("bench.py: no CUDA device -- seplib-b200 has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        if name != "butane":
+            raise RuntimeError("bench.py: decomposed molecular runs shard the butane sequence (bonded terms); water needs Coulomb")
+        return run_butane_decomposed(args, emit, local_rank, rank, world, reps)
     w = wl.butane(reps) if name == "butane" else wl.water(reps)
     n = w["n"]
     gsys = capi.make_sys(w["L"], P["cf"], P["dt"], skin=args.skin)
@@ -622,7 +725,7 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     if args.workload != "lj":
-        if rank != 0:
+        if rank != 0 and not (args.workload == "butane" and args.gpus > 1 and args.impl != "reference"):
             return 0
         if args.impl == "reference":
             info = cpu_arm_child("mol", name=args.workload, skin=args.skin, target_seconds=max(args.cpu_seconds, 5.0) * 2, threads=host_cores())

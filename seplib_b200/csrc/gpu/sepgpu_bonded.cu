@@ -14,10 +14,34 @@
 #include <stdlib.h>
 #include <math.h>
 
+int sepgpu_dd_nglobal(sepgpu_ctx *c);
+int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
+int sepgpu_dd_gmap(sepgpu_ctx *c, const int **gmap);
+
 #define BONDED_BLOCK 128
 #define SEPGPU_PI 3.14159265358979      // SEP_PI, include/sepdef.h:40
 
 struct BoxB { double Lx, Ly, Lz; };
+
+// Slab-decomposed runs (sepgpu_dd.cu): the topology lists and the inverse topology are indexed by GLOBAL atom ids, the
+// per-atom arrays by local rows.  A thread owns one of the rank's own rows; partners are found through the global-id ->
+// row map of the last rebuild and may be halo atoms, whose current coordinates sit in the halo slots of the sorted copy
+// xs (continuous coordinates: the wrap of the separation below absorbs the box shifts they may carry).  Every term is
+// evaluated by each rank that owns one of its atoms, for that atom only; energy and virial by the owner of its first atom
+// (SURVEY.md section 8e).  on == 0: single domain, everything is indexed by atom.
+struct BondedDD {
+    const int *gid, *gmap, *rank;
+    const d4 *xs;
+    int n_own, on;
+};
+
+__device__ __forceinline__ d4 atom_pos(const d4 *__restrict__ x4, const BondedDD &D, unsigned a, int *missing)
+{
+    if (!D.on) return x4[a];
+    const int row = D.gmap[a];
+    if (row < 0) { *missing = 1; return x4[0]; }
+    return row < D.n_own ? x4[row] : D.xs[D.rank[row]];
+}
 
 __device__ __forceinline__ void diff_wrap(const d4 &a, const d4 &b, const BoxB &B, double r[3])
 {
@@ -34,15 +58,17 @@ __device__ __forceinline__ double dot3(const double a[3], const double b[3])
 __global__ void __launch_bounds__(BONDED_BLOCK)
 k_bond(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned *__restrict__ blist,
        const int *__restrict__ aptr, const int *__restrict__ aidx, int type, double lbond, double ks,
-       BoxB B, int f_zero, double *__restrict__ blengths, double *__restrict__ partial)
+       BoxB B, int f_zero, double *__restrict__ blengths, double *__restrict__ partial, BondedDD D, DevScalars *scal)
 {
     __shared__ double red[SEPGPU_NPART_F * (BONDED_BLOCK / 32)];
     double acc[SEPGPU_NPART_F];
 #pragma unroll
     for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
     const int i = blockIdx.x * BONDED_BLOCK + threadIdx.x;
+    int missing = 0;
     if (i < n) {
-        const int b0 = aptr[i], b1 = aptr[i + 1];
+        const int ig = D.on ? D.gid[i] : i;                      // the atom's index in the topology
+        const int b0 = aptr[ig], b1 = aptr[ig + 1];
         if (b1 > b0 || f_zero) {
             d4 f;
             if (f_zero) { f.x = f.y = f.z = f.w = 0.0; } else f = f4[i];
@@ -51,7 +77,7 @@ k_bond(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned *__
                 if ((int)blist[3 * term + 2] != type) continue;
                 const unsigned a = blist[3 * term], b = blist[3 * term + 1];
                 double r[3];
-                diff_wrap(x4[a], x4[b], B, r);
+                diff_wrap(atom_pos(x4, D, a, &missing), atom_pos(x4, D, b, &missing), B, r);
                 const double r2 = dot3(r, r);
                 const double dist = sqrt(r2);
                 const double ft = -ks * (dist - lbond) / dist;            // source/sepmol.c:394
@@ -69,6 +95,7 @@ k_bond(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned *__
             f4[i] = f;
         }
     }
+    if (missing) scal->error = SEPGPU_ECELL;                       // a bonded partner is neither mine nor in my halo
     block_sum<SEPGPU_NPART_F, BONDED_BLOCK>(acc, red);
     if (threadIdx.x == 0)
         for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
@@ -79,15 +106,17 @@ template <bool COSSQ>
 __global__ void __launch_bounds__(BONDED_BLOCK)
 k_angle(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned *__restrict__ alist,
         const int *__restrict__ aptr, const int *__restrict__ aidx, int type, double angle0, double kc,
-        double cCon, BoxB B, int f_zero, double *__restrict__ angles, double *__restrict__ partial)
+        double cCon, BoxB B, int f_zero, double *__restrict__ angles, double *__restrict__ partial, BondedDD D, DevScalars *scal)
 {
     __shared__ double red[SEPGPU_NPART_F * (BONDED_BLOCK / 32)];
     double acc[SEPGPU_NPART_F];
 #pragma unroll
     for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
     const int i = blockIdx.x * BONDED_BLOCK + threadIdx.x;
+    int missing = 0;
     if (i < n) {
-        const int b0 = aptr[i], b1 = aptr[i + 1];
+        const int ig = D.on ? D.gid[i] : i;                      // the atom's index in the topology
+        const int b0 = aptr[ig], b1 = aptr[ig + 1];
         if (b1 > b0 || f_zero) {
             d4 f;
             if (f_zero) { f.x = f.y = f.z = f.w = 0.0; } else f = f4[i];
@@ -96,9 +125,9 @@ k_angle(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned *_
                 if ((int)alist[4 * term + 3] != type) continue;
                 const unsigned a = alist[4 * term], b = alist[4 * term + 1], c = alist[4 * term + 2];
                 double d1[3], d2[3];
-                const d4 xb = x4[b];
-                diff_wrap(xb, x4[a], B, d1);                               // dr1 = x_b - x_a
-                diff_wrap(x4[c], xb, B, d2);                               // dr2 = x_c - x_b
+                const d4 xb = atom_pos(x4, D, b, &missing);
+                diff_wrap(xb, atom_pos(x4, D, a, &missing), B, d1);        // dr1 = x_b - x_a
+                diff_wrap(atom_pos(x4, D, c, &missing), xb, B, d2);        // dr2 = x_c - x_b
                 const double c11 = dot3(d1, d1), c12 = dot3(d1, d2), c22 = dot3(d2, d2);
                 const double cD = sqrt(c11 * c22);
                 double fm, en, ang;
@@ -125,6 +154,7 @@ k_angle(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned *_
             f4[i] = f;
         }
     }
+    if (missing) scal->error = SEPGPU_ECELL;                       // a bonded partner is neither mine nor in my halo
     block_sum<SEPGPU_NPART_F, BONDED_BLOCK>(acc, red);
     if (threadIdx.x == 0)
         for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
@@ -136,7 +166,7 @@ struct RBCoef { double g[6]; };
 __global__ void __launch_bounds__(BONDED_BLOCK)
 k_torsion(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned *__restrict__ dlist,
           const int *__restrict__ aptr, const int *__restrict__ aidx, int type, RBCoef G, BoxB B,
-          int f_zero, double *__restrict__ dihedrals, double *__restrict__ partial)
+          int f_zero, double *__restrict__ dihedrals, double *__restrict__ partial, BondedDD D, DevScalars *scal)
 {
     __shared__ double red[SEPGPU_NPART_F * (BONDED_BLOCK / 32)];
     double acc[SEPGPU_NPART_F];
@@ -144,8 +174,10 @@ k_torsion(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned 
     for (int q = 0; q < SEPGPU_NPART_F; q++) acc[q] = 0.0;
     const double *g = G.g;
     const int i = blockIdx.x * BONDED_BLOCK + threadIdx.x;
+    int missing = 0;
     if (i < n) {
-        const int b0 = aptr[i], b1 = aptr[i + 1];
+        const int ig = D.on ? D.gid[i] : i;                      // the atom's index in the topology
+        const int b0 = aptr[ig], b1 = aptr[ig + 1];
         if (b1 > b0 || f_zero) {
             d4 f;
             if (f_zero) { f.x = f.y = f.z = f.w = 0.0; } else f = f4[i];
@@ -154,10 +186,10 @@ k_torsion(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned 
                 if ((int)dlist[5 * term + 4] != type) continue;
                 const unsigned a = dlist[5 * term], b = dlist[5 * term + 1], c = dlist[5 * term + 2], d = dlist[5 * term + 3];
                 double d1[3], d2[3], d3[3];
-                const d4 xb = x4[b], xc = x4[c];
-                diff_wrap(xb, x4[a], B, d1);
+                const d4 xb = atom_pos(x4, D, b, &missing), xc = atom_pos(x4, D, c, &missing);
+                diff_wrap(xb, atom_pos(x4, D, a, &missing), B, d1);
                 diff_wrap(xc, xb, B, d2);
-                diff_wrap(x4[d], xc, B, d3);
+                diff_wrap(atom_pos(x4, D, d, &missing), xc, B, d3);
                 const double c11 = dot3(d1, d1), c12 = dot3(d1, d2), c13 = dot3(d1, d3);
                 const double c22 = dot3(d2, d2), c23 = dot3(d2, d3), c33 = dot3(d3, d3);
                 const double cA = c13 * c22 - c12 * c23;                   // source/sepmol.c:555-559
@@ -188,6 +220,7 @@ k_torsion(const d4 *__restrict__ x4, d4 *__restrict__ f4, int n, const unsigned 
             f4[i] = f;
         }
     }
+    if (missing) scal->error = SEPGPU_ECELL;                       // a bonded partner is neither mine nor in my halo
     block_sum<SEPGPU_NPART_F, BONDED_BLOCK>(acc, red);
     if (threadIdx.x == 0)
         for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = acc[q];
@@ -242,9 +275,10 @@ extern "C" int sepgpu_set_topology(sepgpu_ctx *c, const unsigned *blist, unsigne
     if ((rc = upload((void **)&c->blist, blist, sizeof(unsigned) * 3 * (size_t)nb))) return rc;
     if ((rc = upload((void **)&c->alist, alist, sizeof(unsigned) * 4 * (size_t)na))) return rc;
     if ((rc = upload((void **)&c->dlist, dlist, sizeof(unsigned) * 5 * (size_t)nd))) return rc;
-    if ((rc = build_inverse(c->n, blist, nb, 3, 2, &c->atom_bond_ptr, &c->atom_bond_idx))) return rc;
-    if ((rc = build_inverse(c->n, alist, na, 4, 3, &c->atom_angle_ptr, &c->atom_angle_idx))) return rc;
-    if ((rc = build_inverse(c->n, dlist, nd, 5, 4, &c->atom_dihed_ptr, &c->atom_dihed_idx))) return rc;
+    const int natoms = c->dd ? sepgpu_dd_nglobal(c) : c->n;        // decomposed: lists and inverse topology by global id
+    if ((rc = build_inverse(natoms, blist, nb, 3, 2, &c->atom_bond_ptr, &c->atom_bond_idx))) return rc;
+    if ((rc = build_inverse(natoms, alist, na, 4, 3, &c->atom_angle_ptr, &c->atom_angle_idx))) return rc;
+    if ((rc = build_inverse(natoms, dlist, nd, 5, 4, &c->atom_dihed_ptr, &c->atom_dihed_idx))) return rc;
     if (c->blengths) cudaFree(c->blengths);
     if (c->angles) cudaFree(c->angles);
     if (c->dihedrals) cudaFree(c->dihedrals);
@@ -261,6 +295,7 @@ extern "C" int sepgpu_set_topology(sepgpu_ctx *c, const unsigned *blist, unsigne
 extern "C" int sepgpu_get_bonded_values(sepgpu_ctx *c, double *blengths, double *angles, double *dihedrals)
 {
     if (!c) return SEPGPU_EINVAL;
+    if (c->dd) { sepgpu_set_error("get_bonded_values: per-term values stay on the rank that owns the term's first atom in decomposed runs"); return SEPGPU_ESTATE; }
     SEPGPU_ENTER(c);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (blengths && c->nb) CUDA_TRY(cudaMemcpy(blengths, c->blengths, sizeof(double) * c->nb, cudaMemcpyDeviceToHost));
@@ -270,6 +305,21 @@ extern "C" int sepgpu_get_bonded_values(sepgpu_ctx *c, double *blengths, double 
 }
 
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags);
+
+// what the bonded kernels need to know about a decomposed run; also brings the halo coordinates of this step into xs
+static int bonded_view(sepgpu_ctx *c, const sepgpu_sys *sys, BondedDD *D, int *nrows)
+{
+    memset(D, 0, sizeof *D);
+    *nrows = c->n;
+    if (!c->dd) return 0;
+    int rc = sepgpu_dd_halo_update(c, sys);
+    if (rc) return rc;
+    const int *gmap = NULL;
+    if ((rc = sepgpu_dd_gmap(c, &gmap))) return rc;
+    D->gid = c->gid; D->gmap = gmap; D->rank = c->rank; D->xs = c->xs; D->n_own = c->n_own; D->on = 1;
+    *nrows = c->n_own;
+    return 0;
+}
 
 static BoxB make_box(const sepgpu_sys *sys)
 {
@@ -282,10 +332,12 @@ extern "C" int sepgpu_stretch_harmonic(sepgpu_ctx *c, const sepgpu_sys *sys, int
     if (!c || !sys) return SEPGPU_EINVAL;
     if (!c->atom_bond_ptr) { sepgpu_set_error("stretch_harmonic: no topology on the device"); return SEPGPU_ESTATE; }
     SEPGPU_ENTER(c);
-    const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
+    BondedDD D; int nrows;
+    { const int rcv = bonded_view(c, sys, &D, &nrows); if (rcv) return rcv; }
+    const int grid = (nrows + BONDED_BLOCK - 1) / BONDED_BLOCK;
     ktimer_begin(c, &c->t_bonded);
-    k_bond<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->blist, c->atom_bond_ptr, c->atom_bond_idx,
-                                                 type, lbond, ks, make_box(sys), c->f_zero ? 1 : 0, c->blengths, c->partial);
+    k_bond<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, nrows, c->blist, c->atom_bond_ptr, c->atom_bond_idx,
+                                                 type, lbond, ks, make_box(sys), c->f_zero ? 1 : 0, c->blengths, c->partial, D, c->scal);
     ktimer_end(c, &c->t_bonded);
     KERNEL_CHECK();
     c->f_zero = false;
@@ -297,15 +349,17 @@ static int run_angle(sepgpu_ctx *c, const sepgpu_sys *sys, int type, double angl
     if (!c || !sys) return SEPGPU_EINVAL;
     if (!c->atom_angle_ptr) { sepgpu_set_error("angle force: no topology on the device"); return SEPGPU_ESTATE; }
     SEPGPU_ENTER(c);
-    const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
+    BondedDD D; int nrows;
+    { const int rcv = bonded_view(c, sys, &D, &nrows); if (rcv) return rcv; }
+    const int grid = (nrows + BONDED_BLOCK - 1) / BONDED_BLOCK;
     const double cCon = cos(SEPGPU_PI - angle0);        // host libm, as the reference (source/sepmol.c:422)
     ktimer_begin(c, &c->t_bonded);
     if (cossq)
-        k_angle<true><<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->alist, c->atom_angle_ptr, c->atom_angle_idx,
-                                                            type, angle0, k, cCon, make_box(sys), c->f_zero ? 1 : 0, c->angles, c->partial);
+        k_angle<true><<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, nrows, c->alist, c->atom_angle_ptr, c->atom_angle_idx,
+                                                            type, angle0, k, cCon, make_box(sys), c->f_zero ? 1 : 0, c->angles, c->partial, D, c->scal);
     else
-        k_angle<false><<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->alist, c->atom_angle_ptr, c->atom_angle_idx,
-                                                             type, angle0, k, cCon, make_box(sys), c->f_zero ? 1 : 0, c->angles, c->partial);
+        k_angle<false><<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, nrows, c->alist, c->atom_angle_ptr, c->atom_angle_idx,
+                                                             type, angle0, k, cCon, make_box(sys), c->f_zero ? 1 : 0, c->angles, c->partial, D, c->scal);
     ktimer_end(c, &c->t_bonded);
     KERNEL_CHECK();
     c->f_zero = false;
@@ -327,11 +381,13 @@ extern "C" int sepgpu_torsion_ryckaert(sepgpu_ctx *c, const sepgpu_sys *sys, int
     if (!c || !sys || !g) return SEPGPU_EINVAL;
     if (!c->atom_dihed_ptr) { sepgpu_set_error("torsion force: no topology on the device"); return SEPGPU_ESTATE; }
     SEPGPU_ENTER(c);
-    const int grid = (c->n + BONDED_BLOCK - 1) / BONDED_BLOCK;
+    BondedDD D; int nrows;
+    { const int rcv = bonded_view(c, sys, &D, &nrows); if (rcv) return rcv; }
+    const int grid = (nrows + BONDED_BLOCK - 1) / BONDED_BLOCK;
     RBCoef G; for (int k = 0; k < 6; k++) G.g[k] = g[k];
     ktimer_begin(c, &c->t_bonded);
-    k_torsion<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, c->n, c->dlist, c->atom_dihed_ptr, c->atom_dihed_idx,
-                                                    type, G, make_box(sys), c->f_zero ? 1 : 0, c->dihedrals, c->partial);
+    k_torsion<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f4, nrows, c->dlist, c->atom_dihed_ptr, c->atom_dihed_idx,
+                                                    type, G, make_box(sys), c->f_zero ? 1 : 0, c->dihedrals, c->partial, D, c->scal);
     ktimer_end(c, &c->t_bonded);
     KERNEL_CHECK();
     c->f_zero = false;

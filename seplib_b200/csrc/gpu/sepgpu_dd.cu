@@ -113,6 +113,9 @@ struct DDState {
     unsigned char **bases_dev;
     size_t gather_off, gflag_off;
     unsigned long long gseq;
+    // bonded terms: global id -> local row of the last rebuild
+    int *gmap;
+    int gmap_gen;
 };
 
 extern "C" int sepgpu_dd_unique_id(void *out128)
@@ -305,6 +308,7 @@ void sepgpu_dd_destroy(sepgpu_ctx *c)
     if (d->bases_dev) cudaFree(d->bases_dev);
     if (d->ipc_base) cudaFree(d->ipc_base);
     if (d->done_ctr) cudaFree(d->done_ctr);
+    if (d->gmap) cudaFree(d->gmap);
     if (d->ev_ready) cudaEventDestroy(d->ev_ready);
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     if (d->comm) g_nccl.CommDestroy(d->comm);
@@ -331,6 +335,36 @@ bool sepgpu_dd_gather_next(sepgpu_ctx *c, GatherDev *g)
     return true;
 }
 int sepgpu_dd_uses_p2p(sepgpu_ctx *c) { return c->dd && c->dd->p2p ? 1 : 0; }
+int sepgpu_dd_nglobal(sepgpu_ctx *c) { return c->dd ? (int)c->n_global : c->n; }
+
+// ---- global id -> local row (own and halo), for the bonded terms: rebuilt lazily after every list build -------------
+__global__ void k_dd_gmap_fill(int *gmap, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) gmap[i] = -1; }
+__global__ void k_dd_gmap_scatter(const int *__restrict__ gid, int first, int last, int *gmap)
+{
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < last) gmap[gid[i]] = i;
+}
+
+int sepgpu_dd_gmap(sepgpu_ctx *c, const int **gmap)
+{
+    DDState *d = c->dd;
+    const int ng = (int)c->n_global;
+    if (!d->gmap) { if (dmalloc(&d->gmap, (size_t)ng)) return SEPGPU_ECUDA; d->gmap_gen = -1; }
+    if (d->gmap_gen != c->list_gen) {
+        // an atom can be own AND halo only in a slab that is its own neighbour through the periodic boundary (never with
+        // >= 2 ranks); own rows are written last so that they win
+        k_dd_gmap_fill<<<(ng + 255) / 256, 256, 0, c->stream>>>(d->gmap, ng);
+        if (c->n > c->n_own)
+            k_dd_gmap_scatter<<<(c->n - c->n_own + 255) / 256, 256, 0, c->stream>>>(c->gid, c->n_own, c->n, d->gmap);
+        if (c->n_own)
+            k_dd_gmap_scatter<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->gid, 0, c->n_own, d->gmap);
+        KERNEL_CHECK();
+        d->gmap_gen = c->list_gen;
+    }
+    *gmap = d->gmap;
+    return 0;
+}
+
 void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks) { *rank = c->dd->rank; *nranks = c->dd->nranks; }
 
 int sepgpu_dd_allreduce(sepgpu_ctx *c, double *sum_buf, int nsum, double *max_buf, int nmax)

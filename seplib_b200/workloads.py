@@ -62,7 +62,8 @@ def _tile_terms(lst, reps3, n0, natoms_cols):
 
 
 def tiled_molecular(fixture, reps):
-    """Tile a recorded molecular unit cell reps^3 times.  Returns a dict of numpy arrays."""
+    """Tile a recorded molecular unit cell reps^3 times (or rx x ry x rz for a tuple).  Returns a dict of numpy arrays."""
+    rx, ry, rz = (reps, reps, reps) if np.isscalar(reps) else reps
     g = np.load(os.path.join(GOLDEN, fixture))
     L0 = np.atleast_1d(g["L"]).astype(float)
     if L0.size == 1:
@@ -80,13 +81,13 @@ def tiled_molecular(fixture, reps):
         if same[i]:
             d = x0[i] - x0[i - 1]
             x0[i] = x0[i - 1] + (d - L0 * np.round(d / L0))
-    reps3 = reps ** 3
+    reps3 = rx * ry * rz
     x = np.empty((reps3 * n0, 3)); v = np.empty((reps3 * n0, 3))
     mol = np.empty(reps3 * n0, dtype=np.int32)
     k = 0
-    for iz in range(reps):
-        for iy in range(reps):
-            for ix in range(reps):
+    for iz in range(rz):
+        for iy in range(ry):
+            for ix in range(rx):
                 x[k * n0:(k + 1) * n0] = x0 + np.array([ix, iy, iz]) * L0
                 v[k * n0:(k + 1) * n0] = v0
                 mol[k * n0:(k + 1) * n0] = g["molindex"] + k * nmol0
@@ -96,7 +97,7 @@ def tiled_molecular(fixture, reps):
         a = g[key] if key in g.files else np.full(n0, default)
         return np.ascontiguousarray(np.tile(a, reps3), dtype=dtype)
 
-    Lbig = L0 * reps
+    Lbig = L0 * np.array([rx, ry, rz])
     x -= Lbig * np.floor(x / Lbig)                  # back into [0, L)
     x[x >= Lbig] = 0.0                              # guard the rounding case x == L
     out = dict(x=np.ascontiguousarray(x), v=np.ascontiguousarray(v), L=Lbig, n=reps3 * n0, nmol=reps3 * nmol0,

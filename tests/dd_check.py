@@ -33,9 +33,39 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if os.environ.get("DD_MOL") == "butane":
+        ok = run_butane(rank, world, local, int(os.environ.get("DD_STEPS", "60")))
+        dist.destroy_process_group()
+        return 0 if ok else 1
     res = run(rank, world, local, NSTEPS, NCELL)
     dist.destroy_process_group()
     return 0 if res["ok"] else 1
+
+
+def run_butane(rank, world, local, nsteps):
+    """Bonded terms in a decomposed run (tests/dd_mol.py): the reference's evolved butane cell over `world` slabs against the
+    reference's golden vectors and a single-GPU run on rank 0.  Collective."""
+    import dd_mol
+    g = dd_mol.golden()
+    gsys = capi.make_sys(list(g["L"]), float(g["cf"]), float(g["dt"]), skin=0.25)
+    n = len(g["x0"])
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(capi.dd_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    s = capi.System(int(1.6 * n / world) + int(3.0 * n / gsys.nsubbox[2]) + 1024, device=local)
+    res = dd_mol.rank_run(s, g, gsys, rank, world, bytes(idt.cpu().numpy().tobytes()), nsteps)
+    dist.barrier()
+    s.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    ok = True
+    if rank == 0:
+        rec, x = dd_mol.single_run(g, gsys, nsteps, device=local)
+        ok = dd_mol.check(g, gathered, rec, x, log=lambda m: print(m, file=sys.stderr, flush=True))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
 
 
 def run(rank, world, local, nsteps, ncell, verbose=True):

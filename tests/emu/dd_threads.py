@@ -29,7 +29,44 @@ import common as cm  # noqa: E402
 WORLD = int(os.environ.get("DD_WORLD", "2"))
 
 
+def main_butane():
+    """python tests/emu/dd_threads.py butane [nsteps]: bonded terms in a decomposed run (tests/dd_mol.py)"""
+    import dd_mol
+    nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+    g = dd_mol.golden()
+    gsys = capi.make_sys(list(g["L"]), float(g["cf"]), float(g["dt"]), skin=0.25)
+    n = len(g["x0"])
+    id_bytes = capi.dd_unique_id()
+    barrier = threading.Barrier(WORLD)
+    results, errs = [None] * WORLD, []
+
+    def rank_main(rank):
+        try:
+            s = capi.System(int(1.6 * n / WORLD) + int(3.0 * n / gsys.nsubbox[2]) + 1024, device=0)
+            results[rank] = dd_mol.rank_run(s, g, gsys, rank, WORLD, id_bytes, nsteps)
+            barrier.wait()
+            s.close()
+        except BaseException as e:                              # noqa: BLE001 -- reported by the main thread
+            import traceback
+            sys.stderr.write("rank %d: %s\n" % (rank, traceback.format_exc())); sys.stderr.flush()
+            errs.append((rank, repr(e)))
+            barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(WORLD)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        print("rank failure:", errs)
+        return 1
+    rec, x = dd_mol.single_run(g, gsys, nsteps)
+    return 0 if dd_mol.check(g, results, rec, x) else 1
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "butane":
+        return main_butane()
     ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 24
     opts = dict(kv.split("=") for kv in sys.argv[3].split(",")) if len(sys.argv) > 3 and sys.argv[3] else {}

@@ -61,6 +61,12 @@ def test_two_rank_decomposition_on_the_emulator():
                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
                                  env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc, DD_WORLD=world))
              for k, (opts, no_ipc, world, ncell) in cases.items()}
+    # bonded terms in decomposed runs (tests/dd_mol.py): the reference's butane cell on two slabs against its golden vectors
+    # and a single-domain run, on both transports
+    for k, no_ipc in (("butane-peer-memory", "0"), ("butane-nccl-path", "1")):
+        procs[k] = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "butane", "24"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
+                                    env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc, DD_WORLD="2"))
     for k, p in procs.items():
         out, err = p.communicate(timeout=900)
         assert p.returncode == 0 and "-> OK" in out, (k, out[-2000:], err[-2000:])

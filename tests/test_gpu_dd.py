@@ -30,6 +30,19 @@ def test_two_rank_decomposition_matches_oracle(ncell):
     assert r.returncode == 0 and "-> OK" in (r.stdout + r.stderr), (r.stdout[-2000:], r.stderr[-2000:])
 
 
+def test_two_rank_butane_matches_the_reference_golden():
+    """Bonded terms in a decomposed run: the reference's evolved 4000-atom butane cell on two slabs -- forces after each of
+    prg2's four force routines against the reference's recorded vectors (1e-10), the step's positions / velocities /
+    thermostat, then 60 steps (several rebuilds with migration) against a single-GPU run (tests/dd_mol.py)."""
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    env = dict(os.environ, DD_MOL="butane", DD_STEPS="60")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", os.path.join(cm.ROOT, "tests", "dd_check.py")],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "-> OK" in (r.stdout + r.stderr), (r.stdout[-2000:], r.stderr[-2000:])
+
+
 def _build_prog(tmp_path, name):
     """our own test program (tests/progs/), compiled against include/sep.h and libsep.so"""
     exe = os.path.join(str(tmp_path), name)
