@@ -29,6 +29,14 @@
  *   full            like step, plus forces are written back after every force call.
  * In step / lazy / full mode, writing into atoms[] from user code between hot calls needs sep_gpu_invalidate(atoms);
  * in auto mode the library notices by itself.
+ *
+ * Pair functions: sep_force_pairs recognises sep_lj, sep_lj_shift and sep_wca by address; any other
+ * double fun(double r2, char opt) is sampled once per (function, cutoff) and interpolated on the device
+ * (env SEP_TABLE_N, SEP_TABLE_RMIN; sep_pairs_retabulate()).
+ *
+ * Several GPUs: env SEP_NGPU=N runs the unchanged program on N GPUs of the node -- the library forks one copy per GPU at
+ * the first hot call and decomposes the box into slabs along z (INTEGRATION.md section 5 lists what the program must
+ * satisfy).
  */
 #ifndef SEP_B200_SEP_H
 #define SEP_B200_SEP_H
