@@ -118,14 +118,18 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
     // The first round of staging entries is requested together with the header: they lie inside this tile's stride of
     // tile_src whatever `total` turns out to be, and the two loads then share one trip to memory instead of two.
     constexpr int UN = 4, UN2 = 2 * UN;
-    const unsigned *src = tile_src + (size_t)blockIdx.x * stride;
+    // decomposed runs start one brick layer up, so that the tiles that have to wait for the neighbours' coordinates run
+    // at the end of the launch, when those have long arrived, instead of spinning on an SM at its start
+    int tile = (int)blockIdx.x + H.rot;
+    if (tile >= (int)gridDim.x) tile -= (int)gridDim.x;
+    const unsigned *src = tile_src + (size_t)tile * stride;
     unsigned e[UN2];
 #pragma unroll
     for (int u = 0; u < UN2; u++) {
         const int q = threadIdx.x + u * TILE_THREADS;
         e[u] = q < stride ? __ldg(src + q) : 0xffffffffu;
     }
-    const int4 hdr = tile_hdr[blockIdx.x];
+    const int4 hdr = tile_hdr[tile];
     const int a0 = hdr.x, nhome = hdr.y, total = hdr.z;
     const bool image = (hdr.w & 1) != 0;
     // slab runs on the peer-memory path: the neighbours store their boundary coordinates straight into this rank's
@@ -133,7 +137,7 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
     // this launch computes while the transfer is still on its way -- and they read the halo atoms from those buffers.
     const bool halo = (hdr.w & 2) != 0 && H.seq != 0;
     if (nhome == 0 || total > stage_cap) {                           // (the second cannot happen: the builder sized stage_cap)
-        if (threadIdx.x < SEPGPU_NPART_F) partial[blockIdx.x * SEPGPU_NPART_F + threadIdx.x] = 0.0;
+        if (threadIdx.x < SEPGPU_NPART_F) partial[tile * SEPGPU_NPART_F + threadIdx.x] = 0.0;
         return;
     }
     if (halo) {
@@ -262,7 +266,7 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
     }
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[blockIdx.x * SEPGPU_NPART_F + q] = tot[q];
+        for (int q = 0; q < SEPGPU_NPART_F; q++) partial[tile * SEPGPU_NPART_F + q] = tot[q];
     }
 }
 
@@ -284,6 +288,11 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, 
         if (rh == 0 && (rh = sepgpu_dd_halo_update(c, sys))) return rh;
     }
     const int grid = c->tile_count;
+    if (c->dd && H.seq != 0) {
+        const CellGrid &G = c->tile_grid;
+        const int per_layer = G.nbx * G.nby * (BRICK_YZ * BRICK_YZ / c->tile_R);      // tiles in one layer of bricks
+        if (per_layer > 0 && per_layer < grid) H.rot = per_layer;
+    }
     const int stage_cap = c->tile_stage_used;
     const size_t smem = sepgpu_tile_force_smem(stage_cap);
     // the kernel works on coordinates divided by sigma: cutoff and force prefactor follow

@@ -321,6 +321,7 @@ struct HaloArgs {
     int n0, n_own;                       // halo atoms from hi (the ones from lo follow); local atoms n_own.. are the halo
     const unsigned long long *flags;     // [0] raised by the hi neighbour, [1] by the lo neighbour
     unsigned long long seq;              // refresh number to wait for; 0 = nothing to wait for (not decomposed)
+    int rot;                             // CTA b works on tile (b + rot) mod gridDim: the brick layers next to the halo come last
 };
 int sepgpu_dd_halo_args(sepgpu_ctx *c, const sepgpu_sys *sys, HaloArgs *out);
 
