@@ -636,9 +636,12 @@ def run_molecular(args, emit, local_rank):
 
 
 # ---------------------------------------------------------------------------------------------------
-def weak_lattice_dims(ncell, world):
+def weak_lattice_dims(ncell, world, box="cubic"):
     """Lattice sides for `world` GPUs at ncell^3 atoms per GPU (weak scaling, near-cubic box, z longest):
-    1 -> n,n,n ; 2 -> n,n,2n ; 4 -> n,2n,2n ; 8 -> 2n,2n,2n."""
+    1 -> n,n,n ; 2 -> n,n,2n ; 4 -> n,2n,2n ; 8 -> 2n,2n,2n.  box="stacked": n,n,world*n (the cross-section a slab
+    decomposition likes best; not the default -- a bulk fluid is simulated in a cubic box)."""
+    if box == "stacked":
+        return [ncell, ncell, ncell * world]
     dims = [ncell, ncell, ncell]
     k, w = 2, world
     while w > 1:
@@ -699,6 +702,7 @@ def main():
     ap.add_argument("--no-other", action="store_true", help="skip the short C2 (butane) / C3 (water) runs appended as other_workloads")
     ap.add_argument("--equilibrate", type=int, default=300, help="untimed steps from the lattice before the warm-up (thermalisation)")
     ap.add_argument("--e2e-steps", type=int, default=1000, help="the e2e arm runs max(--steps, this) steps (it carries one upload and one download of atoms[])")
+    ap.add_argument("--box", default="cubic", choices=["cubic", "stacked"], help="N>1: near-cubic box (default) or N cubes stacked along the slab axis")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of domain decomposition")
@@ -780,7 +784,7 @@ def main():
 
     # ---------------- workload ---------------------------------------------------------------------
     if decomposed:
-        dims = weak_lattice_dims(args.ncell, world)
+        dims = weak_lattice_dims(args.ncell, world, args.box)
     else:
         dims = [args.ncell] * 3
     Lvec, a_lat = lattice_box(dims, args.rho)
