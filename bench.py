@@ -866,8 +866,10 @@ def main():
     barrier()
     t_wall0 = time.time()
     s.call("sepgpu_timer_start")
-    for _ in range(K):
-        step_dev()
+    # the K timed steps are driven from C (sepgpu_md_lj_nvt: the same five calls per step as step_dev), as a seplib program
+    # would drive them -- no interpreter, and no clock-sampler thread contending for it, between the calls
+    if lib.sepgpu_md_lj_nvt(s.ctx, gs_ref, b"AA", lj_ref, 1, temp, 0, tau, K):
+        raise RuntimeError("device step failed: " + lib.sepgpu_last_error().decode())
     ms = C.c_float()
     s.call("sepgpu_timer_stop", C.byref(ms))
     barrier()

@@ -121,6 +121,13 @@ int sepgpu_set_topology(sepgpu_ctx *ctx, const unsigned *blist, unsigned nbonds,
                         const unsigned *dlist, unsigned ndihedrals);
 int sepgpu_get_bonded_values(sepgpu_ctx *ctx, double *blengths, double *angles, double *dihedrals);
 
+/* Convenience: nsteps of the Lennard-Jones NVT loop of the reference's prg1 (prgs/prg1.c:52-70), driven from C -- per step
+ * exactly sepgpu_reset_ret, sepgpu_reset_force, sepgpu_force_lj(epot_assign = 1; rebuilds the list when the trigger fired),
+ * sepgpu_nosehoover, sepgpu_leapfrog.  Same results as making those calls one by one; no interpreter between them when the
+ * caller is not C.  Collective in decomposed runs.  Stops at the first error. */
+int sepgpu_md_lj_nvt(sepgpu_ctx *ctx, const sepgpu_sys *sys, const char types[2], const sepgpu_ljparam *p, unsigned opt,
+                     double temp, int alpha_slot, double tau, int nsteps);
+
 /* ---- per-step hot path -------------------------------------------------------------------------- */
 /* sep_reset_retval (source/sepret.c:19-47) */
 int sepgpu_reset_ret(sepgpu_ctx *ctx);

@@ -956,3 +956,20 @@ extern "C" int sepgpu_scale_positions(sepgpu_ctx *c, double xi)
     KERNEL_CHECK();
     return 0;
 }
+
+
+// ---- the prg1 loop, driven from C (reference prgs/prg1.c:52-70) ---------------------------------------------------------
+extern "C" int sepgpu_md_lj_nvt(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], const sepgpu_ljparam *p, unsigned opt,
+                                double temp, int alpha_slot, double tau, int nsteps)
+{
+    if (!c || !sys || !types || !p || nsteps < 0) return SEPGPU_EINVAL;
+    for (int n = 0; n < nsteps; n++) {
+        int rc = sepgpu_reset_ret(c);
+        if (!rc) rc = sepgpu_reset_force(c);
+        if (!rc) rc = sepgpu_force_lj(c, sys, types, p, opt, 1);
+        if (!rc) rc = sepgpu_nosehoover(c, sys, temp, alpha_slot, tau);
+        if (!rc) rc = sepgpu_leapfrog(c, sys);
+        if (rc) return rc;
+    }
+    return 0;
+}

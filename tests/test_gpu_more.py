@@ -208,6 +208,33 @@ def test_small_grid_exact_fallback_and_capacity_growth():
     s.close()
 
 
+def test_c_driven_loop_equals_the_calls_one_by_one():
+    """sepgpu_md_lj_nvt (the prg1 loop driven from C) against the same five calls per step made from here: bit-identical
+    state and sums after 30 steps with several list rebuilds."""
+    x, L = cm.lattice(12, 0.8, jitter=0.05, seed=41)
+    n = len(x)
+    v = cm.velocities(n, 2.5, seed=42)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    p = capi.lj_param(2.5, kind="lj_shift")
+    out = []
+    for c_loop in (False, True):
+        s = capi.System(n); s.put(capi.F_X, x); s.put(capi.F_V, v)
+        s.call("sepgpu_set_alpha", 0, 0.05)
+        if c_loop:
+            s.call("sepgpu_md_lj_nvt", C.byref(sys_), b"AA", C.byref(p), 1, 1.0, 0, 0.1, 30)
+        else:
+            for _ in range(30):
+                s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+                s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), 1, 1)
+                s.call("sepgpu_nosehoover", C.byref(sys_), 1.0, 0, 0.1)
+                s.call("sepgpu_leapfrog", C.byref(sys_))
+        sc = s.scalars()
+        out.append((s.get(capi.F_X), s.get(capi.F_V), sc.epot, sc.ekin, sc.alpha[0], sc.nbuild))
+        s.close()
+    a, b = out
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2:] == b[2:] and a[5] >= 3
+
+
 # ---- the reference-facing API: host seppart[] buffers through libsep.so -----------------------------------
 PAIRFUN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_char)
 
