@@ -46,40 +46,30 @@ __device__ __forceinline__ int imin3(int a, int b, int c) { return __vimin3_s32(
 __device__ __forceinline__ unsigned shift_in_sign(unsigned m, float d) { return __funnelshift_l(__float_as_uint(d), m, 1); }
 #endif
 
-template <bool F16>
-struct RowWriter {
-    unsigned long long lo, hi;
-    unsigned pad;                 // F16: every unused 16-bit field names the tile's far-away pad slot
-    __device__ __forceinline__ void init(unsigned pad_slot)
+// 32-bit rows (four entries per 128-bit chunk): the last four entries ride in registers, a whole chunk leaves with one
+// store through a pointer that walks the row (no address arithmetic from the atom index at store time)
+struct RowWriter32 {
+    unsigned v0, v1, v2, v3;
+    uint4 *chunk;
+    __device__ __forceinline__ void init(unsigned *nbr, int s)
     {
-        pad = F16 ? pad_slot : 0u;
-        clear();
+        v0 = v1 = v2 = v3 = 0u;
+        chunk = reinterpret_cast<uint4 *>(nbr) + s;
     }
-    __device__ __forceinline__ void clear()
+    // entry number `count` of the row
+    __device__ __forceinline__ void push(unsigned e, int count, int npad)
     {
-        const unsigned long long p = F16 ? (unsigned long long)pad * 0x0001000100010001ULL : 0ULL;
-        lo = p; hi = p;
+        v0 = v1; v1 = v2; v2 = v3; v3 = e;
+        if ((count & 3) == 3) { *chunk = make_uint4(v0, v1, v2, v3); chunk += npad; }
     }
-    // entry number `count` of sorted atom s
-    __device__ __forceinline__ void push(unsigned e, int count, int s, int npad, unsigned *__restrict__ nbr)
+    // the last, partial chunk: its entries sit in the upper registers
+    __device__ __forceinline__ void finish(int count)
     {
-        constexpr int PER = F16 ? 8 : 4, BITS = F16 ? 16 : 32;
-        const int p = count & (PER - 1);
-        const unsigned long long v = (unsigned long long)(e ^ pad) << (BITS * (p & (PER / 2 - 1)));
-        if (p < PER / 2) lo ^= v; else hi ^= v;
-        if (p == PER - 1) { store(count, s, npad, nbr); clear(); }
-    }
-    __device__ __forceinline__ void store(int count, int s, int npad, unsigned *__restrict__ nbr) const
-    {
-        constexpr int SH = F16 ? 3 : 2;
-        uint4 v;
-        v.x = (unsigned)lo; v.y = (unsigned)(lo >> 32); v.z = (unsigned)hi; v.w = (unsigned)(hi >> 32);
-        reinterpret_cast<uint4 *>(nbr)[(size_t)(count >> SH) * npad + s] = v;
-    }
-    __device__ __forceinline__ void finish(int count, int s, int npad, unsigned *__restrict__ nbr) const
-    {
-        constexpr int PER = F16 ? 8 : 4;
-        if (count & (PER - 1)) store(count, s, npad, nbr);
+        const int k = count & 3;
+        if (k == 0) return;
+        if (k == 1) *chunk = make_uint4(v3, 0u, 0u, 0u);
+        else if (k == 2) *chunk = make_uint4(v2, v3, 0u, 0u);
+        else *chunk = make_uint4(v1, v2, v3, 0u);
     }
 };
 
@@ -194,8 +184,8 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             int count = 0, half_count = 0;
             // F16: entries leave one by one as 16-bit stores into the row's current 128-bit chunk
             unsigned short *row16 = reinterpret_cast<unsigned short *>(nbr) + (size_t)s * 8;
-            RowWriter<false> W;
-            W.init(0u);
+            RowWriter32 W;
+            W.init(nbr, s);
             const bool img_tile = F16 && T.any_image != 0;
 #pragma unroll 1
             for (int r = 0; r < 9; r++) {
@@ -356,7 +346,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                             while (mask) {
                                 const int b = __ffs(mask) - 1;
                                 mask &= mask - 1;
-                                W.push(candW[q0 + b], count, s, P.npad, nbr);
+                                W.push(candW[q0 + b], count, P.npad);
                                 count++;
                             }
                         }
@@ -367,7 +357,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             }
             if (count <= P.cap) {
                 if (F16) { for (int k = count; k & 7; k++) *row16++ = (unsigned short)total; }   // pad the last chunk with the far-away slot
-                else W.finish(count, s, P.npad, nbr);
+                else W.finish(count);
             }
             cnt[s] = min(count, P.cap);
             blk_max = max(blk_max, count); blk_half = max(blk_half, half_count); blk_sum += count;
