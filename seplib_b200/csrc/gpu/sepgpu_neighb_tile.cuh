@@ -73,6 +73,28 @@ struct RowWriter32 {
     }
 };
 
+// 16-bit rows (eight tile slots per chunk): the same scheme, entries shifted in from the top, 16 bits at a time
+struct RowWriter16 {
+    unsigned v0, v1, v2, v3;
+    uint4 *chunk;
+    __device__ __forceinline__ void init(unsigned *nbr, int s)
+    {
+        v0 = v1 = v2 = v3 = 0u;
+        chunk = reinterpret_cast<uint4 *>(nbr) + s;
+    }
+    __device__ __forceinline__ void push(unsigned e, int count, int npad)
+    {
+        v0 = (v0 >> 16) | (v1 << 16); v1 = (v1 >> 16) | (v2 << 16); v2 = (v2 >> 16) | (v3 << 16);      // (one PRMT each)
+        v3 = (v3 >> 16) | (e << 16);
+        if ((count & 7) == 7) { *chunk = make_uint4(v0, v1, v2, v3); chunk += npad; }
+    }
+    // the last, partial chunk is filled up with the tile's far-away pad slot
+    __device__ __forceinline__ void finish(int count, unsigned pad, int npad)
+    {
+        for (int k = count; k & 7; k++) push(pad, k, npad);
+    }
+};
+
 template <unsigned OPT, bool F16>
 #ifndef BUILD_MINB
 #define BUILD_MINB 4
@@ -183,7 +205,8 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             const int mol_x = mol_i == -1 ? 0x3ffffffe : mol_i;
             int count = 0, half_count = 0;
             // F16: entries leave one by one as 16-bit stores into the row's current 128-bit chunk
-            unsigned short *row16 = reinterpret_cast<unsigned short *>(nbr) + (size_t)s * 8;
+            RowWriter16 W16;
+            W16.init(nbr, s);
             RowWriter32 W;
             W.init(nbr, s);
             const bool img_tile = F16 && T.any_image != 0;
@@ -327,17 +350,15 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                                 while (mask) {
                                     const int b = __ffs(mask) - 1;
                                     mask &= mask - 1;
-                                    *row16 = (unsigned short)((unsigned)(q0 + b) | (((imgbits >> b) & 1u) << 15));
+                                    W16.push((unsigned)(q0 + b) | (((imgbits >> b) & 1u) << 15), count, P.npad);
                                     count++;
-                                    row16 += (count & 7) ? 1 : P.npad * 8 - 7;
                                 }
                             } else {
                                 while (mask) {
                                     const int b = __ffs(mask) - 1;
                                     mask &= mask - 1;
-                                    *row16 = (unsigned short)(q0 + b);
+                                    W16.push((unsigned)(q0 + b), count, P.npad);
                                     count++;
-                                    row16 += (count & 7) ? 1 : P.npad * 8 - 7;
                                 }
                             }
                         } else {
@@ -356,7 +377,7 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
                 }
             }
             if (count <= P.cap) {
-                if (F16) { for (int k = count; k & 7; k++) *row16++ = (unsigned short)total; }   // pad the last chunk with the far-away slot
+                if (F16) W16.finish(count, (unsigned)total, P.npad);
                 else W.finish(count);
             }
             cnt[s] = min(count, P.cap);
