@@ -14,8 +14,7 @@
 // F16 = true : rows of 16-bit tile slots (sepgpu_tile.cuh) for the tile force kernels, 8 per 128-bit chunk.
 // F16 = false: rows of 32-bit entries  sorted index | image code << 26, 4 per chunk, for the kernels that
 //              gather from global memory (DPD, the molecule-pair table, small grids).
-// 16-bit entries leave one by one into the row's current 128-bit chunk (L2 merges the partial sectors); 32-bit rows
-// are assembled in registers and leave as whole chunks.
+// Rows are assembled in a register window (RowWriter16 / RowWriter32) and leave as whole 128-bit chunks.
 #pragma once
 
 #include "sepgpu_tile.cuh"
@@ -204,7 +203,6 @@ k_build_tile(const d4 *__restrict__ xs, const float4 *__restrict__ xf, const int
             const int band_bits = __float_as_int(P.fband);
             const int mol_x = mol_i == -1 ? 0x3ffffffe : mol_i;
             int count = 0, half_count = 0;
-            // F16: entries leave one by one as 16-bit stores into the row's current 128-bit chunk
             RowWriter16 W16;
             W16.init(nbr, s);
             RowWriter32 W;
