@@ -397,7 +397,8 @@ int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_begin(sepgpu_ctx *c, const sepgpu_sys *sys);
 int sepgpu_dd_halo_end(sepgpu_ctx *c);
 int sepgpu_need_global_rows(sepgpu_ctx *c, const sepgpu_sys *sys);
-int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows);
+int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows,
+                          d4 *f_out = nullptr, const int *cancel = nullptr);
 
 // Option fin_multi: the same reduction spread over several CTAs.  CTA b sums a fixed chunk of rows into stage row b;
 // the CTA that draws the last ticket adds the stage rows in index order and applies the result -- fixed chunks and a
@@ -687,6 +688,36 @@ extern "C" int sepgpu_force_table(sepgpu_ctx *c, const sepgpu_sys *sys, const ch
     return force_pairs_dev(c, sys, types, P, opt, epot_assign);
 }
 
+static bool spec_same(const sepgpu_ctx::SpecForce &S, const sepgpu_sys *sys, const char types[2], const LJDev &P, unsigned opt,
+                      int epot_assign, bool typed)
+{
+    if (S.streak <= 0) return false;
+    const LJDev &Q = S.P;
+    bool eq = Q.cf2 == P.cf2 && Q.sig2 == P.sig2 && Q.eps48 == P.eps48 && Q.eps4 == P.eps4 && Q.aw == P.aw && Q.awh == P.awh &&
+              Q.shift == P.shift && Q.t0 == P.t0 && Q.t1 == P.t1 && !P.tab && !Q.tab;
+    eq = eq && S.types[0] == types[0] && S.types[1] == types[1] && S.opt == opt && S.epot_assign == epot_assign && S.typed == typed;
+    for (int k = 0; k < 3; k++)
+        eq = eq && S.sys.length[k] == sys->length[k] && S.sys.lsubbox[k] == sys->lsubbox[k] && S.sys.nsubbox[k] == sys->nsubbox[k];
+    return eq && S.sys.cf == sys->cf && S.sys.skin == sys->skin && S.sys.neighb_update == sys->neighb_update;
+}
+
+// Called by the integrators once their finaliser is queued: launch the step's first force routine for the NEXT step now,
+// guarded by the rebuild flag that finaliser is about to write.  Forces go to the spare array.
+int sepgpu_spec_force_launch(sepgpu_ctx *c)
+{
+    sepgpu_ctx::SpecForce &S = c->spec;
+    S.launched = false;
+    if (!S.on || S.streak < 3 || c->dd || !c->list_valid || !c->list_f16 || c->fij) return 0;
+    if (!c->f4_alt) CUDA_TRY(cudaMalloc((void **)&c->f4_alt, sizeof(d4) * (size_t)c->ncap));
+    int nrows = 0;
+    ktimer_begin(c, &c->t_force);
+    const int rc = sepgpu_lj_tile_launch(c, &S.sys, S.P, S.B, S.typed, true, &nrows, c->f4_alt, &c->scal->neighb_flag);
+    ktimer_end(c, &c->t_force);
+    if (rc) return rc;
+    S.launched = true; S.cancelled = false; S.nrows = nrows; S.list_gen = c->list_gen; S.api_seq = c->api_seq;
+    return 0;
+}
+
 static int force_pairs_dev(sepgpu_ctx *c, const sepgpu_sys *sys, const char types[2], const LJDev &P, unsigned opt, int epot_assign)
 {
     BoxDev B; B.Lx = sys->length[0]; B.Ly = sys->length[1]; B.Lz = sys->length[2];
@@ -719,6 +750,29 @@ static int force_pairs_dev(sepgpu_ctx *c, const sepgpu_sys *sys, const char type
     }
     if (c->list_f16) {                                   // rows of 16-bit tile slots: shared-memory staged tile kernel
         int nrows = 0;
+        sepgpu_ctx::SpecForce &S = c->spec;
+        const bool same = spec_same(S, sys, types, P, opt, epot_assign, typed);
+        if (S.launched) {
+            // this very call was launched ahead of time behind the last integrator (sepgpu_spec_force_launch): adopt it when
+            // nothing has happened since that could change its result, drop it otherwise (it wrote into the spare array)
+            const bool adopt = !S.cancelled && store && same && c->list_gen == S.list_gen && c->api_seq == S.api_seq + 1;
+            S.launched = false;
+            if (adopt) {
+                d4 *t = c->f4; c->f4 = c->f4_alt; c->f4_alt = t;
+                c->spec_adopted++;
+                c->f_zero = false;
+                return sepgpu_finalize_force(c, S.nrows, 0.5, epot_assign ? 1 : 0);
+            }
+            if (c->t_force.enabled && c->t_force.used > 0) c->t_force.used--;      // not one of the step's force launches
+        }
+        // the first force routine after sep_reset_force, repeated unchanged step after step, is what gets launched ahead
+        if (store && !P.tab && !c->dd) {
+            if (same) S.streak++;
+            else {
+                S.streak = 1; S.P = P; S.B = B; S.typed = typed; S.types[0] = types[0]; S.types[1] = types[1];
+                S.opt = opt; S.epot_assign = epot_assign; S.sys = *sys;
+            }
+        }
         ktimer_begin(c, &c->t_force);
         rc = sepgpu_lj_tile_launch(c, sys, P, B, typed, store, &nrows);
         ktimer_end(c, &c->t_force);
@@ -726,6 +780,7 @@ static int force_pairs_dev(sepgpu_ctx *c, const sepgpu_sys *sys, const char type
         c->f_zero = false;
         return sepgpu_finalize_force(c, nrows, 0.5, epot_assign ? 1 : 0);
     }
+    c->spec.streak = 0;
     const int tpa = c->tpa;
     // contiguous ranges of the sorted atoms per CTA; several CTAs per SM, a few waves for load balance
     const int groups = FORCE_BLOCK / tpa;

@@ -136,7 +136,9 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
     // receive buffers every step and raise a flag.  Only tiles next to a halo layer wait for it -- every other CTA of
     // this launch computes while the transfer is still on its way -- and they read the halo atoms from those buffers.
     const bool halo = (hdr.w & 2) != 0 && H.seq != 0;
-    if (nhome == 0 || total > stage_cap) {                           // (the second cannot happen: the builder sized stage_cap)
+    // speculative launch (sepgpu_spec_force_launch): the integrator's finaliser has just asked for a list rebuild -> nothing to do
+    const bool cancelled = H.cancel != nullptr && *reinterpret_cast<const volatile int *>(H.cancel) != 0;
+    if (cancelled || nhome == 0 || total > stage_cap) {              // (the last cannot happen: the builder sized stage_cap)
         if (threadIdx.x < SEPGPU_NPART_F) partial[tile * SEPGPU_NPART_F + threadIdx.x] = 0.0;
         return;
     }
@@ -276,7 +278,8 @@ size_t sepgpu_tile_force_smem(int stage_cap)
 }
 
 // Launches the tile kernel on the context's current tile-format list; returns the number of partial rows.
-int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows)
+int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, const BoxDev &B, bool typed, bool store, int *nrows,
+                          d4 *f_out, const int *cancel)
 {
     // decomposed run: peer-memory path -> the kernel waits for and reads the neighbours' coordinates itself;
     // otherwise refresh the halo entries of xs first
@@ -287,6 +290,8 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, 
         if (rh < 0) return rh;
         if (rh == 0 && (rh = sepgpu_dd_halo_update(c, sys))) return rh;
     }
+    H.cancel = cancel;
+    d4 *const f4 = f_out ? f_out : c->f4;
     const int grid = c->tile_count;
     if (c->dd && H.seq != 0) {
         const CellGrid &G = c->tile_grid;
@@ -304,12 +309,12 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, 
         if (P.tab) {                                                                                                             \
             CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
             k_lj_tile<TY, ST, 3, true><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt, \
-                c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);    \
+                c->order, c->tile_hdr, c->tile_src, f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);       \
             break;                                                                                                               \
         }                                                                                                                        \
         CUDA_TRY(cudaFuncSetAttribute(k_lj_tile<TY, ST, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         k_lj_tile<TY, ST, MB, false><<<grid, TILE_THREADS, smem, c->stream>>>(c->xs, reinterpret_cast<const uint4 *>(c->nbr), c->cnt,   \
-            c->order, c->tile_hdr, c->tile_src, c->f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);    \
+            c->order, c->tile_hdr, c->tile_src, f4, c->tile_stride, c->npad, stage_cap, Ps, B, isig, c->partial, H, c->scal);       \
     } while (0)
 #define LJT_LAUNCH(TY, ST) LJT_LAUNCH3(TY, ST, 3)        // 3 CTAs per SM (72 registers); 4 spill and were measured slower
     if (typed) { if (store) LJT_LAUNCH(true, true); else LJT_LAUNCH(true, false); }

@@ -78,6 +78,18 @@ struct CellGrid {
 
 struct DDState;            // slab domain decomposition (sepgpu_dd.cu); NULL when the context is not decomposed
 
+// parameters of one Lennard-Jones-family pair call, as the kernels take them (sepgpu_pair.cuh has the arithmetic)
+struct LJDev {
+    double cf2, sig2, eps48, eps4, aw, awh, shift;
+    int t0, t1;
+    // tabulated pair function (user callbacks of sep_force_pairs): n samples {f, u} on a uniform r^2 grid [t_lo, t_lo + (n-1)/t_inv];
+    // NULL = the Lennard-Jones family above
+    const double2 *tab;
+    double t_lo, t_inv;
+    int t_n;
+};
+struct BoxDev { double Lx, Ly, Lz; };
+
 struct sepgpu_ctx {
     int n;                 // atoms in the sorted arrays: owned + halo (== n_own when not decomposed)
     int n_own;             // atoms this context integrates
@@ -204,6 +216,27 @@ struct sepgpu_ctx {
 
     const int *host_rows;          // sepgpu_set_host_rows
 
+    // Speculative force launch (option spec_force): after an integrator call the first force call of the previous steps
+    // is launched again at once, behind the finaliser and guarded by the device-side rebuild flag, into a second force
+    // array; the host reads the flag beside it on its own stream.  The next sepgpu_force_lj with the same arguments adopts
+    // the launch (swaps the force arrays) instead of launching -- the device never waits for the host's decision.
+    struct SpecForce {
+        int on, streak;
+        bool launched, cancelled;
+        LJDev P; BoxDev B; bool typed;
+        char types[2]; unsigned opt; int epot_assign;
+        sepgpu_sys sys;
+        int nrows, list_gen;
+        unsigned long long api_seq;
+    } spec;
+    d4 *f4_alt;
+    long long spec_adopted;        // launches adopted so far (tests, sepgpu_get_option)
+    bool scal_cache_valid;         // scal_host holds the block as the last integrator's finaliser left it ...
+    unsigned long long scal_cache_seq;     // ... and nothing but readers has entered the library since
+    unsigned long long api_seq;    // entries into the library that may change state (SEPGPU_ENTER; readers take themselves out)
+    cudaStream_t flag_stream;
+    cudaEvent_t ev_fin;
+
     // measurement
     cudaEvent_t ev0, ev1;
     KernelTimer t_force, t_build, t_intgr, t_coul, t_bonded, t_halo, t_migr;
@@ -234,8 +267,10 @@ void sepgpu_set_error(const char *fmt, ...);
 int sepgpu_settle(sepgpu_ctx *c);
 int sepgpu_nh_update_now(sepgpu_ctx *c);
 int sepgpu_dd_uses_p2p(sepgpu_ctx *c);             // sepgpu_dd.cu: decomposed run on the peer-memory path
+#define SEPGPU_BENIGN(c) ((c)->api_seq--)          /* after SEPGPU_ENTER in entries that only read or set lazy flags */
 #define SEPGPU_ENTER(c)                                                                     \
     do {                                                                                    \
+        (c)->api_seq++;                                                                     \
         CUDA_TRY(cudaSetDevice((c)->device));                                               \
         if ((c)->fin_pending.active || (c)->nh_pending.active) {                            \
             int _rs = sepgpu_settle(c);                                                     \
@@ -322,6 +357,7 @@ struct HaloArgs {
     const unsigned long long *flags;     // [0] raised by the hi neighbour, [1] by the lo neighbour
     unsigned long long seq;              // refresh number to wait for; 0 = nothing to wait for (not decomposed)
     int rot;                             // CTA b works on tile (b + rot) mod gridDim: the brick layers next to the halo come last
+    const int *cancel;                   // speculative launch: every CTA leaves at once when this flag is set (rebuild requested)
 };
 int sepgpu_dd_halo_args(sepgpu_ctx *c, const sepgpu_sys *sys, HaloArgs *out);
 

@@ -494,6 +494,31 @@ __global__ void k_partial2_to_comm(const double *__restrict__ partial, int nrows
 }
 __global__ void k_comm_to_mv2(DevScalars *scal, const double *comm) { scal->sum_mv2 = comm[0]; }
 
+int sepgpu_spec_force_launch(sepgpu_ctx *c);
+
+// reads the scalar block (the rebuild trigger) after the finaliser that has just been queued; returns < 0 on error
+static int sepgpu_spec_force_launch_after(sepgpu_ctx *c)
+{
+    if (c->spec.on && c->spec.streak >= 3 && !c->dd) {
+        if (!c->flag_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&c->flag_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fin, cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_fin, c->stream));
+        const int rc = sepgpu_spec_force_launch(c);
+        if (rc) return rc < 0 ? rc : -1;
+        if (c->spec.launched) {
+            CUDA_TRY(cudaStreamWaitEvent(c->flag_stream, c->ev_fin, 0));
+            CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->flag_stream));
+            CUDA_TRY(cudaStreamSynchronize(c->flag_stream));
+            return 0;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double lambda, int stepnow)
 {
     CUDA_TRY(cudaSetDevice(c->device));
@@ -584,9 +609,13 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
     if (!P.write_xs) c->xs_current = false;
     sepgpu_dd_positions_moved(c);
 
-    // the trigger is needed by the host before the next force call: small D2H + stream sync per step
-    CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // the trigger is needed by the host before the next force call: small D2H + stream sync per step.  With a force launch
+    // sent ahead (sepgpu_spec_force_launch) the copy runs on a stream of its own, right behind the finaliser and beside
+    // that launch, so that the host decides while the device already computes.
+    {
+        int rs = sepgpu_spec_force_launch_after(c);
+        if (rs < 0) return rs;
+    }
     if (c->dd && c->scal_host->error == SEPGPU_ENCCL) {
         sepgpu_set_error("decomposed step: a neighbour's data never arrived (peer-memory wait timed out)");
         return SEPGPU_ENCCL;
@@ -595,7 +624,10 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
         sepgpu_set_error("a pair came closer than the tabulated pair function reaches (raise its resolution towards r = 0: SEP_TABLE_RMIN)");
         return SEPGPU_ETABLE;
     }
+    c->scal_cache_valid = !c->dd;                          // sepgpu_read_scalars right after this call needs no second copy
+    c->scal_cache_seq = c->api_seq;
     if (c->scal_host->neighb_flag) {
+        c->spec.cancelled = true;                          // (the launch sent ahead has seen the flag on the device and left)
         k_set_xn<<<(c->n_own + 255) / 256, 256, 0, c->stream>>>(c->x4, c->xn4, c->cr4, c->n_own);
         KERNEL_CHECK();
         c->list_valid = false;

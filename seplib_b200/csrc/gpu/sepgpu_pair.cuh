@@ -6,15 +6,7 @@
 
 #include <math.h>
 
-struct LJDev {
-    double cf2, sig2, eps48, eps4, aw, awh, shift;
-    int t0, t1;
-    // tabulated pair function (user callbacks of sep_force_pairs): n samples {f, u} on a uniform r^2 grid [t_lo, t_lo + (n-1)/t_inv];
-    // NULL = the Lennard-Jones family above
-    const double2 *tab;
-    double t_lo, t_inv;
-    int t_n;
-};
+// (struct LJDev and struct BoxDev live in sepgpu_internal.cuh: the context keeps a copy of the last force call's)
 
 // {force factor, energy} of a tabulated pair function at r2: cubic Lagrange interpolation through the four grid points
 // around r2 (uniform grid in r^2).  Error <= (3/128) h^4 max|d4/d(r2)4|; with the 32768-point table the host layer
@@ -32,7 +24,6 @@ __device__ __forceinline__ double2 table_eval(const LJDev &P, double r2, bool &b
     return make_double2(c0 * a.x + c1 * b.x + c2 * c.x + c3 * d.x, c0 * a.y + c1 * b.y + c2 * c.y + c3 * d.y);
 }
 
-struct BoxDev { double Lx, Ly, Lz; };
 
 // 1/x to ~1 ulp: MUFU.RCP64H seed (relative error <= 2^-23) + two Newton steps (4 DFMA) instead of the
 // IEEE division sequence; inputs are r^2 of in-range pairs, far from denormals/inf.

@@ -82,6 +82,7 @@ extern "C" int sepgpu_create(sepgpu_ctx **out, size_t npart, int device)
     c->typed_sublist = 1;
     c->step_fold = 1;
     c->fin_multi = 1;
+    c->spec.on = 1;
     c->tile_list = 1;
     c->build_window = 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -141,6 +142,9 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     if (c->xq) cudaFree(c->xq);
     if (c->fin_ticket) cudaFree(c->fin_ticket);
     for (int q = 0; q < SEPGPU_NTAB; q++) if (c->tab[q].dev) cudaFree(c->tab[q].dev);
+    if (c->f4_alt) cudaFree(c->f4_alt);
+    if (c->flag_stream) cudaStreamDestroy(c->flag_stream);
+    if (c->ev_fin) cudaEventDestroy(c->ev_fin);
     if (c->tile_hdr) cudaFree(c->tile_hdr);
     if (c->tile_src) cudaFree(c->tile_src);
     if (c->randn4) cudaFree(c->randn4);
@@ -485,6 +489,7 @@ extern "C" int sepgpu_get_fields(sepgpu_ctx *c, void *base, size_t stride, int n
 {
     if (!c || !base || nfields <= 0 || nfields > SEPGPU_MAX_FIELDS || !fields) return SEPGPU_EINVAL;
     SEPGPU_ENTER(c);
+    SEPGPU_BENIGN(c);
     const size_t n = (size_t)c->n_own;
     size_t row[SEPGPU_MAX_FIELDS], off[SEPGPU_MAX_FIELDS], hoff[SEPGPU_MAX_FIELDS], total = 0;
     for (int f = 0; f < nfields; f++) {
@@ -591,6 +596,7 @@ extern "C" int sepgpu_reset_force(sepgpu_ctx *c)
 {
     if (!c) return SEPGPU_EINVAL;
     SEPGPU_ENTER(c);
+    SEPGPU_BENIGN(c);
     // f <- 0 is not written out: the first force kernel after this call stores instead of adding.
     c->f_zero = true;
     c->pending_alpha_slot = -1;       // a pending f -= alpha m v dies with the force it would modify
@@ -610,9 +616,15 @@ extern "C" int sepgpu_read_scalars(sepgpu_ctx *c, sepgpu_scalars *out)
 {
     if (!c || !out) return SEPGPU_EINVAL;
     SEPGPU_ENTER(c);
-    { int rcf = sepgpu_flush_resets(c); if (rcf) return rcf; }
-    CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    SEPGPU_BENIGN(c);
+    // straight after an integrator call the block is on the host already (it was fetched with the rebuild trigger)
+    const bool cached = c->scal_cache_valid && c->scal_cache_seq == c->api_seq && !c->ret_reset_pending && !c->maxd_reset_pending;
+    if (!cached) {
+        { int rcf = sepgpu_flush_resets(c); if (rcf) return rcf; }
+        CUDA_TRY(cudaMemcpyAsync(c->scal_host, c->scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->scal_cache_valid = false;
+    }
     const DevScalars *s = c->scal_host;
     if (s->error == SEPGPU_ETABLE) {
         sepgpu_set_error("a pair came closer than the tabulated pair function reaches (SEP_TABLE_RMIN)");
@@ -717,6 +729,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
     if (!strcmp(name, "step_fold")) { if (!value) { int rs = sepgpu_settle(c); if (rs) return rs; } c->step_fold = value != 0; return 0; }
     if (!strcmp(name, "fin_multi")) { c->fin_multi = value != 0; return 0; }
+    if (!strcmp(name, "spec_force")) { c->spec.on = value != 0; c->spec.streak = 0; return 0; }
     if (!strcmp(name, "build_window")) { if (value < 0 || value > 2) return SEPGPU_EINVAL; c->build_window = (int)value; return 0; }
     if (!strcmp(name, "tile_list")) { c->tile_list = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
@@ -754,6 +767,8 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "build_window")) *value = c->build_window;
     else if (!strcmp(name, "fin_multi")) *value = c->fin_multi;
     else if (!strcmp(name, "step_fold")) *value = c->step_fold;
+    else if (!strcmp(name, "spec_force")) *value = c->spec.on;
+    else if (!strcmp(name, "spec_adopted")) *value = c->spec_adopted;
     else if (!strcmp(name, "list_f16")) *value = c->list_valid && c->list_f16 ? 1 : 0;       // rows of 16-bit tile slots
     else if (!strcmp(name, "tile_R")) *value = c->tile_R;
     else if (!strcmp(name, "tile_stage")) *value = c->tile_stage_used;

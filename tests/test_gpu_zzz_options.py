@@ -301,6 +301,47 @@ def test_tabulated_pair_function_on_tile_lists(typed):
     s.close()
 
 
+def test_force_launch_sent_ahead_changes_nothing():
+    """spec_force (default on): after three identical steps the step's first force call is launched behind the integrator's
+    finaliser, guarded by the device-side rebuild flag, into a spare force array, and the next sepgpu_force_lj adopts it.
+    Same program with the option off: every step's sums, the rebuild steps and the final state are bit-identical -- also
+    across a host-side upload between integrator and force call (the launch must be dropped), steps with a second force
+    call on top, and forces read back in between."""
+    x, L = _lj(12, seed=51, jitter=0.05)
+    n = len(x)
+    v = cm.velocities(n, 3.0, seed=52)
+    sys_ = capi.make_sys([L] * 3, 2.5, 0.005)
+    p = capi.lj_param(2.5, kind="lj_shift")
+    p2 = capi.lj_param(2.0, eps=0.05, sigma=1.0, aw=1.0, kind="param")
+    runs = {}
+    for on in (0, 1):
+        s = capi.System(n)
+        s.put(capi.F_X, x); s.put(capi.F_V, v)
+        s.call("sepgpu_set_option", b"spec_force", on)
+        s.call("sepgpu_set_alpha", 0, 0.0)
+        rec = []
+        for step in range(48):
+            s.call("sepgpu_reset_ret"); s.call("sepgpu_reset_force")
+            if step == 20:                                   # host edit between the integrator and the force call
+                vv = s.get(capi.F_V); vv[:, 0] *= 1.001; s.put(capi.F_V, vv)
+            s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p), cm.ALL, 1)
+            if 30 <= step < 34:                              # a second routine on top in some steps
+                s.call("sepgpu_force_lj", C.byref(sys_), b"AA", C.byref(p2), cm.ALL, 0)
+            f = s.get(capi.F_F) if step % 8 == 5 else None
+            s.call("sepgpu_nosehoover", C.byref(sys_), 2.0, 0, 0.1)
+            s.call("sepgpu_leapfrog", C.byref(sys_))
+            sc = s.scalars()
+            rec.append((sc.epot, sc.ekin, sc.alpha[0], sc.pot_P[0], sc.max_dist2, sc.neighb_flag, sc.nbuild,
+                        None if f is None else f.tobytes()))
+        runs[on] = (rec, s.get(capi.F_X).copy(), s.get(capi.F_V).copy(), s.get(capi.F_F).copy(), _opt(s, "spec_adopted"))
+        s.close()
+    assert runs[0][4] == 0 and runs[1][4] >= 20, (runs[0][4], runs[1][4])
+    assert runs[0][0] == runs[1][0]
+    for k in (1, 2, 3):
+        assert np.array_equal(runs[0][k], runs[1][k])
+    assert runs[0][0][-1][6] >= 4                              # several rebuilds: launches that left at the flag
+
+
 def test_tile_trajectory_follows_the_global_row_kernels():
     """24 NVT steps (prg1-style loop through the C ABI) with the tile kernels (default) and with global-index rows +
     the gather kernel (tile_list = 0): same rebuild steps, energies equal to rounding growth."""
