@@ -834,6 +834,7 @@ static int before_build_p2p(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int
     c->n_own = n_new;
     c->n = n_new + n_halo;
     d->halo_current = true;
+    d->halo_inflight = false;                            // a refresh pushed before this rebuild (a force launch sent ahead) is obsolete
     *zoff = d->z0 - 1;
     *nz_local = (d->z1 - d->z0) + 2;
     return 0;
@@ -917,6 +918,7 @@ int sepgpu_dd_before_build(sepgpu_ctx *c, const sepgpu_sys *sys, int *zoff, int 
     c->n_own = n_own;
     c->n = n_own + n_halo;
     d->halo_current = true;
+    d->halo_inflight = false;
     *zoff = d->z0 - 1;
     *nz_local = (d->z1 - d->z0) + 2;
     return 0;
