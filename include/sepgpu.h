@@ -213,17 +213,18 @@ int sepgpu_request_rebuild(sepgpu_ctx *ctx);
 int sepgpu_set_option(sepgpu_ctx *ctx, const char *name, long long value);
 /* Options (also through the environment, SEPGPU_OPTS="name=value,..." read by sepgpu_create):
  *   tpa, prefilter, overlap, force_grid, time_kernels, neighb_cap      tuning / measurement
- *   coulomb_kernel = 1 | 2     list Coulomb kernel: first version | charge-in-record, branch-free (default 1)
- *   typed_sublist  = 0 | 1     typed Lennard-Jones calls walk a per-type sub-list (default 0)
- *   step_fold      = 0 | 1     the step's last force reduction and the Nose-Hoover multiplier update are folded into the
- *                              integrator's kernels (3 launches per Lennard-Jones step instead of 5; single GPU; default 0)
- *   fin_multi      = 0 | 1     final reduction of the force partial rows on several CTAs with a last-block pass (default 0)
- *   build_prune    = 0 | 1     the tiled list builder skips candidate cells whose nearest point is beyond the cutoff (default 0)
- *   cell_order     = 0 | 1     slots inside a cell by atom index | along a Morton curve of 4^3 sub-cells (default 0)
- *   pair_tile      = 0 | 1     lists hold rows per PAIR of sorted atoms, served by k_lj_pairtile; uncharged single-GPU
- *                              systems only -- Coulomb and DPD need per-atom rows (default 0)
- *   pt_ctas, coul2_ctas = 4 | 5 | 6   register budget (CTAs per SM) of k_lj_pairtile / k_coulomb_list2 (default 5)
- * sepgpu_get_option also answers "list_pair" (1 when the current list is in pair-tile format). */
+ *   tile_list      = 1 | 0     rows of 16-bit tile slots + the shared-memory tile force kernel (default) | global-index rows
+ *                              and the gather kernel (contexts with charges, DPD state, the molecule-pair table and small
+ *                              grids use global-index rows in any case)
+ *   build_window   = 1 | 0 | 2 per-lane x-window in the list builder: by cell occupancy (default) | never | always
+ *   coulomb_kernel = 2 | 1     list Coulomb kernel: charge-in-record, branch-free (default) | first version
+ *   typed_sublist  = 1 | 0     typed Lennard-Jones calls on global-index rows walk a per-type sub-list (default on)
+ *   step_fold      = 1 | 0     the step's last force reduction and the Nose-Hoover multiplier update are folded into the
+ *                              integrator's kernels (3 launches per Lennard-Jones step instead of 5; default on)
+ *   fin_multi      = 1 | 0     final reductions on several CTAs with a last-block pass (default on)
+ *   spec_force     = 1 | 0     the step's first force call is queued for the next step behind the integrator, guarded by the
+ *                              device-side rebuild flag, and adopted by the next sepgpu_force_lj (default on; single GPU)
+ * sepgpu_get_option also answers "list_f16", "tile_R", "tile_stage", "max_half", "dd_p2p", "spec_adopted". */
 int sepgpu_get_option(sepgpu_ctx *ctx, const char *name, long long *value);
 
 /* ---- spatial domain decomposition over the GPUs of one box (no reference counterpart: the reference
