@@ -709,7 +709,7 @@ int sepgpu_spec_force_launch(sepgpu_ctx *c)
     S.launched = false;
     // (decomposed runs: measured on two B200s, the launch sent ahead ended in a peer-memory wait that never returned at 1 M
     //  atoms per rank although every smaller test passed -- not understood yet, so it stays off there)
-    if (!S.on || S.streak < 3 || c->dd || !c->list_valid || !c->list_f16 || c->fij) return 0;
+    if (!S.on || S.streak < 3 || (c->dd && S.on != 2) || !c->list_valid || !c->list_f16 || c->fij) return 0;
     if (!c->f4_alt) CUDA_TRY(cudaMalloc((void **)&c->f4_alt, sizeof(d4) * (size_t)c->ncap));
     int nrows = 0;
     ktimer_begin(c, &c->t_force);
@@ -768,7 +768,7 @@ static int force_pairs_dev(sepgpu_ctx *c, const sepgpu_sys *sys, const char type
             if (c->t_force.enabled && c->t_force.used > 0) c->t_force.used--;      // not one of the step's force launches
         }
         // the first force routine after sep_reset_force, repeated unchanged step after step, is what gets launched ahead
-        if (store && !P.tab && !c->dd) {
+        if (store && !P.tab && (!c->dd || c->spec.on == 2)) {
             if (same) S.streak++;
             else {
                 S.streak = 1; S.P = P; S.B = B; S.typed = typed; S.types[0] = types[0]; S.types[1] = types[1];

@@ -499,7 +499,7 @@ int sepgpu_spec_force_launch(sepgpu_ctx *c);
 // reads the scalar block (the rebuild trigger) after the finaliser that has just been queued; returns < 0 on error
 static int sepgpu_spec_force_launch_after(sepgpu_ctx *c)
 {
-    if (c->spec.on && c->spec.streak >= 3 && !c->dd) {
+    if (c->spec.on && c->spec.streak >= 3 && (!c->dd || c->spec.on == 2)) {
         if (!c->flag_stream) {
             CUDA_TRY(cudaStreamCreateWithFlags(&c->flag_stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fin, cudaEventDisableTiming));

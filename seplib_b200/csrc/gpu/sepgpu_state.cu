@@ -729,7 +729,7 @@ extern "C" int sepgpu_set_option(sepgpu_ctx *c, const char *name, long long valu
     if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
     if (!strcmp(name, "step_fold")) { if (!value) { int rs = sepgpu_settle(c); if (rs) return rs; } c->step_fold = value != 0; return 0; }
     if (!strcmp(name, "fin_multi")) { c->fin_multi = value != 0; return 0; }
-    if (!strcmp(name, "spec_force")) { c->spec.on = value != 0; c->spec.streak = 0; return 0; }
+    if (!strcmp(name, "spec_force")) { c->spec.on = value == 2 ? 2 : value != 0; c->spec.streak = 0; return 0; }   // 2: also decomposed (experimental)
     if (!strcmp(name, "build_window")) { if (value < 0 || value > 2) return SEPGPU_EINVAL; c->build_window = (int)value; return 0; }
     if (!strcmp(name, "tile_list")) { c->tile_list = value != 0; c->list_valid = false; return 0; }
     if (!strcmp(name, "coulomb_kernel")) { if (value != 1 && value != 2) return SEPGPU_EINVAL; c->coulomb_kernel = (int)value; return 0; }
