@@ -650,7 +650,7 @@ __global__ void k_dd_post_counts(const int *p_stay, const int *p_lo, const int *
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&hi_box_from_below->seq), "l"(seq) : "memory");
     const long long t0 = clock64();
     while (ld_acquire_sys(&my_boxes[0].seq) < seq || ld_acquire_sys(&my_boxes[1].seq) < seq) {
-        if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+        if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; scal->error_where = 1; break; }
         __nanosleep(100);
     }
     const volatile MigBox *b = my_boxes;
@@ -735,7 +735,7 @@ __global__ void k_dd_unpack2(const d4 *from_hi, const d4 *from_lo, const d4 *__r
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_acquire_sys(flags2) < seq || ld_acquire_sys(flags2 + 1) < seq) {
-            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; scal->error_where = 2; break; }
             __nanosleep(100);
         }
     }
@@ -994,7 +994,7 @@ __global__ void k_dd_wait_unpack_xu2(const d4 *in0, int n0, const d4 *in1, int n
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         while (ld_acquire_sys(flags) < seq || ld_acquire_sys(flags + 1) < seq) {
-            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; scal->error_where = 3; break; }
             __nanosleep(100);
         }
     }

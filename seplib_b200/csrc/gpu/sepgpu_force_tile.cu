@@ -150,7 +150,7 @@ k_lj_tile(const d4 *__restrict__ xs, const uint4 *__restrict__ nbr, const int *_
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f0) : "l"(H.flags) : "memory");
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f1) : "l"(H.flags + 1) : "memory");
                 if (f0 >= H.seq && f1 >= H.seq) break;
-                if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+                if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; scal->error_where = 4; break; }
                 __nanosleep(100);
             } while (true);
         }

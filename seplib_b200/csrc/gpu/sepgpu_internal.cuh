@@ -57,6 +57,8 @@ struct DevScalars {
     int max_half;              // longest reference-style half list at the last build
     int aliased_seen;          // list build: an atom outside [0,L) was filed under an aliased cell (reference behaviour)
     int stage_used;            // list build: largest candidate count a tile staged (sizes the tile force kernels' shared memory)
+    int error_where;           // which bounded wait gave up (SEPGPU_ENCCL): 1 migration counts, 2 migration records, 3 halo unpack,
+                               // 4 halo wait inside the tile force kernel, 5 the finaliser's all-gather
 };
 
 struct KernelTimer {

@@ -431,7 +431,7 @@ k_finalize_intgr_p2p(const double *__restrict__ partial, int nrows, DevScalars *
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(my) : "memory");
             if (got >= G.seq) break;
-            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; break; }
+            if (clock64() - t0 > SEPGPU_SPIN_LIMIT) { scal->error = SEPGPU_ENCCL; scal->error_where = 5; break; }
         } while (true);
     }
     __syncthreads();
@@ -617,7 +617,9 @@ static int run_integrator(sepgpu_ctx *c, const sepgpu_sys *sys, bool dpd, double
         if (rs < 0) return rs;
     }
     if (c->dd && c->scal_host->error == SEPGPU_ENCCL) {
-        sepgpu_set_error("decomposed step: a neighbour's data never arrived (peer-memory wait timed out)");
+        sepgpu_set_error("decomposed step: a neighbour's data never arrived (peer-memory wait %d timed out: 1 migration counts, "
+                         "2 migration records, 3 halo unpack, 4 halo wait in the force kernel, 5 all-gather of the step's sums)",
+                         c->scal_host->error_where);
         return SEPGPU_ENCCL;
     }
     if (c->scal_host->error == SEPGPU_ETABLE) {
