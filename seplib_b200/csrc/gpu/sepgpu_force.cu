@@ -710,7 +710,12 @@ int sepgpu_spec_force_launch(sepgpu_ctx *c)
     // (decomposed runs: measured on two B200s, the launch sent ahead ended in a peer-memory wait that never returned at 1 M
     //  atoms per rank although every smaller test passed -- not understood yet, so it stays off there)
     if (!S.on || S.streak < 3 || (c->dd && S.on != 2) || !c->list_valid || !c->list_f16 || c->fij) return 0;
-    if (!c->f4_alt) CUDA_TRY(cudaMalloc((void **)&c->f4_alt, sizeof(d4) * (size_t)c->ncap));
+    if (!c->f4_alt && cudaMalloc((void **)&c->f4_alt, sizeof(d4) * (size_t)c->ncap) != cudaSuccess) {
+        cudaGetLastError();                              // no room for the spare force array: run without launches sent ahead
+        c->f4_alt = NULL;
+        S.on = 0;
+        return 0;
+    }
     int nrows = 0;
     ktimer_begin(c, &c->t_force);
     const int rc = sepgpu_lj_tile_launch(c, &S.sys, S.P, S.B, S.typed, true, &nrows, c->f4_alt, &c->scal->neighb_flag);
