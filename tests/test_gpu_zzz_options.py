@@ -4,8 +4,9 @@
   fin_multi=1            multi-CTA final reductions          step_fold=1       force reduction + Nose-Hoover update folded
                                                                                into the integrator's kernels
 Same parity bar everywhere: forces 1e-10 of the oracle / the reference's golden vectors, pair sets bit-exact, sums 1e-10,
-and agreement between alternative kernels to rounding over runs with many rebuilds.  All of these ran on a B200
-(round 2, scripts/gpu_r2_ab.sh); the CPU suite runs the same file on the kernel emulator (tests/test_cpu_emu.py).
+and agreement between alternative kernels to rounding over runs with many rebuilds.  All of these run on a B200
+(scripts/gpu_r2_full.sh; A/B records in profiles/r02_optin_ab.txt); the CPU suite runs the same file on the kernel emulator
+(tests/test_cpu_emu.py).  spec_force=1 (default): the step's first force call launched ahead of the host's rebuild decision.
 """
 import ctypes as C
 import os
