@@ -335,6 +335,7 @@ bool sepgpu_dd_gather_next(sepgpu_ctx *c, GatherDev *g)
     return true;
 }
 int sepgpu_dd_uses_p2p(sepgpu_ctx *c) { return c->dd && c->dd->p2p ? 1 : 0; }
+int sepgpu_dd_push_carveout_max(void);
 int sepgpu_dd_nglobal(sepgpu_ctx *c) { return c->dd ? (int)c->n_global : c->n; }
 
 // ---- global id -> local row (own and halo), for the bonded terms: rebuilt lazily after every list build -------------
@@ -983,6 +984,16 @@ __global__ void k_dd_push_xu2(const d4 *__restrict__ x4, const i4 *__restrict__ 
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag1), "l"(seq) : "memory");
         }
     }
+}
+
+// Hypothesis for the open issue with launches sent ahead in decomposed runs (docs/ROUND_NOTES.md): the push kernel asks for
+// the default shared-memory carve-out, the tile force kernel for the largest; an SM changes its carve-out only when it is
+// empty, and a force grid whose ~200 waiting tiles sit on every SM then keeps the push -- which those tiles wait for, on the
+// other GPU -- from ever being placed.  With the same preference the push can share an SM with them.  (Used with
+// spec_force=2 only; not verified on hardware.)
+int sepgpu_dd_push_carveout_max(void)
+{
+    return cudaFuncSetAttribute(k_dd_push_xu2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess ? 0 : SEPGPU_ECUDA;
 }
 
 // waits until both neighbours have delivered refresh number `seq`, then scatters into the halo slots of xs.

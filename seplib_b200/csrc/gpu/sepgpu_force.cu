@@ -703,10 +703,13 @@ static bool spec_same(const sepgpu_ctx::SpecForce &S, const sepgpu_sys *sys, con
 
 // Called by the integrators once their finaliser is queued: launch the step's first force routine for the NEXT step now,
 // guarded by the rebuild flag that finaliser is about to write.  Forces go to the spare array.
+int sepgpu_dd_push_carveout_max(void);
+
 int sepgpu_spec_force_launch(sepgpu_ctx *c)
 {
     sepgpu_ctx::SpecForce &S = c->spec;
     S.launched = false;
+    if (c->dd && S.on == 2 && !c->f4_alt) sepgpu_dd_push_carveout_max();      // (once: f4_alt is allocated below)
     // (decomposed runs: measured on two B200s, the launch sent ahead ended in a peer-memory wait that never returned at 1 M
     //  atoms per rank although every smaller test passed -- not understood yet, so it stays off there)
     if (!S.on || S.streak < 3 || (c->dd && S.on != 2) || !c->list_valid || !c->list_f16 || c->fij) return 0;
