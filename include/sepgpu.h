@@ -239,6 +239,8 @@ int sepgpu_get_option(sepgpu_ctx *ctx, const char *name, long long *value);
  * behind the sep_* API use it with the global ids so that each process touches only its own atoms of the full array. */
 int sepgpu_set_host_rows(sepgpu_ctx *ctx, const int *rows);
 int sepgpu_dd_unique_id(void *out128);
+/* decomposed sep_coulomb_sf: the charges of ALL atoms by global id, on every rank (after sepgpu_dd_init) */
+int sepgpu_dd_set_charges(sepgpu_ctx *ctx, const double *z_global);
 int sepgpu_dd_init(sepgpu_ctx *ctx, int rank, int nranks, const void *id128, const sepgpu_sys *sys, long long n_global);
 int sepgpu_dd_set_owned(sepgpu_ctx *ctx, int n_own);
 int sepgpu_dd_layers(sepgpu_ctx *ctx, int *z0, int *z1, int *n_own, int *n_halo);

@@ -121,7 +121,7 @@ def atoms_view(ptr, n):
 SEPGPU_SYMBOLS = [
     "sepgpu_create", "sepgpu_destroy", "sepgpu_last_error", "sepgpu_device_count", "sepgpu_put",
     "sepgpu_get", "sepgpu_put_fields", "sepgpu_get_fields", "sepgpu_set_topology", "sepgpu_get_bonded_values", "sepgpu_reset_ret",
-    "sepgpu_reset_force", "sepgpu_neighb_build", "sepgpu_force_lj", "sepgpu_force_table", "sepgpu_set_host_rows", "sepgpu_md_lj_nvt", "sepgpu_coulomb_sf",
+    "sepgpu_reset_force", "sepgpu_neighb_build", "sepgpu_force_lj", "sepgpu_force_table", "sepgpu_set_host_rows", "sepgpu_md_lj_nvt", "sepgpu_dd_set_charges", "sepgpu_coulomb_sf",
     "sepgpu_force_dpd", "sepgpu_stretch_harmonic", "sepgpu_angle_harmonic", "sepgpu_angle_cossq",
     "sepgpu_torsion_ryckaert", "sepgpu_nosehoover", "sepgpu_nosehoover_type", "sepgpu_set_alpha",
     "sepgpu_leapfrog", "sepgpu_verlet_dpd", "sepgpu_reset_momentum", "sepgpu_scale_positions",

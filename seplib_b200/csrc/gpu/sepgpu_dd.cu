@@ -116,6 +116,9 @@ struct DDState {
     // bonded terms: global id -> local row of the last rebuild
     int *gmap;
     int gmap_gen;
+    // charges by global id (they never change): the local copy follows ownership and halo membership at every rebuild
+    double *zglob;
+    int z_gen;
 };
 
 extern "C" int sepgpu_dd_unique_id(void *out128)
@@ -309,6 +312,7 @@ void sepgpu_dd_destroy(sepgpu_ctx *c)
     if (d->ipc_base) cudaFree(d->ipc_base);
     if (d->done_ctr) cudaFree(d->done_ctr);
     if (d->gmap) cudaFree(d->gmap);
+    if (d->zglob) cudaFree(d->zglob);
     if (d->ev_ready) cudaEventDestroy(d->ev_ready);
     if (d->ev_halo) cudaEventDestroy(d->ev_halo);
     if (d->comm) g_nccl.CommDestroy(d->comm);
@@ -364,6 +368,48 @@ int sepgpu_dd_gmap(sepgpu_ctx *c, const int **gmap)
     }
     *gmap = d->gmap;
     return 0;
+}
+
+// ---- charges in decomposed runs (sep_coulomb_sf) -------------------------------------------------------------------
+// Every rank holds the charges of ALL atoms by global id (8 B per atom; they are constants of the run); the per-row array
+// the Coulomb kernels read is refilled from it after every rebuild, for own and halo rows alike -- nothing to migrate.
+extern "C" int sepgpu_dd_set_charges(sepgpu_ctx *c, const double *z_global)
+{
+    if (!c || !z_global) return SEPGPU_EINVAL;
+    if (!c->dd) { sepgpu_set_error("dd_set_charges: call sepgpu_dd_init first"); return SEPGPU_ESTATE; }
+    SEPGPU_ENTER(c);
+    DDState *d = c->dd;
+    const size_t ng = (size_t)c->n_global;
+    if (!d->zglob && dmalloc(&d->zglob, ng)) return SEPGPU_ECUDA;
+    CUDA_TRY(cudaMemcpyAsync(d->zglob, z_global, sizeof(double) * ng, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    bool any = false;
+    for (size_t i = 0; i < ng && !any; i++) any = z_global[i] != 0.0;
+    c->have_charge = any;                     // lists in global-index rows from the next build on
+    c->zs_valid = false;
+    c->list_valid = false;
+    d->z_gen = -1;
+    return 0;
+}
+
+__global__ void k_dd_gather_charges(const double *__restrict__ zglob, const int *__restrict__ gid, double *__restrict__ z, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = zglob[gid[i]];
+}
+
+// the per-row charges of the current ownership / halo membership; returns 1 when there are global charges at all
+int sepgpu_dd_refresh_charges(sepgpu_ctx *c)
+{
+    DDState *d = c->dd;
+    if (!d || !d->zglob) return 0;
+    if (d->z_gen != c->list_gen) {
+        if (c->n) k_dd_gather_charges<<<(c->n + 255) / 256, 256, 0, c->stream>>>(d->zglob, c->gid, c->z, c->n);
+        KERNEL_CHECK();
+        d->z_gen = c->list_gen;
+        c->zs_valid = false;
+    }
+    return 1;
 }
 
 void sepgpu_dd_rank(sepgpu_ctx *c, int *rank, int *nranks) { *rank = c->dd->rank; *nranks = c->dd->nranks; }

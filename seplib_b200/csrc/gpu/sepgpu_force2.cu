@@ -17,6 +17,8 @@ struct BoxC { double Lx, Ly, Lz; };
 int sepgpu_finalize_force(sepgpu_ctx *c, int nrows, double scale, int flags);
 int sepgpu_ensure_dpd(sepgpu_ctx *c);
 int sepgpu_need_global_rows(sepgpu_ctx *c, const sepgpu_sys *sys);
+int sepgpu_dd_refresh_charges(sepgpu_ctx *c);
+int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
 
 __device__ __forceinline__ double rsqrt_nr(double x)
 {
@@ -384,7 +386,16 @@ extern "C" int sepgpu_coulomb_sf(sepgpu_ctx *c, const sepgpu_sys *sys, double cf
         int rcb = sepgpu_need_global_rows(c, sys);
         if (rcb) return rcb;
     }
-    if (c->coulomb_kernel == 2 && !c->fij && !c->dd) {
+    if (c->dd) {
+        // decomposed run: per-row charges follow the rebuild (own and halo rows), halo coordinates of this step into xs
+        if (!sepgpu_dd_refresh_charges(c)) {
+            sepgpu_set_error("coulomb_sf: decomposed runs take the charges of all atoms by global id (sepgpu_dd_set_charges)");
+            return SEPGPU_ESTATE;
+        }
+        int rch = sepgpu_dd_halo_update(c, sys);
+        if (rch) return rch;
+    }
+    if ((c->coulomb_kernel == 2 || c->dd) && !c->fij) {
         if (!c->xq) CUDA_TRY(cudaMalloc((void **)&c->xq, sizeof(d4) * (size_t)c->ncap));
         CoulDev P; P.cf2 = cf * cf; P.icf2 = 1.0 / P.cf2; P.twoicf = 2.0 / cf;
         // contiguous ranges of the sorted atoms per CTA, as in the Lennard-Jones list kernel

@@ -33,8 +33,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if os.environ.get("DD_MOL") == "butane":
-        ok = run_butane(rank, world, local, int(os.environ.get("DD_STEPS", "60")))
+    if os.environ.get("DD_MOL") in ("butane", "water"):
+        run_mol = run_butane if os.environ["DD_MOL"] == "butane" else run_water
+        ok = run_mol(rank, world, local, int(os.environ.get("DD_STEPS", "60")))
         dist.destroy_process_group()
         return 0 if ok else 1
     res = run(rank, world, local, NSTEPS, NCELL)
@@ -63,6 +64,32 @@ def run_butane(rank, world, local, nsteps):
     if rank == 0:
         rec, x = dd_mol.single_run(g, gsys, nsteps, device=local)
         ok = dd_mol.check(g, gathered, rec, x, log=lambda m: print(m, file=sys.stderr, flush=True))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    return bool(flag.item())
+
+
+def run_water(rank, world, local, nsteps):
+    """Typed Lennard-Jones on global-index rows, bonds, cos^2 angles and the shifted-force Coulomb sum in a decomposed run
+    (tests/dd_mol.py): the reference's water box tiled 2^3 over `world` slabs against a single-GPU run on rank 0.  Collective."""
+    import dd_mol
+    w = dd_mol.water_system()
+    gsys = capi.make_sys(list(w["L"]), dd_mol.WATER["cf"], dd_mol.WATER["dt"], skin=0.25)
+    n = len(w["x"])
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(capi.dd_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    s = capi.System(int(1.6 * n / world) + int(3.0 * n / gsys.nsubbox[2]) + 1024, device=local)
+    res = dd_mol.water_rank_run(s, w, gsys, rank, world, bytes(idt.cpu().numpy().tobytes()), nsteps)
+    dist.barrier()
+    s.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    ok = True
+    if rank == 0:
+        ok = dd_mol.water_check(w, gathered, dd_mol.water_single_run(w, gsys, nsteps, device=local),
+                                log=lambda m: print(m, file=sys.stderr, flush=True))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     return bool(flag.item())

@@ -64,9 +64,45 @@ def main_butane():
     return 0 if dd_mol.check(g, results, rec, x) else 1
 
 
+def main_water():
+    """python tests/emu/dd_threads.py water [nsteps]: typed LJ + bonds + cos^2 angles + Coulomb in a decomposed run"""
+    import dd_mol
+    nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+    w = dd_mol.water_system()
+    gsys = capi.make_sys(list(w["L"]), dd_mol.WATER["cf"], dd_mol.WATER["dt"], skin=0.25)
+    n = len(w["x"])
+    id_bytes = capi.dd_unique_id()
+    barrier = threading.Barrier(WORLD)
+    results, errs = [None] * WORLD, []
+
+    def rank_main(rank):
+        try:
+            s = capi.System(int(1.6 * n / WORLD) + int(3.0 * n / gsys.nsubbox[2]) + 1024, device=0)
+            results[rank] = dd_mol.water_rank_run(s, w, gsys, rank, WORLD, id_bytes, nsteps)
+            barrier.wait()
+            s.close()
+        except BaseException as e:                              # noqa: BLE001 -- reported by the main thread
+            import traceback
+            sys.stderr.write("rank %d: %s\n" % (rank, traceback.format_exc())); sys.stderr.flush()
+            errs.append((rank, repr(e)))
+            barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(WORLD)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        print("rank failure:", errs)
+        return 1
+    return 0 if dd_mol.water_check(w, results, dd_mol.water_single_run(w, gsys, nsteps)) else 1
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "butane":
         return main_butane()
+    if len(sys.argv) > 1 and sys.argv[1] == "water":
+        return main_water()
     ncell = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 24
     opts = dict(kv.split("=") for kv in sys.argv[3].split(",")) if len(sys.argv) > 3 and sys.argv[3] else {}

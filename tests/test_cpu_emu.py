@@ -67,6 +67,10 @@ def test_two_rank_decomposition_on_the_emulator():
         procs[k] = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "butane", "24"],
                                     stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
                                     env=dict(os.environ, SEPGPU_EMU_NO_IPC=no_ipc, DD_WORLD="2"))
+    # ... and prg3's force sequence with the Coulomb sum (charges by global id) on two slabs against one domain
+    procs["water-peer-memory"] = subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu", "dd_threads.py"), "water", "12"],
+                                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
+                                                  env=dict(os.environ, SEPGPU_EMU_NO_IPC="0", DD_WORLD="2"))
     for k, p in procs.items():
         out, err = p.communicate(timeout=900)
         assert p.returncode == 0 and "-> OK" in out, (k, out[-2000:], err[-2000:])
