@@ -310,6 +310,8 @@ void sep_vector_set(double *vec, size_t length, double value);
 /* ---- samplers (reference include/sepsampler.h): host post-processing of the synchronised data.
  * "sacf", "vacf", "msd", "gh", "profs", "radial", "msacf", "mvacf" and "mgh" write the reference's files in the reference's
  * format (seplib_b200/csrc/host/sep_sampler.c); the remaining names are accepted and record nothing.
+ * With env SEP_SAMPLER_FEEDS=1 (single-GPU runs) "vacf", "msd", "profs", "gh" and "radial" take their sums from the device
+ * (sepgpu_feed_*, include/sepgpu.h) and atoms[] is not downloaded for them; "gh" then leaves atoms[].xtrue untouched.
  * The per-sampler state is private to the library. ----------------------------------------------------- */
 typedef struct {
     sepmol *molptr;

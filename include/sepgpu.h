@@ -200,6 +200,29 @@ int sepgpu_force_x0(sepgpu_ctx *ctx, const sepgpu_sys *sys, char type, double ks
 int sepgpu_fp(sepgpu_ctx *ctx, const sepgpu_sys *sys, double temp, const double *noise4);
 int sepgpu_langevin_gjf(sepgpu_ctx *ctx, const sepgpu_sys *sys, double temp, double alpha, const double *noise4);
 
+/* ---- sampler feeds: what the reference's run-time samplers consume, reduced on the device.
+ * sep_sample (source/sepsampler.c:177-240) hands the host atoms[] to each sampler; behind the sep_* API that costs a download
+ * of the whole array per sample (per STEP for "msd", which follows the atoms across the boundaries itself, :537-552).  The
+ * calls below return the sums those samplers form instead.  Single-domain contexts only (SEPGPU_ESTATE otherwise); all are
+ * stream-synchronising reads and change no simulation state.  The host layer uses them when SEP_SAMPLER_FEEDS=1. */
+/* "vacf" (:658-722): stores v_x of every atom as the next row of a device-resident block of lvec rows; when the block is
+ * full, *completed = 1 and acf_block[t] = sum over atoms and time origins t0 of v_x(t0) v_x(t0 + t), t < lvec <= 768. */
+int sepgpu_feed_vacf(sepgpu_ctx *ctx, int lvec, double *acf_block, int *completed);
+/* "msd" (:555-655): sums[0] = sum |dr|^2, sums[1] = sum |dr|^4, sums[2] = number of atoms, over the atoms of `type`;
+ * fs[i] = sum cos(k[i] dx).  dr is the displacement since the last call with new_origin != 0, unwrapped with the device's own
+ * crossing counters (seppart.crossings) and the box lengths given. */
+int sepgpu_feed_msd(sepgpu_ctx *ctx, int new_origin, char type, const double length[3], int nk, const double *k,
+                    double *sums, double *fs);
+/* "profs" (:1416-1525): nbins slabs along z over [0, lz); out4 = {sum m v_x}[nbins], {sum m}[nbins], {sum m (v_y^2 + v_z^2)}[nbins],
+ * {atoms}[nbins] for the atoms of `type` (FP64 atomics: sums are order-dependent in the last bits).  nbins <= 1024. */
+int sepgpu_feed_profile(sepgpu_ctx *ctx, char type, double lz, int nbins, double *out4);
+/* "gh" (:926-1107): for each wave vector (0, k[n], 0), with e = exp(i k y_true), out16[16 n + ...] = Re, Im of
+ * sum e, sum m e, sum m v_x e, sum m v_y e, sum (m v^2 / 2) e, sum m a_y e, sum m v_y^2 e; then [14] = sum m v^2 / 2, [15] = 0. */
+int sepgpu_feed_fourier(sepgpu_ctx *ctx, double ly, int nwave, const double *k, double *out16);
+/* "radial" (:361-468): counts[lvec][ncomb] of this configuration, bin width lbox / (2 lvec), every pair i < j once, type
+ * combinations (a <= b) in the reference's order; integer counts, identical to the host loop.  All pairs: O(N^2). */
+int sepgpu_feed_radial(sepgpu_ctx *ctx, double lbox, int lvec, int ntypes, const char *types, long long *counts);
+
 /* ---- results -------------------------------------------------------------------------------------- */
 /* stream-synchronising read of the scalar block */
 int sepgpu_read_scalars(sepgpu_ctx *ctx, sepgpu_scalars *out);

@@ -122,6 +122,7 @@ SEPGPU_SYMBOLS = [
     "sepgpu_create", "sepgpu_destroy", "sepgpu_last_error", "sepgpu_device_count", "sepgpu_put",
     "sepgpu_get", "sepgpu_put_fields", "sepgpu_get_fields", "sepgpu_set_topology", "sepgpu_get_bonded_values", "sepgpu_reset_ret",
     "sepgpu_reset_force", "sepgpu_neighb_build", "sepgpu_force_lj", "sepgpu_force_table", "sepgpu_set_host_rows", "sepgpu_md_lj_nvt", "sepgpu_dd_set_charges", "sepgpu_coulomb_sf",
+    "sepgpu_feed_vacf", "sepgpu_feed_msd", "sepgpu_feed_profile", "sepgpu_feed_fourier", "sepgpu_feed_radial",
     "sepgpu_force_dpd", "sepgpu_stretch_harmonic", "sepgpu_angle_harmonic", "sepgpu_angle_cossq",
     "sepgpu_torsion_ryckaert", "sepgpu_nosehoover", "sepgpu_nosehoover_type", "sepgpu_set_alpha",
     "sepgpu_leapfrog", "sepgpu_verlet_dpd", "sepgpu_reset_momentum", "sepgpu_scale_positions",
@@ -274,6 +275,11 @@ def load():
     lib.sepgpu_force_x0.argtypes = [ctx, C.POINTER(GpuSys), C.c_char, C.c_double]
     lib.sepgpu_fp.argtypes = [ctx, C.POINTER(GpuSys), C.c_double, C.c_void_p]
     lib.sepgpu_langevin_gjf.argtypes = [ctx, C.POINTER(GpuSys), C.c_double, C.c_double, C.c_void_p]
+    lib.sepgpu_feed_vacf.argtypes = [ctx, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.sepgpu_feed_msd.argtypes = [ctx, C.c_int, C.c_char, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sepgpu_feed_profile.argtypes = [ctx, C.c_char, C.c_double, C.c_int, C.c_void_p]
+    lib.sepgpu_feed_fourier.argtypes = [ctx, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    lib.sepgpu_feed_radial.argtypes = [ctx, C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_void_p]
     lib.sepgpu_fij_enable.argtypes = [ctx, C.c_int]
     lib.sepgpu_fij_reset.argtypes = [ctx]
     lib.sepgpu_fij_get.argtypes = [ctx, C.c_void_p]

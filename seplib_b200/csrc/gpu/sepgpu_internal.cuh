@@ -79,6 +79,7 @@ struct CellGrid {
 };
 
 struct DDState;            // slab domain decomposition (sepgpu_dd.cu); NULL when the context is not decomposed
+struct FeedState;          // sampler feeds (sepgpu_feeds.cu); NULL until a feed is asked for
 
 // parameters of one Lennard-Jones-family pair call, as the kernels take them (sepgpu_pair.cuh has the arithmetic)
 struct LJDev {
@@ -99,6 +100,7 @@ struct sepgpu_ctx {
     long long n_global;    // atoms of the whole system (sep_nosehoover divides by it)
     int npad;              // ncap rounded up to 32: row stride of the neighbour list
     DDState *dd;
+    FeedState *feeds;
     int *gid;              // global atom id per local atom (decomposed runs only)
     int device;
     cudaStream_t stream;
@@ -233,6 +235,7 @@ struct sepgpu_ctx {
     } spec;
     d4 *f4_alt;
     long long spec_adopted;        // launches adopted so far (tests, sepgpu_get_option)
+    long long feed_calls, get_calls;   // sampler feeds / per-atom downloads served so far (tests, sepgpu_get_option)
     bool scal_cache_valid;         // scal_host holds the block as the last integrator's finaliser left it ...
     unsigned long long scal_cache_seq;     // ... and nothing but readers has entered the library since
     unsigned long long api_seq;    // entries into the library that may change state (SEPGPU_ENTER; readers take themselves out)

@@ -6,6 +6,7 @@
 #include <functional>
 
 void sepgpu_dd_destroy(sepgpu_ctx *c);
+void sepgpu_feeds_destroy(sepgpu_ctx *c);
 int sepgpu_dd_reduce_force_scalars(sepgpu_ctx *c, double *epot, double *ecoul, double *pot_P, double *pot_P_bond);
 
 static thread_local char g_err[512] = "";
@@ -132,6 +133,7 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     sepgpu_dd_destroy(c);
+    sepgpu_feeds_destroy(c);
     if (c->gid) cudaFree(c->gid);
     if (c->fij) cudaFree(c->fij);
     if (c->cls) cudaFree(c->cls);
@@ -490,6 +492,7 @@ extern "C" int sepgpu_get_fields(sepgpu_ctx *c, void *base, size_t stride, int n
     if (!c || !base || nfields <= 0 || nfields > SEPGPU_MAX_FIELDS || !fields) return SEPGPU_EINVAL;
     SEPGPU_ENTER(c);
     SEPGPU_BENIGN(c);
+    c->get_calls++;
     const size_t n = (size_t)c->n_own;
     size_t row[SEPGPU_MAX_FIELDS], off[SEPGPU_MAX_FIELDS], hoff[SEPGPU_MAX_FIELDS], total = 0;
     for (int f = 0; f < nfields; f++) {
@@ -769,6 +772,8 @@ extern "C" int sepgpu_get_option(sepgpu_ctx *c, const char *name, long long *val
     else if (!strcmp(name, "step_fold")) *value = c->step_fold;
     else if (!strcmp(name, "spec_force")) *value = c->spec.on;
     else if (!strcmp(name, "spec_adopted")) *value = c->spec_adopted;
+    else if (!strcmp(name, "feed_calls")) *value = c->feed_calls;          // sampler feeds served so far (sepgpu_feeds.cu)
+    else if (!strcmp(name, "get_calls")) *value = c->get_calls;            // per-atom downloads served so far (sepgpu_get_fields)
     else if (!strcmp(name, "list_f16")) *value = c->list_valid && c->list_f16 ? 1 : 0;       // rows of 16-bit tile slots
     else if (!strcmp(name, "tile_R")) *value = c->tile_R;
     else if (!strcmp(name, "tile_stage")) *value = c->tile_stage_used;

@@ -16,6 +16,13 @@
  *                                              -> mgh-wavevector.dat mgh-*-acf.dat mgh-*-ccf.dat (:1110-1415)
  * "mprofs", "mcacf", "mavacf", "mmsd" and "scatt" are accepted and record nothing (one warning each).
  *
+ * Sampler feeds (SEP_SAMPLER_FEEDS=1, single-GPU runs): "vacf", "msd", "profs", "gh" and "radial" take their per-sample sums
+ * from the device (include/sepgpu.h, sepgpu_feed_*) instead of reading atoms[] -- no download of the array per sample, and
+ * none per step for "msd", whose boundary tracking is replaced by the device's own crossing counters.  Same files, same
+ * numbers to printed precision ("radial" exactly: integer counts).  Off by default this round: the feed kernels were
+ * written after the round's GPU budget was spent (tests/test_gpu_zzzz_feeds.py compares both paths on hardware).
+ * Not taken over in feed mode: the side effect of "gh" on atoms[].xtrue (sep_eval_xtrue on the host copy).
+ *
  * All correlation samplers share one block accumulator: lvec rows of ncol channels are collected, then every
  * channel's products x[t0] x[t0+t] are added to acf[t] and the file is rewritten.
  */
@@ -23,6 +30,16 @@
 
 #include <complex.h>
 #include <math.h>
+
+static int feeds_enabled(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SEP_SAMPLER_FEEDS");
+        v = e && atoi(e) > 0 ? 1 : 0;
+    }
+    return v;
+}
 
 /* ---- block correlation accumulator ------------------------------------------------------------------- */
 typedef struct {
@@ -198,6 +215,31 @@ static const fk_corr_spec GH_CORR[] = {
     {"gh-long-momentum-energy-ccf.dat", GH_E, 0, 1, GH_LV, 1, 0, 0},
     {"gh-X-acf.dat", GH_X, 0, 0, GH_LV, 1, 1, 0},
 };
+
+/* the same fields from the device's Fourier sums (sepgpu_feed_fourier): S1 = sum e, Sm = sum m e, ... with e = exp(+i k y);
+ * the -k fields are the conjugates, except that the auxiliary field keeps -i k on both sides (:975-977) */
+static void sample_gh_feed(sep_fkacc *g, sep_binding *b, sepsys *sys)
+{
+    const unsigned t = g->fill;
+    double *o = sep_vector((size_t)16 * g->nwave);
+    sepb_check(sepgpu_feed_fourier(b->gpu, sys->length[1], (int)g->nwave, g->k, o), "gh sampler feed");
+    g->ncalls++;
+    g->avekin += o[14] / (sys->npart * g->ncalls);
+    for (unsigned n = 0; n < g->nwave; n++) {
+        const double *q = o + 16 * (size_t)n;
+        const double complex S1 = q[0] + I * q[1], Sm = q[2] + I * q[3], Stv = q[4] + I * q[5], Slv = q[6] + I * q[7],
+                             Se = q[8] + I * q[9], Sa = q[10] + I * q[11], Svv = q[12] + I * q[13];
+        const double complex E = Se - g->avekin * S1;
+        fk_field(g, GH_RHO, 0, t)[n] = Sm;  fk_field(g, GH_RHO, 1, t)[n] = conj(Sm);
+        fk_field(g, GH_TV, 0, t)[n] = Stv;  fk_field(g, GH_TV, 1, t)[n] = conj(Stv);
+        fk_field(g, GH_LV, 0, t)[n] = Slv;  fk_field(g, GH_LV, 1, t)[n] = conj(Slv);
+        fk_field(g, GH_E, 0, t)[n] = E;     fk_field(g, GH_E, 1, t)[n] = conj(E);
+        fk_field(g, GH_X, 0, t)[n] = Sa - I * g->k[n] * Svv;
+        fk_field(g, GH_X, 1, t)[n] = conj(Sa) - I * g->k[n] * conj(Svv);
+    }
+    free(o);
+    fk_push(g, "sep_gh_sampler", sys->volume);
+}
 
 static void sample_gh(sep_fkacc *g, seppart *atoms, sepsys *sys)
 {
@@ -466,6 +508,17 @@ static void sample_vacf(sep_corr *c, const seppart *atoms, const sepsys *sys)
     if (corr_push(c)) write_acf("vacf.dat", c, 1.0, (size_t)sys->npart);
 }
 
+/* the device keeps the block's rows; a completed block comes back already summed over atoms and time origins */
+static void sample_vacf_feed(sep_corr *c, sep_binding *b, const sepsys *sys)
+{
+    int done = 0;
+    sepb_check(sepgpu_feed_vacf(b->gpu, (int)c->lvec, c->rows, &done), "vacf sampler feed");
+    if (!done) return;
+    for (unsigned t = 0; t < c->lvec; t++) c->acf[t] += c->rows[t];
+    c->nblocks++;
+    write_acf("vacf.dat", c, 1.0, (size_t)sys->npart);
+}
+
 static void sample_msacf(sep_corr *c, seppart *atoms, sepmol *mols, sepret *ret, sepsys *sys)
 {
     sep_mol_pressure_tensor(atoms, mols, ret, sys);
@@ -487,14 +540,22 @@ static void sample_mvacf(sep_corr *c, seppart *atoms, sepmol *mols, sepsys *sys)
     if (corr_push(c)) write_acf("mvacf.dat", c, 1.0, nmol);
 }
 
-static void sample_profs(sep_profile *p, const seppart *atoms, const sepsys *sys)
+static void sample_profs(sep_profile *p, const seppart *atoms, const sepsys *sys, sep_binding *feed)
 {
     const int dir = 2, dirvel = 0;                                             /* fixed in the reference, :1430-1431 */
     const double dl = sys->length[dir] / p->lvec;
     const double dV = sys->length[0] * sys->length[1] * dl;
     double *j = sep_vector(p->lvec), *rho = sep_vector(p->lvec), *sumv2 = sep_vector(p->lvec);
     int *numb = sep_vector_int(p->lvec);
-    for (long n = 0; n < sys->npart; n++) {
+    if (feed) {                                                                /* the slab sums, formed on the device */
+        double *o = sep_vector((size_t)4 * p->lvec);
+        sepb_check(sepgpu_feed_profile(feed->gpu, p->type, sys->length[dir], (int)p->lvec, o), "profs sampler feed");
+        for (unsigned n = 0; n < p->lvec; n++) {
+            j[n] = o[n]; rho[n] = o[p->lvec + n]; sumv2[n] = o[2 * p->lvec + n]; numb[n] = (int)o[3 * p->lvec + n];
+        }
+        free(o);
+    }
+    else for (long n = 0; n < sys->npart; n++) {
         if (atoms[n].type != p->type) continue;
         int i = (int)(atoms[n].x[dir] / dl);
         if (i < 0) i = 0;
@@ -530,12 +591,20 @@ static void sample_profs(sep_profile *p, const seppart *atoms, const sepsys *sys
     }
 }
 
-static void sample_radial(sep_rdf *r, const seppart *atoms, const sepsys *sys)
+static void sample_radial(sep_rdf *r, const seppart *atoms, const sepsys *sys, sep_binding *feed)
 {
     const long npart = sys->npart;
     const double lbox = sys->length[0];
     const double dg = 0.5 * lbox / r->lvec;
-    for (long i = 0; i < npart - 1; i++)
+    if (feed) {                                                                /* this configuration's counts from the device */
+        const size_t nb = (size_t)r->lvec * r->ncomb;
+        long long *cnt = malloc(nb * sizeof *cnt);
+        if (!cnt) sep_error("sep_radial_sample: Couldn't allocate memory");
+        sepb_check(sepgpu_feed_radial(feed->gpu, lbox, r->lvec, r->ntypes, r->types, cnt), "radial sampler feed");
+        for (size_t q = 0; q < nb; q++) r->hist[q] += (long)cnt[q];
+        free(cnt);
+    }
+    else for (long i = 0; i < npart - 1; i++)
         for (long jx = i + 1; jx < npart; jx++) {
             double r2 = 0.0;
             for (int k = 0; k < 3; k++) {
@@ -579,16 +648,25 @@ static void msd_track(sep_msdacc *m, const seppart *atoms, const sepsys *sys)
         }
 }
 
-static void msd_take(sep_msdacc *m, const seppart *atoms, const sepsys *sys)
+static void msd_take(sep_msdacc *m, const seppart *atoms, const sepsys *sys, sep_binding *feed)
 {
     int index = m->fill;
+    double sd = 0.0, qd = 0.0;
+    int ntype_feed = 0;
+    if (feed) {                 /* sums from the device; its crossing counters stand in for msd_track's (origin reset at index 0) */
+        double sums[3], *fsv = sep_vector((size_t)(m->nk > 0 ? m->nk : 1));
+        sepb_check(sepgpu_feed_msd(feed->gpu, index == 0, m->type, sys->length, m->nk, m->k, sums, fsv), "msd sampler feed");
+        sd = sums[0]; qd = sums[1]; ntype_feed = (int)sums[2];
+        for (int i = 0; i < m->nk; i++) m->fs[(size_t)index * m->nk + i] += fsv[i];
+        free(fsv);
+    }
+    else {
     if (index == 0)
         for (long n = 0; n < sys->npart; n++)
             for (int k = 0; k < 3; k++) {
                 m->prev[3 * n + k] = m->pos0[3 * n + k] = atoms[n].x[k];
                 m->cross[3 * n + k] = 0;
             }
-    double sd = 0.0, qd = 0.0;
     for (long n = 0; n < sys->npart; n++) {
         if (atoms[n].type != m->type) continue;
         double a = 0.0, dx0 = 0.0;
@@ -601,12 +679,13 @@ static void msd_take(sep_msdacc *m, const seppart *atoms, const sepsys *sys)
         qd += a * a;
         for (int i = 0; i < m->nk; i++) m->fs[(size_t)index * m->nk + i] += cos(m->k[i] * dx0);    /* Re exp(i k dx) */
     }
+    }
     m->msd[index] += sd;
     m->msdsq[index] += qd;
     index++;
     if (index == m->lvec) {
         m->nsample++;
-        const int ntype = sep_count_type((seppart *)atoms, m->type, m->npart);
+        const int ntype = feed ? ntype_feed : sep_count_type((seppart *)atoms, m->type, m->npart);
         const double norm = (double)ntype * m->nsample;
         FILE *fout = fopen("msd.dat", "w");
         if (!fout) sep_error("sep_msd_sample: Couldn't open file");
@@ -636,23 +715,29 @@ void sep_sample(seppart *pptr, sepsampler *sptr, sepret *ret, sepsys sys, unsign
 {
     struct sep_sampler_set *S = (struct sep_sampler_set *)sptr->impl;
     if (!S) return;
-    if ((S->vacf && n % S->vacf->isample == 0) || (S->profs && n % S->profs->isample == 0) || (S->gh && n % S->gh->isample == 0) ||
-        (S->radial && n % (unsigned)S->radial->isample == 0) || S->msd)
+    /* sampler feeds: the device forms the sums, atoms[] stays where it is (pending host writes are uploaded first) */
+    sep_binding *feed = NULL;
+    if (feeds_enabled() && sepdd_world() <= 1 && (S->vacf || S->profs || S->gh || S->radial || S->msd)) {
+        feed = sepb_prepare(pptr, &sys);
+        if (!feed->gpu || feed->dd) feed = NULL;
+    }
+    if (!feed && ((S->vacf && n % S->vacf->isample == 0) || (S->profs && n % S->profs->isample == 0) || (S->gh && n % S->gh->isample == 0) ||
+        (S->radial && n % (unsigned)S->radial->isample == 0) || S->msd))
         sep_gpu_sync(pptr);                                    /* the samplers below read atoms[] on the host */
     if (S->sacf && n % S->sacf->isample == 0) sample_sacf(S->sacf, ret, &sys);
-    if (S->vacf && n % S->vacf->isample == 0) sample_vacf(S->vacf, pptr, &sys);
+    if (S->vacf && n % S->vacf->isample == 0) { if (feed) sample_vacf_feed(S->vacf, feed, &sys); else sample_vacf(S->vacf, pptr, &sys); }
     if (S->msacf && n % S->msacf->isample == 0) sample_msacf(S->msacf, pptr, sptr->molptr, ret, &sys);
-    if (S->gh && n % S->gh->isample == 0) sample_gh(S->gh, pptr, &sys);
+    if (S->gh && n % S->gh->isample == 0) { if (feed) sample_gh_feed(S->gh, feed, &sys); else sample_gh(S->gh, pptr, &sys); }
     if (S->mgh && n % S->mgh->isample == 0) sample_mgh(S->mgh, pptr, sptr->molptr, &sys);
-    if (S->profs && n % S->profs->isample == 0) sample_profs(S->profs, pptr, &sys);
+    if (S->profs && n % S->profs->isample == 0) sample_profs(S->profs, pptr, &sys, feed);
     if (S->mvacf && n % S->mvacf->isample == 0) sample_mvacf(S->mvacf, pptr, sptr->molptr, &sys);
-    if (S->radial && n % (unsigned)S->radial->isample == 0) sample_radial(S->radial, pptr, &sys);
+    if (S->radial && n % (unsigned)S->radial->isample == 0) sample_radial(S->radial, pptr, &sys, feed);
     if (S->msd) {                                              /* source/sepsampler.c:213-231 */
         sep_msdacc *m = S->msd;
-        msd_track(m, pptr, &sys);
-        if (!m->logmode && n % (unsigned)m->isample == 0) msd_take(m, pptr, &sys);
+        if (!feed) msd_track(m, pptr, &sys);
+        if (!m->logmode && n % (unsigned)m->isample == 0) msd_take(m, pptr, &sys, feed);
         else if (m->logmode && sptr->msd_counter % (unsigned long)m->logcounter == 0) {
-            msd_take(m, pptr, &sys);
+            msd_take(m, pptr, &sys, feed);
             m->logcounter = m->fill == 0 ? 1 : 2 * m->logcounter;
         }
         sptr->msd_counter++;

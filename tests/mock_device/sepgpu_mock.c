@@ -522,6 +522,16 @@ long long sepgpu_get_pairs(sepgpu_ctx *c, int *pairs, long long max_pairs)
 }
 
 /* SEP_NGPU needs real devices: the mock only satisfies the linker */
+/* sampler feeds: the mock keeps no device-side sampler state (the host samplers run on the synchronised atoms[] here) */
+static int no_feed(void) { set_error("mock device: no sampler feeds"); return SEPGPU_ESTATE; }
+int sepgpu_feed_vacf(sepgpu_ctx *c, int lvec, double *acf_block, int *completed) { (void)c; (void)lvec; (void)acf_block; (void)completed; return no_feed(); }
+int sepgpu_feed_msd(sepgpu_ctx *c, int new_origin, char type, const double length[3], int nk, const double *k, double *sums, double *fs)
+{ (void)c; (void)new_origin; (void)type; (void)length; (void)nk; (void)k; (void)sums; (void)fs; return no_feed(); }
+int sepgpu_feed_profile(sepgpu_ctx *c, char type, double lz, int nbins, double *out4) { (void)c; (void)type; (void)lz; (void)nbins; (void)out4; return no_feed(); }
+int sepgpu_feed_fourier(sepgpu_ctx *c, double ly, int nwave, const double *k, double *out16) { (void)c; (void)ly; (void)nwave; (void)k; (void)out16; return no_feed(); }
+int sepgpu_feed_radial(sepgpu_ctx *c, double lbox, int lvec, int ntypes, const char *types, long long *counts)
+{ (void)c; (void)lbox; (void)lvec; (void)ntypes; (void)types; (void)counts; return no_feed(); }
+
 int sepgpu_set_host_rows(sepgpu_ctx *c, const int *rows) { (void)c; return rows ? SEPGPU_ESTATE : 0; }
 int sepgpu_dd_unique_id(void *out128) { (void)out128; set_error("mock device: no decomposition"); return SEPGPU_ESTATE; }
 int sepgpu_dd_init(sepgpu_ctx *c, int rank, int nranks, const void *id128, const sepgpu_sys *sys, long long n_global)

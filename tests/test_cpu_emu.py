@@ -48,6 +48,13 @@ def test_kernel_options_pass_on_the_emulator():
     assert n >= 25, n
 
 
+def test_sampler_feeds_pass_on_the_emulator():
+    """The sampler feeds (tests/test_gpu_zzzz_feeds.py): every feed against numpy on the downloaded arrays, and a sampled
+    run through the sep_* API with SEP_SAMPLER_FEEDS=1 against the host samplers (same files, no download of atoms[])."""
+    n = _run(["tests/test_gpu_zzzz_feeds.py", "-m", "gpu", "-q", "-n", WORKERS, "-p", "no:cacheprovider"])
+    assert n >= 6, n
+
+
 def test_two_rank_decomposition_on_the_emulator():
     """Slab decomposition with two ranks as two THREADS on the emulated kernels (tests/emu/dd_threads.py): union of the
     ranks' pair sets == single-domain set, per-step sums, trigger steps, final positions, atom conservation over several
