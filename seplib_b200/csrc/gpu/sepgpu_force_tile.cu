@@ -19,6 +19,7 @@
 #include "sepgpu_tile.cuh"
 
 int sepgpu_dd_halo_update(sepgpu_ctx *c, const sepgpu_sys *sys);
+int sepgpu_dd_before_positions_change(sepgpu_ctx *c);
 
 // One listed pair.  Coordinates arrive divided by sigma, so 1/r^2 needs no rescaling; 48 eps / sigma is applied once per
 // atom.  19 FP64 instructions: 3 sub, 3 for r^2, 3 for 1/r^2 (MUFU seed + one third-order step), 2 for its cube,
@@ -289,6 +290,10 @@ int sepgpu_lj_tile_launch(sepgpu_ctx *c, const sepgpu_sys *sys, const LJDev &P, 
         int rh = sepgpu_dd_halo_args(c, sys, &H);
         if (rh < 0) return rh;
         if (rh == 0 && (rh = sepgpu_dd_halo_update(c, sys))) return rh;
+        // launch sent ahead in a decomposed run (spec_force=2, experimental): this grid and my push become runnable on the
+        // same event; ordering the grid behind the push means my neighbours' waiting tiles never depend on a push that
+        // sits behind my own waiting tiles (docs/ROUND_NOTES.md, open issue; not verified on hardware)
+        if (cancel && c->spec.on == 2 && (rh = sepgpu_dd_before_positions_change(c))) return rh;
     }
     H.cancel = cancel;
     d4 *const f4 = f_out ? f_out : c->f4;
