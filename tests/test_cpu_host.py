@@ -145,6 +145,58 @@ def test_oracle_pairs_and_forces_vs_reference_live(skin, opt):
     s.close()
 
 
+def _edge_systems():
+    """the inputs of tests/test_gpu_zzzz_edge.py: three different box edges, a half-empty box, atoms exactly on the box faces"""
+    a = np.array([1.30, 1.05, 0.95]); cells = (9, 12, 16)
+    g = [(np.arange(cells[k]) + 0.5) * a[k] for k in range(3)]
+    z, y, x = np.meshgrid(g[2], g[1], g[0], indexing="ij")
+    length = a * np.array(cells)
+    rng = np.random.default_rng(72)
+    pos = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    pos = np.mod(pos + rng.uniform(-0.12, 0.12, size=pos.shape) * a, length)
+    pos[pos >= length] = 0.0
+    yield "edges", np.ascontiguousarray(pos), length
+    x, L = cm.lattice(14, 0.8, jitter=0.1, seed=73)
+    yield "slab", np.ascontiguousarray(x[x[:, 2] < 0.5 * L]), np.array([L] * 3)
+    x, L = cm.lattice(12, 0.8, jitter=0.1, seed=75)
+    below = np.nextafter(L, 0.0)
+    x[0] = [0.0, 0.0, 0.0]; x[1] = [below, below, L - 1.0]; x[2] = [0.0, below, 1.2]; x[3] = [below, 0.0, L - 2.1]
+    d = x[None, :4, :] - x[4:, None, :]
+    d -= L * np.round(d / L)
+    keep = np.ones(len(x), dtype=bool)
+    keep[4:] = (np.linalg.norm(d, axis=2) > 0.8).all(axis=1)
+    yield "faces", np.ascontiguousarray(x[keep]), np.array([L] * 3)
+
+
+@needs_ref
+def test_oracle_edge_cases_vs_reference_live():
+    """The oracle against the compiled reference on the edge-case inputs the GPU parity tests use (same pairs in the same
+    row order, bit-identical forces and sums), so that those GPU tests are pinned to the reference and not to the port."""
+    r = cm.ref()
+    orc = cm.oracle()
+    for name, x, length in _edge_systems():
+        n = len(x)
+        rng = np.random.default_rng(len(name))
+        types = np.where(rng.random(n) < 0.35, ord("B"), ord("A")).astype(np.uint8)
+        s = cm.ApiSystem(r, x, length, 2.5, 0.005, types=types)
+        for tsel in (b"AA", b"AB", b"XX"):
+            r.sep_reset_retval(s.R); r.sep_reset_force(s.atoms, s.S)
+            r.sep_force_pairs(s.atoms, tsel, 2.5, s.fun("sep_lj_shift"), s.S, s.R, 1)
+            ref_pairs = s.neighb_pairs()
+            raw = cm.oracle_pairs(x, length, 2.5, 0.25, max_pairs=80 * n + 4096)
+            assert np.array_equal(raw, ref_pairs), name
+            f = np.zeros((n, 3)); ret = cm.OrcRet(); lv = cm.dvec3(length)
+            pp = np.ascontiguousarray(raw, dtype=np.int32)
+            orc.orc_force_pairs_list(n, cm.ptr(x), cm.ptr(types), cm.ptr(lv), cm.ptr(pp), len(pp), tsel, 2.5, cm.POT_LJ_SHIFT,
+                                     None, cm.ptr(f), C.byref(ret))
+            assert np.array_equal(f, s.view["f"]), (name, tsel)
+            assert ret.epot == s.ret.epot, (name, tsel)
+            assert np.array_equal(np.array(ret.pot_P[:]), np.array(s.ret.pot_P).reshape(9)), (name, tsel)
+            if tsel == b"XX":
+                assert not f.any() and ret.epot == 0.0
+        s.close()
+
+
 @needs_ref
 def test_oracle_coulomb_list_and_nosehoover_type_vs_reference_live():
     r = cm.ref()
