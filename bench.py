@@ -636,6 +636,50 @@ def run_molecular(args, emit, local_rank):
 
 
 # ---------------------------------------------------------------------------------------------------
+def sampled_run_record(ncell=46, steps=300, timeout_s=90):
+    """prg1's kind of run -- the NVT loop WITH run-time samplers (vacf, sacf, msd every step, profs, gh) -- through the sep_*
+    API, once with the samplers reading atoms[] on the host (what an unchanged program gets: a download per sample) and once
+    fed from the device (SEP_SAMPLER_FEEDS=1, sepgpu_feeds.cu).  Each run is its own process (tests/feeds_driver.py) under a
+    timeout; whatever goes wrong ends up in the record, never in the bench line's own numbers."""
+    import tempfile
+    rec = {"workload": "two-species LJ NVT + samplers vacf sacf msd profs gh through sep_* (SEP_SYNC=auto)", "steps": steps}
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            outs = {}
+            for name, flag in (("host_samplers", "0"), ("device_feeds", "1")):
+                env = dict(os.environ, SEP_SAMPLER_FEEDS=flag, FEEDS_NCELL=str(ncell), FEEDS_SAMPLERS="vacf,sacf,msd,profs,gh")
+                env.pop("SEP_SYNC", None)
+                out = os.path.join(td, name)
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "feeds_driver.py"), out, str(steps)],
+                                   capture_output=True, text=True, timeout=timeout_s, env=env)
+                if r.returncode != 0:
+                    rec[name] = {"error": (r.stderr or r.stdout)[-300:]}
+                    continue
+                w = r.stdout.split()
+                get = lambda k: w[w.index(k) + 1]            # noqa: E731
+                n, secs = int(get("natoms")), float(get("loop_s"))
+                rec["natoms"] = n
+                rec[name] = {"value": n * steps / secs, "unit": UNIT, "ms_per_step": secs * 1e3 / steps,
+                             "atoms_downloads": int(get("get_calls")), "feed_calls": int(get("feed_calls"))}
+                outs[name] = out
+            if len(outs) == 2:
+                worst = 0.0
+                files = sorted(f for f in os.listdir(outs["host_samplers"]) if f.endswith(".dat"))
+                for f in files:
+                    a = np.loadtxt(os.path.join(outs["host_samplers"], f), ndmin=2)
+                    b = np.loadtxt(os.path.join(outs["device_feeds"], f), ndmin=2)
+                    if a.shape != b.shape:
+                        worst = float("inf")
+                        break
+                    if a.size:
+                        worst = max(worst, float(np.nanmax(np.abs(a - b))))
+                rec["files_compared"] = len(files)
+                rec["max_abs_difference_between_the_files"] = worst
+    except Exception as e:      # noqa: BLE001
+        rec["error"] = repr(e)
+    return rec
+
+
 def weak_lattice_dims(ncell, world, box="cubic"):
     """Lattice sides for `world` GPUs at ncell^3 atoms per GPU (weak scaling, near-cubic box, z longest):
     1 -> n,n,n ; 2 -> n,n,2n ; 4 -> n,2n,2n ; 8 -> 2n,2n,2n.  box="stacked": n,n,world*n (the cross-section a slab
@@ -1054,7 +1098,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
         if not args.no_cpu_matrix:
             cpu["matrix"] = cpu_matrix(args.rho, rc, dt, temp, tau, 2.5, skip_big=False)
-    other = None
+    other = sampled = None
     if world == 1 and not args.no_other:
         # short runs of the C2 / C3 configurations (device loop only), so that the driver's record carries them too
         import copy
@@ -1073,6 +1117,7 @@ def main():
                               "kernel_ms": g["kernel_ms"]})
             except Exception as e:      # noqa: BLE001
                 other.append({"workload": wname, "value": None, "error": repr(e)})
+        sampled = sampled_run_record()
 
     # kernels of this rank in the timed region: force, finalize, nh_update, integrate, finalize (+ lazy resets);
     # decomposed: + halo push and wait/unpack (peer-memory path); per rebuild: set_xn + 10 build kernels (+ ~25 migration/halo)
@@ -1100,6 +1145,8 @@ def main():
     }
     if other is not None:
         line["other_workloads"] = other
+    if sampled is not None:
+        line["sampled_run"] = sampled
     if dd_check is not None:
         line["dd_check"] = dd_check
     emit(line)
