@@ -680,6 +680,60 @@ def sampled_run_record(ncell=46, steps=300, timeout_s=90):
     return rec
 
 
+def nested_dd_check(mol="water", steps=40, timeout_s=150):
+    """A two-rank decomposed MOLECULAR run checked against a single-GPU run (tests/dd_check.py DD_MOL=..., tests/dd_mol.py),
+    launched as a torchrun job of its own after this bench's process group is gone: the scaling record then carries a
+    decomposed-vs-single comparison of sep_coulomb_sf + typed LJ + bonds + angles on real GPUs.  Own session, own timeout,
+    own rendezvous port; its outcome is a record, never an error of the bench."""
+    import signal
+    import socket
+    import uuid
+    rec = {"check": f"two-rank decomposed {mol} ({steps} steps) against the same calls on one GPU: first-step forces 1e-10, sums, final positions"}
+    t0 = time.perf_counter()
+    try:
+        drop = {"RANK", "LOCAL_RANK", "GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_WORLD_SIZE",
+                "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"}
+        env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC") and not k.startswith("TORCH_NCCL")}
+        marker = uuid.uuid4().hex
+        env.update(DD_MOL=mol, DD_STEPS=str(steps), SEPB_NESTED_RUN=marker)
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        p = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                              "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dd_check.py")],
+                             env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+        try:
+            out, _ = p.communicate(timeout=timeout_s)
+            rec["ok"] = p.returncode == 0 and "-> OK" in out
+            lines = out.splitlines()
+            keep = [ln for ln in lines if "dd_mol" in ln and "-> " in ln] or \
+                   [ln for ln in lines if "Error" in ln and "ChildFailedError" not in ln]
+            rec["tail"] = (keep[-1] if keep else out[-300:])[-400:]
+        except subprocess.TimeoutExpired:
+            rec["ok"] = False
+            rec["tail"] = f"no answer within {timeout_s} s"
+            try:
+                os.killpg(p.pid, signal.SIGKILL)
+            except OSError:
+                pass
+            for pid in os.listdir("/proc"):             # workers the launcher may have put into sessions of their own
+                if pid.isdigit():
+                    try:
+                        if ("SEPB_NESTED_RUN=" + marker).encode() in open(f"/proc/{pid}/environ", "rb").read():
+                            os.kill(int(pid), signal.SIGKILL)
+                    except OSError:
+                        pass
+            try:
+                p.communicate(timeout=10)
+            except Exception:      # noqa: BLE001
+                pass
+    except Exception as e:      # noqa: BLE001
+        rec["ok"] = False
+        rec["tail"] = repr(e)
+    rec["seconds"] = time.perf_counter() - t0
+    return rec
+
+
 def weak_lattice_dims(ncell, world, box="cubic"):
     """Lattice sides for `world` GPUs at ncell^3 atoms per GPU (weak scaling, near-cubic box, z longest):
     1 -> n,n,n ; 2 -> n,n,2n ; 4 -> n,2n,2n ; 8 -> 2n,2n,2n.  box="stacked": n,n,world*n (the cross-section a slab
@@ -1149,9 +1203,12 @@ def main():
         line["sampled_run"] = sampled
     if dd_check is not None:
         line["dd_check"] = dd_check
-    emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if decomposed and world == 2 and not args.no_other:
+        # the other rank has left (it returns right after the e2e arm): both GPUs are free for a two-rank job of its own
+        line["dd_water_check"] = nested_dd_check("water")
+    emit(line)
     return 0
 
 
