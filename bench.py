@@ -734,6 +734,70 @@ def nested_dd_check(mol="water", steps=40, timeout_s=150):
     return rec
 
 
+def own_run_at_size(ncell, rho=0.8, steps=2000, warmup=300):
+    """this library's prg1-style loop (FP64, NVT, C-driven) at ncell^3 atoms on the current device: the same-size line
+    next to the reference's CUDA path (reference_cuda_baseline)"""
+    from seplib_b200 import capi
+    lib = capi.load()
+    x, L = lj_lattice(ncell, rho)
+    v = lj_velocities(len(x), 1.0, seed=5)
+    s = capi.System(len(x))
+    try:
+        s.put(capi.F_X, x); s.put(capi.F_V, v)
+        s.call("sepgpu_set_alpha", 0, 0.1)
+        gs = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
+        lj = capi.lj_param(2.5, kind="lj_shift")
+        for k in (warmup, steps):
+            t0 = time.perf_counter()
+            if lib.sepgpu_md_lj_nvt(s.ctx, C.byref(gs), b"AA", C.byref(lj), 1, 1.0, 0, 0.01, k):
+                raise RuntimeError(lib.sepgpu_last_error().decode())
+            epot = s.scalars().epot          # a synchronising read
+            secs = time.perf_counter() - t0
+        return {"value": len(x) * steps / secs, "unit": UNIT, "dtype": "f64", "natoms": len(x), "steps": steps, "seconds": secs,
+                "steps_per_s": steps / secs, "epot_per_atom": epot / len(x),
+                "sample": "sepgpu_md_lj_nvt (force + Nose-Hoover + leapfrog, list mode, skin 0.25), wall clock around the C loop"}
+    finally:
+        s.close()
+
+
+def reference_cuda_baseline(ncell=30, rho=0.8, steps=2000, warmup=300, timeout_s=90):
+    """The reference's OWN CUDA Lennard-Jones path (reference cuda/sepcuda*.cu: single precision, all-pairs list build) on
+    this GPU, at the largest size of its own benchmark table (27 000 atoms, reference cuda/notes.txt) and with the loop of
+    its benchmark program (cuda/tgpu_0.cu:17-29) -- oracle/_ref/refcuda_lj, built by oracle/Makefile from the reference
+    sources where they lie.  A second stated baseline beside the CPU one; a process of its own under a timeout."""
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "refcuda_lj")
+    rec = {"kind": "reference cuda/ (sep_cuda_* API, FP32), loop of cuda/tgpu_0.cu", "unit": UNIT, "dtype": "f32"}
+    if not os.path.exists(exe):
+        rec["unavailable"] = "oracle/_ref/refcuda_lj not built (needs the reference tree at build time)"
+        return rec
+    try:
+        x, L = lj_lattice(ncell, rho)
+        v = lj_velocities(len(x), 1.0, seed=5)
+        with tempfile.TemporaryDirectory() as td:
+            start = os.path.join(td, "start.xyz")
+            with open(start, "w") as fh:
+                fh.write("%d\n%f %f %f\n" % (len(x), L, L, L))
+                for (a, b, c), (va, vb, vc) in zip(x, v):
+                    fh.write("A %f %f %f %f %f %f 1.000000 0.000000\n" % (a, b, c, va, vb, vc))
+            r = subprocess.run([exe, start, str(steps), str(warmup)], capture_output=True, text=True, timeout=timeout_s, cwd=td)
+        if r.returncode != 0:
+            rec["unavailable"] = ("rc %d: " % r.returncode) + (r.stderr or r.stdout)[-200:]
+            return rec
+        w = r.stdout.split()
+        n, k, secs = int(w[w.index("natoms") + 1]), int(w[w.index("steps") + 1]), float(w[w.index("seconds") + 1])
+        rec.update(value=n * k / secs, natoms=n, steps=k, seconds=secs, steps_per_s=k / secs,
+                   sample="%d atoms (sc lattice, rho=%.1f, rc=2.5, its skin 0.3, dt 0.005, NVE) x %d steps after %d warm-up steps" % (n, rho, k, warmup),
+                   published_elsewhere="762 steps/s at 27 000 atoms on an RTX 4090 (reference cuda/notes.txt)")
+        try:
+            rec["this_library_same_size"] = own_run_at_size(ncell, rho, steps, warmup)
+        except Exception as e:      # noqa: BLE001
+            rec["this_library_same_size"] = {"error": repr(e)}
+    except Exception as e:      # noqa: BLE001
+        rec["unavailable"] = repr(e)
+    return rec
+
+
 def weak_lattice_dims(ncell, world, box="cubic"):
     """Lattice sides for `world` GPUs at ncell^3 atoms per GPU (weak scaling, near-cubic box, z longest):
     1 -> n,n,n ; 2 -> n,n,2n ; 4 -> n,2n,2n ; 8 -> 2n,2n,2n.  box="stacked": n,n,world*n (the cross-section a slab
@@ -1152,6 +1216,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
         if not args.no_cpu_matrix:
             cpu["matrix"] = cpu_matrix(args.rho, rc, dt, temp, tau, 2.5, skip_big=False)
+            cpu["reference_cuda"] = reference_cuda_baseline()
     other = sampled = None
     if world == 1 and not args.no_other:
         # short runs of the C2 / C3 configurations (device loop only), so that the driver's record carries them too
