@@ -680,53 +680,64 @@ def sampled_run_record(ncell=46, steps=300, timeout_s=90):
     return rec
 
 
+def run_bounded(cmd, env, timeout_s, cwd=None):
+    """a child job in a session of its own: (returncode or None when it had to be killed, merged output).  Everything the
+    job started is killed with it -- its process group, and any process carrying the job's marker in its environment."""
+    import signal
+    import uuid
+    marker = uuid.uuid4().hex
+    env = dict(env, SEPB_NESTED_RUN=marker)
+    p = subprocess.Popen(cmd, env=env, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        out, _ = p.communicate(timeout=timeout_s)
+        return p.returncode, out
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except OSError:
+            pass
+        for pid in os.listdir("/proc"):             # workers a launcher may have put into sessions of their own
+            if pid.isdigit():
+                try:
+                    if ("SEPB_NESTED_RUN=" + marker).encode() in open(f"/proc/{pid}/environ", "rb").read():
+                        os.kill(int(pid), signal.SIGKILL)
+                except OSError:
+                    pass
+        try:
+            p.communicate(timeout=10)
+        except Exception:      # noqa: BLE001
+            pass
+        return None, f"no answer within {timeout_s} s"
+
+
+def env_without_launcher():
+    """this process's environment without what torchrun gave it (a nested job gets ranks and a rendezvous of its own)"""
+    drop = {"RANK", "LOCAL_RANK", "GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_WORLD_SIZE",
+            "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"}
+    return {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC") and not k.startswith("TORCH_NCCL")}
+
+
 def nested_dd_check(mol="water", steps=40, timeout_s=150):
     """A two-rank decomposed MOLECULAR run checked against a single-GPU run (tests/dd_check.py DD_MOL=..., tests/dd_mol.py),
     launched as a torchrun job of its own after this bench's process group is gone: the scaling record then carries a
     decomposed-vs-single comparison of sep_coulomb_sf + typed LJ + bonds + angles on real GPUs.  Own session, own timeout,
     own rendezvous port; its outcome is a record, never an error of the bench."""
-    import signal
     import socket
-    import uuid
     rec = {"check": f"two-rank decomposed {mol} ({steps} steps) against the same calls on one GPU: first-step forces 1e-10, sums, final positions"}
     t0 = time.perf_counter()
     try:
-        drop = {"RANK", "LOCAL_RANK", "GROUP_RANK", "ROLE_RANK", "ROLE_NAME", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_WORLD_SIZE",
-                "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"}
-        env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC") and not k.startswith("TORCH_NCCL")}
-        marker = uuid.uuid4().hex
-        env.update(DD_MOL=mol, DD_STEPS=str(steps), SEPB_NESTED_RUN=marker)
+        env = env_without_launcher()
+        env.update(DD_MOL=mol, DD_STEPS=str(steps))
         with socket.socket() as sk:
             sk.bind(("127.0.0.1", 0))
             port = sk.getsockname()[1]
-        p = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                              "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dd_check.py")],
-                             env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, start_new_session=True)
-        try:
-            out, _ = p.communicate(timeout=timeout_s)
-            rec["ok"] = p.returncode == 0 and "-> OK" in out
-            lines = out.splitlines()
-            keep = [ln for ln in lines if "dd_mol" in ln and "-> " in ln] or \
-                   [ln for ln in lines if "Error" in ln and "ChildFailedError" not in ln]
-            rec["tail"] = (keep[-1] if keep else out[-300:])[-400:]
-        except subprocess.TimeoutExpired:
-            rec["ok"] = False
-            rec["tail"] = f"no answer within {timeout_s} s"
-            try:
-                os.killpg(p.pid, signal.SIGKILL)
-            except OSError:
-                pass
-            for pid in os.listdir("/proc"):             # workers the launcher may have put into sessions of their own
-                if pid.isdigit():
-                    try:
-                        if ("SEPB_NESTED_RUN=" + marker).encode() in open(f"/proc/{pid}/environ", "rb").read():
-                            os.kill(int(pid), signal.SIGKILL)
-                    except OSError:
-                        pass
-            try:
-                p.communicate(timeout=10)
-            except Exception:      # noqa: BLE001
-                pass
+        rc_, out = run_bounded([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                                "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dd_check.py")], env, timeout_s)
+        rec["ok"] = rc_ == 0 and "-> OK" in out
+        lines = out.splitlines()
+        keep = [ln for ln in lines if "dd_mol" in ln and "-> " in ln] or \
+               [ln for ln in lines if "Error" in ln and "ChildFailedError" not in ln]
+        rec["tail"] = (keep[-1] if keep else out[-300:])[-400:]
     except Exception as e:      # noqa: BLE001
         rec["ok"] = False
         rec["tail"] = repr(e)
@@ -734,67 +745,38 @@ def nested_dd_check(mol="water", steps=40, timeout_s=150):
     return rec
 
 
-def own_run_at_size(ncell, rho=0.8, steps=2000, warmup=300):
-    """this library's prg1-style loop (FP64, NVT, C-driven) at ncell^3 atoms on the current device: the same-size line
-    next to the reference's CUDA path (reference_cuda_baseline)"""
-    from seplib_b200 import capi
-    lib = capi.load()
-    x, L = lj_lattice(ncell, rho)
-    v = lj_velocities(len(x), 1.0, seed=5)
-    s = capi.System(len(x))
-    try:
-        s.put(capi.F_X, x); s.put(capi.F_V, v)
-        s.call("sepgpu_set_alpha", 0, 0.1)
-        gs = capi.make_sys([L] * 3, 2.5, 0.005, skin=0.25)
-        lj = capi.lj_param(2.5, kind="lj_shift")
-        for k in (warmup, steps):
-            t0 = time.perf_counter()
-            if lib.sepgpu_md_lj_nvt(s.ctx, C.byref(gs), b"AA", C.byref(lj), 1, 1.0, 0, 0.01, k):
-                raise RuntimeError(lib.sepgpu_last_error().decode())
-            epot = s.scalars().epot          # a synchronising read
-            secs = time.perf_counter() - t0
-        return {"value": len(x) * steps / secs, "unit": UNIT, "dtype": "f64", "natoms": len(x), "steps": steps, "seconds": secs,
-                "steps_per_s": steps / secs, "epot_per_atom": epot / len(x),
-                "sample": "sepgpu_md_lj_nvt (force + Nose-Hoover + leapfrog, list mode, skin 0.25), wall clock around the C loop"}
-    finally:
-        s.close()
-
-
-def reference_cuda_baseline(ncell=30, rho=0.8, steps=2000, warmup=300, timeout_s=90):
-    """The reference's OWN CUDA Lennard-Jones path (reference cuda/sepcuda*.cu: single precision, all-pairs list build) on
-    this GPU, at the largest size of its own benchmark table (27 000 atoms, reference cuda/notes.txt) and with the loop of
-    its benchmark program (cuda/tgpu_0.cu:17-29) -- oracle/_ref/refcuda_lj, built by oracle/Makefile from the reference
-    sources where they lie.  A second stated baseline beside the CPU one; a process of its own under a timeout."""
+def sep_ngpu_e2e_record(ngpu, nside, steps=1000, warm=300, timeout_s=180):
+    """End to end through the sep_* API on `ngpu` GPUs: tests/progs/nvt_time.c -- the prg1 loop written against include/sep.h,
+    compiled here with gcc and linked with libsep.so like any seplib program -- run with SEP_NGPU=ngpu (the library forks one
+    copy per GPU at the first hot call, seplib_b200/csrc/host/sep_dd.c).  A process of its own under a timeout; its outcome
+    is a record, never an error of the bench."""
     import tempfile
-    exe = os.path.join(ROOT, "oracle", "_ref", "refcuda_lj")
-    rec = {"kind": "reference cuda/ (sep_cuda_* API, FP32), loop of cuda/tgpu_0.cu", "unit": UNIT, "dtype": "f32"}
-    if not os.path.exists(exe):
-        rec["unavailable"] = "oracle/_ref/refcuda_lj not built (needs the reference tree at build time)"
-        return rec
+    rec = {"path": f"sep_* API (include/sep.h), unchanged C program, SEP_NGPU={ngpu}, SEP_SYNC=auto: sepret refreshed after every hot call",
+           "unit": UNIT}
     try:
-        x, L = lj_lattice(ncell, rho)
-        v = lj_velocities(len(x), 1.0, seed=5)
         with tempfile.TemporaryDirectory() as td:
-            start = os.path.join(td, "start.xyz")
-            with open(start, "w") as fh:
-                fh.write("%d\n%f %f %f\n" % (len(x), L, L, L))
-                for (a, b, c), (va, vb, vc) in zip(x, v):
-                    fh.write("A %f %f %f %f %f %f 1.000000 0.000000\n" % (a, b, c, va, vb, vc))
-            r = subprocess.run([exe, start, str(steps), str(warmup)], capture_output=True, text=True, timeout=timeout_s, cwd=td)
-        if r.returncode != 0:
-            rec["unavailable"] = ("rc %d: " % r.returncode) + (r.stderr or r.stdout)[-200:]
+            exe = os.path.join(td, "nvt_time")
+            subprocess.check_call(["gcc", "-std=c99", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "progs", "nvt_time.c"),
+                                   "-L" + os.path.join(ROOT, "seplib_b200"), "-lsep", "-lm", "-o", exe])
+            env = env_without_launcher()
+            libdir = os.path.join(ROOT, "seplib_b200")
+            if env.get("SEPGPU_EMU_LIB"):             # plumbing test on the CPU kernel emulator (tests/emu): libsep.so -> libsep_emu.so
+                libdir = os.path.join(os.path.dirname(env["SEPGPU_EMU_LIB"]), "emu_lib")
+            env["LD_LIBRARY_PATH"] = libdir + ":" + env.get("LD_LIBRARY_PATH", "")
+            env.pop("SEP_SYNC", None)
+            env["SEP_NGPU"] = str(ngpu)
+            rc_, out = run_bounded([exe, str(nside), str(steps), str(warm)], env, timeout_s, cwd=td)
+        w = out.split()
+        if rc_ != 0 or "seconds_loop" not in w:
+            rec["error"] = ("rc %r: " % rc_) + out[-300:]
             return rec
-        w = r.stdout.split()
-        n, k, secs = int(w[w.index("natoms") + 1]), int(w[w.index("steps") + 1]), float(w[w.index("seconds") + 1])
-        rec.update(value=n * k / secs, natoms=n, steps=k, seconds=secs, steps_per_s=k / secs,
-                   sample="%d atoms (sc lattice, rho=%.1f, rc=2.5, its skin 0.3, dt 0.005, NVE) x %d steps after %d warm-up steps" % (n, rho, k, warmup),
-                   published_elsewhere="762 steps/s at 27 000 atoms on an RTX 4090 (reference cuda/notes.txt)")
-        try:
-            rec["this_library_same_size"] = own_run_at_size(ncell, rho, steps, warmup)
-        except Exception as e:      # noqa: BLE001
-            rec["this_library_same_size"] = {"error": repr(e)}
+        get = lambda k: float(w[w.index(k) + 1])             # noqa: E731
+        n, k = int(get("natoms")), int(get("steps"))
+        rec.update(value=n * k / get("seconds_loop"), natoms=n, steps=k, ms_per_step=1e3 * get("seconds_loop") / k,
+                   seconds_first_calls=get("seconds_warm"), warm_steps=int(get("warm")), seconds_download=get("seconds_download"),
+                   epot_per_atom=get("epot_per_atom"), ekin_per_atom=get("ekin_per_atom"), list_rebuilds=int(get("rebuilds")))
     except Exception as e:      # noqa: BLE001
-        rec["unavailable"] = repr(e)
+        rec["error"] = repr(e)
     return rec
 
 
@@ -1273,6 +1255,7 @@ def main():
     if decomposed and world == 2 and not args.no_other:
         # the other rank has left (it returns right after the e2e arm): both GPUs are free for a two-rank job of its own
         line["dd_water_check"] = nested_dd_check("water")
+        line["e2e_sep_ngpu"] = sep_ngpu_e2e_record(2, 126)        # 2.0 M atoms, as the decomposed run above
     emit(line)
     return 0
 

@@ -41,7 +41,13 @@ void sep_error(char *str, ...)
     va_end(ap);
     printf("BAILING OUT\n");
     fflush(stdout);
-    if (sepdd_rank() > 0) fprintf(stderr, "sep-error in copy %d of a SEP_NGPU run: %s\n", sepdd_rank(), str);
+    if (sepdd_rank() > 0) {                      /* copies 1..N-1 have no stdout: say it where somebody can see it */
+        fprintf(stderr, "sep-error in copy %d of a SEP_NGPU run: ", sepdd_rank());
+        va_start(ap, str);
+        vfprintf(stderr, str, ap);
+        va_end(ap);
+        fputc('\n', stderr);
+    }
     sepdd_mark_failed();
     exit(EXIT_FAILURE);
 }
