@@ -717,7 +717,7 @@ def env_without_launcher():
     return {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC") and not k.startswith("TORCH_NCCL")}
 
 
-def nested_dd_check(mol="water", steps=40, timeout_s=150):
+def nested_dd_check(mol="water", steps=40, timeout_s=100):
     """A two-rank decomposed MOLECULAR run checked against a single-GPU run (tests/dd_check.py DD_MOL=..., tests/dd_mol.py),
     launched as a torchrun job of its own after this bench's process group is gone: the scaling record then carries a
     decomposed-vs-single comparison of sep_coulomb_sf + typed LJ + bonds + angles on real GPUs.  Own session, own timeout,
@@ -745,7 +745,7 @@ def nested_dd_check(mol="water", steps=40, timeout_s=150):
     return rec
 
 
-def sep_ngpu_e2e_record(ngpu, nside, steps=1000, warm=300, timeout_s=180):
+def sep_ngpu_e2e_record(ngpu, nside, steps=1000, warm=300, timeout_s=100):
     """End to end through the sep_* API on `ngpu` GPUs: tests/progs/nvt_time.c -- the prg1 loop written against include/sep.h,
     compiled here with gcc and linked with libsep.so like any seplib program -- run with SEP_NGPU=ngpu (the library forks one
     copy per GPU at the first hot call, seplib_b200/csrc/host/sep_dd.c).  A process of its own under a timeout; its outcome
