@@ -745,6 +745,39 @@ def nested_dd_check(mol="water", steps=40, timeout_s=100):
     return rec
 
 
+def spec_force2_trial(timeout_s=110):
+    """The launch sent ahead in a DECOMPOSED run (SEPGPU_OPTS=spec_force=2, experimental: on two B200s it ended in a halo wait
+    that never returned, docs/ROUND_NOTES.md; since then the grid sent ahead is ordered behind the rank's own halo push) tried
+    as a two-rank bench job of its own -- same 1 M atoms per rank, its own decomposed-vs-single check first.  Whatever
+    happens is a record: the device-side waits are bounded (about 60 s), the job is bounded by timeout_s."""
+    import socket
+    rec = {"what": "bench.py --gpus 2 --steps 200 --warmup 50 with SEPGPU_OPTS=spec_force=2 (force launch sent ahead in decomposed runs, experimental)"}
+    t0 = time.perf_counter()
+    try:
+        env = env_without_launcher()
+        env["SEPGPU_OPTS"] = "spec_force=2"
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        rc_, out = run_bounded([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                                "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__), "--gpus", "2", "--steps", "200",
+                                "--warmup", "50", "--no-cpu", "--no-e2e", "--no-other"], env, timeout_s)
+        got = None
+        for ln in out.splitlines():
+            if ln.startswith("{") and '"metric"' in ln:
+                got = json.loads(ln)
+        if rc_ == 0 and got:
+            rec.update(ok=True, value=got["value"], unit=got["unit"], ms_per_step=got["ms_per_step"], steps=got["steps"],
+                       kernel_ms=got.get("kernel_ms"), dd_check=got.get("dd_check", {}).get("ok") if isinstance(got.get("dd_check"), dict) else None)
+        else:
+            keep = [ln for ln in out.splitlines() if "Error" in ln and "ChildFailedError" not in ln]
+            rec.update(ok=False, tail=(keep[-1] if keep else out[-300:])[-400:])
+    except Exception as e:      # noqa: BLE001
+        rec.update(ok=False, tail=repr(e))
+    rec["seconds"] = time.perf_counter() - t0
+    return rec
+
+
 def sep_ngpu_e2e_record(ngpu, nside, steps=1000, warm=300, timeout_s=100):
     """End to end through the sep_* API on `ngpu` GPUs: tests/progs/nvt_time.c -- the prg1 loop written against include/sep.h,
     compiled here with gcc and linked with libsep.so like any seplib program -- run with SEP_NGPU=ngpu (the library forks one
@@ -1256,6 +1289,8 @@ def main():
         # the other rank has left (it returns right after the e2e arm): both GPUs are free for a two-rank job of its own
         line["dd_water_check"] = nested_dd_check("water")
         line["e2e_sep_ngpu"] = sep_ngpu_e2e_record(2, 126)        # 2.0 M atoms, as the decomposed run above
+        if not os.environ.get("SEPGPU_OPTS"):
+            line["spec_force2_trial"] = spec_force2_trial()
     emit(line)
     return 0
 
