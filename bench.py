@@ -17,6 +17,12 @@ on a lattice-initialised Lennard-Jones fluid (prg1-style NVT, SURVEY.md section 
   cpu_baseline  the reference's own OpenMP CPU path (oracle/_ref, compiled from its unmodified sources)
             on the box's host cores, bounded sample of the same workload
 
+            (+ cpu_baseline.reference_cuda: the reference's own CUDA path, oracle/_ref/refcuda_lj, on the same GPU)
+  side records, each a bounded job of its own whose outcome never touches the numbers above:
+            other_workloads (C2 butane / C3 water), sampled_run (run-time samplers: host path against device feeds);
+            at N = 2 dd_water_check (decomposed Coulomb against one GPU), e2e_sep_ngpu (an unchanged C program with SEP_NGPU=2),
+            spec_force2_trial (the experimental launch sent ahead in a decomposed run).  --no-other skips them all.
+
 --impl reference runs only that CPU arm and prints its own line.
 N>1 (torchrun): slab domain decomposition, N x 1 M atoms (weak scaling; 8 GPUs = the 8 M-atom C4 configuration);
 --replicas runs N independent copies instead.  --workload butane|water runs the C2 / C3 configurations (1 GPU).

@@ -11,11 +11,14 @@
 
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <sys/mman.h>
 #include <ucontext.h>
 
 #include <algorithm>
 #include <mutex>
+#include <unordered_map>
+#include <utility>
 #include <vector>
 
 // All scheduler state is per HOST thread: the ranks of an emulated decomposed run are threads that launch kernels
@@ -344,15 +347,51 @@ const char *cudaGetErrorString(cudaError_t e)
     default: return "unknown error";
     }
 }
+// SEPGPU_EMU_GUARD=1: every device allocation ends (to 32 bytes, the widest vector access) at an inaccessible page, so that a
+// kernel reading or writing past its array stops the run with SIGSEGV at the offending access instead of passing by luck.
+static bool guard_mode(void)
+{
+    static const bool on = getenv("SEPGPU_EMU_GUARD") && atoi(getenv("SEPGPU_EMU_GUARD")) != 0;
+    return on;
+}
+static std::mutex g_guard_mu;
+static std::unordered_map<void *, std::pair<void *, size_t>> g_guard_map;      // user pointer -> (mapping, length)
+
 cudaError_t cudaMalloc(void **p, size_t bytes)
 {
+    if (guard_mode()) {
+        const size_t page = 4096, body = ((bytes ? bytes : 32) + 31) & ~(size_t)31;
+        const size_t len = ((body + page - 1) / page + 1) * page;
+        char *base = (char *)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (base == MAP_FAILED) return cudaErrorMemoryAllocation;
+        mprotect(base + len - page, page, PROT_NONE);
+        char *q = base + len - page - body;
+        memset(q, 0xCD, bytes);
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        g_guard_map[q] = {base, len};
+        *p = q;
+        return cudaSuccess;
+    }
     void *q = nullptr;
     if (posix_memalign(&q, 256, bytes ? bytes : 256)) return cudaErrorMemoryAllocation;
     memset(q, 0xCD, bytes);
     *p = q;
     return cudaSuccess;
 }
-cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void *p)
+{
+    if (guard_mode()) {
+        if (!p) return cudaSuccess;
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        auto it = g_guard_map.find(p);
+        if (it == g_guard_map.end()) return cudaErrorInvalidValue;
+        munmap(it->second.first, it->second.second);
+        g_guard_map.erase(it);
+        return cudaSuccess;
+    }
+    free(p);
+    return cudaSuccess;
+}
 cudaError_t cudaMallocHost(void **p, size_t bytes)
 {
     void *q = nullptr;
