@@ -1,9 +1,9 @@
 /* sep.h -- the seplib C99 API, as served by seplib-b200 (B200 / sm_100a device path).
  *
  * This header is the drop-in boundary: programs written against the reference's include/sep.h
- * (prgs/prg0-4.c, prg6-9.c) compile against it unchanged and link with -lsep.  Not provided: the OpenMP
- * tasking model II of prg5 (sep_omp_bond / sep_omp_angle / sep_omp_torsion, source/sepomp.c -- a CPU
- * idiom with nothing to do on a device) and the sep_matrix_* helpers it uses.  Type names, field
+ * (prgs/prg0-9.c) compile against it unchanged and link with -lsep -- prg5 included: its OpenMP "model II"
+ * helpers sep_omp_bond / sep_omp_angle / sep_omp_torsion (source/sepomp.c) are served from the device; the pair-force
+ * members of that family (sep_omp_pairs, sep_omp_coulomb, sep_omp_dpd_pairs) are not provided.  Type names, field
  * names, field order, constants and prototypes follow the reference so that user code which reads
  * atoms[i].x/v/f, sys.nupdate_neighb or ret.epot directly keeps working; each block cites the
  * reference header it mirrors (paths relative to the reference root).
@@ -241,6 +241,12 @@ void sep_angle_harmonic(sepatom *ptr, int type, const double angle0, const doubl
 void sep_angle_cossq(sepatom *ptr, int type, const double angle0, const double k,
                      sepsys *sys, sepret *ret);
 void sep_torsion_Ryckaert(sepatom *ptr, int type, const double g[6], sepsys *sys, sepret *ret);
+/* OpenMP "model II" helpers of prgs/prg5.c (reference include/sepomp.h:87-123, source/sepomp.c:179-329): the forces of one
+ * bonded term kind ADDED to the caller's matrix ftot[npart][3]; atoms[].f and sepret are not touched.  Computed on the
+ * device from the current positions; calls from different OpenMP sections are serialised inside the library. */
+void sep_omp_bond(double **ftot, seppart *aptr, int type, const double lbond, const double ks, sepsys *sys);
+void sep_omp_angle(double **ftot, seppart *ptr, int type, const double angle0, const double k, sepsys *sys);
+void sep_omp_torsion(double **ftot, seppart *ptr, int type, const double g[6], sepsys *sys);
 void sep_mol_cm(seppart *ptr, sepmol *mol, sepsys *sys);
 void sep_mol_eval_xtrue(seppart *ptr, sepmol *mol, sepsys sys);
 void sep_mol_spin(sepatom *atom, sepmol *mol, sepsys *sys, bool safe);
@@ -302,6 +308,7 @@ double *sep_vector(size_t length);
 int *sep_vector_int(size_t length);
 double **sep_matrix(size_t nrow, size_t ncol);
 void sep_free_matrix(double **ptr, size_t nrow);
+void sep_matrix_set(double **a, size_t nrow, size_t ncol, double value);
 float ***sep_tensor_float(size_t nx, size_t ny, size_t nz);
 void sep_free_tensor_float(float ***ptr, size_t nx, size_t ny);
 double sep_dot(double *a, double *b, int length);

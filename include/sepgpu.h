@@ -161,6 +161,11 @@ int sepgpu_stretch_harmonic(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, do
 int sepgpu_angle_harmonic(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, double angle0, double k);
 int sepgpu_angle_cossq(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, double angle0, double k);
 int sepgpu_torsion_ryckaert(sepgpu_ctx *ctx, const sepgpu_sys *sys, int type, const double g[6]);
+/* The forces of ONE bonded term kind in an array of their own, nothing else touched (no sums, no change of the atoms' force
+ * array): what the reference's OpenMP "model II" helpers compute -- sep_omp_bond (source/sepomp.c:179-213, kind 0, par =
+ * {lbond, ks}), sep_omp_angle (:215-262, kind 1, the cos^2 form, par = {angle0, k}), sep_omp_torsion (:265-329, kind 2,
+ * par = g[6]).  out3[3 i + k] is written for every atom.  Single-domain contexts. */
+int sepgpu_bonded_side(sepgpu_ctx *ctx, const sepgpu_sys *sys, int kind, int type, const double *par, double *out3);
 /* sep_nosehoover (source/sepintgr.c:149-168).  alpha lives in device slot `slot` (0..3); the
  * f -= alpha m v update is fused into the next integrator kernel. */
 int sepgpu_nosehoover(sepgpu_ctx *ctx, const sepgpu_sys *sys, double temp0, int slot, double tau);

@@ -8,13 +8,14 @@ REF=${REF:-/root/reference}
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 OUT=$ROOT/oracle/_ref/prgs
 mkdir -p "$OUT"
-for p in prg0 prg1 prg2 prg3 prg4 prg6 prg7 prg8 prg9; do
-  gcc -std=c99 -O2 -w -I"$ROOT/include" "$REF/prgs/$p.c" -L"$ROOT/seplib_b200" -lsep -lm \
+for p in prg0 prg1 prg2 prg3 prg4 prg5 prg6 prg7 prg8 prg9; do
+  OMP=""; [ $p = prg5 ] && OMP="-fopenmp"      # prg5 calls the library from two OpenMP sections at once (prgs/prg5.c:56-70)
+  gcc -std=c99 -O2 -w $OMP -I"$ROOT/include" "$REF/prgs/$p.c" -L"$ROOT/seplib_b200" -lsep -lm \
       -Wl,-rpath,'$ORIGIN/../../../seplib_b200' -o "$OUT/$p"
   echo "built $p against seplib-b200"
 done
 if [ -f "$ROOT/oracle/_ref/libsep_ref.so" ]; then
-  for p in prg0 prg1 prg2 prg3 prg4 prg7 prg9; do
+  for p in prg0 prg1 prg2 prg3 prg4 prg5 prg7 prg9; do
     gcc -std=c99 -O2 -w -DCOMPLEX -fopenmp -I"$REF/include" "$REF/prgs/$p.c" "$ROOT/oracle/_ref/libsep_ref.so" -lm \
         -Wl,-rpath,'$ORIGIN/..' -o "$OUT/${p}_ref"
     echo "built ${p}_ref against the reference"

@@ -124,7 +124,7 @@ SEPGPU_SYMBOLS = [
     "sepgpu_reset_force", "sepgpu_neighb_build", "sepgpu_force_lj", "sepgpu_force_table", "sepgpu_set_host_rows", "sepgpu_md_lj_nvt", "sepgpu_dd_set_charges", "sepgpu_coulomb_sf",
     "sepgpu_feed_vacf", "sepgpu_feed_msd", "sepgpu_feed_profile", "sepgpu_feed_fourier", "sepgpu_feed_radial",
     "sepgpu_force_dpd", "sepgpu_stretch_harmonic", "sepgpu_angle_harmonic", "sepgpu_angle_cossq",
-    "sepgpu_torsion_ryckaert", "sepgpu_nosehoover", "sepgpu_nosehoover_type", "sepgpu_set_alpha",
+    "sepgpu_torsion_ryckaert", "sepgpu_bonded_side", "sepgpu_nosehoover", "sepgpu_nosehoover_type", "sepgpu_set_alpha",
     "sepgpu_leapfrog", "sepgpu_verlet_dpd", "sepgpu_reset_momentum", "sepgpu_scale_positions",
     "sepgpu_read_scalars", "sepgpu_sync", "sepgpu_get_pairs", "sepgpu_request_rebuild",
     "sepgpu_set_option", "sepgpu_get_option", "sepgpu_timer_start", "sepgpu_timer_stop", "sepgpu_kernel_time",
@@ -250,6 +250,7 @@ def load():
     lib.sepgpu_angle_harmonic.argtypes = [ctx, C.POINTER(GpuSys), C.c_int, C.c_double, C.c_double]
     lib.sepgpu_angle_cossq.argtypes = [ctx, C.POINTER(GpuSys), C.c_int, C.c_double, C.c_double]
     lib.sepgpu_torsion_ryckaert.argtypes = [ctx, C.POINTER(GpuSys), C.c_int, C.POINTER(C.c_double)]
+    lib.sepgpu_bonded_side.argtypes = [ctx, C.POINTER(GpuSys), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.sepgpu_nosehoover.argtypes = [ctx, C.POINTER(GpuSys), C.c_double, C.c_int, C.c_double]
     lib.sepgpu_nosehoover_type.argtypes = [ctx, C.POINTER(GpuSys), C.c_char, C.c_double, C.POINTER(C.c_double), C.c_double]
     lib.sepgpu_set_alpha.argtypes = [ctx, C.c_int, C.c_double]

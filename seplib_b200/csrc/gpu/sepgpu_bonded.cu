@@ -393,3 +393,51 @@ extern "C" int sepgpu_torsion_ryckaert(sepgpu_ctx *c, const sepgpu_sys *sys, int
     c->f_zero = false;
     return sepgpu_finalize_force(c, grid, 1.0, 0);
 }
+
+// ---- one bonded term kind into an array of its own ------------------------------------------------------------
+// The reference's "OpenMP model II" helpers (source/sepomp.c:179-329: sep_omp_bond, sep_omp_angle, sep_omp_torsion) add the
+// forces of one term kind to a matrix of the caller's and touch nothing else -- no sepret sums, no atoms[].f.  Same kernels
+// as the entries above, pointed at a spare force array and a spare block-sum array; the simulation state does not change.
+// kind 0: harmonic bonds (par = {lbond, ks})   1: cos^2 angles (par = {angle0, k}, :218-262)   2: Ryckaert-Bellemans (par = g[6])
+// out3[3 * i + k] = force component k of atom i from those terms.
+extern "C" int sepgpu_bonded_side(sepgpu_ctx *c, const sepgpu_sys *sys, int kind, int type, const double *par, double *out3)
+{
+    if (!c || !sys || !par || !out3 || kind < 0 || kind > 2) return SEPGPU_EINVAL;
+    if (c->dd) { sepgpu_set_error("bonded_side: single-domain contexts only"); return SEPGPU_ESTATE; }
+    if (!(kind == 0 ? c->atom_bond_ptr : kind == 1 ? c->atom_angle_ptr : c->atom_dihed_ptr)) {
+        sepgpu_set_error("bonded_side: no topology on the device");
+        return SEPGPU_ESTATE;
+    }
+    SEPGPU_ENTER(c);
+    SEPGPU_BENIGN(c);
+    const int n = c->n;
+    if (n <= 0) return 0;
+    if (!c->f_side) CUDA_TRY(cudaMalloc((void **)&c->f_side, sizeof(d4) * (size_t)c->ncap));
+    if (!c->partial_side) CUDA_TRY(cudaMalloc((void **)&c->partial_side, sizeof(double) * (size_t)SEPGPU_MAX_BLOCKS_PARTIAL * 16));
+    BondedDD D;
+    memset(&D, 0, sizeof D);
+    const int grid = (n + BONDED_BLOCK - 1) / BONDED_BLOCK;
+    if (grid > SEPGPU_MAX_BLOCKS_PARTIAL) { sepgpu_set_error("bonded_side: system too large"); return SEPGPU_EINVAL; }
+    if (kind == 0) {
+        k_bond<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f_side, n, c->blist, c->atom_bond_ptr, c->atom_bond_idx, type, par[0], par[1],
+                                                     make_box(sys), 1, c->blengths, c->partial_side, D, c->scal);
+    } else if (kind == 1) {
+        const double cCon = cos(SEPGPU_PI - par[0]);
+        k_angle<true><<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f_side, n, c->alist, c->atom_angle_ptr, c->atom_angle_idx, type, par[0],
+                                                            par[1], cCon, make_box(sys), 1, c->angles, c->partial_side, D, c->scal);
+    } else {
+        RBCoef G; for (int k = 0; k < 6; k++) G.g[k] = par[k];
+        k_torsion<<<grid, BONDED_BLOCK, 0, c->stream>>>(c->x4, c->f_side, n, c->dlist, c->atom_dihed_ptr, c->atom_dihed_idx, type, G,
+                                                        make_box(sys), 1, c->dihedrals, c->partial_side, D, c->scal);
+    }
+    KERNEL_CHECK();
+    const size_t bytes = sizeof(d4) * (size_t)n;
+    int rc = sepgpu_ensure_stage(c, bytes);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));                // an earlier asynchronous copy may still read the staging buffer
+    CUDA_TRY(cudaMemcpyAsync(c->stage, c->f_side, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const d4 *h = (const d4 *)c->stage;
+    for (int i = 0; i < n; i++) { out3[3 * i] = h[i].x; out3[3 * i + 1] = h[i].y; out3[3 * i + 2] = h[i].z; }
+    return 0;
+}

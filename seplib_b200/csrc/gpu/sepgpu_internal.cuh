@@ -234,6 +234,10 @@ struct sepgpu_ctx {
         unsigned long long api_seq;
     } spec;
     d4 *f4_alt;
+    int *put_changed;              // device flag: an upload that may leave the list alone found different values (sepgpu_put_fields)
+    bool put_check;                // ... and that flag has to be read before the upload returns
+    d4 *f_side;                    // forces of ONE bonded term kind on their own (sepgpu_bonded_side: the reference's sep_omp_bond family)
+    double *partial_side;          // ... and the block sums that kernel leaves behind (not used)
     long long spec_adopted;        // launches adopted so far (tests, sepgpu_get_option)
     long long feed_calls, get_calls;   // sampler feeds / per-atom downloads served so far (tests, sepgpu_get_option)
     bool scal_cache_valid;         // scal_host holds the block as the last integrator's finaliser left it ...

@@ -135,6 +135,9 @@ extern "C" void sepgpu_destroy(sepgpu_ctx *c)
     sepgpu_dd_destroy(c);
     sepgpu_feeds_destroy(c);
     if (c->gid) cudaFree(c->gid);
+    if (c->f_side) cudaFree(c->f_side);
+    if (c->put_changed) cudaFree(c->put_changed);
+    if (c->partial_side) cudaFree(c->partial_side);
     if (c->fij) cudaFree(c->fij);
     if (c->cls) cudaFree(c->cls);
     if (c->x0) cudaFree(c->x0);
@@ -192,6 +195,40 @@ __global__ void k_vec3_to_d4(d4 *dst, const double *src, int n)
     d4 v = dst[i];
     v.x = src[3 * i]; v.y = src[3 * i + 1]; v.z = src[3 * i + 2];
     dst[i] = v;
+}
+// Uploads that invalidate the neighbour list only when they bring different values: a program that edits one member of
+// atoms[] between hot calls (reference prgs/prg5.c:72-76 adds to atoms[i].f) makes the host layer upload every member --
+// it cannot know which one changed -- and positions, types, molecule indices and exclusion tables that come back
+// unchanged must not cost a list rebuild per step.
+__global__ void k_vec3_to_d4_changed(d4 *dst, const double *src, int n, int *changed)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d4 v = dst[i];
+    const double a = src[3 * i], b = src[3 * i + 1], c = src[3 * i + 2];
+    if (v.x != a || v.y != b || v.z != c) {
+        v.x = a; v.y = b; v.z = c;
+        dst[i] = v;
+        *changed = 1;
+    }
+}
+__global__ void k_set_tag_changed(d4 *x4, const char *types, const int *mols, int n, int *changed)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double w = x4[i].w;
+    const int t = types ? (int)(unsigned char)types[i] : tag_type(w), m = mols ? mols[i] : tag_mol(w);
+    if (t != tag_type(w) || m != tag_mol(w)) {
+        x4[i].w = make_tag((unsigned char)t, m);
+        *changed = 1;
+    }
+}
+__global__ void k_copy_int_changed(int *dst, const int *src, size_t count, int *changed)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int v = src[i];
+    if (dst[i] != v) { dst[i] = v; *changed = 1; }
 }
 __global__ void k_d4_to_vec3(double *dst, const d4 *src, int n)
 {
@@ -306,8 +343,17 @@ static int put_dispatch(sepgpu_ctx *c, int field, const void *dsrc, const void *
     const size_t row = fi.elem * fi.width, n = (size_t)c->n_own;
     const int B = 256, G = (c->n_own + B - 1) / B;
     int rc;
+    // single domain with a valid list: see k_vec3_to_d4_changed (decomposed runs rebuild collectively: no shortcut there)
+    const bool cmp = !c->dd && c->list_valid && c->xs_current;
+    if (cmp && !c->put_check && (field == SEPGPU_F_X || field == SEPGPU_F_TYPE || field == SEPGPU_F_MOLINDEX ||
+                                 field == SEPGPU_F_BOND || field == SEPGPU_F_ANGLE || field == SEPGPU_F_DIHED)) {
+        if (!c->put_changed) CUDA_TRY(cudaMalloc((void **)&c->put_changed, sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(c->put_changed, 0, sizeof(int), c->stream));
+        c->put_check = true;
+    }
     switch (field) {
     case SEPGPU_F_X:
+        if (cmp) { k_vec3_to_d4_changed<<<G, B, 0, c->stream>>>(c->x4, (const double *)dsrc, c->n_own, c->put_changed); break; }
         k_vec3_to_d4<<<G, B, 0, c->stream>>>(c->x4, (const double *)dsrc, c->n_own);
         c->xs_current = false; c->list_valid = false;
         break;
@@ -349,15 +395,18 @@ static int put_dispatch(sepgpu_ctx *c, int field, const void *dsrc, const void *
         break;
     }
     case SEPGPU_F_TYPE: {
-        k_set_type<<<G, B, 0, c->stream>>>(c->x4, (const char *)dsrc, c->n_own);
+        if (cmp) k_set_tag_changed<<<G, B, 0, c->stream>>>(c->x4, (const char *)dsrc, NULL, c->n_own, c->put_changed);
+        else k_set_type<<<G, B, 0, c->stream>>>(c->x4, (const char *)dsrc, c->n_own);
         const unsigned char *ht = (const unsigned char *)hsrc;
         int st = ht[0];
         for (size_t i = 1; i < n && st >= 0; i++) if (ht[i] != ht[0]) st = -1;
         c->single_type = st;
+        if (cmp) break;
         c->xs_current = false; c->list_valid = false;
         break;
     }
     case SEPGPU_F_MOLINDEX:
+        if (cmp) { k_set_tag_changed<<<G, B, 0, c->stream>>>(c->x4, NULL, (const int *)dsrc, c->n_own, c->put_changed); break; }
         k_set_mol<<<G, B, 0, c->stream>>>(c->x4, (const int *)dsrc, c->n_own);
         c->xs_current = false; c->list_valid = false;
         break;
@@ -373,6 +422,11 @@ static int put_dispatch(sepgpu_ctx *c, int field, const void *dsrc, const void *
         break;
     case SEPGPU_F_BOND: case SEPGPU_F_ANGLE: case SEPGPU_F_DIHED: {
         int **tab = field == SEPGPU_F_BOND ? &c->excl_bond : field == SEPGPU_F_ANGLE ? &c->excl_angle : &c->excl_dihed;
+        if (cmp && *tab) {
+            const size_t count = (size_t)fi.width * n;
+            k_copy_int_changed<<<(unsigned)((count + B - 1) / B), B, 0, c->stream>>>(*tab, (const int *)dsrc, count, c->put_changed);
+            break;
+        }
         if (!*tab && dalloc(tab, (size_t)fi.width * c->ncap)) return SEPGPU_ECUDA;
         CUDA_TRY(cudaMemcpyAsync(*tab, dsrc, row * n, cudaMemcpyDeviceToDevice, c->stream));
         c->have_excl = c->excl_bond && c->excl_angle && c->excl_dihed;
@@ -419,6 +473,13 @@ extern "C" int sepgpu_put_fields(sepgpu_ctx *c, const void *base, size_t stride,
     CUDA_TRY(cudaMemcpyAsync(c->dstage, c->stage, total, cudaMemcpyHostToDevice, c->stream));
     for (int f = 0; f < nfields; f++)
         if ((rc = put_dispatch(c, fields[f], (const char *)c->dstage + off[f], (const char *)c->stage + off[f]))) return rc;
+    if (c->put_check) {                    // did positions / types / molecule indices / exclusion tables come back different?
+        int changed = 1;
+        c->put_check = false;
+        CUDA_TRY(cudaMemcpyAsync(&changed, c->put_changed, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (changed) { c->xs_current = false; c->list_valid = false; }
+    }
     return 0;
 }
 

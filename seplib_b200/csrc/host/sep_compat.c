@@ -30,6 +30,12 @@ void sep_free_matrix(double **ptr, size_t nrow)
     free(ptr);
 }
 
+void sep_matrix_set(double **a, size_t nrow, size_t ncol, double value)
+{
+    for (size_t r = 0; r < nrow; r++)
+        for (size_t c = 0; c < ncol; c++) a[r][c] = value;
+}
+
 float ***sep_tensor_float(size_t nx, size_t ny, size_t nz)
 {
     float ***t = malloc(sizeof(float **) * (nx ? nx : 1));

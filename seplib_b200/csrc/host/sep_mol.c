@@ -6,6 +6,7 @@
  * sep_stretch_harmonic / sep_angle_harmonic / sep_angle_cossq / sep_torsion_Ryckaert
  * (source/sepmol.c:372-587) are device kernels (sepgpu_bonded.cu).
  */
+#include <pthread.h>
 #include "sep_host.h"
 #include <float.h>
 
@@ -395,6 +396,42 @@ void sep_torsion_Ryckaert(sepatom *ptr, int type, const double g[6], sepsys *sys
 /* ---- molecular pressure tensor (source/sepmol.c:913-963, source/sepret.c:85-102) --------------------------
  * The molecule-molecule force table Fij is accumulated on the device by the pair kernels (FP64 there,
  * float in the reference); it is copied into the caller-visible float table when the tensor is evaluated. */
+/* ---- prg5's helpers: one term kind into the caller's matrix (reference source/sepomp.c:179-329) ---------------------- */
+static pthread_mutex_t g_omp_mu = PTHREAD_MUTEX_INITIALIZER;      /* prg5 calls them from two OpenMP sections at once */
+
+static void omp_side(double **ftot, sepatom *ptr, sepsys *sys, int kind, int type, const double *par, const char *who)
+{
+    pthread_mutex_lock(&g_omp_mu);
+    sepgpu_sys gs;
+    sep_binding *b = bonded_prepare(ptr, sys, &gs, who);
+    if (b->dd) sep_error("%s: not available with SEP_NGPU", (char *)who);
+    const size_t n = (size_t)sys->npart;
+    double *flat = malloc(sizeof(double) * 3 * (n ? n : 1));
+    if (!flat) sep_error("%s: out of memory", (char *)who);
+    sepb_check(sepgpu_bonded_side(b->gpu, &gs, kind, type, par, flat), who);
+    for (size_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) ftot[i][k] += flat[3 * i + k];
+    free(flat);
+    pthread_mutex_unlock(&g_omp_mu);
+}
+
+void sep_omp_bond(double **ftot, sepatom *aptr, int type, const double lbond, const double ks, sepsys *sys)
+{
+    const double par[2] = {lbond, ks};
+    omp_side(ftot, aptr, sys, 0, type, par, "sep_omp_bond");
+}
+
+void sep_omp_angle(double **ftot, sepatom *ptr, int type, const double angle0, const double k, sepsys *sys)
+{
+    const double par[2] = {angle0, k};
+    omp_side(ftot, ptr, sys, 1, type, par, "sep_omp_angle");
+}
+
+void sep_omp_torsion(double **ftot, sepatom *ptr, int type, const double g[6], sepsys *sys)
+{
+    omp_side(ftot, ptr, sys, 2, type, g, "sep_omp_torsion");
+}
+
 void sep_reset_force_mol(sepsys *sys)
 {
     sys->fun_cstate = 0;

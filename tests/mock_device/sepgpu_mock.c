@@ -348,6 +348,18 @@ int sepgpu_torsion_ryckaert(sepgpu_ctx *c, const sepgpu_sys *sys, int type, cons
     return 0;
 }
 
+int sepgpu_bonded_side(sepgpu_ctx *c, const sepgpu_sys *sys, int kind, int type, const double *par, double *out3)
+{
+    orc_ret t;
+    memset(&t, 0, sizeof t);
+    memset(out3, 0, sizeof(double) * 3 * (size_t)c->n);
+    if (kind == 0) orc_stretch_harmonic(c->x, sys->length, c->blist, c->nb, type, par[0], par[1], out3, &t, c->blengths);
+    else if (kind == 1) orc_angle_cossq(c->x, sys->length, c->alist, c->na, type, par[0], par[1], out3, &t, c->angles);
+    else if (kind == 2) orc_torsion_ryckaert(c->x, sys->length, c->dlist, c->nd, type, par, out3, &t, c->dihedrals);
+    else return SEPGPU_EINVAL;
+    return 0;
+}
+
 int sepgpu_nosehoover(sepgpu_ctx *c, const sepgpu_sys *sys, double temp0, int slot, double tau)
 {
     c->alpha[slot] = orc_nosehoover(c->n, c->v, c->m, c->f, temp0, c->alpha[slot], tau, sys->dt);

@@ -37,8 +37,8 @@ def _run(args, timeout=1500, env=None):
 def test_gpu_parity_tests_pass_on_the_emulated_kernels():
     # tests/test_golden.py: the reference's own recorded butane / water / DPD vectors against the emulated kernels
     n = _run(["tests/test_gpu_lj.py", "tests/test_gpu_more.py", "tests/test_gpu_zz_next.py", "tests/test_gpu_zzzz_edge.py",
-              "tests/test_golden.py", "-m", "gpu", "-q", "-n", WORKERS, "-k", FAST, "-p", "no:cacheprovider"])
-    assert n >= 47, n
+              "tests/test_gpu_zzzz_omp.py", "tests/test_golden.py", "-m", "gpu", "-q", "-n", WORKERS, "-k", FAST, "-p", "no:cacheprovider"])
+    assert n >= 49, n
 
 
 def test_kernel_options_pass_on_the_emulator():
