@@ -149,7 +149,7 @@ SEP_SYMBOLS = [
     "sep_box_length", "sep_count_type", "sep_set_x0", "sep_set_xn", "sep_save_xyz", "sep_eval_mom",
     "sep_eval_mom_type", "sep_compress_box", "sep_set_charge", "sep_set_mass", "sep_set_type",
     "sep_set_omp", "sep_set_skin", "sep_set_ndof", "sep_reset_momentum", "sep_dist_ij",
-    "sep_eval_xtrue", "sep_vector", "sep_vector_int", "sep_matrix", "sep_free_matrix",
+    "sep_eval_xtrue", "sep_vector", "sep_vector_int", "sep_matrix", "sep_free_matrix", "sep_matrix_set", "sep_omp_bond", "sep_omp_angle", "sep_omp_torsion",
     "sep_tensor_float", "sep_free_tensor_float", "sep_dot", "sep_vector_set", "sep_init_sampler",
     "sep_add_sampler", "sep_add_mol_sampler", "sep_sample", "sep_close_sampler", "sep_gpu_set_sync",
     "sep_gpu_sync", "sep_gpu_invalidate", "sep_gpu_sync_scalars", "sep_gpu_export_neighb",
