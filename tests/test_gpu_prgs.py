@@ -111,19 +111,3 @@ def test_prg2_prg3_prg6_run(tmp_path):
     assert np.isfinite(got6).all()
     assert abs(got6[10:, 4].mean() - 1.0) < 0.05                             # DPD thermostat holds T = 1.0
     assert np.abs(got6[:, 6]).max() < 1e-10                                  # momentum conserved by the pair noise
-
-
-def test_prg5_omp_model_two(tmp_path):
-    """prgs/prg5.c, unchanged and compiled with -fopenmp: butane with the bonded forces taken through sep_omp_bond /
-    sep_omp_angle / sep_omp_torsion from two OpenMP sections into matrices of its own, added to atoms[i].f BY THE PROGRAM
-    between the hot calls (the page-protected atoms[] notices), box compression + momentum reset every 10 steps.
-    Deterministic (velocities come from the start file): the printed temperature against the same program linked with the
-    compiled reference (tests/golden/prg5.ref.out, tests/golden/make_prg_outputs.sh).  columns: n t T"""
-    cm.write_molecular_start_files(tmp_path)
-    got, _ = run_prg("prg5", tmp_path=tmp_path)
-    ref = golden("prg5.ref.out")
-    assert got.shape == ref.shape == (10, 3)
-    assert abs(got[0, 2] - ref[0, 2]) <= 1.1e-3, (got[0], ref[0])            # step 0: printed precision
-    assert abs(got[1, 2] - ref[1, 2]) <= 0.02, (got[1], ref[1])              # step 100: rounding has grown, not decorrelated
-    assert abs(got[2:, 2].mean() - ref[2:, 2].mean()) < 0.08                 # thermostatted temperature (4.0), 8 samples of +-0.06
-

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import common as cm
+import test_gpu_prgs as prgs
 from seplib_b200 import capi
 
 pytestmark = pytest.mark.gpu
@@ -137,3 +138,19 @@ def test_uploads_that_change_nothing_keep_the_neighbour_list():
     f3, nb3 = force()
     assert nb3 == nb2 + 1 and np.all(f3[3] == 0.0)                     # atom 3 left the "AA" selection
     s.close()
+
+
+def test_prg5_omp_model_two(tmp_path):
+    """prgs/prg5.c, unchanged and compiled with -fopenmp: butane with the bonded forces taken through sep_omp_bond /
+    sep_omp_angle / sep_omp_torsion from two OpenMP sections into matrices of its own, added to atoms[i].f BY THE PROGRAM
+    between the hot calls (the page-protected atoms[] notices), box compression + momentum reset every 10 steps.
+    Deterministic (velocities come from the start file): the printed temperature against the same program linked with the
+    compiled reference (tests/golden/prg5.ref.out, tests/golden/make_prg_outputs.sh).  columns: n t T"""
+    cm.write_molecular_start_files(tmp_path)
+    got, _ = prgs.run_prg("prg5", tmp_path=tmp_path)
+    ref = prgs.golden("prg5.ref.out")
+    assert got.shape == ref.shape == (10, 3)
+    assert abs(got[0, 2] - ref[0, 2]) <= 1.1e-3, (got[0], ref[0])            # step 0: printed precision
+    assert abs(got[1, 2] - ref[1, 2]) <= 0.02, (got[1], ref[1])              # step 100: rounding has grown, not decorrelated
+    assert abs(got[2:, 2].mean() - ref[2:, 2].mean()) < 0.08                 # thermostatted temperature (4.0), 8 samples of +-0.06
+
