@@ -154,3 +154,26 @@ def test_prg5_omp_model_two(tmp_path):
     assert abs(got[1, 2] - ref[1, 2]) <= 0.02, (got[1], ref[1])              # step 100: rounding has grown, not decorrelated
     assert abs(got[2:, 2].mean() - ref[2:, 2].mean()) < 0.08                 # thermostatted temperature (4.0), 8 samples of +-0.06
 
+
+
+def test_editing_forces_on_the_host_every_step_does_not_rebuild_the_list_every_step():
+    """prg5's pattern through the sep_* API in the default coherence mode (page-protected atoms[]): the program adds to
+    atoms[i].f between the force call and the integrator, every step.  Same number of list rebuilds as without the edit."""
+    lib = capi.load()
+    _declare(lib)
+    lib.sep_gpu_set_sync(3)                                   # SEP_SYNC_AUTO
+    g = np.load(os.path.join(cm.GOLDEN, "butane_n4000.npz"))
+    counts = []
+    for edit in (False, True):
+        s = _butane(lib, g)
+        alpha = C.c_double(0.1)
+        for _ in range(30):
+            lib.sep_reset_retval(s.R); lib.sep_reset_force(s.atoms, s.S)
+            lib.sep_force_pairs(s.atoms, b"CC", 2.5, s.fun("sep_lj_shift"), s.S, s.R, 3)
+            if edit:
+                s.view["f"][:, 0] += 1e-9
+            lib.sep_nosehoover(s.atoms, C.c_double(4.0), C.byref(alpha), C.c_double(0.1), s.S)
+            lib.sep_leapfrog(s.atoms, s.S, s.R)
+        counts.append(int(s.sys.nupdate_neighb))
+        s.close()
+    assert counts[0] == counts[1] and 1 <= counts[0] <= 10, counts
