@@ -882,7 +882,7 @@ def main():
     ap.add_argument("--cpu-ncell", type=int, default=100, help="CPU arms: lattice side (100 = the 1 M-atom configuration itself)")
     ap.add_argument("--cpu-arm-json", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-matrix", action="store_true", help="skip the section-8d matrix of smaller CPU samples")
-    ap.add_argument("--no-other", action="store_true", help="skip the short C2 (butane) / C3 (water) runs appended as other_workloads")
+    ap.add_argument("--no-other", action="store_true", help="skip the side records: other_workloads (C2 butane / C3 water), sampled_run, and at N = 2 the nested jobs")
     ap.add_argument("--equilibrate", type=int, default=300, help="untimed steps from the lattice before the warm-up (thermalisation)")
     ap.add_argument("--e2e-steps", type=int, default=1000, help="the e2e arm runs max(--steps, this) steps (it carries one upload and one download of atoms[])")
     ap.add_argument("--box", default="cubic", choices=["cubic", "stacked"], help="N>1: near-cubic box (default) or N cubes stacked along the slab axis")
