@@ -1293,6 +1293,7 @@ def main():
         dist.destroy_process_group()
     if decomposed and world == 2 and not args.no_other:
         # the other rank has left (it returns right after the e2e arm): both GPUs are free for a two-rank job of its own
+        log("bench line complete (a copy, should the nested jobs be cut short): " + json.dumps(line))
         line["dd_water_check"] = nested_dd_check("water")
         line["e2e_sep_ngpu"] = sep_ngpu_e2e_record(2, 126)        # 2.0 M atoms, as the decomposed run above
         if not os.environ.get("SEPGPU_OPTS"):
